@@ -1,0 +1,583 @@
+// Fused latent-head loss block, exact-fp32 (FFMA) path.
+//
+// Replaces, per term (content / style), the reference's
+//   vae.py:56-60      reparameterisation  z = mu + eps * exp(logvar / 2)
+//   losses.py:48-49   Gaussian KL
+//   losses.py:98-137  pair mask, pairwise similarity, snn_loss, finite-row mean
+// and their autograd backward, with two launches per training step.
+//
+// Tiling: one warp owns RM rows of the local shard; the 32 lanes sweep the
+// (global) columns, which are staged TN at a time in shared memory in [d][j]
+// order (conflict-free, one thread normalises one column).  The B x B matrix is
+// never materialised: each lane keeps a running masked sum-of-exponentials and
+// the row result is a warp-shuffle reduction.
+//
+// cosine + moderate temperature ("FAST"): |s| <= 1, so every exponent is taken
+// relative to the constant shift 1/tau; sums from different lanes / CTAs / ranks
+// then add without rescaling and exp(.) is symmetric in (i, j), which lets the
+// backward fold the column-side gradient G^T into the row pass:
+//     dL/dn_i = w * sum_j e_ij (c_i + c_j - [pos_ij](q_i + q_j)) n_j
+// (c = [finite]/sum_all, q = [finite]/sum_pos) — no transposed pass, no atomics
+// and under data parallelism no reduce-scatter of dZ.
+// Other similarities / tiny temperatures use running maxima (two accumulators
+// per set) like the reference's logsumexp (losses.py:87-95).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTN = 256;       // columns per shared-memory tile == threads per CTA
+constexpr int kWarps = 8;
+constexpr float kCosEps = 1e-8f;  // F.cosine_similarity eps (losses.py:55)
+
+struct TermF {
+  const float *mu, *lv, *eps, *mu_cols, *lv_cols;
+  float *z, *stats;
+  int snn, ps;
+};
+struct FwdParams {
+  TermF t[2];
+  const long long *lab_r, *lab_c;
+  long long B, Bg, row_off;
+  int D, z_stride, finalize, max_ctas;
+  float inv_tau;
+  float* scalars;
+  unsigned* ticket;
+  float* kl_partial;  // [2][max_ctas]
+};
+struct TermB {
+  const float *mu, *lv, *eps, *mu_cols, *stats_all, *dz;
+  float *dmu, *dlv;
+  int snn, ps;
+};
+struct BwdParams {
+  TermB t[2];
+  const long long *lab_r, *lab_c;
+  long long B, Bg, row_off;
+  int D, z_stride;
+  float inv_tau;
+  const float *scalars, *gscal;
+};
+
+enum { SIM_COS = CLEARVAE_SIM_COSINE, SIM_L2 = CLEARVAE_SIM_L2 };
+
+// ---------------------------------------------------------------------------
+// column tile: thread `tid` stages column j0 + tid (normalised for cosine)
+// ---------------------------------------------------------------------------
+template <int DP, int SIM>
+__device__ __forceinline__ void stage_column(const float* __restrict__ cols, const long long* __restrict__ lab,
+                                             long long j, long long Bg, int D, float* sN, long long* sL) {
+  float v[DP];
+  const int tid = threadIdx.x;
+  if (j < Bg) {
+    const float* src = cols + j * (long long)D;
+    if ((D & 3) == 0) {
+#pragma unroll
+      for (int d = 0; d < DP; d += 4) {
+        if (d < D) {
+          float4 q = __ldg(reinterpret_cast<const float4*>(src + d));
+          v[d] = q.x; v[d + 1] = q.y; v[d + 2] = q.z; v[d + 3] = q.w;
+        } else {
+          v[d] = v[d + 1] = v[d + 2] = v[d + 3] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < DP; ++d) v[d] = d < D ? __ldg(src + d) : 0.f;
+    }
+    if (SIM == SIM_COS) {
+      float ss = 0.f;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) ss = fmaf(v[d], v[d], ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), kCosEps);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) v[d] *= inv;
+    }
+    sL[tid] = lab[j];
+  } else {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) v[d] = 0.f;
+    sL[tid] = 0;
+  }
+#pragma unroll
+  for (int d = 0; d < DP; ++d) sN[d * kTN + tid] = v[d];
+}
+
+template <int DP, int RM, int SIM>
+__device__ __forceinline__ void load_rows(const float* __restrict__ mu, const long long* __restrict__ lab,
+                                          long long row0, long long B, int D, float (&row)[RM][DP],
+                                          float (&inv_norm)[RM], long long (&rl)[RM]) {
+#pragma unroll
+  for (int r = 0; r < RM; ++r) {
+    const long long i = row0 + r;
+    float ss = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      row[r][d] = (i < B && d < D) ? __ldg(mu + i * (long long)D + d) : 0.f;
+      ss = fmaf(row[r][d], row[r][d], ss);
+    }
+    rl[r] = i < B ? lab[i] : 0;
+    inv_norm[r] = 1.f;
+    if (SIM == SIM_COS) {
+      inv_norm[r] = 1.f / fmaxf(sqrtf(ss), kCosEps);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) row[r][d] *= inv_norm[r];
+    }
+  }
+}
+
+template <int DP, int SIM>
+__device__ __forceinline__ float pair_sim(const float (&a)[DP], const float (&x)[DP]) {
+  float acc = 0.f;
+  if (SIM == SIM_COS) {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) acc = fmaf(a[d], x[d], acc);
+  } else {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const float df = x[d] - a[d];
+      acc = fmaf(-df, df, acc);
+    }
+  }
+  return acc;
+}
+
+// finite-row mean of one term from row stats (losses.py:125-126); thread 0 writes.
+__device__ void finalize_term(const float* stats, long long Bg, int term, float* scalars, float* sred) {
+  float s = 0.f, c = 0.f;
+  for (long long i = threadIdx.x; i < Bg; i += blockDim.x) {
+    const float a = __ldcg(stats + 2 * i), b = __ldcg(stats + 2 * i + 1);
+    const float l = a - b;
+    if (isfinite(l)) { s += l; c += 1.f; }
+  }
+  s = cv::block_sum<kTN>(s, sred);
+  c = cv::block_sum<kTN>(c, sred);
+  if (threadIdx.x == 0) {
+    scalars[CLEARVAE_S_SUM0 + term] = s;
+    scalars[CLEARVAE_S_CNT0 + term] = c;
+    scalars[CLEARVAE_S_LOSS0 + term] = s / c;  // 0/0 = nan, like mean of an empty tensor
+  }
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+template <int DP, int RM, int SIM, bool FAST>
+__global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sN = reinterpret_cast<float*>(smem_raw);                 // [DP][kTN]
+  long long* sL = reinterpret_cast<long long*>(sN + DP * kTN);    // [kTN]
+  float* sRed = reinterpret_cast<float*>(sL + kTN);               // [kWarps + 1]
+  const int term = blockIdx.y;
+  const TermF& t = p.t[term];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * (kWarps * RM) + warp * RM;
+  const int D = p.D;
+
+  // ---- reparameterisation + KL for the rows of this warp (lanes over d)
+  if (t.lv != nullptr) {
+    float kl = 0.f;
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      const long long i = row0 + r;
+      if (i < p.B) {
+        for (int d = lane; d < D; d += 32) {
+          const float m = t.mu[i * D + d], lv = t.lv[i * D + d];
+          kl += 1.f + lv - m * m - expf(lv);
+          if (t.z != nullptr && t.eps != nullptr) t.z[i * p.z_stride + d] = fmaf(t.eps[i * D + d], expf(0.5f * lv), m);
+        }
+      }
+    }
+    kl = cv::block_sum<kTN>(kl, sRed);
+    if (threadIdx.x == 0) p.kl_partial[term * p.max_ctas + blockIdx.x] = kl;
+  }
+
+  if (t.snn) {
+    float row[RM][DP], inv_norm[RM];
+    long long rl[RM];
+    load_rows<DP, RM, SIM>(t.mu, p.lab_r, row0, p.B, D, row, inv_norm, rl);
+    float sa[RM], sp[RM], ma[RM], mp[RM];
+#pragma unroll
+    for (int r = 0; r < RM; ++r) { sa[r] = sp[r] = 0.f; ma[r] = mp[r] = -INFINITY; }
+    const float k2 = p.inv_tau * CV_LOG2E;
+    const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+    for (long long j0 = 0; j0 < p.Bg; j0 += kTN) {
+      __syncthreads();
+      stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL);
+      __syncthreads();
+      for (int jj = lane; jj < kTN; jj += 32) {
+        const long long j = j0 + jj;
+        if (j >= p.Bg) break;
+        float x[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) x[d] = sN[d * kTN + jj];
+        const long long lab = sL[jj];
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          const float s = pair_sim<DP, SIM>(row[r], x);
+          const bool cand = (j != p.row_off + row0 + r);
+          const bool pos = cand && ((lab == rl[r]) != (t.ps != 0));
+          if (FAST) {
+            const float e = exp2f(fmaf(s, k2, -k2));
+            sa[r] += cand ? e : 0.f;
+            sp[r] += pos ? e : 0.f;
+          } else {
+            const float xs = s * p.inv_tau;
+            if (cand) cv::lse_push(ma[r], sa[r], xs);
+            if (pos) cv::lse_push(mp[r], sp[r], xs);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      float oa, op;
+      if (FAST) {
+        oa = logf(cv::warp_sum(sa[r]));
+        op = logf(cv::warp_sum(sp[r]));
+      } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          cv::lse_merge(ma[r], sa[r], __shfl_xor_sync(0xffffffffu, ma[r], o), __shfl_xor_sync(0xffffffffu, sa[r], o));
+          cv::lse_merge(mp[r], sp[r], __shfl_xor_sync(0xffffffffu, mp[r], o), __shfl_xor_sync(0xffffffffu, sp[r], o));
+        }
+        oa = ma[r] + logf(sa[r]);  // (-inf) + log(0) = -inf
+        op = mp[r] + logf(sp[r]);
+      }
+      const long long i = row0 + r;
+      if (lane == 0 && i < p.B) {
+        t.stats[2 * i] = oa;
+        t.stats[2 * i + 1] = op;
+      }
+    }
+  }
+
+  // ---- last CTA: deterministic reduction of the per-CTA partials
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(p.ticket, 1u);
+    sRed[kWarps] = (tk == gridDim.x * gridDim.y - 1) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (sRed[kWarps] != 0.f) {
+    __threadfence();
+    for (int tt = 0; tt < (int)gridDim.y; ++tt) {
+      if (p.t[tt].lv != nullptr) {
+        float s = 0.f;
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += kTN) s += __ldcg(p.kl_partial + tt * p.max_ctas + c);
+        s = cv::block_sum<kTN>(s, sRed);
+        if (threadIdx.x == 0) p.scalars[CLEARVAE_S_KL0 + tt] = -0.5f * s / (float)p.B;
+      }
+      if (p.finalize && p.t[tt].snn) finalize_term(p.t[tt].stats, p.Bg, tt, p.scalars, sRed);
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kTN) snn_finalize_kernel(const float* stats, long long Bg, int term, float* scalars) {
+  __shared__ float sred[kWarps];
+  finalize_term(stats, Bg, term, scalars, sred);
+}
+
+// ---------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------
+template <int DP, int RM, int SIM, bool FAST>
+__global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sN = reinterpret_cast<float*>(smem_raw);               // [DP][kTN]
+  long long* sL = reinterpret_cast<long long*>(sN + DP * kTN);  // [kTN]
+  float* sC = reinterpret_cast<float*>(sL + kTN);               // [kTN]
+  float* sQ = sC + kTN;                                         // [kTN]
+  const int term = blockIdx.y;
+  const TermB& t = p.t[term];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * (kWarps * RM) + warp * RM;
+  const int D = p.D;
+  const float g_kl = p.gscal[term], g_loss = p.gscal[2 + term];
+
+  float dn[RM][DP], row[RM][DP], inv_norm[RM], csum[RM];
+  long long rl[RM];
+#pragma unroll
+  for (int r = 0; r < RM; ++r) {
+    csum[r] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) dn[r][d] = 0.f;
+  }
+  float w = 0.f;
+  if (t.snn) {
+    load_rows<DP, RM, SIM>(t.mu, p.lab_r, row0, p.B, D, row, inv_norm, rl);
+    w = g_loss * p.inv_tau / p.scalars[CLEARVAE_S_CNT0 + term];
+    // row-side coefficients from the forward stats of the global rows
+    float ci[RM], qi[RM];
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      const long long i = row0 + r;
+      float a = INFINITY, b = INFINITY;
+      if (i < p.B) {
+        a = t.stats_all[2 * (p.row_off + i)];
+        b = t.stats_all[2 * (p.row_off + i) + 1];
+      }
+      const bool fin = isfinite(a - b);
+      if (FAST) { ci[r] = fin ? __expf(-a) : 0.f; qi[r] = fin ? __expf(-b) : 0.f; }
+      else      { ci[r] = fin ? a : INFINITY;   qi[r] = fin ? b : INFINITY; }
+    }
+    const float k2 = p.inv_tau * CV_LOG2E;
+    const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+    for (long long j0 = 0; j0 < p.Bg; j0 += kTN) {
+      __syncthreads();
+      stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL);
+      {
+        const long long j = j0 + threadIdx.x;
+        float a = INFINITY, b = INFINITY;
+        if (j < p.Bg) { a = t.stats_all[2 * j]; b = t.stats_all[2 * j + 1]; }
+        const bool fin = isfinite(a - b);
+        if (FAST) { sC[threadIdx.x] = fin ? __expf(-a) : 0.f; sQ[threadIdx.x] = fin ? __expf(-b) : 0.f; }
+        else      { sC[threadIdx.x] = fin ? a : INFINITY;   sQ[threadIdx.x] = fin ? b : INFINITY; }
+      }
+      __syncthreads();
+      for (int jj = lane; jj < kTN; jj += 32) {
+        const long long j = j0 + jj;
+        if (j >= p.Bg) break;
+        float x[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) x[d] = sN[d * kTN + jj];
+        const long long lab = sL[jj];
+        const float cj = sC[jj], qj = sQ[jj];
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          const float s = pair_sim<DP, SIM>(row[r], x);
+          const bool cand = (j != p.row_off + row0 + r);
+          const bool pos = cand && ((lab == rl[r]) != (t.ps != 0));
+          float coef;
+          if (FAST) {
+            const float e = exp2f(fmaf(s, k2, -k2));
+            coef = e * ((ci[r] + cj) - (pos ? (qi[r] + qj) : 0.f));
+          } else {
+            const float xs = s * p.inv_tau;
+            coef = __expf(xs - ci[r]) + __expf(xs - cj);
+            if (pos) coef -= __expf(xs - qi[r]) + __expf(xs - qj);
+          }
+          coef = cand ? coef : 0.f;
+          csum[r] += coef;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) dn[r][d] = fmaf(coef, x[d], dn[r][d]);
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: reduce over lanes, chain through the similarity operand, add KL / reparam grads
+#pragma unroll
+  for (int r = 0; r < RM; ++r) {
+    const long long i = row0 + r;
+    float dot = 0.f;
+    if (t.snn) {
+      csum[r] = cv::warp_sum(csum[r]);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        dn[r][d] = cv::warp_sum(dn[r][d]);
+        dot = fmaf(dn[r][d], row[r][d], dot);
+      }
+    }
+    if (i >= p.B) continue;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      if ((d & 31) != lane || d >= D) continue;
+      float gm = 0.f, gl = 0.f;
+      if (t.snn) {
+        if (SIM == SIM_COS) {
+          // n = mu / max(|mu|, eps): the clamp is outside the graph (SURVEY §8a')
+          const bool live = inv_norm[r] < 1.f / kCosEps;
+          gm = w * (dn[r][d] - (live ? row[r][d] * dot : 0.f)) * inv_norm[r];
+        } else {
+          gm = w * 2.f * (dn[r][d] - csum[r] * row[r][d]);
+        }
+      }
+      if (t.lv != nullptr) {
+        const float m = t.mu[i * D + d], lv = t.lv[i * D + d];
+        const float invB = 1.f / (float)p.B;
+        gm = fmaf(g_kl * invB, m, gm);
+        gl = g_kl * invB * 0.5f * (expf(lv) - 1.f);
+        if (t.dz != nullptr) {
+          const float gz = t.dz[i * p.z_stride + d];
+          gm += gz;
+          if (t.eps != nullptr) gl = fmaf(0.5f * gz * t.eps[i * D + d], expf(0.5f * lv), gl);
+        }
+      }
+      t.dmu[i * D + d] = gm;
+      if (t.dlv != nullptr) t.dlv[i * D + d] = gl;
+    }
+  }
+}
+
+__global__ void pair_mask_kernel(const long long* lab_r, const long long* lab_c, long long B, long long Bg,
+                                 long long row_off, int ps, unsigned char* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Bg) return;
+  const long long i = idx / Bg, j = idx % Bg;
+  const bool cand = (j != row_off + i);
+  const bool pos = cand && ((lab_c[j] == lab_r[i]) != (ps != 0));
+  out[idx] = (unsigned char)((cand ? 1 : 0) | (pos ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------
+template <int DP>
+constexpr size_t fwd_smem() { return (size_t)DP * kTN * 4 + kTN * 8 + (kWarps + 1) * 4; }
+template <int DP>
+constexpr size_t bwd_smem() { return (size_t)DP * kTN * 4 + kTN * 8 + 2 * kTN * 4; }
+
+template <int DP, int RM, int SIM, bool FAST>
+int launch_fwd(const FwdParams& p, int n_terms, cudaStream_t st) {
+  auto kern = snn_fwd_kernel<DP, RM, SIM, FAST>;
+  constexpr size_t smem = fwd_smem<DP>();
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms);
+  kern<<<grid, kTN, smem, st>>>(p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+template <int DP, int RM, int SIM, bool FAST>
+int launch_bwd(const BwdParams& p, int n_terms, cudaStream_t st) {
+  auto kern = snn_bwd_kernel<DP, RM, SIM, FAST>;
+  constexpr size_t smem = bwd_smem<DP>();
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms);
+  kern<<<grid, kTN, smem, st>>>(p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+// rows per warp: register-block when there are enough rows to still fill the GPU
+inline int pick_rm(int dp, long long B) {
+  if (B <= 2048) return 1;
+  return dp == 8 ? 4 : (dp == 16 ? 2 : 1);
+}
+
+#define CV_DISPATCH(LAUNCH, P, NT, ST, DPV, RMV, SIMV, FASTV)                                    \
+  do {                                                                                            \
+    if (SIMV == SIM_COS) {                                                                        \
+      if (FASTV) return LAUNCH<DPV, RMV, SIM_COS, true>(P, NT, ST);                               \
+      return LAUNCH<DPV, RMV, SIM_COS, false>(P, NT, ST);                                         \
+    }                                                                                             \
+    return LAUNCH<DPV, RMV, SIM_L2, false>(P, NT, ST);                                            \
+  } while (0)
+
+#define CV_DISPATCH_D(LAUNCH, P, NT, ST, dp, rm, sim, fast)                                      \
+  do {                                                                                            \
+    if (dp == 8) { if (rm == 4) CV_DISPATCH(LAUNCH, P, NT, ST, 8, 4, sim, fast); CV_DISPATCH(LAUNCH, P, NT, ST, 8, 1, sim, fast); } \
+    if (dp == 16) { if (rm == 2) CV_DISPATCH(LAUNCH, P, NT, ST, 16, 2, sim, fast); CV_DISPATCH(LAUNCH, P, NT, ST, 16, 1, sim, fast); } \
+    if (dp == 32) CV_DISPATCH(LAUNCH, P, NT, ST, 32, 1, sim, fast);                               \
+    if (dp == 64) CV_DISPATCH(LAUNCH, P, NT, ST, 64, 1, sim, fast);                               \
+  } while (0)
+
+inline int pad_d(int D) { return D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : D <= 64 ? 64 : -1; }
+// shared-shift path is safe while exp(-2/tau) stays a normal float
+inline bool fast_ok(int sim, float tau) { return sim == SIM_COS && tau > 0.f && 2.f / tau <= 80.f; }
+
+int dispatch_fwd(const FwdParams& p, int n_terms, int sim, bool fast, cudaStream_t st) {
+  const int dp = pad_d(p.D), rm = pick_rm(dp, p.B);
+  CV_DISPATCH_D(launch_fwd, p, n_terms, st, dp, rm, sim, fast);
+  return CLEARVAE_EUNSUPPORTED;
+}
+int dispatch_bwd(const BwdParams& p, int n_terms, int sim, bool fast, cudaStream_t st) {
+  const int dp = pad_d(p.D), rm = pick_rm(dp, p.B);
+  CV_DISPATCH_D(launch_bwd, p, n_terms, st, dp, rm, sim, fast);
+  return CLEARVAE_EUNSUPPORTED;
+}
+
+struct WsLayout {
+  unsigned ticket;
+  unsigned pad[63];
+};
+
+inline int max_ctas_for(long long B) { return (int)((B + kWarps - 1) / kWarps); }
+
+}  // namespace
+
+extern "C" {
+
+int clearvae_version(void) { return 100; }
+
+size_t clearvae_latent_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms) {
+  (void)Bg; (void)D; (void)n_terms;
+  if (B < 0) return 0;
+  return sizeof(WsLayout) + (size_t)2 * max_ctas_for(B) * sizeof(float);
+}
+
+int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const int64_t* label_rows,
+                        const int64_t* label_cols, int64_t B, int64_t Bg, int64_t row_offset, int32_t D,
+                        int32_t z_stride, int32_t sim_fn, int32_t loss_name, float temperature, float* scalars,
+                        int32_t finalize, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !workspace || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
+  if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
+  if (sim_fn != SIM_COS && sim_fn != SIM_L2) return CLEARVAE_EUNSUPPORTED;
+  if (pad_d(D) < 0) return CLEARVAE_EUNSUPPORTED;
+  if (workspace_bytes < clearvae_latent_workspace_bytes(B, Bg, D, n_terms)) return CLEARVAE_EWORKSPACE;
+  if (row_offset < 0 || row_offset + B > Bg) return CLEARVAE_EINVAL;
+  FwdParams p{};
+  bool any_snn = false;
+  for (int i = 0; i < n_terms; ++i) {
+    const clearvae_term_fwd& s = terms[i];
+    if (!s.mu) return CLEARVAE_EINVAL;
+    if (s.snn_enable && (!s.row_stats || !label_rows)) return CLEARVAE_EINVAL;
+    p.t[i] = TermF{s.mu, s.logvar, s.eps, s.mu_cols, s.logvar_cols, s.z, s.row_stats, s.snn_enable, s.ps};
+    any_snn |= s.snn_enable != 0;
+  }
+  p.lab_r = reinterpret_cast<const long long*>(label_rows);
+  p.lab_c = reinterpret_cast<const long long*>(label_cols ? label_cols : label_rows);
+  p.B = B; p.Bg = Bg; p.row_off = row_offset; p.D = D; p.z_stride = z_stride; p.finalize = finalize;
+  p.max_ctas = max_ctas_for(B);
+  p.inv_tau = 1.f / temperature;
+  p.scalars = scalars;
+  p.ticket = &reinterpret_cast<WsLayout*>(workspace)->ticket;
+  p.kl_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sizeof(WsLayout));
+  (void)any_snn;
+  return dispatch_fwd(p, n_terms, sim_fn, fast_ok(sim_fn, temperature), (cudaStream_t)stream);
+}
+
+int clearvae_snn_finalize(const float* row_stats_all, int64_t Bg, int32_t term, float* scalars, void* stream) {
+  if (!row_stats_all || !scalars || Bg <= 0 || term < 0 || term > 1) return CLEARVAE_EINVAL;
+  snn_finalize_kernel<<<1, kTN, 0, (cudaStream_t)stream>>>(row_stats_all, Bg, term, scalars);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_latent_bwd(const clearvae_term_bwd* terms, int32_t n_terms, const int64_t* label_rows,
+                        const int64_t* label_cols, int64_t B, int64_t Bg, int64_t row_offset, int32_t D,
+                        int32_t z_stride, int32_t sim_fn, int32_t loss_name, float temperature,
+                        const float* scalars, const float* gscal, void* stream) {
+  if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !gscal || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
+  if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
+  if (sim_fn != SIM_COS && sim_fn != SIM_L2) return CLEARVAE_EUNSUPPORTED;
+  if (pad_d(D) < 0) return CLEARVAE_EUNSUPPORTED;
+  if (row_offset < 0 || row_offset + B > Bg) return CLEARVAE_EINVAL;
+  BwdParams p{};
+  for (int i = 0; i < n_terms; ++i) {
+    const clearvae_term_bwd& s = terms[i];
+    if (!s.mu || !s.dmu) return CLEARVAE_EINVAL;
+    if (s.snn_enable && (!s.row_stats_all || !label_rows)) return CLEARVAE_EINVAL;
+    p.t[i] = TermB{s.mu, s.logvar, s.eps, s.mu_cols, s.row_stats_all, s.dz, s.dmu, s.dlogvar, s.snn_enable, s.ps};
+  }
+  p.lab_r = reinterpret_cast<const long long*>(label_rows);
+  p.lab_c = reinterpret_cast<const long long*>(label_cols ? label_cols : label_rows);
+  p.B = B; p.Bg = Bg; p.row_off = row_offset; p.D = D; p.z_stride = z_stride;
+  p.inv_tau = 1.f / temperature;
+  p.scalars = scalars; p.gscal = gscal;
+  return dispatch_bwd(p, n_terms, sim_fn, fast_ok(sim_fn, temperature), (cudaStream_t)stream);
+}
+
+int clearvae_pair_mask(const int64_t* label_rows, const int64_t* label_cols, int64_t B, int64_t Bg,
+                       int64_t row_offset, int32_t ps, uint8_t* out, void* stream) {
+  if (!label_rows || !out || B <= 0 || Bg <= 0) return CLEARVAE_EINVAL;
+  const long long n = B * Bg;
+  pair_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(label_rows),
+      reinterpret_cast<const long long*>(label_cols ? label_cols : label_rows), B, Bg, row_offset, ps, out);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// Thin torch custom-op shim over the C ABI of libclearvae_b200.so.
+//
+// Ops live in the `clearvae` namespace and are registered for the CUDA
+// dispatch key ONLY: calling them with CPU tensors raises (no CPU fallback by
+// design).  The shim checks device / dtype / contiguity, allocates outputs from
+// the caching allocator, launches on the current stream and never synchronises.
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include <vector>
+
+#include "clearvae_b200.h"
+
+namespace {
+
+using at::Tensor;
+using OptTensor = std::optional<Tensor>;
+
+void check_f32(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), "clearvae: ", name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kFloat, "clearvae: ", name, " must be float32");
+  TORCH_CHECK(t.is_contiguous(), "clearvae: ", name, " must be contiguous");
+}
+void check_i64(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), "clearvae: ", name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kLong, "clearvae: ", name, " must be int64");
+  TORCH_CHECK(t.is_contiguous(), "clearvae: ", name, " must be contiguous");
+}
+const float* fptr(const OptTensor& t, const char* name, int64_t rows, int64_t cols) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  check_f32(*t, name);
+  TORCH_CHECK(t->dim() == 2 && t->size(0) == rows && t->size(1) == cols, "clearvae: bad shape for ", name);
+  return t->data_ptr<float>();
+}
+void check_rc(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, "clearvae: ", what, " failed with code ", rc,
+              rc > 0 ? " (cudaError)" : rc == CLEARVAE_EUNSUPPORTED ? " (unsupported configuration)"
+                                                                   : rc == CLEARVAE_EWORKSPACE ? " (workspace)" : " (invalid argument)");
+}
+void* cur_stream() { return (void*)at::cuda::getCurrentCUDAStream().stream(); }
+
+// ---------------------------------------------------------------------------
+std::tuple<Tensor, Tensor, std::vector<Tensor>> latent_fwd(
+    at::TensorList mu, const c10::List<OptTensor>& logvar, const c10::List<OptTensor>& eps,
+    const c10::List<OptTensor>& mu_cols, const Tensor& label_rows, const OptTensor& label_cols,
+    at::IntArrayRef snn, at::IntArrayRef ps, int64_t row_offset, int64_t sim_fn, int64_t loss_name, double tau,
+    bool finalize, bool want_z, Tensor workspace) {
+  const int n = (int)mu.size();
+  TORCH_CHECK(n >= 1 && n <= 2, "clearvae: 1 or 2 terms");
+  TORCH_CHECK((int)logvar.size() == n && (int)eps.size() == n && (int)mu_cols.size() == n && (int)snn.size() == n &&
+                  (int)ps.size() == n, "clearvae: per-term argument lists must have equal length");
+  check_f32(mu[0], "mu");
+  const c10::cuda::CUDAGuard guard(mu[0].device());
+  const int64_t B = mu[0].size(0), D = mu[0].size(1);
+  check_i64(label_rows, "label");
+  TORCH_CHECK(label_rows.numel() == B, "clearvae: label must have B entries");
+  int64_t Bg = B;
+  const int64_t* lab_c = nullptr;
+  if (label_cols.has_value() && label_cols->defined()) {
+    check_i64(*label_cols, "label_cols");
+    Bg = label_cols->numel();
+    lab_c = label_cols->data_ptr<int64_t>();
+  }
+  auto fopt = mu[0].options();
+  Tensor z = want_z ? at::empty({B, n * D}, fopt) : Tensor();
+  Tensor scalars = at::zeros({CLEARVAE_NSCALARS}, fopt);
+  std::vector<Tensor> stats;
+  clearvae_term_fwd terms[2];
+  for (int i = 0; i < n; ++i) {
+    check_f32(mu[i], "mu");
+    TORCH_CHECK(mu[i].dim() == 2 && mu[i].size(0) == B && mu[i].size(1) == D, "clearvae: mu shapes differ");
+    terms[i].mu = mu[i].data_ptr<float>();
+    terms[i].logvar = fptr(logvar.get(i), "logvar", B, D);
+    terms[i].eps = fptr(eps.get(i), "eps", B, D);
+    terms[i].mu_cols = fptr(mu_cols.get(i), "mu_cols", Bg, D);
+    terms[i].logvar_cols = nullptr;
+    terms[i].z = want_z ? z.data_ptr<float>() + i * D : nullptr;
+    terms[i].snn_enable = (int32_t)snn[i];
+    terms[i].ps = (int32_t)ps[i];
+    stats.push_back(snn[i] ? at::empty({B, 2}, fopt) : at::empty({0, 2}, fopt));
+    terms[i].row_stats = snn[i] ? stats.back().data_ptr<float>() : nullptr;
+  }
+  TORCH_CHECK(workspace.is_cuda() && workspace.is_contiguous(), "clearvae: workspace must be a contiguous CUDA tensor");
+  check_rc(clearvae_latent_fwd(terms, n, label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)D,
+                               (int32_t)(n * D), (int32_t)sim_fn, (int32_t)loss_name, (float)tau,
+                               scalars.data_ptr<float>(), finalize ? 1 : 0, workspace.data_ptr(),
+                               (size_t)workspace.nbytes(), cur_stream()),
+           "latent_fwd");
+  if (!want_z) z = at::empty({0}, fopt);
+  return {z, scalars, stats};
+}
+
+void snn_finalize(const Tensor& stats_all, int64_t term, Tensor scalars) {
+  check_f32(stats_all, "stats_all");
+  check_f32(scalars, "scalars");
+  const c10::cuda::CUDAGuard guard(stats_all.device());
+  check_rc(clearvae_snn_finalize(stats_all.data_ptr<float>(), stats_all.size(0), (int32_t)term,
+                                 scalars.data_ptr<float>(), cur_stream()),
+           "snn_finalize");
+}
+
+std::tuple<std::vector<Tensor>, std::vector<Tensor>> latent_bwd(
+    at::TensorList mu, const c10::List<OptTensor>& logvar, const c10::List<OptTensor>& eps,
+    const c10::List<OptTensor>& mu_cols, const c10::List<OptTensor>& stats_all, const OptTensor& dz,
+    const Tensor& label_rows, const OptTensor& label_cols, at::IntArrayRef snn, at::IntArrayRef ps,
+    int64_t row_offset, int64_t sim_fn, int64_t loss_name, double tau, const Tensor& scalars, const Tensor& gscal) {
+  const int n = (int)mu.size();
+  TORCH_CHECK(n >= 1 && n <= 2, "clearvae: 1 or 2 terms");
+  check_f32(mu[0], "mu");
+  const c10::cuda::CUDAGuard guard(mu[0].device());
+  const int64_t B = mu[0].size(0), D = mu[0].size(1);
+  check_i64(label_rows, "label");
+  int64_t Bg = B;
+  const int64_t* lab_c = nullptr;
+  if (label_cols.has_value() && label_cols->defined()) {
+    check_i64(*label_cols, "label_cols");
+    Bg = label_cols->numel();
+    lab_c = label_cols->data_ptr<int64_t>();
+  }
+  check_f32(scalars, "scalars");
+  check_f32(gscal, "gscal");
+  TORCH_CHECK(gscal.numel() >= 4 && scalars.numel() == CLEARVAE_NSCALARS, "clearvae: bad scalar buffers");
+  const float* dzp = nullptr;
+  if (dz.has_value() && dz->defined()) {
+    check_f32(*dz, "dz");
+    TORCH_CHECK(dz->size(0) == B && dz->size(1) == n * D, "clearvae: bad dz shape");
+    dzp = dz->data_ptr<float>();
+  }
+  std::vector<Tensor> dmu, dlv;
+  clearvae_term_bwd terms[2];
+  auto fopt = mu[0].options();
+  for (int i = 0; i < n; ++i) {
+    check_f32(mu[i], "mu");
+    terms[i].mu = mu[i].data_ptr<float>();
+    terms[i].logvar = fptr(logvar.get(i), "logvar", B, D);
+    terms[i].eps = fptr(eps.get(i), "eps", B, D);
+    terms[i].mu_cols = fptr(mu_cols.get(i), "mu_cols", Bg, D);
+    terms[i].row_stats_all = snn[i] ? fptr(stats_all.get(i), "stats_all", Bg, 2) : nullptr;
+    TORCH_CHECK(!snn[i] || terms[i].row_stats_all, "clearvae: stats_all missing for an enabled term");
+    terms[i].dz = dzp ? dzp + i * D : nullptr;
+    dmu.push_back(at::empty({B, D}, fopt));
+    terms[i].dmu = dmu.back().data_ptr<float>();
+    if (terms[i].logvar) {
+      dlv.push_back(at::empty({B, D}, fopt));
+      terms[i].dlogvar = dlv.back().data_ptr<float>();
+    } else {
+      dlv.push_back(at::empty({0, D}, fopt));
+      terms[i].dlogvar = nullptr;
+    }
+    terms[i].snn_enable = (int32_t)snn[i];
+    terms[i].ps = (int32_t)ps[i];
+  }
+  check_rc(clearvae_latent_bwd(terms, n, label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)D,
+                               (int32_t)(n * D), (int32_t)sim_fn, (int32_t)loss_name, (float)tau,
+                               scalars.data_ptr<float>(), gscal.data_ptr<float>(), cur_stream()),
+           "latent_bwd");
+  return {dmu, dlv};
+}
+
+Tensor pair_mask(const Tensor& label_rows, const OptTensor& label_cols, int64_t row_offset, int64_t ps) {
+  check_i64(label_rows, "label");
+  const c10::cuda::CUDAGuard guard(label_rows.device());
+  const int64_t B = label_rows.numel();
+  int64_t Bg = B;
+  const int64_t* lab_c = nullptr;
+  if (label_cols.has_value() && label_cols->defined()) {
+    check_i64(*label_cols, "label_cols");
+    Bg = label_cols->numel();
+    lab_c = label_cols->data_ptr<int64_t>();
+  }
+  Tensor out = at::empty({B, Bg}, label_rows.options().dtype(at::kByte));
+  check_rc(clearvae_pair_mask(label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)ps,
+                              out.data_ptr<uint8_t>(), cur_stream()),
+           "pair_mask");
+  return out;
+}
+
+int64_t latent_workspace_bytes(int64_t B, int64_t Bg, int64_t D, int64_t n_terms) {
+  return (int64_t)clearvae_latent_workspace_bytes(B, Bg, (int32_t)D, (int32_t)n_terms);
+}
+
+Tensor recon_fwd(const Tensor& xhat, const Tensor& x, Tensor workspace) {
+  check_f32(xhat, "xhat");
+  check_f32(x, "x");
+  TORCH_CHECK(xhat.sizes() == x.sizes() && xhat.dim() >= 1, "clearvae: xhat / x shape mismatch");
+  const c10::cuda::CUDAGuard guard(xhat.device());
+  const int64_t B = xhat.size(0);
+  Tensor out = at::empty({}, xhat.options());
+  check_rc(clearvae_recon_fwd(xhat.data_ptr<float>(), x.data_ptr<float>(), B, xhat.numel() / B, out.data_ptr<float>(),
+                              workspace.data_ptr(), (size_t)workspace.nbytes(), cur_stream()),
+           "recon_fwd");
+  return out;
+}
+
+Tensor recon_bwd(const Tensor& xhat, const Tensor& x, const Tensor& grad_out) {
+  check_f32(xhat, "xhat");
+  check_f32(x, "x");
+  check_f32(grad_out, "grad_out");
+  const c10::cuda::CUDAGuard guard(xhat.device());
+  const int64_t B = xhat.size(0);
+  Tensor dx = at::empty_like(xhat);
+  check_rc(clearvae_recon_bwd(xhat.data_ptr<float>(), x.data_ptr<float>(), grad_out.data_ptr<float>(), B,
+                              xhat.numel() / B, dx.data_ptr<float>(), cur_stream()),
+           "recon_bwd");
+  return dx;
+}
+
+int64_t recon_workspace_bytes() { return (int64_t)clearvae_recon_workspace_bytes(); }
+
+}  // namespace
+
+TORCH_LIBRARY(clearvae, m) {
+  m.def("latent_fwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor label_rows, "
+        "Tensor? label_cols, int[] snn, int[] ps, int row_offset, int sim_fn, int loss_name, float tau, "
+        "bool finalize, bool want_z, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor[])");
+  m.def("snn_finalize(Tensor stats_all, int term, Tensor(a!) scalars) -> ()");
+  m.def("latent_bwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor?[] stats_all, "
+        "Tensor? dz, Tensor label_rows, Tensor? label_cols, int[] snn, int[] ps, int row_offset, int sim_fn, "
+        "int loss_name, float tau, Tensor scalars, Tensor gscal) -> (Tensor[], Tensor[])");
+  m.def("pair_mask(Tensor label_rows, Tensor? label_cols, int row_offset, int ps) -> Tensor");
+  m.def("latent_workspace_bytes(int B, int Bg, int D, int n_terms) -> int", &latent_workspace_bytes);
+  m.def("recon_fwd(Tensor xhat, Tensor x, Tensor(a!) workspace) -> Tensor");
+  m.def("recon_bwd(Tensor xhat, Tensor x, Tensor grad_out) -> Tensor");
+  m.def("recon_workspace_bytes() -> int", &recon_workspace_bytes);
+}
+
+TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
+  m.impl("latent_fwd", &latent_fwd);
+  m.impl("snn_finalize", &snn_finalize);
+  m.impl("latent_bwd", &latent_bwd);
+  m.impl("pair_mask", &pair_mask);
+  m.impl("recon_fwd", &recon_fwd);
+  m.impl("recon_bwd", &recon_bwd);
+}

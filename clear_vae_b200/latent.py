@@ -1,0 +1,146 @@
+"""Autograd front-end of the fused latent-head loss block.
+
+`latent_block` is one forward launch + one backward launch for everything the
+reference does between `encode` and `decode` plus its latent losses:
+  reparameterisation (vae.py:56-60), Gaussian KL (losses.py:48-49) and the
+  contrastive / anti-contrastive SNN terms (losses.py:98-137),
+for one or two latent heads.  Under data parallelism the column side is the
+all-gathered global batch (`DistSpec`); the backward needs only the gathered
+forward row statistics (no reduce-scatter of dZ — see DESIGN.md §3).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _ops
+
+SIM_IDS = {"cosine": 0, "l2": 1, "modified_l2": 2, "jeffrey": 3, "mahalanobis": 4}
+LOSS_IDS = {"snn_loss": 0, "supcon_in_loss": 1, "supcon_out_loss": 2}
+
+# indices into the packed scalar vector (include/clearvae_b200.h)
+S_KL0, S_KL1, S_LOSS0, S_LOSS1, S_SUM0, S_SUM1, S_CNT0, S_CNT1 = range(8)
+
+_workspaces: dict = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+@dataclass
+class DistSpec:
+    """Data-parallel context: rows [rank*B, (rank+1)*B) of a global batch."""
+    group: object
+    rank: int
+    world: int
+
+
+def _all_gather_rows(t, dist):
+    import torch.distributed as td
+    out = torch.empty((dist.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    td.all_gather_into_tensor(out, t.contiguous(), group=dist.group)
+    return out
+
+
+class _LatentBlock(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, label, *flat):
+        n = cfg["n"]
+        mu = [t.contiguous() for t in flat[0:n]]
+        logvar = [None if t is None else t.contiguous() for t in flat[n:2 * n]]
+        eps = [None if t is None else t.contiguous() for t in flat[2 * n:3 * n]]
+        ops = _ops.ops()
+        dist = cfg["dist"]
+        B, D = mu[0].shape
+        label = label.contiguous()
+        want_z = cfg["want_z"]
+        if dist is None or dist.world == 1:
+            ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n))
+            z, scalars, stats = ops.latent_fwd(mu, logvar, eps, [None] * n, label, None, cfg["snn"], cfg["ps"], 0,
+                                               cfg["sim"], cfg["loss"], cfg["tau"], True, want_z, ws)
+            cols, label_cols, stats_all, row_off = [None] * n, None, stats, 0
+        else:
+            # one packed all-gather of the similarity operands + labels
+            snn_terms = [i for i in range(n) if cfg["snn"][i]]
+            packed = torch.cat([mu[i] for i in snn_terms] + [label.view(B, 1).view(torch.float32)], dim=1)
+            g = _all_gather_rows(packed, dist)
+            cols = [None] * n
+            for k, i in enumerate(snn_terms):
+                cols[i] = g[:, k * D:(k + 1) * D].contiguous()
+            label_cols = g[:, len(snn_terms) * D:].contiguous().view(torch.int64).view(-1)
+            row_off = dist.rank * B
+            Bg = dist.world * B
+            ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, Bg, D, n))
+            z, scalars, stats = ops.latent_fwd(mu, logvar, eps, cols, label, label_cols, cfg["snn"], cfg["ps"], row_off,
+                                               cfg["sim"], cfg["loss"], cfg["tau"], False, want_z, ws)
+            st_cat = _all_gather_rows(torch.cat([stats[i] for i in snn_terms], dim=1), dist) if snn_terms else None
+            stats_all = [None] * n
+            for k, i in enumerate(snn_terms):
+                stats_all[i] = st_cat[:, 2 * k:2 * k + 2].contiguous()
+                ops.snn_finalize(stats_all[i], i, scalars)
+        ctx.cfg = cfg
+        ctx.row_off = row_off
+        ctx.n_saved = (len(mu), len(logvar), len(eps))
+        ctx.save_for_backward(label, label_cols, scalars, *mu, *logvar, *eps, *cols, *stats_all)
+        return z, scalars
+
+    @staticmethod
+    def backward(ctx, dz, dscal):
+        cfg = ctx.cfg
+        n = cfg["n"]
+        saved = ctx.saved_tensors
+        label, label_cols, scalars = saved[0], saved[1], saved[2]
+        rest = list(saved[3:])
+        mu, logvar, eps, cols, stats_all = (rest[k * n:(k + 1) * n] for k in range(5))
+        ops = _ops.ops()
+        if dscal is None:
+            dscal = torch.zeros(8, dtype=scalars.dtype, device=scalars.device)
+        dscal = dscal.contiguous()
+        dist = cfg["dist"]
+        if dist is not None and dist.world > 1:
+            # gradients are averaged over ranks afterwards; the SNN term is a *global* loss
+            dscal = dscal.clone()
+            dscal[S_LOSS0:S_LOSS1 + 1] *= float(dist.world)
+        if dz is not None:
+            dz = dz.contiguous()
+            if dz.numel() == 0:
+                dz = None
+        dmu, dlv = ops.latent_bwd(mu, logvar, eps, cols, stats_all, dz, label, label_cols, cfg["snn"], cfg["ps"],
+                                  ctx.row_off, cfg["sim"], cfg["loss"], cfg["tau"], scalars, dscal)
+        g_mu = list(dmu)
+        g_lv = [dlv[i] if logvar[i] is not None else None for i in range(n)]
+        g_eps = [None] * n
+        return (None, None, *g_mu, *g_lv, *g_eps)
+
+
+def latent_block(mu, logvar, eps, label, *, snn, ps, sim_fn="cosine", temperature=0.1, loss_name="snn_loss",
+                 want_z=True, dist: DistSpec | None = None):
+    """Fused latent block over `len(mu)` heads.
+
+    mu/logvar/eps: lists of [B, D] tensors (logvar/eps entries may be None);
+    snn[i]: whether head i carries a contrastive term; ps[i]: its pair-switch flag.
+    Returns (z [B, n*D] or None, scalars[8]) with kl_i = scalars[i],
+    loss_i = scalars[2 + i] (global finite-row mean), count_i = scalars[6 + i].
+    """
+    if sim_fn not in SIM_IDS:
+        raise ValueError("unimplemented similarity measure.")  # losses.py:122-123
+    if loss_name not in LOSS_IDS:
+        raise NameError(f"name '{loss_name}' is not defined")  # reference: eval(loss_name) (losses.py:124)
+    n = len(mu)
+    cfg = dict(n=n, snn=[int(bool(s)) for s in snn], ps=[1 if p else 0 for p in ps], sim=SIM_IDS[sim_fn],
+               loss=LOSS_IDS[loss_name], tau=float(temperature), want_z=bool(want_z), dist=dist)
+    z, scalars = _LatentBlock.apply(cfg, label, *mu, *logvar, *eps)
+    return (z if want_z else None), scalars
+
+
+def pair_mask(label, ps=False, label_cols=None, row_offset=0):
+    """Debug view of the kernels' pair indexing: uint8 [B, Bg], bit0 = candidate
+    (j != i), bit1 = positive (losses.py:107-110,131-135)."""
+    return _ops.ops().pair_mask(label.contiguous(), label_cols, int(row_offset), 1 if ps else 0)

@@ -1,0 +1,134 @@
+/*
+ * clearvae_b200.h — C ABI of libclearvae_b200.so (sm_100a CUDA, no torch types).
+ *
+ * The reference (scotsun/clear-vae) has no FFI layer of its own: its hot path is
+ * Python calling PyTorch.  Each entry point below replaces the
+ * arithmetic of the cited reference lines; the torch custom ops in
+ * clear_vae_b200/csrc/torch_binding.cpp are thin shims over exactly these
+ * symbols, and INTEGRATION.md shows the ctypes stub a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are contiguous; fp32 unless stated; labels are int64;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises, every
+ *     launch is CUDA-graph capturable, no function allocates or frees;
+ *   - return 0 on success, a negative CLEARVAE_E* on bad arguments, or a
+ *     positive cudaError_t when a launch fails; no exceptions cross the ABI.
+ */
+#ifndef CLEARVAE_B200_H_
+#define CLEARVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLEARVAE_OK 0
+#define CLEARVAE_EINVAL (-1)      /* null pointer / negative size */
+#define CLEARVAE_EUNSUPPORTED (-2) /* shape or mode not built */
+#define CLEARVAE_EWORKSPACE (-3)   /* workspace too small */
+
+/* similarity selector: reference `sim_fn` strings (losses.py:111-123) */
+enum { CLEARVAE_SIM_COSINE = 0, CLEARVAE_SIM_L2 = 1, CLEARVAE_SIM_MODIFIED_L2 = 2,
+       CLEARVAE_SIM_JEFFREY = 3, CLEARVAE_SIM_MAHALANOBIS = 4 };
+/* row-loss selector: reference `loss_name` strings (losses.py:124,129-170) */
+enum { CLEARVAE_LOSS_SNN = 0, CLEARVAE_LOSS_SUPCON_IN = 1, CLEARVAE_LOSS_SUPCON_OUT = 2 };
+
+int clearvae_version(void);
+
+/* ---------------------------------------------------------------------------
+ * Latent-head loss block.
+ *
+ * One "term" = one contrastive_loss call of the reference
+ * (losses.py:98-137: pair mask, pairwise similarity, snn_loss, finite-row
+ * mean).  The block handles up to two terms (content, style) in one launch and
+ * fuses, per term, the reparameterisation (vae.py:56-60) and the Gaussian KL
+ * (losses.py:48-49).
+ *
+ * Row side = this rank's shard [B, D]; column side = the (all-gathered) global
+ * batch [Bg, D].  Single GPU: cols == rows, Bg == B, row_offset == 0.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  /* row side (local shard) */
+  const float* mu;      /* [B, D]                                    */
+  const float* logvar;  /* [B, D] or NULL (no KL / reparam)          */
+  const float* eps;     /* [B, D] or NULL (no reparam)               */
+  /* column side (global batch); NULL means "same as rows" */
+  const float* mu_cols; /* [Bg, D]                                   */
+  const float* logvar_cols; /* [Bg, D], only for logvar-dependent sims */
+  /* outputs */
+  float* z;             /* [B, z_stride] slice start, or NULL        */
+  float* row_stats;     /* [B, 2]: (sum_all, sum_pos) — see DESIGN.md */
+  /* configuration */
+  int32_t snn_enable;   /* 0: only reparam/KL for this term          */
+  int32_t ps;           /* 0: same-label positives, 1: flipped mask  */
+} clearvae_term_fwd;
+
+/* scalars written by the forward (float[CLEARVAE_NSCALARS]) */
+enum { CLEARVAE_S_KL0 = 0, CLEARVAE_S_KL1 = 1, CLEARVAE_S_LOSS0 = 2, CLEARVAE_S_LOSS1 = 3,
+       CLEARVAE_S_SUM0 = 4, CLEARVAE_S_SUM1 = 5, CLEARVAE_S_CNT0 = 6, CLEARVAE_S_CNT1 = 7,
+       CLEARVAE_NSCALARS = 8 };
+
+size_t clearvae_latent_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms);
+
+/* forward: replaces vae.py:56-60 (sample), losses.py:48-49 (KL), losses.py:98-137.
+ * `finalize` != 0 : the last CTA also reduces row_stats -> LOSS/SUM/CNT scalars
+ *                   (single GPU).  With finalize == 0 call clearvae_snn_finalize
+ *                   on the gathered stats.  `workspace` must be zero-initialised
+ *                   once; the kernels leave it zeroed. */
+int clearvae_latent_fwd(const clearvae_term_fwd* terms_host, int32_t n_terms,
+                        const int64_t* label_rows, const int64_t* label_cols,
+                        int64_t B, int64_t Bg, int64_t row_offset, int32_t D, int32_t z_stride,
+                        int32_t sim_fn, int32_t loss_name, float temperature,
+                        float* scalars, int32_t finalize,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* reduce gathered row stats [Bg,2] of one term to (loss, sum, count); losses.py:125-126 */
+int clearvae_snn_finalize(const float* row_stats_all, int64_t Bg, int32_t term,
+                          float* scalars, void* stream);
+
+typedef struct {
+  const float* mu;       /* [B, D] */
+  const float* logvar;   /* [B, D] or NULL */
+  const float* eps;      /* [B, D] or NULL */
+  const float* mu_cols;  /* [Bg, D] or NULL (= rows) */
+  const float* row_stats_all; /* [Bg, 2] forward stats of ALL global rows */
+  const float* dz;       /* [B, z_stride] slice start or NULL: grad wrt z */
+  float* dmu;            /* [B, D] out */
+  float* dlogvar;        /* [B, D] out or NULL */
+  int32_t snn_enable;
+  int32_t ps;
+} clearvae_term_bwd;
+
+/* backward of the block. `gscal` (device, float[4]) = upstream grads of
+ * (kl0, kl1, loss0, loss1); `scalars` = the forward's scalar buffer (CNT used). */
+int clearvae_latent_bwd(const clearvae_term_bwd* terms_host, int32_t n_terms,
+                        const int64_t* label_rows, const int64_t* label_cols,
+                        int64_t B, int64_t Bg, int64_t row_offset, int32_t D, int32_t z_stride,
+                        int32_t sim_fn, int32_t loss_name, float temperature,
+                        const float* scalars, const float* gscal, void* stream);
+
+/* debug/test: positive/candidate sets of losses.py:107-110,131-135 as bytes
+ * (bit0 = candidate j!=i, bit1 = positive), [B, Bg] — same index math as the kernels. */
+int clearvae_pair_mask(const int64_t* label_rows, const int64_t* label_cols, int64_t B, int64_t Bg,
+                       int64_t row_offset, int32_t ps, uint8_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Reconstruction term: replaces losses.py:36-47 (F.mse_loss(reduction="none")
+ * summed per sample, batch mean) and its backward.  xhat / x are any contiguous
+ * [B, per_sample] fp32 views, 16-byte aligned.
+ * ------------------------------------------------------------------------- */
+size_t clearvae_recon_workspace_bytes(void);
+int clearvae_recon_fwd(const float* xhat, const float* x, int64_t B, int64_t per_sample, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* dxhat = 2 (xhat - x) / B * (*grad_out);  grad_out is a device scalar */
+int clearvae_recon_bwd(const float* xhat, const float* x, const float* grad_out, int64_t B, int64_t per_sample,
+                       float* dxhat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLEARVAE_B200_H_ */

@@ -1,0 +1,170 @@
+"""GPU parity: fused latent-loss kernels vs the reference goldens and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import latent_oracle as lo
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+LOSS_REL, LOSS_ABS = 1e-5, 2e-6   # north_star: loss components within 1e-5 relative in fp32 (+ fp32 LSE floor)
+GRAD_REL = 1e-4                   # north_star: gradients within 1e-4
+
+
+def close(a, b, rel=LOSS_REL, ab=LOSS_ABS):
+    if np.isnan(b):
+        return np.isnan(a)
+    return abs(a - b) <= rel * abs(b) + ab
+
+
+def cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "contrastive.npz"))
+    for name in g["names"]:
+        sim, tau, ln, ps = g[f"{name}/meta"]
+        yield name, g, str(sim), float(tau), str(ln), eval(str(ps))
+
+
+def test_contrastive_matches_reference_goldens(golden_dir):
+    from clear_vae_b200.losses import contrastive_loss
+    n = 0
+    for name, g, sim, tau, ln, ps in cases(golden_dir):
+        if sim not in ("cosine", "l2") or ln != "snn_loss":
+            continue
+        mu = torch.tensor(g[f"{name}/mu"], device=DEV, requires_grad=True)
+        lv = torch.tensor(g[f"{name}/logvar"], device=DEV)
+        lab = torch.tensor(g[f"{name}/label"], device=DEV)
+        loss = contrastive_loss(mu, lv, lab, sim, tau, ln, ps)
+        want = float(g[f"{name}/loss"])
+        assert loss.dim() == 0
+        assert close(float(loss), want), (name, float(loss), want)
+        if np.isfinite(want):
+            loss.backward()
+            wg = g[f"{name}/dmu"]
+            err = np.abs(mu.grad.cpu().numpy() - wg).max()
+            assert err <= GRAD_REL * np.abs(wg).max() + 1e-7, (name, err, np.abs(wg).max())
+        n += 1
+    assert n >= 30
+
+
+def test_pair_mask_bit_exact():
+    from clear_vae_b200.latent import pair_mask
+    gen = torch.Generator().manual_seed(5)
+    for B, ncls in [(1, 2), (7, 3), (257, 10), (1000, 500)]:
+        lab = torch.randint(0, ncls, (B,), generator=gen)
+        for ps in (False, True, None):
+            got = pair_mask(lab.to(DEV), ps).cpu().numpy()
+            cand, pos = lo.positive_sets(lab.numpy(), ps)
+            assert np.array_equal(got & 1, cand) and np.array_equal(got >> 1, pos), (B, ps)
+    # sharded rows against a global column set
+    lab = torch.randint(0, 6, (96,), generator=gen)
+    for r in range(3):
+        rows = lab[r * 32:(r + 1) * 32]
+        got = pair_mask(rows.to(DEV), True, label_cols=lab.to(DEV), row_offset=r * 32).cpu().numpy()
+        cand, pos = lo.positive_sets(rows.numpy(), True, row_offset=r * 32, label_cols=lab.numpy())
+        assert np.array_equal(got & 1, cand) and np.array_equal(got >> 1, pos)
+
+
+@pytest.mark.parametrize("B,D,ncls,tau,ps", [(128, 8, 10, 0.1, True), (1024, 8, 10, 0.1, False), (512, 32, 4, 0.1, True),
+                                              (300, 32, 7, 0.5, None), (64, 16, 32, 0.02, False), (2500, 8, 10, 0.1, True)])
+def test_fused_block_matches_oracle(B, D, ncls, tau, ps):
+    """reparam + KL + content SNN + style (anti-)SNN in one fwd/bwd pair vs the fp64 oracle."""
+    from clear_vae_b200.latent import latent_block
+    gen = torch.Generator().manual_seed(B + D)
+    mu_c, lv_c, mu_s, lv_s, e_c, e_s = (torch.randn(B, D, generator=gen) * s for s in (1, .3, 1, .3, 1, 1))
+    lab = torch.randint(0, ncls, (B,), generator=gen)
+    dev = [t.to(DEV).requires_grad_(True) for t in (mu_c, lv_c, mu_s, lv_s)]
+    z, sc = latent_block([dev[0], dev[2]], [dev[1], dev[3]], [e_c.to(DEV), e_s.to(DEV)], lab.to(DEV), snn=[1, 1],
+                         ps=[False, ps], temperature=tau)
+    # oracle in float64 with autograd
+    o = [t.double().requires_grad_(True) for t in (mu_c, lv_c, mu_s, lv_s)]
+    zc = o[0] + e_c.double() * torch.exp(0.5 * o[1])
+    zs = o[2] + e_s.double() * torch.exp(0.5 * o[3])
+    kl = lambda m, l: -0.5 * (1 + l - m * m - l.exp()).sum(1).mean()
+    c = mo.contrastive(o[0], o[1], lab, "cosine", tau)
+    s = mo.contrastive(o[2], o[3], lab, "cosine", tau, ps=ps)
+    assert np.abs(z.detach().cpu().numpy() - torch.cat([zc, zs], 1).detach().numpy()).max() < 2e-6
+    got = sc.detach().cpu().numpy()
+    for g_, w_ in ((got[0], kl(o[0], o[1])), (got[1], kl(o[2], o[3])), (got[2], c), (got[3], s)):
+        assert close(float(g_), float(w_)), (float(g_), float(w_))
+    # also against the numpy closed form (independent restatement)
+    assert close(float(got[2]), lo.contrastive(mu_c.numpy(), lv_c.numpy(), lab.numpy(), "cosine", tau))
+    # gradients of a trainer-like combination
+    wz = torch.randn(B, 2 * D, generator=gen)
+    coef = (0.07, 0.05, 100.0, -100.0 if not ps else 100.0)
+    tot = (z * wz.to(DEV)).sum() + coef[0] * sc[0] + coef[1] * sc[1] + coef[2] * sc[2] + coef[3] * sc[3]
+    tot.backward()
+    tot_o = (torch.cat([zc, zs], 1) * wz.double()).sum() + coef[0] * kl(o[0], o[1]) + coef[1] * kl(o[2], o[3]) + coef[2] * c + coef[3] * s
+    tot_o.backward()
+    for a, b in zip(dev, o):
+        w = b.grad.numpy()
+        err = np.abs(a.grad.cpu().numpy() - w).max()
+        assert err <= GRAD_REL * np.abs(w).max() + 1e-7, (err, np.abs(w).max())
+
+
+def test_large_batch_against_chunked_oracle():
+    from clear_vae_b200.losses import contrastive_loss
+    gen = torch.Generator().manual_seed(9)
+    B, D = 8192, 32
+    mu = torch.randn(B, D, generator=gen)
+    lab = torch.randint(0, 10, (B,), generator=gen)
+    for ps in (False, True):
+        m = mu.to(DEV).requires_grad_(True)
+        got = contrastive_loss(m, torch.zeros_like(m), lab.to(DEV), "cosine", 0.1, ps=ps)
+        want = lo.contrastive(mu.numpy(), np.zeros((B, D)), lab.numpy(), "cosine", 0.1, ps=ps)
+        assert close(float(got), want), (float(got), want)
+        got.backward()
+        wg = lo.snn_grad(mu.numpy(), lab.numpy(), "cosine", 0.1, ps)
+        err = np.abs(m.grad.cpu().numpy() - wg).max()
+        assert err <= GRAD_REL * np.abs(wg).max() + 1e-9
+
+
+def test_sharded_rows_sum_to_global_loss():
+    """size-independent property: per-shard (sum, count) against gathered columns add up to the global loss."""
+    from clear_vae_b200 import _ops
+    from clear_vae_b200.latent import _workspace
+    ops = _ops.ops()
+    gen = torch.Generator().manual_seed(3)
+    Bg, D, W = 4096, 8, 4
+    mu = torch.randn(Bg, D, generator=gen).to(DEV)
+    lab = torch.randint(0, 10, (Bg,), generator=gen).to(DEV)
+    ws = _workspace(mu.device, ops.latent_workspace_bytes(Bg, Bg, D, 1))
+    _, sc_full, st_full = ops.latent_fwd([mu], [None], [None], [None], lab, None, [1], [0], 0, 0, 0, 0.1, True, False, ws)
+    B = Bg // W
+    parts = []
+    for r in range(W):
+        rows = mu[r * B:(r + 1) * B].contiguous()
+        _, _, st = ops.latent_fwd([rows], [None], [None], [mu], lab[r * B:(r + 1) * B].contiguous(), lab, [1], [0], r * B,
+                                  0, 0, 0.1, False, False, ws)
+        parts.append(st[0])
+    st_all = torch.cat(parts)
+    assert torch.equal(st_all, st_full[0])  # same arithmetic per row -> bit-identical stats
+    sc = torch.zeros(8, device=DEV)
+    ops.snn_finalize(st_all, 0, sc)
+    assert float(sc[2]) == float(sc_full[2])
+
+
+def test_error_behaviour():
+    from clear_vae_b200.losses import contrastive_loss
+    mu = torch.randn(8, 4, device=DEV)
+    lab = torch.zeros(8, dtype=torch.long, device=DEV)
+    with pytest.raises(ValueError, match="unimplemented similarity measure"):
+        contrastive_loss(mu, mu, lab, "euclid", 0.1)
+    # every row dropped -> nan, not an exception (losses.py:125-126)
+    assert torch.isnan(contrastive_loss(mu, mu, lab, "cosine", 0.1, ps=True))
+
+
+def test_vae_loss_matches_golden(golden_dir):
+    from clear_vae_b200.losses import vae_loss
+    h = np.load(os.path.join(golden_dir, "heads.npz"))
+    t = lambda k: torch.tensor(h[k], device=DEV)
+    xh = t("elbo/xhat").requires_grad_(True)
+    rec, kc, ks = vae_loss(xh, t("elbo/x"), mu_c=t("elbo/mu_c"), mu_s=t("elbo/mu_s"), logvar_c=t("elbo/logvar_c"),
+                           logvar_s=t("elbo/logvar_s"))
+    assert close(float(rec), float(h["elbo/recon"])) and close(float(kc), float(h["elbo/kl_c"])) and close(float(ks), float(h["elbo/kl_s"]))
+    (3.0 * rec).backward()
+    want = 3.0 * 2.0 * (h["elbo/xhat"] - h["elbo/x"]) / h["elbo/x"].shape[0]
+    assert np.abs(xh.grad.cpu().numpy() - want).max() < 1e-6
