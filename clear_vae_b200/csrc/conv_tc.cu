@@ -1,0 +1,443 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   dst[m, n] = sum_k A[m, k] * W[n, k]           m = output pixel, n = output channel,
+//                                                  k = (tap, input channel)
+//   * A (im2col rows) is never materialised: 128 producer threads (one per tile row)
+//     gather 16-byte channel runs straight from the NHWC activation, apply the
+//     previous layer's BatchNorm scale/shift + ReLU on the fly, convert to bf16 and
+//     store them in the UMMA K-major "interleave" (no-swizzle) layout
+//     [k-chunk][row][8 x bf16]: conflict-free 16-byte shared stores.
+//   * W comes from a packed bf16 [N][Kp] copy through TMA (128-byte swizzle).
+//   * one elected thread issues tcgen05.mma (M = 128, N = BN, K = 16) into a TMEM
+//     accumulator; tcgen05.commit releases shared-memory stages / signals the epilogue.
+//   * the epilogue reads TMEM (tcgen05.ld 32x32b), adds bias, writes the raw output and
+//     reduces the BatchNorm batch statistics (or the ReLU/BN-backward sums) with a
+//     transposing warp-shuffle reduction + one double atomicAdd per column per warp.
+// 4-stage mbarrier pipeline, warp roles: 0-3 gather + epilogue, 4 TMA, 5 MMA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_plan.h"
+#include "sm100_ptx.cuh"
+
+namespace {
+
+using namespace sm100;
+using cvplan::Cls;
+using cvplan::Plan;
+
+constexpr int BM = 128, BK = 64, NS = 4;
+constexpr int kAStage = BM * BK * 2;  // 16 KiB
+constexpr int kThreads = 192;
+
+struct TmapPack {
+  CUtensorMap t[cvplan::kMaxClasses];
+};
+
+struct GemmParams {
+  Plan plan;
+  long long batch;
+  const void* src; long long s_n, s_h, s_w, s_c; int src_bf16;
+  const float *pre_scale, *pre_shift; int pre_relu;
+  const float* bias;
+  void* dst; long long d_n, d_h, d_w, d_c; int dst_bf16;
+  int epi;
+  const void* msk; long long m_n, m_h, m_w, m_c; int msk_bf16;
+  const float *msk_scale, *msk_shift;
+  double* stats;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ld_elem(const void* base, long long off, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]) : reinterpret_cast<const float*>(base)[off];
+}
+
+// column sums of a 32-row x 32-column register tile held one row per lane:
+// after the call v[0] of lane j is sum over lanes of their v[j]
+__device__ __forceinline__ void transpose_reduce32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ TmapPack tm, const GemmParams p) {
+  constexpr int kBStage = BN * BK * 2;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte-swizzle atoms need 1024-byte alignment (the launch reserves the slack)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + NS * kAStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + NS * kBStage);
+  uint64_t* empty = full + NS;
+  uint64_t* tmem_full = empty + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const Cls& c = p.plan.cls[blockIdx.z];
+  const long long Mc = p.batch * c.Hd * c.Wd;
+  const long long m0 = (long long)blockIdx.x * BM;
+  if (m0 >= Mc) return;
+  const int n0 = blockIdx.y * BN;
+  const int nkb = c.Kp / BK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], BM + 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) prefetch_tmap(&tm.t[blockIdx.z]);
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================= A producer: one thread per tile row =================
+    const int r = threadIdx.x;
+    const long long m = m0 + r;
+    const bool mvalid = m < Mc;
+    const long long mm = mvalid ? m : 0;
+    const int wd = (int)(mm % c.Wd);
+    const int hd = (int)((mm / c.Wd) % c.Hd);
+    const long long img = mm / ((long long)c.Wd * c.Hd);
+    const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
+    const int Cs = p.plan.Cs, Kreal = c.ntaps * Cs;
+    const bool vec = (Cs % 8 == 0) && p.s_c == 1;
+    const long long img_off = img * p.s_n;
+    int t_cur = 0, c_cur = 0;  // incremental (tap, channel) of the next 8-chunk (vector path)
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NS;
+      mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+      unsigned char* a_st = sA + s * kAStage;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kg = kb * BK + j * 8;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (vec) {
+          if (kg < Kreal && mvalid) {
+            const int hs = hbase + c.dh[t_cur], ws = wbase + c.dw[t_cur];
+            if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
+              const long long off = img_off + hs * p.s_h + ws * p.s_w + c_cur;
+              float v[8];
+              if (p.src_bf16) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+              } else {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off + 4));
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+              }
+              if (p.pre_scale != nullptr) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + c_cur));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + c_cur + 4));
+                const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + c_cur));
+                const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + c_cur + 4));
+                v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+                v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+              }
+              if (p.pre_relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+          c_cur += 8;
+          if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
+        } else {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = kg + i;
+            float x = 0.f;
+            if (k < Kreal && mvalid) {
+              const int t = k / Cs, ch = k - t * Cs;
+              const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+              if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
+                x = ld_elem(p.src, img_off + hs * p.s_h + ws * p.s_w + ch * p.s_c, p.src_bf16);
+                if (p.pre_scale != nullptr) x = fmaf(x, __ldg(p.pre_scale + ch), __ldg(p.pre_shift + ch));
+                if (p.pre_relu) x = fmaxf(x, 0.f);
+              }
+            }
+            v[i] = x;
+          }
+          out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = out;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+
+    // ================= epilogue: TMEM -> registers -> global =================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const long long dst_off = img * p.d_n + (long long)(hd * p.plan.os + c.oa) * p.d_h + (long long)(wd * p.plan.os + c.ob) * p.d_w;
+    const long long msk_off = img * p.m_n + (long long)(hd * p.plan.os + c.oa) * p.m_h + (long long)(wd * p.plan.os + c.ob) * p.m_w;
+    const int Nn = p.plan.Nn;
+    constexpr int CH = BN < 32 ? BN : 32;
+#pragma unroll 1
+    for (int ch0 = 0; ch0 < BN; ch0 += CH) {
+      uint32_t raw[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
+      if (CH == 32) {
+        tmem_ld32(taddr, raw);
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(taddr, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+      }
+      tmem_ld_wait();
+      float v[32], u[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int n = n0 + ch0 + i;
+        float a = __uint_as_float(raw[i]);
+        float second = 0.f;
+        const bool live = mvalid && i < CH && n < Nn;
+        if (p.epi == CLEARVAE_EPI_BIAS_STATS) {
+          if (live && p.bias != nullptr) a += __ldg(p.bias + n);
+          if (!live) a = 0.f;
+          second = a * a;
+        } else {
+          if (live) {
+            const float y = ld_elem(p.msk, msk_off + n * p.m_c, p.msk_bf16);
+            const float act = p.msk_scale ? fmaf(y, __ldg(p.msk_scale + n), __ldg(p.msk_shift + n)) : y;
+            a = act > 0.f ? a : 0.f;
+            second = a * y;
+          } else {
+            a = 0.f;
+          }
+        }
+        v[i] = a;
+        u[i] = second;
+      }
+      // ---- store (vectorised when channels are the innermost dst dimension)
+      if (mvalid) {
+        if (p.d_c == 1 && n0 + ch0 + CH <= Nn && (CH % 8) == 0) {
+          if (p.dst_bf16) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + n0 + ch0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8)
+              *reinterpret_cast<uint4*>(d + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                                                            pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+          } else {
+            float* d = reinterpret_cast<float*>(p.dst) + dst_off + n0 + ch0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int n = n0 + ch0 + i;
+            if (n < Nn) {
+              if (p.dst_bf16) reinterpret_cast<__nv_bfloat16*>(p.dst)[dst_off + n * p.d_c] = __float2bfloat16(v[i]);
+              else reinterpret_cast<float*>(p.dst)[dst_off + n * p.d_c] = v[i];
+            }
+          }
+        }
+      }
+      // ---- per-channel statistics
+      if (p.stats != nullptr) {
+        transpose_reduce32(v);
+        transpose_reduce32(u);
+        const int n = n0 + ch0 + lane;
+        if (lane < CH && n < Nn) {
+          atomicAdd(p.stats + n, (double)v[0]);
+          atomicAdd(p.stats + Nn + n, (double)u[0]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================= B producer: TMA =================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], kBStage);
+        tma_load_2d(sB + s * kBStage, &tm.t[blockIdx.z], &full[s], kb * BK, n0);
+      }
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        mbar_wait(&full[s], (kb / NS) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * kAStage), b_base = smem_u32(sB + s * kBStage);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4) {
+          // A: interleave layout, 16-byte k-chunks BM*16 bytes apart (LBO), 8-row groups 128 bytes apart (SBO)
+          const uint64_t ad = smem_desc(a_base + k4 * 2 * (BM * 16), BM * 16, 128, kLayoutNone);
+          // B: 128-byte swizzled rows, 8-row groups 1024 bytes apart; K advance = +32 bytes inside the atom
+          const uint64_t bd = smem_desc(b_base + k4 * 32, 16, 1024, kLayoutSw128);
+          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// weight packing: fp32 reference layout -> bf16 [class][n_pad][Kp], zero padded
+// ---------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const Cls& c = plan.cls[blockIdx.y];
+  const int n_pad = (plan.Nn + 15) / 16 * 16;
+  const long long total = (long long)n_pad * c.Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / c.Kp), k = (int)(i % c.Kp);
+    float v = 0.f;
+    if (n < plan.Nn && k < c.ntaps * plan.Cs) {
+      const int t = k / plan.Cs, ch = k - t * plan.Cs;
+      v = w[n * plan.ws_n + ch * plan.ws_c + c.wtap[t]];
+    }
+    out[c.w_off + i] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+inline int pick_bn(int Nn) {
+  const int n_pad = (Nn + 15) / 16 * 16;
+  return n_pad >= 128 ? 128 : n_pad > 32 ? 64 : n_pad > 16 ? 32 : 16;
+}
+
+template <int BN>
+int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + (2 * NS + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tm, p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+void fill_t4(const clearvae_tensor4* t, const void*& ptr, long long& sn, long long& sh, long long& sw, long long& sc, int& bf) {
+  ptr = t->ptr; sn = t->sn; sh = t->sh; sw = t->sw; sc = t->sc; bf = t->dtype == CLEARVAE_BF16;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t clearvae_conv_packed_weight_bytes(const clearvae_conv_geom* g, int32_t role) {
+  Plan plan;
+  if (!g || !cvplan::make_plan(*g, role, BK, &plan)) return 0;
+  return (size_t)cvplan::packed_weight_elems(plan) * 2;
+}
+
+int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const float* weight, void* packed, void* stream) {
+  if (!g || !weight || !packed) return CLEARVAE_EINVAL;
+  Plan plan;
+  if (!cvplan::make_plan(*g, role, BK, &plan)) return CLEARVAE_EUNSUPPORTED;
+  const int n_pad = (plan.Nn + 15) / 16 * 16;
+  long long mx = 0;
+  for (int i = 0; i < plan.n_classes; ++i) mx = std::max(mx, (long long)n_pad * plan.cls[i].Kp);
+  dim3 grid((unsigned)std::min<long long>((mx + 255) / 256, 148 * 8), (unsigned)plan.n_classes);
+  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, weight, reinterpret_cast<__nv_bfloat16*>(packed));
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch, const clearvae_tensor4* src,
+                       const float* pre_scale, const float* pre_shift, int32_t pre_relu, const void* packed_weight,
+                       const float* bias, const clearvae_tensor4* dst, int32_t epilogue, const clearvae_tensor4* mask_src,
+                       const float* mask_scale, const float* mask_shift, double* stats, void* stream) {
+  if (!g || !src || !src->ptr || !dst || !dst->ptr || !packed_weight || batch <= 0) return CLEARVAE_EINVAL;
+  if (epilogue == CLEARVAE_EPI_MASK_STATS && (!mask_src || !mask_src->ptr)) return CLEARVAE_EINVAL;
+  if ((pre_scale == nullptr) != (pre_shift == nullptr)) return CLEARVAE_EINVAL;
+  if ((uintptr_t)packed_weight & 127) return CLEARVAE_EINVAL;
+  GemmParams p{};
+  if (!cvplan::make_plan(*g, role, BK, &p.plan)) return CLEARVAE_EUNSUPPORTED;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return CLEARVAE_EUNSUPPORTED;
+  const int BN = pick_bn(p.plan.Nn);
+  const int n_pad = (p.plan.Nn + 15) / 16 * 16;
+  TmapPack tm{};
+  long long max_m = 0;
+  for (int i = 0; i < p.plan.n_classes; ++i) {
+    const Cls& c = p.plan.cls[i];
+    cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)c.Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    void* base = (void*)(reinterpret_cast<const char*>(packed_weight) + (size_t)c.w_off * 2);
+    CUresult r = enc(&tm.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CLEARVAE_EINVAL;
+    max_m = std::max(max_m, (long long)batch * c.Hd * c.Wd);
+  }
+  p.batch = batch;
+  fill_t4(src, p.src, p.s_n, p.s_h, p.s_w, p.s_c, p.src_bf16);
+  p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
+  p.bias = bias;
+  { const void* q; fill_t4(dst, q, p.d_n, p.d_h, p.d_w, p.d_c, p.dst_bf16); p.dst = const_cast<void*>(q); }
+  p.epi = epilogue;
+  if (mask_src) fill_t4(mask_src, p.msk, p.m_n, p.m_h, p.m_w, p.m_c, p.msk_bf16);
+  p.msk_scale = mask_scale; p.msk_shift = mask_shift;
+  p.stats = stats;
+  dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)((n_pad + BN - 1) / BN), (unsigned)p.plan.n_classes);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 16: return launch<16>(tm, p, grid, st);
+    case 32: return launch<32>(tm, p, grid, st);
+    case 64: return launch<64>(tm, p, grid, st);
+    default: return launch<128>(tm, p, grid, st);
+  }
+}
+
+}  // extern "C"

@@ -209,6 +209,68 @@ Tensor recon_bwd(const Tensor& xhat, const Tensor& x, const Tensor& grad_out) {
 
 int64_t recon_workspace_bytes() { return (int64_t)clearvae_recon_workspace_bytes(); }
 
+// ---------------------------------------------------------------------------
+// convolution-shaped GEMMs
+// ---------------------------------------------------------------------------
+clearvae_conv_geom geom_from(at::IntArrayRef g) {
+  TORCH_CHECK(g.size() == 9, "clearvae: conv geometry = [transposed,k,stride,pad,out_pad,Cin,Cout,Hin,Win]");
+  clearvae_conv_geom q;
+  q.transposed = (int32_t)g[0]; q.k = (int32_t)g[1]; q.stride = (int32_t)g[2]; q.pad = (int32_t)g[3]; q.out_pad = (int32_t)g[4];
+  q.Cin = (int32_t)g[5]; q.Cout = (int32_t)g[6]; q.Hin = (int32_t)g[7]; q.Win = (int32_t)g[8];
+  return q;
+}
+// view [N,H,W,C] logical dims through explicit element strides (sn,sh,sw,sc)
+clearvae_tensor4 t4(const Tensor& t, at::IntArrayRef strides, const char* name) {
+  TORCH_CHECK(t.is_cuda(), "clearvae: ", name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kFloat || t.scalar_type() == at::kBFloat16, "clearvae: ", name, " must be fp32 or bf16");
+  TORCH_CHECK(strides.size() == 4, "clearvae: 4 strides expected for ", name);
+  clearvae_tensor4 q;
+  q.ptr = t.data_ptr();
+  q.sn = strides[0]; q.sh = strides[1]; q.sw = strides[2]; q.sc = strides[3];
+  q.dtype = t.scalar_type() == at::kBFloat16 ? CLEARVAE_BF16 : CLEARVAE_F32;
+  return q;
+}
+const float* optf(const OptTensor& t, const char* name) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  check_f32(*t, name);
+  return t->data_ptr<float>();
+}
+
+Tensor conv_pack_weight(at::IntArrayRef geom, int64_t role, const Tensor& weight) {
+  check_f32(weight, "weight");
+  const c10::cuda::CUDAGuard guard(weight.device());
+  auto g = geom_from(geom);
+  const size_t bytes = clearvae_conv_packed_weight_bytes(&g, (int32_t)role);
+  TORCH_CHECK(bytes > 0, "clearvae: unsupported conv geometry");
+  TORCH_CHECK(weight.numel() == (int64_t)g.Cin * g.Cout * g.k * g.k, "clearvae: weight size does not match the geometry");
+  Tensor packed = at::empty({(int64_t)(bytes / 2)}, weight.options().dtype(at::kBFloat16));
+  check_rc(clearvae_conv_pack_weight(&g, (int32_t)role, weight.data_ptr<float>(), packed.data_ptr(), cur_stream()), "conv_pack_weight");
+  return packed;
+}
+
+void conv_gemm(at::IntArrayRef geom, int64_t role, int64_t batch, const Tensor& src, at::IntArrayRef src_strides,
+               const OptTensor& pre_scale, const OptTensor& pre_shift, bool pre_relu, const Tensor& packed_weight,
+               const OptTensor& bias, Tensor dst, at::IntArrayRef dst_strides, int64_t epilogue, const OptTensor& mask_src,
+               at::IntArrayRef mask_strides, const OptTensor& mask_scale, const OptTensor& mask_shift, const OptTensor& stats) {
+  const c10::cuda::CUDAGuard guard(src.device());
+  auto g = geom_from(geom);
+  auto s4 = t4(src, src_strides, "src");
+  auto d4 = t4(dst, dst_strides, "dst");
+  clearvae_tensor4 m4{};
+  const clearvae_tensor4* mp = nullptr;
+  if (mask_src.has_value() && mask_src->defined()) { m4 = t4(*mask_src, mask_strides, "mask_src"); mp = &m4; }
+  double* st = nullptr;
+  if (stats.has_value() && stats->defined()) {
+    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kDouble && stats->is_contiguous(), "clearvae: stats must be a contiguous CUDA float64 tensor");
+    st = stats->data_ptr<double>();
+  }
+  TORCH_CHECK(packed_weight.is_cuda() && packed_weight.scalar_type() == at::kBFloat16, "clearvae: packed weight must be bf16");
+  check_rc(clearvae_conv_gemm(&g, (int32_t)role, batch, &s4, optf(pre_scale, "pre_scale"), optf(pre_shift, "pre_shift"),
+                              pre_relu ? 1 : 0, packed_weight.data_ptr(), optf(bias, "bias"), &d4, (int32_t)epilogue, mp,
+                              optf(mask_scale, "mask_scale"), optf(mask_shift, "mask_shift"), st, cur_stream()),
+           "conv_gemm");
+}
+
 }  // namespace
 
 TORCH_LIBRARY(clearvae, m) {
@@ -224,6 +286,10 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("recon_fwd(Tensor xhat, Tensor x, Tensor(a!) workspace) -> Tensor");
   m.def("recon_bwd(Tensor xhat, Tensor x, Tensor grad_out) -> Tensor");
   m.def("recon_workspace_bytes() -> int", &recon_workspace_bytes);
+  m.def("conv_pack_weight(int[] geom, int role, Tensor weight) -> Tensor");
+  m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "
+        "bool pre_relu, Tensor packed_weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, int epilogue, "
+        "Tensor? mask_src, int[] mask_strides, Tensor? mask_scale, Tensor? mask_shift, Tensor(b!)? stats) -> ()");
 }
 
 TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
@@ -233,4 +299,6 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("pair_mask", &pair_mask);
   m.impl("recon_fwd", &recon_fwd);
   m.impl("recon_bwd", &recon_bwd);
+  m.impl("conv_pack_weight", &conv_pack_weight);
+  m.impl("conv_gemm", &conv_gemm);
 }

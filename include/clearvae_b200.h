@@ -128,6 +128,45 @@ int clearvae_recon_fwd(const float* xhat, const float* x, int64_t B, int64_t per
 int clearvae_recon_bwd(const float* xhat, const float* x, const float* grad_out, int64_t B, int64_t per_sample,
                        float* dxhat, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Convolution-shaped GEMMs (encoder / decoder layers and the linear heads).
+ *
+ * Replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward and data-gradient
+ * as the reference stacks them at vae.py:15-46 and vae.py:113-156, with the
+ * preceding BatchNorm-apply + ReLU folded into the operand load ("pre-op") and
+ * the following BatchNorm's batch statistics accumulated in the epilogue.
+ * Tensor-core path: bf16 operands, fp32 accumulation in TMEM (tcgen05), weights
+ * staged by TMA from a packed K-major copy.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t transposed;  /* 0: Conv2d [Cout,Cin,k,k]; 1: ConvTranspose2d [Cin,Cout,k,k] */
+  int32_t k, stride, pad, out_pad;
+  int32_t Cin, Cout, Hin, Win;   /* a Linear(in,out) is k=1,stride=1,pad=0,Hin=Win=1 */
+} clearvae_conv_geom;
+
+/* strided view of a 4-D activation, element (n, h, w, c) at ptr + n*sn + h*sh + w*sw + c*sc (in elements) */
+typedef struct {
+  void* ptr;
+  int64_t sn, sh, sw, sc;
+  int32_t dtype;  /* CLEARVAE_F32 or CLEARVAE_BF16 */
+} clearvae_tensor4;
+enum { CLEARVAE_F32 = 0, CLEARVAE_BF16 = 1 };
+enum { CLEARVAE_ROLE_FPROP = 0, CLEARVAE_ROLE_DGRAD = 1 };
+/* epilogue of clearvae_conv_gemm */
+enum { CLEARVAE_EPI_BIAS_STATS = 0,  /* dst = acc + bias; stats += (sum v, sum v^2) per output channel      */
+       CLEARVAE_EPI_MASK_STATS = 1   /* dst = g = acc * [mask_src*mask_scale+mask_shift > 0];
+                                        stats += (sum g, sum g*mask_src): ReLU + BatchNorm backward sums    */ };
+
+size_t clearvae_conv_packed_weight_bytes(const clearvae_conv_geom* g, int32_t role);
+/* fp32 reference-layout weight -> bf16 packed GEMM operand(s) of (geometry, role) */
+int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const float* weight, void* packed, void* stream);
+
+int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
+                       const clearvae_tensor4* src, const float* pre_scale, const float* pre_shift, int32_t pre_relu,
+                       const void* packed_weight, const float* bias, const clearvae_tensor4* dst, int32_t epilogue,
+                       const clearvae_tensor4* mask_src, const float* mask_scale, const float* mask_shift,
+                       double* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

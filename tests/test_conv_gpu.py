@@ -1,0 +1,141 @@
+"""GPU: tcgen05 implicit-GEMM conv kernels vs torch convolutions on bf16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def nhwc_strides(t):  # t is [N,H,W,C] contiguous
+    return [t.stride(0), t.stride(1), t.stride(2), t.stride(3)]
+
+
+def run_gemm(geom, role, batch, src, src_strides, w, bias, dst, dst_strides, pre=None, relu=False, epi=0, mask=None,
+             mask_strides=(0, 0, 0, 0), mscale=None, mshift=None, stats=None):
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    pw = ops.conv_pack_weight(geom, role, w.contiguous())
+    ops.conv_gemm(geom, role, batch, src, list(src_strides), None if pre is None else pre[0], None if pre is None else pre[1],
+                  relu, pw, bias, dst, list(dst_strides), epi, mask, list(mask_strides), mscale, mshift, stats)
+    return dst
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("B,K,N", [(300, 2048, 32), (256, 64, 2048), (128, 16, 2048), (1000, 2048, 128), (77, 40, 20)])
+def test_linear_as_1x1(B, K, N):
+    g = torch.Generator().manual_seed(B + K + N)
+    x = bf(torch.randn(B, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    geom = [0, 1, 1, 0, 0, K, N, 1, 1]
+    dst = torch.empty(B, N, device=DEV)
+    stats = torch.zeros(2 * N, dtype=torch.float64, device=DEV)
+    run_gemm(geom, 0, B, x, (K, 0, 0, 1), w, b, dst, (N, 0, 0, 1), stats=stats)
+    want = F.linear(x, w, b)
+    assert rel_err(dst, want) < 2e-5, rel_err(dst, want)
+    assert torch.allclose(stats[:N].float(), want.sum(0), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[N:].float(), (want * want).sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("k,cin,cout,H,B", [(4, 32, 64, 32, 8), (3, 32, 64, 14, 16), (4, 3, 32, 64, 4), (3, 1, 32, 28, 8),
+                                             (4, 256, 512, 4, 32), (3, 64, 128, 7, 33)])
+def test_conv2d_fprop_and_dgrad(k, cin, cout, H, B):
+    g = torch.Generator().manual_seed(k * 1000 + cin + cout)
+    x = bf(torch.randn(B, cin, H, H, generator=g)).to(DEV)        # NCHW like the reference
+    w = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    want = F.conv2d(x, w, b, stride=2, padding=1)
+    Ho = want.shape[-1]
+    geom = [0, k, 2, 1, 0, cin, cout, H, H]
+    # NCHW source read through strides (n, h, w, c)
+    dst = torch.empty(B, Ho, Ho, cout, device=DEV)
+    run_gemm(geom, 0, B, x, (x.stride(0), x.stride(2), x.stride(3), x.stride(1)), w, b, dst, nhwc_strides(dst))
+    assert rel_err(dst.permute(0, 3, 1, 2), want) < 2e-5
+    # NHWC source (vector gather path when cin % 8 == 0)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    dst2 = torch.empty(B, Ho, Ho, cout, device=DEV)
+    run_gemm(geom, 0, B, xn, nhwc_strides(xn), w, b, dst2, nhwc_strides(dst2))
+    assert rel_err(dst2.permute(0, 3, 1, 2), want) < 2e-5
+    # data gradient: dy [B,Ho,Ho,cout] -> dx [B,H,H,cin]
+    dy = bf(torch.randn(B, cout, Ho, Ho, generator=g)).to(DEV)
+    dx_want = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=2, padding=1)
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dx = torch.empty(B, H, H, cin, device=DEV)
+    run_gemm(geom, 1, B, dyn, nhwc_strides(dyn), w, None, dx, nhwc_strides(dx))
+    assert rel_err(dx.permute(0, 3, 1, 2), dx_want) < 2e-5
+
+
+@pytest.mark.parametrize("k,op,cin,cout,H,B", [(4, 0, 64, 32, 16, 8), (3, 0, 128, 64, 4, 16), (3, 1, 64, 32, 7, 8),
+                                                (3, 1, 32, 3, 14, 8), (4, 0, 32, 3, 32, 4), (4, 0, 512, 256, 2, 32)])
+def test_conv_transpose_fprop_and_dgrad(k, op, cin, cout, H, B):
+    g = torch.Generator().manual_seed(k * 100 + op + cin + cout)
+    x = bf(torch.randn(B, cin, H, H, generator=g)).to(DEV)
+    w = bf(torch.randn(cin, cout, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    want = F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=op)
+    Ho = want.shape[-1]
+    geom = [1, k, 2, 1, op, cin, cout, H, H]
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    dst = torch.empty(B, Ho, Ho, cout, device=DEV)
+    run_gemm(geom, 0, B, xn, nhwc_strides(xn), w, b, dst, nhwc_strides(dst))
+    assert rel_err(dst.permute(0, 3, 1, 2), want) < 2e-5
+    # NCHW destination written through strides (what the last decoder layer does)
+    dst2 = torch.empty(B, cout, Ho, Ho, device=DEV)
+    run_gemm(geom, 0, B, xn, nhwc_strides(xn), w, b, dst2, (dst2.stride(0), dst2.stride(2), dst2.stride(3), dst2.stride(1)))
+    assert rel_err(dst2, want) < 2e-5
+    # data gradient of the transposed conv = strided gather
+    dy = bf(torch.randn(B, cout, Ho, Ho, generator=g)).to(DEV)
+    dx_want = F.conv2d(dy, w, None, stride=2, padding=1)
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dx = torch.empty(B, H, H, cin, device=DEV)
+    run_gemm(geom, 1, B, dyn, nhwc_strides(dyn), w, None, dx, nhwc_strides(dx))
+    assert rel_err(dx.permute(0, 3, 1, 2), dx_want) < 2e-5
+
+
+def test_preop_bf16_io_and_mask_epilogue():
+    g = torch.Generator().manual_seed(42)
+    B, cin, cout, H, k = 8, 64, 128, 16, 4
+    raw = torch.randn(B, H, H, cin, generator=g).to(DEV)
+    scale = (torch.rand(cin, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(cin, generator=g) * 0.3).to(DEV)
+    w = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    raw16 = raw.to(torch.bfloat16)
+    act = bf(torch.relu(raw16.float() * scale + shift))
+    want = F.conv2d(act.permute(0, 3, 1, 2), w, b, stride=2, padding=1)
+    Ho = want.shape[-1]
+    geom = [0, k, 2, 1, 0, cin, cout, H, H]
+    dst = torch.empty(B, Ho, Ho, cout, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    run_gemm(geom, 0, B, raw16, nhwc_strides(raw16), w, b, dst, nhwc_strides(dst), pre=(scale, shift), relu=True, stats=stats)
+    assert rel_err(dst.float().permute(0, 3, 1, 2), want) < 6e-3            # bf16 output rounding
+    assert torch.allclose(stats[:cout].float(), want.sum((0, 2, 3)), rtol=1e-3, atol=5e-2)  # stats from fp32 accumulators
+    # dgrad with the ReLU mask of the previous layer + BN-backward sums in the epilogue
+    dy = bf(torch.randn(B, Ho, Ho, cout, generator=g)).to(DEV)
+    dact_want = torch.nn.grad.conv2d_input((B, cin, H, H), w, dy.permute(0, 3, 1, 2), stride=2, padding=1).permute(0, 2, 3, 1)
+    mask = (raw16.float() * scale + shift) > 0
+    g_want = dact_want * mask
+    gout = torch.empty(B, H, H, cin, device=DEV)
+    st2 = torch.zeros(2 * cin, dtype=torch.float64, device=DEV)
+    run_gemm(geom, 1, B, dy, nhwc_strides(dy), w, None, gout, nhwc_strides(gout), epi=1, mask=raw16,
+             mask_strides=nhwc_strides(raw16), mscale=scale, mshift=shift, stats=st2)
+    assert rel_err(gout, g_want) < 2e-5
+    assert torch.allclose(st2[:cin].float(), g_want.sum((0, 1, 2)), rtol=1e-3, atol=1e-3)
+    assert torch.allclose(st2[cin:].float(), (g_want * raw16.float()).sum((0, 1, 2)), rtol=1e-3, atol=1e-3)
