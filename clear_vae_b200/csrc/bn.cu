@@ -1,0 +1,319 @@
+// Train-mode BatchNorm pieces around the conv GEMMs (nn.BatchNorm1d / nn.BatchNorm2d as
+// stacked at vae.py:17-44,115-154; semantics in SURVEY.md §8a': biased batch variance for
+// normalisation, unbiased for the running estimate, momentum 0.1, eps 1e-5).
+//
+// The batch statistics themselves are accumulated by the GEMM epilogues (double
+// atomics into a [2][C] buffer); the kernels here turn them into per-channel
+// scale/shift (forward) or into the affine coefficients of the BatchNorm backward,
+//     dy = a_c * g + b_c * y + c_c,
+// and stream the few elementwise passes that cannot ride on a GEMM (fc block, final
+// BN + sigmoid + reconstruction error).  All elementwise kernels are HBM-bound:
+// 16-byte accesses, grid = multiple of the SM count.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+constexpr int kNT = 256;
+
+__device__ __forceinline__ float ldf(const void* p, long long i, int bf) {
+  return bf ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void stf(void* p, long long i, int bf, float v) {
+  if (bf) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+inline int grid_for(long long n, int per_thread = 4) {
+  long long g = (n / per_thread + kNT - 1) / kNT;
+  const long long cap = 148 * 8;
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+// ---------------------------------------------------------------------------
+// stats[0..Cs) = sum, stats[Cs..2Cs) = sum of squares, Cs = C * group entries;
+// channel c owns entries [c*group, (c+1)*group).  Writes scale/shift (optionally
+// expanded `expand` times), saves mean / invstd, updates the running estimates and
+// clears the accumulator for the next step.
+// ---------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(double* stats, int C, int group, double count, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                                   float* shift, int expand, float* save_mean, float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int Cs = C * group;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < group; ++i) {
+    s += stats[c * group + i];
+    q += stats[Cs + c * group + i];
+    stats[c * group + i] = 0.0;
+    stats[Cs + c * group + i] = 0.0;
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd, sh = b - (float)mean * g * invstd;
+  for (int i = 0; i < expand; ++i) { scale[c * expand + i] = sc; shift[c * expand + i] = sh; }
+  save_mean[c] = (float)mean;
+  save_invstd[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// generic two-moment reduction over a flat tensor, channel(idx) = (idx / inner) % C.
+//   mode 0: (sum y, sum y^2)
+//   mode 1: g' = g * [act > 0] (act optional), (sum g', sum g'*y)
+// one CTA handles a contiguous slab of rows so per-thread channels stay fixed when inner == 1
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) bn_reduce_kernel(const void* y, int y_bf, const void* g, int g_bf, const void* act,
+                                                        int act_bf, long long total, int C, long long inner, int mode,
+                                                        double* stats) {
+  // thread-private accumulation is only valid when a thread always sees the same channel:
+  // stride through the tensor in steps of C*inner*k. Fall back to atomics per element group otherwise.
+  const long long period = (long long)C * inner;
+  const long long nper = total / period;  // samples
+  // each thread owns positions pos in [0, period) with pos = tid + j*stride, loops over samples
+  for (long long pos = (long long)blockIdx.x * kNT + threadIdx.x; pos < period; pos += (long long)gridDim.x * kNT) {
+    float s0 = 0.f, s1 = 0.f;
+    double d0 = 0.0, d1 = 0.0;
+    int cnt = 0;
+    for (long long smp = blockIdx.y; smp < nper; smp += gridDim.y) {
+      const long long i = smp * period + pos;
+      const float yv = ldf(y, i, y_bf);
+      if (mode == 0) {
+        s0 += yv; s1 = fmaf(yv, yv, s1);
+      } else {
+        float gv = ldf(g, i, g_bf);
+        if (act != nullptr && !(ldf(act, i, act_bf) > 0.f)) gv = 0.f;
+        s0 += gv; s1 = fmaf(gv, yv, s1);
+      }
+      if (++cnt == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }
+    }
+    d0 += s0; d1 += s1;
+    const int c = (int)(pos / inner);
+    atomicAdd(stats + c, d0);
+    atomicAdd(stats + C + c, d1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// out = act(raw * scale[ch] + shift[ch]); act: 0 none, 1 relu, 2 sigmoid.
+// optional fused reconstruction error vs `target` (sum of squares, * invB) like losses.py:45-47.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) bn_act_fwd_kernel(const void* raw, int raw_bf, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, long long total, int C,
+                                                         long long inner, int act, void* out, int out_bf,
+                                                         const float* __restrict__ target, float invB, float* sse_out,
+                                                         float* partial, unsigned* ticket) {
+  __shared__ float sred[kNT / 32 + 1];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < total; i += (long long)gridDim.x * kNT) {
+    const int ch = (int)((i / inner) % C);
+    float v = fmaf(ldf(raw, i, raw_bf), __ldg(scale + ch), __ldg(shift + ch));
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = 1.f / (1.f + __expf(-v));
+    stf(out, i, out_bf, v);
+    if (target != nullptr) { const float d = v - __ldg(target + i); acc = fmaf(d, d, acc); }
+  }
+  if (target == nullptr) return;
+  acc = cv::block_sum<kNT>(acc, sred);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc;
+    __threadfence();
+    sred[kNT / 32] = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (sred[kNT / 32] != 0.f) {
+    __threadfence();
+    float s = 0.f;
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += kNT) s += __ldcg(partial + c);
+    s = cv::block_sum<kNT>(s, sred);
+    if (threadIdx.x == 0) { *sse_out = s * invB; *ticket = 0u; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// final layer backward: xhat = sigmoid(bn(raw)); recon = invB * sum (xhat - x)^2
+//   g_pre = (grad_xhat_ext + grad_recon * 2 invB (xhat - x)) * xhat (1 - xhat)
+// writes g_pre and accumulates (sum g_pre, sum g_pre * raw) per channel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) sigmoid_mse_bwd_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
+                                                              const float* __restrict__ grad_recon,
+                                                              const float* __restrict__ grad_ext, const void* raw, int raw_bf,
+                                                              long long total, int C, long long inner, float twoInvB,
+                                                              float* __restrict__ g_pre, double* stats) {
+  const float gr = grad_recon ? __ldg(grad_recon) * twoInvB : 0.f;
+  const long long period = (long long)C * inner;
+  const long long nper = total / period;
+  for (long long pos = (long long)blockIdx.x * kNT + threadIdx.x; pos < period; pos += (long long)gridDim.x * kNT) {
+    double d0 = 0.0, d1 = 0.0;
+    float s0 = 0.f, s1 = 0.f;
+    int cnt = 0;
+    for (long long smp = blockIdx.y; smp < nper; smp += gridDim.y) {
+      const long long i = smp * period + pos;
+      const float xh = __ldg(xhat + i);
+      float g = gr * (xh - __ldg(x + i));
+      if (grad_ext) g += __ldg(grad_ext + i);
+      g *= xh * (1.f - xh);
+      g_pre[i] = g;
+      s0 += g; s1 = fmaf(g, ldf(raw, i, raw_bf), s1);
+      if (++cnt == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }
+    }
+    d0 += s0; d1 += s1;
+    const int c = (int)(pos / inner);
+    atomicAdd(stats + c, d0);
+    atomicAdd(stats + C + c, d1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BatchNorm backward coefficients from (S1 = sum g, S2 = sum g*y):
+//   sum g*xhat = r (S2 - mu S1);  dgamma = that;  dbeta = S1
+//   dy = gamma r g  -  gamma r^2 (sum g xhat)/M * y  +  gamma r (mu r (sum g xhat) - S1)/M
+// coef layout [3][C] (a, b, c); clears the accumulator.
+// ---------------------------------------------------------------------------
+__global__ void bn_bwd_coef_kernel(double* stats, int C, int group, double count, const float* gamma, const float* save_mean,
+                                   const float* save_invstd, float* coef, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int Cs = C * group;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < group; ++i) {
+    s1 += stats[c * group + i];
+    s2 += stats[Cs + c * group + i];
+    stats[c * group + i] = 0.0;
+    stats[Cs + c * group + i] = 0.0;
+  }
+  const double mu = save_mean[c], r = save_invstd[c], g = gamma ? gamma[c] : 1.0;
+  const double sgx = r * (s2 - mu * s1);
+  coef[c] = (float)(g * r);
+  coef[C + c] = (float)(-g * r * r * sgx / count);
+  coef[2 * C + c] = (float)(g * r * (mu * r * sgx - s1) / count);
+  if (dgamma) dgamma[c] = (float)sgx;
+  if (dbeta) dbeta[c] = (float)s1;
+}
+
+// dy = a[ch] * g' + b[ch] * y + c[ch],  g' = g * [act > 0] when act is given
+__global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_bf, const void* y, int y_bf, const void* act,
+                                                           int act_bf, const float* __restrict__ coef, long long total, int C,
+                                                           long long inner, void* dy, int dy_bf) {
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < total; i += (long long)gridDim.x * kNT) {
+    const int ch = (int)((i / inner) % C);
+    float gv = ldf(g, i, g_bf);
+    if (act != nullptr && !(ldf(act, i, act_bf) > 0.f)) gv = 0.f;
+    const float v = fmaf(__ldg(coef + ch), gv, fmaf(__ldg(coef + C + ch), ldf(y, i, y_bf), __ldg(coef + 2 * C + ch)));
+    stf(dy, i, dy_bf, v);
+  }
+}
+
+// out[c] (+)= sum over rows of x[r][c]  (bias gradients of the linear heads)
+__global__ void __launch_bounds__(kNT) colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* out) {
+  for (int c = blockIdx.x * kNT + threadIdx.x; c < cols; c += gridDim.x * kNT) {
+    float s = 0.f;
+    for (long long r = 0; r < rows; ++r) s += x[r * cols + c];
+    out[c] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int clearvae_bn_finalize(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                         int32_t expand, float* save_mean, float* save_invstd, void* stream) {
+  if (!stats || !scale || !shift || !save_mean || !save_invstd || C <= 0 || group <= 0 || expand <= 0 || count <= 0) return CLEARVAE_EINVAL;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, C, group, count, gamma, beta, running_mean,
+                                                                         running_var, momentum, eps, scale, shift, expand,
+                                                                         save_mean, save_invstd);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_bn_reduce(const void* y, int32_t y_dtype, const void* g, int32_t g_dtype, const void* act, int32_t act_dtype,
+                       int64_t total, int32_t C, int64_t inner, int32_t mode, double* stats, void* stream) {
+  if (!y || !stats || total <= 0 || C <= 0 || inner <= 0 || (mode == 1 && !g)) return CLEARVAE_EINVAL;
+  const long long period = (long long)C * inner;
+  if (total % period) return CLEARVAE_EINVAL;
+  const long long nper = total / period;
+  int gx = (int)((period + kNT - 1) / kNT);
+  if (gx > 148 * 4) gx = 148 * 4;
+  long long gy = (148 * 8 + gx - 1) / gx;
+  if (gy > nper) gy = nper;
+  if (gy < 1) gy = 1;
+  bn_reduce_kernel<<<dim3(gx, (unsigned)gy), kNT, 0, (cudaStream_t)stream>>>(y, y_dtype, g, g_dtype, act, act_dtype, total, C,
+                                                                             inner, mode, stats);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t clearvae_bn_act_workspace_bytes(void) { return 256 + 148 * 8 * sizeof(float); }
+
+int clearvae_bn_act_fwd(const void* raw, int32_t raw_dtype, const float* scale, const float* shift, int64_t total, int32_t C,
+                        int64_t inner, int32_t act, void* out, int32_t out_dtype, const float* target, int64_t batch,
+                        float* sse_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!raw || !scale || !shift || !out || total <= 0 || C <= 0 || inner <= 0) return CLEARVAE_EINVAL;
+  unsigned* ticket = nullptr;
+  float* partial = nullptr;
+  if (target) {
+    if (!sse_out || !workspace || batch <= 0) return CLEARVAE_EINVAL;
+    if (workspace_bytes < clearvae_bn_act_workspace_bytes()) return CLEARVAE_EWORKSPACE;
+    ticket = reinterpret_cast<unsigned*>(workspace);
+    partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  }
+  bn_act_fwd_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(raw, raw_dtype, scale, shift, total, C, inner, act, out,
+                                                                       out_dtype, target, target ? 1.f / (float)batch : 0.f,
+                                                                       sse_out, partial, ticket);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_sigmoid_mse_bwd(const float* xhat, const float* x, const float* grad_recon, const float* grad_ext, const void* raw,
+                             int32_t raw_dtype, int64_t total, int32_t C, int64_t inner, int64_t batch, float* g_pre,
+                             double* stats, void* stream) {
+  if (!xhat || !x || !raw || !g_pre || !stats || total <= 0 || C <= 0 || inner <= 0 || batch <= 0) return CLEARVAE_EINVAL;
+  const long long period = (long long)C * inner;
+  if (total % period) return CLEARVAE_EINVAL;
+  const long long nper = total / period;
+  int gx = (int)((period + kNT - 1) / kNT);
+  if (gx > 148 * 4) gx = 148 * 4;
+  long long gy = (148 * 8 + gx - 1) / gx;
+  if (gy > nper) gy = nper;
+  if (gy < 1) gy = 1;
+  sigmoid_mse_bwd_kernel<<<dim3(gx, (unsigned)gy), kNT, 0, (cudaStream_t)stream>>>(xhat, x, grad_recon, grad_ext, raw, raw_dtype,
+                                                                                   total, C, inner, 2.f / (float)batch, g_pre, stats);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_bn_bwd_coef(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* save_mean,
+                         const float* save_invstd, float* coef, float* dgamma, float* dbeta, void* stream) {
+  if (!stats || !save_mean || !save_invstd || !coef || C <= 0 || group <= 0 || count <= 0) return CLEARVAE_EINVAL;
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, C, group, count, gamma, save_mean, save_invstd, coef,
+                                                                         dgamma, dbeta);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t y_dtype, const void* act, int32_t act_dtype,
+                          const float* coef, int64_t total, int32_t C, int64_t inner, void* dy, int32_t dy_dtype, void* stream) {
+  if (!g || !y || !coef || !dy || total <= 0 || C <= 0 || inner <= 0) return CLEARVAE_EINVAL;
+  bn_bwd_apply_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(g, g_dtype, y, y_dtype, act, act_dtype, coef, total, C,
+                                                                         inner, dy, dy_dtype);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0) return CLEARVAE_EINVAL;
+  colsum_kernel<<<(cols + kNT - 1) / kNT, kNT, 0, (cudaStream_t)stream>>>(x, rows, cols, out);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -309,6 +309,222 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------
+// weight gradient:  dW[kidx, n] += sum_{pixels m} act[m @ tap(kidx), c(kidx)] * dy[m, n]
+//   GEMM with M = (tap, channel) rows, N = output channels, K = pixels (split over CTAs).
+//   Both operands are pixel-major in HBM (NHWC: channels contiguous), i.e. MN-major for
+//   this GEMM, so the producers copy 16-byte channel runs into the UMMA MN-major
+//   interleave layout [mn-group][pixel][8 x bf16] unchanged — no transposition anywhere.
+//   Partial sums of the split-K CTAs are reduced with fp32 red.global.add into the
+//   reference weight layout.
+// ---------------------------------------------------------------------------
+struct WgradParams {
+  Plan plan;   // the FPROP plan of the layer
+  long long batch;
+  const void* src; long long s_n, s_h, s_w, s_c; int src_bf16;
+  const float *pre_scale, *pre_shift; int pre_relu;
+  const void* dy; long long y_n, y_h, y_w, y_c; int dy_bf16;
+  float* dw;
+  int splits;
+};
+
+constexpr int WK = 64;                       // pixels per k-block
+constexpr int kWStageA = 128 * WK * 2;       // 16 KiB
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p) {
+  constexpr int kBStage = BN * WK * 2;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + NS * kWStageA;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + NS * kBStage);
+  uint64_t* empty = full + NS;
+  uint64_t* tmem_full = empty + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const Cls& c = p.plan.cls[cls_id];
+  const int Cs = p.plan.Cs, Kreal = c.ntaps * Cs;
+  const int k0 = blockIdx.x * 128;  // first (tap, channel) row of this tile
+  if (k0 >= Kreal) return;
+  const int n0 = blockIdx.y * BN;
+  const long long Mc = p.batch * c.Hd * c.Wd;
+  const long long nkb_total = (Mc + WK - 1) / WK;
+  const long long kb_begin = nkb_total * split / p.splits, kb_end = nkb_total * (split + 1) / p.splits;
+  const int nkb = (int)(kb_end - kb_begin);
+  if (nkb <= 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // producers: thread = (pixel px of the k-block, half hf); 8 A chunks + BN/16 B chunks each
+    const int px = threadIdx.x & 63, hf = threadIdx.x >> 6;
+    const bool vec = (Cs % 8 == 0) && p.s_c == 1;
+    const int Nn = p.plan.Nn;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NS;
+      const long long m = (kb_begin + kb) * WK + px;
+      const bool mvalid = m < Mc;
+      const long long mm = mvalid ? m : 0;
+      const int wd = (int)(mm % c.Wd);
+      const int hd = (int)((mm / c.Wd) % c.Hd);
+      const long long img = mm / ((long long)c.Wd * c.Hd);
+      const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
+      const long long img_off = img * p.s_n;
+      const long long dy_off = img * p.y_n + (long long)(hd * p.plan.os + c.oa) * p.y_h + (long long)(wd * p.plan.os + c.ob) * p.y_w;
+      mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+      unsigned char* a_st = sA + s * kWStageA;
+      unsigned char* b_st = sB + s * kBStage;
+      // ---- A: gathered activation, mn-groups hf*8 .. hf*8+7
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int grp = hf * 8 + j;
+        const int kidx = k0 + grp * 8;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (mvalid && kidx < Kreal) {
+          float v[8];
+          if (vec) {
+            const int t = kidx / Cs, ch = kidx - t * Cs;
+            const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+            if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
+              const long long off = img_off + hs * p.s_h + ws * p.s_w + ch;
+              if (p.src_bf16) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+              } else {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off + 4));
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (p.pre_scale != nullptr) v[i] = fmaf(v[i], __ldg(p.pre_scale + ch + i), __ldg(p.pre_shift + ch + i));
+                if (p.pre_relu) v[i] = fmaxf(v[i], 0.f);
+              }
+              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int kk = kidx + i;
+              float x = 0.f;
+              if (kk < Kreal) {
+                const int t = kk / Cs, ch = kk - t * Cs;
+                const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+                if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
+                  x = ld_elem(p.src, img_off + hs * p.s_h + ws * p.s_w + ch * p.s_c, p.src_bf16);
+                  if (p.pre_scale != nullptr) x = fmaf(x, __ldg(p.pre_scale + ch), __ldg(p.pre_shift + ch));
+                  if (p.pre_relu) x = fmaxf(x, 0.f);
+                }
+              }
+              v[i] = x;
+            }
+            out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+        }
+        *reinterpret_cast<uint4*>(a_st + grp * (WK * 16) + px * 16) = out;
+      }
+      // ---- B: dy rows, n-groups split between the two halves
+      constexpr int NG = BN / 8;
+#pragma unroll
+      for (int j = 0; j < (NG + 1) / 2; ++j) {
+        const int grp = hf * ((NG + 1) / 2) + j;
+        if (grp < NG) {
+          const int n = n0 + grp * 8;
+          uint4 out = make_uint4(0u, 0u, 0u, 0u);
+          if (mvalid && n < Nn) {
+            if (p.y_c == 1 && n + 8 <= Nn) {
+              if (p.dy_bf16) {
+                out = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + dy_off + n));
+              } else {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + dy_off + n));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + dy_off + n + 4));
+                out = make_uint4(pack_bf16(q0.x, q0.y), pack_bf16(q0.z, q0.w), pack_bf16(q1.x, q1.y), pack_bf16(q1.z, q1.w));
+              }
+            } else {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = (n + i < Nn) ? ld_elem(p.dy, dy_off + (n + i) * p.y_c, p.dy_bf16) : 0.f;
+              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+          *reinterpret_cast<uint4*>(b_st + grp * (WK * 16) + px * 16) = out;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+
+    // ---- epilogue: scatter-add the tile into the reference weight layout
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int kidx = k0 + threadIdx.x;
+    const bool rvalid = kidx < Kreal;
+    const int t = rvalid ? kidx / Cs : 0, ch = rvalid ? kidx - t * Cs : 0;
+    const long long row_off = ch * p.plan.ws_c + c.wtap[t];
+    constexpr int CH = BN < 32 ? BN : 32;
+#pragma unroll 1
+    for (int ch0 = 0; ch0 < BN; ch0 += CH) {
+      uint32_t raw[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
+      if (CH == 32) {
+        tmem_ld32(taddr, raw);
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(taddr, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+      }
+      tmem_ld_wait();
+      if (rvalid) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int n = n0 + ch0 + i;
+          if (n < Nn) atomicAdd(p.dw + n * p.plan.ws_n + row_off, __uint_as_float(raw[i]));
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(kFmtBF16, 128, BN, 1, 1);  // both operands MN-major
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        mbar_wait(&full[s], (kb / NS) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * kWStageA), b_base = smem_u32(sB + s * kBStage);
+#pragma unroll
+        for (int k4 = 0; k4 < WK / 16; ++k4) {
+          // MN-major interleave: 8-pixel k-groups 128 B apart (LBO), 8-channel mn-groups WK*16 B apart (SBO)
+          const uint64_t ad = smem_desc(a_base + k4 * 256, 128, WK * 16, kLayoutNone);
+          const uint64_t bd = smem_desc(b_base + k4 * 256, 128, WK * 16, kLayoutNone);
+          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // ---------------------------------------------------------------------------
 // weight packing: fp32 reference layout -> bf16 [class][n_pad][Kp], zero padded
 // ---------------------------------------------------------------------------
@@ -370,9 +586,58 @@ void fill_t4(const clearvae_tensor4* t, const void*& ptr, long long& sn, long lo
   ptr = t->ptr; sn = t->sn; sh = t->sh; sw = t->sw; sc = t->sc; bf = t->dtype == CLEARVAE_BF16;
 }
 
+
+template <int BN>
+int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = NS * kWStageA + NS * BN * WK * 2 + (2 * NS + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  wgrad_tc_kernel<BN><<<grid, kThreads, smem, st>>>(p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
+                        const float* pre_shift, int32_t pre_relu, const clearvae_tensor4* dy, float* dweight, void* stream) {
+  if (!g || !src || !src->ptr || !dy || !dy->ptr || !dweight || batch <= 0) return CLEARVAE_EINVAL;
+  if ((pre_scale == nullptr) != (pre_shift == nullptr)) return CLEARVAE_EINVAL;
+  WgradParams p{};
+  if (!cvplan::make_plan(*g, cvplan::kFprop, BK, &p.plan)) return CLEARVAE_EUNSUPPORTED;
+  const int BN = pick_bn(p.plan.Nn);
+  const int n_pad = (p.plan.Nn + 15) / 16 * 16;
+  p.batch = batch;
+  fill_t4(src, p.src, p.s_n, p.s_h, p.s_w, p.s_c, p.src_bf16);
+  p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
+  fill_t4(dy, p.dy, p.y_n, p.y_h, p.y_w, p.y_c, p.dy_bf16);
+  p.dw = dweight;
+  int max_k = 0;
+  long long max_m = 0;
+  for (int i = 0; i < p.plan.n_classes; ++i) {
+    max_k = std::max(max_k, p.plan.cls[i].ntaps * p.plan.Cs);
+    max_m = std::max(max_m, (long long)batch * p.plan.cls[i].Hd * p.plan.cls[i].Wd);
+  }
+  const int tiles = ((max_k + 127) / 128) * ((n_pad + BN - 1) / BN) * p.plan.n_classes;
+  // split the pixel reduction so the grid is ~2 waves of 148 SMs, each CTA keeping >= 4 k-blocks
+  long long splits = std::max<long long>(1, (2 * 148 + tiles - 1) / tiles);
+  splits = std::min<long long>(splits, std::max<long long>(1, max_m / (WK * 4)));
+  p.splits = (int)splits;
+  dim3 grid((unsigned)((max_k + 127) / 128), (unsigned)((n_pad + BN - 1) / BN), (unsigned)(p.plan.n_classes * p.splits));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 16: return launch_wgrad<16>(p, grid, st);
+    case 32: return launch_wgrad<32>(p, grid, st);
+    case 64: return launch_wgrad<64>(p, grid, st);
+    default: return launch_wgrad<128>(p, grid, st);
+  }
+}
 
 size_t clearvae_conv_packed_weight_bytes(const clearvae_conv_geom* g, int32_t role) {
   Plan plan;

@@ -271,6 +271,126 @@ void conv_gemm(at::IntArrayRef geom, int64_t role, int64_t batch, const Tensor& 
            "conv_gemm");
 }
 
+void conv_wgrad(at::IntArrayRef geom, int64_t batch, const Tensor& src, at::IntArrayRef src_strides, const OptTensor& pre_scale,
+                const OptTensor& pre_shift, bool pre_relu, const Tensor& dy, at::IntArrayRef dy_strides, Tensor dweight) {
+  const c10::cuda::CUDAGuard guard(src.device());
+  auto g = geom_from(geom);
+  auto s4 = t4(src, src_strides, "src");
+  auto y4 = t4(dy, dy_strides, "dy");
+  check_f32(dweight, "dweight");
+  TORCH_CHECK(dweight.numel() == (int64_t)g.Cin * g.Cout * g.k * g.k, "clearvae: dweight size does not match the geometry");
+  check_rc(clearvae_conv_wgrad(&g, batch, &s4, optf(pre_scale, "pre_scale"), optf(pre_shift, "pre_shift"), pre_relu ? 1 : 0, &y4,
+                               dweight.data_ptr<float>(), cur_stream()),
+           "conv_wgrad");
+}
+
+int dt_of(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous(), "clearvae: ", name, " must be a contiguous CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kFloat || t.scalar_type() == at::kBFloat16, "clearvae: ", name, " must be fp32 or bf16");
+  return t.scalar_type() == at::kBFloat16 ? CLEARVAE_BF16 : CLEARVAE_F32;
+}
+double* stats_ptr(const Tensor& t) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kDouble && t.is_contiguous(), "clearvae: stats must be contiguous CUDA float64");
+  return t.data_ptr<double>();
+}
+float* optf_mut(const OptTensor& t, const char* name) { return const_cast<float*>(optf(t, name)); }
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> bn_finalize(Tensor stats, int64_t C, int64_t group, double count, const OptTensor& gamma,
+                                                       const OptTensor& beta, const OptTensor& running_mean,
+                                                       const OptTensor& running_var, double momentum, double eps, int64_t expand) {
+  const c10::cuda::CUDAGuard guard(stats.device());
+  TORCH_CHECK(stats.numel() >= 2 * C * group, "clearvae: stats too small");
+  auto fopt = stats.options().dtype(at::kFloat);
+  Tensor scale = at::empty({C * expand}, fopt), shift = at::empty({C * expand}, fopt), mean = at::empty({C}, fopt), invstd = at::empty({C}, fopt);
+  check_rc(clearvae_bn_finalize(stats_ptr(stats), (int32_t)C, (int32_t)group, count, optf(gamma, "gamma"), optf(beta, "beta"),
+                                optf_mut(running_mean, "running_mean"), optf_mut(running_var, "running_var"), (float)momentum,
+                                (float)eps, scale.data_ptr<float>(), shift.data_ptr<float>(), (int32_t)expand,
+                                mean.data_ptr<float>(), invstd.data_ptr<float>(), cur_stream()),
+           "bn_finalize");
+  return {scale, shift, mean, invstd};
+}
+
+void bn_reduce(const Tensor& y, const OptTensor& g, const OptTensor& act, int64_t C, int64_t inner, int64_t mode, Tensor stats) {
+  const c10::cuda::CUDAGuard guard(y.device());
+  const bool hg = g.has_value() && g->defined(), ha = act.has_value() && act->defined();
+  TORCH_CHECK(!hg || g->numel() == y.numel(), "clearvae: g / y size mismatch");
+  TORCH_CHECK(stats.numel() >= 2 * C, "clearvae: stats too small");
+  check_rc(clearvae_bn_reduce(y.data_ptr(), dt_of(y, "y"), hg ? g->data_ptr() : nullptr, hg ? dt_of(*g, "g") : 0,
+                              ha ? act->data_ptr() : nullptr, ha ? dt_of(*act, "act") : 0, y.numel(), (int32_t)C, inner,
+                              (int32_t)mode, stats_ptr(stats), cur_stream()),
+           "bn_reduce");
+}
+
+std::tuple<Tensor, Tensor> bn_act_fwd(const Tensor& raw, const Tensor& scale, const Tensor& shift, int64_t C, int64_t inner,
+                                      int64_t act, int64_t out_dtype, const OptTensor& target, int64_t batch, Tensor workspace) {
+  const c10::cuda::CUDAGuard guard(raw.device());
+  check_f32(scale, "scale");
+  check_f32(shift, "shift");
+  Tensor out = at::empty(raw.sizes(), raw.options().dtype(out_dtype == CLEARVAE_BF16 ? at::kBFloat16 : at::kFloat));
+  const bool ht = target.has_value() && target->defined();
+  Tensor sse = at::empty({}, raw.options().dtype(at::kFloat));
+  if (ht) { check_f32(*target, "target"); TORCH_CHECK(target->numel() == raw.numel(), "clearvae: target size mismatch"); }
+  check_rc(clearvae_bn_act_fwd(raw.data_ptr(), dt_of(raw, "raw"), scale.data_ptr<float>(), shift.data_ptr<float>(), raw.numel(),
+                               (int32_t)C, inner, (int32_t)act, out.data_ptr(), (int32_t)out_dtype,
+                               ht ? target->data_ptr<float>() : nullptr, batch, sse.data_ptr<float>(), workspace.data_ptr(),
+                               (size_t)workspace.nbytes(), cur_stream()),
+           "bn_act_fwd");
+  return {out, sse};
+}
+
+Tensor sigmoid_mse_bwd(const Tensor& xhat, const Tensor& x, const OptTensor& grad_recon, const OptTensor& grad_ext, const Tensor& raw,
+                       int64_t C, int64_t inner, int64_t batch, Tensor stats) {
+  const c10::cuda::CUDAGuard guard(xhat.device());
+  check_f32(xhat, "xhat");
+  check_f32(x, "x");
+  TORCH_CHECK(xhat.numel() == x.numel() && raw.numel() == x.numel(), "clearvae: size mismatch");
+  Tensor g = at::empty_like(xhat);
+  check_rc(clearvae_sigmoid_mse_bwd(xhat.data_ptr<float>(), x.data_ptr<float>(), optf(grad_recon, "grad_recon"),
+                                    optf(grad_ext, "grad_ext"), raw.data_ptr(), dt_of(raw, "raw"), xhat.numel(), (int32_t)C, inner,
+                                    batch, g.data_ptr<float>(), stats_ptr(stats), cur_stream()),
+           "sigmoid_mse_bwd");
+  return g;
+}
+
+std::tuple<Tensor, Tensor, Tensor> bn_bwd_coef(Tensor stats, int64_t C, int64_t group, double count, const OptTensor& gamma,
+                                               const Tensor& mean, const Tensor& invstd) {
+  const c10::cuda::CUDAGuard guard(stats.device());
+  check_f32(mean, "mean");
+  check_f32(invstd, "invstd");
+  auto fopt = mean.options();
+  Tensor coef = at::empty({3, C}, fopt), dgamma = at::empty({C}, fopt), dbeta = at::empty({C}, fopt);
+  check_rc(clearvae_bn_bwd_coef(stats_ptr(stats), (int32_t)C, (int32_t)group, count, optf(gamma, "gamma"), mean.data_ptr<float>(),
+                                invstd.data_ptr<float>(), coef.data_ptr<float>(), dgamma.data_ptr<float>(),
+                                dbeta.data_ptr<float>(), cur_stream()),
+           "bn_bwd_coef");
+  return {coef, dgamma, dbeta};
+}
+
+Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, const Tensor& coef, int64_t C, int64_t inner,
+                    int64_t out_dtype) {
+  const c10::cuda::CUDAGuard guard(g.device());
+  check_f32(coef, "coef");
+  TORCH_CHECK(g.numel() == y.numel(), "clearvae: g / y size mismatch");
+  const bool ha = act.has_value() && act->defined();
+  Tensor dy = at::empty(y.sizes(), y.options().dtype(out_dtype == CLEARVAE_BF16 ? at::kBFloat16 : at::kFloat));
+  check_rc(clearvae_bn_bwd_apply(g.data_ptr(), dt_of(g, "g"), y.data_ptr(), dt_of(y, "y"), ha ? act->data_ptr() : nullptr,
+                                 ha ? dt_of(*act, "act") : 0, coef.data_ptr<float>(), g.numel(), (int32_t)C, inner, dy.data_ptr(),
+                                 (int32_t)out_dtype, cur_stream()),
+           "bn_bwd_apply");
+  return dy;
+}
+
+Tensor colsum(const Tensor& x) {
+  check_f32(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2, "clearvae: colsum expects a matrix");
+  Tensor out = at::empty({x.size(1)}, x.options());
+  check_rc(clearvae_colsum(x.data_ptr<float>(), x.size(0), (int32_t)x.size(1), out.data_ptr<float>(), cur_stream()), "colsum");
+  return out;
+}
+
+int64_t bn_act_workspace_bytes() { return (int64_t)clearvae_bn_act_workspace_bytes(); }
+
 }  // namespace
 
 TORCH_LIBRARY(clearvae, m) {
@@ -287,6 +407,19 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("recon_bwd(Tensor xhat, Tensor x, Tensor grad_out) -> Tensor");
   m.def("recon_workspace_bytes() -> int", &recon_workspace_bytes);
   m.def("conv_pack_weight(int[] geom, int role, Tensor weight) -> Tensor");
+  m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
+        "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
+  m.def("bn_finalize(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
+        "Tensor(c!)? running_var, float momentum, float eps, int expand) -> (Tensor, Tensor, Tensor, Tensor)");
+  m.def("bn_reduce(Tensor y, Tensor? g, Tensor? act, int C, int inner, int mode, Tensor(a!) stats) -> ()");
+  m.def("bn_act_fwd(Tensor raw, Tensor scale, Tensor shift, int C, int inner, int act, int out_dtype, Tensor? target, int batch, "
+        "Tensor(a!) workspace) -> (Tensor, Tensor)");
+  m.def("sigmoid_mse_bwd(Tensor xhat, Tensor x, Tensor? grad_recon, Tensor? grad_ext, Tensor raw, int C, int inner, int batch, "
+        "Tensor(a!) stats) -> Tensor");
+  m.def("bn_bwd_coef(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor mean, Tensor invstd) -> (Tensor, Tensor, Tensor)");
+  m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor coef, int C, int inner, int out_dtype) -> Tensor");
+  m.def("colsum(Tensor x) -> Tensor");
+  m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "
         "bool pre_relu, Tensor packed_weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, int epilogue, "
         "Tensor? mask_src, int[] mask_strides, Tensor? mask_scale, Tensor? mask_shift, Tensor(b!)? stats) -> ()");
@@ -301,4 +434,12 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("recon_bwd", &recon_bwd);
   m.impl("conv_pack_weight", &conv_pack_weight);
   m.impl("conv_gemm", &conv_gemm);
+  m.impl("conv_wgrad", &conv_wgrad);
+  m.impl("bn_finalize", &bn_finalize);
+  m.impl("bn_reduce", &bn_reduce);
+  m.impl("bn_act_fwd", &bn_act_fwd);
+  m.impl("sigmoid_mse_bwd", &sigmoid_mse_bwd);
+  m.impl("bn_bwd_coef", &bn_bwd_coef);
+  m.impl("bn_bwd_apply", &bn_bwd_apply);
+  m.impl("colsum", &colsum);
 }

@@ -1,0 +1,366 @@
+"""Layer engine: runs the conv encoder / decoder stacks of `VAE` / `VAE64`
+(reference `code/src/models/vae.py:15-46,113-156`) on the sm_100a kernels and
+implements their backward by hand (no autograd graph inside a stack).
+
+Data layout in HBM
+  * activations between layers: raw (pre-BatchNorm) conv outputs, NHWC, bf16 by default
+    (`act_dtype`); BatchNorm-apply + ReLU is folded into the *consumer's* operand load, so
+    every activation is written once and read once per consumer;
+  * boundary tensors keep the reference layout: input `x` and `xhat` are NCHW fp32 (read /
+    written through strides), the encoder output feeding the linear heads and the decoder
+    fc output are stored in the reference's flatten order (channel-major) so the
+    `Linear(2048, D)` / `Linear(2D, 2048)` weights are used unpermuted;
+  * weights: fp32 masters in the reference layout (state_dict-compatible) + packed bf16
+    K-major copies per GEMM role, re-packed when the master's version counter changes.
+
+Per conv block the forward is 2 launches (GEMM with fused bias + batch-statistics epilogue,
+BatchNorm finalize) and the backward 4 (coefficients, dy materialisation, weight-gradient
+GEMM, data-gradient GEMM with the previous block's ReLU mask + BatchNorm sums fused into
+its epilogue).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _ops
+
+F32, BF16 = 0, 1
+FPROP, DGRAD = 0, 1
+EPI_BIAS_STATS, EPI_MASK_STATS = 0, 1
+BN_MOMENTUM, BN_EPS = 0.1, 1e-5
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def nhwc_strides(H, W, C):
+    return [H * W * C, W * C, C, 1]
+
+
+def nchw_strides(C, H, W):
+    """(n, h, w, c) strides of an NCHW / channel-major-flattened buffer."""
+    return [C * H * W, W, 1, H * W]
+
+
+def out_hw(transposed, k, s, p, op, h):
+    return (h - 1) * s - 2 * p + k + op if transposed else (h + 2 * p - k) // s + 1
+
+
+class _PackCache:
+    """bf16 packed copies of a weight, keyed by GEMM role; refreshed when the master changes."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def get(self, key, w: torch.Tensor, geom, role, cacheable=True):
+        key = (key, role)
+        ent = self.entries.get(key)
+        ver = w._version
+        if (cacheable and ent is not None and ent[0] == ver and ent[1] == w.data_ptr()
+                and not torch.cuda.is_current_stream_capturing()):
+            return ent[2]
+        packed = _ops.ops().conv_pack_weight(geom, role, w.detach().contiguous())
+        self.entries[key] = (ver, w.data_ptr(), packed)
+        return packed
+
+
+class LayerSpec:
+    __slots__ = ("transposed", "k", "s", "p", "op", "cin", "cout", "hin", "hout", "geom", "conv", "bn")
+
+    def __init__(self, transposed, k, s, p, op, cin, cout, hin, conv, bn):
+        self.transposed, self.k, self.s, self.p, self.op = transposed, k, s, p, op
+        self.cin, self.cout, self.hin = cin, cout, hin
+        self.hout = out_hw(transposed, k, s, p, op, hin)
+        self.geom = [int(transposed), k, s, p, op, cin, cout, hin, hin]
+        self.conv, self.bn = conv, bn  # module names inside the Sequential
+
+
+def linear_geom(k, n):
+    return [0, 1, 1, 0, 0, k, n, 1, 1]
+
+
+def _stats(C, dev):
+    return torch.zeros(2 * C, dtype=torch.float64, device=dev)
+
+
+def _ws(dev):
+    from .latent import _workspace
+    return _workspace(dev, max(_ops.ops().bn_act_workspace_bytes(), 1 << 16))
+
+
+# ======================================================================================
+# encoder: x -> latent parameters [B, 4D]
+# ======================================================================================
+class EncoderFn(torch.autograd.Function):
+    """forward(x, heads_w, heads_b, *[conv_w, conv_b, bn_w, bn_b] per layer) -> lat [B, 4D] fp32"""
+
+    @staticmethod
+    def forward(ctx, eng, x, heads_w, heads_b, *params):
+        ops = _ops.ops()
+        specs = eng.enc_specs
+        B = x.shape[0]
+        dev = x.device
+        x = x.contiguous()
+        need_grad = any(ctx.needs_input_grad)
+        src, src_strides, pre = x, nchw_strides(specs[0].cin, specs[0].hin, specs[0].hin), None
+        saved_raw, saved_pre, saved_stats = [], [], []
+        n = len(specs)
+        for i, sp in enumerate(specs):
+            w, b, gamma, beta = params[4 * i:4 * i + 4]
+            rm, rv = eng.enc_buffers[i]
+            last = i == n - 1
+            H = sp.hout
+            if last:
+                raw = torch.empty(B, sp.cout * H * H, dtype=eng.act_dtype, device=dev)
+                dst_strides = nchw_strides(sp.cout, H, H)
+            else:
+                raw = torch.empty(B, H, H, sp.cout, dtype=eng.act_dtype, device=dev)
+                dst_strides = nhwc_strides(H, H, sp.cout)
+            st = eng.stat_buf(("enc", i), sp.cout, dev) if eng.training else None
+            pw = eng.packs.get(("enc", i), w, sp.geom, FPROP)
+            ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                          pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
+            if eng.training:
+                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(B * H * H), gamma, beta, rm, rv,
+                                                             BN_MOMENTUM, BN_EPS, H * H if last else 1)
+            else:
+                scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, H * H if last else 1)
+            saved_raw.append((raw, dst_strides))
+            saved_pre.append((scale, shift))
+            saved_stats.append((mean, invstd))
+            src, src_strides, pre = raw, dst_strides, (scale, shift)
+        # linear heads on the flattened (channel-major) encoder output
+        K = specs[-1].cout * specs[-1].hout ** 2
+        N = heads_w.shape[0]
+        lat = torch.empty(B, N, dtype=torch.float32, device=dev)
+        hg = linear_geom(K, N)
+        pw = eng.packs.get("heads", heads_w, hg, FPROP, cacheable=False)
+        ops.conv_gemm(hg, FPROP, B, src, [K, 0, 0, 1], pre[0], pre[1], True, pw, heads_b, lat, [N, 0, 0, 1], EPI_BIAS_STATS,
+                      None, [0, 0, 0, 0], None, None, None)
+        if eng.debug is not None:
+            eng.debug["enc_raw"] = [r for r, _ in saved_raw]
+        if need_grad:
+            ctx.eng = eng
+            ctx.saved = (x, saved_raw, saved_pre, saved_stats, heads_w, params)
+        return lat
+
+    @staticmethod
+    def backward(ctx, dlat):
+        ops = _ops.ops()
+        eng = ctx.eng
+        x, saved_raw, saved_pre, saved_stats, heads_w, params = ctx.saved
+        specs = eng.enc_specs
+        if not eng.training:
+            raise RuntimeError("clear_vae_b200: backward through eval-mode BatchNorm is not implemented")
+        B = x.shape[0]
+        dev = x.device
+        n = len(specs)
+        dlat = dlat.contiguous()
+        K = specs[-1].cout * specs[-1].hout ** 2
+        N = heads_w.shape[0]
+        hg = linear_geom(K, N)
+        raw_last, _ = saved_raw[-1]
+        sc_last, sh_last = saved_pre[-1]
+        # heads: weight / bias gradients
+        d_heads_w = torch.zeros_like(heads_w)
+        ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w)
+        d_heads_b = ops.colsum(dlat)
+        # heads: data gradient with the last block's ReLU mask + BatchNorm sums in the epilogue
+        g = torch.empty(B, K, dtype=eng.grad_dtype, device=dev)
+        st = eng.stat_buf(("enc_b", n - 1), K, dev)
+        pw = eng.packs.get("heads", heads_w, hg, DGRAD, cacheable=False)
+        ops.conv_gemm(hg, DGRAD, B, dlat, [N, 0, 0, 1], None, None, False, pw, None, g, [K, 0, 0, 1], EPI_MASK_STATS,
+                      raw_last, [K, 0, 0, 1], sc_last, sh_last, st)
+        grads = [None] * len(params)
+        for i in range(n - 1, -1, -1):
+            sp = specs[i]
+            w, b, gamma, beta = params[4 * i:4 * i + 4]
+            raw, raw_strides = saved_raw[i]
+            mean, invstd = saved_stats[i]
+            H = sp.hout
+            last = i == n - 1
+            group = H * H if last else 1
+            coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, group, float(B * H * H), gamma, mean, invstd)
+            dy = ops.bn_bwd_apply(g, raw, None, coef, sp.cout, group, BF16)
+            dw = torch.zeros_like(w)
+            if i == 0:
+                src, src_strides, pre = x, nchw_strides(sp.cin, sp.hin, sp.hin), None
+            else:
+                src, src_strides = saved_raw[i - 1]
+                pre = saved_pre[i - 1]
+            ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
+                           dy, raw_strides, dw)
+            grads[4 * i], grads[4 * i + 2], grads[4 * i + 3] = dw, dgamma, dbeta
+            # grads[4*i+1] (conv bias) stays None: a bias feeding a train-mode BatchNorm has exactly zero gradient
+            if i > 0:
+                g = torch.empty(B, sp.hin, sp.hin, sp.cin, dtype=eng.grad_dtype, device=dev)
+                st = eng.stat_buf(("enc_b", i - 1), sp.cin, dev)
+                pwd = eng.packs.get(("enc", i), w, sp.geom, DGRAD)
+                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g, nhwc_strides(sp.hin, sp.hin, sp.cin),
+                              EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
+        return (None, None, d_heads_w, d_heads_b, *grads)
+
+
+# ======================================================================================
+# decoder: z -> xhat (NCHW fp32) [+ fused reconstruction term]
+# ======================================================================================
+class DecoderFn(torch.autograd.Function):
+    """forward(z, target|None, fc_w, fc_b, fc_bn_w, fc_bn_b, *[w, b, bn_w, bn_b] per convT) -> (xhat, recon)"""
+
+    @staticmethod
+    def forward(ctx, eng, z, target, fc_w, fc_b, fc_g, fc_beta, *params):
+        ops = _ops.ops()
+        specs = eng.dec_specs
+        B = z.shape[0]
+        dev = z.device
+        z = z.contiguous()
+        need_grad = any(ctx.needs_input_grad)
+        K0, N0 = fc_w.shape[1], fc_w.shape[0]
+        fg = linear_geom(K0, N0)
+        raw_fc = torch.empty(B, N0, dtype=torch.float32, device=dev)
+        st = eng.stat_buf(("dec_fc",), N0, dev) if eng.training else None
+        ops.conv_gemm(fg, FPROP, B, z, [K0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, FPROP), fc_b, raw_fc,
+                      [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
+        rm, rv = eng.dec_fc_buffers
+        if eng.training:
+            sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1)
+        else:
+            sc, sh, mean_fc, inv_fc = eng.eval_affine(fc_g, fc_beta, rm, rv, 1)
+        a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, _DT[eng.act_dtype], None, B, _ws(dev))
+        C0, H0 = specs[0].cin, specs[0].hin
+        src, src_strides, pre = a_fc, nchw_strides(C0, H0, H0), None
+        saved_raw, saved_pre, saved_stats = [], [], []
+        n = len(specs)
+        for j, sp in enumerate(specs):
+            w, b, gamma, beta = params[4 * j:4 * j + 4]
+            rm, rv = eng.dec_buffers[j]
+            last = j == n - 1
+            H = sp.hout
+            if last:
+                raw = torch.empty(B, sp.cout, H, H, dtype=torch.float32, device=dev)
+                dst_strides = nchw_strides(sp.cout, H, H)
+            else:
+                raw = torch.empty(B, H, H, sp.cout, dtype=eng.act_dtype, device=dev)
+                dst_strides = nhwc_strides(H, H, sp.cout)
+            st = eng.stat_buf(("dec", j), sp.cout, dev) if eng.training else None
+            ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                          pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS, None,
+                          [0, 0, 0, 0], None, None, st)
+            if eng.training:
+                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(B * H * H), gamma, beta, rm, rv,
+                                                             BN_MOMENTUM, BN_EPS, 1)
+            else:
+                scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, 1)
+            saved_raw.append((raw, dst_strides))
+            saved_pre.append((scale, shift))
+            saved_stats.append((mean, invstd))
+            src, src_strides, pre = raw, dst_strides, (scale, shift)
+        sp = specs[-1]
+        H = sp.hout
+        xhat, recon = ops.bn_act_fwd(src, pre[0], pre[1], sp.cout, H * H, 2, F32, target, B, _ws(dev))
+        if eng.debug is not None:
+            eng.debug["dec_raw"] = [r for r, _ in saved_raw]
+            eng.debug["fc_raw"], eng.debug["fc_act"] = raw_fc, a_fc
+        if need_grad:
+            ctx.eng = eng
+            ctx.has_target = target is not None
+            ctx.saved = (z, target, fc_w, fc_g, raw_fc, a_fc, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params)
+            ctx.save_for_backward(xhat)
+        return xhat, recon
+
+    @staticmethod
+    def backward(ctx, d_xhat, d_recon):
+        ops = _ops.ops()
+        eng = ctx.eng
+        (z, target, fc_w, fc_g, raw_fc, a_fc, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params) = ctx.saved
+        (xhat,) = ctx.saved_tensors
+        if not eng.training:
+            raise RuntimeError("clear_vae_b200: backward through eval-mode BatchNorm is not implemented")
+        specs = eng.dec_specs
+        B = z.shape[0]
+        dev = z.device
+        n = len(specs)
+        sp = specs[-1]
+        H = sp.hout
+        raw_last, last_strides = saved_raw[-1]
+        st = eng.stat_buf(("dec_b", n - 1), sp.cout, dev)
+        gr = d_recon.contiguous() if (ctx.has_target and d_recon is not None) else None
+        ge = d_xhat.contiguous() if d_xhat is not None else None
+        tgt = target if ctx.has_target else xhat  # without a target the MSE term is absent (gr is None)
+        g = ops.sigmoid_mse_bwd(xhat, tgt, gr, ge, raw_last, sp.cout, H * H, B, st)
+        grads = [None] * len(params)
+        for j in range(n - 1, -1, -1):
+            sp = specs[j]
+            w, b, gamma, beta = params[4 * j:4 * j + 4]
+            raw, raw_strides = saved_raw[j]
+            mean, invstd = saved_stats[j]
+            H = sp.hout
+            last = j == n - 1
+            inner = H * H if last else 1
+            coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(B * H * H), gamma, mean, invstd)
+            dy = ops.bn_bwd_apply(g, raw, None, coef, sp.cout, inner, BF16)
+            dw = torch.zeros_like(w)
+            if j == 0:
+                src, src_strides, pre = a_fc, nchw_strides(sp.cin, sp.hin, sp.hin), None
+            else:
+                src, src_strides = saved_raw[j - 1]
+                pre = saved_pre[j - 1]
+            ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
+                           dy, raw_strides, dw)
+            grads[4 * j], grads[4 * j + 2], grads[4 * j + 3] = dw, dgamma, dbeta
+            pwd = eng.packs.get(("dec", j), w, sp.geom, DGRAD)
+            if j > 0:
+                g = torch.empty(B, sp.hin, sp.hin, sp.cin, dtype=eng.grad_dtype, device=dev)
+                st = eng.stat_buf(("dec_b", j - 1), sp.cin, dev)
+                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g,
+                              nhwc_strides(sp.hin, sp.hin, sp.cin), EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
+            else:
+                # gradient w.r.t. the activated fc output, channel-major like a_fc
+                N0 = fc_w.shape[0]
+                g_a = torch.empty(B, N0, dtype=torch.float32, device=dev)
+                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g_a, src_strides, EPI_BIAS_STATS,
+                              None, [0, 0, 0, 0], None, None, None)
+        # fc block: BatchNorm1d + ReLU backward, then Linear
+        K0, N0 = fc_w.shape[1], fc_w.shape[0]
+        fg = linear_geom(K0, N0)
+        st = eng.stat_buf(("dec_fc_b",), N0, dev)
+        ops.bn_reduce(raw_fc, g_a, a_fc, N0, 1, 1, st)
+        coef, d_fc_g, d_fc_beta = ops.bn_bwd_coef(st, N0, 1, float(B), fc_g, mean_fc, inv_fc)
+        dy_fc = ops.bn_bwd_apply(g_a, raw_fc, a_fc, coef, N0, 1, F32)
+        d_fc_w = torch.zeros_like(fc_w)
+        ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
+        dz = torch.empty(B, K0, dtype=torch.float32, device=dev)
+        ops.conv_gemm(fg, DGRAD, B, dy_fc, [N0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, DGRAD), None, dz,
+                      [K0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
+        return (None, dz, None, d_fc_w, None, d_fc_g, d_fc_beta, *grads)
+
+
+class Engine:
+    """Per-model execution state: layer specs, packed-weight cache, statistic accumulators."""
+
+    def __init__(self, enc_specs, dec_specs, act_dtype=torch.bfloat16):
+        self.enc_specs, self.dec_specs = enc_specs, dec_specs
+        self.act_dtype = act_dtype
+        self.grad_dtype = torch.float32
+        self.packs = _PackCache()
+        self.training = True
+        self.enc_buffers, self.dec_buffers, self.dec_fc_buffers = [], [], None
+        self._stat = {}
+        self.debug = None  # set to a dict to capture raw activations (tests / tools only)
+
+    def stat_buf(self, key, C, dev):
+        k = (key, C, dev)
+        t = self._stat.get(k)
+        if t is None:
+            t = _stats(C, dev)
+            self._stat[k] = t
+        return t
+
+    @staticmethod
+    def eval_affine(gamma, beta, rm, rv, expand):
+        invstd = torch.rsqrt(rv + BN_EPS)
+        scale = gamma * invstd
+        shift = beta - rm * scale
+        if expand > 1:
+            scale = scale.repeat_interleave(expand)
+            shift = shift.repeat_interleave(expand)
+        return scale.contiguous(), shift.contiguous(), rm, invstd

@@ -1,0 +1,181 @@
+"""`VAE` (28x28) and `VAE64` (64x64) with the reference's constructor signatures, attribute
+names and `state_dict()` keys (`code/src/models/vae.py:7-156`), executed by the sm_100a
+engine (`clear_vae_b200.engine`).
+
+The sub-modules (`encoder`, `mu_c`, ..., `decoder`) are ordinary `torch.nn` containers that
+only *hold* parameters / buffers (so checkpoints move both ways and the RNG consumption at
+construction equals the reference's); they are never called.  All arithmetic goes through the
+fused conv / BatchNorm / latent kernels.  There is no CPU execution path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..engine import DecoderFn, EncoderFn, Engine, LayerSpec
+from ..latent import latent_block
+
+__all__ = ["VAE", "VAE64"]
+
+
+def _conv_stack(chans, k, transposed, out_pads=None, final_sigmoid=False, head=()):
+    """Conv/BN/ReLU triplets in the reference's order (module indices matter for state_dict keys)."""
+    mods = list(head)
+    n = len(chans) - 1
+    for i in range(n):
+        if transposed:
+            mods.append(nn.ConvTranspose2d(chans[i], chans[i + 1], k, 2, 1, out_pads[i] if out_pads else 0))
+        else:
+            mods.append(nn.Conv2d(chans[i], chans[i + 1], k, 2, 1))
+        mods.append(nn.BatchNorm2d(chans[i + 1]))
+        mods.append(nn.Sigmoid() if (final_sigmoid and i == n - 1) else nn.ReLU())
+    return mods
+
+
+class VAE(nn.Module):
+    """Weakly-supervised VAE with content / style latent halves (reference vae.py:7-102)."""
+
+    _K, _ENC, _DEC, _UNFLAT, _OUT_PADS, _IMG = 3, (32, 64, 128), (128, 64, 32), (128, 4, 4), (0, 1, 1), 28
+
+    def __init__(self, total_z_dim, in_channel: int = 1, group_mode: str | None = None) -> None:
+        super().__init__()
+        self.mode = group_mode
+        self.z_dim = int(total_z_dim / 2)
+        self.in_channel = in_channel
+        self._build(self._K, self._ENC, self._DEC, self._UNFLAT, self._OUT_PADS, in_channel)
+        self._engine = None
+
+    # -- construction ---------------------------------------------------------------
+    def _build(self, k, enc, dec, unflat, out_pads, in_channel):
+        self.encoder = nn.Sequential(*_conv_stack((in_channel,) + tuple(enc), k, False), nn.Flatten())
+        self.mu_c = nn.Linear(2048, self.z_dim)
+        self.logvar_c = nn.Linear(2048, self.z_dim)
+        self.mu_s = nn.Linear(2048, self.z_dim)
+        self.logvar_s = nn.Linear(2048, self.z_dim)
+        head = (nn.Linear(self.z_dim * 2, 2048), nn.BatchNorm1d(2048), nn.ReLU(), nn.Unflatten(1, unflat))
+        self.decoder = nn.Sequential(*_conv_stack(tuple(dec) + (in_channel,), k, True, out_pads, True, head))
+        self._arch = (k, tuple(enc), tuple(dec), tuple(unflat), tuple(out_pads), self._IMG_FOR(k))
+
+    @staticmethod
+    def _IMG_FOR(k):
+        return 28 if k == 3 else 64
+
+    # -- engine ----------------------------------------------------------------------
+    def _eng(self) -> Engine:
+        if self._engine is None:
+            k, enc, dec, unflat, out_pads, img = self._arch
+            enc_specs, h = [], img
+            chans = (self.in_channel,) + enc
+            for i in range(len(enc)):
+                sp = LayerSpec(False, k, 2, 1, 0, chans[i], chans[i + 1], h, 3 * i, 3 * i + 1)
+                enc_specs.append(sp)
+                h = sp.hout
+            dec_specs, h = [], unflat[1]
+            chans = dec + (self.in_channel,)
+            for i in range(len(dec)):
+                sp = LayerSpec(True, k, 2, 1, out_pads[i], chans[i], chans[i + 1], h, 4 + 3 * i, 5 + 3 * i)
+                dec_specs.append(sp)
+                h = sp.hout
+            self._engine = Engine(enc_specs, dec_specs)
+        e = self._engine
+        e.training = self.training
+        e.enc_buffers = [(self.encoder[s.bn].running_mean, self.encoder[s.bn].running_var) for s in e.enc_specs]
+        e.dec_buffers = [(self.decoder[s.bn].running_mean, self.decoder[s.bn].running_var) for s in e.dec_specs]
+        e.dec_fc_buffers = (self.decoder[1].running_mean, self.decoder[1].running_var)
+        return e
+
+    def _tick(self, bns):
+        if self.training:
+            torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
+
+    def _enc_params(self):
+        out = []
+        for s in self._eng().enc_specs:
+            c, b = self.encoder[s.conv], self.encoder[s.bn]
+            out += [c.weight, c.bias, b.weight, b.bias]
+        return out
+
+    def _dec_params(self):
+        out = []
+        for s in self._eng().dec_specs:
+            c, b = self.decoder[s.conv], self.decoder[s.bn]
+            out += [c.weight, c.bias, b.weight, b.bias]
+        return out
+
+    # -- reference API ---------------------------------------------------------------
+    def encode(self, x):
+        eng = self._eng()
+        heads = (self.mu_c, self.logvar_c, self.mu_s, self.logvar_s)
+        hw = torch.cat([h.weight for h in heads], 0)
+        hb = torch.cat([h.bias for h in heads], 0)
+        lat = EncoderFn.apply(eng, x, hw, hb, *self._enc_params())
+        self._tick([self.encoder[s.bn] for s in eng.enc_specs])
+        D = self.z_dim
+        return tuple(lat[:, i * D:(i + 1) * D].contiguous() for i in range(4))
+
+    def decode(self, z):
+        return self._decode(z, None)[0]
+
+    def _decode(self, z, target):
+        eng = self._eng()
+        fc, bn = self.decoder[0], self.decoder[1]
+        xhat, recon = DecoderFn.apply(eng, z, target, fc.weight, fc.bias, bn.weight, bn.bias, *self._dec_params())
+        self._tick([bn] + [self.decoder[s.bn] for s in eng.dec_specs])
+        return xhat, recon
+
+    def sample(self, mu, logvar):
+        """Reparameterisation (vae.py:56-60); the noise is drawn exactly like the reference
+        (`randn_like` on a tensor of logvar's shape), the arithmetic runs in the latent kernel."""
+        eps = torch.randn_like(logvar)
+        dummy = torch.zeros(mu.shape[0], dtype=torch.int64, device=mu.device)
+        z, _ = latent_block([mu], [logvar], [eps], dummy, snn=[0], ps=[0])
+        return z
+
+    def generate(self, mu_c, logvar_c, mu_s, logvar_s, g_dict: dict | None = None, explicit=False):
+        if g_dict is not None:
+            raise NotImplementedError("group-evidence (ML-VAE / GVAE) sampling is outside the CLEAR-VAE hot path")
+        eps_c = torch.randn_like(logvar_c)  # c first, then s: same Philox consumption as vae.py:70,73
+        eps_s = torch.randn_like(logvar_s)
+        dummy = torch.zeros(mu_c.shape[0], dtype=torch.int64, device=mu_c.device)
+        z, _ = latent_block([mu_c, mu_s], [logvar_c, logvar_s], [eps_c, eps_s], dummy, snn=[0, 0], ps=[0, 0])
+        xhat = self.decode(z)
+        return (xhat, z) if explicit else xhat
+
+    def forward(self, x, label=None, explicit=False) -> tuple:
+        if label is not None:
+            raise NotImplementedError("label-conditioned group evidence (ML-VAE / GVAE) is outside the CLEAR-VAE hot path")
+        mu_c, logvar_c, mu_s, logvar_s = self.encode(x)
+        latent_params = {"mu_c": mu_c, "logvar_c": logvar_c, "mu_s": mu_s, "logvar_s": logvar_s}
+        if explicit:
+            xhat, z = self.generate(mu_c, logvar_c, mu_s, logvar_s, None, True)
+            return xhat, latent_params, z
+        return self.generate(mu_c, logvar_c, mu_s, logvar_s, None, False), latent_params
+
+    # -- fused training-step forward (used by the trainers) ----------------------------
+    def fused_step_forward(self, x, label, *, temperature, snn, ps, sim_fn="cosine", eps=None, dist=None):
+        """encode -> [reparam + KL + SNN terms] -> decode + reconstruction error.
+
+        Returns (xhat, recon, z, scalars, latent_params); `scalars` as in `latent_block`.
+        Equivalent to `forward(x, explicit=True)` followed by `vae_loss` and the
+        `contrastive_loss` calls of the trainers (trainer.py:452-470), with the same
+        random draws.
+        """
+        mu_c, logvar_c, mu_s, logvar_s = self.encode(x)
+        if eps is None:
+            eps = (torch.randn_like(logvar_c), torch.randn_like(logvar_s))
+        z, sc = latent_block([mu_c, mu_s], [logvar_c, logvar_s], list(eps), label, snn=snn, ps=ps, sim_fn=sim_fn,
+                             temperature=temperature, dist=dist)
+        xhat, recon = self._decode(z, x)
+        return xhat, recon, z, sc, {"mu_c": mu_c, "logvar_c": logvar_c, "mu_s": mu_s, "logvar_s": logvar_s}
+
+
+class VAE64(VAE):
+    """64x64 variant (reference vae.py:105-156).  Like the reference it first builds the
+    28x28 layers and then replaces them, which keeps the construction-time RNG stream —
+    and therefore seeded initial weights — identical."""
+
+    def __init__(self, total_z_dim, in_channel: int = 3, group_mode: str | None = None) -> None:
+        super().__init__(total_z_dim, in_channel, group_mode)
+        self.z_dim = int(total_z_dim / 2)
+        self._build(4, (32, 64, 128, 256, 512), (512, 256, 128, 64, 32), (512, 2, 2), (0, 0, 0, 0, 0), in_channel)
+        self._engine = None

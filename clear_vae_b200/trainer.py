@@ -1,0 +1,333 @@
+"""Trainer classes with the reference's names, constructor signatures, `fit` return values and
+hyper-parameter dictionaries (`code/src/trainer.py:22-75, 415-493, 573-709, 781-897`).
+
+The per-batch bodies run the fused sm_100a path:
+  encode (tcgen05 conv stack) -> one latent kernel (reparam + KL + SNN terms) -> decode with the
+  reconstruction error fused into the last elementwise pass -> hand-written backward -> optimiser.
+Scalars are read back once per step and only when a progress bar is shown; the per-step lists
+that `fit` returns are filled from device buffers at the end of the epoch (same values, no
+per-step synchronisation).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.optim.optimizer import Optimizer
+from torch.utils.data import DataLoader
+from tqdm import tqdm
+
+from .latent import S_KL0, S_KL1, S_LOSS0, S_LOSS1, DistSpec
+from .losses import contrastive_loss, vae_loss  # noqa: F401  (re-exported like the reference module)
+from .models.vae import VAE
+
+
+class LogisticAnnealer:
+    """KL weight beta / (1 + exp(-(step - loc) / scale))  (trainer.py:22-38)."""
+
+    def __init__(self, loc, scale, beta) -> None:
+        self.current_step = 0
+        self.loc = loc
+        self.scale = scale
+        self.beta = beta
+
+    def __call__(self, kl_loss) -> torch.Tensor:
+        return kl_loss * self.slope()
+
+    def slope(self) -> float:
+        exponent = -(self.current_step - self.loc) / self.scale
+        return self.beta / (1 + math.exp(exponent))
+
+    def step(self) -> None:
+        self.current_step += 1
+
+
+class Trainer:
+    def __init__(self, model: nn.Module, optimizer: Optimizer, verbose_period: int, device: torch.device, transform=None) -> None:
+        self.model = model
+        self.optimizer = optimizer
+        self.verbose_period = verbose_period
+        self.device = device
+        self.transform = transform
+
+    def fit(self, epochs: int, train_loader: DataLoader, valid_loader: None | DataLoader = None):
+        for epoch in range(epochs):
+            verbose = (epoch % self.verbose_period) == 0
+            self._train(train_loader, verbose, epoch)
+            if valid_loader is not None:
+                self._valid(valid_loader, verbose, epoch)
+
+    def evaluate(self, **kwarg):
+        pass
+
+    def _train(self, **kwarg):
+        pass
+
+    def _valid(self, **kwarg):
+        pass
+
+
+class VAETrainer(Trainer):
+    def _valid(self, dataloader, verbose, epoch_id):
+        if verbose:
+            mig, mse = self.evaluate(dataloader, verbose, epoch_id)
+            print(f"gMIG: {round(mig, 3)}; mse: {round(float(mse), 3)}")
+
+    # ---- shared pieces of the fused step ---------------------------------------------
+    def _batch(self, batch):
+        X, label = batch[0], batch[1].reshape(-1).long()
+        X, label = X.to(self.device, non_blocking=True), label.to(self.device, non_blocking=True)
+        if self.transform:
+            X = self.transform(X)
+        return X, label
+
+    def _weights(self, slope, alpha_c, alpha_s, dev):
+        """grad weights of the packed scalars (kl_c, kl_s, c, s, ...) for autograd.backward."""
+        host = getattr(self, "_w_host", None)
+        if host is None:
+            host = torch.zeros(8, dtype=torch.float32)
+            if torch.cuda.is_available():
+                host = host.pin_memory()
+            self._w_host = host
+        host[S_KL0], host[S_KL1], host[S_LOSS0], host[S_LOSS1] = slope, slope, alpha_c, alpha_s
+        return host.to(dev, non_blocking=True)
+
+    dist: DistSpec | None = None
+
+    def _sync_grads(self, params):
+        """data-parallel gradient averaging (one flat all-reduce); no-op on a single GPU."""
+        d = self.dist
+        if d is None or d.world == 1:
+            return
+        import torch.distributed as td
+        grads = [p.grad for p in params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        td.all_reduce(flat, group=d.group)
+        flat.mul_(1.0 / d.world)
+        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+
+class CLEARVAETrainer(VAETrainer):
+    def __init__(self, model: VAE, optimizer: Optimizer, sim_fn: str, hyperparameter: dict[str, float], verbose_period: int,
+                 device: torch.device, transform=None) -> None:
+        super().__init__(model, optimizer, verbose_period, device, transform)
+        self.sim_fn = sim_fn
+        self.hyperparameter = hyperparameter
+        self.annealer = LogisticAnnealer(loc=hyperparameter["loc"], scale=hyperparameter["scale"], beta=hyperparameter["beta"])
+
+    def train_step(self, X, label, eps=None):
+        """One iteration of the reference loop body (trainer.py:446-484); returns device scalars."""
+        vae, hp = self.model, self.hyperparameter
+        ps, alpha = hp["ps"], hp["alpha"]
+        self.optimizer.zero_grad()
+        xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 1],
+                                                        ps=[False, bool(ps)], sim_fn=self.sim_fn, eps=eps, dist=self.dist)
+        # loss = recon + ann(kl_c) + ann(kl_s) + alpha*c + alpha*s, with s = -s_same when not ps (trainer.py:471-480)
+        w = self._weights(self.annealer.slope(), alpha, alpha if ps else -alpha, X.device)
+        torch.autograd.backward([recon, sc], [torch.ones_like(recon), w])
+        self._sync_grads(list(vae.parameters()))
+        self.optimizer.step()
+        self.annealer.step()
+        return recon, sc
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        vae = self.model
+        vae.train()
+        ps = self.hyperparameter["ps"]
+        with tqdm(dataloader, unit="batch", mininterval=0, disable=not verbose) as bar:
+            bar.set_description(f"Epoch {epoch_id}")
+            for batch in bar:
+                X, label = self._batch(batch)
+                recon, sc = self.train_step(X, label)
+                if verbose:
+                    v = torch.cat([recon.detach().view(1), sc.detach()[:4]]).tolist()  # one read-back per step
+                    bar.set_postfix(recontr_loss=v[0], kl_c=v[1], kl_s=v[2], c_loss=v[3], s_loss=v[4] if ps else -v[4])
+        return
+
+    def evaluate(self, dataloader, verbose, epoch_id):
+        return _evaluate(self, dataloader, verbose, epoch_id, style_term=True)
+
+
+def factor_shuffling(z: torch.Tensor, strategy: str = "permute_1"):
+    """z = (z_c, z_s); 'permute_1' rolls the style half up by one row (trainer.py:573-587)."""
+    z_dim = int(z.shape[1] / 2)
+    z_c, z_s = z[:, :z_dim], z[:, z_dim:]
+    if strategy == "permute_1":
+        return torch.cat([z_c, torch.roll(z_s, -1, 0)], dim=1)
+    if strategy == "full":
+        raise TypeError("'Tensor' object is not callable")  # the reference's 'full' branch calls a tensor (trainer.py:581)
+    raise ValueError("this strategy is not implemented yet")
+
+
+class ClearTCVAETrainer(VAETrainer):
+    def __init__(self, model: VAE, factor_cls: nn.Module, optimizers: dict[str, Optimizer], sim_fn: str,
+                 hyperparameter: dict[str, float], verbose_period: int, device: torch.device, transform=None) -> None:
+        super().__init__(model, optimizers["vae_optim"], verbose_period, device, transform)
+        self.sim_fn = sim_fn
+        self.factor_optimizer = optimizers["factor_optim"]
+        self.factor_cls = factor_cls
+        self.hyperparameter = hyperparameter
+        self.annealer = LogisticAnnealer(loc=hyperparameter["loc"], scale=hyperparameter["scale"], beta=hyperparameter["beta"])
+
+    def fit(self, epochs: int, train_loader: DataLoader, valid_loader: None | DataLoader = None):
+        factor_d_losses = []
+        for epoch in range(epochs):
+            verbose = (epoch % self.verbose_period) == 0
+            self._train(train_loader, verbose, epoch, factor_d_losses)
+            if valid_loader is not None:
+                self._valid(valid_loader, verbose, epoch)
+        return factor_d_losses
+
+    def train_step(self, X, label, eps=None, eps2=None):
+        vae, fc, hp = self.model, self.factor_cls, self.hyperparameter
+        # --- VAE update (trainer.py:654-677)
+        self.optimizer.zero_grad()
+        xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
+                                                        sim_fn=self.sim_fn, eps=eps, dist=self.dist)
+        d_score = fc(z)
+        mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
+        w = self._weights(self.annealer.slope(), hp["alpha"], 0.0, X.device)
+        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), w, torch.full_like(mi, hp["lambda"])])
+        self._sync_grads(list(vae.parameters()))
+        self.optimizer.step()
+        self.annealer.step()
+        # --- density-ratio discriminator update (trainer.py:680-699)
+        with torch.no_grad():
+            _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
+        self.factor_optimizer.zero_grad()
+        d_joint = fc(z2)
+        d_marg = fc(factor_shuffling(z2))
+        factor_loss = F.binary_cross_entropy(torch.cat([d_joint, d_marg], 0),
+                                             torch.cat([torch.ones_like(d_joint), torch.zeros_like(d_marg)], 0))
+        factor_loss.backward()
+        self._sync_grads(list(fc.parameters()))
+        self.factor_optimizer.step()
+        return recon, sc, mi.detach(), factor_loss.detach()
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, factor_d_losses: list):
+        self.model.train()
+        self.factor_cls.train()
+        pending = []
+        with tqdm(dataloader, unit="batch", mininterval=0, disable=not verbose) as bar:
+            bar.set_description(f"Epoch {epoch_id}")
+            for batch in bar:
+                X, label = self._batch(batch)
+                recon, sc, mi, fl = self.train_step(X, label)
+                pending.append(fl)
+                if verbose:
+                    v = torch.cat([fl.view(1), recon.detach().view(1), sc.detach()[:3], mi.view(1)]).tolist()
+                    bar.set_postfix(factor_cls_loss=v[0], recontr_loss=v[1], kl_c=v[2], kl_s=v[3], c_loss=v[4], mi_loss=v[5])
+        if pending:
+            factor_d_losses.extend(torch.stack(pending).tolist())
+
+    def evaluate(self, dataloader, verbose, epoch_id):
+        return _evaluate(self, dataloader, verbose, epoch_id, style_term=False)
+
+
+class ClearMIMVAETrainer(VAETrainer):
+    def __init__(self, model: VAE, mi_estimator: nn.Module, optimizers: dict[str, Optimizer], sim_fn: str,
+                 hyperparameter: dict[str, float], verbose_period: int, device: torch.device, transform=None) -> None:
+        super().__init__(model, optimizers["vae_optim"], verbose_period, device, transform)
+        self.sim_fn = sim_fn
+        self.mi_estimator_optimizer = optimizers["mi_estimator_optim"]
+        self.mi_estimator = mi_estimator
+        self.hyperparameter = hyperparameter
+        self.annealer = LogisticAnnealer(loc=hyperparameter["loc"], scale=hyperparameter["scale"], beta=hyperparameter["beta"])
+
+    def fit(self, epochs: int, train_loader: DataLoader, valid_loader: None | DataLoader = None):
+        mi_losses, mi_learning_losses = [], []
+        for epoch in range(epochs):
+            verbose = (epoch % self.verbose_period) == 0
+            self._train(train_loader, verbose, epoch, mi_losses, mi_learning_losses)
+            if valid_loader is not None:
+                self._valid(valid_loader, verbose, epoch)
+        return mi_losses, mi_learning_losses
+
+    def train_step(self, X, label, eps=None, inner_eps=None, perm=None):
+        vae, est, hp = self.model, self.mi_estimator, self.hyperparameter
+        D = vae.z_dim
+        # --- VAE update (trainer.py:848-871)
+        self.optimizer.zero_grad()
+        xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
+                                                        sim_fn=self.sim_fn, eps=eps, dist=self.dist)
+        zc, zs = z[:, :D], z[:, D:]
+        mi = est(zc, zs, perm) if perm is not None else est(zc, zs)
+        w = self._weights(self.annealer.slope(), hp["alpha"], 0.0, X.device)
+        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), w, torch.full_like(mi, hp["lambda"])])
+        self._sync_grads(list(vae.parameters()))
+        self.optimizer.step()
+        self.annealer.step()
+        # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
+        learn = []
+        for j in range(5):
+            with torch.no_grad():
+                _, _, z2 = vae(X, explicit=True) if inner_eps is None else _forward_with_eps(vae, X, inner_eps[j])
+            ll = est.learning_loss(z2[:, :D], z2[:, D:])
+            self.mi_estimator_optimizer.zero_grad()
+            ll.backward()
+            self._sync_grads(list(est.parameters()))
+            self.mi_estimator_optimizer.step()
+            learn.append(ll.detach())
+        return recon, sc, mi.detach(), torch.stack(learn)
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, mi_losses: list, mi_learning_losses: list):
+        self.model.train()
+        self.mi_estimator.train()
+        p_mi, p_learn = [], []
+        with tqdm(dataloader, unit="batch", mininterval=0, disable=not verbose) as bar:
+            bar.set_description(f"Epoch {epoch_id}")
+            for batch in bar:
+                X, label = self._batch(batch)
+                recon, sc, mi, learn = self.train_step(X, label)
+                p_mi.append(mi)
+                p_learn.append(learn)
+                if verbose:
+                    v = torch.cat([recon.detach().view(1), sc.detach()[:3], mi.view(1)]).tolist()
+                    bar.set_postfix(recontr_loss=v[0], kl_c=v[1], kl_s=v[2], c_loss=v[3], mi_loss=v[4])
+        if p_mi:
+            mi_losses.extend(torch.stack(p_mi).tolist())
+            mi_learning_losses.extend(torch.cat(p_learn).tolist())
+
+    def evaluate(self, dataloader, verbose, epoch_id):
+        return _evaluate(self, dataloader, verbose, epoch_id, style_term=False)
+
+
+def _forward_with_eps(vae, X, eps):
+    """`vae(X, explicit=True)` with injected reparameterisation noise (tests / parity runs)."""
+    xhat, recon, z, sc, lp = vae.fused_step_forward(X, torch.zeros(X.shape[0], dtype=torch.int64, device=X.device),
+                                                    temperature=1.0, snn=[0, 0], ps=[False, False], eps=eps)
+    return xhat, lp, z
+
+
+def _evaluate(tr, dataloader, verbose, epoch_id, style_term):
+    """Eval-mode pass: running-stat BatchNorm, losses accumulated on device, gMIG through the
+    reference's sklearn estimator (trainer.py:495-570, 711-778, 899-965; losses.py:10-16)."""
+    vae = tr.model
+    vae.eval()
+    hp = tr.hyperparameter
+    tot = None
+    labels, lat_c, lat_s = [], [], []
+    n = 0
+    with torch.no_grad():
+        for batch in tqdm(dataloader, disable=not verbose, desc=f"val-epoch {epoch_id}"):
+            X, label = tr._batch(batch)
+            ps = bool(hp.get("ps", False)) if style_term else False
+            xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"],
+                                                            snn=[1, 1 if style_term else 0], ps=[False, ps], sim_fn=tr.sim_fn)
+            vals = torch.cat([recon.view(1), sc[:4]])
+            if style_term and not ps:
+                vals[4] = -vals[4]
+            tot = vals if tot is None else tot + vals
+            labels.append(label)
+            lat_c.append(z[:, :vae.z_dim])
+            lat_s.append(z[:, vae.z_dim:])
+            n += 1
+    from .metrics import mutual_info_gap
+    mig = mutual_info_gap(torch.cat(labels), torch.cat(lat_c), torch.cat(lat_s))
+    t = (tot / n).tolist()
+    if verbose:
+        print("val_recontr_loss={:.3f}, val_kl_c={:.3f}, val_kl_s={:.3f}, val_c_loss={:.3f}".format(*t[:4])
+              + (", val_s_loss={:.3f}".format(t[4]) if style_term else ""))
+    return mig, float(t[0])

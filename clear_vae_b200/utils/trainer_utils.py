@@ -1,0 +1,59 @@
+"""Factories with the reference's names and argument lists
+(`code/src/utils/trainer_utils.py:87-201`): config -> model + Adam optimiser(s) + trainer.
+Modules are constructed in the reference's order (VAE first, then the auxiliary network), so a
+given `torch.manual_seed` yields the reference's initial weights."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..models.mi_estimator import CLUBSample, L1OutUB
+from ..models.vae import VAE, VAE64
+from ..trainer import CLEARVAETrainer, ClearMIMVAETrainer, ClearTCVAETrainer
+
+_ARCHS = {"VAE": VAE, "VAE64": VAE64}
+_ESTIMATORS = {"CLUBSample": CLUBSample, "L1OutUB": L1OutUB}
+
+
+def _arch(name):
+    if name not in _ARCHS:
+        raise NameError(f"name '{name}' is not defined")  # the reference resolves the string with eval()
+    return _ARCHS[name]
+
+
+def get_clearvae_trainer(beta, ps, vae_lr, z_dim, alpha, temperature, device, vae_arch: str = "VAE", in_channel: int = 1,
+                         verbose_period: int = 5):
+    vae = _arch(vae_arch)(total_z_dim=z_dim, in_channel=in_channel).to(device)
+    optimizer = torch.optim.Adam(vae.parameters(), lr=vae_lr)
+    return CLEARVAETrainer(vae, optimizer, sim_fn="cosine",
+                           hyperparameter={"temperature": temperature, "alpha": alpha, "beta": beta, "ps": ps, "loc": 0,
+                                           "scale": 1},
+                           verbose_period=verbose_period, device=device)
+
+
+def get_cleartcvae_trainer(beta, la, vae_lr, factor_cls_lr, z_dim, alpha, temperature, device, vae_arch: str = "VAE",
+                           in_channel: int = 1, verbose_period: int = 5):
+    vae = _arch(vae_arch)(total_z_dim=z_dim, in_channel=in_channel).to(device)
+    factor_cls = nn.Sequential(nn.Linear(z_dim, z_dim), nn.ReLU(), nn.Linear(z_dim, 1), nn.Sigmoid()).to(device)
+    vae_optimizer = torch.optim.Adam(vae.parameters(), lr=vae_lr)
+    factor_optimizer = torch.optim.Adam(factor_cls.parameters(), lr=factor_cls_lr)
+    return ClearTCVAETrainer(vae, factor_cls, optimizers={"vae_optim": vae_optimizer, "factor_optim": factor_optimizer},
+                             sim_fn="cosine",
+                             hyperparameter={"temperature": temperature, "alpha": alpha, "beta": beta, "loc": 0, "scale": 1,
+                                             "lambda": la},
+                             verbose_period=verbose_period, device=device)
+
+
+def get_clearmimvae_trainer(beta, mi_estimator: str, la, vae_lr, mi_estimator_lr, z_dim, alpha, temperature, device,
+                            vae_arch: str = "VAE", in_channel: int = 1, verbose_period: int = 5):
+    vae = _arch(vae_arch)(total_z_dim=z_dim, in_channel=in_channel).to(device)
+    if mi_estimator not in _ESTIMATORS:
+        raise NameError(f"name '{mi_estimator}' is not defined")
+    est = _ESTIMATORS[mi_estimator](x_dim=z_dim // 2, y_dim=z_dim // 2, hidden_size=z_dim).to(device)
+    vae_optimizer = torch.optim.Adam(vae.parameters(), lr=vae_lr)
+    est_optimizer = torch.optim.Adam(est.parameters(), lr=mi_estimator_lr)
+    return ClearMIMVAETrainer(vae, est, optimizers={"vae_optim": vae_optimizer, "mi_estimator_optim": est_optimizer},
+                              sim_fn="cosine",
+                              hyperparameter={"temperature": temperature, "beta": beta, "loc": 0, "scale": 1, "alpha": alpha,
+                                              "lambda": la},
+                              verbose_period=verbose_period, device=device)

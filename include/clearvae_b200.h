@@ -167,6 +167,43 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
                        const clearvae_tensor4* mask_src, const float* mask_scale, const float* mask_shift,
                        double* stats, void* stream);
 
+/* weight gradient of the layer (replaces autograd's conv / conv-transpose / linear wgrad):
+ * dweight (fp32, reference layout, must be zero or hold the value to accumulate into) +=
+ *   sum over pixels of pre(src)[pixel @ tap, cin] * dy[pixel, cout].  `dy` is the gradient
+ *   w.r.t. the layer's raw output, indexed like the forward dst. */
+int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src,
+                        const float* pre_scale, const float* pre_shift, int32_t pre_relu,
+                        const clearvae_tensor4* dy, float* dweight, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Train-mode BatchNorm around the GEMMs (nn.BatchNorm1d/2d at vae.py:17-44,115-154).
+ * Flat tensors; channel(idx) = (idx / inner) % C  (inner = 1 for NHWC, H*W for NCHW).
+ * `stats` is a [2][C*group] double accumulator filled by GEMM epilogues or
+ * clearvae_bn_reduce; finalize / coef consume and clear it.
+ * ------------------------------------------------------------------------- */
+int clearvae_bn_finalize(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                         int32_t expand, float* save_mean, float* save_invstd, void* stream);
+/* mode 0: (sum y, sum y^2); mode 1: (sum g', sum g'*y) with g' = g*[act>0] when act != NULL */
+int clearvae_bn_reduce(const void* y, int32_t y_dtype, const void* g, int32_t g_dtype, const void* act, int32_t act_dtype,
+                       int64_t total, int32_t C, int64_t inner, int32_t mode, double* stats, void* stream);
+size_t clearvae_bn_act_workspace_bytes(void);
+/* out = act(raw*scale[ch]+shift[ch]); act 0 none / 1 relu / 2 sigmoid; with `target`, *sse_out = sum((out-target)^2)/batch */
+int clearvae_bn_act_fwd(const void* raw, int32_t raw_dtype, const float* scale, const float* shift, int64_t total, int32_t C,
+                        int64_t inner, int32_t act, void* out, int32_t out_dtype, const float* target, int64_t batch,
+                        float* sse_out, void* workspace, size_t workspace_bytes, void* stream);
+/* backward of xhat = sigmoid(bn(raw)) under recon = sum((xhat-x)^2)/batch (+ optional external grad on xhat) */
+int clearvae_sigmoid_mse_bwd(const float* xhat, const float* x, const float* grad_recon, const float* grad_ext, const void* raw,
+                             int32_t raw_dtype, int64_t total, int32_t C, int64_t inner, int64_t batch, float* g_pre,
+                             double* stats, void* stream);
+/* coef [3][C]: dy = coef0[ch]*g + coef1[ch]*y + coef2[ch]; also BatchNorm weight / bias gradients */
+int clearvae_bn_bwd_coef(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* save_mean,
+                         const float* save_invstd, float* coef, float* dgamma, float* dbeta, void* stream);
+int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t y_dtype, const void* act, int32_t act_dtype,
+                          const float* coef, int64_t total, int32_t C, int64_t inner, void* dy, int32_t dy_dtype, void* stream);
+/* out[c] = sum_r x[r][c]  (bias gradients of the linear heads) */
+int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

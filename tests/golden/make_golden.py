@@ -64,7 +64,8 @@ def injected(randn_queue=None, perm_queue=None, cuda_identity=False):
 
 
 def npy(t):
-    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    # copy: .numpy() aliases the tensor and parameters are updated in place later
+    return t.detach().cpu().numpy().copy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
 # --------------------------------------------------------------------------

@@ -1,0 +1,73 @@
+"""Shared test helpers (CPU + GPU)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import model_oracle as mo
+from oracle.engine_emulator import Emulator
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_step(tag):
+    g = np.load(os.path.join(GOLDEN, f"step_{tag}.npz"))
+    kind, arch, zdim, cin, B, hw, ncls, seed, est = (str(v) for v in g["meta"])
+    hyper = {str(k): eval(str(v)) for k, v in zip(g["hyper_keys"], g["hyper_vals"])}
+    meta = dict(kind=kind, arch=arch, zdim=int(zdim), cin=int(cin), B=int(B), hw=int(hw), ncls=int(ncls), seed=int(seed),
+                est=None if est == "None" else est)
+    return g, meta, hyper
+
+
+def seeded_model(meta, device="cpu"):
+    """The product module built under the golden's seed == the reference's initial weights
+    (same constructors in the same order; checked against the recorded digests)."""
+    from clear_vae_b200.models.vae import VAE, VAE64
+    torch.manual_seed(meta["seed"])
+    m = (VAE if meta["arch"] == "VAE" else VAE64)(total_z_dim=meta["zdim"], in_channel=meta["cin"])
+    return m.to(device)
+
+
+def digest(t):
+    t = t.detach().double().flatten().cpu()
+    return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+
+
+def state_of(model):
+    return {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+
+
+def sample_of(t, n):
+    f = t.detach().flatten()
+    step = max(1, f.numel() // n)
+    return f[::step][:n].cpu().numpy()
+
+
+def emulated_step(st, meta, hyper, g, round_bf16, slope, device="cpu"):
+    """Engine-emulator forward/backward of the trainer's VAE loss (aux MI/TC terms excluded)."""
+    st = {k: v.to(device) for k, v in st.items()}
+    em = Emulator(st, meta["arch"], meta["cin"], round_bf16=round_bf16)
+    X = torch.tensor(g["X"], device=device)
+    label = torch.tensor(g["label"], device=device)
+    e_c, e_s = torch.tensor(g["eps/0"], device=device), torch.tensor(g["eps/1"], device=device)
+    out = em.forward(X, e_c, e_s, target=X)
+    dgrads, dz = em.backward_decoder(out["tape"], X, 1.0)
+    lat = out["lat"].detach().requires_grad_(True)
+    D = lat.shape[1] // 4
+    mu_c, lv_c, mu_s, lv_s = (lat[:, j * D:(j + 1) * D] for j in range(4))
+    z = torch.cat([mu_c + e_c * torch.exp(0.5 * lv_c), mu_s + e_s * torch.exp(0.5 * lv_s)], 1)
+    kl = lambda m, l: -0.5 * (1 + l - m * m - l.exp()).sum(1).mean()
+    kl_c, kl_s = kl(mu_c, lv_c), kl(mu_s, lv_s)
+    c = mo.contrastive(mu_c, lv_c, label, "cosine", hyper["temperature"])
+    tot = (z * dz).sum() + slope * kl_c + slope * kl_s + hyper["alpha"] * c
+    s = None
+    if meta["kind"] == "clear":
+        ps = hyper["ps"]
+        s = mo.contrastive(mu_s, lv_s, label, "cosine", hyper["temperature"], ps=ps)
+        if not ps:
+            s = -s
+        tot = tot + hyper["alpha"] * s
+    (dlat,) = torch.autograd.grad(tot, lat)
+    egrads = em.backward_encoder(out["tape"], dlat)
+    grads = {**dgrads, **egrads}
+    return dict(xhat=out["xhat"], recon=out["recon"], lat=out["lat"], z=out["z"], kl_c=kl_c, kl_s=kl_s, c=c, s=s, grads=grads)

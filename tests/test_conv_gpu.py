@@ -139,3 +139,33 @@ def test_preop_bf16_io_and_mask_epilogue():
     assert rel_err(gout, g_want) < 2e-5
     assert torch.allclose(st2[:cin].float(), g_want.sum((0, 1, 2)), rtol=1e-3, atol=1e-3)
     assert torch.allclose(st2[cin:].float(), (g_want * raw16.float()).sum((0, 1, 2)), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("transposed,k,op,cin,cout,H,B", [(0, 4, 0, 32, 64, 32, 8), (0, 3, 0, 3, 32, 28, 16), (0, 4, 0, 256, 512, 4, 32),
+                                                           (1, 4, 0, 512, 256, 2, 32), (1, 3, 1, 32, 3, 14, 8), (1, 4, 0, 64, 32, 16, 8),
+                                                           (0, 4, 0, 3, 32, 64, 8), (1, 4, 0, 32, 3, 32, 8)])
+def test_weight_gradient(transposed, k, op, cin, cout, H, B):
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(7 * k + cin + cout + transposed)
+    x = bf(torch.randn(B, cin, H, H, generator=g)).to(DEV)
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    w = torch.randn(*wshape, generator=g).to(DEV).requires_grad_(True)
+    if transposed:
+        y = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=op)
+    else:
+        y = F.conv2d(x, w, None, stride=2, padding=1)
+    Ho = y.shape[-1]
+    dy = bf(torch.randn(B, cout, Ho, Ho, generator=g)).to(DEV)
+    (dw_want,) = torch.autograd.grad(y, w, dy)
+    geom = [transposed, k, 2, 1, op, cin, cout, H, H]
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dw = torch.zeros(*wshape, device=DEV)
+    ops.conv_wgrad(geom, B, xn, nhwc_strides(xn), None, None, False, dyn, nhwc_strides(dyn), dw)
+    assert rel_err(dw, dw_want) < 2e-5, rel_err(dw, dw_want)
+    # strided (NCHW) operands + accumulate-into semantics
+    dw2 = torch.ones(*wshape, device=DEV)
+    ops.conv_wgrad(geom, B, x, [x.stride(0), x.stride(2), x.stride(3), x.stride(1)], None, None, False, dy,
+                   [dy.stride(0), dy.stride(2), dy.stride(3), dy.stride(1)], dw2)
+    assert rel_err(dw2 - 1.0, dw_want) < 5e-5
