@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — CLEAR-VAE training-step throughput on B200 (metric of BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W [--config NAME] [--impl reference]
+
+A "step" = one iteration of the reference trainer's loop body (`_train`, trainer.py:446-492 /
+646-709 / 841-897) on one synthetic batch per GPU: forward, backward, optimiser update(s),
+including the 5 estimator iterations of CLEAR-MIM / the discriminator update of CLEAR-TC.
+Default workload = BASELINE.json configs[1]: CLEAR-MIM-VAE (CLUB-S), Styled-MNIST-shaped
+3x28x28, batch 1024 per GPU (weak scaling).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: kind, arch, total_z, in_ch, image, per-GPU batch, n_classes, hyper-parameters (reference scripts)
+    "clear28": dict(kind="clear", arch="VAE", z=16, cin=3, hw=28, B=128, ncls=10,
+                    hp=dict(beta=1 / 8, ps=True, lr=5e-4, alpha=1e2, temperature=0.1)),
+    "mim_club": dict(kind="mim", est="CLUBSample", arch="VAE", z=16, cin=3, hw=28, B=1024, ncls=10,
+                     hp=dict(beta=1 / 8, lr=5e-4, alpha=1e2, temperature=0.1, la=3, aux_lr=2e-3)),
+    "mim_l1out": dict(kind="mim", est="L1OutUB", arch="VAE", z=16, cin=3, hw=28, B=1024, ncls=10,
+                      hp=dict(beta=1 / 8, lr=5e-4, alpha=1e2, temperature=0.1, la=3, aux_lr=2e-3)),
+    "tc64": dict(kind="tc", arch="VAE64", z=64, cin=3, hw=64, B=512, ncls=4,
+                 hp=dict(beta=1 / 32, lr=3e-5, alpha=1e2, temperature=0.1, la=1, aux_lr=1e-4)),
+    "clear64": dict(kind="clear", arch="VAE64", z=64, cin=3, hw=64, B=128, ncls=7,
+                    hp=dict(beta=1 / 32, ps=True, lr=3e-5, alpha=1e2, temperature=0.1)),
+}
+WORKLOAD_NAMES = {
+    "clear28": "CLEAR-VAE, synthetic Styled-MNIST-shaped 3x28x28, batch 128/GPU (BASELINE configs[0])",
+    "mim_club": "CLEAR-MIM-VAE (CLUB-S), synthetic Styled-MNIST-shaped 3x28x28, batch 1024/GPU (BASELINE configs[1])",
+    "mim_l1out": "CLEAR-MIM-VAE (L1OutUB), synthetic Styled-MNIST-shaped 3x28x28, batch 1024/GPU (BASELINE configs[1])",
+    "tc64": "CLEAR-TC-VAE, synthetic CelebA-shaped 3x64x64, batch 512/GPU (BASELINE configs[2])",
+    "clear64": "CLEAR-VAE, synthetic PACS-shaped 3x64x64, batch 128/GPU (BASELINE configs[3])",
+}
+N_POOL = 16  # distinct input batches rotated through the timed region
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+def layer_flops(arch, cin, zdim, B):
+    D = zdim // 2
+    if arch == "VAE":
+        enc = [(cin, 32, 3, 14), (32, 64, 3, 7), (64, 128, 3, 4)]          # (cin, cout, k, hout)
+        dec = [(128, 64, 3, 4), (64, 32, 3, 7), (32, cin, 3, 14)]          # (cin, cout, k, hin)
+    else:
+        ch = [cin, 32, 64, 128, 256, 512]
+        enc = [(ch[i], ch[i + 1], 4, 64 >> (i + 1)) for i in range(5)]
+        rc = ch[::-1]
+        dec = [(rc[i], rc[i + 1], 4, 2 << i) for i in range(5)]
+    f_enc = [2.0 * B * h * h * co * ci * k * k for (ci, co, k, h) in enc]
+    f_dec = [2.0 * B * h * h * ci * co * k * k for (ci, co, k, h) in dec]
+    f_lin = [2.0 * B * 2048 * 4 * D, 2.0 * B * 2 * D * 2048]
+    fwd = sum(f_enc) + sum(f_dec) + sum(f_lin)
+    dgrad = fwd - f_enc[0]
+    return dict(fwd=fwd, dgrad=dgrad, wgrad=fwd)
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host CPU (oracle port), same config
+# --------------------------------------------------------------------------------------
+def oracle_stepper(cfg, seed=101):
+    import torch
+    from oracle import model_oracle as mo
+    hp = cfg["hp"]
+    B = cfg["B"]
+    st = mo.init_state(cfg["arch"], cfg["z"], cfg["cin"], seed=seed)
+    hyper = dict(temperature=hp["temperature"], alpha=hp["alpha"], beta=hp["beta"], loc=0, scale=1, ps=hp.get("ps"))
+    aux, aux_lr = None, None
+    if cfg["kind"] == "tc":
+        aux, aux_lr = mo.init_factor_state(cfg["z"], seed), hp["aux_lr"]
+        hyper["lambda"] = hp["la"]
+    elif cfg["kind"] == "mim":
+        aux, aux_lr = mo.init_estimator_state(cfg["z"] // 2, cfg["z"] // 2, cfg["z"], seed), hp["aux_lr"]
+        hyper["lambda"] = hp["la"]
+    so = mo.StepOracle(cfg["kind"], st, cfg["arch"], cfg["cin"], hyper, hp["lr"], aux=aux, aux_lr=aux_lr,
+                       estimator=cfg.get("est", "CLUBSample"))
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(B, cfg["cin"], cfg["hw"], cfg["hw"], generator=g)
+    label = torch.randint(0, cfg["ncls"], (B,), generator=g)
+    return lambda: so.step(X, label)
+
+
+def time_cpu(cfg, steps, warmup):
+    import torch
+    if cfg.get("est") == "L1OutUB":
+        note = "closed-form O(B*D) L1OutUB (the reference's own forward is CUDA-only: mi_estimator.py:185)"
+    else:
+        note = "same step as the GPU arm"
+    step = oracle_stepper(cfg)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return cfg["B"] / dt, dt * 1e3, torch.get_num_threads(), note
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    sps, ms, cores, note = time_cpu(cfg, steps, warm)
+    sample = f"{steps} full steps of batch {cfg['B']} after {warm} warm-up ({note})"
+    line = dict(impl="reference", metric="train samples/sec", value=sps, unit="samples/s", n_gpus=args.gpus, steps=steps,
+                warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload=WORKLOAD_NAMES[args.config], device="host CPU", threads=cores),
+                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], None, set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx = float(c[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def build_trainer(cfg, device):
+    import torch
+    from clear_vae_b200.utils.trainer_utils import get_clearmimvae_trainer, get_cleartcvae_trainer, get_clearvae_trainer
+    hp = cfg["hp"]
+    torch.manual_seed(101)  # the reference scripts' default seed (run_mig_expr_mnist.py:35)
+    if cfg["kind"] == "clear":
+        return get_clearvae_trainer(hp["beta"], hp["ps"], hp["lr"], cfg["z"], hp["alpha"], hp["temperature"], device, cfg["arch"], cfg["cin"])
+    if cfg["kind"] == "tc":
+        return get_cleartcvae_trainer(hp["beta"], hp["la"], hp["lr"], hp["aux_lr"], cfg["z"], hp["alpha"], hp["temperature"], device,
+                                      cfg["arch"], cfg["cin"])
+    return get_clearmimvae_trainer(hp["beta"], cfg["est"], hp["la"], hp["lr"], hp["aux_lr"], cfg["z"], hp["alpha"], hp["temperature"],
+                                   device, cfg["arch"], cfg["cin"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="mim_club", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as td
+    from clear_vae_b200 import _ops
+    from clear_vae_b200.latent import DistSpec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    _ops.load()
+    cfg = CONFIGS[args.config]
+    B, K, W = cfg["B"], args.steps, max(3, args.warmup)
+    tr = build_trainer(cfg, dev)
+    if world > 1:
+        tr.dist = DistSpec(td.group.WORLD, rank, world)
+        for p in list(tr.model.parameters()):  # identical replicas
+            td.broadcast(p.data, 0)
+    tr.model.train()
+
+    g = torch.Generator().manual_seed(101 + rank)
+    pool_h = [(torch.rand(B, cfg["cin"], cfg["hw"], cfg["hw"], generator=g).pin_memory(),
+               torch.randint(0, cfg["ncls"], (B,), generator=g).pin_memory()) for _ in range(N_POOL)]
+    pool_d = [(x.to(dev), y.to(dev)) for x, y in pool_h]
+
+    def step_dev(i):
+        x, y = pool_d[i % N_POOL]
+        return tr.train_step(x, y)
+
+    def step_e2e(i):
+        xh, yh = pool_h[i % N_POOL]
+        x, y = xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)
+        out = tr.train_step(x, y)
+        vals = torch.cat([out[0].detach().view(1), out[1].detach().view(-1)]).to("cpu")  # the step's scalars, one read-back
+        return vals
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also fills the packed-weight caches / cuBLAS handles)
+    for i in range(W):
+        step_dev(i)
+    barrier()
+
+    # ---- one profiling pass: which of OUR kernels dominates the step?
+    meter = _ops.meter
+    meter.reset()
+    meter.timed = {"conv_gemm", "conv_wgrad", "latent_fwd", "latent_bwd", "bn_finalize", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd",
+                   "bn_reduce", "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize"}
+    for i in range(2):
+        step_dev(i)
+    torch.cuda.synchronize()
+    prof = meter.elapsed_ms()
+    launches_per_step = meter.launches() // 2
+    dominant = max(prof, key=lambda k: prof[k][1]) if prof else None
+    breakdown = {k: round(v[1] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    meter.reset()
+    meter.timed = {dominant} if dominant else set()
+
+    # ---- timed region: device-resident inputs
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step_dev(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    clocks = sampler.stop()
+    dom = meter.elapsed_ms().get(dominant, (0, 0.0))
+    launches = meter.launches()
+    meter.timed = set()
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the step's scalars
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        vals = step_e2e(i)
+    t1.record()
+    barrier()
+    ms_e2e = max(t0.elapsed_time(t1), (time.perf_counter() - wall0) * 1e3) / K
+    h2d = pool_h[0][0].numel() * 4 + pool_h[0][1].numel() * 8
+    d2h = vals.numel() * 4
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel (algorithmic flops from the layer geometry)
+    pk = peaks()
+    fl = layer_flops(cfg["arch"], cfg["cin"], cfg["z"], B)
+    n_fwd = {"clear": 1, "tc": 2, "mim": 6}[cfg["kind"]]
+    alg = {"conv_gemm": n_fwd * fl["fwd"] + fl["dgrad"], "conv_wgrad": fl["wgrad"]}
+    roof = None
+    if dominant in alg and dom[0] > 0:
+        per_step_ms = dom[1] / K
+        ach = alg[dominant] / (per_step_ms * 1e-3) / 1e12
+        roof = dict(kernel=dominant, bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=None,
+                    launches_per_step=dom[0] // K, ms_per_step=per_step_ms, peak_source=pk["src"] + " bf16 sustained",
+                    algorithmic_gflop_per_step=alg[dominant] / 1e9)
+    elif dominant is not None and dom[0] > 0:
+        roof = dict(kernel=dominant, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None,
+                    launches_per_step=dom[0] // K, ms_per_step=dom[1] / K, peak_source=pk["src"])
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            csteps = 10
+            sps, cms, cores, note = time_cpu(cfg, csteps, 2)
+            cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                       sample=f"{csteps} full steps of batch {B} after 2 warm-up on the host ({note}); {cms:.0f} ms/step")
+        line = dict(metric="train samples/sec", value=world * B / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload=WORKLOAD_NAMES[args.config], per_gpu_batch=B, global_batch=world * B,
+                                parallelism=f"dp{world}", l2=f"rotating {N_POOL} distinct input batches "
+                                f"({N_POOL * h2d / 1e6:.0f} MB) > 126 MB L2; activations are rewritten every step",
+                                bn="per-GPU batch statistics", conv_math="bf16 operands, fp32 accumulate (tcgen05)",
+                                latent_math="fp32"),
+                    clocks=clocks,
+                    e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=ms_e2e),
+                    gpu_launches=launches, gpu_launches_per_step=launches_per_step, kernel_ms_per_step=breakdown,
+                    roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

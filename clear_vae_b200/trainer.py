@@ -21,6 +21,7 @@ from tqdm import tqdm
 
 from .latent import S_KL0, S_KL1, S_LOSS0, S_LOSS1, DistSpec
 from .losses import contrastive_loss, vae_loss  # noqa: F401  (re-exported like the reference module)
+from .models.mi_estimator import CLUBSample
 from .models.vae import VAE
 
 
@@ -253,7 +254,7 @@ class ClearMIMVAETrainer(VAETrainer):
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
                                                         sim_fn=self.sim_fn, eps=eps, dist=self.dist)
         zc, zs = z[:, :D], z[:, D:]
-        mi = est(zc, zs, perm) if perm is not None else est(zc, zs)
+        mi = est(zc, zs, perm) if (perm is not None and isinstance(est, CLUBSample)) else est(zc, zs)
         w = self._weights(self.annealer.slope(), hp["alpha"], 0.0, X.device)
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), w, torch.full_like(mi, hp["lambda"])])
         self._sync_grads(list(vae.parameters()))
