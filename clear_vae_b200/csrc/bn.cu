@@ -37,7 +37,7 @@ inline int grid_for(long long n, int per_thread = 4) {
 // ---------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(double* stats, int C, int group, double count, const float* gamma, const float* beta,
                                    float* running_mean, float* running_var, float momentum, float eps, float* scale,
-                                   float* shift, int expand, float* save_mean, float* save_invstd) {
+                                   float* shift, int expand, float* save_mean, float* save_invstd, int repeat) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int Cs = C * group;
@@ -59,8 +59,13 @@ __global__ void bn_finalize_kernel(double* stats, int C, int group, double count
   save_invstd[c] = invstd;
   if (running_mean) {
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    float rm = running_mean[c], rv = running_var[c];
+    for (int i = 0; i < repeat; ++i) {  // `repeat` identical forwards (CLEAR-MIM inner loop) = repeated momentum updates
+      rm = (1.f - momentum) * rm + momentum * (float)mean;
+      rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
   }
 }
 
@@ -68,19 +73,52 @@ __global__ void bn_finalize_kernel(double* stats, int C, int group, double count
 // generic two-moment reduction over a flat tensor, channel(idx) = (idx / inner) % C.
 //   mode 0: (sum y, sum y^2)
 //   mode 1: g' = g * [act > 0] (act optional), (sum g', sum g'*y)
-// one CTA handles a contiguous slab of rows so per-thread channels stay fixed when inner == 1
 // ---------------------------------------------------------------------------
+// position owned by this thread inside one sample's [C * inner] period; `blocked` mapping gives every
+// thread of a CTA the same channel (one atomic pair per CTA instead of one per thread)
+__device__ __forceinline__ long long reduce_pos(int C, long long inner, int blocked, int* chan) {
+  if (blocked) {
+    const int chunks = (int)((inner + kNT - 1) / kNT);
+    const int c = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const long long i = (long long)chunk * kNT + threadIdx.x;
+    *chan = c;
+    return i < inner ? c * inner + i : -1;
+  }
+  const long long pos = (long long)blockIdx.x * kNT + threadIdx.x;
+  *chan = (int)(pos / inner);
+  return pos < (long long)C * inner ? pos : -1;
+}
+__device__ __forceinline__ void reduce_commit(double d0, double d1, int c, int C, int blocked, double* stats) {
+  if (blocked) {
+    __shared__ double sh[2][kNT / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = d0; sh[1][threadIdx.x >> 5] = d1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int i = 0; i < kNT / 32; ++i) { a += sh[0][i]; b += sh[1][i]; }
+      atomicAdd(stats + c, a);
+      atomicAdd(stats + C + c, b);
+    }
+  } else if (c < C) {
+    atomicAdd(stats + c, d0);
+    atomicAdd(stats + C + c, d1);
+  }
+}
+
 __global__ void __launch_bounds__(kNT) bn_reduce_kernel(const void* y, int y_bf, const void* g, int g_bf, const void* act,
-                                                        int act_bf, long long total, int C, long long inner, int mode,
-                                                        double* stats) {
-  // thread-private accumulation is only valid when a thread always sees the same channel:
-  // stride through the tensor in steps of C*inner*k. Fall back to atomics per element group otherwise.
+                                                        int act_bf, const float* __restrict__ mscale,
+                                                        const float* __restrict__ mshift, long long total, int C,
+                                                        long long inner, int mode, int blocked, double* stats) {
   const long long period = (long long)C * inner;
   const long long nper = total / period;  // samples
-  // each thread owns positions pos in [0, period) with pos = tid + j*stride, loops over samples
-  for (long long pos = (long long)blockIdx.x * kNT + threadIdx.x; pos < period; pos += (long long)gridDim.x * kNT) {
+  int c;
+  const long long pos = reduce_pos(C, inner, blocked, &c);
+  double d0 = 0.0, d1 = 0.0;
+  if (pos >= 0) {
     float s0 = 0.f, s1 = 0.f;
-    double d0 = 0.0, d1 = 0.0;
     int cnt = 0;
     for (long long smp = blockIdx.y; smp < nper; smp += gridDim.y) {
       const long long i = smp * period + pos;
@@ -90,15 +128,14 @@ __global__ void __launch_bounds__(kNT) bn_reduce_kernel(const void* y, int y_bf,
       } else {
         float gv = ldf(g, i, g_bf);
         if (act != nullptr && !(ldf(act, i, act_bf) > 0.f)) gv = 0.f;
+        if (mscale != nullptr && !(fmaf(yv, __ldg(mscale + c), __ldg(mshift + c)) > 0.f)) gv = 0.f;
         s0 += gv; s1 = fmaf(gv, yv, s1);
       }
       if (++cnt == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }
     }
     d0 += s0; d1 += s1;
-    const int c = (int)(pos / inner);
-    atomicAdd(stats + c, d0);
-    atomicAdd(stats + C + c, d1);
   }
+  reduce_commit(d0, d1, c, C, blocked, stats);
 }
 
 // ---------------------------------------------------------------------------
@@ -107,7 +144,7 @@ __global__ void __launch_bounds__(kNT) bn_reduce_kernel(const void* y, int y_bf,
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNT) bn_act_fwd_kernel(const void* raw, int raw_bf, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, long long total, int C,
-                                                         long long inner, int act, void* out, int out_bf,
+                                                         long long inner, int act, int tC, int tHW, void* out, int out_bf,
                                                          const float* __restrict__ target, float invB, float* sse_out,
                                                          float* partial, unsigned* ticket) {
   __shared__ float sred[kNT / 32 + 1];
@@ -117,7 +154,13 @@ __global__ void __launch_bounds__(kNT) bn_act_fwd_kernel(const void* raw, int ra
     float v = fmaf(ldf(raw, i, raw_bf), __ldg(scale + ch), __ldg(shift + ch));
     if (act == 1) v = fmaxf(v, 0.f);
     else if (act == 2) v = 1.f / (1.f + __expf(-v));
-    stf(out, i, out_bf, v);
+    long long o = i;
+    if (tC > 0) {  // channel-major [b][c][hw] -> channels-last [b][hw][c]
+      const long long per = (long long)tC * tHW, b = i / per, r = i - b * per;
+      const int c2 = (int)(r / tHW), hw = (int)(r - (long long)c2 * tHW);
+      o = b * per + (long long)hw * tC + c2;
+    }
+    stf(out, o, out_bf, v);
     if (target != nullptr) { const float d = v - __ldg(target + i); acc = fmaf(d, d, acc); }
   }
   if (target == nullptr) return;
@@ -146,12 +189,14 @@ __global__ void __launch_bounds__(kNT) sigmoid_mse_bwd_kernel(const float* __res
                                                               const float* __restrict__ grad_recon,
                                                               const float* __restrict__ grad_ext, const void* raw, int raw_bf,
                                                               long long total, int C, long long inner, float twoInvB,
-                                                              float* __restrict__ g_pre, double* stats) {
+                                                              int blocked, float* __restrict__ g_pre, double* stats) {
   const float gr = grad_recon ? __ldg(grad_recon) * twoInvB : 0.f;
   const long long period = (long long)C * inner;
   const long long nper = total / period;
-  for (long long pos = (long long)blockIdx.x * kNT + threadIdx.x; pos < period; pos += (long long)gridDim.x * kNT) {
-    double d0 = 0.0, d1 = 0.0;
+  int c;
+  const long long pos = reduce_pos(C, inner, blocked, &c);
+  double d0 = 0.0, d1 = 0.0;
+  if (pos >= 0) {
     float s0 = 0.f, s1 = 0.f;
     int cnt = 0;
     for (long long smp = blockIdx.y; smp < nper; smp += gridDim.y) {
@@ -165,10 +210,8 @@ __global__ void __launch_bounds__(kNT) sigmoid_mse_bwd_kernel(const float* __res
       if (++cnt == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }
     }
     d0 += s0; d1 += s1;
-    const int c = (int)(pos / inner);
-    atomicAdd(stats + c, d0);
-    atomicAdd(stats + C + c, d1);
   }
+  reduce_commit(d0, d1, c, C, blocked, stats);
 }
 
 // ---------------------------------------------------------------------------
@@ -200,13 +243,16 @@ __global__ void bn_bwd_coef_kernel(double* stats, int C, int group, double count
 
 // dy = a[ch] * g' + b[ch] * y + c[ch],  g' = g * [act > 0] when act is given
 __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_bf, const void* y, int y_bf, const void* act,
-                                                           int act_bf, const float* __restrict__ coef, long long total, int C,
-                                                           long long inner, void* dy, int dy_bf) {
+                                                           int act_bf, const float* __restrict__ mscale,
+                                                           const float* __restrict__ mshift, const float* __restrict__ coef,
+                                                           long long total, int C, long long inner, void* dy, int dy_bf) {
   for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < total; i += (long long)gridDim.x * kNT) {
     const int ch = (int)((i / inner) % C);
     float gv = ldf(g, i, g_bf);
+    const float yv = ldf(y, i, y_bf);
     if (act != nullptr && !(ldf(act, i, act_bf) > 0.f)) gv = 0.f;
-    const float v = fmaf(__ldg(coef + ch), gv, fmaf(__ldg(coef + C + ch), ldf(y, i, y_bf), __ldg(coef + 2 * C + ch)));
+    if (mscale != nullptr && !(fmaf(yv, __ldg(mscale + ch), __ldg(mshift + ch)) > 0.f)) gv = 0.f;
+    const float v = fmaf(__ldg(coef + ch), gv, fmaf(__ldg(coef + C + ch), yv, __ldg(coef + 2 * C + ch)));
     stf(dy, i, dy_bf, v);
   }
 }
@@ -220,34 +266,44 @@ __global__ void __launch_bounds__(kNT) colsum_kernel(const float* __restrict__ x
   }
 }
 
+
+// grid for the two-moment reductions: channel-blocked mapping when a channel spans >= 64 positions
+inline void reduce_grid(int C, long long inner, long long nper, dim3* grid, int* blocked) {
+  const long long period = (long long)C * inner;
+  long long gx;
+  if (inner >= 64) { *blocked = 1; gx = (long long)C * ((inner + kNT - 1) / kNT); }
+  else { *blocked = 0; gx = (period + kNT - 1) / kNT; }
+  long long gy = (148 * 4 + gx - 1) / gx;
+  if (gy > nper) gy = nper;
+  if (gy < 1) gy = 1;
+  *grid = dim3((unsigned)gx, (unsigned)gy);
+}
 }  // namespace
 
 extern "C" {
 
 int clearvae_bn_finalize(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
-                         int32_t expand, float* save_mean, float* save_invstd, void* stream) {
-  if (!stats || !scale || !shift || !save_mean || !save_invstd || C <= 0 || group <= 0 || expand <= 0 || count <= 0) return CLEARVAE_EINVAL;
+                         int32_t expand, float* save_mean, float* save_invstd, int32_t repeat, void* stream) {
+  if (!stats || !scale || !shift || !save_mean || !save_invstd || C <= 0 || group <= 0 || expand <= 0 || count <= 0 || repeat < 1) return CLEARVAE_EINVAL;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, C, group, count, gamma, beta, running_mean,
                                                                          running_var, momentum, eps, scale, shift, expand,
-                                                                         save_mean, save_invstd);
+                                                                         save_mean, save_invstd, repeat);
   CV_LAUNCH_CHECK();
   return 0;
 }
 
 int clearvae_bn_reduce(const void* y, int32_t y_dtype, const void* g, int32_t g_dtype, const void* act, int32_t act_dtype,
-                       int64_t total, int32_t C, int64_t inner, int32_t mode, double* stats, void* stream) {
+                       const float* mask_scale, const float* mask_shift, int64_t total, int32_t C, int64_t inner, int32_t mode,
+                       double* stats, void* stream) {
   if (!y || !stats || total <= 0 || C <= 0 || inner <= 0 || (mode == 1 && !g)) return CLEARVAE_EINVAL;
   const long long period = (long long)C * inner;
   if (total % period) return CLEARVAE_EINVAL;
-  const long long nper = total / period;
-  int gx = (int)((period + kNT - 1) / kNT);
-  if (gx > 148 * 4) gx = 148 * 4;
-  long long gy = (148 * 8 + gx - 1) / gx;
-  if (gy > nper) gy = nper;
-  if (gy < 1) gy = 1;
-  bn_reduce_kernel<<<dim3(gx, (unsigned)gy), kNT, 0, (cudaStream_t)stream>>>(y, y_dtype, g, g_dtype, act, act_dtype, total, C,
-                                                                             inner, mode, stats);
+  dim3 grid;
+  int blocked;
+  reduce_grid(C, inner, total / period, &grid, &blocked);
+  bn_reduce_kernel<<<grid, kNT, 0, (cudaStream_t)stream>>>(y, y_dtype, g, g_dtype, act, act_dtype, mask_scale, mask_shift, total, C,
+                                                           inner, mode, blocked, stats);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -255,7 +311,8 @@ int clearvae_bn_reduce(const void* y, int32_t y_dtype, const void* g, int32_t g_
 size_t clearvae_bn_act_workspace_bytes(void) { return 256 + 148 * 8 * sizeof(float); }
 
 int clearvae_bn_act_fwd(const void* raw, int32_t raw_dtype, const float* scale, const float* shift, int64_t total, int32_t C,
-                        int64_t inner, int32_t act, void* out, int32_t out_dtype, const float* target, int64_t batch,
+                        int64_t inner, int32_t act, int32_t to_nhwc_C, int32_t to_nhwc_HW, void* out, int32_t out_dtype,
+                        const float* target, int64_t batch,
                         float* sse_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!raw || !scale || !shift || !out || total <= 0 || C <= 0 || inner <= 0) return CLEARVAE_EINVAL;
   unsigned* ticket = nullptr;
@@ -266,8 +323,8 @@ int clearvae_bn_act_fwd(const void* raw, int32_t raw_dtype, const float* scale, 
     ticket = reinterpret_cast<unsigned*>(workspace);
     partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   }
-  bn_act_fwd_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(raw, raw_dtype, scale, shift, total, C, inner, act, out,
-                                                                       out_dtype, target, target ? 1.f / (float)batch : 0.f,
+  bn_act_fwd_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(raw, raw_dtype, scale, shift, total, C, inner, act, to_nhwc_C,
+                                                                       to_nhwc_HW, out, out_dtype, target, target ? 1.f / (float)batch : 0.f,
                                                                        sse_out, partial, ticket);
   CV_LAUNCH_CHECK();
   return 0;
@@ -279,14 +336,11 @@ int clearvae_sigmoid_mse_bwd(const float* xhat, const float* x, const float* gra
   if (!xhat || !x || !raw || !g_pre || !stats || total <= 0 || C <= 0 || inner <= 0 || batch <= 0) return CLEARVAE_EINVAL;
   const long long period = (long long)C * inner;
   if (total % period) return CLEARVAE_EINVAL;
-  const long long nper = total / period;
-  int gx = (int)((period + kNT - 1) / kNT);
-  if (gx > 148 * 4) gx = 148 * 4;
-  long long gy = (148 * 8 + gx - 1) / gx;
-  if (gy > nper) gy = nper;
-  if (gy < 1) gy = 1;
-  sigmoid_mse_bwd_kernel<<<dim3(gx, (unsigned)gy), kNT, 0, (cudaStream_t)stream>>>(xhat, x, grad_recon, grad_ext, raw, raw_dtype,
-                                                                                   total, C, inner, 2.f / (float)batch, g_pre, stats);
+  dim3 grid;
+  int blocked;
+  reduce_grid(C, inner, total / period, &grid, &blocked);
+  sigmoid_mse_bwd_kernel<<<grid, kNT, 0, (cudaStream_t)stream>>>(xhat, x, grad_recon, grad_ext, raw, raw_dtype, total, C, inner,
+                                                                 2.f / (float)batch, blocked, g_pre, stats);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -301,10 +355,11 @@ int clearvae_bn_bwd_coef(double* stats, int32_t C, int32_t group, double count, 
 }
 
 int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t y_dtype, const void* act, int32_t act_dtype,
-                          const float* coef, int64_t total, int32_t C, int64_t inner, void* dy, int32_t dy_dtype, void* stream) {
+                          const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
+                          int64_t inner, void* dy, int32_t dy_dtype, void* stream) {
   if (!g || !y || !coef || !dy || total <= 0 || C <= 0 || inner <= 0) return CLEARVAE_EINVAL;
-  bn_bwd_apply_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(g, g_dtype, y, y_dtype, act, act_dtype, coef, total, C,
-                                                                         inner, dy, dy_dtype);
+  bn_bwd_apply_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(g, g_dtype, y, y_dtype, act, act_dtype, mask_scale,
+                                                                         mask_shift, coef, total, C, inner, dy, dy_dtype);
   CV_LAUNCH_CHECK();
   return 0;
 }

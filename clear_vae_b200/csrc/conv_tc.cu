@@ -48,6 +48,7 @@ struct GemmParams {
   const void* msk; long long m_n, m_h, m_w, m_c; int msk_bf16;
   const float *msk_scale, *msk_shift;
   double* stats;
+  int splits;  // split-K over grid.z (fp32 atomic epilogue); 1 = off
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -88,12 +89,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   uint64_t* tmem_full = empty + NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-  const Cls& c = p.plan.cls[blockIdx.z];
+  const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const Cls& c = p.plan.cls[cls_id];
   const long long Mc = p.batch * c.Hd * c.Wd;
   const long long m0 = (long long)blockIdx.x * BM;
   if (m0 >= Mc) return;
   const int n0 = blockIdx.y * BN;
-  const int nkb = c.Kp / BK;
+  const int nkb_all = c.Kp / BK;
+  const int kb0 = nkb_all * split / p.splits;
+  const int nkb = nkb_all * (split + 1) / p.splits - kb0;
+  if (nkb <= 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 4) {
-    if (lane == 0) prefetch_tmap(&tm.t[blockIdx.z]);
+    if (lane == 0) prefetch_tmap(&tm.t[cls_id]);
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -125,14 +130,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int Cs = p.plan.Cs, Kreal = c.ntaps * Cs;
     const bool vec = (Cs % 8 == 0) && p.s_c == 1;
     const long long img_off = img * p.s_n;
-    int t_cur = 0, c_cur = 0;  // incremental (tap, channel) of the next 8-chunk (vector path)
+    // incremental (tap, channel) of the next 8-chunk (vector path)
+    int t_cur = vec ? (kb0 * BK) / Cs : 0, c_cur = vec ? (kb0 * BK) % Cs : 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % NS;
       mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
       unsigned char* a_st = sA + s * kAStage;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int kg = kb * BK + j * 8;
+        const int kg = (kb0 + kb) * BK + j * 8;
         uint4 out = make_uint4(0u, 0u, 0u, 0u);
         if (vec) {
           if (kg < Kreal && mvalid) {
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         float second = 0.f;
         const bool live = mvalid && i < CH && n < Nn;
         if (p.epi == CLEARVAE_EPI_BIAS_STATS) {
-          if (live && p.bias != nullptr) a += __ldg(p.bias + n);
+          if (live && p.bias != nullptr && split == 0) a += __ldg(p.bias + n);
           if (!live) a = 0.f;
           second = a * a;
         } else {
@@ -237,7 +243,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         u[i] = second;
       }
       // ---- store (vectorised when channels are the innermost dst dimension)
-      if (mvalid) {
+      if (mvalid && p.splits > 1) {
+        float* d = reinterpret_cast<float*>(p.dst) + dst_off;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int n = n0 + ch0 + i;
+          if (n < Nn) atomicAdd(d + n * p.d_c, v[i]);
+        }
+      } else if (mvalid) {
         if (p.d_c == 1 && n0 + ch0 + CH <= Nn && (CH % 8) == 0) {
           if (p.dst_bf16) {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + n0 + ch0;
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         const int s = kb % NS;
         mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], kBStage);
-        tma_load_2d(sB + s * kBStage, &tm.t[blockIdx.z], &full[s], kb * BK, n0);
+        tma_load_2d(sB + s * kBStage, &tm.t[cls_id], &full[s], (kb0 + kb) * BK, n0);
       }
     }
   } else {
@@ -695,8 +708,24 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   if (mask_src) fill_t4(mask_src, p.msk, p.m_n, p.m_h, p.m_w, p.m_c, p.msk_bf16);
   p.msk_scale = mask_scale; p.msk_shift = mask_shift;
   p.stats = stats;
-  dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)((n_pad + BN - 1) / BN), (unsigned)p.plan.n_classes);
+  p.splits = 1;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // skinny-M / deep-K linear layers (the latent heads, the fc data-gradient): split K across CTAs so the
+    // GPU is filled; partial sums meet in fp32 atomics on a zeroed destination
+    const long long ctas = ((max_m + BM - 1) / BM) * ((n_pad + BN - 1) / BN) * p.plan.n_classes;
+    const int nkb = p.plan.cls[0].Kp / BK;
+    const bool dense_dst = !p.dst_bf16 && p.d_c == 1 && p.d_n == p.plan.Nn && g->k == 1 && g->Hin == 1 && g->Win == 1;
+    if (dense_dst && stats == nullptr && epilogue == CLEARVAE_EPI_BIAS_STATS && nkb >= 8 && ctas * 2 <= 148) {
+      int sp = (int)std::min<long long>(nkb / 2, 148 / ctas);
+      if (sp > 1) {
+        p.splits = sp;
+        cudaError_t e = cudaMemsetAsync(p.dst, 0, (size_t)batch * p.plan.Nn * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+      }
+    }
+  }
+  dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)((n_pad + BN - 1) / BN), (unsigned)(p.plan.n_classes * p.splits));
   switch (BN) {
     case 16: return launch<16>(tm, p, grid, st);
     case 32: return launch<32>(tm, p, grid, st);

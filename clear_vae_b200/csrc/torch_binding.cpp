@@ -297,7 +297,7 @@ float* optf_mut(const OptTensor& t, const char* name) { return const_cast<float*
 
 std::tuple<Tensor, Tensor, Tensor, Tensor> bn_finalize(Tensor stats, int64_t C, int64_t group, double count, const OptTensor& gamma,
                                                        const OptTensor& beta, const OptTensor& running_mean,
-                                                       const OptTensor& running_var, double momentum, double eps, int64_t expand) {
+                                                       const OptTensor& running_var, double momentum, double eps, int64_t expand, int64_t repeat) {
   const c10::cuda::CUDAGuard guard(stats.device());
   TORCH_CHECK(stats.numel() >= 2 * C * group, "clearvae: stats too small");
   auto fopt = stats.options().dtype(at::kFloat);
@@ -305,24 +305,26 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> bn_finalize(Tensor stats, int64_t C, 
   check_rc(clearvae_bn_finalize(stats_ptr(stats), (int32_t)C, (int32_t)group, count, optf(gamma, "gamma"), optf(beta, "beta"),
                                 optf_mut(running_mean, "running_mean"), optf_mut(running_var, "running_var"), (float)momentum,
                                 (float)eps, scale.data_ptr<float>(), shift.data_ptr<float>(), (int32_t)expand,
-                                mean.data_ptr<float>(), invstd.data_ptr<float>(), cur_stream()),
+                                mean.data_ptr<float>(), invstd.data_ptr<float>(), (int32_t)repeat, cur_stream()),
            "bn_finalize");
   return {scale, shift, mean, invstd};
 }
 
-void bn_reduce(const Tensor& y, const OptTensor& g, const OptTensor& act, int64_t C, int64_t inner, int64_t mode, Tensor stats) {
+void bn_reduce(const Tensor& y, const OptTensor& g, const OptTensor& act, const OptTensor& mscale, const OptTensor& mshift, int64_t C,
+               int64_t inner, int64_t mode, Tensor stats) {
   const c10::cuda::CUDAGuard guard(y.device());
   const bool hg = g.has_value() && g->defined(), ha = act.has_value() && act->defined();
   TORCH_CHECK(!hg || g->numel() == y.numel(), "clearvae: g / y size mismatch");
   TORCH_CHECK(stats.numel() >= 2 * C, "clearvae: stats too small");
   check_rc(clearvae_bn_reduce(y.data_ptr(), dt_of(y, "y"), hg ? g->data_ptr() : nullptr, hg ? dt_of(*g, "g") : 0,
-                              ha ? act->data_ptr() : nullptr, ha ? dt_of(*act, "act") : 0, y.numel(), (int32_t)C, inner,
-                              (int32_t)mode, stats_ptr(stats), cur_stream()),
+                              ha ? act->data_ptr() : nullptr, ha ? dt_of(*act, "act") : 0, optf(mscale, "mask_scale"),
+                              optf(mshift, "mask_shift"), y.numel(), (int32_t)C, inner, (int32_t)mode, stats_ptr(stats), cur_stream()),
            "bn_reduce");
 }
 
 std::tuple<Tensor, Tensor> bn_act_fwd(const Tensor& raw, const Tensor& scale, const Tensor& shift, int64_t C, int64_t inner,
-                                      int64_t act, int64_t out_dtype, const OptTensor& target, int64_t batch, Tensor workspace) {
+                                      int64_t act, int64_t tC, int64_t tHW, int64_t out_dtype, const OptTensor& target, int64_t batch,
+                                      Tensor workspace) {
   const c10::cuda::CUDAGuard guard(raw.device());
   check_f32(scale, "scale");
   check_f32(shift, "shift");
@@ -331,7 +333,7 @@ std::tuple<Tensor, Tensor> bn_act_fwd(const Tensor& raw, const Tensor& scale, co
   Tensor sse = at::empty({}, raw.options().dtype(at::kFloat));
   if (ht) { check_f32(*target, "target"); TORCH_CHECK(target->numel() == raw.numel(), "clearvae: target size mismatch"); }
   check_rc(clearvae_bn_act_fwd(raw.data_ptr(), dt_of(raw, "raw"), scale.data_ptr<float>(), shift.data_ptr<float>(), raw.numel(),
-                               (int32_t)C, inner, (int32_t)act, out.data_ptr(), (int32_t)out_dtype,
+                               (int32_t)C, inner, (int32_t)act, (int32_t)tC, (int32_t)tHW, out.data_ptr(), (int32_t)out_dtype,
                                ht ? target->data_ptr<float>() : nullptr, batch, sse.data_ptr<float>(), workspace.data_ptr(),
                                (size_t)workspace.nbytes(), cur_stream()),
            "bn_act_fwd");
@@ -366,15 +368,16 @@ std::tuple<Tensor, Tensor, Tensor> bn_bwd_coef(Tensor stats, int64_t C, int64_t 
   return {coef, dgamma, dbeta};
 }
 
-Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, const Tensor& coef, int64_t C, int64_t inner,
-                    int64_t out_dtype) {
+Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, const OptTensor& mscale, const OptTensor& mshift,
+                    const Tensor& coef, int64_t C, int64_t inner, int64_t out_dtype) {
   const c10::cuda::CUDAGuard guard(g.device());
   check_f32(coef, "coef");
   TORCH_CHECK(g.numel() == y.numel(), "clearvae: g / y size mismatch");
   const bool ha = act.has_value() && act->defined();
   Tensor dy = at::empty(y.sizes(), y.options().dtype(out_dtype == CLEARVAE_BF16 ? at::kBFloat16 : at::kFloat));
   check_rc(clearvae_bn_bwd_apply(g.data_ptr(), dt_of(g, "g"), y.data_ptr(), dt_of(y, "y"), ha ? act->data_ptr() : nullptr,
-                                 ha ? dt_of(*act, "act") : 0, coef.data_ptr<float>(), g.numel(), (int32_t)C, inner, dy.data_ptr(),
+                                 ha ? dt_of(*act, "act") : 0, optf(mscale, "mask_scale"), optf(mshift, "mask_shift"),
+                                 coef.data_ptr<float>(), g.numel(), (int32_t)C, inner, dy.data_ptr(),
                                  (int32_t)out_dtype, cur_stream()),
            "bn_bwd_apply");
   return dy;
@@ -410,14 +413,14 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
   m.def("bn_finalize(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
-        "Tensor(c!)? running_var, float momentum, float eps, int expand) -> (Tensor, Tensor, Tensor, Tensor)");
-  m.def("bn_reduce(Tensor y, Tensor? g, Tensor? act, int C, int inner, int mode, Tensor(a!) stats) -> ()");
-  m.def("bn_act_fwd(Tensor raw, Tensor scale, Tensor shift, int C, int inner, int act, int out_dtype, Tensor? target, int batch, "
+        "Tensor(c!)? running_var, float momentum, float eps, int expand, int repeat) -> (Tensor, Tensor, Tensor, Tensor)");
+  m.def("bn_reduce(Tensor y, Tensor? g, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, int C, int inner, int mode, Tensor(a!) stats) -> ()");
+  m.def("bn_act_fwd(Tensor raw, Tensor scale, Tensor shift, int C, int inner, int act, int to_nhwc_C, int to_nhwc_HW, int out_dtype, Tensor? target, int batch, "
         "Tensor(a!) workspace) -> (Tensor, Tensor)");
   m.def("sigmoid_mse_bwd(Tensor xhat, Tensor x, Tensor? grad_recon, Tensor? grad_ext, Tensor raw, int C, int inner, int batch, "
         "Tensor(a!) stats) -> Tensor");
   m.def("bn_bwd_coef(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor mean, Tensor invstd) -> (Tensor, Tensor, Tensor)");
-  m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor coef, int C, int inner, int out_dtype) -> Tensor");
+  m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, Tensor coef, int C, int inner, int out_dtype) -> Tensor");
   m.def("colsum(Tensor x) -> Tensor");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "

@@ -121,7 +121,7 @@ class EncoderFn(torch.autograd.Function):
                           pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
             if eng.training:
                 scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(B * H * H), gamma, beta, rm, rv,
-                                                             BN_MOMENTUM, BN_EPS, H * H if last else 1)
+                                                             BN_MOMENTUM, BN_EPS, H * H if last else 1, eng.bn_repeat)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, H * H if last else 1)
             saved_raw.append((raw, dst_strides))
@@ -180,7 +180,7 @@ class EncoderFn(torch.autograd.Function):
             last = i == n - 1
             group = H * H if last else 1
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, group, float(B * H * H), gamma, mean, invstd)
-            dy = ops.bn_bwd_apply(g, raw, None, coef, sp.cout, group, BF16)
+            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, BF16)
             dw = torch.zeros_like(w)
             if i == 0:
                 src, src_strides, pre = x, nchw_strides(sp.cin, sp.hin, sp.hin), None
@@ -222,12 +222,13 @@ class DecoderFn(torch.autograd.Function):
                       [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
         rm, rv = eng.dec_fc_buffers
         if eng.training:
-            sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1)
+            sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1, 1)
         else:
             sc, sh, mean_fc, inv_fc = eng.eval_affine(fc_g, fc_beta, rm, rv, 1)
-        a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, _DT[eng.act_dtype], None, B, _ws(dev))
         C0, H0 = specs[0].cin, specs[0].hin
-        src, src_strides, pre = a_fc, nchw_strides(C0, H0, H0), None
+        # BatchNorm1d + ReLU, written channels-last so the first transposed conv gathers 16-byte channel runs
+        a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, C0, H0 * H0, _DT[eng.act_dtype], None, B, _ws(dev))
+        src, src_strides, pre = a_fc, nhwc_strides(H0, H0, C0), None
         saved_raw, saved_pre, saved_stats = [], [], []
         n = len(specs)
         for j, sp in enumerate(specs):
@@ -247,7 +248,7 @@ class DecoderFn(torch.autograd.Function):
                           [0, 0, 0, 0], None, None, st)
             if eng.training:
                 scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(B * H * H), gamma, beta, rm, rv,
-                                                             BN_MOMENTUM, BN_EPS, 1)
+                                                             BN_MOMENTUM, BN_EPS, 1, 1)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, 1)
             saved_raw.append((raw, dst_strides))
@@ -256,14 +257,17 @@ class DecoderFn(torch.autograd.Function):
             src, src_strides, pre = raw, dst_strides, (scale, shift)
         sp = specs[-1]
         H = sp.hout
-        xhat, recon = ops.bn_act_fwd(src, pre[0], pre[1], sp.cout, H * H, 2, F32, target, B, _ws(dev))
+        if eng.stats_only:  # caller only wants the BatchNorm running-statistic side effects (CLEAR-MIM inner loop)
+            e = torch.empty(0, device=dev)
+            return e, e
+        xhat, recon = ops.bn_act_fwd(src, pre[0], pre[1], sp.cout, H * H, 2, 0, 0, F32, target, B, _ws(dev))
         if eng.debug is not None:
             eng.debug["dec_raw"] = [r for r, _ in saved_raw]
             eng.debug["fc_raw"], eng.debug["fc_act"] = raw_fc, a_fc
         if need_grad:
             ctx.eng = eng
             ctx.has_target = target is not None
-            ctx.saved = (z, target, fc_w, fc_g, raw_fc, a_fc, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params)
+            ctx.saved = (z, target, fc_w, fc_g, raw_fc, a_fc, (sc, sh), mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params)
             ctx.save_for_backward(xhat)
         return xhat, recon
 
@@ -271,7 +275,7 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, d_xhat, d_recon):
         ops = _ops.ops()
         eng = ctx.eng
-        (z, target, fc_w, fc_g, raw_fc, a_fc, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params) = ctx.saved
+        (z, target, fc_w, fc_g, raw_fc, a_fc, fc_aff, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params) = ctx.saved
         (xhat,) = ctx.saved_tensors
         if not eng.training:
             raise RuntimeError("clear_vae_b200: backward through eval-mode BatchNorm is not implemented")
@@ -297,10 +301,10 @@ class DecoderFn(torch.autograd.Function):
             last = j == n - 1
             inner = H * H if last else 1
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(B * H * H), gamma, mean, invstd)
-            dy = ops.bn_bwd_apply(g, raw, None, coef, sp.cout, inner, BF16)
+            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, BF16)
             dw = torch.zeros_like(w)
             if j == 0:
-                src, src_strides, pre = a_fc, nchw_strides(sp.cin, sp.hin, sp.hin), None
+                src, src_strides, pre = a_fc, nhwc_strides(sp.hin, sp.hin, sp.cin), None
             else:
                 src, src_strides = saved_raw[j - 1]
                 pre = saved_pre[j - 1]
@@ -317,15 +321,15 @@ class DecoderFn(torch.autograd.Function):
                 # gradient w.r.t. the activated fc output, channel-major like a_fc
                 N0 = fc_w.shape[0]
                 g_a = torch.empty(B, N0, dtype=torch.float32, device=dev)
-                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g_a, src_strides, EPI_BIAS_STATS,
-                              None, [0, 0, 0, 0], None, None, None)
+                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g_a,
+                              nchw_strides(sp.cin, sp.hin, sp.hin), EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
         # fc block: BatchNorm1d + ReLU backward, then Linear
         K0, N0 = fc_w.shape[1], fc_w.shape[0]
         fg = linear_geom(K0, N0)
         st = eng.stat_buf(("dec_fc_b",), N0, dev)
-        ops.bn_reduce(raw_fc, g_a, a_fc, N0, 1, 1, st)
+        ops.bn_reduce(raw_fc, g_a, None, fc_aff[0], fc_aff[1], N0, 1, 1, st)  # ReLU mask recomputed from the raw fc output
         coef, d_fc_g, d_fc_beta = ops.bn_bwd_coef(st, N0, 1, float(B), fc_g, mean_fc, inv_fc)
-        dy_fc = ops.bn_bwd_apply(g_a, raw_fc, a_fc, coef, N0, 1, F32)
+        dy_fc = ops.bn_bwd_apply(g_a, raw_fc, None, fc_aff[0], fc_aff[1], coef, N0, 1, F32)
         d_fc_w = torch.zeros_like(fc_w)
         ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
         dz = torch.empty(B, K0, dtype=torch.float32, device=dev)
@@ -346,6 +350,8 @@ class Engine:
         self.enc_buffers, self.dec_buffers, self.dec_fc_buffers = [], [], None
         self._stat = {}
         self.debug = None  # set to a dict to capture raw activations (tests / tools only)
+        self.bn_repeat = 1    # momentum updates per encoder forward (see VAE.encode)
+        self.stats_only = False
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev)

@@ -84,9 +84,9 @@ class VAE(nn.Module):
         e.dec_fc_buffers = (self.decoder[1].running_mean, self.decoder[1].running_var)
         return e
 
-    def _tick(self, bns):
+    def _tick(self, bns, n=1):
         if self.training:
-            torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
+            torch._foreach_add_([b.num_batches_tracked for b in bns], n)
 
     def _enc_params(self):
         out = []
@@ -103,23 +103,34 @@ class VAE(nn.Module):
         return out
 
     # -- reference API ---------------------------------------------------------------
-    def encode(self, x):
+    def encode(self, x, bn_repeat: int = 1):
+        """`bn_repeat` > 1 accounts for that many identical train-mode forwards in one pass: the
+        BatchNorm running statistics receive `bn_repeat` momentum updates with the same batch
+        statistics (what CLEAR-MIM's 5 inner forwards on an unchanged encoder amount to)."""
         eng = self._eng()
         heads = (self.mu_c, self.logvar_c, self.mu_s, self.logvar_s)
         hw = torch.cat([h.weight for h in heads], 0)
         hb = torch.cat([h.bias for h in heads], 0)
-        lat = EncoderFn.apply(eng, x, hw, hb, *self._enc_params())
-        self._tick([self.encoder[s.bn] for s in eng.enc_specs])
+        eng.bn_repeat = int(bn_repeat)
+        try:
+            lat = EncoderFn.apply(eng, x, hw, hb, *self._enc_params())
+        finally:
+            eng.bn_repeat = 1
+        self._tick([self.encoder[s.bn] for s in eng.enc_specs], int(bn_repeat))
         D = self.z_dim
         return tuple(lat[:, i * D:(i + 1) * D].contiguous() for i in range(4))
 
     def decode(self, z):
         return self._decode(z, None)[0]
 
-    def _decode(self, z, target):
+    def _decode(self, z, target, stats_only=False):
         eng = self._eng()
         fc, bn = self.decoder[0], self.decoder[1]
-        xhat, recon = DecoderFn.apply(eng, z, target, fc.weight, fc.bias, bn.weight, bn.bias, *self._dec_params())
+        eng.stats_only = bool(stats_only)
+        try:
+            xhat, recon = DecoderFn.apply(eng, z, target, fc.weight, fc.bias, bn.weight, bn.bias, *self._dec_params())
+        finally:
+            eng.stats_only = False
         self._tick([bn] + [self.decoder[s.bn] for s in eng.dec_specs])
         return xhat, recon
 

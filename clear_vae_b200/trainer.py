@@ -19,7 +19,7 @@ from torch.optim.optimizer import Optimizer
 from torch.utils.data import DataLoader
 from tqdm import tqdm
 
-from .latent import S_KL0, S_KL1, S_LOSS0, S_LOSS1, DistSpec
+from .latent import S_KL0, S_KL1, S_LOSS0, S_LOSS1, DistSpec, latent_block
 from .losses import contrastive_loss, vae_loss  # noqa: F401  (re-exported like the reference module)
 from .models.mi_estimator import CLUBSample
 from .models.vae import VAE
@@ -261,10 +261,18 @@ class ClearMIMVAETrainer(VAETrainer):
         self.optimizer.step()
         self.annealer.step()
         # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
+        # The encoder is unchanged across the 5 iterations, so its output is computed once and its BatchNorm
+        # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and
+        # runs the decoder for its running-statistic side effects, as the reference's full forwards do.
         learn = []
+        dummy = torch.zeros(X.shape[0], dtype=torch.int64, device=X.device)
+        with torch.no_grad():
+            mu_c, lv_c, mu_s, lv_s = vae.encode(X, bn_repeat=5)
         for j in range(5):
             with torch.no_grad():
-                _, _, z2 = vae(X, explicit=True) if inner_eps is None else _forward_with_eps(vae, X, inner_eps[j])
+                e = (torch.randn_like(lv_c), torch.randn_like(lv_s)) if inner_eps is None else inner_eps[j]
+                z2, _ = latent_block([mu_c, mu_s], [lv_c, lv_s], list(e), dummy, snn=[0, 0], ps=[0, 0])
+                vae._decode(z2, None, stats_only=True)
             ll = est.learning_loss(z2[:, :D], z2[:, D:])
             self.mi_estimator_optimizer.zero_grad()
             ll.backward()

@@ -183,14 +183,16 @@ int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearv
  * ------------------------------------------------------------------------- */
 int clearvae_bn_finalize(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
-                         int32_t expand, float* save_mean, float* save_invstd, void* stream);
+                         int32_t expand, float* save_mean, float* save_invstd, int32_t repeat /* momentum updates applied */, void* stream);
 /* mode 0: (sum y, sum y^2); mode 1: (sum g', sum g'*y) with g' = g*[act>0] when act != NULL */
 int clearvae_bn_reduce(const void* y, int32_t y_dtype, const void* g, int32_t g_dtype, const void* act, int32_t act_dtype,
-                       int64_t total, int32_t C, int64_t inner, int32_t mode, double* stats, void* stream);
+                       const float* mask_scale, const float* mask_shift /* or: g' = g*[y*scale+shift > 0] */, int64_t total,
+                       int32_t C, int64_t inner, int32_t mode, double* stats, void* stream);
 size_t clearvae_bn_act_workspace_bytes(void);
 /* out = act(raw*scale[ch]+shift[ch]); act 0 none / 1 relu / 2 sigmoid; with `target`, *sse_out = sum((out-target)^2)/batch */
 int clearvae_bn_act_fwd(const void* raw, int32_t raw_dtype, const float* scale, const float* shift, int64_t total, int32_t C,
-                        int64_t inner, int32_t act, void* out, int32_t out_dtype, const float* target, int64_t batch,
+                        int64_t inner, int32_t act, int32_t to_nhwc_C, int32_t to_nhwc_HW /* >0: write [b][hw][c] */, void* out,
+                        int32_t out_dtype, const float* target, int64_t batch,
                         float* sse_out, void* workspace, size_t workspace_bytes, void* stream);
 /* backward of xhat = sigmoid(bn(raw)) under recon = sum((xhat-x)^2)/batch (+ optional external grad on xhat) */
 int clearvae_sigmoid_mse_bwd(const float* xhat, const float* x, const float* grad_recon, const float* grad_ext, const void* raw,
@@ -200,7 +202,8 @@ int clearvae_sigmoid_mse_bwd(const float* xhat, const float* x, const float* gra
 int clearvae_bn_bwd_coef(double* stats, int32_t C, int32_t group, double count, const float* gamma, const float* save_mean,
                          const float* save_invstd, float* coef, float* dgamma, float* dbeta, void* stream);
 int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t y_dtype, const void* act, int32_t act_dtype,
-                          const float* coef, int64_t total, int32_t C, int64_t inner, void* dy, int32_t dy_dtype, void* stream);
+                          const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
+                          int64_t inner, void* dy, int32_t dy_dtype, void* stream);
 /* out[c] = sum_r x[r][c]  (bias gradients of the linear heads) */
 int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 
