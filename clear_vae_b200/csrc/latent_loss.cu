@@ -22,6 +22,7 @@
 // Other similarities / tiny temperatures use running maxima (two accumulators
 // per set) like the reference's logsumexp (losses.py:87-95).
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace {
 
@@ -279,6 +280,317 @@ __global__ void __launch_bounds__(kTN) snn_finalize_kernel(const float* stats, l
   finalize_term(stats, Bg, term, scalars, sred);
 }
 
+
+// ---------------------------------------------------------------------------
+// forward, tensor-core path (cosine, shared-shift): large batches
+//
+//   S = N_rows * N_cols^T on tcgen05 with a 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32-grade:
+//   the temperature multiplies similarity error by 1/tau before the exponential, so a single
+//   TF32 / bf16 product would miss the 1e-5 gate), accumulators in TMEM, double buffered so
+//   the masked exp / running-sum epilogue of column tile j overlaps the MMA of tile j+1.
+//   Per pair the epilogue spends 1 FFMA + 1 MUFU.EX2 + 2 FADD (+ label compare); the kernel is
+//   bound by the MUFU pipe (16 ex2/clk/SM), which is the roofline bench.py reports against.
+//   Warp roles: 0-3 column-tile producers (normalise + split + UMMA K-major interleave layout),
+//   4 MMA issuer, 5-12 epilogue (each warp: 32 TMEM lanes x half of the tile's columns).
+// ---------------------------------------------------------------------------
+template <int DP> struct TcCfg {
+  static constexpr int BN = DP <= 16 ? 256 : 128;     // columns per tile
+  static constexpr int KT = 3 * DP;                   // hi | lo | hi  (A)   x   hi | hi | lo  (B)
+  static constexpr int A_BYTES = 128 * KT * 4;
+  static constexpr int B_BYTES = BN * KT * 4;
+  static constexpr int SMEM = A_BYTES + 2 * B_BYTES + 2 * BN * 8 /*labels lo/hi x2*/ + 2048 /*barriers, flags, partials*/ + 1024;
+};
+constexpr int kTcThreads = 13 * 32;
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// stage one normalised row / column vector as [hi | second | third] K-major interleave chunks
+template <int DP>
+__device__ __forceinline__ void stage_split(const float* __restrict__ src, bool valid, int D, unsigned char* base, int rows,
+                                            int r, bool a_side) {
+  float v[DP];
+  float ss = 0.f;
+#pragma unroll
+  for (int d = 0; d < DP; ++d) {
+    v[d] = (valid && d < D) ? __ldg(src + d) : 0.f;
+    ss = fmaf(v[d], v[d], ss);
+  }
+  const float inv = 1.f / fmaxf(sqrtf(ss), kCosEps);
+  float hi[DP], lo[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) {
+    const float n = v[d] * inv;
+    hi[d] = tf32_rna(n);
+    lo[d] = tf32_rna(n - hi[d]);
+  }
+  constexpr int NC = DP / 4;  // 16-byte chunks per D-block
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float4 h4 = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+    const float4 l4 = make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    *reinterpret_cast<float4*>(base + (size_t)(c) * rows * 16 + r * 16) = h4;
+    *reinterpret_cast<float4*>(base + (size_t)(NC + c) * rows * 16 + r * 16) = a_side ? l4 : h4;
+    *reinterpret_cast<float4*>(base + (size_t)(2 * NC + c) * rows * 16 + r * 16) = a_side ? h4 : l4;
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdParams p) {
+  using C = TcCfg<DP>;
+  constexpr int BN = C::BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (sm100::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + C::A_BYTES;
+  int* sLab = reinterpret_cast<int*>(sB + 2 * C::B_BYTES);            // [2][2][BN]: buffer, (lo, hi), column
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLab + 4 * BN);
+  uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);                 // [0..1] sticky per-buffer "a column label's high word differs"
+  float* sRed = reinterpret_cast<float*>(sFlags + 4);                  // [kWarps + 1] + 2*128 partial sums
+  float* sPart = sRed + 16;
+
+  const int term = blockIdx.y;
+  const TermF& t = p.t[term];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int D = p.D;
+  const int ntiles = (int)((p.Bg + BN - 1) / BN);
+  const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+
+  // ---- reparameterisation + KL for this CTA's rows (same arithmetic as the FFMA kernel)
+  if (t.lv != nullptr) {
+    float kl = 0.f;
+    if (threadIdx.x < 256) {
+      for (int rr = threadIdx.x >> 5; rr < 128; rr += 8) {
+        const long long i = m0 + rr;
+        if (i < p.B) {
+          for (int d = lane; d < D; d += 32) {
+            const float m = t.mu[i * D + d], lv = t.lv[i * D + d];
+            kl += 1.f + lv - m * m - expf(lv);
+            if (t.z != nullptr && t.eps != nullptr) t.z[i * p.z_stride + d] = fmaf(t.eps[i * D + d], expf(0.5f * lv), m);
+          }
+        }
+      }
+    }
+    kl = cv::warp_sum(kl);
+    if (lane == 0) sPart[warp] = kl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 13; ++w) s += sPart[w];
+      p.kl_partial[term * p.max_ctas + blockIdx.x] = s;
+    }
+    __syncthreads();
+  }
+
+  if (t.snn) {
+    using namespace sm100;
+    if (threadIdx.x == 0) {
+      for (int b = 0; b < 2; ++b) { mbar_init(&b_full[b], 128); mbar_init(&b_empty[b], 1); mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
+      fence_barrier_init();
+      sFlags[0] = sFlags[1] = 0;
+    }
+    if (warp == 4) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+    // rows: A operand [hi | lo | hi], staged once (threads 0..127 = rows)
+    const long long hi_ref = (long long)(p.lab_c[0] >> 32);
+    if (threadIdx.x < 128) {
+      const long long i = m0 + threadIdx.x;
+      stage_split<DP>(t.mu + (i < p.B ? i : 0) * (long long)D, i < p.B, D, sA, 128, threadIdx.x, true);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp < 4) {
+      // ================= column-tile producers =================
+      for (int jt = 0; jt < ntiles; ++jt) {
+        const int b = jt & 1;
+        const uint32_t ph = ((jt >> 1) & 1) ^ 1;
+        mbar_wait(&b_empty[b], ph);
+        mbar_wait(&t_empty[b], ph);
+        unsigned char* bs = sB + b * C::B_BYTES;
+        int any_diff = 0;
+        for (int cc = threadIdx.x; cc < BN; cc += 128) {
+          const long long j = (long long)jt * BN + cc;
+          const bool valid = j < p.Bg;
+          stage_split<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, bs, BN, cc, false);
+          const long long lab = valid ? p.lab_c[j] : 0;
+          sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
+          sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
+          any_diff |= (valid && (lab >> 32) != hi_ref) ? 1 : 0;
+        }
+        any_diff = __any_sync(0xffffffffu, any_diff);
+        if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);
+        fence_proxy_async();
+        mbar_arrive(&b_full[b]);
+      }
+    } else if (warp == 4) {
+      // ================= MMA issuer =================
+      if (lane == 0) {
+        constexpr uint32_t idesc = instr_desc(kFmtTF32, 128, BN, 0, 0);
+        for (int jt = 0; jt < ntiles; ++jt) {
+          const int b = jt & 1;
+          mbar_wait(&b_full[b], (jt >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + b * C::B_BYTES);
+#pragma unroll
+          for (int k8 = 0; k8 < C::KT / 8; ++k8) {
+            const uint64_t ad = smem_desc(a_base + k8 * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
+            const uint64_t bd = smem_desc(b_base + k8 * 2 * (BN * 16), BN * 16, 128, kLayoutNone);
+            umma_tf32(tmem_base + b * BN, ad, bd, idesc, k8 != 0 ? 1u : 0u);
+          }
+          umma_commit(&b_empty[b]);
+          umma_commit(&t_full[b]);
+        }
+      }
+    } else {
+      // ================= epilogue: masked exp + running sums =================
+      const int ew = warp - 5;                 // 0..7
+      const int lane_grp = warp & 3;           // TMEM lanes this warp may touch: 32 * (warp % 4)
+      const int half = ew >> 2;                // which half of the tile's columns
+      const int r = lane_grp * 32 + lane;      // row inside the tile
+      const long long i = m0 + r;
+      const long long my_lab = i < p.B ? p.lab_r[i] : 0;
+      const int my_lo = (int)(my_lab & 0xffffffffll), my_hi = (int)(my_lab >> 32);
+      const bool my_hi_odd = (my_lab >> 32) != hi_ref;  // then equality of the low words is not enough
+      const long long diag = p.row_off + i;    // global column index of this row's diagonal
+      const bool ps = t.ps != 0;
+      const float k2 = p.inv_tau * CV_LOG2E;
+      float sa = 0.f, sp = 0.f;
+      constexpr int HALF = BN / 2;
+      for (int jt = 0; jt < ntiles; ++jt) {
+        const int b = jt & 1;
+        mbar_wait(&t_full[b], (jt >> 1) & 1);
+        tc_fence_after();
+        const long long jbase = (long long)jt * BN + half * HALF;
+        const bool edge = (jbase + HALF > p.Bg) || (diag >= jbase && diag < jbase + HALF) || sFlags[b] || my_hi_odd;
+        const int* lab_lo = sLab + (b * 2 + 0) * BN + half * HALF;
+        const int* lab_hi = sLab + (b * 2 + 1) * BN + half * HALF;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * BN + half * HALF + c0), raw);
+          tmem_ld_wait();
+          if (!edge) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              const int4 l4 = *reinterpret_cast<const int4*>(lab_lo + c0 + q);
+              const float e0 = ex2_approx(fmaf(__uint_as_float(raw[q]), k2, -k2));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(raw[q + 1]), k2, -k2));
+              const float e2 = ex2_approx(fmaf(__uint_as_float(raw[q + 2]), k2, -k2));
+              const float e3 = ex2_approx(fmaf(__uint_as_float(raw[q + 3]), k2, -k2));
+              sa += (e0 + e1) + (e2 + e3);
+              sp += ((l4.x == my_lo) != ps) ? e0 : 0.f;
+              sp += ((l4.y == my_lo) != ps) ? e1 : 0.f;
+              sp += ((l4.z == my_lo) != ps) ? e2 : 0.f;
+              sp += ((l4.w == my_lo) != ps) ? e3 : 0.f;
+            }
+          } else {
+#pragma unroll 4
+            for (int q = 0; q < 32; ++q) {
+              const long long j = jbase + c0 + q;
+              const float e = ex2_approx(fmaf(__uint_as_float(raw[q]), k2, -k2));
+              const bool cand = (j < p.Bg) && (j != diag);
+              const bool same = (lab_lo[c0 + q] == my_lo) && (lab_hi[c0 + q] == my_hi);
+              sa += cand ? e : 0.f;
+              sp += (cand && (same != ps)) ? e : 0.f;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[b]);
+      }
+      // combine the two column halves of each row
+      if (half == 1) { sPart[r] = sa; sPart[128 + r] = sp; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && i < p.B) {
+        t.stats[2 * i] = logf(sa + sPart[r]);
+        t.stats[2 * i + 1] = logf(sp + sPart[128 + r]);
+      }
+    }
+    sm100::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) sm100::tmem_dealloc(tmem_base, 2 * BN);
+  }
+
+  // ---- last CTA: deterministic reduction of the per-CTA partials (same as the FFMA kernel)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(p.ticket, 1u);
+    sRed[kWarps] = (tk == gridDim.x * gridDim.y - 1) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (sRed[kWarps] != 0.f && threadIdx.x < kTN) {
+    __threadfence();
+    for (int tt = 0; tt < (int)gridDim.y; ++tt) {
+      if (p.t[tt].lv != nullptr) {
+        float s = 0.f;
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += kTN) s += __ldcg(p.kl_partial + tt * p.max_ctas + c);
+        s = cv::warp_sum(s);
+        if (lane == 0) sPart[warp] = s;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+          float a = 0.f;
+          for (int w = 0; w < kWarps; ++w) a += sPart[w];
+          p.scalars[CLEARVAE_S_KL0 + tt] = -0.5f * a / (float)p.B;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      if (p.finalize && p.t[tt].snn) {
+        const float* stats = p.t[tt].stats;
+        float s = 0.f, c = 0.f;
+        for (long long ii = threadIdx.x; ii < p.Bg; ii += kTN) {
+          const float l = __ldcg(stats + 2 * ii) - __ldcg(stats + 2 * ii + 1);
+          if (isfinite(l)) { s += l; c += 1.f; }
+        }
+        s = cv::warp_sum(s);
+        c = cv::warp_sum(c);
+        if (lane == 0) { sPart[warp] = s; sPart[16 + warp] = c; }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+          float a = 0.f, n = 0.f;
+          for (int w = 0; w < kWarps; ++w) { a += sPart[w]; n += sPart[16 + w]; }
+          p.scalars[CLEARVAE_S_SUM0 + tt] = a;
+          p.scalars[CLEARVAE_S_CNT0 + tt] = n;
+          p.scalars[CLEARVAE_S_LOSS0 + tt] = a / n;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;
+  }
+}
+
+template <int DP>
+int launch_fwd_tc(const FwdParams& p, int n_terms, cudaStream_t st) {
+  auto kern = snn_fwd_tc_kernel<DP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<DP>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((p.B + 127) / 128), (unsigned)n_terms);
+  kern<<<grid, kTcThreads, TcCfg<DP>::SMEM, st>>>(p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
@@ -477,8 +789,20 @@ inline int pad_d(int D) { return D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : D <=
 // shared-shift path is safe while exp(-2/tau) stays a normal float
 inline bool fast_ok(int sim, float tau) { return sim == SIM_COS && tau > 0.f && 2.f / tau <= 80.f; }
 
+// the tensor-core forward pays off once there are enough 128-row tiles to cover the SMs
+int g_tc_min_rows = 4096;
+
 int dispatch_fwd(const FwdParams& p, int n_terms, int sim, bool fast, cudaStream_t st) {
   const int dp = pad_d(p.D), rm = pick_rm(dp, p.B);
+  if (fast && sim == SIM_COS && dp <= 32 && p.B >= g_tc_min_rows) {
+    bool all_snn = true;  // KL/reparam-only terms have no tile loop; keep them on the FFMA kernel
+    for (int i = 0; i < n_terms; ++i) all_snn &= p.t[i].snn != 0;
+    if (all_snn) {
+      if (dp == 8) return launch_fwd_tc<8>(p, n_terms, st);
+      if (dp == 16) return launch_fwd_tc<16>(p, n_terms, st);
+      return launch_fwd_tc<32>(p, n_terms, st);
+    }
+  }
   CV_DISPATCH_D(launch_fwd, p, n_terms, st, dp, rm, sim, fast);
   return CLEARVAE_EUNSUPPORTED;
 }
@@ -500,6 +824,9 @@ inline int max_ctas_for(long long B) { return (int)((B + kWarps - 1) / kWarps); 
 extern "C" {
 
 int clearvae_version(void) { return 100; }
+
+/* tuning / test hook: minimum local batch for the tensor-core latent forward (default 4096) */
+void clearvae_set_latent_tc_min_rows(int32_t rows) { g_tc_min_rows = rows; }
 
 size_t clearvae_latent_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms) {
   (void)Bg; (void)D; (void)n_terms;

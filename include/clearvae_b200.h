@@ -38,6 +38,8 @@ enum { CLEARVAE_SIM_COSINE = 0, CLEARVAE_SIM_L2 = 1, CLEARVAE_SIM_MODIFIED_L2 = 
 enum { CLEARVAE_LOSS_SNN = 0, CLEARVAE_LOSS_SUPCON_IN = 1, CLEARVAE_LOSS_SUPCON_OUT = 2 };
 
 int clearvae_version(void);
+/* tuning / test hook: minimum local batch for the tensor-core (tcgen05) latent forward; default 4096 */
+void clearvae_set_latent_tc_min_rows(int32_t rows);
 
 /* ---------------------------------------------------------------------------
  * Latent-head loss block.

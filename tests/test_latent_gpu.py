@@ -170,3 +170,43 @@ def test_vae_loss_matches_golden(golden_dir):
     (3.0 * rec).backward()
     want = 3.0 * 2.0 * (h["elbo/xhat"] - h["elbo/x"]) / h["elbo/x"].shape[0]
     assert np.abs(xh.grad.cpu().numpy() - want).max() < 1e-6
+
+
+def _set_tc_min_rows(n):
+    import ctypes
+    from clear_vae_b200 import _ops
+    _ops.load()
+    lib = ctypes.CDLL(_ops.lib_paths()[0])
+    lib.clearvae_set_latent_tc_min_rows(ctypes.c_int32(n))
+
+
+def test_tensor_core_forward_matches_goldens_and_ffma(golden_dir):
+    """The tcgen05 (3xTF32) forward, forced on for every size, against the reference goldens, and
+    bit-compatible enough with the FFMA path that the shared backward stays within 1e-4."""
+    from clear_vae_b200.losses import contrastive_loss
+    try:
+        _set_tc_min_rows(1)
+        n = 0
+        for name, g, sim, tau, ln, ps in cases(golden_dir):
+            if sim != "cosine" or ln != "snn_loss" or tau < 0.03:
+                continue
+            mu = torch.tensor(g[f"{name}/mu"], device=DEV, requires_grad=True)
+            lab = torch.tensor(g[f"{name}/label"], device=DEV)
+            loss = contrastive_loss(mu, torch.zeros_like(mu), lab, sim, tau, ln, ps)
+            want = float(g[f"{name}/loss"])
+            assert close(float(loss), want), (name, float(loss), want)
+            if np.isfinite(want):
+                loss.backward()
+                wg = g[f"{name}/dmu"]
+                assert np.abs(mu.grad.cpu().numpy() - wg).max() <= GRAD_REL * np.abs(wg).max() + 1e-7, name
+            n += 1
+        assert n >= 20
+        # labels whose high 32 bits differ must still compare as full int64
+        gen = torch.Generator().manual_seed(1)
+        mu = torch.randn(300, 8, generator=gen)
+        lab = torch.randint(0, 3, (300,), generator=gen) + (torch.randint(0, 2, (300,), generator=gen) << 33)
+        got = contrastive_loss(mu.to(DEV), mu.to(DEV), lab.to(DEV), "cosine", 0.1)
+        want = lo.contrastive(mu.numpy(), mu.numpy(), lab.numpy(), "cosine", 0.1)
+        assert close(float(got), want)
+    finally:
+        _set_tc_min_rows(4096)
