@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
       const long long diag = p.row_off + i;    // global column index of this row's diagonal
       const bool ps = t.ps != 0;
       const float k2 = p.inv_tau * CV_LOG2E;
-      float sa = 0.f, sp = 0.f;
+      float sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f, sp0 = 0.f, sp1 = 0.f, sp2 = 0.f, sp3 = 0.f;
       constexpr int HALF = BN / 2;
       for (int jt = 0; jt < ntiles; ++jt) {
         const int b = jt & 1;
@@ -479,34 +479,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
         const bool edge = (jbase + HALF > p.Bg) || (diag >= jbase && diag < jbase + HALF) || sFlags[b] || my_hi_odd;
         const int* lab_lo = sLab + (b * 2 + 0) * BN + half * HALF;
         const int* lab_hi = sLab + (b * 2 + 1) * BN + half * HALF;
-#pragma unroll 1
-        for (int c0 = 0; c0 < HALF; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * BN + half * HALF + c0), raw);
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is exponentiated
+        constexpr int NCH = HALF / 32;
+        uint32_t raw[2][32];
+        const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * BN + half * HALF);
+        tmem_ld32(tcol, raw[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = ch * 32;
           tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld32(tcol + (uint32_t)(c0 + 32), raw[(ch + 1) & 1]);
+          const uint32_t(&rw)[32] = raw[ch & 1];
           if (!edge) {
 #pragma unroll
             for (int q = 0; q < 32; q += 4) {
               const int4 l4 = *reinterpret_cast<const int4*>(lab_lo + c0 + q);
-              const float e0 = ex2_approx(fmaf(__uint_as_float(raw[q]), k2, -k2));
-              const float e1 = ex2_approx(fmaf(__uint_as_float(raw[q + 1]), k2, -k2));
-              const float e2 = ex2_approx(fmaf(__uint_as_float(raw[q + 2]), k2, -k2));
-              const float e3 = ex2_approx(fmaf(__uint_as_float(raw[q + 3]), k2, -k2));
-              sa += (e0 + e1) + (e2 + e3);
-              sp += ((l4.x == my_lo) != ps) ? e0 : 0.f;
-              sp += ((l4.y == my_lo) != ps) ? e1 : 0.f;
-              sp += ((l4.z == my_lo) != ps) ? e2 : 0.f;
-              sp += ((l4.w == my_lo) != ps) ? e3 : 0.f;
+              const float e0 = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(rw[q + 1]), k2, -k2));
+              const float e2 = ex2_approx(fmaf(__uint_as_float(rw[q + 2]), k2, -k2));
+              const float e3 = ex2_approx(fmaf(__uint_as_float(rw[q + 3]), k2, -k2));
+              sa0 += e0; sa1 += e1; sa2 += e2; sa3 += e3;
+              sp0 += ((l4.x == my_lo) != ps) ? e0 : 0.f;
+              sp1 += ((l4.y == my_lo) != ps) ? e1 : 0.f;
+              sp2 += ((l4.z == my_lo) != ps) ? e2 : 0.f;
+              sp3 += ((l4.w == my_lo) != ps) ? e3 : 0.f;
             }
           } else {
-#pragma unroll 4
+#pragma unroll
             for (int q = 0; q < 32; ++q) {
               const long long j = jbase + c0 + q;
-              const float e = ex2_approx(fmaf(__uint_as_float(raw[q]), k2, -k2));
+              const float e = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
               const bool cand = (j < p.Bg) && (j != diag);
               const bool same = (lab_lo[c0 + q] == my_lo) && (lab_hi[c0 + q] == my_hi);
-              sa += cand ? e : 0.f;
-              sp += (cand && (same != ps)) ? e : 0.f;
+              sa0 += cand ? e : 0.f;
+              sp0 += (cand && (same != ps)) ? e : 0.f;
             }
           }
         }
@@ -515,6 +521,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
         if (lane == 0) mbar_arrive(&t_empty[b]);
       }
       // combine the two column halves of each row
+      const float sa = (sa0 + sa1) + (sa2 + sa3), sp = (sp0 + sp1) + (sp2 + sp3);
       if (half == 1) { sPart[r] = sa; sPart[128 + r] = sp; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0 && i < p.B) {
@@ -723,6 +730,262 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// backward, tensor-core path (cosine, shared-shift): FlashAttention-backward-shaped
+//   per column tile:  S = N_rows N_cols^T (3xTF32, TMEM)  ->  epilogue turns S into the coefficient tile
+//   P_ij = e_ij ((c_i + c_j) - [pos_ij](q_i + q_j)) and writes it back over S in TMEM (tcgen05.st)
+//   ->  second MMA with A = P taken from TMEM:  dN += P [N_hi | N_lo]   (same shared tile, read MN-major)
+//   The [128 x 2D] gradient accumulator stays in TMEM for the whole column sweep.
+// ---------------------------------------------------------------------------
+template <int DP> struct TcBwdCfg {
+  static constexpr int BN = 128;
+  static constexpr int KT = 3 * DP;
+  static constexpr int A_BYTES = 128 * KT * 4;
+  static constexpr int B_BYTES = BN * KT * 4;
+  static constexpr int SMEM = A_BYTES + 2 * B_BYTES + 2 * BN * 16 /*labels lo/hi, c, q*/ + 2048 + 1024;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdParams p) {
+  using namespace sm100;
+  using C = TcBwdCfg<DP>;
+  constexpr int BN = C::BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + C::A_BYTES;
+  int* sLab = reinterpret_cast<int*>(sB + 2 * C::B_BYTES);   // [2][2][BN]
+  float* sCQ = reinterpret_cast<float*>(sLab + 4 * BN);      // [2][2][BN]  (c_j, q_j)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCQ + 4 * BN);
+  uint64_t *b_full = bars, *b_empty = bars + 2, *s_full = bars + 4, *p_full = bars + 6, *dn_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int term = blockIdx.y;
+  const TermB& t = p.t[term];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int D = p.D;
+  const int ntiles = (int)((p.Bg + BN - 1) / BN);
+  const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+  constexpr uint32_t kDnCol = 2 * BN;  // TMEM column of the gradient accumulator
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&b_full[b], 128); mbar_init(&b_empty[b], 1); mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
+    mbar_init(dn_full, 1);
+    fence_barrier_init();
+    sFlags[0] = sFlags[1] = 0;
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  const long long hi_ref = (long long)(p.lab_c[0] >> 32);
+  if (threadIdx.x < 128) {
+    const long long i = m0 + threadIdx.x;
+    stage_split<DP>(t.mu + (i < p.B ? i : 0) * (long long)D, i < p.B, D, sA, 128, threadIdx.x, true);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================= column-tile producers =================
+    for (int jt = 0; jt < ntiles; ++jt) {
+      const int b = jt & 1;
+      mbar_wait(&b_empty[b], ((jt >> 1) & 1) ^ 1);
+      unsigned char* bs = sB + b * C::B_BYTES;
+      const int cc = threadIdx.x;
+      const long long j = (long long)jt * BN + cc;
+      const bool valid = j < p.Bg;
+      stage_split<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, bs, BN, cc, false);
+      const long long lab = valid ? p.lab_c[j] : 0;
+      sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
+      sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
+      float a = INFINITY, q = INFINITY;
+      if (valid) { a = t.stats_all[2 * j]; q = t.stats_all[2 * j + 1]; }
+      const bool fin = isfinite(a - q);
+      sCQ[(b * 2 + 0) * BN + cc] = fin ? __expf(-a) : 0.f;
+      sCQ[(b * 2 + 1) * BN + cc] = fin ? __expf(-q) : 0.f;
+      const int any_diff = __any_sync(0xffffffffu, (valid && (lab >> 32) != hi_ref) ? 1 : 0);
+      if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);
+      fence_proxy_async();
+      mbar_arrive(&b_full[b]);
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = instr_desc(kFmtTF32, 128, BN, 0, 0);
+      constexpr uint32_t idesc2 = instr_desc(kFmtTF32, 128, 2 * DP, 0, 1);  // B = [N_hi | N_lo], MN-major
+      const uint32_t a_base = smem_u32(sA);
+      auto mma2 = [&](int jt) {
+        const int b = jt & 1;
+        mbar_wait(&p_full[b], (jt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t bmn = smem_u32(sB + b * C::B_BYTES) + (DP / 4) * (BN * 16);  // blocks 1,2 of [hi | hi | lo]
+#pragma unroll
+        for (int k8 = 0; k8 < BN / 8; ++k8) {
+          const uint64_t bd = smem_desc(bmn + k8 * 128, 128, BN * 16, kLayoutNone);
+          umma_tf32_ts(tmem_base + kDnCol, tmem_base + b * BN + k8 * 8, bd, idesc2, (jt | k8) != 0 ? 1u : 0u);
+        }
+        umma_commit(&b_empty[b]);
+      };
+      for (int jt = 0; jt < ntiles; ++jt) {
+        const int b = jt & 1;
+        mbar_wait(&b_full[b], (jt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(sB + b * C::B_BYTES);
+#pragma unroll
+        for (int k8 = 0; k8 < C::KT / 8; ++k8) {
+          const uint64_t ad = smem_desc(a_base + k8 * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
+          const uint64_t bd = smem_desc(b_base + k8 * 2 * (BN * 16), BN * 16, 128, kLayoutNone);
+          umma_tf32(tmem_base + b * BN, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[b]);
+        if (jt > 0) mma2(jt - 1);
+      }
+      mma2(ntiles - 1);
+      umma_commit(dn_full);
+    }
+  } else {
+    // ================= epilogue: S -> coefficient tile P (in place), then the final gradient =================
+    const int ew = warp - 5, lane_grp = warp & 3, half = ew >> 2;
+    const int r = lane_grp * 32 + lane;
+    const long long i = m0 + r;
+    const long long my_lab = i < p.B ? p.lab_r[i] : 0;
+    const int my_lo = (int)(my_lab & 0xffffffffll), my_hi = (int)(my_lab >> 32);
+    const bool my_hi_odd = (my_lab >> 32) != hi_ref;
+    const long long diag = p.row_off + i;
+    const bool ps = t.ps != 0;
+    const float k2 = p.inv_tau * CV_LOG2E;
+    float ci = 0.f, qi = 0.f;
+    if (i < p.B) {
+      const float a = t.stats_all[2 * diag], q = t.stats_all[2 * diag + 1];
+      if (isfinite(a - q)) { ci = __expf(-a); qi = __expf(-q); }
+    }
+    constexpr int HALF = BN / 2, NCH = HALF / 32;
+    for (int jt = 0; jt < ntiles; ++jt) {
+      const int b = jt & 1;
+      mbar_wait(&s_full[b], (jt >> 1) & 1);
+      tc_fence_after();
+      const long long jbase = (long long)jt * BN + half * HALF;
+      const bool edge = (jbase + HALF > p.Bg) || (diag >= jbase && diag < jbase + HALF) || sFlags[b] || my_hi_odd;
+      const int* lab_lo = sLab + (b * 2 + 0) * BN + half * HALF;
+      const int* lab_hi = sLab + (b * 2 + 1) * BN + half * HALF;
+      const float* cj = sCQ + (b * 2 + 0) * BN + half * HALF;
+      const float* qj = sCQ + (b * 2 + 1) * BN + half * HALF;
+      const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * BN + half * HALF);
+      uint32_t raw[2][32];
+      tmem_ld32(tcol, raw[0]);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c0 = ch * 32;
+        tmem_ld_wait();
+        if (ch + 1 < NCH) tmem_ld32(tcol + (uint32_t)(c0 + 32), raw[(ch + 1) & 1]);
+        uint32_t(&rw)[32] = raw[ch & 1];
+        if (!edge) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const int4 l4 = *reinterpret_cast<const int4*>(lab_lo + c0 + q);
+            const float4 c4 = *reinterpret_cast<const float4*>(cj + c0 + q);
+            const float4 q4 = *reinterpret_cast<const float4*>(qj + c0 + q);
+            const float e0 = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(rw[q + 1]), k2, -k2));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(rw[q + 2]), k2, -k2));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(rw[q + 3]), k2, -k2));
+            const float f0 = (ci + c4.x) - (((l4.x == my_lo) != ps) ? (qi + q4.x) : 0.f);
+            const float f1 = (ci + c4.y) - (((l4.y == my_lo) != ps) ? (qi + q4.y) : 0.f);
+            const float f2 = (ci + c4.z) - (((l4.z == my_lo) != ps) ? (qi + q4.z) : 0.f);
+            const float f3 = (ci + c4.w) - (((l4.w == my_lo) != ps) ? (qi + q4.w) : 0.f);
+            rw[q] = __float_as_uint(tf32_rna(e0 * f0));
+            rw[q + 1] = __float_as_uint(tf32_rna(e1 * f1));
+            rw[q + 2] = __float_as_uint(tf32_rna(e2 * f2));
+            rw[q + 3] = __float_as_uint(tf32_rna(e3 * f3));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const long long j = jbase + c0 + q;
+            const float e = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
+            const bool cand = (j < p.Bg) && (j != diag);
+            const bool same = (lab_lo[c0 + q] == my_lo) && (lab_hi[c0 + q] == my_hi);
+            const float f = (ci + cj[c0 + q]) - ((same != ps) ? (qi + qj[c0 + q]) : 0.f);
+            rw[q] = __float_as_uint(cand ? tf32_rna(e * f) : 0.f);
+          }
+        }
+        tmem_st32(tcol + (uint32_t)c0, rw);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+    // ---- final: dN (TMEM) -> chain through the normalisation, add KL / reparam gradients
+    mbar_wait(dn_full, 0);
+    tc_fence_after();
+    if (half == 0) {
+      float acc[2 * DP];
+#pragma unroll
+      for (int c0 = 0; c0 < 2 * DP; c0 += 16) {
+        uint32_t r16[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + kDnCol + (uint32_t)c0, r16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[c0 + q] = __uint_as_float(r16[q]);
+      }
+      if (i < p.B) {
+        const float g_kl = p.gscal[term], g_loss = p.gscal[2 + term];
+        const float w = g_loss * p.inv_tau / p.scalars[CLEARVAE_S_CNT0 + term];
+        float n[DP], mu[DP];
+        float ss = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { mu[d] = d < D ? t.mu[i * D + d] : 0.f; ss = fmaf(mu[d], mu[d], ss); }
+        const float inv = 1.f / fmaxf(sqrtf(ss), kCosEps);
+        const bool live = inv < 1.f / kCosEps;
+        float dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { n[d] = mu[d] * inv; acc[d] += acc[DP + d]; dot = fmaf(acc[d], n[d], dot); }
+        const float invB = 1.f / (float)p.B;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          if (d >= D) continue;
+          float gm = w * (acc[d] - (live ? n[d] * dot : 0.f)) * inv, gl = 0.f;
+          if (t.lv != nullptr) {
+            const float lv = t.lv[i * D + d];
+            gm = fmaf(g_kl * invB, mu[d], gm);
+            gl = g_kl * invB * 0.5f * (expf(lv) - 1.f);
+            if (t.dz != nullptr) {
+              const float gz = t.dz[i * p.z_stride + d];
+              gm += gz;
+              if (t.eps != nullptr) gl = fmaf(0.5f * gz * t.eps[i * D + d], expf(0.5f * lv), gl);
+            }
+          }
+          t.dmu[i * D + d] = gm;
+          if (t.dlv != nullptr) t.dlv[i * D + d] = gl;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+template <int DP>
+int launch_bwd_tc(const BwdParams& p, int n_terms, cudaStream_t st) {
+  auto kern = snn_bwd_tc_kernel<DP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwdCfg<DP>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((p.B + 127) / 128), (unsigned)n_terms);
+  kern<<<grid, kTcThreads, TcBwdCfg<DP>::SMEM, st>>>(p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void pair_mask_kernel(const long long* lab_r, const long long* lab_c, long long B, long long Bg,
                                  long long row_off, int ps, unsigned char* out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -808,6 +1071,15 @@ int dispatch_fwd(const FwdParams& p, int n_terms, int sim, bool fast, cudaStream
 }
 int dispatch_bwd(const BwdParams& p, int n_terms, int sim, bool fast, cudaStream_t st) {
   const int dp = pad_d(p.D), rm = pick_rm(dp, p.B);
+  if (fast && sim == SIM_COS && dp <= 32 && p.B >= g_tc_min_rows) {
+    bool all_snn = true;
+    for (int i = 0; i < n_terms; ++i) all_snn &= p.t[i].snn != 0;
+    if (all_snn) {
+      if (dp == 8) return launch_bwd_tc<8>(p, n_terms, st);
+      if (dp == 16) return launch_bwd_tc<16>(p, n_terms, st);
+      return launch_bwd_tc<32>(p, n_terms, st);
+    }
+  }
   CV_DISPATCH_D(launch_bwd, p, n_terms, st, dp, rm, sim, fast);
   return CLEARVAE_EUNSUPPORTED;
 }

@@ -143,10 +143,11 @@ def test_sharded_rows_sum_to_global_loss():
                                   0, 0, 0.1, False, False, ws)
         parts.append(st[0])
     st_all = torch.cat(parts)
-    assert torch.equal(st_all, st_full[0])  # same arithmetic per row -> bit-identical stats
+    # row statistics do not depend on how rows are sharded (full batch may take the tensor-core path)
+    assert torch.allclose(st_all, st_full[0], rtol=0, atol=2e-6)
     sc = torch.zeros(8, device=DEV)
     ops.snn_finalize(st_all, 0, sc)
-    assert float(sc[2]) == float(sc_full[2])
+    assert abs(float(sc[2]) - float(sc_full[2])) <= 1e-6 * abs(float(sc_full[2])) + 1e-7
 
 
 def test_error_behaviour():
