@@ -316,7 +316,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // stage one normalised row / column vector as [hi | second | third] K-major interleave chunks
 template <int DP>
 __device__ __forceinline__ void stage_split(const float* __restrict__ src, bool valid, int D, unsigned char* base, int rows,
-                                            int r, bool a_side) {
+                                            int r, bool a_side, unsigned char* kmajor2 = nullptr) {
   float v[DP];
   float ss = 0.f;
 #pragma unroll
@@ -340,6 +340,12 @@ __device__ __forceinline__ void stage_split(const float* __restrict__ src, bool 
     *reinterpret_cast<float4*>(base + (size_t)(c) * rows * 16 + r * 16) = h4;
     *reinterpret_cast<float4*>(base + (size_t)(NC + c) * rows * 16 + r * 16) = a_side ? l4 : h4;
     *reinterpret_cast<float4*>(base + (size_t)(2 * NC + c) * rows * 16 + r * 16) = a_side ? h4 : l4;
+  }
+  if (kmajor2 != nullptr) {
+    // second-GEMM operand [n = (hi | lo) x d][k = column r]: K-major interleave, 2*DP rows
+    float* dst = reinterpret_cast<float*>(kmajor2 + (size_t)(r >> 2) * (2 * DP * 16) + (r & 3) * 4);
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { dst[d * 4] = hi[d]; dst[(DP + d) * 4] = lo[d]; }
   }
 }
 
@@ -739,11 +745,12 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
 //   The [128 x 2D] gradient accumulator stays in TMEM for the whole column sweep.
 // ---------------------------------------------------------------------------
 template <int DP> struct TcBwdCfg {
-  static constexpr int BN = 128;
+  static constexpr int BN = 96;                       // columns per tile: 2 x (S/P_hi + P_lo) + dN must fit 512 TMEM columns
   static constexpr int KT = 3 * DP;
   static constexpr int A_BYTES = 128 * KT * 4;
   static constexpr int B_BYTES = BN * KT * 4;
-  static constexpr int SMEM = A_BYTES + 2 * B_BYTES + 2 * BN * 16 /*labels lo/hi, c, q*/ + 2048 + 1024;
+  static constexpr int B2_BYTES = BN * 2 * DP * 4;    // [N_hi | N_lo]^T, K-major for the second GEMM
+  static constexpr int SMEM = A_BYTES + 2 * B_BYTES + 2 * B2_BYTES + 2 * BN * 16 /*labels lo/hi, c, q*/ + 2048 + 1024;
 };
 
 template <int DP>
@@ -751,12 +758,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   using namespace sm100;
   using C = TcBwdCfg<DP>;
   constexpr int BN = C::BN;
+  constexpr uint32_t kBufCols = 2 * BN;      // per buffer: [0,BN) S then P_hi, [BN,2BN) P_lo
+  constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulator [128 x 2DP]
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::A_BYTES;
-  int* sLab = reinterpret_cast<int*>(sB + 2 * C::B_BYTES);   // [2][2][BN]
-  float* sCQ = reinterpret_cast<float*>(sLab + 4 * BN);      // [2][2][BN]  (c_j, q_j)
+  unsigned char* sB2 = sB + 2 * C::B_BYTES;
+  int* sLab = reinterpret_cast<int*>(sB2 + 2 * C::B2_BYTES);  // [2][2][BN]
+  float* sCQ = reinterpret_cast<float*>(sLab + 4 * BN);       // [2][2][BN]  (c_j, q_j)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sCQ + 4 * BN);
   uint64_t *b_full = bars, *b_empty = bars + 2, *s_full = bars + 4, *p_full = bars + 6, *dn_full = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
@@ -769,10 +779,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   const int D = p.D;
   const int ntiles = (int)((p.Bg + BN - 1) / BN);
   const float* cols = t.mu_cols ? t.mu_cols : t.mu;
-  constexpr uint32_t kDnCol = 2 * BN;  // TMEM column of the gradient accumulator
 
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&b_full[b], 128); mbar_init(&b_empty[b], 1); mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); }
     mbar_init(dn_full, 1);
     fence_barrier_init();
     sFlags[0] = sFlags[1] = 0;
@@ -790,43 +799,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ================= column-tile producers =================
-    for (int jt = 0; jt < ntiles; ++jt) {
-      const int b = jt & 1;
-      mbar_wait(&b_empty[b], ((jt >> 1) & 1) ^ 1);
-      unsigned char* bs = sB + b * C::B_BYTES;
-      const int cc = threadIdx.x;
-      const long long j = (long long)jt * BN + cc;
-      const bool valid = j < p.Bg;
-      stage_split<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, bs, BN, cc, false);
-      const long long lab = valid ? p.lab_c[j] : 0;
-      sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
-      sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
-      float a = INFINITY, q = INFINITY;
-      if (valid) { a = t.stats_all[2 * j]; q = t.stats_all[2 * j + 1]; }
-      const bool fin = isfinite(a - q);
-      sCQ[(b * 2 + 0) * BN + cc] = fin ? __expf(-a) : 0.f;
-      sCQ[(b * 2 + 1) * BN + cc] = fin ? __expf(-q) : 0.f;
-      const int any_diff = __any_sync(0xffffffffu, (valid && (lab >> 32) != hi_ref) ? 1 : 0);
-      if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);
-      fence_proxy_async();
-      mbar_arrive(&b_full[b]);
+    // ================= column-tile producers (one thread per column; warps 0-2 active) =================
+    if (threadIdx.x < BN) {
+      for (int jt = 0; jt < ntiles; ++jt) {
+        const int b = jt & 1;
+        mbar_wait(&b_empty[b], ((jt >> 1) & 1) ^ 1);
+        const int cc = threadIdx.x;
+        const long long j = (long long)jt * BN + cc;
+        const bool valid = j < p.Bg;
+        stage_split<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, sB + b * C::B_BYTES, BN, cc, false, sB2 + b * C::B2_BYTES);
+        const long long lab = valid ? p.lab_c[j] : 0;
+        sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
+        sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
+        float a = INFINITY, q = INFINITY;
+        if (valid) { a = t.stats_all[2 * j]; q = t.stats_all[2 * j + 1]; }
+        const bool fin = isfinite(a - q);
+        sCQ[(b * 2 + 0) * BN + cc] = fin ? __expf(-a) : 0.f;
+        sCQ[(b * 2 + 1) * BN + cc] = fin ? __expf(-q) : 0.f;
+        const int any_diff = __any_sync(0xffffffffu, (valid && (lab >> 32) != hi_ref) ? 1 : 0);
+        if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);
+        fence_proxy_async();
+        mbar_arrive(&b_full[b]);
+      }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = instr_desc(kFmtTF32, 128, BN, 0, 0);
-      constexpr uint32_t idesc2 = instr_desc(kFmtTF32, 128, 2 * DP, 0, 1);  // B = [N_hi | N_lo], MN-major
+      constexpr uint32_t idesc2 = instr_desc(kFmtTF32, 128, 2 * DP, 0, 0);
       const uint32_t a_base = smem_u32(sA);
       auto mma2 = [&](int jt) {
         const int b = jt & 1;
         mbar_wait(&p_full[b], (jt >> 1) & 1);
         tc_fence_after();
-        const uint32_t bmn = smem_u32(sB + b * C::B_BYTES) + (DP / 4) * (BN * 16);  // blocks 1,2 of [hi | hi | lo]
+        const uint32_t b2 = smem_u32(sB2 + b * C::B2_BYTES);
 #pragma unroll
-        for (int k8 = 0; k8 < BN / 8; ++k8) {
-          const uint64_t bd = smem_desc(bmn + k8 * 128, 128, BN * 16, kLayoutNone);
-          umma_tf32_ts(tmem_base + kDnCol, tmem_base + b * BN + k8 * 8, bd, idesc2, (jt | k8) != 0 ? 1u : 0u);
+        for (int part = 0; part < 2; ++part) {        // A = P_hi, then P_lo (split keeps the coefficient at fp32 grade)
+#pragma unroll
+          for (int k8 = 0; k8 < BN / 8; ++k8) {
+            const uint64_t bd = smem_desc(b2 + k8 * 2 * (2 * DP * 16), 2 * DP * 16, 128, kLayoutNone);
+            umma_tf32_ts(tmem_base + kDnCol, tmem_base + b * kBufCols + part * BN + k8 * 8, bd, idesc2, (jt | part | k8) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&b_empty[b]);
       };
@@ -839,7 +852,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
         for (int k8 = 0; k8 < C::KT / 8; ++k8) {
           const uint64_t ad = smem_desc(a_base + k8 * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
           const uint64_t bd = smem_desc(b_base + k8 * 2 * (BN * 16), BN * 16, 128, kLayoutNone);
-          umma_tf32(tmem_base + b * BN, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
+          umma_tf32(tmem_base + b * kBufCols, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[b]);
         if (jt > 0) mma2(jt - 1);
@@ -848,8 +861,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       umma_commit(dn_full);
     }
   } else {
-    // ================= epilogue: S -> coefficient tile P (in place), then the final gradient =================
-    const int ew = warp - 5, lane_grp = warp & 3, half = ew >> 2;
+    // ================= epilogue: two groups of 4 warps alternate over the column tiles =================
+    const int ew = warp - 5, lane_grp = warp & 3, grp = ew >> 2;
     const int r = lane_grp * 32 + lane;
     const long long i = m0 + r;
     const long long my_lab = i < p.B ? p.lab_r[i] : 0;
@@ -863,26 +876,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       const float a = t.stats_all[2 * diag], q = t.stats_all[2 * diag + 1];
       if (isfinite(a - q)) { ci = __expf(-a); qi = __expf(-q); }
     }
-    constexpr int HALF = BN / 2, NCH = HALF / 32;
-    for (int jt = 0; jt < ntiles; ++jt) {
-      const int b = jt & 1;
+    for (int jt = grp; jt < ntiles; jt += 2) {
+      const int b = grp;
       mbar_wait(&s_full[b], (jt >> 1) & 1);
       tc_fence_after();
-      const long long jbase = (long long)jt * BN + half * HALF;
-      const bool edge = (jbase + HALF > p.Bg) || (diag >= jbase && diag < jbase + HALF) || sFlags[b] || my_hi_odd;
-      const int* lab_lo = sLab + (b * 2 + 0) * BN + half * HALF;
-      const int* lab_hi = sLab + (b * 2 + 1) * BN + half * HALF;
-      const float* cj = sCQ + (b * 2 + 0) * BN + half * HALF;
-      const float* qj = sCQ + (b * 2 + 1) * BN + half * HALF;
-      const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * BN + half * HALF);
-      uint32_t raw[2][32];
-      tmem_ld32(tcol, raw[0]);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int c0 = ch * 32;
+      const long long jbase = (long long)jt * BN;
+      const bool edge = (jbase + BN > p.Bg) || (diag >= jbase && diag < jbase + BN) || sFlags[b] || my_hi_odd;
+      const int* lab_lo = sLab + (b * 2 + 0) * BN;
+      const int* lab_hi = sLab + (b * 2 + 1) * BN;
+      const float* cj = sCQ + (b * 2 + 0) * BN;
+      const float* qj = sCQ + (b * 2 + 1) * BN;
+      const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * kBufCols);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t rw[32], lw[32];
+        tmem_ld32(tcol + (uint32_t)c0, rw);
         tmem_ld_wait();
-        if (ch + 1 < NCH) tmem_ld32(tcol + (uint32_t)(c0 + 32), raw[(ch + 1) & 1]);
-        uint32_t(&rw)[32] = raw[ch & 1];
         if (!edge) {
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
@@ -893,14 +902,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
             const float e1 = ex2_approx(fmaf(__uint_as_float(rw[q + 1]), k2, -k2));
             const float e2 = ex2_approx(fmaf(__uint_as_float(rw[q + 2]), k2, -k2));
             const float e3 = ex2_approx(fmaf(__uint_as_float(rw[q + 3]), k2, -k2));
-            const float f0 = (ci + c4.x) - (((l4.x == my_lo) != ps) ? (qi + q4.x) : 0.f);
-            const float f1 = (ci + c4.y) - (((l4.y == my_lo) != ps) ? (qi + q4.y) : 0.f);
-            const float f2 = (ci + c4.z) - (((l4.z == my_lo) != ps) ? (qi + q4.z) : 0.f);
-            const float f3 = (ci + c4.w) - (((l4.w == my_lo) != ps) ? (qi + q4.w) : 0.f);
-            rw[q] = __float_as_uint(tf32_rna(e0 * f0));
-            rw[q + 1] = __float_as_uint(tf32_rna(e1 * f1));
-            rw[q + 2] = __float_as_uint(tf32_rna(e2 * f2));
-            rw[q + 3] = __float_as_uint(tf32_rna(e3 * f3));
+            const float x0 = e0 * ((ci + c4.x) - (((l4.x == my_lo) != ps) ? (qi + q4.x) : 0.f));
+            const float x1 = e1 * ((ci + c4.y) - (((l4.y == my_lo) != ps) ? (qi + q4.y) : 0.f));
+            const float x2 = e2 * ((ci + c4.z) - (((l4.z == my_lo) != ps) ? (qi + q4.z) : 0.f));
+            const float x3 = e3 * ((ci + c4.w) - (((l4.w == my_lo) != ps) ? (qi + q4.w) : 0.f));
+            const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+            rw[q] = __float_as_uint(h0); rw[q + 1] = __float_as_uint(h1); rw[q + 2] = __float_as_uint(h2); rw[q + 3] = __float_as_uint(h3);
+            lw[q] = __float_as_uint(x0 - h0); lw[q + 1] = __float_as_uint(x1 - h1);
+            lw[q + 2] = __float_as_uint(x2 - h2); lw[q + 3] = __float_as_uint(x3 - h3);
           }
         } else {
 #pragma unroll
@@ -909,11 +918,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
             const float e = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
             const bool cand = (j < p.Bg) && (j != diag);
             const bool same = (lab_lo[c0 + q] == my_lo) && (lab_hi[c0 + q] == my_hi);
-            const float f = (ci + cj[c0 + q]) - ((same != ps) ? (qi + qj[c0 + q]) : 0.f);
-            rw[q] = __float_as_uint(cand ? tf32_rna(e * f) : 0.f);
+            const float x = cand ? e * ((ci + cj[c0 + q]) - ((same != ps) ? (qi + qj[c0 + q]) : 0.f)) : 0.f;
+            const float h = tf32_rna(x);
+            rw[q] = __float_as_uint(h);
+            lw[q] = __float_as_uint(x - h);
           }
         }
         tmem_st32(tcol + (uint32_t)c0, rw);
+        tmem_st32(tcol + (uint32_t)(BN + c0), lw);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -921,9 +933,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       if (lane == 0) mbar_arrive(&p_full[b]);
     }
     // ---- final: dN (TMEM) -> chain through the normalisation, add KL / reparam gradients
-    mbar_wait(dn_full, 0);
-    tc_fence_after();
-    if (half == 0) {
+    if (grp == 0) {
+      mbar_wait(dn_full, 0);
+      tc_fence_after();
       float acc[2 * DP];
 #pragma unroll
       for (int c0 = 0; c0 < 2 * DP; c0 += 16) {
