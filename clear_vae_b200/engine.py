@@ -82,6 +82,16 @@ def _stats(C, dev):
     return torch.zeros(2 * C, dtype=torch.float64, device=dev)
 
 
+def _reduce_stats(eng, st):
+    """SyncBN: sum the per-channel accumulators over the data-parallel group (SURVEY.md §8e "BN")."""
+    d = eng.dist
+    if eng.sync_bn and d is not None and d.world > 1:
+        import torch.distributed as td
+        td.all_reduce(st, group=d.group)
+        return d.world
+    return 1
+
+
 def _ws(dev):
     from .latent import _workspace
     return _workspace(dev, max(_ops.ops().bn_act_workspace_bytes(), 1 << 16))
@@ -120,7 +130,8 @@ class EncoderFn(torch.autograd.Function):
             ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
                           pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
             if eng.training:
-                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(B * H * H), gamma, beta, rm, rv,
+                nw = _reduce_stats(eng, st)
+                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
                                                              BN_MOMENTUM, BN_EPS, H * H if last else 1, eng.bn_repeat)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, H * H if last else 1)
@@ -179,7 +190,8 @@ class EncoderFn(torch.autograd.Function):
             H = sp.hout
             last = i == n - 1
             group = H * H if last else 1
-            coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, group, float(B * H * H), gamma, mean, invstd)
+            nw = _reduce_stats(eng, st)
+            coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, group, float(nw * B * H * H), gamma, mean, invstd)
             dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, BF16)
             dw = torch.zeros_like(w)
             if i == 0:
@@ -222,7 +234,8 @@ class DecoderFn(torch.autograd.Function):
                       [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
         rm, rv = eng.dec_fc_buffers
         if eng.training:
-            sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1, 1)
+            nw = _reduce_stats(eng, st)
+            sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1, 1)
         else:
             sc, sh, mean_fc, inv_fc = eng.eval_affine(fc_g, fc_beta, rm, rv, 1)
         C0, H0 = specs[0].cin, specs[0].hin
@@ -247,7 +260,8 @@ class DecoderFn(torch.autograd.Function):
                           pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS, None,
                           [0, 0, 0, 0], None, None, st)
             if eng.training:
-                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(B * H * H), gamma, beta, rm, rv,
+                nw = _reduce_stats(eng, st)
+                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
                                                              BN_MOMENTUM, BN_EPS, 1, 1)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, 1)
@@ -300,7 +314,8 @@ class DecoderFn(torch.autograd.Function):
             H = sp.hout
             last = j == n - 1
             inner = H * H if last else 1
-            coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(B * H * H), gamma, mean, invstd)
+            nw = _reduce_stats(eng, st)
+            coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(nw * B * H * H), gamma, mean, invstd)
             dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, BF16)
             dw = torch.zeros_like(w)
             if j == 0:
@@ -328,7 +343,8 @@ class DecoderFn(torch.autograd.Function):
         fg = linear_geom(K0, N0)
         st = eng.stat_buf(("dec_fc_b",), N0, dev)
         ops.bn_reduce(raw_fc, g_a, None, fc_aff[0], fc_aff[1], N0, 1, 1, st)  # ReLU mask recomputed from the raw fc output
-        coef, d_fc_g, d_fc_beta = ops.bn_bwd_coef(st, N0, 1, float(B), fc_g, mean_fc, inv_fc)
+        nw = _reduce_stats(eng, st)
+        coef, d_fc_g, d_fc_beta = ops.bn_bwd_coef(st, N0, 1, float(nw * B), fc_g, mean_fc, inv_fc)
         dy_fc = ops.bn_bwd_apply(g_a, raw_fc, None, fc_aff[0], fc_aff[1], coef, N0, 1, F32)
         d_fc_w = torch.zeros_like(fc_w)
         ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
@@ -352,6 +368,8 @@ class Engine:
         self.debug = None  # set to a dict to capture raw activations (tests / tools only)
         self.bn_repeat = 1    # momentum updates per encoder forward (see VAE.encode)
         self.stats_only = False
+        self.dist = None      # DistSpec for SyncBN
+        self.sync_bn = False
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev)

@@ -79,6 +79,7 @@ class VAE(nn.Module):
             self._engine = Engine(enc_specs, dec_specs)
         e = self._engine
         e.training = self.training
+        e.dist, e.sync_bn = getattr(self, "dist", None), bool(getattr(self, "sync_bn", False))
         e.enc_buffers = [(self.encoder[s.bn].running_mean, self.encoder[s.bn].running_var) for s in e.enc_specs]
         e.dec_buffers = [(self.decoder[s.bn].running_mean, self.decoder[s.bn].running_var) for s in e.dec_specs]
         e.dec_fc_buffers = (self.decoder[1].running_mean, self.decoder[1].running_var)

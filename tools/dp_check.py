@@ -1,0 +1,64 @@
+"""torchrun --nproc-per-node N tools/dp_check.py : data-parallel parity on real GPUs.
+(1) latent block: sharded rows + gathered columns == single-GPU result on the global batch (loss, row grads)
+(2) full CLEAR-VAE step with SyncBN: rank-averaged gradients == single-GPU gradients on the global batch (bf16 noise)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as td
+from clear_vae_b200.latent import DistSpec, latent_block
+from clear_vae_b200.models.vae import VAE
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+td.init_process_group("nccl", device_id=dev)
+dist = DistSpec(td.group.WORLD, rank, world)
+g = torch.Generator().manual_seed(1)
+for Bl, D in [(64, 8), (512, 32), (4096, 8)]:
+    Bg = Bl * world
+    mu_c, lv_c, mu_s, lv_s, e_c, e_s = ((torch.randn(Bg, D, generator=g) * s).to(dev) for s in (1, .3, 1, .3, 1, 1))
+    lab = torch.randint(0, 10, (Bg,), generator=g).to(dev)
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    full = [t.clone().requires_grad_(True) for t in (mu_c, lv_c, mu_s, lv_s)]
+    z, sc = latent_block([full[0], full[2]], [full[1], full[3]], [e_c, e_s], lab, snn=[1, 1], ps=[False, True], temperature=0.1)
+    w = torch.tensor([0.1, 0.1, 100.0, 100.0, 0, 0, 0, 0], device=dev)
+    torch.autograd.backward([sc], [w])
+    loc = [t[sl].clone().requires_grad_(True) for t in (mu_c, lv_c, mu_s, lv_s)]
+    z2, sc2 = latent_block([loc[0], loc[2]], [loc[1], loc[3]], [e_c[sl].contiguous(), e_s[sl].contiguous()], lab[sl].contiguous(),
+                           snn=[1, 1], ps=[False, True], temperature=0.1, dist=dist)
+    torch.autograd.backward([sc2], [w])
+    ok_loss = torch.allclose(sc2[2:4], sc[2:4], rtol=2e-6, atol=1e-7)
+    # SNN grads come back scaled by `world` (the trainers average over ranks afterwards); KL is a local mean over Bl rows
+    gm = loc[0].grad / world
+    ref = full[0].grad[sl]
+    kl_part_ref = 0.1 * full[0].detach()[sl] / Bg
+    kl_part_loc = 0.1 * loc[0].detach() / Bl / world
+    err = ((gm - kl_part_loc) - (ref - kl_part_ref)).abs().max() / ref.abs().max()
+    if rank == 0:
+        print(f"latent DP Bl={Bl} D={D} world={world}: loss match {bool(ok_loss)} ({sc2[2].item():.6f} vs {sc[2].item():.6f}), row-grad relerr {err.item():.2e}", flush=True)
+
+# ---- full model step with SyncBN
+torch.manual_seed(7)
+m1 = VAE(16, 3).to(dev); m1.train()
+m2 = VAE(16, 3).to(dev); m2.load_state_dict(m1.state_dict()); m2.train()
+m2.dist, m2.sync_bn = dist, True
+Bl = 64; Bg = Bl * world
+X = torch.rand(Bg, 3, 28, 28, generator=g).to(dev); lab = torch.randint(0, 10, (Bg,), generator=g).to(dev)
+eps = (torch.randn(Bg, 8, generator=g).to(dev), torch.randn(Bg, 8, generator=g).to(dev))
+w = torch.tensor([0.06, 0.06, 100.0, 100.0, 0, 0, 0, 0], device=dev)
+xh, rec, z, sc, _ = m1.fused_step_forward(X, lab, temperature=0.1, snn=[1, 1], ps=[False, True], eps=eps)
+torch.autograd.backward([rec, sc], [torch.ones_like(rec), w])
+sl = slice(rank * Bl, (rank + 1) * Bl)
+xh2, rec2, z2, sc2, _ = m2.fused_step_forward(X[sl].contiguous(), lab[sl].contiguous(), temperature=0.1, snn=[1, 1], ps=[False, True],
+                                              eps=(eps[0][sl].contiguous(), eps[1][sl].contiguous()), dist=dist)
+torch.autograd.backward([rec2, sc2], [torch.ones_like(rec2), w])
+worst = 0.0
+for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+    if p1.grad is None:
+        continue
+    g2 = p2.grad.clone(); td.all_reduce(g2); g2 /= world
+    e = ((g2 - p1.grad).norm() / (p1.grad.norm() + 1e-30)).item()
+    worst = max(worst, e)
+rec_g = rec2.clone(); td.all_reduce(rec_g); rec_g /= world
+if rank == 0:
+    print(f"model DP+SyncBN world={world}: recon {rec_g.item():.4f} vs {rec.item():.4f}; c_loss {sc2[2].item():.5f} vs {sc[2].item():.5f}; worst grad l2 relerr {worst:.2e}", flush=True)
+td.destroy_process_group()
