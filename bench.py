@@ -256,10 +256,24 @@ def main():
     for i in range(W):
         step_dev(i)
     barrier()
+    graphed = False
+    if not args.no_graph:
+        try:
+            tr.use_cuda_graph = True
+            for i in range(3):      # first call captures the device body of the step, the others replay it
+                step_dev(i)
+            barrier()
+            graphed = True
+        except Exception as e:      # capture is an optimisation, never a requirement
+            tr.use_cuda_graph = False
+            tr._graph = None
+            torch.cuda.synchronize()
+            print(f"[bench] CUDA-graph capture unavailable, running eagerly: {e!r}", file=sys.stderr, flush=True)
 
     # ---- one profiling pass: which of OUR kernels dominates the step?
     meter = _ops.meter
     meter.reset()
+    tr.use_cuda_graph = False   # per-kernel event timing needs the eager path (same kernels, same order)
     meter.timed = {"conv_gemm", "conv_wgrad", "latent_fwd", "latent_bwd", "bn_finalize", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd",
                    "bn_reduce", "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize"}
     for i in range(2):
@@ -271,6 +285,14 @@ def main():
     breakdown = {k: round(v[1] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     meter.reset()
     meter.timed = {dominant} if dominant else set()
+    for i in range(K):          # eager pass over the same K steps: live CUDA-event timing of the dominant kernel
+        step_dev(i)
+    torch.cuda.synchronize()
+    dom = meter.elapsed_ms().get(dominant, (0, 0.0))
+    eager_launches = meter.launches()
+    meter.reset()
+    meter.timed = set()
+    tr.use_cuda_graph = graphed
 
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local)
@@ -284,9 +306,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / K
     clocks = sampler.stop()
-    dom = meter.elapsed_ms().get(dominant, (0, 0.0))
-    launches = meter.launches()
-    meter.timed = set()
+    launches = tr._graph["launches"] * K if graphed else meter.launches()
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the step's scalars
     for i in range(2):
@@ -320,6 +340,7 @@ def main():
         ach = alg[dominant] / (per_step_ms * 1e-3) / 1e12
         roof = dict(kernel=dominant, bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=None,
                     launches_per_step=dom[0] // K, ms_per_step=per_step_ms, peak_source=pk["src"] + " bf16 sustained",
+                    timing="CUDA events around every launch of this kernel, eager pass over the same K steps",
                     algorithmic_gflop_per_step=alg[dominant] / 1e9)
     elif dominant is not None and dom[0] > 0:
         roof = dict(kernel=dominant, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None,
@@ -335,7 +356,7 @@ def main():
         line = dict(metric="train samples/sec", value=world * B / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload=WORKLOAD_NAMES[args.config], per_gpu_batch=B, global_batch=world * B,
-                                parallelism=f"dp{world}", l2=f"rotating {N_POOL} distinct input batches "
+                                parallelism=f"dp{world}", cuda_graph=graphed, l2=f"rotating {N_POOL} distinct input batches "
                                 f"({N_POOL * h2d / 1e6:.0f} MB) > 126 MB L2; activations are rewritten every step",
                                 bn="per-GPU batch statistics", conv_math="bf16 operands, fp32 accumulate (tcgen05)",
                                 latent_math="fp32"),

@@ -192,6 +192,8 @@ class EncoderFn(torch.autograd.Function):
             group = H * H if last else 1
             nw = _reduce_stats(eng, st)
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, group, float(nw * B * H * H), gamma, mean, invstd)
+            if nw > 1:  # sums were global: undo the later rank-averaging's double count of the affine grads
+                dgamma, dbeta = dgamma / nw, dbeta / nw
             dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, BF16)
             dw = torch.zeros_like(w)
             if i == 0:
@@ -316,6 +318,8 @@ class DecoderFn(torch.autograd.Function):
             inner = H * H if last else 1
             nw = _reduce_stats(eng, st)
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(nw * B * H * H), gamma, mean, invstd)
+            if nw > 1:
+                dgamma, dbeta = dgamma / nw, dbeta / nw
             dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, BF16)
             dw = torch.zeros_like(w)
             if j == 0:
@@ -345,6 +349,8 @@ class DecoderFn(torch.autograd.Function):
         ops.bn_reduce(raw_fc, g_a, None, fc_aff[0], fc_aff[1], N0, 1, 1, st)  # ReLU mask recomputed from the raw fc output
         nw = _reduce_stats(eng, st)
         coef, d_fc_g, d_fc_beta = ops.bn_bwd_coef(st, N0, 1, float(nw * B), fc_g, mean_fc, inv_fc)
+        if nw > 1:
+            d_fc_g, d_fc_beta = d_fc_g / nw, d_fc_beta / nw
         dy_fc = ops.bn_bwd_apply(g_a, raw_fc, None, fc_aff[0], fc_aff[1], coef, N0, 1, F32)
         d_fc_w = torch.zeros_like(fc_w)
         ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)

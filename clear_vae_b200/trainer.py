@@ -84,8 +84,10 @@ class VAETrainer(Trainer):
             X = self.transform(X)
         return X, label
 
-    def _weights(self, slope, alpha_c, alpha_s, dev):
-        """grad weights of the packed scalars (kl_c, kl_s, c, s, ...) for autograd.backward."""
+    # A step is split into a host part (annealer / weights, before and after) and a device body that is free of
+    # host decisions, so the body can be captured once in a CUDA graph and replayed (no tracing compiler involved).
+    def _set_weights(self, slope, alpha_c, alpha_s):
+        """grad weights of the packed scalars (kl_c, kl_s, c, s, ...) for autograd.backward, staged in pinned memory."""
         host = getattr(self, "_w_host", None)
         if host is None:
             host = torch.zeros(8, dtype=torch.float32)
@@ -93,7 +95,62 @@ class VAETrainer(Trainer):
                 host = host.pin_memory()
             self._w_host = host
         host[S_KL0], host[S_KL1], host[S_LOSS0], host[S_LOSS1] = slope, slope, alpha_c, alpha_s
-        return host.to(dev, non_blocking=True)
+
+    def _weights_dev(self, dev):
+        return self._w_host.to(dev, non_blocking=True)  # inside a graph: a memcpy node re-reading the pinned buffer
+
+    use_cuda_graph = False
+    _graph = None
+
+    def _needs_perm(self):
+        return False
+
+    def train_step(self, X, label, **inject):
+        """One iteration of the reference loop body.  With `use_cuda_graph` the device body is captured on first
+        use (per input shape) and replayed afterwards; injected noise / permutations force the eager path."""
+        self._host_pre()
+        if self.use_cuda_graph and not inject and X.is_cuda:
+            out = self._graph_step(X, label)
+        else:
+            out = self._device_step(X, label, **inject)
+        self.annealer.step()
+        return out
+
+    def _graph_step(self, X, label):
+        g = self._graph
+        if g is None or g["X"].shape != X.shape:
+            g = self._capture(X, label)
+        g["X"].copy_(X, non_blocking=True)
+        g["label"].copy_(label, non_blocking=True)
+        if g["perm"] is not None:  # CLUB-S: the CPU generator draws the permutation exactly like the reference
+            g["perm_host"].copy_(torch.randperm(X.shape[0]))
+            g["perm"].copy_(g["perm_host"], non_blocking=True)
+        g["graph"].replay()
+        return tuple(t.clone() for t in g["out"])  # the graph's output buffers are overwritten by the next replay
+
+    def _capture(self, X, label):
+        sX, sl = X.clone(), label.clone()
+        perm = perm_host = None
+        kw = {}
+        if self._needs_perm():
+            perm_host = torch.randperm(X.shape[0]).pin_memory()
+            perm = perm_host.to(X.device)
+            kw["perm"] = perm
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # optimiser state / workspaces / caches must exist before capture
+            for _ in range(2):
+                self._device_step(sX, sl, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        from . import _ops
+        before = _ops.meter.launches()
+        with torch.cuda.graph(graph):
+            out = self._device_step(sX, sl, **kw)
+        self._graph = dict(graph=graph, X=sX, label=sl, perm=perm, perm_host=perm_host, out=out,
+                           launches=_ops.meter.launches() - before)
+        return self._graph
 
     dist: DistSpec | None = None
 
@@ -118,19 +175,20 @@ class CLEARVAETrainer(VAETrainer):
         self.hyperparameter = hyperparameter
         self.annealer = LogisticAnnealer(loc=hyperparameter["loc"], scale=hyperparameter["scale"], beta=hyperparameter["beta"])
 
-    def train_step(self, X, label, eps=None):
-        """One iteration of the reference loop body (trainer.py:446-484); returns device scalars."""
+    def _host_pre(self):
+        # loss = recon + ann(kl_c) + ann(kl_s) + alpha*c + alpha*s, with s = -s_same when not ps (trainer.py:471-480)
+        ps, alpha = self.hyperparameter["ps"], self.hyperparameter["alpha"]
+        self._set_weights(self.annealer.slope(), alpha, alpha if ps else -alpha)
+
+    def _device_step(self, X, label, eps=None):
+        """Device body of one iteration (trainer.py:446-484); returns device scalars (recon, packed scalars)."""
         vae, hp = self.model, self.hyperparameter
-        ps, alpha = hp["ps"], hp["alpha"]
         self.optimizer.zero_grad()
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 1],
-                                                        ps=[False, bool(ps)], sim_fn=self.sim_fn, eps=eps, dist=self.dist)
-        # loss = recon + ann(kl_c) + ann(kl_s) + alpha*c + alpha*s, with s = -s_same when not ps (trainer.py:471-480)
-        w = self._weights(self.annealer.slope(), alpha, alpha if ps else -alpha, X.device)
-        torch.autograd.backward([recon, sc], [torch.ones_like(recon), w])
+                                                        ps=[False, bool(hp["ps"])], sim_fn=self.sim_fn, eps=eps, dist=self.dist)
+        torch.autograd.backward([recon, sc], [torch.ones_like(recon), self._weights_dev(X.device)])
         self._sync_grads(list(vae.parameters()))
         self.optimizer.step()
-        self.annealer.step()
         return recon, sc
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -181,7 +239,10 @@ class ClearTCVAETrainer(VAETrainer):
                 self._valid(valid_loader, verbose, epoch)
         return factor_d_losses
 
-    def train_step(self, X, label, eps=None, eps2=None):
+    def _host_pre(self):
+        self._set_weights(self.annealer.slope(), self.hyperparameter["alpha"], 0.0)
+
+    def _device_step(self, X, label, eps=None, eps2=None):
         vae, fc, hp = self.model, self.factor_cls, self.hyperparameter
         # --- VAE update (trainer.py:654-677)
         self.optimizer.zero_grad()
@@ -189,11 +250,9 @@ class ClearTCVAETrainer(VAETrainer):
                                                         sim_fn=self.sim_fn, eps=eps, dist=self.dist)
         d_score = fc(z)
         mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
-        w = self._weights(self.annealer.slope(), hp["alpha"], 0.0, X.device)
-        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), w, torch.full_like(mi, hp["lambda"])])
+        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         self._sync_grads(list(vae.parameters()))
         self.optimizer.step()
-        self.annealer.step()
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
@@ -246,7 +305,13 @@ class ClearMIMVAETrainer(VAETrainer):
                 self._valid(valid_loader, verbose, epoch)
         return mi_losses, mi_learning_losses
 
-    def train_step(self, X, label, eps=None, inner_eps=None, perm=None):
+    def _host_pre(self):
+        self._set_weights(self.annealer.slope(), self.hyperparameter["alpha"], 0.0)
+
+    def _needs_perm(self):
+        return isinstance(self.mi_estimator, CLUBSample)
+
+    def _device_step(self, X, label, eps=None, inner_eps=None, perm=None):
         vae, est, hp = self.model, self.mi_estimator, self.hyperparameter
         D = vae.z_dim
         # --- VAE update (trainer.py:848-871)
@@ -255,11 +320,9 @@ class ClearMIMVAETrainer(VAETrainer):
                                                         sim_fn=self.sim_fn, eps=eps, dist=self.dist)
         zc, zs = z[:, :D], z[:, D:]
         mi = est(zc, zs, perm) if (perm is not None and isinstance(est, CLUBSample)) else est(zc, zs)
-        w = self._weights(self.annealer.slope(), hp["alpha"], 0.0, X.device)
-        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), w, torch.full_like(mi, hp["lambda"])])
+        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         self._sync_grads(list(vae.parameters()))
         self.optimizer.step()
-        self.annealer.step()
         # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
         # The encoder is unchanged across the 5 iterations, so its output is computed once and its BatchNorm
         # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and

@@ -15,6 +15,14 @@ _ARCHS = {"VAE": VAE, "VAE64": VAE64}
 _ESTIMATORS = {"CLUBSample": CLUBSample, "L1OutUB": L1OutUB}
 
 
+def _adam(params, lr, device):
+    """`torch.optim.Adam(params, lr=lr)` like the reference factories; on CUDA the graph-capturable variant
+    (device-side step counters) so that a whole training step can be replayed as one CUDA graph."""
+    if torch.device(device).type == "cuda":
+        return torch.optim.Adam(params, lr=lr, capturable=True, foreach=True)
+    return torch.optim.Adam(params, lr=lr)
+
+
 def _arch(name):
     if name not in _ARCHS:
         raise NameError(f"name '{name}' is not defined")  # the reference resolves the string with eval()
@@ -24,7 +32,7 @@ def _arch(name):
 def get_clearvae_trainer(beta, ps, vae_lr, z_dim, alpha, temperature, device, vae_arch: str = "VAE", in_channel: int = 1,
                          verbose_period: int = 5):
     vae = _arch(vae_arch)(total_z_dim=z_dim, in_channel=in_channel).to(device)
-    optimizer = torch.optim.Adam(vae.parameters(), lr=vae_lr)
+    optimizer = _adam(vae.parameters(), vae_lr, device)
     return CLEARVAETrainer(vae, optimizer, sim_fn="cosine",
                            hyperparameter={"temperature": temperature, "alpha": alpha, "beta": beta, "ps": ps, "loc": 0,
                                            "scale": 1},
@@ -35,8 +43,8 @@ def get_cleartcvae_trainer(beta, la, vae_lr, factor_cls_lr, z_dim, alpha, temper
                            in_channel: int = 1, verbose_period: int = 5):
     vae = _arch(vae_arch)(total_z_dim=z_dim, in_channel=in_channel).to(device)
     factor_cls = nn.Sequential(nn.Linear(z_dim, z_dim), nn.ReLU(), nn.Linear(z_dim, 1), nn.Sigmoid()).to(device)
-    vae_optimizer = torch.optim.Adam(vae.parameters(), lr=vae_lr)
-    factor_optimizer = torch.optim.Adam(factor_cls.parameters(), lr=factor_cls_lr)
+    vae_optimizer = _adam(vae.parameters(), vae_lr, device)
+    factor_optimizer = _adam(factor_cls.parameters(), factor_cls_lr, device)
     return ClearTCVAETrainer(vae, factor_cls, optimizers={"vae_optim": vae_optimizer, "factor_optim": factor_optimizer},
                              sim_fn="cosine",
                              hyperparameter={"temperature": temperature, "alpha": alpha, "beta": beta, "loc": 0, "scale": 1,
@@ -50,8 +58,8 @@ def get_clearmimvae_trainer(beta, mi_estimator: str, la, vae_lr, mi_estimator_lr
     if mi_estimator not in _ESTIMATORS:
         raise NameError(f"name '{mi_estimator}' is not defined")
     est = _ESTIMATORS[mi_estimator](x_dim=z_dim // 2, y_dim=z_dim // 2, hidden_size=z_dim).to(device)
-    vae_optimizer = torch.optim.Adam(vae.parameters(), lr=vae_lr)
-    est_optimizer = torch.optim.Adam(est.parameters(), lr=mi_estimator_lr)
+    vae_optimizer = _adam(vae.parameters(), vae_lr, device)
+    est_optimizer = _adam(est.parameters(), mi_estimator_lr, device)
     return ClearMIMVAETrainer(vae, est, optimizers={"vae_optim": vae_optimizer, "mi_estimator_optim": est_optimizer},
                               sim_fn="cosine",
                               hyperparameter={"temperature": temperature, "beta": beta, "loc": 0, "scale": 1, "alpha": alpha,

@@ -58,6 +58,8 @@ for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
     g2 = p2.grad.clone(); td.all_reduce(g2); g2 /= world
     e = ((g2 - p1.grad).norm() / (p1.grad.norm() + 1e-30)).item()
     worst = max(worst, e)
+    if rank == 0 and e > 5e-2:
+        print("   large deviation:", k, e, flush=True)
 rec_g = rec2.clone(); td.all_reduce(rec_g); rec_g /= world
 if rank == 0:
     print(f"model DP+SyncBN world={world}: recon {rec_g.item():.4f} vs {rec.item():.4f}; c_loss {sc2[2].item():.5f} vs {sc[2].item():.5f}; worst grad l2 relerr {worst:.2e}", flush=True)
