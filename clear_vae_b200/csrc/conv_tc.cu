@@ -32,6 +32,8 @@ using cvplan::Plan;
 constexpr int BM = 128, BK = 64, NS = 4;
 constexpr int kAStage = BM * BK * 2;  // 16 KiB
 constexpr int kThreads = 192;
+constexpr int kTabMax = 256;    // entries of the k -> (tap, channel) table used by the scalar gather
+constexpr int kMaxPreC = 2048;  // source channels whose BatchNorm scale/shift are staged in shared memory
 
 struct TmapPack {
   CUtensorMap t[cvplan::kMaxClasses];
@@ -88,6 +90,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   uint64_t* empty = full + NS;
   uint64_t* tmem_full = empty + NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  int4* sTab = reinterpret_cast<int4*>(tmem_slot + 4);                  // k -> (tap, channel, -, -) for the scalar gather
+  float* sScale = reinterpret_cast<float*>(sTab + kTabMax);             // pre-op scale / shift of the source channels
+  float* sShift = sScale + kMaxPreC;
 
   const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const Cls& c = p.plan.cls[cls_id];
@@ -112,6 +117,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  {
+    const int Cs = p.plan.Cs;
+    if (p.pre_scale != nullptr)
+      for (int i = threadIdx.x; i < Cs; i += kThreads) { sScale[i] = __ldg(p.pre_scale + i); sShift[i] = __ldg(p.pre_shift + i); }
+    const int Kreal = c.ntaps * Cs;
+    for (int k = threadIdx.x; k < kTabMax && k < Kreal; k += kThreads) { const int t = k / Cs; sTab[k] = make_int4(t, k - t * Cs, 0, 0); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,67 +144,103 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const long long img_off = img * p.s_n;
     // incremental (tap, channel) of the next 8-chunk (vector path)
     int t_cur = vec ? (kb0 * BK) / Cs : 0, c_cur = vec ? (kb0 * BK) % Cs : 0;
+    const bool has_pre = p.pre_scale != nullptr;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % NS;
-      mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
       unsigned char* a_st = sA + s * kAStage;
+      if (vec) {
+        // ---- phase 1: addresses + ALL loads of the k-block in flight (clamped address, masked afterwards)
+        uint4 q0[8], q1[8];
+        int cch[8];
+        bool ok[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kg = (kb0 + kb) * BK + j * 8;
-        uint4 out = make_uint4(0u, 0u, 0u, 0u);
-        if (vec) {
-          if (kg < Kreal && mvalid) {
+        for (int j = 0; j < 8; ++j) {
+          const int kg = (kb0 + kb) * BK + j * 8;
+          bool v = mvalid && kg < Kreal;
+          long long off = 0;
+          if (v) {
             const int hs = hbase + c.dh[t_cur], ws = wbase + c.dw[t_cur];
-            if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
-              const long long off = img_off + hs * p.s_h + ws * p.s_w + c_cur;
-              float v[8];
-              if (p.src_bf16) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-              } else {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off + 4));
-                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-              }
-              if (p.pre_scale != nullptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + c_cur));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + c_cur + 4));
-                const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + c_cur));
-                const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + c_cur + 4));
-                v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-                v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-              }
-              if (p.pre_relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-              }
-              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
+            v = hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws;
+            off = v ? img_off + hs * p.s_h + ws * p.s_w + c_cur : 0;
+          }
+          ok[j] = v;
+          cch[j] = c_cur;
+          if (p.src_bf16) {
+            q0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
+          } else {
+            q0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off));
+            q1[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off + 4));
           }
           c_cur += 8;
           if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
-        } else {
+        }
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        // ---- phase 2: BatchNorm-apply + ReLU (scale/shift from shared memory), bf16 pack, 16-byte stores
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
           float v[8];
+          if (p.src_bf16) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q0[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+          } else {
+            v[0] = __uint_as_float(q0[j].x); v[1] = __uint_as_float(q0[j].y); v[2] = __uint_as_float(q0[j].z); v[3] = __uint_as_float(q0[j].w);
+            v[4] = __uint_as_float(q1[j].x); v[5] = __uint_as_float(q1[j].y); v[6] = __uint_as_float(q1[j].z); v[7] = __uint_as_float(q1[j].w);
+          }
+          if (has_pre) {
+            const float4 s0 = *reinterpret_cast<const float4*>(sScale + cch[j]);
+            const float4 s1 = *reinterpret_cast<const float4*>(sScale + cch[j] + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sShift + cch[j]);
+            const float4 h1 = *reinterpret_cast<const float4*>(sShift + cch[j] + 4);
+            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+          }
+          if (p.pre_relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          uint4 out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          if (!ok[j]) out = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = out;
+        }
+      } else {
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          const int kg = (kb0 + kb) * BK + j * 8;
+          float v[8];
+          bool ok[8];
+          int chn[8];
+          // phase 1: eight independent loads (k -> (tap, channel, offset) from the shared-memory table)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int k = kg + i;
-            float x = 0.f;
-            if (k < Kreal && mvalid) {
-              const int t = k / Cs, ch = k - t * Cs;
+            bool vld = mvalid && k < Kreal;
+            long long off = 0;
+            int ch = 0;
+            if (vld) {
+              int t, koff;
+              if (k < kTabMax) { const int4 e = sTab[k]; t = e.x; ch = e.y; koff = e.z; }
+              else { t = k / Cs; ch = k - t * Cs; koff = 0; }
               const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
-              if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
-                x = ld_elem(p.src, img_off + hs * p.s_h + ws * p.s_w + ch * p.s_c, p.src_bf16);
-                if (p.pre_scale != nullptr) x = fmaf(x, __ldg(p.pre_scale + ch), __ldg(p.pre_shift + ch));
-                if (p.pre_relu) x = fmaxf(x, 0.f);
-              }
+              vld = hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws;
+              (void)koff;
+              off = vld ? img_off + hs * p.s_h + ws * p.s_w + ch * p.s_c : 0;
             }
-            v[i] = x;
+            ok[i] = vld;
+            chn[i] = ch;
+            v[i] = ld_elem(p.src, off, p.src_bf16);
           }
-          out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x = v[i];
+            if (has_pre) x = fmaf(x, sScale[chn[i]], sShift[chn[i]]);
+            if (p.pre_relu) x = fmaxf(x, 0.f);
+            v[i] = ok[i] ? x : 0.f;
+          }
+          *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
-        *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = out;
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
@@ -399,83 +447,120 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
       const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
       const long long img_off = img * p.s_n;
       const long long dy_off = img * p.y_n + (long long)(hd * p.plan.os + c.oa) * p.y_h + (long long)(wd * p.plan.os + c.ob) * p.y_w;
-      mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
       unsigned char* a_st = sA + s * kWStageA;
       unsigned char* b_st = sB + s * kBStage;
-      // ---- A: gathered activation, mn-groups hf*8 .. hf*8+7
+      constexpr int NG = BN / 8, NGH = (NG + 1) / 2;
+      const bool dyvec = p.y_c == 1;
+      // ---- phase 1: every load of this k-block in flight before the stage is even free
+      uint4 qa0[8], qa1[8], qb0[NGH], qb1[NGH];
+      bool oka[8], okb[NGH];
+      int cha[8];
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kidx = k0 + (hf * 8 + j) * 8;
+          bool v = mvalid && kidx < Kreal;
+          long long off = 0;
+          int ch = 0;
+          if (v) {
+            const int t = kidx / Cs;
+            ch = kidx - t * Cs;
+            const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+            v = hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws;
+            off = v ? img_off + hs * p.s_h + ws * p.s_w + ch : 0;
+          }
+          oka[j] = v;
+          cha[j] = ch;
+          if (p.src_bf16) {
+            qa0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
+          } else {
+            qa0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off));
+            qa1[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off + 4));
+          }
+        }
+      }
+      if (dyvec) {
+#pragma unroll
+        for (int j = 0; j < NGH; ++j) {
+          const int grp = hf * NGH + j;
+          const int n = n0 + grp * 8;
+          const bool v = mvalid && grp < NG && n + 8 <= Nn;
+          okb[j] = v;
+          const long long off = v ? dy_off + n : 0;
+          if (p.dy_bf16) {
+            qb0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + off));
+          } else {
+            qb0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.dy) + off));
+            qb1[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.dy) + off + 4));
+          }
+        }
+      }
+      mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+      // ---- phase 2a: A = gathered activation (BatchNorm-apply + ReLU), mn-groups hf*8 .. hf*8+7
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int grp = hf * 8 + j;
         const int kidx = k0 + grp * 8;
         uint4 out = make_uint4(0u, 0u, 0u, 0u);
-        if (mvalid && kidx < Kreal) {
-          float v[8];
-          if (vec) {
-            const int t = kidx / Cs, ch = kidx - t * Cs;
-            const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
-            if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
-              const long long off = img_off + hs * p.s_h + ws * p.s_w + ch;
-              if (p.src_bf16) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+        float v[8];
+        if (vec) {
+          if (p.src_bf16) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qa0[j]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-              } else {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src) + off + 4));
-                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (p.pre_scale != nullptr) v[i] = fmaf(v[i], __ldg(p.pre_scale + ch + i), __ldg(p.pre_shift + ch + i));
-                if (p.pre_relu) v[i] = fmaxf(v[i], 0.f);
-              }
-              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
+            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
           } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int kk = kidx + i;
-              float x = 0.f;
-              if (kk < Kreal) {
-                const int t = kk / Cs, ch = kk - t * Cs;
-                const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
-                if (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) {
-                  x = ld_elem(p.src, img_off + hs * p.s_h + ws * p.s_w + ch * p.s_c, p.src_bf16);
-                  if (p.pre_scale != nullptr) x = fmaf(x, __ldg(p.pre_scale + ch), __ldg(p.pre_shift + ch));
-                  if (p.pre_relu) x = fmaxf(x, 0.f);
-                }
-              }
-              v[i] = x;
-            }
-            out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            v[0] = __uint_as_float(qa0[j].x); v[1] = __uint_as_float(qa0[j].y); v[2] = __uint_as_float(qa0[j].z); v[3] = __uint_as_float(qa0[j].w);
+            v[4] = __uint_as_float(qa1[j].x); v[5] = __uint_as_float(qa1[j].y); v[6] = __uint_as_float(qa1[j].z); v[7] = __uint_as_float(qa1[j].w);
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (p.pre_scale != nullptr) v[i] = fmaf(v[i], __ldg(p.pre_scale + cha[j] + i), __ldg(p.pre_shift + cha[j] + i));
+            if (p.pre_relu) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (oka[j]) out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        } else if (mvalid && kidx < Kreal) {
+          bool okk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int kk = kidx + i;
+            bool vld = kk < Kreal;
+            long long off = 0;
+            int ch = 0;
+            if (vld) {
+              const int t = kk / Cs;
+              ch = kk - t * Cs;
+              const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+              vld = hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws;
+              off = vld ? img_off + hs * p.s_h + ws * p.s_w + ch * p.s_c : 0;
+            }
+            okk[i] = vld;
+            cha[0] = ch;
+            float x = ld_elem(p.src, off, p.src_bf16);
+            if (p.pre_scale != nullptr) x = fmaf(x, __ldg(p.pre_scale + ch), __ldg(p.pre_shift + ch));
+            if (p.pre_relu) x = fmaxf(x, 0.f);
+            v[i] = vld ? x : 0.f;
+          }
+          (void)okk;
+          out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
         *reinterpret_cast<uint4*>(a_st + grp * (WK * 16) + px * 16) = out;
       }
-      // ---- B: dy rows, n-groups split between the two halves
-      constexpr int NG = BN / 8;
+      // ---- phase 2b: B = dy rows, n-groups split between the two halves
 #pragma unroll
-      for (int j = 0; j < (NG + 1) / 2; ++j) {
-        const int grp = hf * ((NG + 1) / 2) + j;
+      for (int j = 0; j < NGH; ++j) {
+        const int grp = hf * NGH + j;
         if (grp < NG) {
           const int n = n0 + grp * 8;
           uint4 out = make_uint4(0u, 0u, 0u, 0u);
-          if (mvalid && n < Nn) {
-            if (p.y_c == 1 && n + 8 <= Nn) {
-              if (p.dy_bf16) {
-                out = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + dy_off + n));
-              } else {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + dy_off + n));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + dy_off + n + 4));
-                out = make_uint4(pack_bf16(q0.x, q0.y), pack_bf16(q0.z, q0.w), pack_bf16(q1.x, q1.y), pack_bf16(q1.z, q1.w));
-              }
-            } else {
-              float v[8];
+          if (dyvec && okb[j]) {
+            if (p.dy_bf16) out = qb0[j];
+            else out = make_uint4(pack_bf16(__uint_as_float(qb0[j].x), __uint_as_float(qb0[j].y)), pack_bf16(__uint_as_float(qb0[j].z), __uint_as_float(qb0[j].w)),
+                                  pack_bf16(__uint_as_float(qb1[j].x), __uint_as_float(qb1[j].y)), pack_bf16(__uint_as_float(qb1[j].z), __uint_as_float(qb1[j].w)));
+          } else if (mvalid && n < Nn && !(dyvec && n + 8 <= Nn)) {
+            float v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = (n + i < Nn) ? ld_elem(p.dy, dy_off + (n + i) * p.y_c, p.dy_bf16) : 0.f;
-              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
+            for (int i = 0; i < 8; ++i) v[i] = (n + i < Nn) ? ld_elem(p.dy, dy_off + (n + i) * p.y_c, p.dy_bf16) : 0.f;
+            out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
           *reinterpret_cast<uint4*>(b_st + grp * (WK * 16) + px * 16) = out;
         }
@@ -583,7 +668,7 @@ inline int pick_bn(int Nn) {
 
 template <int BN>
 int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + (2 * NS + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + (2 * NS + 1) * 8 + 32 + kTabMax * 16 + 2 * kMaxPreC * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -681,6 +766,7 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   if ((uintptr_t)packed_weight & 127) return CLEARVAE_EINVAL;
   GemmParams p{};
   if (!cvplan::make_plan(*g, role, BK, &p.plan)) return CLEARVAE_EUNSUPPORTED;
+  if (pre_scale != nullptr && p.plan.Cs > kMaxPreC) return CLEARVAE_EUNSUPPORTED;
   EncodeTiledFn enc = get_encode();
   if (!enc) return CLEARVAE_EUNSUPPORTED;
   const int BN = pick_bn(p.plan.Nn);
