@@ -245,7 +245,8 @@ __global__ void bn_bwd_coef_kernel(double* stats, int C, int group, double count
 __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_bf, const void* y, int y_bf, const void* act,
                                                            int act_bf, const float* __restrict__ mscale,
                                                            const float* __restrict__ mshift, const float* __restrict__ coef,
-                                                           long long total, int C, long long inner, void* dy, int dy_bf) {
+                                                           long long total, int C, long long inner, int to_nhwc, void* dy,
+                                                           int dy_bf) {
   for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < total; i += (long long)gridDim.x * kNT) {
     const int ch = (int)((i / inner) % C);
     float gv = ldf(g, i, g_bf);
@@ -253,7 +254,12 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_
     if (act != nullptr && !(ldf(act, i, act_bf) > 0.f)) gv = 0.f;
     if (mscale != nullptr && !(fmaf(yv, __ldg(mscale + ch), __ldg(mshift + ch)) > 0.f)) gv = 0.f;
     const float v = fmaf(__ldg(coef + ch), gv, fmaf(__ldg(coef + C + ch), yv, __ldg(coef + 2 * C + ch)));
-    stf(dy, i, dy_bf, v);
+    long long o = i;
+    if (to_nhwc) {  // channel-major [b][c][hw] -> channels-last [b][hw][c] so the consumers gather 16-byte channel runs
+      const long long per = (long long)C * inner, b = i / per;
+      o = b * per + (i % inner) * C + ch;
+    }
+    stf(dy, o, dy_bf, v);
   }
 }
 
@@ -356,10 +362,10 @@ int clearvae_bn_bwd_coef(double* stats, int32_t C, int32_t group, double count, 
 
 int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t y_dtype, const void* act, int32_t act_dtype,
                           const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
-                          int64_t inner, void* dy, int32_t dy_dtype, void* stream) {
+                          int64_t inner, int32_t to_nhwc, void* dy, int32_t dy_dtype, void* stream) {
   if (!g || !y || !coef || !dy || total <= 0 || C <= 0 || inner <= 0) return CLEARVAE_EINVAL;
   bn_bwd_apply_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(g, g_dtype, y, y_dtype, act, act_dtype, mask_scale,
-                                                                         mask_shift, coef, total, C, inner, dy, dy_dtype);
+                                                                         mask_shift, coef, total, C, inner, to_nhwc, dy, dy_dtype);
   CV_LAUNCH_CHECK();
   return 0;
 }

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   uint64_t* empty = full + NS;
   uint64_t* tmem_full = empty + NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  int4* sTab = reinterpret_cast<int4*>(tmem_slot + 4);                  // k -> (tap, channel, -, -) for the scalar gather
+  int4* sTab = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(full) + 96);  // 16-byte aligned; k -> (tap, channel)
   float* sScale = reinterpret_cast<float*>(sTab + kTabMax);             // pre-op scale / shift of the source channels
   float* sShift = sScale + kMaxPreC;
 
@@ -322,14 +322,24 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
           }
         }
       }
-      // ---- per-channel statistics
+      // ---- per-channel statistics: warp transpose-reduce, then across the 4 epilogue warps in shared
+      //      memory, so one double atomic per column per CTA reaches L2
       if (p.stats != nullptr) {
         transpose_reduce32(v);
         transpose_reduce32(u);
-        const int n = n0 + ch0 + lane;
-        if (lane < CH && n < Nn) {
-          atomicAdd(p.stats + n, (double)v[0]);
-          atomicAdd(p.stats + Nn + n, (double)u[0]);
+        float* sSt = sScale;  // the pre-op staging area is dead once the producers are done with the main loop
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        sSt[(warp * 2 + 0) * 32 + lane] = v[0];
+        sSt[(warp * 2 + 1) * 32 + lane] = u[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0) {
+          const int n = n0 + ch0 + lane;
+          if (lane < CH && n < Nn) {
+            const float a = (sSt[lane] + sSt[64 + lane]) + (sSt[128 + lane] + sSt[192 + lane]);
+            const float b = (sSt[32 + lane] + sSt[96 + lane]) + (sSt[160 + lane] + sSt[224 + lane]);
+            atomicAdd(p.stats + n, (double)a);
+            atomicAdd(p.stats + Nn + n, (double)b);
+          }
         }
       }
     }
@@ -405,6 +415,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
   uint64_t* empty = full + NS;
   uint64_t* tmem_full = empty + NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* sScale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full) + 96);
+  float* sShift = sScale + kMaxPreC;
 
   const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const Cls& c = p.plan.cls[cls_id];
@@ -426,6 +438,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
     fence_barrier_init();
   }
   if (warp == 4) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  if (p.pre_scale != nullptr)
+    for (int i = threadIdx.x; i < Cs; i += kThreads) { sScale[i] = __ldg(p.pre_scale + i); sShift[i] = __ldg(p.pre_shift + i); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -512,10 +526,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
             v[0] = __uint_as_float(qa0[j].x); v[1] = __uint_as_float(qa0[j].y); v[2] = __uint_as_float(qa0[j].z); v[3] = __uint_as_float(qa0[j].w);
             v[4] = __uint_as_float(qa1[j].x); v[5] = __uint_as_float(qa1[j].y); v[6] = __uint_as_float(qa1[j].z); v[7] = __uint_as_float(qa1[j].w);
           }
+          if (p.pre_scale != nullptr) {
+            const float4 s0 = *reinterpret_cast<const float4*>(sScale + cha[j]), s1 = *reinterpret_cast<const float4*>(sScale + cha[j] + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sShift + cha[j]), h1 = *reinterpret_cast<const float4*>(sShift + cha[j] + 4);
+            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+          }
+          if (p.pre_relu) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (p.pre_scale != nullptr) v[i] = fmaf(v[i], __ldg(p.pre_scale + cha[j] + i), __ldg(p.pre_shift + cha[j] + i));
-            if (p.pre_relu) v[i] = fmaxf(v[i], 0.f);
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (oka[j]) out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         } else if (mvalid && kidx < Kreal) {
@@ -536,7 +555,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
             okk[i] = vld;
             cha[0] = ch;
             float x = ld_elem(p.src, off, p.src_bf16);
-            if (p.pre_scale != nullptr) x = fmaf(x, __ldg(p.pre_scale + ch), __ldg(p.pre_shift + ch));
+            if (p.pre_scale != nullptr) x = fmaf(x, sScale[ch], sShift[ch]);
             if (p.pre_relu) x = fmaxf(x, 0.f);
             v[i] = vld ? x : 0.f;
           }
@@ -668,7 +687,7 @@ inline int pick_bn(int Nn) {
 
 template <int BN>
 int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + (2 * NS + 1) * 8 + 32 + kTabMax * 16 + 2 * kMaxPreC * 4 + 1024;
+  constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + 96 /*barriers + tmem slot*/ + kTabMax * 16 + 2 * kMaxPreC * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -687,7 +706,7 @@ void fill_t4(const clearvae_tensor4* t, const void*& ptr, long long& sn, long lo
 
 template <int BN>
 int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = NS * kWStageA + NS * BN * WK * 2 + (2 * NS + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = NS * kWStageA + NS * BN * WK * 2 + 96 + 2 * kMaxPreC * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -709,6 +728,7 @@ int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearv
   if ((pre_scale == nullptr) != (pre_shift == nullptr)) return CLEARVAE_EINVAL;
   WgradParams p{};
   if (!cvplan::make_plan(*g, cvplan::kFprop, BK, &p.plan)) return CLEARVAE_EUNSUPPORTED;
+  if (pre_scale != nullptr && p.plan.Cs > kMaxPreC) return CLEARVAE_EUNSUPPORTED;
   const int BN = pick_bn(p.plan.Nn);
   const int n_pad = (p.plan.Nn + 15) / 16 * 16;
   p.batch = batch;

@@ -369,7 +369,7 @@ std::tuple<Tensor, Tensor, Tensor> bn_bwd_coef(Tensor stats, int64_t C, int64_t 
 }
 
 Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, const OptTensor& mscale, const OptTensor& mshift,
-                    const Tensor& coef, int64_t C, int64_t inner, int64_t out_dtype) {
+                    const Tensor& coef, int64_t C, int64_t inner, bool to_nhwc, int64_t out_dtype) {
   const c10::cuda::CUDAGuard guard(g.device());
   check_f32(coef, "coef");
   TORCH_CHECK(g.numel() == y.numel(), "clearvae: g / y size mismatch");
@@ -377,7 +377,7 @@ Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, cons
   Tensor dy = at::empty(y.sizes(), y.options().dtype(out_dtype == CLEARVAE_BF16 ? at::kBFloat16 : at::kFloat));
   check_rc(clearvae_bn_bwd_apply(g.data_ptr(), dt_of(g, "g"), y.data_ptr(), dt_of(y, "y"), ha ? act->data_ptr() : nullptr,
                                  ha ? dt_of(*act, "act") : 0, optf(mscale, "mask_scale"), optf(mshift, "mask_shift"),
-                                 coef.data_ptr<float>(), g.numel(), (int32_t)C, inner, dy.data_ptr(),
+                                 coef.data_ptr<float>(), g.numel(), (int32_t)C, inner, to_nhwc ? 1 : 0, dy.data_ptr(),
                                  (int32_t)out_dtype, cur_stream()),
            "bn_bwd_apply");
   return dy;
@@ -420,7 +420,7 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("sigmoid_mse_bwd(Tensor xhat, Tensor x, Tensor? grad_recon, Tensor? grad_ext, Tensor raw, int C, int inner, int batch, "
         "Tensor(a!) stats) -> Tensor");
   m.def("bn_bwd_coef(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor mean, Tensor invstd) -> (Tensor, Tensor, Tensor)");
-  m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, Tensor coef, int C, int inner, int out_dtype) -> Tensor");
+  m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, Tensor coef, int C, int inner, bool to_nhwc, int out_dtype) -> Tensor");
   m.def("colsum(Tensor x) -> Tensor");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "

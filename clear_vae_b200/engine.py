@@ -194,7 +194,10 @@ class EncoderFn(torch.autograd.Function):
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, group, float(nw * B * H * H), gamma, mean, invstd)
             if nw > 1:  # sums were global: undo the later rank-averaging's double count of the affine grads
                 dgamma, dbeta = dgamma / nw, dbeta / nw
-            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, BF16)
+            # the last block's tensors are channel-major (flatten order of the heads); its dy is written channels-last
+            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, last, BF16)
+            if last:
+                raw_strides = nhwc_strides(H, H, sp.cout)
             dw = torch.zeros_like(w)
             if i == 0:
                 src, src_strides, pre = x, nchw_strides(sp.cin, sp.hin, sp.hin), None
@@ -320,7 +323,7 @@ class DecoderFn(torch.autograd.Function):
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(nw * B * H * H), gamma, mean, invstd)
             if nw > 1:
                 dgamma, dbeta = dgamma / nw, dbeta / nw
-            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, BF16)
+            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, False, BF16)
             dw = torch.zeros_like(w)
             if j == 0:
                 src, src_strides, pre = a_fc, nhwc_strides(sp.hin, sp.hin, sp.cin), None
@@ -351,7 +354,7 @@ class DecoderFn(torch.autograd.Function):
         coef, d_fc_g, d_fc_beta = ops.bn_bwd_coef(st, N0, 1, float(nw * B), fc_g, mean_fc, inv_fc)
         if nw > 1:
             d_fc_g, d_fc_beta = d_fc_g / nw, d_fc_beta / nw
-        dy_fc = ops.bn_bwd_apply(g_a, raw_fc, None, fc_aff[0], fc_aff[1], coef, N0, 1, F32)
+        dy_fc = ops.bn_bwd_apply(g_a, raw_fc, None, fc_aff[0], fc_aff[1], coef, N0, 1, False, F32)
         d_fc_w = torch.zeros_like(fc_w)
         ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
         dz = torch.empty(B, K0, dtype=torch.float32, device=dev)

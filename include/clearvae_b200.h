@@ -205,7 +205,8 @@ int clearvae_bn_bwd_coef(double* stats, int32_t C, int32_t group, double count, 
                          const float* save_invstd, float* coef, float* dgamma, float* dbeta, void* stream);
 int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t y_dtype, const void* act, int32_t act_dtype,
                           const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
-                          int64_t inner, void* dy, int32_t dy_dtype, void* stream);
+                          int64_t inner, int32_t to_nhwc /* write [b][hw][c] instead of [b][c][hw] */, void* dy,
+                          int32_t dy_dtype, void* stream);
 /* out[c] = sum_r x[r][c]  (bias gradients of the linear heads) */
 int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 
