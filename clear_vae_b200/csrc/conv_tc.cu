@@ -31,8 +31,8 @@ using cvplan::Plan;
 
 constexpr int BM = 128, BK = 64, NS = 4;
 constexpr int kAStage = BM * BK * 2;  // 16 KiB
-constexpr int kThreads = 448;   // conv GEMM: 2 x 4 producer warps (alternating k-blocks), TMA, MMA, 4 epilogue warps
-constexpr int kWThreads = 192;  // wgrad GEMM: 4 producer/epilogue warps, (idle), MMA
+constexpr int kThreads = 192;
+constexpr int kTabMax = 256;    // entries of the k -> (tap, channel) table used by the scalar gather
 constexpr int kMaxPreC = 2048;  // source channels whose BatchNorm scale/shift are staged in shared memory
 
 struct TmapPack {
@@ -50,9 +50,7 @@ struct GemmParams {
   const void* msk; long long m_n, m_h, m_w, m_c; int msk_bf16;
   const float *msk_scale, *msk_shift;
   double* stats;
-  int splits;  // split-K (fp32 atomic epilogue); 1 = off
-  int n_tiles, n_ntiles;                     // persistent scheduler: total work items, n-tiles per m-tile
-  int tile_start[cvplan::kMaxClasses];       // first work item of each class
+  int splits;  // split-K over grid.z (fp32 atomic epilogue); 1 = off
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -79,425 +77,321 @@ __device__ __forceinline__ void transpose_reduce32(float (&v)[32]) {
   }
 }
 
-// ---- persistent tile scheduler -------------------------------------------------------
-struct Tile {
-  int cls, split, n0, kb0, nkb;
-  long long m0;
-};
-__device__ __forceinline__ bool get_tile(const GemmParams& p, int tile_id, int BN, Tile* t) {
-  if (tile_id >= p.n_tiles) return false;
-  int cls = 0;
-#pragma unroll
-  for (int i = 1; i < cvplan::kMaxClasses; ++i)
-    if (i < p.plan.n_classes && tile_id >= p.tile_start[i]) cls = i;
-  int local = tile_id - p.tile_start[cls];
-  const int nt = local % p.n_ntiles;
-  local /= p.n_ntiles;
-  const int split = local % p.splits;
-  const int mt = local / p.splits;
-  const int nkb_all = p.plan.cls[cls].Kp / BK;
-  t->cls = cls; t->split = split; t->n0 = nt * BN; t->m0 = (long long)mt * BM;
-  t->kb0 = nkb_all * split / p.splits;
-  t->nkb = nkb_all * (split + 1) / p.splits - t->kb0;
-  return true;
-}
-
-struct RowCtx {
-  bool mvalid;
-  int hd, wd;
-  long long img, base;
-  unsigned tapmask;
-};
-__device__ __forceinline__ void decode_row(const GemmParams& p, const Cls& c, long long m, RowCtx* r) {
-  const long long Mc = p.batch * c.Hd * c.Wd;
-  r->mvalid = m < Mc;
-  const long long mm = r->mvalid ? m : 0;
-  r->wd = (int)(mm % c.Wd);
-  r->hd = (int)((mm / c.Wd) % c.Hd);
-  r->img = mm / ((long long)c.Wd * c.Hd);
-  const int hbase = r->hd * p.plan.sh, wbase = r->wd * p.plan.sh;
-  r->base = r->img * p.s_n + hbase * p.s_h + wbase * p.s_w;
-  unsigned mask = 0;
-  if (r->mvalid) {
-#pragma unroll 1
-    for (int t = 0; t < c.ntaps; ++t) {
-      const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
-      mask |= (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) ? (1u << t) : 0u;
-    }
-  }
-  r->tapmask = mask;
-}
-
-// rare: scalar-gather layers whose K exceeds the table (kept out of line so the hot loop stays small)
-__device__ __noinline__ void slow_k_lookup(const GemmParams& p, const Cls& c, int k, int Cs, int* t, int* ch, int* koff) {
-  *t = k / Cs;
-  *ch = k - *t * Cs;
-  *koff = (int)(c.dh[*t] * p.s_h + c.dw[*t] * p.s_w + *ch * p.s_c);
-}
-
-constexpr int kTabPerCls = 64;   // k -> (tap, channel, offset) entries per class for the scalar gather (K <= 64 there)
-
-// Persistent, warp-specialised implicit-GEMM kernel.  Each CTA walks a static round-robin list of
-// (class, m-tile, split, n-tile) work items; producers, the TMA warp, the MMA warp and the epilogue
-// warps each run that list on their own, coupled only through mbarriers:
-//   smem stage ring   full[NS] / empty[NS]          (producers + TMA  ->  MMA)
-//   TMEM accumulators acc_full[2] / acc_empty[2]    (MMA -> epilogue), double buffered so the epilogue of
-//                                                   tile i overlaps the gather + MMA of tile i+1.
-template <int BN, bool SRC_BF16, int EPI>
+template <int BN>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ TmapPack tm, const GemmParams p) {
   constexpr int kBStage = BN * BK * 2;
-  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
   extern __shared__ unsigned char smem_raw[];
+  // 128-byte-swizzle atoms need 1024-byte alignment (the launch reserves the slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + NS * kAStage;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + NS * kBStage);
   uint64_t* empty = full + NS;
-  uint64_t* acc_full = empty + NS;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  int4* sTab = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(full) + 128);   // [classes][kTabPerCls]
-  int* sTapOff = reinterpret_cast<int*>(sTab + cvplan::kMaxClasses * kTabPerCls);       // [classes][16]
-  float* sStat = reinterpret_cast<float*>(sTapOff + cvplan::kMaxClasses * cvplan::kMaxTaps);  // [4 warps][2][BN]
-  float* sScale = sStat + 4 * 2 * 128;
-  float* sShift = sScale + p.plan.Cs;
+  uint64_t* tmem_full = empty + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  int4* sTab = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(full) + 96);  // 16-byte aligned; k -> (tap, channel)
+  int* sTapOff = reinterpret_cast<int*>(sTab + kTabMax);                // per-tap element offset (16 entries)
+  float* sScale = reinterpret_cast<float*>(sTapOff + cvplan::kMaxTaps); // pre-op scale / shift of the source channels
+  float* sShift = sScale + kMaxPreC;
 
+  const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const Cls& c = p.plan.cls[cls_id];
+  const long long Mc = p.batch * c.Hd * c.Wd;
+  const long long m0 = (long long)blockIdx.x * BM;
+  if (m0 >= Mc) return;
+  const int n0 = blockIdx.y * BN;
+  const int nkb_all = c.Kp / BK;
+  const int kb0 = nkb_all * split / p.splits;
+  const int nkb = nkb_all * (split + 1) / p.splits - kb0;
+  if (nkb <= 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Cs = p.plan.Cs;
-  const bool vec = (Cs % 8 == 0) && p.s_c == 1;
 
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], BM + 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
-  if (warp == 8 && lane == 0)
-    for (int i = 0; i < p.plan.n_classes; ++i) prefetch_tmap(&tm.t[i]);
-  if (p.pre_scale != nullptr)
-    for (int i = threadIdx.x; i < Cs; i += kThreads) { sScale[i] = __ldg(p.pre_scale + i); sShift[i] = __ldg(p.pre_shift + i); }
-  for (int ci = 0; ci < p.plan.n_classes; ++ci) {
-    const Cls& c = p.plan.cls[ci];
+  if (warp == 4) {
+    if (lane == 0) prefetch_tmap(&tm.t[cls_id]);
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  {
+    const int Cs = p.plan.Cs;
+    if (p.pre_scale != nullptr)
+      for (int i = threadIdx.x; i < Cs; i += kThreads) { sScale[i] = __ldg(p.pre_scale + i); sShift[i] = __ldg(p.pre_shift + i); }
     const int Kreal = c.ntaps * Cs;
-    for (int k = threadIdx.x; k < kTabPerCls && k < Kreal; k += kThreads) {
+    // k -> (tap, channel, element offset of (tap, channel) relative to the row's base pixel); thread independent
+    for (int k = threadIdx.x; k < kTabMax && k < Kreal; k += kThreads) {
       const int t = k / Cs, ch = k - t * Cs;
-      sTab[ci * kTabPerCls + k] = make_int4(t, ch, (int)(c.dh[t] * p.s_h + c.dw[t] * p.s_w + ch * p.s_c), 0);
+      sTab[k] = make_int4(t, ch, (int)(c.dh[t] * p.s_h + c.dw[t] * p.s_w + ch * p.s_c), 0);
     }
     if (threadIdx.x < cvplan::kMaxTaps)
-      sTapOff[ci * cvplan::kMaxTaps + threadIdx.x] =
-          threadIdx.x < c.ntaps ? (int)(c.dh[threadIdx.x] * p.s_h + c.dw[threadIdx.x] * p.s_w) : 0;
+      sTapOff[threadIdx.x] = threadIdx.x < c.ntaps ? (int)(c.dh[threadIdx.x] * p.s_h + c.dw[threadIdx.x] * p.s_w) : 0;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool has_pre = p.pre_scale != nullptr;
 
-  if (warp < 8) {
-    // ================= A producers: one thread per tile row; two groups of 4 warps take alternate k-blocks, so
-    // two k-blocks' worth of gathers are in flight per CTA (memory-level parallelism is what bounds this kernel)
-    const int r = threadIdx.x & 127;
-    const uint32_t grp = threadIdx.x >> 7;
-    uint32_t kbg = 0;  // k-blocks produced so far by this CTA (stage ring position)
-    Tile tl;
-    for (int tile = blockIdx.x; get_tile(p, tile, BN, &tl); tile += gridDim.x) {
-      const Cls& c = p.plan.cls[tl.cls];
-      const int Kreal = c.ntaps * Cs;
-      RowCtx rc;
-      decode_row(p, c, tl.m0 + r, &rc);
-      const int* tapoff = sTapOff + tl.cls * cvplan::kMaxTaps;
-      const int4* tab = sTab + tl.cls * kTabPerCls;
-      for (int kb = 0; kb < tl.nkb; ++kb, ++kbg) {
-        if ((kbg & 1u) != grp) continue;
-        const int s = kbg % NS;
-        const uint32_t ph = ((kbg / NS) & 1) ^ 1;
-        unsigned char* a_st = sA + s * kAStage;
-        if (vec) {
-          int t_cur = ((tl.kb0 + kb) * BK) / Cs, c_cur = ((tl.kb0 + kb) * BK) % Cs;
-          // phase 1: every load of the k-block in flight (clamped address, masked afterwards)
-          uint4 q0[8], q1[8];
-          int cch[8];
-          bool ok[8];
+  if (warp < 4) {
+    // ================= A producer: one thread per tile row =================
+    const int r = threadIdx.x;
+    const long long m = m0 + r;
+    const bool mvalid = m < Mc;
+    const long long mm = mvalid ? m : 0;
+    const int wd = (int)(mm % c.Wd);
+    const int hd = (int)((mm / c.Wd) % c.Hd);
+    const long long img = mm / ((long long)c.Wd * c.Hd);
+    const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
+    const int Cs = p.plan.Cs, Kreal = c.ntaps * Cs;
+    const bool vec = (Cs % 8 == 0) && p.s_c == 1;
+    const long long img_off = img * p.s_n;
+    const long long base = img_off + hbase * p.s_h + wbase * p.s_w;  // element offset of this row's (dh = dw = 0) pixel
+    unsigned tapmask = 0;                                            // taps whose source pixel is inside the image
+    if (mvalid) {
+      for (int t = 0; t < c.ntaps; ++t) {
+        const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+        tapmask |= (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) ? (1u << t) : 0u;
+      }
+    }
+    // incremental (tap, channel) of the next 8-chunk (vector path)
+    int t_cur = vec ? (kb0 * BK) / Cs : 0, c_cur = vec ? (kb0 * BK) % Cs : 0;
+    const bool has_pre = p.pre_scale != nullptr;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NS;
+      unsigned char* a_st = sA + s * kAStage;
+      if (vec) {
+        // ---- phase 1: addresses + ALL loads of the k-block in flight (clamped address, masked afterwards)
+        uint4 q0[8], q1[8];
+        int cch[8];
+        bool ok[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int kg = (tl.kb0 + kb) * BK + j * 8;
-            const bool v = kg < Kreal && ((rc.tapmask >> t_cur) & 1u);
-            const long long off = v ? rc.base + tapoff[t_cur & (cvplan::kMaxTaps - 1)] + c_cur : 0;
-            ok[j] = v;
-            cch[j] = c_cur;
-            if (SRC_BF16) {
-              q0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
-            } else {
-              q0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off));
-              q1[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off + 4));
-            }
-            c_cur += 8;
-            if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
+        for (int j = 0; j < 8; ++j) {
+          const int kg = (kb0 + kb) * BK + j * 8;
+          const bool v = kg < Kreal && ((tapmask >> t_cur) & 1u);
+          const long long off = v ? base + sTapOff[t_cur & (cvplan::kMaxTaps - 1)] + c_cur : 0;
+          ok[j] = v;
+          cch[j] = c_cur;
+          if (p.src_bf16) {
+            q0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.src) + off));
+          } else {
+            q0[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off));
+            q1[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off + 4));
           }
-          mbar_wait(&empty[s], ph);
-          // phase 2: BatchNorm-apply + ReLU (scale/shift from shared memory), bf16 pack, 16-byte stores
+          c_cur += 8;
+          if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
+        }
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        // ---- phase 2: BatchNorm-apply + ReLU (scale/shift from shared memory), bf16 pack, 16-byte stores
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v[8];
-            if (SRC_BF16) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q0[j]);
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+          if (p.src_bf16) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q0[j]);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-            } else {
-              v[0] = __uint_as_float(q0[j].x); v[1] = __uint_as_float(q0[j].y); v[2] = __uint_as_float(q0[j].z); v[3] = __uint_as_float(q0[j].w);
-              v[4] = __uint_as_float(q1[j].x); v[5] = __uint_as_float(q1[j].y); v[6] = __uint_as_float(q1[j].z); v[7] = __uint_as_float(q1[j].w);
-            }
-            if (has_pre) {
-              const float4 s0 = *reinterpret_cast<const float4*>(sScale + cch[j]);
-              const float4 s1 = *reinterpret_cast<const float4*>(sScale + cch[j] + 4);
-              const float4 h0 = *reinterpret_cast<const float4*>(sShift + cch[j]);
-              const float4 h1 = *reinterpret_cast<const float4*>(sShift + cch[j] + 4);
-              v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-              v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-            }
-            if (p.pre_relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            uint4 out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            if (!ok[j]) out = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = out;
+            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+          } else {
+            v[0] = __uint_as_float(q0[j].x); v[1] = __uint_as_float(q0[j].y); v[2] = __uint_as_float(q0[j].z); v[3] = __uint_as_float(q0[j].w);
+            v[4] = __uint_as_float(q1[j].x); v[5] = __uint_as_float(q1[j].y); v[6] = __uint_as_float(q1[j].z); v[7] = __uint_as_float(q1[j].w);
           }
-        } else {
-          mbar_wait(&empty[s], ph);
+          if (has_pre) {
+            const float4 s0 = *reinterpret_cast<const float4*>(sScale + cch[j]);
+            const float4 s1 = *reinterpret_cast<const float4*>(sScale + cch[j] + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sShift + cch[j]);
+            const float4 h1 = *reinterpret_cast<const float4*>(sShift + cch[j] + 4);
+            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+          }
+          if (p.pre_relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          uint4 out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          if (!ok[j]) out = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = out;
+        }
+      } else {
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
 #pragma unroll 1
-          for (int j = 0; j < 8; ++j) {
-            const int kg = (tl.kb0 + kb) * BK + j * 8;
-            if (kg >= Kreal || rc.tapmask == 0u) {  // zero padding of K (or a row outside the problem)
-              *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = make_uint4(0u, 0u, 0u, 0u);
-              continue;
-            }
-            float v[8];
-            bool ok[8];
-            int chn[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {  // eight independent loads; (tap, channel, offset) from the shared table
-              const int k = kg + i;
-              bool vld = false;
-              long long off = 0;
-              int ch = 0;
-              if (k < Kreal) {
-                int t, koff;
-                if (k < kTabPerCls) { const int4 e = tab[k]; t = e.x; ch = e.y; koff = e.z; }
-                else slow_k_lookup(p, c, k, Cs, &t, &ch, &koff);
-                vld = (rc.tapmask >> t) & 1u;
-                off = vld ? rc.base + koff : 0;
-              }
-              ok[i] = vld;
-              chn[i] = ch;
-              v[i] = ld_elem(p.src, off, SRC_BF16);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float x = v[i];
-              if (has_pre) x = fmaf(x, sScale[chn[i]], sShift[chn[i]]);
-              if (p.pre_relu) x = fmaxf(x, 0.f);
-              v[i] = ok[i] ? x : 0.f;
-            }
-            *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        for (int j = 0; j < 8; ++j) {
+          const int kg = (kb0 + kb) * BK + j * 8;
+          if (kg >= Kreal || tapmask == 0u) {  // zero padding of K (or a row outside the problem)
+            *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
           }
-        }
-        fence_proxy_async();
-        mbar_arrive(&full[s]);
-      }
-    }
-  } else if (warp == 8) {
-    // ================= B producer: TMA =================
-    if (lane == 0) {
-      uint32_t kbg = 0;
-      Tile tl;
-      for (int tile = blockIdx.x; get_tile(p, tile, BN, &tl); tile += gridDim.x) {
-        for (int kb = 0; kb < tl.nkb; ++kb, ++kbg) {
-          const int s = kbg % NS;
-          mbar_wait(&empty[s], ((kbg / NS) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[s], kBStage);
-          tma_load_2d(sB + s * kBStage, &tm.t[tl.cls], &full[s], (tl.kb0 + kb) * BK, tl.n0);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
-      uint32_t kbg = 0, tcount = 0;
-      Tile tl;
-      for (int tile = blockIdx.x; get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
-        const uint32_t b = tcount & 1;
-        mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < tl.nkb; ++kb, ++kbg) {
-          const int s = kbg % NS;
-          mbar_wait(&full[s], (kbg / NS) & 1);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * kAStage), b_base = smem_u32(sB + s * kBStage);
+          float v[8];
+          bool ok[8];
+          int chn[8];
+          // phase 1: eight independent loads (k -> (tap, channel, offset) from the shared-memory table)
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) {
-            // A: interleave layout, 16-byte k-chunks BM*16 bytes apart (LBO), 8-row groups 128 bytes apart (SBO)
-            const uint64_t ad = smem_desc(a_base + k4 * 2 * (BM * 16), BM * 16, 128, kLayoutNone);
-            // B: 128-byte swizzled rows, 8-row groups 1024 bytes apart; K advance = +32 bytes inside the atom
-            const uint64_t bd = smem_desc(b_base + k4 * 32, 16, 1024, kLayoutSw128);
-            umma_f16(tmem_base + b * kAccCols, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          for (int i = 0; i < 8; ++i) {
+            const int k = kg + i;
+            bool vld = false;
+            long long off = 0;
+            int ch = 0;
+            if (k < Kreal) {
+              int t, koff;
+              if (k < kTabMax) { const int4 e = sTab[k]; t = e.x; ch = e.y; koff = e.z; }
+              else { t = k / Cs; ch = k - t * Cs; koff = (int)(c.dh[t] * p.s_h + c.dw[t] * p.s_w + ch * p.s_c); }
+              vld = (tapmask >> t) & 1u;
+              off = vld ? base + koff : 0;
+            }
+            ok[i] = vld;
+            chn[i] = ch;
+            v[i] = ld_elem(p.src, off, p.src_bf16);
           }
-          umma_commit(&empty[s]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x = v[i];
+            if (has_pre) x = fmaf(x, sScale[chn[i]], sShift[chn[i]]);
+            if (p.pre_relu) x = fmaxf(x, 0.f);
+            v[i] = ok[i] ? x : 0.f;
+          }
+          *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
-        umma_commit(&acc_full[b]);
       }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
     }
-  } else {
-    // ================= epilogue warps: TMEM -> registers -> global =================
-    const int ew = warp - 10;
-    const int lane_grp = warp & 3;            // TMEM lanes 32*(warp%4) .. +31
-    const int r = lane_grp * 32 + lane;
+
+    // ================= epilogue: TMEM -> registers -> global =================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const long long dst_off = img * p.d_n + (long long)(hd * p.plan.os + c.oa) * p.d_h + (long long)(wd * p.plan.os + c.ob) * p.d_w;
+    const long long msk_off = img * p.m_n + (long long)(hd * p.plan.os + c.oa) * p.m_h + (long long)(wd * p.plan.os + c.ob) * p.m_w;
     const int Nn = p.plan.Nn;
     constexpr int CH = BN < 32 ? BN : 32;
-    float* myAcc = sStat + ew * 2 * 128;       // running per-column statistics of this warp: [2][BN], lane j owns column ch0 + j
-    for (int i = lane; i < 2 * 128; i += 32) myAcc[i] = 0.f;
-    __syncwarp();
-    int acc_n0 = -1;
-    auto flush_stats = [&]() {
-      // combine the four epilogue warps in shared memory: one double atomic per column reaches L2
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (acc_n0 >= 0) {
-        for (int col = threadIdx.x - 10 * 32; col < BN; col += 128) {
-          const int n = acc_n0 + col;
-          if (n < Nn) {
-            float a = 0.f, b = 0.f;
+#pragma unroll 1
+    for (int ch0 = 0; ch0 < BN; ch0 += CH) {
+      uint32_t raw[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
+      if (CH == 32) {
+        tmem_ld32(taddr, raw);
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(taddr, r16);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { a += sStat[(w * 2 + 0) * 128 + col]; b += sStat[(w * 2 + 1) * 128 + col]; }
+        for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+      }
+      tmem_ld_wait();
+      float v[32], u[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int n = n0 + ch0 + i;
+        float a = __uint_as_float(raw[i]);
+        float second = 0.f;
+        const bool live = mvalid && i < CH && n < Nn;
+        if (p.epi == CLEARVAE_EPI_BIAS_STATS) {
+          if (live && p.bias != nullptr && split == 0) a += __ldg(p.bias + n);
+          if (!live) a = 0.f;
+          second = a * a;
+        } else {
+          if (live) {
+            const float y = ld_elem(p.msk, msk_off + n * p.m_c, p.msk_bf16);
+            const float act = p.msk_scale ? fmaf(y, __ldg(p.msk_scale + n), __ldg(p.msk_shift + n)) : y;
+            a = act > 0.f ? a : 0.f;
+            second = a * y;
+          } else {
+            a = 0.f;
+          }
+        }
+        v[i] = a;
+        u[i] = second;
+      }
+      // ---- store (vectorised when channels are the innermost dst dimension)
+      if (mvalid && p.splits > 1) {
+        float* d = reinterpret_cast<float*>(p.dst) + dst_off;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int n = n0 + ch0 + i;
+          if (n < Nn) atomicAdd(d + n * p.d_c, v[i]);
+        }
+      } else if (mvalid) {
+        if (p.d_c == 1 && n0 + ch0 + CH <= Nn && (CH % 8) == 0) {
+          if (p.dst_bf16) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + n0 + ch0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8)
+              *reinterpret_cast<uint4*>(d + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                                                            pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+          } else {
+            float* d = reinterpret_cast<float*>(p.dst) + dst_off + n0 + ch0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int n = n0 + ch0 + i;
+            if (n < Nn) {
+              if (p.dst_bf16) reinterpret_cast<__nv_bfloat16*>(p.dst)[dst_off + n * p.d_c] = __float2bfloat16(v[i]);
+              else reinterpret_cast<float*>(p.dst)[dst_off + n * p.d_c] = v[i];
+            }
+          }
+        }
+      }
+      // ---- per-channel statistics: warp transpose-reduce, then across the 4 epilogue warps in shared
+      //      memory, so one double atomic per column per CTA reaches L2
+      if (p.stats != nullptr) {
+        transpose_reduce32(v);
+        transpose_reduce32(u);
+        float* sSt = sScale;  // the pre-op staging area is dead once the producers are done with the main loop
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        sSt[(warp * 2 + 0) * 32 + lane] = v[0];
+        sSt[(warp * 2 + 1) * 32 + lane] = u[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0) {
+          const int n = n0 + ch0 + lane;
+          if (lane < CH && n < Nn) {
+            const float a = (sSt[lane] + sSt[64 + lane]) + (sSt[128 + lane] + sSt[192 + lane]);
+            const float b = (sSt[32 + lane] + sSt[96 + lane]) + (sSt[160 + lane] + sSt[224 + lane]);
             atomicAdd(p.stats + n, (double)a);
             atomicAdd(p.stats + Nn + n, (double)b);
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = lane; i < 2 * 128; i += 32) myAcc[i] = 0.f;
-      __syncwarp();
-    };
-    uint32_t tcount = 0;
-    Tile tl;
-    for (int tile = blockIdx.x; get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
-      const Cls& c = p.plan.cls[tl.cls];
-      const long long Mc = p.batch * c.Hd * c.Wd;
-      const long long m = tl.m0 + r;
-      const bool mvalid = m < Mc;
-      const long long mm = mvalid ? m : 0;
-      const int wd = (int)(mm % c.Wd), hd = (int)((mm / c.Wd) % c.Hd);
-      const long long img = mm / ((long long)c.Wd * c.Hd);
-      const long long dst_off = img * p.d_n + (long long)(hd * p.plan.os + c.oa) * p.d_h + (long long)(wd * p.plan.os + c.ob) * p.d_w;
-      const long long msk_off = img * p.m_n + (long long)(hd * p.plan.os + c.oa) * p.m_h + (long long)(wd * p.plan.os + c.ob) * p.m_w;
-      if (p.stats != nullptr && tl.n0 != acc_n0) {  // column block changed: publish what was accumulated so far
-        if (acc_n0 >= 0) flush_stats();
-        acc_n0 = tl.n0;
-      }
-      const uint32_t b = tcount & 1;
-      mbar_wait(&acc_full[b], (tcount >> 1) & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch0 = 0; ch0 < BN; ch0 += CH) {
-        uint32_t raw[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * kAccCols + ch0);
-        if (CH == 32) {
-          tmem_ld32(taddr, raw);
-        } else {
-          uint32_t r16[16];
-          tmem_ld16(taddr, r16);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
-        }
-        tmem_ld_wait();
-        const int nbase = tl.n0 + ch0;
-        const int nlive = mvalid ? min(CH, Nn - nbase) : 0;  // leading columns of this chunk that exist
-        float v[32], u[32];
-        if (EPI == CLEARVAE_EPI_BIAS_STATS) {
-          const bool add_bias = p.bias != nullptr && tl.split == 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = __uint_as_float(raw[i]);
-            if (add_bias && i < nlive) a += __ldg(p.bias + nbase + i);
-            a = i < nlive ? a : 0.f;
-            v[i] = a;
-            u[i] = a * a;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = 0.f, second = 0.f;
-            if (i < nlive) {
-              const int n = nbase + i;
-              const float y = ld_elem(p.msk, msk_off + n * p.m_c, p.msk_bf16);
-              const float act = p.msk_scale ? fmaf(y, __ldg(p.msk_scale + n), __ldg(p.msk_shift + n)) : y;
-              a = act > 0.f ? __uint_as_float(raw[i]) : 0.f;
-              second = a * y;
-            }
-            v[i] = a;
-            u[i] = second;
-          }
-        }
-        // ---- store (vectorised when channels are the innermost dst dimension)
-        if (mvalid && p.splits > 1) {
-          float* d = reinterpret_cast<float*>(p.dst) + dst_off + (long long)nbase * p.d_c;
-#pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            if (i < nlive) atomicAdd(d, v[i]);
-            d += p.d_c;
-          }
-        } else if (mvalid) {
-          if (p.d_c == 1 && nlive == CH && (CH % 8) == 0) {
-            if (p.dst_bf16) {
-              __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + nbase;
-#pragma unroll
-              for (int i = 0; i < CH; i += 8)
-                *reinterpret_cast<uint4*>(d + i) = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                                                              pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-            } else {
-              float* d = reinterpret_cast<float*>(p.dst) + dst_off + nbase;
-#pragma unroll
-              for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-          } else if (p.dst_bf16) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + (long long)nbase * p.d_c;
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              if (i < nlive) *d = __float2bfloat16(v[i]);
-              d += p.d_c;
-            }
-          } else {
-            float* d = reinterpret_cast<float*>(p.dst) + dst_off + (long long)nbase * p.d_c;
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              if (i < nlive) *d = v[i];
-              d += p.d_c;
-            }
-          }
-        }
-        // ---- per-channel statistics: transposing warp reduce into this warp's running sums (shared memory)
-        if (p.stats != nullptr) {
-          transpose_reduce32(v);
-          transpose_reduce32(u);
-          if (lane < CH) {
-            myAcc[ch0 + lane] += v[0];
-            myAcc[128 + ch0 + lane] += u[0];
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[b]);
     }
-    if (p.stats != nullptr) flush_stats();
+  } else if (warp == 4) {
+    // ================= B producer: TMA =================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], kBStage);
+        tma_load_2d(sB + s * kBStage, &tm.t[cls_id], &full[s], (kb0 + kb) * BK, n0);
+      }
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        mbar_wait(&full[s], (kb / NS) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * kAStage), b_base = smem_u32(sB + s * kBStage);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4) {
+          // A: interleave layout, 16-byte k-chunks BM*16 bytes apart (LBO), 8-row groups 128 bytes apart (SBO)
+          const uint64_t ad = smem_desc(a_base + k4 * 2 * (BM * 16), BM * 16, 128, kLayoutNone);
+          // B: 128-byte swizzled rows, 8-row groups 1024 bytes apart; K advance = +32 bytes inside the atom
+          const uint64_t bd = smem_desc(b_base + k4 * 32, 16, 1024, kLayoutSw128);
+          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
+
 
 // ---------------------------------------------------------------------------
 // weight gradient:  dW[kidx, n] += sum_{pixels m} act[m @ tap(kidx), c(kidx)] * dy[m, n]
@@ -522,7 +416,7 @@ constexpr int WK = 64;                       // pixels per k-block
 constexpr int kWStageA = 128 * WK * 2;       // 16 KiB
 
 template <int BN>
-__global__ void __launch_bounds__(kWThreads) wgrad_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p) {
   constexpr int kBStage = BN * WK * 2;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
   extern __shared__ unsigned char smem_raw[];
@@ -557,7 +451,7 @@ __global__ void __launch_bounds__(kWThreads) wgrad_tc_kernel(const WgradParams p
   }
   if (warp == 4) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   if (p.pre_scale != nullptr)
-    for (int i = threadIdx.x; i < Cs; i += kWThreads) { sScale[i] = __ldg(p.pre_scale + i); sShift[i] = __ldg(p.pre_shift + i); }
+    for (int i = threadIdx.x; i < Cs; i += kThreads) { sScale[i] = __ldg(p.pre_scale + i); sShift[i] = __ldg(p.pre_shift + i); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -803,36 +697,18 @@ inline int pick_bn(int Nn) {
   return n_pad >= 128 ? 128 : n_pad > 32 ? 64 : n_pad > 16 ? 32 : 16;
 }
 
-inline size_t conv_smem_bytes(int BN, int Cs) {
-  return (size_t)NS * kAStage + (size_t)NS * BN * BK * 2 + 128 /*barriers + tmem slot*/ +
-         cvplan::kMaxClasses * kTabPerCls * 16 + cvplan::kMaxClasses * cvplan::kMaxTaps * 4 + 4 * 2 * 128 * 4 +
-         2 * (size_t)Cs * 4 + 1024;
-}
-
-template <int BN, bool SRC_BF16, int EPI>
-int launch(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
+template <int BN>
+int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + 96 /*barriers + tmem slot*/ + kTabMax * 16 + 64 + 2 * kMaxPreC * 4 + 1024;
   static bool attr_done = false;
-  static int num_sms = 148;
-  auto kern = conv_tc_kernel<BN, SRC_BF16, EPI>;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(BN, kMaxPreC));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_done = true;
   }
-  const size_t smem = conv_smem_bytes(BN, p.plan.Cs);
-  const int grid = std::min(p.n_tiles, num_sms);
-  kern<<<grid, kThreads, smem, st>>>(tm, p);
+  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tm, p);
   CV_LAUNCH_CHECK();
   return 0;
-}
-template <int BN>
-int launch_bn(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
-  if (p.epi == CLEARVAE_EPI_BIAS_STATS)
-    return p.src_bf16 ? launch<BN, true, CLEARVAE_EPI_BIAS_STATS>(tm, p, st) : launch<BN, false, CLEARVAE_EPI_BIAS_STATS>(tm, p, st);
-  return p.src_bf16 ? launch<BN, true, CLEARVAE_EPI_MASK_STATS>(tm, p, st) : launch<BN, false, CLEARVAE_EPI_MASK_STATS>(tm, p, st);
 }
 
 void fill_t4(const clearvae_tensor4* t, const void*& ptr, long long& sn, long long& sh, long long& sw, long long& sc, int& bf) {
@@ -849,7 +725,7 @@ int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  wgrad_tc_kernel<BN><<<grid, kWThreads, smem, st>>>(p);
+  wgrad_tc_kernel<BN><<<grid, kThreads, smem, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -967,21 +843,12 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
       }
     }
   }
-  // work list of the persistent kernel: class-major, then m-tile, split, n-tile (n fastest: neighbouring CTAs
-  // gather the same activation rows at the same time and share them through L2)
-  p.n_ntiles = (n_pad + BN - 1) / BN;
-  int total = 0;
-  for (int i = 0; i < p.plan.n_classes; ++i) {
-    p.tile_start[i] = total;
-    const long long mc = (long long)batch * p.plan.cls[i].Hd * p.plan.cls[i].Wd;
-    total += (int)((mc + BM - 1) / BM) * p.splits * p.n_ntiles;
-  }
-  p.n_tiles = total;
+  dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)((n_pad + BN - 1) / BN), (unsigned)(p.plan.n_classes * p.splits));
   switch (BN) {
-    case 16: return launch_bn<16>(tm, p, st);
-    case 32: return launch_bn<32>(tm, p, st);
-    case 64: return launch_bn<64>(tm, p, st);
-    default: return launch_bn<128>(tm, p, st);
+    case 16: return launch<16>(tm, p, grid, st);
+    case 32: return launch<32>(tm, p, grid, st);
+    case 64: return launch<64>(tm, p, grid, st);
+    default: return launch<128>(tm, p, grid, st);
   }
 }
 
