@@ -146,7 +146,8 @@ class VAETrainer(Trainer):
         graph = torch.cuda.CUDAGraph()
         from . import _ops
         before = _ops.meter.launches()
-        with torch.cuda.graph(graph):
+        # thread-local error mode: the NCCL watchdog thread may touch CUDA while this thread captures (data parallel)
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             out = self._device_step(sX, sl, **kw)
         self._graph = dict(graph=graph, X=sX, label=sl, perm=perm, perm_host=perm_host, out=out,
                            launches=_ops.meter.launches() - before)
