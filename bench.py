@@ -262,6 +262,9 @@ def main():
             tr.use_cuda_graph = True
             for i in range(3):      # first call captures the device body of the step, the others replay it
                 step_dev(i)
+                if os.environ.get("CLEARVAE_DEBUG"):
+                    torch.cuda.synchronize()
+                    print(f"[bench] rank {rank} graph step {i} done", file=sys.stderr, flush=True)
             barrier()
             graphed = True
         except Exception as e:      # capture is an optimisation, never a requirement
@@ -270,6 +273,12 @@ def main():
             torch.cuda.synchronize()
             print(f"[bench] CUDA-graph capture unavailable, running eagerly: {e!r}", file=sys.stderr, flush=True)
 
+    def dbg(msg):
+        if os.environ.get("CLEARVAE_DEBUG"):
+            torch.cuda.synchronize()
+            print(f"[bench] rank {rank}: {msg}", file=sys.stderr, flush=True)
+
+    dbg("graphs ready")
     # ---- one profiling pass: which of OUR kernels dominates the step?
     meter = _ops.meter
     meter.reset()
@@ -279,6 +288,7 @@ def main():
     for i in range(2):
         step_dev(i)
     torch.cuda.synchronize()
+    dbg("profiling pass done")
     prof = meter.elapsed_ms()
     launches_per_step = meter.launches() // 2
     dominant = max(prof, key=lambda k: prof[k][1]) if prof else None
@@ -293,6 +303,7 @@ def main():
     meter.reset()
     meter.timed = set()
     tr.use_cuda_graph = graphed
+    dbg("eager kernel-timing pass done")
 
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local)
@@ -305,6 +316,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / K
+    dbg("timed region done")
     clocks = sampler.stop()
     launches = tr._graph["launches"] * K if graphed else meter.launches()
 
@@ -321,6 +333,7 @@ def main():
     t1.record()
     barrier()
     ms_e2e = max(t0.elapsed_time(t1), (time.perf_counter() - wall0) * 1e3) / K
+    dbg("e2e region done")
     h2d = pool_h[0][0].numel() * 4 + pool_h[0][1].numel() * 8
     d2h = vals.numel() * 4
 
@@ -367,7 +380,14 @@ def main():
                     roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     if world > 1:
-        td.destroy_process_group()
+        # CUDA graphs that captured NCCL kernels keep the communicator busy: tearing the process group down with
+        # them alive can hang, so release the graphs first and leave without the (optional) NCCL teardown
+        tr._graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        td.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":

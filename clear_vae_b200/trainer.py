@@ -129,6 +129,8 @@ class VAETrainer(Trainer):
         return tuple(t.clone() for t in g["out"])  # the graph's output buffers are overwritten by the next replay
 
     def _capture(self, X, label):
+        import os, sys
+        dbg = (lambda m: print(f"[capture] {m}", file=sys.stderr, flush=True)) if os.environ.get("CLEARVAE_DEBUG") else (lambda m: None)
         sX, sl = X.clone(), label.clone()
         perm = perm_host = None
         kw = {}
@@ -138,17 +140,20 @@ class VAETrainer(Trainer):
             kw["perm"] = perm
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        dbg("side-stream warm-up")
         with torch.cuda.stream(side):       # optimiser state / workspaces / caches must exist before capture
             for _ in range(2):
                 self._device_step(sX, sl, **kw)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        dbg("begin capture")
         graph = torch.cuda.CUDAGraph()
         from . import _ops
         before = _ops.meter.launches()
         # thread-local error mode: the NCCL watchdog thread may touch CUDA while this thread captures (data parallel)
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             out = self._device_step(sX, sl, **kw)
+        dbg("captured")
         self._graph = dict(graph=graph, X=sX, label=sl, perm=perm, perm_host=perm_host, out=out,
                            launches=_ops.meter.launches() - before)
         return self._graph
