@@ -195,6 +195,54 @@ def build_trainer(cfg, device):
                                    device, cfg["arch"], cfg["cin"])
 
 
+def latent_roofline(dev, pk):
+    """Fused latent-loss kernel pair at the top of BASELINE configs[4] (65536 all-gathered latents, D = 8):
+    pairs/s against the measured MUFU ex2 rate — the pipe that bounds it (1 exp per (row, column) pair)."""
+    import torch
+    from clear_vae_b200.latent import latent_block
+    B, D = 65536, 8
+    g = torch.Generator().manual_seed(0)
+    mu_c = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+    mu_s = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+    lv = (torch.randn(B, D, generator=g) * .3).to(dev).requires_grad_(True)
+    eps = torch.randn(B, D, generator=g).to(dev)
+    lab = torch.randint(0, 10, (B,), generator=g).to(dev)
+    w = torch.tensor([0.1, 0.1, 100.0, 100.0, 0, 0, 0, 0], device=dev)
+
+    def run(n):
+        tf = tb = 0.0
+        for _ in range(n):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            z, sc = latent_block([mu_c, mu_s], [lv, lv], [eps, eps], lab, snn=[1, 1], ps=[False, True], temperature=0.1)
+            e1.record()
+            torch.autograd.backward([sc], [w])
+            e2.record()
+            torch.cuda.synchronize()
+            tf += e0.elapsed_time(e1)
+            tb += e1.elapsed_time(e2)
+            mu_c.grad = mu_s.grad = lv.grad = None
+        return tf / n, tb / n
+
+    run(3)
+    tf, tb = run(5)
+    pairs = 2.0 * B * B  # two terms (content, style)
+    probe = os.path.join(ROOT, "tools", "mufu_probe")
+    peak, src = 4594.0, "recorded (tools/mufu_probe on this pool: 148 SMs x 16 ex2/clk)"
+    try:
+        out = subprocess.run([probe], capture_output=True, text=True, timeout=60).stdout
+        vals = [json.loads(l)["gexp_per_s"] for l in out.splitlines() if '"ex2"' in l]
+        if vals:
+            peak, src = max(vals), "measured now (tools/mufu_probe)"
+    except Exception:
+        pass
+    f, b = pairs / tf * 1e-6, pairs / tb * 1e-6
+    return dict(workload="contrastive + anti-contrastive terms, 65536 x 65536 pairs each, D=8, fp32 (3xTF32 on tcgen05)",
+                bound="mufu_ex2", unit="Gpair/s", peak=peak, peak_source=src,
+                forward=dict(ms=tf, achieved=f, frac=f / peak), backward=dict(ms=tb, achieved=b, frac=b / peak),
+                algorithmic="1 ex2 + 2*D (fwd) / 6*D (bwd) flop per pair; HBM bytes O(B*D), negligible")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +252,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-latent", action="store_true", help="skip the latent-loss roofline point")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -351,7 +400,10 @@ def main():
     if dominant in alg and dom[0] > 0:
         per_step_ms = dom[1] / K
         ach = alg[dominant] / (per_step_ms * 1e-3) / 1e12
-        roof = dict(kernel=dominant, bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=None,
+        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r1_conv_tc_ncu_raw.csv: mean of
+        # dram__bytes_read.sum + dram__bytes_write.sum over the 8 conv launches of one forward); null for other kernels
+        traffic = 7.28e6 if (dominant == "conv_gemm" and args.config.startswith("mim")) else None
+        roof = dict(kernel=dominant, bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=traffic,
                     launches_per_step=dom[0] // K, ms_per_step=per_step_ms, peak_source=pk["src"] + " bf16 sustained",
                     timing="CUDA events around every launch of this kernel, eager pass over the same K steps",
                     algorithmic_gflop_per_step=alg[dominant] / 1e9)
@@ -366,6 +418,12 @@ def main():
             sps, cms, cores, note = time_cpu(cfg, csteps, 2)
             cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
                        sample=f"{csteps} full steps of batch {B} after 2 warm-up on the host ({note}); {cms:.0f} ms/step")
+        lat = None
+        if world == 1 and not args.no_latent:
+            try:
+                lat = latent_roofline(dev, pk)
+            except Exception as e:  # never lose the headline line to the side measurement
+                lat = dict(error=repr(e))
         line = dict(metric="train samples/sec", value=world * B / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload=WORKLOAD_NAMES[args.config], per_gpu_batch=B, global_batch=world * B,
@@ -377,7 +435,7 @@ def main():
                     e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e),
                     gpu_launches=launches, gpu_launches_per_step=launches_per_step, kernel_ms_per_step=breakdown,
-                    roofline=roof, cpu_baseline=cpu)
+                    roofline=roof, latent_roofline=lat, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels keep the communicator busy: tearing the process group down with

@@ -63,7 +63,7 @@ typedef struct {
   const float* logvar_cols; /* [Bg, D], only for logvar-dependent sims */
   /* outputs */
   float* z;             /* [B, z_stride] slice start, or NULL        */
-  float* row_stats;     /* [B, 2]: (sum_all, sum_pos) — see DESIGN.md */
+  float* row_stats;     /* [B, 2]: (lse_all, lse_pos) minus the shared shift — DESIGN.md §3.1 */
   /* configuration */
   int32_t snn_enable;   /* 0: only reparam/KL for this term          */
   int32_t ps;           /* 0: same-label positives, 1: flipped mask  */
