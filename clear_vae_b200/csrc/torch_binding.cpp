@@ -392,6 +392,24 @@ Tensor colsum(const Tensor& x) {
   return out;
 }
 
+bool conv_direct_fwd(at::IntArrayRef geom, int64_t batch, const Tensor& src, at::IntArrayRef src_strides, const OptTensor& pre_scale,
+                     const OptTensor& pre_shift, bool pre_relu, const Tensor& weight, const OptTensor& bias, Tensor dst,
+                     at::IntArrayRef dst_strides, const OptTensor& stats) {
+  const c10::cuda::CUDAGuard guard(src.device());
+  auto g = geom_from(geom);
+  auto s4 = t4(src, src_strides, "src");
+  auto d4 = t4(dst, dst_strides, "dst");
+  if (!clearvae_conv_direct_supported(&g, &s4, &d4)) return false;
+  if (!g.transposed && (pre_relu || (pre_scale.has_value() && pre_scale->defined()))) return false;
+  check_f32(weight, "weight");
+  double* st = nullptr;
+  if (stats.has_value() && stats->defined()) st = stats_ptr(*stats);
+  check_rc(clearvae_conv_direct_fwd(&g, batch, &s4, optf(pre_scale, "pre_scale"), optf(pre_shift, "pre_shift"), pre_relu ? 1 : 0,
+                                    weight.data_ptr<float>(), optf(bias, "bias"), &d4, st, cur_stream()),
+           "conv_direct_fwd");
+  return true;
+}
+
 int64_t bn_act_workspace_bytes() { return (int64_t)clearvae_bn_act_workspace_bytes(); }
 
 }  // namespace
@@ -410,6 +428,8 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("recon_bwd(Tensor xhat, Tensor x, Tensor grad_out) -> Tensor");
   m.def("recon_workspace_bytes() -> int", &recon_workspace_bytes);
   m.def("conv_pack_weight(int[] geom, int role, Tensor weight) -> Tensor");
+  m.def("conv_direct_fwd(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
+        "Tensor weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, Tensor(b!)? stats) -> bool");
   m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
   m.def("bn_finalize(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
@@ -437,6 +457,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("recon_bwd", &recon_bwd);
   m.impl("conv_pack_weight", &conv_pack_weight);
   m.impl("conv_gemm", &conv_gemm);
+  m.impl("conv_direct_fwd", &conv_direct_fwd);
   m.impl("conv_wgrad", &conv_wgrad);
   m.impl("bn_finalize", &bn_finalize);
   m.impl("bn_reduce", &bn_reduce);

@@ -126,9 +126,12 @@ class EncoderFn(torch.autograd.Function):
                 raw = torch.empty(B, H, H, sp.cout, dtype=eng.act_dtype, device=dev)
                 dst_strides = nhwc_strides(H, H, sp.cout)
             st = eng.stat_buf(("enc", i), sp.cout, dev) if eng.training else None
-            pw = eng.packs.get(("enc", i), w, sp.geom, FPROP)
-            ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
-                          pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
+            # boundary layer (Cin <= 4): direct CUDA-core kernel; everything else: tcgen05 implicit GEMM
+            if not (i == 0 and eng.use_direct and ops.conv_direct_fwd(sp.geom, B, src, src_strides, None, None, False,
+                                                                      w.detach(), b.detach(), raw, dst_strides, st)):
+                pw = eng.packs.get(("enc", i), w, sp.geom, FPROP)
+                ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                              pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
             if eng.training:
                 nw = _reduce_stats(eng, st)
                 scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
@@ -261,9 +264,12 @@ class DecoderFn(torch.autograd.Function):
                 raw = torch.empty(B, H, H, sp.cout, dtype=eng.act_dtype, device=dev)
                 dst_strides = nhwc_strides(H, H, sp.cout)
             st = eng.stat_buf(("dec", j), sp.cout, dev) if eng.training else None
-            ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
-                          pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS, None,
-                          [0, 0, 0, 0], None, None, st)
+            if not (last and eng.use_direct and pre is not None and
+                    ops.conv_direct_fwd(sp.geom, B, src, src_strides, pre[0], pre[1], True, w.detach(), b.detach(), raw,
+                                        dst_strides, st)):
+                ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                              pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS,
+                              None, [0, 0, 0, 0], None, None, st)
             if eng.training:
                 nw = _reduce_stats(eng, st)
                 scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
@@ -379,6 +385,7 @@ class Engine:
         self.stats_only = False
         self.dist = None      # DistSpec for SyncBN
         self.sync_bn = False
+        self.use_direct = True   # direct kernels for the Cin<=4 / Cout<=4 boundary layers
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev)

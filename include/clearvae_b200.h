@@ -210,6 +210,15 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
 /* out[c] = sum_r x[r][c]  (bias gradients of the linear heads) */
 int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 
+/* Direct (CUDA-core) forward of the two boundary layers whose shapes do not suit 128-row tensor-core tiles:
+ * Conv2d(Cin<=4 -> 32) on an NCHW fp32 image (vae.py:16,114) and ConvTranspose2d(32 -> Cout<=4) to an NCHW
+ * fp32 image (vae.py:43,153); k in {3,4}, stride 2, pad 1.  `weight` is the fp32 reference-layout tensor.
+ * clearvae_conv_direct_supported returns 1 when (geometry, views) match, else callers use clearvae_conv_gemm. */
+int clearvae_conv_direct_supported(const clearvae_conv_geom* g, const clearvae_tensor4* src, const clearvae_tensor4* dst);
+int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
+                             const float* pre_shift, int32_t pre_relu, const float* weight, const float* bias,
+                             const clearvae_tensor4* dst, double* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,3 +169,48 @@ def test_weight_gradient(transposed, k, op, cin, cout, H, B):
     ops.conv_wgrad(geom, B, x, [x.stride(0), x.stride(2), x.stride(3), x.stride(1)], None, None, False, dy,
                    [dy.stride(0), dy.stride(2), dy.stride(3), dy.stride(1)], dw2)
     assert rel_err(dw2 - 1.0, dw_want) < 5e-5
+
+
+@pytest.mark.parametrize("k,cin,H,B", [(3, 3, 28, 16), (3, 1, 28, 8), (4, 3, 64, 4)])
+def test_direct_first_conv(k, cin, H, B):
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(k + cin)
+    x = torch.rand(B, cin, H, H, generator=g).to(DEV)
+    w = (torch.randn(32, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(32, generator=g).to(DEV)
+    want = F.conv2d(x, w, b, stride=2, padding=1)
+    Ho = want.shape[-1]
+    for dt in (torch.float32, torch.bfloat16):
+        dst = torch.empty(B, Ho, Ho, 32, device=DEV, dtype=dt)
+        stats = torch.zeros(64, dtype=torch.float64, device=DEV)
+        ok = ops.conv_direct_fwd([0, k, 2, 1, 0, cin, 32, H, H], B, x, [x.stride(0), x.stride(2), x.stride(3), x.stride(1)], None, None,
+                                 False, w, b, dst, nhwc_strides(dst), stats)
+        assert ok
+        assert rel_err(dst.float().permute(0, 3, 1, 2), want) < (1e-5 if dt == torch.float32 else 5e-3)
+        assert torch.allclose(stats[:32].float(), want.sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(stats[32:].float(), (want * want).sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("k,op,cout,H,B", [(3, 1, 3, 14, 8), (3, 1, 1, 14, 8), (4, 0, 3, 32, 4)])
+def test_direct_last_conv_transpose(k, op, cout, H, B):
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(k + cout)
+    raw = torch.randn(B, H, H, 32, generator=g).to(DEV)
+    scale = (torch.rand(32, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(32, generator=g) * 0.3).to(DEV)
+    w = (torch.randn(32, cout, k, k, generator=g) / (32 * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    for dt in (torch.float32, torch.bfloat16):
+        r = raw.to(dt)
+        act = torch.relu(r.float() * scale + shift)
+        want = F.conv_transpose2d(act.permute(0, 3, 1, 2), w, b, stride=2, padding=1, output_padding=op)
+        Ho = want.shape[-1]
+        dst = torch.empty(B, cout, Ho, Ho, device=DEV)
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+        ok = ops.conv_direct_fwd([1, k, 2, 1, op, 32, cout, H, H], B, r, nhwc_strides(r), scale, shift, True, w, b, dst,
+                                 [dst.stride(0), dst.stride(2), dst.stride(3), dst.stride(1)], stats)
+        assert ok
+        assert rel_err(dst, want) < 1e-5
+        assert torch.allclose(stats[:cout].float(), want.sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
