@@ -332,7 +332,7 @@ def main():
     meter = _ops.meter
     meter.reset()
     tr.use_cuda_graph = False   # per-kernel event timing needs the eager path (same kernels, same order)
-    meter.timed = {"conv_gemm", "conv_wgrad", "latent_fwd", "latent_bwd", "bn_finalize", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd",
+    meter.timed = {"conv_gemm", "conv_direct_fwd", "conv_wgrad", "latent_fwd", "latent_bwd", "bn_finalize", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd",
                    "bn_reduce", "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize"}
     for i in range(2):
         step_dev(i)

@@ -100,6 +100,9 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One thread = two horizontally adjacent output pixels (ow = 2j, 2j+1) of one output row; threads are ordered so that
+// a warp stays inside one row parity (uniform set of valid kh) — no divergence, weights are warp-broadcast from
+// shared memory, every needed input pixel is loaded (and BatchNorm+ReLU'ed) exactly once per thread.
 template <int K, bool SRC_BF16>
 __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict__ src, const float* __restrict__ pre_scale,
                                                          const float* __restrict__ pre_shift, int pre_relu,
@@ -120,55 +123,82 @@ __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict_
   }
   __syncthreads();
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-  const long long npix = (long long)B * Ho * Wo;
-  for (long long pix = (long long)blockIdx.x * kNT + threadIdx.x; pix < npix; pix += (long long)gridDim.x * kNT) {
-    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho);
-    const long long n = pix / ((long long)Wo * Ho);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int W2 = (Wo + 1) / 2, H2 = (Ho + 1) / 2;
+  const long long nwork = (long long)B * 2 * H2 * W2;
+  for (long long p = (long long)blockIdx.x * kNT + threadIdx.x; p < nwork; p += (long long)gridDim.x * kNT) {
+    const int j = (int)(p % W2);
+    long long t = p / W2;
+    const int oh2 = (int)(t % H2);
+    t /= H2;
+    const int a = (int)(t & 1);
+    const long long n = t >> 1;
+    const int oh = 2 * oh2 + a;
+    if (oh >= Ho) continue;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int kh = 0; kh < K; ++kh) {
       const int th = oh + 1 - kh;  // = 2 * ih
-      if (th < 0 || (th & 1) || (th >> 1) >= Hi) continue;
+      if (th < 0 || (th & 1) || (th >> 1) >= Hi) continue;   // warp-uniform (same row parity)
+      const int ih = th >> 1;
 #pragma unroll
-      for (int kw = 0; kw < K; ++kw) {
-        const int tw = ow + 1 - kw;
-        if (tw < 0 || (tw & 1) || (tw >> 1) >= Wi) continue;
-        const long long off = ((n * Hi + (th >> 1)) * Wi + (tw >> 1)) * CI;
-        const float4* wr = reinterpret_cast<const float4*>(sW + (kh * K + kw) * CI * 4);
+      for (int d = -1; d <= 1; ++d) {
+        // input column iw = j + d feeds ow = 2j through kw0 = 1 - 2d and ow = 2j + 1 through kw1 = 2 - 2d
+        constexpr int kDummy = 0;
+        (void)kDummy;
+        const int kw0 = 1 - 2 * d, kw1 = 2 - 2 * d;
+        const bool use0 = kw0 >= 0 && kw0 < K, use1 = kw1 >= 0 && kw1 < K;
+        if (!use0 && !use1) continue;                         // compile-time
+        const int iw = j + d;
+        if (iw < 0 || iw >= Wi) continue;
+        const long long off = ((n * Hi + ih) * Wi + iw) * CI;
         float v[CI];
         if (SRC_BF16) {
-          const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + off);
+          const uint4* ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + off);
 #pragma unroll
           for (int c8 = 0; c8 < CI / 8; ++c8) {
-            const uint4 u = __ldg(p + c8);
+            const uint4 u = __ldg(ptr + c8);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[c8 * 8 + 2 * i] = f.x; v[c8 * 8 + 2 * i + 1] = f.y; }
           }
         } else {
-          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
+          const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
 #pragma unroll
-          for (int c4 = 0; c4 < CI / 4; ++c4) { const float4 u = __ldg(p + c4); v[4 * c4] = u.x; v[4 * c4 + 1] = u.y; v[4 * c4 + 2] = u.z; v[4 * c4 + 3] = u.w; }
+          for (int c4 = 0; c4 < CI / 4; ++c4) { const float4 u = __ldg(ptr + c4); v[4 * c4] = u.x; v[4 * c4 + 1] = u.y; v[4 * c4 + 2] = u.z; v[4 * c4 + 3] = u.w; }
         }
+        const float4* w0 = reinterpret_cast<const float4*>(sW + (kh * K + (use0 ? kw0 : 0)) * CI * 4);
+        const float4* w1 = reinterpret_cast<const float4*>(sW + (kh * K + (use1 ? kw1 : 0)) * CI * 4);
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci) {
-          float a = fmaf(v[ci], sScale[ci], sShift[ci]);
-          if (pre_relu) a = fmaxf(a, 0.f);
-          const float4 wv = wr[ci];
-          acc[0] = fmaf(a, wv.x, acc[0]);
-          acc[1] = fmaf(a, wv.y, acc[1]);
-          acc[2] = fmaf(a, wv.z, acc[2]);
-          acc[3] = fmaf(a, wv.w, acc[3]);
+          float x = fmaf(v[ci], sScale[ci], sShift[ci]);
+          if (pre_relu) x = fmaxf(x, 0.f);
+          if (use0) {
+            const float4 wv = w0[ci];
+            acc0[0] = fmaf(x, wv.x, acc0[0]); acc0[1] = fmaf(x, wv.y, acc0[1]); acc0[2] = fmaf(x, wv.z, acc0[2]); acc0[3] = fmaf(x, wv.w, acc0[3]);
+          }
+          if (use1) {
+            const float4 wv = w1[ci];
+            acc1[0] = fmaf(x, wv.x, acc1[0]); acc1[1] = fmaf(x, wv.y, acc1[1]); acc1[2] = fmaf(x, wv.z, acc1[2]); acc1[3] = fmaf(x, wv.w, acc1[3]);
+          }
         }
       }
     }
+    const int ow = 2 * j;
+    const bool two = ow + 1 < Wo;
 #pragma unroll
     for (int co = 0; co < 4; ++co) {
       if (co < Cout) {
-        const float y = acc[co] + (bias ? __ldg(bias + co) : 0.f);
-        out[((n * Cout + co) * Ho + oh) * (long long)Wo + ow] = y;
-        s[co] += y;
-        q[co] = fmaf(y, y, q[co]);
+        const float bsv = bias ? __ldg(bias + co) : 0.f;
+        const float y0 = acc0[co] + bsv, y1 = acc1[co] + bsv;
+        float* o = out + ((n * Cout + co) * Ho + oh) * (long long)Wo + ow;
+        if (two && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+          *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
+        } else {
+          o[0] = y0;
+          if (two) o[1] = y1;
+        }
+        s[co] += y0; q[co] = fmaf(y0, y0, q[co]);
+        if (two) { s[co] += y1; q[co] = fmaf(y1, y1, q[co]); }
       }
     }
   }
@@ -234,7 +264,7 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
                                                           stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho);
   } else {
     const int Ho = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad;
-    const long long npix = batch * Ho * Ho;
+    const long long npix = batch * 2 * ((Ho + 1) / 2) * ((Ho + 1) / 2);  // one thread per output-pixel pair
     const bool bf = src->dtype == CLEARVAE_BF16;
 #define CV_LAUNCH_T(KK, BF)                                                                                                   \
   convt_last_kernel<KK, BF><<<grid_for(npix), kNT, 0, st>>>(src->ptr, pre_scale, pre_shift, pre_relu, weight, bias,           \

@@ -23,10 +23,13 @@ from .model_oracle import BN_EPS, BN_MOMENTUM, arch_spec
 
 
 class Emulator:
-    def __init__(self, st, arch, in_channel, round_bf16=True, update_running=False):
+    def __init__(self, st, arch, in_channel, round_bf16=True, update_running=False, direct_boundary=True):
         self.st, self.arch, self.cin = st, arch, in_channel
         self.round = round_bf16
         self.update_running = update_running
+        # the engine runs the first conv / last conv-transpose *forward* on fp32 CUDA-core kernels (no operand
+        # rounding there); their data- and weight-gradients still go through the bf16 tensor-core GEMMs
+        self.direct = direct_boundary
 
     def r(self, x):
         return x.to(torch.bfloat16).to(x.dtype) if self.round else x
@@ -76,9 +79,12 @@ class Emulator:
         tape = {"x": x}
         a = r(x)
         tape["enc"] = []
-        for (i, ci, co, k, s, p) in enc:
+        for li, (i, ci, co, k, s, p) in enumerate(enc):
             w = r(st[f"encoder.{i}.weight"])
-            acc = F.conv2d(a, w, st[f"encoder.{i}.bias"], stride=s, padding=p)
+            if li == 0 and self.direct:
+                acc = F.conv2d(x, st[f"encoder.{i}.weight"], st[f"encoder.{i}.bias"], stride=s, padding=p)
+            else:
+                acc = F.conv2d(a, w, st[f"encoder.{i}.bias"], stride=s, padding=p)
             scale, shift, mean, invstd = self._bn_fwd(acc, f"encoder.{i + 1}", (0, 2, 3))
             y = r(acc)
             a_in = a
@@ -110,9 +116,15 @@ class Emulator:
         n = len(dec)
         for j, (i, ci, co, k, s, p, op) in enumerate(dec):
             w = r(st[f"decoder.{i}.weight"])
-            acc = F.conv_transpose2d(a, w, st[f"decoder.{i}.bias"], stride=s, padding=p, output_padding=op)
-            scale, shift, mean, invstd = self._bn_fwd(acc, f"decoder.{i + 1}", (0, 2, 3))
             last = j == n - 1
+            if last and self.direct and j > 0:
+                P = tape["dec"][-1]  # unrounded activation of the stored (rounded) raw tensor, fp32 weights
+                a32 = torch.relu(P["y"] * self._bc(P["scale"], 4) + self._bc(P["shift"], 4))
+                acc = F.conv_transpose2d(a32, st[f"decoder.{i}.weight"], st[f"decoder.{i}.bias"], stride=s, padding=p,
+                                         output_padding=op)
+            else:
+                acc = F.conv_transpose2d(a, w, st[f"decoder.{i}.bias"], stride=s, padding=p, output_padding=op)
+            scale, shift, mean, invstd = self._bn_fwd(acc, f"decoder.{i + 1}", (0, 2, 3))
             y = acc if last else r(acc)
             a_in = a
             if last:

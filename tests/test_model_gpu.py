@@ -83,7 +83,7 @@ def test_engine_matches_bf16_emulator_on_shallow_net():
     g, meta, hyper, m, st0, out, slope = run_cuda_step("clear_vae28_ps")
     em = emulated_step(st0, meta, hyper, g, True, slope, device=DEV)
     lat = torch.cat([out["lp"][k] for k in ("mu_c", "logvar_c", "mu_s", "logvar_s")], 1)
-    assert l2(lat, em["lat"]) < 5e-4
+    assert l2(lat, em["lat"]) < 1e-3
     assert l2(out["xhat"], em["xhat"]) < 5e-3
     assert rel(out["recon"], em["recon"]) < 1e-4 and rel(out["sc"][2], em["c"]) < 1e-3
     worst = 0.0
