@@ -410,6 +410,97 @@ bool conv_direct_fwd(at::IntArrayRef geom, int64_t batch, const Tensor& src, at:
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// MI estimators (CLUB-S / L1OutUB) and fused Adam
+// ---------------------------------------------------------------------------
+std::tuple<Tensor, Tensor, Tensor> mi_estimator(int64_t mode, const Tensor& x, const Tensor& y, const OptTensor& perm,
+                                                at::TensorList params, Tensor workspace) {
+  check_f32(x, "x");
+  check_f32(y, "y");
+  const c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && y.dim() == 2 && x.size(0) == y.size(0), "clearvae: x / y must be [B, D] with equal B");
+  TORCH_CHECK(params.size() == 8, "clearvae: 8 estimator parameters expected");
+  const int64_t B = x.size(0), Dx = x.size(1), Dy = y.size(1), H = params[0].size(0);
+  const float* pp[8];
+  const int64_t want[8][2] = {{H, Dx}, {H, 0}, {Dy, H}, {Dy, 0}, {H, Dx}, {H, 0}, {Dy, H}, {Dy, 0}};
+  int64_t P = 0;
+  for (int i = 0; i < 8; ++i) {
+    check_f32(params[i], "estimator parameter");
+    TORCH_CHECK(params[i].size(0) == want[i][0] && (want[i][1] == 0 ? params[i].dim() == 1 : params[i].size(1) == want[i][1]),
+                "clearvae: estimator parameter ", i, " has the wrong shape");
+    pp[i] = params[i].data_ptr<float>();
+    P += params[i].numel();
+  }
+  const int64_t* pm = nullptr;
+  if (perm.has_value() && perm->defined()) {
+    check_i64(*perm, "perm");
+    TORCH_CHECK(perm->numel() == B, "clearvae: perm must have B entries");
+    pm = perm->data_ptr<int64_t>();
+  }
+  auto fopt = x.options();
+  const bool learn = mode == CLEARVAE_MI_LEARN;
+  Tensor out = at::empty({learn ? 1 + P : mode == CLEARVAE_MI_L1OUT ? 1 + 2 * Dy : 1}, fopt);
+  Tensor dx = learn ? at::empty({0}, fopt) : at::empty({B, Dx}, fopt);
+  Tensor dy = learn ? at::empty({0}, fopt) : at::empty({B, Dy}, fopt);
+  TORCH_CHECK(workspace.is_cuda() && workspace.is_contiguous(), "clearvae: workspace must be a contiguous CUDA tensor");
+  check_rc(clearvae_mi_estimator((int32_t)mode, x.data_ptr<float>(), y.data_ptr<float>(), pm, B, (int32_t)Dx, (int32_t)H,
+                                 (int32_t)Dy, pp, out.data_ptr<float>(), learn ? nullptr : dx.data_ptr<float>(),
+                                 learn ? nullptr : dy.data_ptr<float>(), workspace.data_ptr(), (size_t)workspace.nbytes(),
+                                 cur_stream()),
+           "mi_estimator");
+  return {out, dx, dy};
+}
+
+std::tuple<Tensor, Tensor> mi_bound_bwd(int64_t mode, const Tensor& grad_out, const Tensor& dx_unit, const Tensor& dy_unit,
+                                        const Tensor& y, const Tensor& out_fwd) {
+  check_f32(grad_out, "grad_out");
+  check_f32(dx_unit, "dx_unit");
+  check_f32(dy_unit, "dy_unit");
+  check_f32(y, "y");
+  check_f32(out_fwd, "out_fwd");
+  const c10::cuda::CUDAGuard guard(y.device());
+  Tensor gx = at::empty_like(dx_unit), gy = at::empty_like(dy_unit);
+  check_rc(clearvae_mi_bound_bwd((int32_t)mode, grad_out.data_ptr<float>(), dx_unit.data_ptr<float>(), dy_unit.data_ptr<float>(),
+                                 y.data_ptr<float>(), out_fwd.data_ptr<float>(), dx_unit.size(0), (int32_t)dx_unit.size(1),
+                                 (int32_t)dy_unit.size(1), gx.data_ptr<float>(), gy.data_ptr<float>(), cur_stream()),
+           "mi_bound_bwd");
+  return {gx, gy};
+}
+
+int64_t mi_workspace_bytes(int64_t mode, int64_t B, int64_t Dx, int64_t H, int64_t Dy) {
+  return (int64_t)clearvae_mi_workspace_bytes((int32_t)mode, B, (int32_t)Dx, (int32_t)H, (int32_t)Dy);
+}
+
+void adam_step(at::TensorList params, at::TensorList grads, at::TensorList exp_avg, at::TensorList exp_avg_sq, Tensor steps,
+               Tensor counter, double lr, double beta1, double beta2, double eps, double grad_scale) {
+  const size_t n = params.size();
+  TORCH_CHECK(grads.size() == n && exp_avg.size() == n && exp_avg_sq.size() == n, "clearvae: adam lists must have equal length");
+  if (n == 0) return;
+  const c10::cuda::CUDAGuard guard(params[0].device());
+  std::vector<float*> p(n), m(n), v(n);
+  std::vector<const float*> g(n);
+  std::vector<int64_t> ne(n);
+  for (size_t i = 0; i < n; ++i) {
+    check_f32(params[i], "param");
+    check_f32(grads[i], "grad");
+    check_f32(exp_avg[i], "exp_avg");
+    check_f32(exp_avg_sq[i], "exp_avg_sq");
+    ne[i] = params[i].numel();
+    TORCH_CHECK(grads[i].numel() == ne[i] && exp_avg[i].numel() == ne[i] && exp_avg_sq[i].numel() == ne[i],
+                "clearvae: adam tensor sizes differ");
+    p[i] = params[i].data_ptr<float>(); g[i] = grads[i].data_ptr<float>();
+    m[i] = exp_avg[i].data_ptr<float>(); v[i] = exp_avg_sq[i].data_ptr<float>();
+  }
+  check_f32(steps, "steps");
+  TORCH_CHECK(counter.is_cuda() && counter.scalar_type() == at::kInt && counter.numel() >= 1, "clearvae: counter must be a CUDA int32 tensor");
+  check_rc(clearvae_adam_step((int32_t)n, p.data(), g.data(), m.data(), v.data(), ne.data(), steps.data_ptr<float>(),
+                              (int32_t)steps.numel(), reinterpret_cast<unsigned int*>(counter.data_ptr<int32_t>()), (float)lr,
+                              (float)beta1, (float)beta2, (float)eps, (float)grad_scale, cur_stream()),
+           "adam_step");
+  // the packed bf16 weight copies are refreshed when a master's version counter moves (engine._PackCache)
+  for (size_t i = 0; i < n; ++i) params[i].unsafeGetTensorImpl()->bump_version();
+}
+
 int64_t bn_act_workspace_bytes() { return (int64_t)clearvae_bn_act_workspace_bytes(); }
 
 }  // namespace
@@ -442,6 +533,11 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("bn_bwd_coef(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor mean, Tensor invstd) -> (Tensor, Tensor, Tensor)");
   m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, Tensor coef, int C, int inner, bool to_nhwc, int out_dtype) -> Tensor");
   m.def("colsum(Tensor x) -> Tensor");
+  m.def("mi_estimator(int mode, Tensor x, Tensor y, Tensor? perm, Tensor[] params, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor)");
+  m.def("mi_bound_bwd(int mode, Tensor grad_out, Tensor dx_unit, Tensor dy_unit, Tensor y, Tensor out_fwd) -> (Tensor, Tensor)");
+  m.def("mi_workspace_bytes(int mode, int B, int Dx, int H, int Dy) -> int", &mi_workspace_bytes);
+  m.def("adam_step(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, Tensor(d!) steps, "
+        "Tensor(e!) counter, float lr, float beta1, float beta2, float eps, float grad_scale) -> ()");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "
         "bool pre_relu, Tensor packed_weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, int epilogue, "
@@ -466,4 +562,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("bn_bwd_coef", &bn_bwd_coef);
   m.impl("bn_bwd_apply", &bn_bwd_apply);
   m.impl("colsum", &colsum);
+  m.impl("mi_estimator", &mi_estimator);
+  m.impl("mi_bound_bwd", &mi_bound_bwd);
+  m.impl("adam_step", &adam_step);
 }

@@ -23,6 +23,7 @@ from .latent import S_KL0, S_KL1, S_LOSS0, S_LOSS1, DistSpec, latent_block
 from .losses import contrastive_loss, vae_loss  # noqa: F401  (re-exported like the reference module)
 from .models.mi_estimator import CLUBSample
 from .models.vae import VAE
+from .optim import fused_adam_step
 
 
 class LogisticAnnealer:
@@ -194,7 +195,7 @@ class CLEARVAETrainer(VAETrainer):
                                                         ps=[False, bool(hp["ps"])], sim_fn=self.sim_fn, eps=eps, dist=self.dist)
         torch.autograd.backward([recon, sc], [torch.ones_like(recon), self._weights_dev(X.device)])
         self._sync_grads(list(vae.parameters()))
-        self.optimizer.step()
+        fused_adam_step(self.optimizer)
         return recon, sc
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -258,7 +259,7 @@ class ClearTCVAETrainer(VAETrainer):
         mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         self._sync_grads(list(vae.parameters()))
-        self.optimizer.step()
+        fused_adam_step(self.optimizer)
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
@@ -269,7 +270,7 @@ class ClearTCVAETrainer(VAETrainer):
                                              torch.cat([torch.ones_like(d_joint), torch.zeros_like(d_marg)], 0))
         factor_loss.backward()
         self._sync_grads(list(fc.parameters()))
-        self.factor_optimizer.step()
+        fused_adam_step(self.factor_optimizer)
         return recon, sc, mi.detach(), factor_loss.detach()
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, factor_d_losses: list):
@@ -328,7 +329,7 @@ class ClearMIMVAETrainer(VAETrainer):
         mi = est(zc, zs, perm) if (perm is not None and isinstance(est, CLUBSample)) else est(zc, zs)
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         self._sync_grads(list(vae.parameters()))
-        self.optimizer.step()
+        fused_adam_step(self.optimizer)
         # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
         # The encoder is unchanged across the 5 iterations, so its output is computed once and its BatchNorm
         # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and
@@ -342,12 +343,10 @@ class ClearMIMVAETrainer(VAETrainer):
                 e = (torch.randn_like(lv_c), torch.randn_like(lv_s)) if inner_eps is None else inner_eps[j]
                 z2, _ = latent_block([mu_c, mu_s], [lv_c, lv_s], list(e), dummy, snn=[0, 0], ps=[0, 0])
                 vae._decode(z2, None, stats_only=True)
-            ll = est.learning_loss(z2[:, :D], z2[:, D:])
-            self.mi_estimator_optimizer.zero_grad()
-            ll.backward()
+            ll = est.learning_grads(z2[:, :D], z2[:, D:])   # loss + all parameter gradients: one launch
             self._sync_grads(list(est.parameters()))
-            self.mi_estimator_optimizer.step()
-            learn.append(ll.detach())
+            fused_adam_step(self.mi_estimator_optimizer)
+            learn.append(ll)
         return recon, sc, mi.detach(), torch.stack(learn)
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, mi_losses: list, mi_learning_losses: list):

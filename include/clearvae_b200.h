@@ -219,6 +219,40 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
                              const float* pre_shift, int32_t pre_relu, const float* weight, const float* bias,
                              const clearvae_tensor4* dst, double* stats, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Variational MI estimators of CLEAR-MIM (mi_estimator.py:108-198): Gaussian heads
+ *   p_mu = Linear(Dx,H)-ReLU-Linear(H,Dy),  p_logvar = Linear(Dx,H)-ReLU-Linear(H,Dy)-Tanh   (Dx, H, Dy <= 32).
+ * `params_host` = 8 device pointers in nn.Module.parameters() order
+ *   (p_mu.0.weight [H,Dx], p_mu.0.bias, p_mu.2.weight [Dy,H], p_mu.2.bias, p_logvar.0.weight, ...).
+ * One launch runs forward and backward of both MLPs:
+ *   CLEARVAE_MI_LEARN : out[0] = learning_loss(x, y) (mi_estimator.py:129-131,145-146), out[1..] = its gradient
+ *                       w.r.t. the 8 parameters, flattened in the order above;
+ *   CLEARVAE_MI_CLUB  : out[0] = CLUBSample.forward(x, y) with permutation `perm` (int64 [B], mi_estimator.py:133-143);
+ *   CLEARVAE_MI_L1OUT : out[0] = L1OutUB.forward(x, y) as the reference executes it (mi_estimator.py:170-191),
+ *                       out[1 .. 1+2*Dy) = column sums the backward needs;
+ *   the bound modes also write the unit gradients d out[0] / dx, d out[0] / dy (direct part) to dx_unit / dy_unit;
+ *   clearvae_mi_bound_bwd scales them by the incoming gradient (device scalar) and completes dy for L1OUT.
+ * `workspace` must be zero-initialised once (its first word is a self-resetting ticket counter).
+ * ------------------------------------------------------------------------- */
+enum { CLEARVAE_MI_LEARN = 0, CLEARVAE_MI_CLUB = 1, CLEARVAE_MI_L1OUT = 2 };
+size_t clearvae_mi_workspace_bytes(int32_t mode, int64_t B, int32_t Dx, int32_t H, int32_t Dy);
+int clearvae_mi_estimator(int32_t mode, const float* x, const float* y, const int64_t* perm, int64_t B, int32_t Dx, int32_t H,
+                          int32_t Dy, const float* const* params_host, float* out, float* dx_unit, float* dy_unit,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int clearvae_mi_bound_bwd(int32_t mode, const float* grad_out, const float* dx_unit, const float* dy_unit, const float* y,
+                          const float* out_fwd, int64_t B, int32_t Dx, int32_t Dy, float* gx, float* gy, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused multi-tensor Adam: torch.optim.Adam defaults as built by the reference factories
+ * (trainer_utils.py:100,139-140,178-181; no weight decay, no amsgrad).  The *_host arrays hold n_tensors
+ * device pointers; `steps` = n_steps device floats holding the common step count (all advanced by one),
+ * `counter` = one zero-initialised device word (self-resetting); gradients are multiplied by grad_scale.
+ * ------------------------------------------------------------------------- */
+#define CLEARVAE_ADAM_MAX_TENSORS 64 /* per launch; larger lists are split internally */
+int clearvae_adam_step(int32_t n_tensors, float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                       float* const* exp_avg_sq_host, const int64_t* numel_host, float* steps, int32_t n_steps,
+                       unsigned int* counter, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

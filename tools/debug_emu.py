@@ -16,6 +16,8 @@ def run(arch, B, zdim=64, cin=3):
     D = zdim // 2
     eps = (torch.randn(B, D, device="cuda"), torch.randn(B, D, device="cuda"))
     m._eng().debug = {}
+    direct = not os.environ.get("NO_DIRECT")
+    m._eng().use_direct = direct
     xhat, recon, z, sc, lp = m.fused_step_forward(X, label, temperature=0.1, snn=[1, 1], ps=[False, True], eps=eps)
     loss = recon + 0.03 * sc[0] + 0.03 * sc[1] + 100 * sc[2] + 100 * sc[3]
     loss.backward(); torch.cuda.synchronize()
@@ -23,7 +25,7 @@ def run(arch, B, zdim=64, cin=3):
     st = {k: (v.to(edev).to(edt) if v.is_floating_point() else v.to(edev)) for k, v in st.items()}
     X, label = X.to(edev).to(edt), label.to(edev)
     eps = (eps[0].to(edev).to(edt), eps[1].to(edev).to(edt))
-    em = Emulator(st, arch, cin, round_bf16=True, update_running=True)
+    em = Emulator(st, arch, cin, round_bf16=True, update_running=True, direct_boundary=direct)
     out = em.forward(X, eps[0], eps[1], target=X)
     dgr, dz = em.backward_decoder(out["tape"], X, 1.0)
     lat = out["lat"].detach().requires_grad_(True)
