@@ -263,15 +263,51 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_
   }
 }
 
-// out[c] (+)= sum over rows of x[r][c]  (bias gradients of the linear heads)
-__global__ void __launch_bounds__(kNT) colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* out) {
-  for (int c = blockIdx.x * kNT + threadIdx.x; c < cols; c += gridDim.x * kNT) {
-    float s = 0.f;
-    for (long long r = 0; r < rows; ++r) s += x[r * cols + c];
-    out[c] = s;
+// out[c] = sum over rows of x[r][c]  (bias gradients of the linear heads): 32 columns per CTA, 32 row groups
+// per column (coalesced 128-byte row segments), fixed-order shared-memory reduction
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* out) {
+  __shared__ float sp[32][33];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = rg; r < rows; r += 32) s += x[r * cols + c];
+  sp[rg][lane] = s;
+  __syncthreads();
+  if (rg == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += sp[i][lane];
+    out[c] = t;
   }
 }
 
+// act = relu(raw * scale[c] + shift[c]) on a channels-last bf16 tensor (C % 8 == 0): the BatchNorm-apply + ReLU
+// between two tensor-core GEMMs, materialised once so that the consumers' operand loads are plain cp.async copies.
+// HBM/L2 streaming: 16-byte loads and stores, scale / shift staged in shared memory.
+__global__ void __launch_bounds__(kNT) bn_relu_bf16_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, long long n8, int C,
+                                                           uint4* __restrict__ out) {
+  extern __shared__ float sAff[];  // [2][C]
+  for (int i = threadIdx.x; i < C; i += kNT) { sAff[i] = __ldg(scale + i); sAff[C + i] = __ldg(shift + i); }
+  __syncthreads();
+  const int C8 = C >> 3;
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n8; i += (long long)gridDim.x * kNT) {
+    const int c0 = (int)(i % C8) << 3;
+    const uint4 q = __ldg(raw + i);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float4 s0 = *reinterpret_cast<const float4*>(sAff + c0), s1 = *reinterpret_cast<const float4*>(sAff + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(sAff + C + c0), h1 = *reinterpret_cast<const float4*>(sAff + C + c0 + 4);
+    const float2 a = __bfloat1622float2(h2[0]), b = __bfloat1622float2(h2[1]), c = __bfloat1622float2(h2[2]), d = __bfloat1622float2(h2[3]);
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(fmaxf(fmaf(a.x, s0.x, h0.x), 0.f), fmaxf(fmaf(a.y, s0.y, h0.y), 0.f)); o.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(fmaxf(fmaf(b.x, s0.z, h0.z), 0.f), fmaxf(fmaf(b.y, s0.w, h0.w), 0.f)); o.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(fmaxf(fmaf(c.x, s1.x, h1.x), 0.f), fmaxf(fmaf(c.y, s1.y, h1.y), 0.f)); o.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(fmaxf(fmaf(d.x, s1.z, h1.z), 0.f), fmaxf(fmaf(d.y, s1.w, h1.w), 0.f)); o.w = *reinterpret_cast<uint32_t*>(&t);
+    out[i] = o;
+  }
+}
 
 // grid for the two-moment reductions: channel-blocked mapping when a channel spans >= 64 positions
 inline void reduce_grid(int C, long long inner, long long nper, dim3* grid, int* blocked) {
@@ -372,7 +408,20 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
 
 int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream) {
   if (!x || !out || rows <= 0 || cols <= 0) return CLEARVAE_EINVAL;
-  colsum_kernel<<<(cols + kNT - 1) / kNT, kNT, 0, (cudaStream_t)stream>>>(x, rows, cols, out);
+  colsum_kernel<<<(cols + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(x, rows, cols, out);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_bn_relu_apply(const void* raw_bf16, const float* scale, const float* shift, int64_t total, int32_t C, void* act_bf16,
+                           void* stream) {
+  if (!raw_bf16 || !scale || !shift || !act_bf16 || total <= 0 || C <= 0) return CLEARVAE_EINVAL;
+  if (C % 8 != 0 || total % C != 0 || C > 4096 || ((uintptr_t)raw_bf16 & 15) || ((uintptr_t)act_bf16 & 15)) return CLEARVAE_EUNSUPPORTED;
+  const long long n8 = total / 8;
+  long long g = (n8 + kNT - 1) / kNT;
+  if (g > 148 * 8) g = 148 * 8;
+  bn_relu_bf16_kernel<<<(unsigned)g, kNT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(raw_bf16), scale, shift, n8, C, reinterpret_cast<uint4*>(act_bf16));
   CV_LAUNCH_CHECK();
   return 0;
 }

@@ -35,6 +35,18 @@ constexpr int kThreads = 192;
 constexpr int kTabMax = 256;    // entries of the k -> (tap, channel) table used by the scalar gather
 constexpr int kMaxPreC = 2048;  // source channels whose BatchNorm scale/shift are staged in shared memory
 
+// optional per-CTA phase timeline (tools/conv_timeline.py): 8 x int64 per CTA, written by one thread per role
+__device__ long long* g_conv_timeline = nullptr;
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CV_TL(slot)                                                                                          \
+  do {                                                                                                       \
+    if (tl_buf) tl_buf[(((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
+  } while (0)
+
 struct TmapPack {
   CUtensorMap t[cvplan::kMaxClasses];
 };
@@ -95,6 +107,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   float* sScale = reinterpret_cast<float*>(sTapOff + cvplan::kMaxTaps); // pre-op scale / shift of the source channels
   float* sShift = sScale + kMaxPreC;
 
+  long long* const tl_buf = g_conv_timeline;
+  if (threadIdx.x == 0) CV_TL(0);
   const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const Cls& c = p.plan.cls[cls_id];
   const long long Mc = p.batch * c.Hd * c.Wd;
@@ -135,6 +149,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) CV_TL(1);
 
   if (warp < 4) {
     // ================= A producer: one thread per tile row =================
@@ -160,7 +175,44 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // incremental (tap, channel) of the next 8-chunk (vector path)
     int t_cur = vec ? (kb0 * BK) / Cs : 0, c_cur = vec ? (kb0 * BK) % Cs : 0;
     const bool has_pre = p.pre_scale != nullptr;
-    for (int kb = 0; kb < nkb; ++kb) {
+    // Pure-copy operand (already activated bf16, channels contiguous): cp.async straight into the interleave layout,
+    // zero-fill for padding taps / K padding; a k-block is announced two iterations after it was issued, so up to
+    // three k-blocks of loads are in flight per thread and nothing is staged through registers.
+    const bool cpa = vec && p.src_bf16 && !has_pre && !p.pre_relu;
+    if (cpa) {
+      const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        const uint32_t dst = smem_u32(sA + s * kAStage) + r * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kg = (kb0 + kb) * BK + j * 8;
+          const bool v = kg < Kreal && ((tapmask >> t_cur) & 1u);
+          const long long off = v ? base + sTapOff[t_cur & (cvplan::kMaxTaps - 1)] + c_cur : 0;
+          cp_async16(dst + j * (BM * 16), srcb + off, v ? 16u : 0u);
+          c_cur += 8;
+          if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
+        }
+        cp_async_commit();
+        if (kb >= 2) {
+          cp_async_wait<2>();
+          fence_proxy_async();
+          mbar_arrive(&full[(kb - 2) % NS]);
+        }
+      }
+      if (nkb >= 2) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&full[(nkb - 2) % NS]);
+      }
+      if (threadIdx.x == 0) CV_TL(2);
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&full[(nkb - 1) % NS]);
+      if (threadIdx.x == 0) CV_TL(3);
+    }
+    for (int kb = 0; kb < (cpa ? 0 : nkb); ++kb) {
       const int s = kb % NS;
       unsigned char* a_st = sA + s * kAStage;
       if (vec) {
@@ -261,12 +313,118 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // ================= epilogue: TMEM -> registers -> global =================
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) CV_TL(4);
     const long long dst_off = img * p.d_n + (long long)(hd * p.plan.os + c.oa) * p.d_h + (long long)(wd * p.plan.os + c.ob) * p.d_w;
     const long long msk_off = img * p.m_n + (long long)(hd * p.plan.os + c.oa) * p.m_h + (long long)(wd * p.plan.os + c.ob) * p.m_w;
     const int Nn = p.plan.Nn;
     constexpr int CH = BN < 32 ? BN : 32;
+    // Fast epilogue (channels-last destination, full column tile): vector stores straight from the TMEM registers,
+    // and the per-channel sums through a padded shared-memory transposition — thread (column, row-quarter) adds 32
+    // rows of its column, squares formed on the fly — ~170 instructions per 32-column chunk instead of the ~1100
+    // of the generic path below (two warp-butterflies + per-element predicates), which bounded the whole kernel.
+    const bool fast = p.splits == 1 && p.d_c == 1 && n0 + BN <= Nn && ((p.d_n | p.d_h | p.d_w) & 7) == 0 &&
+                      (p.epi == CLEARVAE_EPI_BIAS_STATS || (p.m_c == 1 && ((p.m_n | p.m_h | p.m_w) & 7) == 0));
+    if (fast) {
+      constexpr int LD = 36;                               // padded row stride (floats): conflict-free both ways
+      float* sEp = reinterpret_cast<float*>(sA);           // the operand stages are dead once tmem_full has fired
+      float* sEp2 = sEp + BM * LD;
+      float* sRed = sEp2 + BM * LD;                        // [2][4][32]
+      const bool masked = p.epi != CLEARVAE_EPI_BIAS_STATS;
 #pragma unroll 1
-    for (int ch0 = 0; ch0 < BN; ch0 += CH) {
+      for (int ch0 = 0; ch0 < BN; ch0 += CH) {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
+        if (CH == 32) {
+          tmem_ld32(taddr, raw);
+        } else {
+          uint32_t r16[16];
+          tmem_ld16(taddr, r16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+        }
+        const int nb = n0 + ch0;
+        float v[CH], u[CH];
+        if (!masked) {
+          float bsv[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) bsv[i] = p.bias != nullptr ? __ldg(p.bias + nb + i) : 0.f;
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = mvalid ? __uint_as_float(raw[i]) + bsv[i] : 0.f;
+        } else {
+          float y[CH];
+          if (p.msk_bf16) {
+            const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.msk) + (mvalid ? msk_off + nb : 0));
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+              const uint4 q = __ldg(mp + i);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); y[8 * i + 2 * k] = f.x; y[8 * i + 2 * k + 1] = f.y; }
+            }
+          } else {
+            const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.msk) + (mvalid ? msk_off + nb : 0));
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) { const float4 q = __ldg(mp + i); y[4 * i] = q.x; y[4 * i + 1] = q.y; y[4 * i + 2] = q.z; y[4 * i + 3] = q.w; }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float act = p.msk_scale ? fmaf(y[i], __ldg(p.msk_scale + nb + i), __ldg(p.msk_shift + nb + i)) : y[i];
+            const float a = (mvalid && act > 0.f) ? __uint_as_float(raw[i]) : 0.f;
+            v[i] = a;
+            u[i] = a * y[i];
+          }
+        }
+        if (mvalid) {
+          if (p.dst_bf16) {
+            uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + nb);
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i)
+              d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dst) + dst_off + nb);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+        if (p.stats != nullptr) {
+          float4* row = reinterpret_cast<float4*>(sEp + r * LD);
+#pragma unroll
+          for (int i = 0; i < CH / 4; ++i) row[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (masked) {
+            float4* row2 = reinterpret_cast<float4*>(sEp2 + r * LD);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) row2[i] = make_float4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float s1 = 0.f, s2 = 0.f;
+          if (lane < CH) {
+            const float* col = sEp + (warp * 32) * LD + lane;
+            if (!masked) {
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) { const float a = col[rr * LD]; s1 += a; s2 = fmaf(a, a, s2); }
+            } else {
+              const float* col2 = sEp2 + (warp * 32) * LD + lane;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) { s1 += col[rr * LD]; s2 += col2[rr * LD]; }
+            }
+          }
+          sRed[warp * 32 + lane] = s1;
+          sRed[128 + warp * 32 + lane] = s2;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 0 && lane < CH) {
+            const float a = (sRed[lane] + sRed[32 + lane]) + (sRed[64 + lane] + sRed[96 + lane]);
+            const float b = (sRed[128 + lane] + sRed[160 + lane]) + (sRed[192 + lane] + sRed[224 + lane]);
+            atomicAdd(p.stats + nb + lane, (double)a);
+            atomicAdd(p.stats + Nn + nb + lane, (double)b);
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int ch0 = fast ? BN : 0; ch0 < BN; ch0 += CH) {
       uint32_t raw[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
       if (CH == 32) {
@@ -387,9 +545,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       umma_commit(tmem_full);
     }
   }
+  if (threadIdx.x == 0) CV_TL(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (threadIdx.x == 128) CV_TL(6);
 }
 
 
@@ -462,7 +622,66 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
     const int px = threadIdx.x & 63, hf = threadIdx.x >> 6;
     const bool vec = (Cs % 8 == 0) && p.s_c == 1;
     const int Nn = p.plan.Nn;
-    for (int kb = 0; kb < nkb; ++kb) {
+    // both operands are plain bf16 channel runs: cp.async them into the MN-major interleave layout (zero-fill for
+    // padding taps / rows past the problem), announcing each k-block two iterations after it was issued
+    const bool cpa = vec && p.src_bf16 && p.pre_scale == nullptr && !p.pre_relu && p.y_c == 1 && p.dy_bf16 && (Nn % 8 == 0);
+    if (cpa) {
+      const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
+      const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(p.dy);
+      constexpr int NG = BN / 8, NGH = (NG + 1) / 2;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NS;
+        const long long m = (kb_begin + kb) * WK + px;
+        const bool mvalid = m < Mc;
+        const long long mm = mvalid ? m : 0;
+        const int wd = (int)(mm % c.Wd);
+        const int hd = (int)((mm / c.Wd) % c.Hd);
+        const long long img = mm / ((long long)c.Wd * c.Hd);
+        const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
+        const long long img_off = img * p.s_n;
+        const long long dy_off = img * p.y_n + (long long)(hd * p.plan.os + c.oa) * p.y_h + (long long)(wd * p.plan.os + c.ob) * p.y_w;
+        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        const uint32_t a_dst = smem_u32(sA + s * kWStageA) + px * 16, b_dst = smem_u32(sB + s * kBStage) + px * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int grp = hf * 8 + j;
+          const int kidx = k0 + grp * 8;
+          bool v = mvalid && kidx < Kreal;
+          long long off = 0;
+          if (v) {
+            const int t = kidx / Cs, ch = kidx - t * Cs;
+            const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+            v = hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws;
+            off = v ? img_off + hs * p.s_h + ws * p.s_w + ch : 0;
+          }
+          cp_async16(a_dst + grp * (WK * 16), srcb + off, v ? 16u : 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < NGH; ++j) {
+          const int grp = hf * NGH + j;
+          if (grp < NG) {
+            const int n = n0 + grp * 8;
+            const bool v = mvalid && n + 8 <= Nn;
+            cp_async16(b_dst + grp * (WK * 16), dyb + (v ? dy_off + n : 0), v ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (kb >= 2) {
+          cp_async_wait<2>();
+          fence_proxy_async();
+          mbar_arrive(&full[(kb - 2) % NS]);
+        }
+      }
+      if (nkb >= 2) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&full[(nkb - 2) % NS]);
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&full[(nkb - 1) % NS]);
+    }
+    for (int kb = 0; kb < (cpa ? 0 : nkb); ++kb) {
       const int s = kb % NS;
       const long long m = (kb_begin + kb) * WK + px;
       const bool mvalid = m < Mc;
@@ -733,6 +952,11 @@ int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+int clearvae_debug_conv_timeline(long long* device_buffer) {
+  cudaError_t e = cudaMemcpyToSymbol(g_conv_timeline, &device_buffer, sizeof(device_buffer));
+  return e == cudaSuccess ? 0 : (int)e;
+}
 
 int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
                         const float* pre_shift, int32_t pre_relu, const clearvae_tensor4* dy, float* dweight, void* stream) {

@@ -383,6 +383,19 @@ Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, cons
   return dy;
 }
 
+Tensor bn_relu_apply(const Tensor& raw, const Tensor& scale, const Tensor& shift, int64_t C) {
+  const c10::cuda::CUDAGuard guard(raw.device());
+  TORCH_CHECK(raw.is_cuda() && raw.is_contiguous() && raw.scalar_type() == at::kBFloat16, "clearvae: raw must be contiguous CUDA bf16");
+  check_f32(scale, "scale");
+  check_f32(shift, "shift");
+  TORCH_CHECK(scale.numel() >= C && shift.numel() >= C, "clearvae: scale / shift too small");
+  Tensor out = at::empty_like(raw);
+  check_rc(clearvae_bn_relu_apply(raw.data_ptr(), scale.data_ptr<float>(), shift.data_ptr<float>(), raw.numel(), (int32_t)C,
+                                  out.data_ptr(), cur_stream()),
+           "bn_relu_apply");
+  return out;
+}
+
 Tensor colsum(const Tensor& x) {
   check_f32(x, "x");
   const c10::cuda::CUDAGuard guard(x.device());
@@ -533,6 +546,7 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("bn_bwd_coef(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor mean, Tensor invstd) -> (Tensor, Tensor, Tensor)");
   m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, Tensor coef, int C, int inner, bool to_nhwc, int out_dtype) -> Tensor");
   m.def("colsum(Tensor x) -> Tensor");
+  m.def("bn_relu_apply(Tensor raw, Tensor scale, Tensor shift, int C) -> Tensor");
   m.def("mi_estimator(int mode, Tensor x, Tensor y, Tensor? perm, Tensor[] params, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor)");
   m.def("mi_bound_bwd(int mode, Tensor grad_out, Tensor dx_unit, Tensor dy_unit, Tensor y, Tensor out_fwd) -> (Tensor, Tensor)");
   m.def("mi_workspace_bytes(int mode, int B, int Dx, int H, int Dy) -> int", &mi_workspace_bytes);
@@ -562,6 +576,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("bn_bwd_coef", &bn_bwd_coef);
   m.impl("bn_bwd_apply", &bn_bwd_apply);
   m.impl("colsum", &colsum);
+  m.impl("bn_relu_apply", &bn_relu_apply);
   m.impl("mi_estimator", &mi_estimator);
   m.impl("mi_bound_bwd", &mi_bound_bwd);
   m.impl("adam_step", &adam_step);

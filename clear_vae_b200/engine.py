@@ -112,7 +112,7 @@ class EncoderFn(torch.autograd.Function):
         x = x.contiguous()
         need_grad = any(ctx.needs_input_grad)
         src, src_strides, pre = x, nchw_strides(specs[0].cin, specs[0].hin, specs[0].hin), None
-        saved_raw, saved_pre, saved_stats = [], [], []
+        saved_raw, saved_pre, saved_stats, saved_act = [], [], [], []
         n = len(specs)
         for i, sp in enumerate(specs):
             w, b, gamma, beta = params[4 * i:4 * i + 4]
@@ -141,27 +141,34 @@ class EncoderFn(torch.autograd.Function):
             saved_raw.append((raw, dst_strides))
             saved_pre.append((scale, shift))
             saved_stats.append((mean, invstd))
-            src, src_strides, pre = raw, dst_strides, (scale, shift)
+            if eng.materialize and raw.dtype == torch.bfloat16:
+                # BatchNorm-apply + ReLU written once (bf16): every consumer GEMM then cp.async-copies its operand
+                act = ops.bn_relu_apply(raw, scale, shift, scale.numel())
+                saved_act.append(act)
+                src, src_strides, pre = act, dst_strides, None
+            else:
+                saved_act.append(None)
+                src, src_strides, pre = raw, dst_strides, (scale, shift)
         # linear heads on the flattened (channel-major) encoder output
         K = specs[-1].cout * specs[-1].hout ** 2
         N = heads_w.shape[0]
         lat = torch.empty(B, N, dtype=torch.float32, device=dev)
         hg = linear_geom(K, N)
         pw = eng.packs.get("heads", heads_w, hg, FPROP, cacheable=False)
-        ops.conv_gemm(hg, FPROP, B, src, [K, 0, 0, 1], pre[0], pre[1], True, pw, heads_b, lat, [N, 0, 0, 1], EPI_BIAS_STATS,
-                      None, [0, 0, 0, 0], None, None, None)
+        ops.conv_gemm(hg, FPROP, B, src, [K, 0, 0, 1], pre[0] if pre else None, pre[1] if pre else None, pre is not None, pw,
+                      heads_b, lat, [N, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
         if eng.debug is not None:
             eng.debug["enc_raw"] = [r for r, _ in saved_raw]
         if need_grad:
             ctx.eng = eng
-            ctx.saved = (x, saved_raw, saved_pre, saved_stats, heads_w, params)
+            ctx.saved = (x, saved_raw, saved_pre, saved_stats, saved_act, heads_w, params)
         return lat
 
     @staticmethod
     def backward(ctx, dlat):
         ops = _ops.ops()
         eng = ctx.eng
-        x, saved_raw, saved_pre, saved_stats, heads_w, params = ctx.saved
+        x, saved_raw, saved_pre, saved_stats, saved_act, heads_w, params = ctx.saved
         specs = eng.enc_specs
         if not eng.training:
             raise RuntimeError("clear_vae_b200: backward through eval-mode BatchNorm is not implemented")
@@ -176,7 +183,10 @@ class EncoderFn(torch.autograd.Function):
         sc_last, sh_last = saved_pre[-1]
         # heads: weight / bias gradients
         d_heads_w = torch.zeros_like(heads_w)
-        ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w)
+        if saved_act[-1] is not None:
+            ops.conv_wgrad(hg, B, saved_act[-1], [K, 0, 0, 1], None, None, False, dlat, [N, 0, 0, 1], d_heads_w)
+        else:
+            ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w)
         d_heads_b = ops.colsum(dlat)
         # heads: data gradient with the last block's ReLU mask + BatchNorm sums in the epilogue
         g = torch.empty(B, K, dtype=eng.grad_dtype, device=dev)
@@ -207,8 +217,11 @@ class EncoderFn(torch.autograd.Function):
             else:
                 src, src_strides = saved_raw[i - 1]
                 pre = saved_pre[i - 1]
-            ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
-                           dy, raw_strides, dw)
+            if i > 0 and saved_act[i - 1] is not None:
+                ops.conv_wgrad(sp.geom, B, saved_act[i - 1], src_strides, None, None, False, dy, raw_strides, dw)
+            else:
+                ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
+                               dy, raw_strides, dw)
             grads[4 * i], grads[4 * i + 2], grads[4 * i + 3] = dw, dgamma, dbeta
             # grads[4*i+1] (conv bias) stays None: a bias feeding a train-mode BatchNorm has exactly zero gradient
             if i > 0:
@@ -250,7 +263,7 @@ class DecoderFn(torch.autograd.Function):
         # BatchNorm1d + ReLU, written channels-last so the first transposed conv gathers 16-byte channel runs
         a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, C0, H0 * H0, _DT[eng.act_dtype], None, B, _ws(dev))
         src, src_strides, pre = a_fc, nhwc_strides(H0, H0, C0), None
-        saved_raw, saved_pre, saved_stats = [], [], []
+        saved_raw, saved_pre, saved_stats, saved_act = [], [], [], []
         n = len(specs)
         for j, sp in enumerate(specs):
             w, b, gamma, beta = params[4 * j:4 * j + 4]
@@ -264,9 +277,9 @@ class DecoderFn(torch.autograd.Function):
                 raw = torch.empty(B, H, H, sp.cout, dtype=eng.act_dtype, device=dev)
                 dst_strides = nhwc_strides(H, H, sp.cout)
             st = eng.stat_buf(("dec", j), sp.cout, dev) if eng.training else None
-            if not (last and eng.use_direct and pre is not None and
-                    ops.conv_direct_fwd(sp.geom, B, src, src_strides, pre[0], pre[1], True, w.detach(), b.detach(), raw,
-                                        dst_strides, st)):
+            if not (last and eng.use_direct and j > 0 and
+                    ops.conv_direct_fwd(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                                        pre is not None, w.detach(), b.detach(), raw, dst_strides, st)):
                 ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
                               pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS,
                               None, [0, 0, 0, 0], None, None, st)
@@ -279,7 +292,13 @@ class DecoderFn(torch.autograd.Function):
             saved_raw.append((raw, dst_strides))
             saved_pre.append((scale, shift))
             saved_stats.append((mean, invstd))
-            src, src_strides, pre = raw, dst_strides, (scale, shift)
+            if eng.materialize and not last and raw.dtype == torch.bfloat16:
+                act = ops.bn_relu_apply(raw, scale, shift, sp.cout)
+                saved_act.append(act)
+                src, src_strides, pre = act, dst_strides, None
+            else:
+                saved_act.append(None)
+                src, src_strides, pre = raw, dst_strides, (scale, shift)
         sp = specs[-1]
         H = sp.hout
         if eng.stats_only:  # caller only wants the BatchNorm running-statistic side effects (CLEAR-MIM inner loop)
@@ -292,7 +311,8 @@ class DecoderFn(torch.autograd.Function):
         if need_grad:
             ctx.eng = eng
             ctx.has_target = target is not None
-            ctx.saved = (z, target, fc_w, fc_g, raw_fc, a_fc, (sc, sh), mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params)
+            ctx.saved = (z, target, fc_w, fc_g, raw_fc, a_fc, (sc, sh), mean_fc, inv_fc, saved_raw, saved_pre, saved_stats,
+                         saved_act, params)
             ctx.save_for_backward(xhat)
         return xhat, recon
 
@@ -300,7 +320,8 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, d_xhat, d_recon):
         ops = _ops.ops()
         eng = ctx.eng
-        (z, target, fc_w, fc_g, raw_fc, a_fc, fc_aff, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, params) = ctx.saved
+        (z, target, fc_w, fc_g, raw_fc, a_fc, fc_aff, mean_fc, inv_fc, saved_raw, saved_pre, saved_stats, saved_act,
+         params) = ctx.saved
         (xhat,) = ctx.saved_tensors
         if not eng.training:
             raise RuntimeError("clear_vae_b200: backward through eval-mode BatchNorm is not implemented")
@@ -336,8 +357,11 @@ class DecoderFn(torch.autograd.Function):
             else:
                 src, src_strides = saved_raw[j - 1]
                 pre = saved_pre[j - 1]
-            ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
-                           dy, raw_strides, dw)
+            if j > 0 and saved_act[j - 1] is not None:
+                ops.conv_wgrad(sp.geom, B, saved_act[j - 1], src_strides, None, None, False, dy, raw_strides, dw)
+            else:
+                ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
+                               dy, raw_strides, dw)
             grads[4 * j], grads[4 * j + 2], grads[4 * j + 3] = dw, dgamma, dbeta
             pwd = eng.packs.get(("dec", j), w, sp.geom, DGRAD)
             if j > 0:
@@ -386,6 +410,7 @@ class Engine:
         self.dist = None      # DistSpec for SyncBN
         self.sync_bn = False
         self.use_direct = True   # direct kernels for the Cin<=4 / Cout<=4 boundary layers
+        self.materialize = True  # write relu(bn(raw)) once in bf16 so the GEMM operand loads are pure cp.async copies
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev)

@@ -207,6 +207,10 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
                           const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
                           int64_t inner, int32_t to_nhwc /* write [b][hw][c] instead of [b][c][hw] */, void* dy,
                           int32_t dy_dtype, void* stream);
+/* act = relu(raw * scale[c] + shift[c]) on a channels-last bf16 tensor, C % 8 == 0: BatchNorm-apply + ReLU
+ * (vae.py:17-18 etc.) materialised once between two GEMMs so their operand loads are plain async copies */
+int clearvae_bn_relu_apply(const void* raw_bf16, const float* scale, const float* shift, int64_t total, int32_t C, void* act_bf16,
+                           void* stream);
 /* out[c] = sum_r x[r][c]  (bias gradients of the linear heads) */
 int clearvae_colsum(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 
@@ -218,6 +222,10 @@ int clearvae_conv_direct_supported(const clearvae_conv_geom* g, const clearvae_t
 int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
                              const float* pre_shift, int32_t pre_relu, const float* weight, const float* bias,
                              const clearvae_tensor4* dst, double* stats, void* stream);
+
+/* profiling hook (tools/conv_timeline.py): when non-NULL, every CTA of clearvae_conv_gemm writes 8 int64
+ * %globaltimer stamps (start, prologue done, loads issued, loads landed, accumulator ready, epilogue done, exit) */
+int clearvae_debug_conv_timeline(long long* device_buffer);
 
 /* ---------------------------------------------------------------------------
  * Variational MI estimators of CLEAR-MIM (mi_estimator.py:108-198): Gaussian heads

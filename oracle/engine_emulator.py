@@ -118,9 +118,8 @@ class Emulator:
             w = r(st[f"decoder.{i}.weight"])
             last = j == n - 1
             if last and self.direct and j > 0:
-                P = tape["dec"][-1]  # unrounded activation of the stored (rounded) raw tensor, fp32 weights
-                a32 = torch.relu(P["y"] * self._bc(P["scale"], 4) + self._bc(P["shift"], 4))
-                acc = F.conv_transpose2d(a32, st[f"decoder.{i}.weight"], st[f"decoder.{i}.bias"], stride=s, padding=p,
+                # direct fp32 kernel: the materialised (bf16-rounded) activation times the fp32 master weights
+                acc = F.conv_transpose2d(a, st[f"decoder.{i}.weight"], st[f"decoder.{i}.bias"], stride=s, padding=p,
                                          output_padding=op)
             else:
                 acc = F.conv_transpose2d(a, w, st[f"decoder.{i}.bias"], stride=s, padding=p, output_padding=op)
