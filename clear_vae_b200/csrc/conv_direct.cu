@@ -221,6 +221,113 @@ __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient of the same two boundary layers (Conv2d(C<=4 -> 32) and ConvTranspose2d(32 -> C<=4), stride 2, pad 1):
+// both are  dW[f][c][kh][kw] = sum_{n,h,w} feat[n,h,w,f] * img[n,c,2h-1+kh,2w-1+kw]  with a 32-channel channels-last bf16
+// "feature" side (dy of the first conv / the materialised input activation of the last conv-transpose) and a
+// <=4-channel NCHW "image" side (x / dy of the last layer) — vae.py:16,43,114,153 through autograd.
+// Register-blocked outer product on CUDA cores: lane = (feature group, pixel slot); each lane keeps C*K*K*FPT
+// accumulators, one image value feeds FPT FMAs, image loads are 8/16-lane broadcasts served by L1.  As a 128-row
+// tensor-core GEMM this shape (M = C*K*K = 27..48) ran the scalar gather path and took ~250 us per layer.
+template <int K, int C, int FPT, bool IMG_BF16>
+__global__ void __launch_bounds__(kNT) boundary_wgrad_kernel(const __nv_bfloat16* __restrict__ feat, const void* __restrict__ img,
+                                                             float* __restrict__ dw, int B, int Hf, int Wf, int Hi, int Wi) {
+  constexpr int FG = 32 / FPT;   // lanes per pixel slot
+  constexpr int PS = 32 / FG;    // pixel slots per warp
+  constexpr int KK = K * K;
+  __shared__ float sAcc[C * KK * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fg = lane % FG, pg = lane / FG;
+  float acc[C * KK][FPT];
+#pragma unroll
+  for (int i = 0; i < C * KK; ++i)
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) acc[i][j] = 0.f;
+  const long long npix = (long long)B * Hf * Wf;
+  const long long nwarps = (long long)gridDim.x * (kNT / 32);
+  for (long long q = (long long)blockIdx.x * (kNT / 32) + warp; q * PS < npix; q += nwarps) {
+    const long long pix = q * PS + pg;
+    const bool pv = pix < npix;
+    const long long pp = pv ? pix : 0;
+    const int w = (int)(pp % Wf), h = (int)((pp / Wf) % Hf);
+    const long long n = pp / ((long long)Wf * Hf);
+    float f[FPT];
+    {
+      const __nv_bfloat16* fp = feat + pp * 32 + fg * FPT;
+      if (FPT == 4) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(fp));
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        f[0] = a.x; f[1] = a.y; f[FPT - 2] = b.x; f[FPT - 1] = b.y;
+      } else {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(fp));
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        f[0] = a.x; f[1] = a.y;
+      }
+#pragma unroll
+      for (int j = 0; j < FPT; ++j) f[j] = pv ? f[j] : 0.f;
+    }
+    const int h0 = 2 * h - 1, w0 = 2 * w - 1;
+    bool rok[K], cok[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { rok[k] = pv && h0 + k >= 0 && h0 + k < Hi; cok[k] = w0 + k >= 0 && w0 + k < Wi; }
+    const long long ibase = (n * C * Hi + h0) * (long long)Wi + w0;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const long long off = ibase + ((long long)c * Hi + kh) * Wi + kw;
+          float xv = 0.f;
+          if (rok[kh] && cok[kw])
+            xv = IMG_BF16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(img) + off))
+                          : __ldg(reinterpret_cast<const float*>(img) + off);
+#pragma unroll
+          for (int j = 0; j < FPT; ++j) acc[c * KK + kh * K + kw][j] = fmaf(xv, f[j], acc[c * KK + kh * K + kw][j]);
+        }
+  }
+  // pixel slots -> one value per (tap, feature) per warp; warps -> one per CTA (shared memory); CTAs -> fp32 atomics
+#pragma unroll
+  for (int i = 0; i < C * KK; ++i)
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) {
+      float v = acc[i][j];
+#pragma unroll
+      for (int o = FG; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[i][j] = v;
+    }
+  for (int wv = 0; wv < kNT / 32; ++wv) {
+    if (warp == wv && pg == 0) {
+#pragma unroll
+      for (int i = 0; i < C * KK; ++i)
+#pragma unroll
+        for (int j = 0; j < FPT; ++j) {
+          float* d = sAcc + i * 32 + fg * FPT + j;
+          *d = wv == 0 ? acc[i][j] : *d + acc[i][j];
+        }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < C * KK * 32; e += kNT) {
+    const int i = e >> 5, fch = e & 31;            // i = c * KK + tap
+    atomicAdd(dw + (long long)fch * (C * KK) + i, sAcc[e]);   // reference layout [f][c][kh][kw]
+  }
+}
+
+template <int K, int C, int FPT>
+int launch_bwg(bool img_bf16, const __nv_bfloat16* feat, const void* img, float* dw, int B, int Hf, int Wf, int Hi, int Wi,
+               cudaStream_t st) {
+  const long long items = ((long long)B * Hf * Wf + FPT - 1) / FPT;   // warp iterations (FPT pixel slots per warp)
+  const long long g = (items + kNT / 32 - 1) / (kNT / 32);
+  const long long cap = 148 * 2;                                       // 110-180 registers: two 128-thread CTAs per SM
+  const int grid = (int)(g < 1 ? 1 : g > cap ? cap : g);
+  if (img_bf16) boundary_wgrad_kernel<K, C, FPT, true><<<grid, kNT, 0, st>>>(feat, img, dw, B, Hf, Wf, Hi, Wi);
+  else boundary_wgrad_kernel<K, C, FPT, false><<<grid, kNT, 0, st>>>(feat, img, dw, B, Hf, Wf, Hi, Wi);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
 inline int grid_for(long long npix) {
   long long g = (npix + kNT - 1) / kNT;
   const long long cap = 148 * 8;
@@ -275,6 +382,37 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
   }
   CV_LAUNCH_CHECK();
   return 0;
+}
+
+int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const clearvae_tensor4* dy,
+                               float* dweight, void* stream) {
+  if (!g || !src || !src->ptr || !dy || !dy->ptr || !dweight || batch <= 0) return CLEARVAE_EINVAL;
+  if (g->stride != 2 || g->pad != 1 || (g->k != 3 && g->k != 4) || g->Hin != g->Win || batch > (1 << 24)) return CLEARVAE_EUNSUPPORTED;
+  // feature side: 32 channels, channels-last bf16; image side: C <= 4 channels, NCHW, fp32 or bf16
+  const clearvae_tensor4 *feat, *img;
+  int C, Hf, Hi;
+  if (!g->transposed) {
+    if (g->Cout != 32 || g->Cin < 1 || g->Cin > 4) return CLEARVAE_EUNSUPPORTED;
+    feat = dy; img = src; C = g->Cin; Hi = g->Hin; Hf = (g->Hin + 2 - g->k) / 2 + 1;
+  } else {
+    if (g->Cin != 32 || g->Cout < 1 || g->Cout > 4) return CLEARVAE_EUNSUPPORTED;
+    feat = src; img = dy; C = g->Cout; Hf = g->Hin; Hi = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad;
+  }
+  if (feat->dtype != CLEARVAE_BF16 || feat->sc != 1 || feat->sw != 32 || feat->sh != (int64_t)Hf * 32 ||
+      feat->sn != (int64_t)Hf * Hf * 32 || ((uintptr_t)feat->ptr & 7))
+    return CLEARVAE_EUNSUPPORTED;
+  if (img->sw != 1 || img->sh != Hi || img->sc != (int64_t)Hi * Hi || img->sn != (int64_t)C * Hi * Hi) return CLEARVAE_EUNSUPPORTED;
+  const bool ibf = img->dtype == CLEARVAE_BF16;
+  const __nv_bfloat16* fp = reinterpret_cast<const __nv_bfloat16*>(feat->ptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = (int)batch;
+#define CV_BWG(KK, CC, FF) return launch_bwg<KK, CC, FF>(ibf, fp, img->ptr, dweight, B, Hf, Hf, Hi, Hi, st)
+  if (g->k == 3) {
+    switch (C) { case 1: CV_BWG(3, 1, 4); case 2: CV_BWG(3, 2, 4); case 3: CV_BWG(3, 3, 4); default: CV_BWG(3, 4, 2); }
+  } else {
+    switch (C) { case 1: CV_BWG(4, 1, 4); case 2: CV_BWG(4, 2, 2); case 3: CV_BWG(4, 3, 2); default: CV_BWG(4, 4, 2); }
+  }
+#undef CV_BWG
 }
 
 }  // extern "C"

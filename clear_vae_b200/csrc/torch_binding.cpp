@@ -284,6 +284,20 @@ void conv_wgrad(at::IntArrayRef geom, int64_t batch, const Tensor& src, at::IntA
            "conv_wgrad");
 }
 
+bool conv_direct_wgrad(at::IntArrayRef geom, int64_t batch, const Tensor& src, at::IntArrayRef src_strides, const Tensor& dy,
+                       at::IntArrayRef dy_strides, Tensor dweight) {
+  const c10::cuda::CUDAGuard guard(src.device());
+  auto g = geom_from(geom);
+  auto s4 = t4(src, src_strides, "src");
+  auto y4 = t4(dy, dy_strides, "dy");
+  check_f32(dweight, "dweight");
+  TORCH_CHECK(dweight.numel() == (int64_t)g.Cin * g.Cout * g.k * g.k, "clearvae: dweight size does not match the geometry");
+  const int rc = clearvae_conv_direct_wgrad(&g, batch, &s4, &y4, dweight.data_ptr<float>(), cur_stream());
+  if (rc == CLEARVAE_EUNSUPPORTED) return false;
+  check_rc(rc, "conv_direct_wgrad");
+  return true;
+}
+
 int dt_of(const Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.is_contiguous(), "clearvae: ", name, " must be a contiguous CUDA tensor");
   TORCH_CHECK(t.scalar_type() == at::kFloat || t.scalar_type() == at::kBFloat16, "clearvae: ", name, " must be fp32 or bf16");
@@ -534,6 +548,7 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("conv_pack_weight(int[] geom, int role, Tensor weight) -> Tensor");
   m.def("conv_direct_fwd(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, Tensor(b!)? stats) -> bool");
+  m.def("conv_direct_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> bool");
   m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
   m.def("bn_finalize(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
@@ -569,6 +584,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("conv_gemm", &conv_gemm);
   m.impl("conv_direct_fwd", &conv_direct_fwd);
   m.impl("conv_wgrad", &conv_wgrad);
+  m.impl("conv_direct_wgrad", &conv_direct_wgrad);
   m.impl("bn_finalize", &bn_finalize);
   m.impl("bn_reduce", &bn_reduce);
   m.impl("bn_act_fwd", &bn_act_fwd);

@@ -217,7 +217,9 @@ class EncoderFn(torch.autograd.Function):
             else:
                 src, src_strides = saved_raw[i - 1]
                 pre = saved_pre[i - 1]
-            if i > 0 and saved_act[i - 1] is not None:
+            if i == 0 and eng.use_direct and ops.conv_direct_wgrad(sp.geom, B, src, src_strides, dy, raw_strides, dw):
+                pass  # Cin <= 4: register-blocked CUDA-core kernel
+            elif i > 0 and saved_act[i - 1] is not None:
                 ops.conv_wgrad(sp.geom, B, saved_act[i - 1], src_strides, None, None, False, dy, raw_strides, dw)
             else:
                 ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
@@ -357,7 +359,10 @@ class DecoderFn(torch.autograd.Function):
             else:
                 src, src_strides = saved_raw[j - 1]
                 pre = saved_pre[j - 1]
-            if j > 0 and saved_act[j - 1] is not None:
+            if (last and j > 0 and eng.use_direct and saved_act[j - 1] is not None and
+                    ops.conv_direct_wgrad(sp.geom, B, saved_act[j - 1], src_strides, dy, raw_strides, dw)):
+                pass  # Cout <= 4: register-blocked CUDA-core kernel
+            elif j > 0 and saved_act[j - 1] is not None:
                 ops.conv_wgrad(sp.geom, B, saved_act[j - 1], src_strides, None, None, False, dy, raw_strides, dw)
             else:
                 ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,

@@ -223,6 +223,12 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
                              const float* pre_shift, int32_t pre_relu, const float* weight, const float* bias,
                              const clearvae_tensor4* dst, double* stats, void* stream);
 
+/* weight gradient of the same two boundary layers on CUDA cores (fp32 accumulate, fp32 atomics into `dweight`, which the
+ * caller zero-fills): src / dy as in clearvae_conv_wgrad — the 32-channel side channels-last bf16, the <=4-channel side
+ * NCHW fp32 or bf16.  Returns CLEARVAE_EUNSUPPORTED for any other layer (use clearvae_conv_wgrad). */
+int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const clearvae_tensor4* dy,
+                               float* dweight, void* stream);
+
 /* profiling hook (tools/conv_timeline.py): when non-NULL, every CTA of clearvae_conv_gemm writes 8 int64
  * %globaltimer stamps (start, prologue done, loads issued, loads landed, accumulator ready, epilogue done, exit) */
 int clearvae_debug_conv_timeline(long long* device_buffer);

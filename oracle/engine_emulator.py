@@ -202,7 +202,9 @@ class Emulator:
             dy, dgam, dbeta = self._bn_bwd(g, L["y"], f"encoder.{i + 1}", L["mean"], L["invstd"], (0, 2, 3))
             dy = r(dy)
             w = r(st[f"encoder.{i}.weight"])
-            da, dw = self._lin_grads(lambda a_, w_: F.conv2d(a_, w_, None, stride=L["s"], padding=L["p"]), (L["a_in"], w), dy)
+            # first layer with the direct kernels: its weight gradient multiplies the unrounded fp32 image
+            a_in = tape["x"] if (k == 0 and self.direct) else L["a_in"]
+            da, dw = self._lin_grads(lambda a_, w_: F.conv2d(a_, w_, None, stride=L["s"], padding=L["p"]), (a_in, w), dy)
             grads[f"encoder.{i}.weight"], grads[f"encoder.{i + 1}.weight"], grads[f"encoder.{i + 1}.bias"] = dw, dgam, dbeta
             if k > 0:
                 P = enc[k - 1]

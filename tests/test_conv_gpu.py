@@ -214,3 +214,48 @@ def test_direct_last_conv_transpose(k, op, cout, H, B):
         assert ok
         assert rel_err(dst, want) < 1e-5
         assert torch.allclose(stats[:cout].float(), want.sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("transposed,k,op,c,H,B,img_bf16", [(0, 3, 0, 3, 28, 16, False), (0, 3, 0, 1, 28, 5, False), (0, 4, 0, 3, 64, 3, False),
+                                                            (1, 3, 1, 3, 14, 16, True), (1, 3, 1, 1, 14, 7, True), (1, 4, 0, 3, 32, 3, True),
+                                                            (1, 3, 1, 4, 14, 4, False), (0, 4, 0, 2, 16, 9, True)])
+def test_direct_boundary_weight_gradient(transposed, k, op, c, H, B, img_bf16):
+    """CUDA-core weight gradient of the two boundary layers: 32-channel side channels-last bf16, <=4-channel side NCHW."""
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(3 * k + c + transposed)
+    cin, cout = (32, c) if transposed else (c, 32)
+    x = torch.randn(B, cin, H, H, generator=g).to(DEV)
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    w = torch.randn(*wshape, generator=g).to(DEV).requires_grad_(True)
+    fwd = (lambda a: F.conv_transpose2d(a, w, None, stride=2, padding=1, output_padding=op)) if transposed else \
+          (lambda a: F.conv2d(a, w, None, stride=2, padding=1))
+    Ho = fwd(x).shape[-1]
+    dy = torch.randn(B, cout, Ho, Ho, generator=g).to(DEV)
+    # the 32-channel side is bf16; the image side is fp32 or bf16
+    if transposed:
+        x = bf(x)
+        dy = bf(dy) if img_bf16 else dy
+    else:
+        dy = bf(dy)
+        x = bf(x) if img_bf16 else x
+    (dw_want,) = torch.autograd.grad(fwd(x), w, dy)
+    geom = [transposed, k, 2, 1, op, cin, cout, H, H]
+    if transposed:
+        src = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        src_strides = nhwc_strides(src)
+        dyt = dy.to(torch.bfloat16) if img_bf16 else dy
+        dy_strides = [dyt.stride(0), dyt.stride(2), dyt.stride(3), dyt.stride(1)]
+    else:
+        src = x.to(torch.bfloat16) if img_bf16 else x
+        src_strides = [src.stride(0), src.stride(2), src.stride(3), src.stride(1)]
+        dyt = dy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        dy_strides = nhwc_strides(dyt)
+    dw = torch.zeros(*wshape, device=DEV)
+    assert ops.conv_direct_wgrad(geom, B, src, src_strides, dyt, dy_strides, dw)
+    assert rel_err(dw, dw_want) < 2e-5, rel_err(dw, dw_want)
+    # a layer that is not a boundary layer is declined (the caller then uses the tensor-core kernel)
+    other = torch.zeros(64, 32, 3, 3, device=DEV)
+    a = torch.zeros(2, 14, 14, 32, device=DEV, dtype=torch.bfloat16)
+    b2 = torch.zeros(2, 7, 7, 64, device=DEV, dtype=torch.bfloat16)
+    assert not ops.conv_direct_wgrad([0, 3, 2, 1, 0, 32, 64, 14, 14], 2, a, nhwc_strides(a), b2, nhwc_strides(b2), other)
