@@ -263,6 +263,145 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_
   }
 }
 
+// channels-last fast path of bn_bwd_apply (g fp32, y bf16 -> dy bf16, C % 8 == 0): 8 elements per thread, 16-byte
+// accesses, the three coefficient rows staged in shared memory
+__global__ void __launch_bounds__(kNT) bn_bwd_apply_vec_kernel(const float4* __restrict__ g, const uint4* __restrict__ y,
+                                                               const float* __restrict__ coef, long long n8, int C,
+                                                               uint4* __restrict__ dy) {
+  extern __shared__ float sCoef[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += kNT) sCoef[i] = __ldg(coef + i);
+  __syncthreads();
+  const int C8 = C >> 3;
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n8; i += (long long)gridDim.x * kNT) {
+    const int c0 = (int)(i % C8) << 3;
+    const float4 g0 = __ldg(g + 2 * i), g1 = __ldg(g + 2 * i + 1);
+    const uint4 q = __ldg(y + i);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 yy = __bfloat1622float2(h2[k]);
+      const int c = c0 + 2 * k;
+      v[2 * k] = fmaf(sCoef[c], gv[2 * k], fmaf(sCoef[C + c], yy.x, sCoef[2 * C + c]));
+      v[2 * k + 1] = fmaf(sCoef[c + 1], gv[2 * k + 1], fmaf(sCoef[C + c + 1], yy.y, sCoef[2 * C + c + 1]));
+    }
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+    dy[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BatchNorm finalize + apply + ReLU in ONE launch (replaces bn_finalize followed by an elementwise pass): every CTA
+// turns the fp64 batch moments into per-channel scale/shift in shared memory (C <= 4096 channels: a few hundred
+// flops), CTA 0 also publishes scale/shift/mean/invstd for the backward and updates the running estimates; the last
+// CTA to have read the moments (ticket word stored behind them: stats[2C]) clears the accumulator for the next step.
+//   layout 0: raw bf16 channels-last [.., C]            -> act bf16, same layout          (conv blocks)
+//   layout 1: raw bf16 channel-major [B, C*HW]          -> act bf16, same layout          (last encoder block -> heads)
+//   layout 2: raw fp32 [B, C] with C = C0*HW (c0 major) -> act bf16 [B, HW, C0]           (decoder fc block, BatchNorm1d)
+// ---------------------------------------------------------------------------
+struct BnFaParams {
+  double* stats; int C; double count; const float *gamma, *beta; float *rm, *rv; float momentum, eps; int repeat;
+  float *scale, *shift; int expand; float *mean, *invstd;
+  const void* raw; void* act; long long total; int HW, C0;
+};
+
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kNT) bn_finalize_apply_kernel(const BnFaParams p) {
+  extern __shared__ float sAff[];  // [2][C]
+  const int C = p.C;
+  for (int c = threadIdx.x; c < C; c += kNT) {
+    const double s = p.stats[c], q = p.stats[C + c];
+    const double mean = s / p.count;
+    double var = q / p.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+    const float sc = g * invstd, sh = b - (float)mean * g * invstd;
+    sAff[c] = sc;
+    sAff[C + c] = sh;
+    if (blockIdx.x == 0) {
+      for (int i = 0; i < p.expand; ++i) { p.scale[c * p.expand + i] = sc; p.shift[c * p.expand + i] = sh; }
+      p.mean[c] = (float)mean;
+      p.invstd[c] = invstd;
+      if (p.rm) {
+        const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
+        float rm = p.rm[c], rv = p.rv[c];
+        for (int i = 0; i < p.repeat; ++i) {
+          rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
+          rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
+        }
+        p.rm[c] = rm;
+        p.rv[c] = rv;
+      }
+    }
+  }
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(reinterpret_cast<unsigned int*>(p.stats + 2 * C), 1u) == gridDim.x - 1 ? 1 : 0;
+
+  if (LAYOUT == 0 || LAYOUT == 1) {
+    const uint4* raw = reinterpret_cast<const uint4*>(p.raw);
+    uint4* out = reinterpret_cast<uint4*>(p.act);
+    const long long n8 = p.total >> 3;
+    const int C8 = C >> 3;
+    for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n8; i += (long long)gridDim.x * kNT) {
+      const uint4 q = __ldg(raw + i);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+      if (LAYOUT == 0) {
+        const int c0 = (int)(i % C8) << 3;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sAff[c0 + k], sAff[C + c0 + k]), 0.f);
+      } else {
+        const long long e0 = i << 3;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = (int)(((e0 + k) / p.HW) % C);
+          v[k] = fmaxf(fmaf(v[k], sAff[c], sAff[C + c]), 0.f);
+        }
+      }
+      out[i] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    }
+  } else {
+    const float* raw = reinterpret_cast<const float*>(p.raw);
+    uint4* out = reinterpret_cast<uint4*>(p.act);
+    const int HW = p.HW, C0 = p.C0, G = C0 >> 3;
+    const long long items = (p.total / C) * HW * G;   // (b, hw, group of 8 channels)
+    for (long long it = (long long)blockIdx.x * kNT + threadIdx.x; it < items; it += (long long)gridDim.x * kNT) {
+      const int g8 = (int)(it % G);
+      const long long t2 = it / G;
+      const int hw = (int)(t2 % HW);
+      const long long b = t2 / HW;
+      const float* rp = raw + b * C + (long long)(g8 * 8) * HW + hw;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int n = (g8 * 8 + k) * HW + hw;
+        v[k] = fmaxf(fmaf(__ldg(rp + (long long)k * HW), sAff[n], sAff[C + n]), 0.f);
+      }
+      out[(b * HW + hw) * G + g8] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    }
+  }
+  __syncthreads();
+  if (s_last) {  // every CTA has read the moments: clear them (and the ticket) for the next accumulation
+    for (int i = threadIdx.x; i < 2 * C; i += kNT) p.stats[i] = 0.0;
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(p.stats + 2 * C) = 0u;
+  }
+}
+
 // out[c] = sum over rows of x[r][c]  (bias gradients of the linear heads): 32 columns per CTA, 32 row groups
 // per column (coalesced 128-byte row segments), fixed-order shared-memory reduction
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* out) {
@@ -400,8 +539,49 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
                           const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
                           int64_t inner, int32_t to_nhwc, void* dy, int32_t dy_dtype, void* stream) {
   if (!g || !y || !coef || !dy || total <= 0 || C <= 0 || inner <= 0) return CLEARVAE_EINVAL;
+  if (inner == 1 && !to_nhwc && !act && !mask_scale && g_dtype == CLEARVAE_F32 && y_dtype == CLEARVAE_BF16 &&
+      dy_dtype == CLEARVAE_BF16 && C % 8 == 0 && C <= 4096 && total % C == 0 &&
+      !(((uintptr_t)g | (uintptr_t)y | (uintptr_t)dy) & 15)) {
+    const long long n8 = total / 8;
+    long long gr = (n8 + kNT - 1) / kNT;
+    if (gr > 148 * 8) gr = 148 * 8;
+    bn_bwd_apply_vec_kernel<<<(unsigned)gr, kNT, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(g), reinterpret_cast<const uint4*>(y), coef, n8, C, reinterpret_cast<uint4*>(dy));
+    CV_LAUNCH_CHECK();
+    return 0;
+  }
   bn_bwd_apply_kernel<<<grid_for(total), kNT, 0, (cudaStream_t)stream>>>(g, g_dtype, y, y_dtype, act, act_dtype, mask_scale,
                                                                          mask_shift, coef, total, C, inner, to_nhwc, dy, dy_dtype);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+int clearvae_bn_finalize_apply(double* stats, int32_t C, double count, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float momentum, float eps, int32_t repeat, float* scale, float* shift,
+                               int32_t expand, float* save_mean, float* save_invstd, const void* raw, int32_t layout, int64_t total,
+                               int32_t HW, void* act_bf16, void* stream) {
+  if (!stats || !scale || !shift || !save_mean || !save_invstd || !raw || !act_bf16 || C <= 0 || count <= 0 || repeat < 1 ||
+      expand < 1 || total <= 0 || HW < 1)
+    return CLEARVAE_EINVAL;
+  if (C > 4096 || layout < 0 || layout > 2 || total % 8 != 0 || (((uintptr_t)raw | (uintptr_t)act_bf16) & 15)) return CLEARVAE_EUNSUPPORTED;
+  BnFaParams p{stats, C, count, gamma, beta, running_mean, running_var, momentum, eps, repeat, scale, shift, expand, save_mean,
+               save_invstd, raw, act_bf16, total, HW, 0};
+  long long work = total / 8;
+  if (layout == 0) {
+    if (C % 8 != 0 || total % C != 0) return CLEARVAE_EUNSUPPORTED;
+  } else if (layout == 1) {
+    if (total % ((long long)C * HW) != 0) return CLEARVAE_EUNSUPPORTED;
+  } else {
+    if (C % HW != 0 || (C / HW) % 8 != 0 || total % C != 0) return CLEARVAE_EUNSUPPORTED;
+    p.C0 = C / HW;
+  }
+  long long g = (work + kNT - 1) / kNT;
+  if (g > 148 * 8) g = 148 * 8;
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == 0) bn_finalize_apply_kernel<0><<<(unsigned)g, kNT, smem, st>>>(p);
+  else if (layout == 1) bn_finalize_apply_kernel<1><<<(unsigned)g, kNT, smem, st>>>(p);
+  else bn_finalize_apply_kernel<2><<<(unsigned)g, kNT, smem, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
 }

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const float* __restrict
 // One thread = two horizontally adjacent output pixels (ow = 2j, 2j+1) of one output row; threads are ordered so that
 // a warp stays inside one row parity (uniform set of valid kh) — no divergence, weights are warp-broadcast from
 // shared memory, every needed input pixel is loaded (and BatchNorm+ReLU'ed) exactly once per thread.
-template <int K, bool SRC_BF16>
+template <int K, bool SRC_BF16, bool PRE>
 __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict__ src, const float* __restrict__ pre_scale,
                                                          const float* __restrict__ pre_shift, int pre_relu,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
@@ -170,8 +170,11 @@ __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict_
         const float4* w1 = reinterpret_cast<const float4*>(sW + (kh * K + (use1 ? kw1 : 0)) * CI * 4);
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci) {
-          float x = fmaf(v[ci], sScale[ci], sShift[ci]);
-          if (pre_relu) x = fmaxf(x, 0.f);
+          float x = v[ci];
+          if (PRE) {  // raw input: BatchNorm-apply (+ ReLU) on the fly; a materialised activation is used as is
+            x = fmaf(x, sScale[ci], sShift[ci]);
+            if (pre_relu) x = fmaxf(x, 0.f);
+          }
           if (use0) {
             const float4 wv = w0[ci];
             acc0[0] = fmaf(x, wv.x, acc0[0]); acc0[1] = fmaf(x, wv.y, acc0[1]); acc0[2] = fmaf(x, wv.z, acc0[2]); acc0[3] = fmaf(x, wv.w, acc0[3]);
@@ -190,12 +193,14 @@ __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict_
       if (co < Cout) {
         const float bsv = bias ? __ldg(bias + co) : 0.f;
         const float y0 = acc0[co] + bsv, y1 = acc1[co] + bsv;
-        float* o = out + ((n * Cout + co) * Ho + oh) * (long long)Wo + ow;
-        if (two && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
-          *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
-        } else {
-          o[0] = y0;
-          if (two) o[1] = y1;
+        if (out != nullptr) {  // statistics-only callers (CLEAR-MIM inner forwards) pass no destination
+          float* o = out + ((n * Cout + co) * Ho + oh) * (long long)Wo + ow;
+          if (two && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+            *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
+          } else {
+            o[0] = y0;
+            if (two) o[1] = y1;
+          }
         }
         s[co] += y0; q[co] = fmaf(y0, y0, q[co]);
         if (two) { s[co] += y1; q[co] = fmaf(y1, y1, q[co]); }
@@ -243,17 +248,16 @@ __global__ void __launch_bounds__(kNT) boundary_wgrad_kernel(const __nv_bfloat16
   for (int i = 0; i < C * KK; ++i)
 #pragma unroll
     for (int j = 0; j < FPT; ++j) acc[i][j] = 0.f;
-  const long long npix = (long long)B * Hf * Wf;
-  const long long nwarps = (long long)gridDim.x * (kNT / 32);
-  for (long long q = (long long)blockIdx.x * (kNT / 32) + warp; q * PS < npix; q += nwarps) {
-    const long long pix = q * PS + pg;
+  const int npix = B * Hf * Wf;                      // host guarantees < 2^31
+  const int nwarps = gridDim.x * (kNT / 32);
+  for (int q = blockIdx.x * (kNT / 32) + warp; q * PS < npix; q += nwarps) {
+    const int pix = q * PS + pg;
     const bool pv = pix < npix;
-    const long long pp = pv ? pix : 0;
-    const int w = (int)(pp % Wf), h = (int)((pp / Wf) % Hf);
-    const long long n = pp / ((long long)Wf * Hf);
+    const int pp = pv ? pix : 0;
+    const int w = pp % Wf, t2 = pp / Wf, h = t2 % Hf, n = t2 / Hf;
     float f[FPT];
     {
-      const __nv_bfloat16* fp = feat + pp * 32 + fg * FPT;
+      const __nv_bfloat16* fp = feat + (long long)pp * 32 + fg * FPT;
       if (FPT == 4) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(fp));
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
@@ -271,21 +275,26 @@ __global__ void __launch_bounds__(kNT) boundary_wgrad_kernel(const __nv_bfloat16
     bool rok[K], cok[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { rok[k] = pv && h0 + k >= 0 && h0 + k < Hi; cok[k] = w0 + k >= 0 && w0 + k < Wi; }
-    const long long ibase = (n * C * Hi + h0) * (long long)Wi + w0;
+    const long long ibase = ((long long)n * C * Hi + h0) * Wi + w0;
+    // all image values of the patch first (independent loads in flight), then the FMAs
+    float xv[C * KK];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
       for (int kh = 0; kh < K; ++kh)
 #pragma unroll
         for (int kw = 0; kw < K; ++kw) {
-          const long long off = ibase + ((long long)c * Hi + kh) * Wi + kw;
-          float xv = 0.f;
+          const long long off = ibase + (c * Hi + kh) * Wi + kw;
+          float x = 0.f;
           if (rok[kh] && cok[kw])
-            xv = IMG_BF16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(img) + off))
-                          : __ldg(reinterpret_cast<const float*>(img) + off);
-#pragma unroll
-          for (int j = 0; j < FPT; ++j) acc[c * KK + kh * K + kw][j] = fmaf(xv, f[j], acc[c * KK + kh * K + kw][j]);
+            x = IMG_BF16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(img) + off))
+                         : __ldg(reinterpret_cast<const float*>(img) + off);
+          xv[c * KK + kh * K + kw] = x;
         }
+#pragma unroll
+    for (int i = 0; i < C * KK; ++i)
+#pragma unroll
+      for (int j = 0; j < FPT; ++j) acc[i][j] = fmaf(xv[i], f[j], acc[i][j]);
   }
   // pixel slots -> one value per (tap, feature) per warp; warps -> one per CTA (shared memory); CTAs -> fp32 atomics
 #pragma unroll
@@ -356,7 +365,8 @@ int clearvae_conv_direct_supported(const clearvae_conv_geom* g, const clearvae_t
 int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
                              const float* pre_shift, int32_t pre_relu, const float* weight, const float* bias,
                              const clearvae_tensor4* dst, double* stats, void* stream) {
-  if (!g || !src || !src->ptr || !dst || !dst->ptr || !weight || batch <= 0) return CLEARVAE_EINVAL;
+  if (!g || !src || !src->ptr || !dst || !weight || batch <= 0) return CLEARVAE_EINVAL;
+  if (!dst->ptr && !(g->transposed && stats)) return CLEARVAE_EINVAL;  // no destination = statistics only (last conv-transpose)
   if (!clearvae_conv_direct_supported(g, src, dst)) return CLEARVAE_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (!g->transposed) {
@@ -373,11 +383,14 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
     const int Ho = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad;
     const long long npix = batch * 2 * ((Ho + 1) / 2) * ((Ho + 1) / 2);  // one thread per output-pixel pair
     const bool bf = src->dtype == CLEARVAE_BF16;
-#define CV_LAUNCH_T(KK, BF)                                                                                                   \
-  convt_last_kernel<KK, BF><<<grid_for(npix), kNT, 0, st>>>(src->ptr, pre_scale, pre_shift, pre_relu, weight, bias,           \
-                                                            (float*)dst->ptr, stats, (int)batch, g->Cout, g->Hin, g->Win, Ho, Ho)
-    if (g->k == 3) { if (bf) CV_LAUNCH_T(3, true); else CV_LAUNCH_T(3, false); }
-    else { if (bf) CV_LAUNCH_T(4, true); else CV_LAUNCH_T(4, false); }
+    const bool pre = pre_scale != nullptr || pre_relu;
+#define CV_LAUNCH_T(KK, BF, PR)                                                                                               \
+  convt_last_kernel<KK, BF, PR><<<grid_for(npix), kNT, 0, st>>>(src->ptr, pre_scale, pre_shift, pre_relu, weight, bias,       \
+                                                                (float*)dst->ptr, stats, (int)batch, g->Cout, g->Hin, g->Win, Ho, Ho)
+#define CV_LAUNCH_P(KK, BF) do { if (pre) CV_LAUNCH_T(KK, BF, true); else CV_LAUNCH_T(KK, BF, false); } while (0)
+    if (g->k == 3) { if (bf) CV_LAUNCH_P(3, true); else CV_LAUNCH_P(3, false); }
+    else { if (bf) CV_LAUNCH_P(4, true); else CV_LAUNCH_P(4, false); }
+#undef CV_LAUNCH_P
 #undef CV_LAUNCH_T
   }
   CV_LAUNCH_CHECK();
@@ -387,7 +400,8 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
 int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const clearvae_tensor4* dy,
                                float* dweight, void* stream) {
   if (!g || !src || !src->ptr || !dy || !dy->ptr || !dweight || batch <= 0) return CLEARVAE_EINVAL;
-  if (g->stride != 2 || g->pad != 1 || (g->k != 3 && g->k != 4) || g->Hin != g->Win || batch > (1 << 24)) return CLEARVAE_EUNSUPPORTED;
+  if (g->stride != 2 || g->pad != 1 || (g->k != 3 && g->k != 4) || g->Hin != g->Win || batch * (int64_t)g->Hin * g->Win * 4 >= (1LL << 31))
+    return CLEARVAE_EUNSUPPORTED;
   // feature side: 32 channels, channels-last bf16; image side: C <= 4 channels, NCHW, fp32 or bf16
   const clearvae_tensor4 *feat, *img;
   int C, Hf, Hi;

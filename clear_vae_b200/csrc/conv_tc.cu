@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -63,6 +64,9 @@ struct GemmParams {
   const float *msk_scale, *msk_shift;
   double* stats;
   int splits;  // split-K over grid.z (fp32 atomic epilogue); 1 = off
+  // persistent kernel: flattened (class, n-tile, m-tile) work list
+  int tile_start[cvplan::kMaxClasses + 1];
+  int n_tiles;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -553,6 +557,338 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised variant for the common case (bf16 channels-last operand without pre-op, channels-last
+// destination, full column tiles): each CTA walks a round-robin list of (class, n-tile, m-tile) work items;
+//   warps 0-3  cp.async the A operand (one tile row per thread), announcing k-blocks LAG iterations after issue,
+//   warp  4    TMA for the packed weights,          warp 5   tcgen05.mma issuer,
+//   warps 6-9  epilogue (TMEM -> registers -> vector stores + per-channel sums),
+// coupled only through mbarriers: a shared-memory stage ring (full/empty) and a double-buffered TMEM accumulator
+// (acc_full/acc_empty), so the epilogue of tile i overlaps the loads + MMAs of tile i+1, the ~1.2 us of per-CTA
+// set-up/tear-down is paid once per SM instead of once per tile, and the batch statistics leave the SM as one
+// double atomic per column per CTA instead of one per tile.
+constexpr int kPThreads = 320;
+constexpr int kEpLd = 36;   // padded row stride (floats) of the epilogue staging tile
+
+template <int BN>
+constexpr int persist_stages() { return BN >= 128 ? 4 : 3; }  // BN = 128 runs one CTA per SM (registers), so it can afford the deeper ring
+template <int BN, bool MASKED>
+constexpr size_t persist_smem() {
+  return (size_t)persist_stages<BN>() * (kAStage + BN * BK * 2) + (MASKED ? 2 : 1) * BM * kEpLd * 4 + 2 * 4 * BN * 4 +
+         cvplan::kMaxClasses * cvplan::kMaxTaps * 4 + 256 + 1024;
+}
+
+struct PTile {
+  int cls, n0, nkb;
+  long long m0;
+};
+__device__ __forceinline__ bool p_get_tile(const GemmParams& p, int id, int BN, PTile* t) {
+  if (id >= p.n_tiles) return false;
+  int cls = 0;
+#pragma unroll
+  for (int i = 1; i < cvplan::kMaxClasses; ++i)
+    if (i < p.plan.n_classes && id >= p.tile_start[i]) cls = i;
+  const Cls& c = p.plan.cls[cls];
+  const int local = id - p.tile_start[cls];
+  const int mtiles = (int)((p.batch * c.Hd * c.Wd + BM - 1) / BM);
+  const int nt = local / mtiles;
+  t->cls = cls;
+  t->n0 = nt * BN;
+  t->m0 = (long long)(local - nt * mtiles) * BM;
+  t->nkb = c.Kp / BK;
+  return true;
+}
+
+template <int BN, bool MASKED>
+__global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist_kernel(const __grid_constant__ TmapPack tm, const GemmParams p) {
+  constexpr int NSP = persist_stages<BN>();
+  constexpr int LAG = NSP - 1;
+  constexpr int kBStage = BN * BK * 2;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  constexpr int CH = BN < 32 ? BN : 32;
+  constexpr int NCH = BN / CH;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + NSP * kAStage;
+  float* sEp = reinterpret_cast<float*>(sB + NSP * kBStage);
+  float* sEp2 = sEp + BM * kEpLd;
+  float* sRed = sEp + (MASKED ? 2 : 1) * BM * kEpLd;                 // [2][4][BN]
+  int* sTapOff = reinterpret_cast<int*>(sRed + 2 * 4 * BN);          // [classes][16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sTapOff + cvplan::kMaxClasses * cvplan::kMaxTaps);
+  uint64_t* empty = full + NSP;
+  uint64_t* acc_full = empty + NSP;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Cs = p.plan.Cs;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSP; ++s) { mbar_init(&full[s], BM + 1); mbar_init(&empty[s], 1); }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0)
+      for (int i = 0; i < p.plan.n_classes; ++i) prefetch_tmap(&tm.t[i]);
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < cvplan::kMaxClasses * cvplan::kMaxTaps; i += kPThreads) {
+    const int ci = i / cvplan::kMaxTaps, t = i % cvplan::kMaxTaps;
+    const Cls& c = p.plan.cls[ci];
+    sTapOff[i] = (ci < p.plan.n_classes && t < c.ntaps) ? (int)(c.dh[t] * p.s_h + c.dw[t] * p.s_w) : 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================= A producers =================
+    const int r = threadIdx.x;
+    const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
+    uint32_t kbg = 0, kbs = 0;  // k-blocks issued / announced
+    PTile tl;
+    for (int tile = blockIdx.x; p_get_tile(p, tile, BN, &tl); tile += gridDim.x) {
+      const Cls& c = p.plan.cls[tl.cls];
+      const int Kreal = c.ntaps * Cs;
+      const long long Mc = p.batch * c.Hd * c.Wd;
+      const long long m = tl.m0 + r;
+      const bool mvalid = m < Mc;
+      const long long mm = mvalid ? m : 0;
+      const int wd = (int)(mm % c.Wd), hd = (int)((mm / c.Wd) % c.Hd);
+      const long long img = mm / ((long long)c.Wd * c.Hd);
+      const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
+      const long long base = img * p.s_n + hbase * p.s_h + wbase * p.s_w;
+      unsigned tapmask = 0;
+      if (mvalid) {
+#pragma unroll 1
+        for (int t = 0; t < c.ntaps; ++t) {
+          const int hs = hbase + c.dh[t], ws = wbase + c.dw[t];
+          tapmask |= (hs >= 0 && hs < p.plan.Hs && ws >= 0 && ws < p.plan.Ws) ? (1u << t) : 0u;
+        }
+      }
+      const int* tapoff = sTapOff + tl.cls * cvplan::kMaxTaps;
+      int t_cur = 0, c_cur = 0;
+      for (int kb = 0; kb < tl.nkb; ++kb) {
+        const int s = kbg % NSP;
+        mbar_wait(&empty[s], ((kbg / NSP) & 1) ^ 1);
+        const uint32_t dst = smem_u32(sA + s * kAStage) + r * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kg = kb * BK + j * 8;
+          const bool v = kg < Kreal && ((tapmask >> t_cur) & 1u);
+          const long long off = v ? base + tapoff[t_cur & (cvplan::kMaxTaps - 1)] + c_cur : 0;
+          cp_async16(dst + j * (BM * 16), srcb + off, v ? 16u : 0u);
+          c_cur += 8;
+          if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
+        }
+        cp_async_commit();
+        ++kbg;
+        if (kbg - kbs > (uint32_t)LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(&full[kbs % NSP]);
+          ++kbs;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; kbs < kbg; ++kbs) mbar_arrive(&full[kbs % NSP]);
+  } else if (warp == 4) {
+    // ================= B producer: TMA =================
+    if (lane == 0) {
+      uint32_t kbg = 0;
+      PTile tl;
+      for (int tile = blockIdx.x; p_get_tile(p, tile, BN, &tl); tile += gridDim.x) {
+        for (int kb = 0; kb < tl.nkb; ++kb, ++kbg) {
+          const int s = kbg % NSP;
+          mbar_wait(&empty[s], ((kbg / NSP) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], kBStage);
+          tma_load_2d(sB + s * kBStage, &tm.t[tl.cls], &full[s], kb * BK, tl.n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
+      uint32_t kbg = 0, tcount = 0;
+      PTile tl;
+      for (int tile = blockIdx.x; p_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
+        const uint32_t b = tcount & 1;
+        mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < tl.nkb; ++kb, ++kbg) {
+          const int s = kbg % NSP;
+          mbar_wait(&full[s], (kbg / NSP) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * kAStage), b_base = smem_u32(sB + s * kBStage);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            const uint64_t ad = smem_desc(a_base + k4 * 2 * (BM * 16), BM * 16, 128, kLayoutNone);
+            const uint64_t bd = smem_desc(b_base + k4 * 32, 16, 1024, kLayoutSw128);
+            umma_f16(tmem_base + b * kAccCols, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;
+    const int Nn = p.plan.Nn;
+    float run1[NCH], run2[NCH];             // running column sums of (quarter q, column ch*CH + lane)
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) run1[i] = run2[i] = 0.f;
+    int acc_n0 = -1;
+    auto flush = [&]() {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        if (lane < CH) { sRed[q * BN + i * CH + lane] = run1[i]; sRed[4 * BN + q * BN + i * CH + lane] = run2[i]; }
+        run1[i] = run2[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = (int)threadIdx.x - 192; col < BN; col += 128) {
+        const float a = (sRed[col] + sRed[BN + col]) + (sRed[2 * BN + col] + sRed[3 * BN + col]);
+        const float b2 = (sRed[4 * BN + col] + sRed[5 * BN + col]) + (sRed[6 * BN + col] + sRed[7 * BN + col]);
+        atomicAdd(p.stats + acc_n0 + col, (double)a);
+        atomicAdd(p.stats + Nn + acc_n0 + col, (double)b2);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    uint32_t tcount = 0;
+    PTile tl;
+    for (int tile = blockIdx.x; p_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
+      const Cls& c = p.plan.cls[tl.cls];
+      const long long Mc = p.batch * c.Hd * c.Wd;
+      const long long m = tl.m0 + r;
+      const bool mvalid = m < Mc;
+      const long long mm = mvalid ? m : 0;
+      const int wd = (int)(mm % c.Wd), hd = (int)((mm / c.Wd) % c.Hd);
+      const long long img = mm / ((long long)c.Wd * c.Hd);
+      const long long dst_off = img * p.d_n + (long long)(hd * p.plan.os + c.oa) * p.d_h + (long long)(wd * p.plan.os + c.ob) * p.d_w;
+      const long long msk_off = img * p.m_n + (long long)(hd * p.plan.os + c.oa) * p.m_h + (long long)(wd * p.plan.os + c.ob) * p.m_w;
+      if (p.stats != nullptr && tl.n0 != acc_n0) {
+        if (acc_n0 >= 0) flush();
+        acc_n0 = tl.n0;
+      }
+      const uint32_t b = tcount & 1;
+      mbar_wait(&acc_full[b], (tcount >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int ch0 = ci * CH;
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * kAccCols + ch0);
+        if (CH == 32) {
+          tmem_ld32(taddr, raw);
+        } else {
+          uint32_t r16[16];
+          tmem_ld16(taddr, r16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+        }
+        const int nb = tl.n0 + ch0;
+        float v[CH], u[CH];
+        if (!MASKED) {
+          float bsv[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) bsv[i] = p.bias != nullptr ? __ldg(p.bias + nb + i) : 0.f;
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = mvalid ? __uint_as_float(raw[i]) + bsv[i] : 0.f;
+        } else {
+          float y[CH];
+          if (p.msk_bf16) {
+            const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.msk) + (mvalid ? msk_off + nb : 0));
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+              const uint4 qv = __ldg(mp + i);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); y[8 * i + 2 * k] = f.x; y[8 * i + 2 * k + 1] = f.y; }
+            }
+          } else {
+            const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.msk) + (mvalid ? msk_off + nb : 0));
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) { const float4 qv = __ldg(mp + i); y[4 * i] = qv.x; y[4 * i + 1] = qv.y; y[4 * i + 2] = qv.z; y[4 * i + 3] = qv.w; }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float act = p.msk_scale ? fmaf(y[i], __ldg(p.msk_scale + nb + i), __ldg(p.msk_shift + nb + i)) : y[i];
+            const float a = (mvalid && act > 0.f) ? __uint_as_float(raw[i]) : 0.f;
+            v[i] = a;
+            u[i] = a * y[i];
+          }
+        }
+        if (ci == NCH - 1) {  // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[b]);
+        }
+        if (mvalid) {
+          if (p.dst_bf16) {
+            uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + nb);
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i)
+              d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dst) + dst_off + nb);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+        if (p.stats != nullptr) {
+          float4* row = reinterpret_cast<float4*>(sEp + r * kEpLd);
+#pragma unroll
+          for (int i = 0; i < CH / 4; ++i) row[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (MASKED) {
+            float4* row2 = reinterpret_cast<float4*>(sEp2 + r * kEpLd);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) row2[i] = make_float4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (lane < CH) {
+            const float* col = sEp + (q * 32) * kEpLd + lane;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            if (!MASKED) {
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                const float a0 = col[rr * kEpLd], a1 = col[(rr + 1) * kEpLd];
+                s1a += a0; s1b += a1; s2a = fmaf(a0, a0, s2a); s2b = fmaf(a1, a1, s2b);
+              }
+            } else {
+              const float* col2 = sEp2 + (q * 32) * kEpLd + lane;
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                s1a += col[rr * kEpLd]; s1b += col[(rr + 1) * kEpLd];
+                s2a += col2[rr * kEpLd]; s2b += col2[(rr + 1) * kEpLd];
+              }
+            }
+            run1[ci] += s1a + s1b;
+            run2[ci] += s2a + s2b;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+    }
+    if (p.stats != nullptr && acc_n0 >= 0) flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // ---------------------------------------------------------------------------
 // weight gradient:  dW[kidx, n] += sum_{pixels m} act[m @ tap(kidx), c(kidx)] * dy[m, n]
 //   GEMM with M = (tap, channel) rows, N = output channels, K = pixels (split over CTAs).
@@ -930,6 +1266,33 @@ int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) 
   return 0;
 }
 
+template <int BN, bool MASKED>
+int launch_persist(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
+  constexpr size_t smem = persist_smem<BN, MASKED>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_persist_kernel<BN, MASKED>, kPThreads, smem) != cudaSuccess || occ < 1)
+      occ = 1;
+    per_sm = occ > 2 ? 2 : occ;
+  }
+  int nsm = 148;
+  const int grid = std::min(p.n_tiles, per_sm * nsm);
+  conv_tc_persist_kernel<BN, MASKED><<<grid, kPThreads, smem, st>>>(tm, p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+template <int BN>
+int launch_persist_bn(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
+  return p.epi == CLEARVAE_EPI_BIAS_STATS ? launch_persist<BN, false>(tm, p, st) : launch_persist<BN, true>(tm, p, st);
+}
+
 void fill_t4(const clearvae_tensor4* t, const void*& ptr, long long& sn, long long& sh, long long& sw, long long& sc, int& bf) {
   ptr = t->ptr; sn = t->sn; sh = t->sh; sw = t->sw; sc = t->sc; bf = t->dtype == CLEARVAE_BF16;
 }
@@ -1064,6 +1427,30 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
         p.splits = sp;
         cudaError_t e = cudaMemsetAsync(p.dst, 0, (size_t)batch * p.plan.Nn * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
+      }
+    }
+  }
+  // common case -> persistent warp-specialised kernel (see conv_tc_persist_kernel)
+  static const bool no_persist = getenv("CLEARVAE_NO_PERSIST") != nullptr;
+  const bool masked = epilogue != CLEARVAE_EPI_BIAS_STATS;
+  if (!no_persist && p.splits == 1 && p.src_bf16 && p.s_c == 1 && p.plan.Cs % 8 == 0 && pre_scale == nullptr && !pre_relu &&
+      p.d_c == 1 && p.plan.Nn % BN == 0 && ((p.d_n | p.d_h | p.d_w) & 7) == 0 && !((uintptr_t)p.src & 15) &&
+      ((p.s_n | p.s_h | p.s_w) & 7) == 0 && !((uintptr_t)p.dst & 15) &&
+      (!masked || (p.m_c == 1 && ((p.m_n | p.m_h | p.m_w) & 7) == 0 && !((uintptr_t)p.msk & 15)))) {
+    long long tiles = 0;
+    const int n_ntiles = p.plan.Nn / BN;
+    for (int i = 0; i < p.plan.n_classes; ++i) {
+      p.tile_start[i] = (int)tiles;
+      tiles += (((long long)batch * p.plan.cls[i].Hd * p.plan.cls[i].Wd + BM - 1) / BM) * n_ntiles;
+    }
+    p.tile_start[p.plan.n_classes] = (int)tiles;
+    if (tiles > 0 && tiles < (1LL << 30)) {
+      p.n_tiles = (int)tiles;
+      switch (BN) {
+        case 16: return launch_persist_bn<16>(tm, p, st);
+        case 32: return launch_persist_bn<32>(tm, p, st);
+        case 64: return launch_persist_bn<64>(tm, p, st);
+        default: return launch_persist_bn<128>(tm, p, st);
       }
     }
   }

@@ -225,7 +225,7 @@ clearvae_tensor4 t4(const Tensor& t, at::IntArrayRef strides, const char* name) 
   TORCH_CHECK(t.scalar_type() == at::kFloat || t.scalar_type() == at::kBFloat16, "clearvae: ", name, " must be fp32 or bf16");
   TORCH_CHECK(strides.size() == 4, "clearvae: 4 strides expected for ", name);
   clearvae_tensor4 q;
-  q.ptr = t.data_ptr();
+  q.ptr = t.numel() > 0 ? t.data_ptr() : nullptr;
   q.sn = strides[0]; q.sh = strides[1]; q.sw = strides[2]; q.sc = strides[3];
   q.dtype = t.scalar_type() == at::kBFloat16 ? CLEARVAE_BF16 : CLEARVAE_F32;
   return q;
@@ -397,6 +397,27 @@ Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, cons
   return dy;
 }
 
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor> bn_finalize_apply(Tensor stats, int64_t C, double count, const OptTensor& gamma,
+                                                                     const OptTensor& beta, const OptTensor& running_mean,
+                                                                     const OptTensor& running_var, double momentum, double eps,
+                                                                     int64_t expand, int64_t repeat, const Tensor& raw,
+                                                                     int64_t layout, int64_t HW) {
+  const c10::cuda::CUDAGuard guard(stats.device());
+  TORCH_CHECK(stats.numel() >= 2 * C + 1, "clearvae: stats must hold 2*C moments + the ticket word");
+  TORCH_CHECK(raw.is_cuda() && raw.is_contiguous(), "clearvae: raw must be a contiguous CUDA tensor");
+  TORCH_CHECK(layout == 2 ? raw.scalar_type() == at::kFloat : raw.scalar_type() == at::kBFloat16, "clearvae: raw dtype does not match the layout");
+  auto fopt = stats.options().dtype(at::kFloat);
+  Tensor scale = at::empty({C * expand}, fopt), shift = at::empty({C * expand}, fopt), mean = at::empty({C}, fopt), invstd = at::empty({C}, fopt);
+  Tensor act = at::empty(raw.sizes(), raw.options().dtype(at::kBFloat16));
+  check_rc(clearvae_bn_finalize_apply(stats_ptr(stats), (int32_t)C, count, optf(gamma, "gamma"), optf(beta, "beta"),
+                                      optf_mut(running_mean, "running_mean"), optf_mut(running_var, "running_var"), (float)momentum,
+                                      (float)eps, (int32_t)repeat, scale.data_ptr<float>(), shift.data_ptr<float>(), (int32_t)expand,
+                                      mean.data_ptr<float>(), invstd.data_ptr<float>(), raw.data_ptr(), (int32_t)layout, raw.numel(),
+                                      (int32_t)HW, act.data_ptr(), cur_stream()),
+           "bn_finalize_apply");
+  return {act, scale, shift, mean, invstd};
+}
+
 Tensor bn_relu_apply(const Tensor& raw, const Tensor& scale, const Tensor& shift, int64_t C) {
   const c10::cuda::CUDAGuard guard(raw.device());
   TORCH_CHECK(raw.is_cuda() && raw.is_contiguous() && raw.scalar_type() == at::kBFloat16, "clearvae: raw must be contiguous CUDA bf16");
@@ -562,6 +583,9 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("bn_bwd_apply(Tensor g, Tensor y, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, Tensor coef, int C, int inner, bool to_nhwc, int out_dtype) -> Tensor");
   m.def("colsum(Tensor x) -> Tensor");
   m.def("bn_relu_apply(Tensor raw, Tensor scale, Tensor shift, int C) -> Tensor");
+  m.def("bn_finalize_apply(Tensor(a!) stats, int C, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
+        "Tensor(c!)? running_var, float momentum, float eps, int expand, int repeat, Tensor raw, int layout, int HW) "
+        "-> (Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("mi_estimator(int mode, Tensor x, Tensor y, Tensor? perm, Tensor[] params, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor)");
   m.def("mi_bound_bwd(int mode, Tensor grad_out, Tensor dx_unit, Tensor dy_unit, Tensor y, Tensor out_fwd) -> (Tensor, Tensor)");
   m.def("mi_workspace_bytes(int mode, int B, int Dx, int H, int Dy) -> int", &mi_workspace_bytes);
@@ -593,6 +617,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("bn_bwd_apply", &bn_bwd_apply);
   m.impl("colsum", &colsum);
   m.impl("bn_relu_apply", &bn_relu_apply);
+  m.impl("bn_finalize_apply", &bn_finalize_apply);
   m.impl("mi_estimator", &mi_estimator);
   m.impl("mi_bound_bwd", &mi_bound_bwd);
   m.impl("adam_step", &adam_step);

@@ -79,7 +79,8 @@ def linear_geom(k, n):
 
 
 def _stats(C, dev):
-    return torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    # [sum | sum of squares] + one ticket word used by the fused finalize+apply kernel (kept zero between launches)
+    return torch.zeros(2 * C + 2, dtype=torch.float64, device=dev)
 
 
 def _reduce_stats(eng, st):
@@ -132,18 +133,27 @@ class EncoderFn(torch.autograd.Function):
                 pw = eng.packs.get(("enc", i), w, sp.geom, FPROP)
                 ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
                               pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
+            mat = eng.materialize and raw.dtype == torch.bfloat16
+            act = None
             if eng.training:
                 nw = _reduce_stats(eng, st)
-                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
-                                                             BN_MOMENTUM, BN_EPS, H * H if last else 1, eng.bn_repeat)
+                if mat:
+                    # statistics -> scale/shift, running estimates, and relu(bn(raw)) written once in bf16, in one
+                    # launch: every consumer GEMM then cp.async-copies its operand
+                    act, scale, shift, mean, invstd = ops.bn_finalize_apply(
+                        st, sp.cout, float(nw * B * H * H), gamma, beta, rm, rv, BN_MOMENTUM, BN_EPS, H * H if last else 1,
+                        eng.bn_repeat, raw, 1 if last else 0, H * H if last else 1)
+                else:
+                    scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
+                                                                 BN_MOMENTUM, BN_EPS, H * H if last else 1, eng.bn_repeat)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, H * H if last else 1)
+                if mat:
+                    act = ops.bn_relu_apply(raw, scale, shift, scale.numel())
             saved_raw.append((raw, dst_strides))
             saved_pre.append((scale, shift))
             saved_stats.append((mean, invstd))
-            if eng.materialize and raw.dtype == torch.bfloat16:
-                # BatchNorm-apply + ReLU written once (bf16): every consumer GEMM then cp.async-copies its operand
-                act = ops.bn_relu_apply(raw, scale, shift, scale.numel())
+            if mat:
                 saved_act.append(act)
                 src, src_strides, pre = act, dst_strides, None
             else:
@@ -256,14 +266,19 @@ class DecoderFn(torch.autograd.Function):
         ops.conv_gemm(fg, FPROP, B, z, [K0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, FPROP), fc_b, raw_fc,
                       [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
         rm, rv = eng.dec_fc_buffers
-        if eng.training:
-            nw = _reduce_stats(eng, st)
-            sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1, 1)
-        else:
-            sc, sh, mean_fc, inv_fc = eng.eval_affine(fc_g, fc_beta, rm, rv, 1)
         C0, H0 = specs[0].cin, specs[0].hin
-        # BatchNorm1d + ReLU, written channels-last so the first transposed conv gathers 16-byte channel runs
-        a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, C0, H0 * H0, _DT[eng.act_dtype], None, B, _ws(dev))
+        # BatchNorm1d + ReLU, written channels-last so the first transposed conv copies 16-byte channel runs
+        if eng.training and eng.materialize and eng.act_dtype == torch.bfloat16 and C0 % 8 == 0:
+            nw = _reduce_stats(eng, st)
+            a_fc, sc, sh, mean_fc, inv_fc = ops.bn_finalize_apply(st, N0, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM,
+                                                                   BN_EPS, 1, 1, raw_fc, 2, H0 * H0)
+        else:
+            if eng.training:
+                nw = _reduce_stats(eng, st)
+                sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1, 1)
+            else:
+                sc, sh, mean_fc, inv_fc = eng.eval_affine(fc_g, fc_beta, rm, rv, 1)
+            a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, C0, H0 * H0, _DT[eng.act_dtype], None, B, _ws(dev))
         src, src_strides, pre = a_fc, nhwc_strides(H0, H0, C0), None
         saved_raw, saved_pre, saved_stats, saved_act = [], [], [], []
         n = len(specs)
@@ -273,7 +288,9 @@ class DecoderFn(torch.autograd.Function):
             last = j == n - 1
             H = sp.hout
             if last:
-                raw = torch.empty(B, sp.cout, H, H, dtype=torch.float32, device=dev)
+                # statistics-only forwards (CLEAR-MIM inner loop) need the last layer's batch moments, not its output
+                raw = torch.empty((0,) if (eng.stats_only and eng.use_direct and j > 0) else (B, sp.cout, H, H),
+                                  dtype=torch.float32, device=dev)
                 dst_strides = nchw_strides(sp.cout, H, H)
             else:
                 raw = torch.empty(B, H, H, sp.cout, dtype=eng.act_dtype, device=dev)
@@ -282,20 +299,29 @@ class DecoderFn(torch.autograd.Function):
             if not (last and eng.use_direct and j > 0 and
                     ops.conv_direct_fwd(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
                                         pre is not None, w.detach(), b.detach(), raw, dst_strides, st)):
+                if raw.numel() == 0:
+                    raw = torch.empty(B, sp.cout, H, H, dtype=torch.float32, device=dev)
                 ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
                               pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS,
                               None, [0, 0, 0, 0], None, None, st)
+            mat = eng.materialize and not last and raw.dtype == torch.bfloat16
+            act = None
             if eng.training:
                 nw = _reduce_stats(eng, st)
-                scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
-                                                             BN_MOMENTUM, BN_EPS, 1, 1)
+                if mat:
+                    act, scale, shift, mean, invstd = ops.bn_finalize_apply(st, sp.cout, float(nw * B * H * H), gamma, beta, rm, rv,
+                                                                            BN_MOMENTUM, BN_EPS, 1, 1, raw, 0, 1)
+                else:
+                    scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
+                                                                 BN_MOMENTUM, BN_EPS, 1, 1)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, 1)
+                if mat:
+                    act = ops.bn_relu_apply(raw, scale, shift, sp.cout)
             saved_raw.append((raw, dst_strides))
             saved_pre.append((scale, shift))
             saved_stats.append((mean, invstd))
-            if eng.materialize and not last and raw.dtype == torch.bfloat16:
-                act = ops.bn_relu_apply(raw, scale, shift, sp.cout)
+            if mat:
                 saved_act.append(act)
                 src, src_strides, pre = act, dst_strides, None
             else:

@@ -207,6 +207,14 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
                           const float* mask_scale, const float* mask_shift, const float* coef, int64_t total, int32_t C,
                           int64_t inner, int32_t to_nhwc /* write [b][hw][c] instead of [b][c][hw] */, void* dy,
                           int32_t dy_dtype, void* stream);
+/* clearvae_bn_finalize + BatchNorm-apply + ReLU in one launch (train-mode nn.BatchNorm2d/1d + nn.ReLU, vae.py:17-18,34-35).
+ * `stats` must hold 2*C moments followed by one zero-initialised ticket word (2*C + 1 doubles); it is cleared on exit.
+ * layout 0: raw bf16 channels-last [.., C]; 1: raw bf16 channel-major [B, C*HW]; both -> act bf16 in the same layout;
+ * layout 2: raw fp32 [B, C], C = C0*HW in (c0, hw) order -> act bf16 [B, HW, C0] (decoder fc block).  total = elements. */
+int clearvae_bn_finalize_apply(double* stats, int32_t C, double count, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float momentum, float eps, int32_t repeat, float* scale, float* shift,
+                               int32_t expand, float* save_mean, float* save_invstd, const void* raw, int32_t layout, int64_t total,
+                               int32_t HW, void* act_bf16, void* stream);
 /* act = relu(raw * scale[c] + shift[c]) on a channels-last bf16 tensor, C % 8 == 0: BatchNorm-apply + ReLU
  * (vae.py:17-18 etc.) materialised once between two GEMMs so their operand loads are plain async copies */
 int clearvae_bn_relu_apply(const void* raw_bf16, const float* scale, const float* shift, int64_t total, int32_t C, void* act_bf16,
