@@ -316,89 +316,132 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int LAYOUT>
+// per-channel statistics -> (scale, shift); `publish` threads also store the backward state and the running estimates.
+// The mean / variance are formed in fp64 (cancellation), everything after that in fp32.
+__device__ __forceinline__ void bn_channel_affine(const BnFaParams& p, int c, bool publish, float* sc_out, float* sh_out) {
+  const double inv_count = 1.0 / p.count;
+  const double mean = p.stats[c] * inv_count;
+  double var = p.stats[p.C + c] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = 1.f / sqrtf((float)var + p.eps);
+  const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+  const float sc = g * invstd, sh = b - (float)mean * sc;
+  *sc_out = sc;
+  *sh_out = sh;
+  if (publish) {
+    for (int i = 0; i < p.expand; ++i) { p.scale[c * p.expand + i] = sc; p.shift[c * p.expand + i] = sh; }
+    p.mean[c] = (float)mean;
+    p.invstd[c] = invstd;
+    if (p.rm) {
+      const float unbiased = (float)(p.count > 1.0 ? var * p.count / (p.count - 1.0) : var);
+      float rm = p.rm[c], rv = p.rv[c];
+      for (int i = 0; i < p.repeat; ++i) {
+        rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
+        rv = (1.f - p.momentum) * rv + p.momentum * unbiased;
+      }
+      p.rm[c] = rm;
+      p.rv[c] = rv;
+    }
+  }
+}
+// ticket: the last CTA that has read its moments clears the accumulator (and the ticket) for the next step
+__device__ __forceinline__ void bn_ticket_clear(const BnFaParams& p, int* s_last) {
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    *s_last = atomicAdd(reinterpret_cast<unsigned int*>(p.stats + 2 * p.C), 1u) == total - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < 2 * p.C; i += kNT) p.stats[i] = 0.0;
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(p.stats + 2 * p.C) = 0u;
+  }
+}
+
+template <int LAYOUT>  // 0: channels-last, 1: channel-major
 __global__ void __launch_bounds__(kNT) bn_finalize_apply_kernel(const BnFaParams p) {
   extern __shared__ float sAff[];  // [2][C]
-  const int C = p.C;
-  for (int c = threadIdx.x; c < C; c += kNT) {
-    const double s = p.stats[c], q = p.stats[C + c];
-    const double mean = s / p.count;
-    double var = q / p.count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-    const float sc = g * invstd, sh = b - (float)mean * g * invstd;
-    sAff[c] = sc;
-    sAff[C + c] = sh;
-    if (blockIdx.x == 0) {
-      for (int i = 0; i < p.expand; ++i) { p.scale[c * p.expand + i] = sc; p.shift[c * p.expand + i] = sh; }
-      p.mean[c] = (float)mean;
-      p.invstd[c] = invstd;
-      if (p.rm) {
-        const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
-        float rm = p.rm[c], rv = p.rv[c];
-        for (int i = 0; i < p.repeat; ++i) {
-          rm = (1.f - p.momentum) * rm + p.momentum * (float)mean;
-          rv = (1.f - p.momentum) * rv + p.momentum * (float)unbiased;
-        }
-        p.rm[c] = rm;
-        p.rv[c] = rv;
-      }
-    }
-  }
-  __syncthreads();
   __shared__ int s_last;
-  if (threadIdx.x == 0) s_last = atomicAdd(reinterpret_cast<unsigned int*>(p.stats + 2 * C), 1u) == gridDim.x - 1 ? 1 : 0;
-
-  if (LAYOUT == 0 || LAYOUT == 1) {
-    const uint4* raw = reinterpret_cast<const uint4*>(p.raw);
-    uint4* out = reinterpret_cast<uint4*>(p.act);
-    const long long n8 = p.total >> 3;
-    const int C8 = C >> 3;
-    for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n8; i += (long long)gridDim.x * kNT) {
-      const uint4 q = __ldg(raw + i);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-      float v[8];
+  const int C = p.C;
+  for (int c = threadIdx.x; c < C; c += kNT) bn_channel_affine(p, c, blockIdx.x == 0, &sAff[c], &sAff[C + c]);
+  __syncthreads();
+  bn_ticket_clear(p, &s_last);   // all of this CTA's reads of the moments are done
+  const uint4* raw = reinterpret_cast<const uint4*>(p.raw);
+  uint4* out = reinterpret_cast<uint4*>(p.act);
+  const long long n8 = p.total >> 3;
+  const int C8 = C >> 3;
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n8; i += (long long)gridDim.x * kNT) {
+    const uint4 q = __ldg(raw + i);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+    float v[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
-      if (LAYOUT == 0) {
-        const int c0 = (int)(i % C8) << 3;
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+    if (LAYOUT == 0) {
+      const int c0 = (int)(i % C8) << 3;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sAff[c0 + k], sAff[C + c0 + k]), 0.f);
-      } else {
-        const long long e0 = i << 3;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int c = (int)(((e0 + k) / p.HW) % C);
-          v[k] = fmaxf(fmaf(v[k], sAff[c], sAff[C + c]), 0.f);
-        }
-      }
-      out[i] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
-    }
-  } else {
-    const float* raw = reinterpret_cast<const float*>(p.raw);
-    uint4* out = reinterpret_cast<uint4*>(p.act);
-    const int HW = p.HW, C0 = p.C0, G = C0 >> 3;
-    const long long items = (p.total / C) * HW * G;   // (b, hw, group of 8 channels)
-    for (long long it = (long long)blockIdx.x * kNT + threadIdx.x; it < items; it += (long long)gridDim.x * kNT) {
-      const int g8 = (int)(it % G);
-      const long long t2 = it / G;
-      const int hw = (int)(t2 % HW);
-      const long long b = t2 / HW;
-      const float* rp = raw + b * C + (long long)(g8 * 8) * HW + hw;
-      float v[8];
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sAff[c0 + k], sAff[C + c0 + k]), 0.f);
+    } else {
+      const long long e0 = i << 3;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int n = (g8 * 8 + k) * HW + hw;
-        v[k] = fmaxf(fmaf(__ldg(rp + (long long)k * HW), sAff[n], sAff[C + n]), 0.f);
+        const int c = (int)(((e0 + k) / p.HW) % C);
+        v[k] = fmaxf(fmaf(v[k], sAff[c], sAff[C + c]), 0.f);
       }
-      out[(b * HW + hw) * G + g8] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
     }
+    out[i] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
   }
+}
+
+// layout 2 (decoder fc block): raw fp32 [B, C], C = C0*HW with column n = c0*HW + hw  ->  act bf16 [B, HW, C0].
+// CTA (gx, gy) owns the 8*HW contiguous columns of channel group gx (so it forms only those 8*HW scale/shift pairs)
+// and the rows gy, gy + gridDim.y, ...; thread (row slot, hw) reads 8 values HW apart — for fixed k the 16 threads of
+// a row read 64 contiguous bytes — and writes one 16-byte run of the channels-last output.
+__global__ void __launch_bounds__(kNT) bn_finalize_apply_fc_kernel(const BnFaParams p, int rows) {
+  extern __shared__ float sAff[];  // [2][8*HW]
+  __shared__ int s_last;
+  const int HW = p.HW, C0 = p.C0, W = 8 * HW, n_base = blockIdx.x * W;
+  for (int j = threadIdx.x; j < W; j += kNT) bn_channel_affine(p, n_base + j, blockIdx.y == 0, &sAff[j], &sAff[W + j]);
   __syncthreads();
-  if (s_last) {  // every CTA has read the moments: clear them (and the ticket) for the next accumulation
-    for (int i = threadIdx.x; i < 2 * C; i += kNT) p.stats[i] = 0.0;
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(p.stats + 2 * C) = 0u;
+  bn_ticket_clear(p, &s_last);
+  const float* raw = reinterpret_cast<const float*>(p.raw);
+  uint4* out = reinterpret_cast<uint4*>(p.act);
+  const int hw = threadIdx.x % HW, slot = threadIdx.x / HW, slots = kNT / HW;
+  for (int b = blockIdx.y * slots + slot; b < rows; b += gridDim.y * slots) {
+    const float* rp = raw + (long long)b * p.C + n_base + hw;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(__ldg(rp + k * HW), sAff[k * HW + hw], sAff[W + k * HW + hw]), 0.f);
+    out[((long long)b * HW + hw) * (C0 >> 3) + blockIdx.x] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+  }
+}
+
+// layout 3 (last encoder block): raw bf16 channels-last [B, HW, C] -> channel-major copies [B, C*HW] of the raw tensor
+// (what the heads' data-gradient epilogue and the BatchNorm backward read) and of relu(bn(raw)) (the heads' operand,
+// in the reference's Flatten order, vae.py:26).  One CTA per image, transposition through shared memory.
+__global__ void __launch_bounds__(kNT) bn_finalize_apply_tr_kernel(const BnFaParams p, __nv_bfloat16* __restrict__ raw_cm) {
+  extern __shared__ float sAff[];  // [2][C] then the [HW][C+2] bf16 tile
+  __shared__ int s_last;
+  const int C = p.C, HW = p.HW, LDT = C + 2;
+  __nv_bfloat16* sT = reinterpret_cast<__nv_bfloat16*>(sAff + 2 * C);
+  for (int c = threadIdx.x; c < C; c += kNT) bn_channel_affine(p, c, blockIdx.x == 0, &sAff[c], &sAff[C + c]);
+  __syncthreads();
+  bn_ticket_clear(p, &s_last);
+  const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(p.raw);
+  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p.act);
+  const long long per = (long long)C * HW, nimg = p.total / per;
+  for (long long b = blockIdx.x; b < nimg; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)per / 2; i += kNT) {   // coalesced 4-byte reads of [hw][c]
+      const int e = 2 * i, hw = e / C, c = e - hw * C;
+      *reinterpret_cast<uint32_t*>(sT + hw * LDT + c) = __ldg(reinterpret_cast<const uint32_t*>(raw + b * per + e));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)per; i += kNT) {       // coalesced 2-byte writes of [c][hw]
+      const int c = i / HW, hw = i - c * HW;
+      const __nv_bfloat16 y = sT[hw * LDT + c];
+      raw_cm[b * per + i] = y;
+      act[b * per + i] = __float2bfloat16(fmaxf(fmaf(__bfloat162float(y), sAff[c], sAff[C + c]), 0.f));
+    }
   }
 }
 
@@ -559,29 +602,45 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
 int clearvae_bn_finalize_apply(double* stats, int32_t C, double count, const float* gamma, const float* beta, float* running_mean,
                                float* running_var, float momentum, float eps, int32_t repeat, float* scale, float* shift,
                                int32_t expand, float* save_mean, float* save_invstd, const void* raw, int32_t layout, int64_t total,
-                               int32_t HW, void* act_bf16, void* stream) {
+                               int32_t HW, void* act_bf16, void* raw_cm_bf16, void* stream) {
   if (!stats || !scale || !shift || !save_mean || !save_invstd || !raw || !act_bf16 || C <= 0 || count <= 0 || repeat < 1 ||
       expand < 1 || total <= 0 || HW < 1)
     return CLEARVAE_EINVAL;
-  if (C > 4096 || layout < 0 || layout > 2 || total % 8 != 0 || (((uintptr_t)raw | (uintptr_t)act_bf16) & 15)) return CLEARVAE_EUNSUPPORTED;
+  if (C > 4096 || layout < 0 || layout > 3 || total % 8 != 0 || (((uintptr_t)raw | (uintptr_t)act_bf16) & 15)) return CLEARVAE_EUNSUPPORTED;
   BnFaParams p{stats, C, count, gamma, beta, running_mean, running_var, momentum, eps, repeat, scale, shift, expand, save_mean,
                save_invstd, raw, act_bf16, total, HW, 0};
-  long long work = total / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == 2) {
+    if (C % HW != 0 || (C / HW) % 8 != 0 || total % C != 0 || kNT % HW != 0 || HW > kNT) return CLEARVAE_EUNSUPPORTED;
+    p.C0 = C / HW;
+    const int rows = (int)(total / C), slots = kNT / HW;
+    int gy = (rows + slots * 4 - 1) / (slots * 4);   // ~4 rows per thread
+    gy = gy < 1 ? 1 : gy > 64 ? 64 : gy;
+    bn_finalize_apply_fc_kernel<<<dim3((unsigned)(p.C0 / 8), (unsigned)gy), kNT, 2 * 8 * HW * sizeof(float), st>>>(p, rows);
+    CV_LAUNCH_CHECK();
+    return 0;
+  }
+  if (layout == 3) {
+    if (!raw_cm_bf16 || C % 2 != 0 || total % ((long long)C * HW) != 0) return CLEARVAE_EUNSUPPORTED;
+    const size_t smem = 2 * (size_t)C * sizeof(float) + (size_t)HW * (C + 2) * 2;
+    if (smem > 48 * 1024) return CLEARVAE_EUNSUPPORTED;
+    long long g = total / ((long long)C * HW);
+    if (g > 148 * 8) g = 148 * 8;
+    bn_finalize_apply_tr_kernel<<<(unsigned)g, kNT, smem, st>>>(p, reinterpret_cast<__nv_bfloat16*>(raw_cm_bf16));
+    CV_LAUNCH_CHECK();
+    return 0;
+  }
   if (layout == 0) {
     if (C % 8 != 0 || total % C != 0) return CLEARVAE_EUNSUPPORTED;
-  } else if (layout == 1) {
-    if (total % ((long long)C * HW) != 0) return CLEARVAE_EUNSUPPORTED;
   } else {
-    if (C % HW != 0 || (C / HW) % 8 != 0 || total % C != 0) return CLEARVAE_EUNSUPPORTED;
-    p.C0 = C / HW;
+    if (total % ((long long)C * HW) != 0) return CLEARVAE_EUNSUPPORTED;
   }
-  long long g = (work + kNT - 1) / kNT;
-  if (g > 148 * 8) g = 148 * 8;
+  long long g = (total / 8 + kNT * 4 - 1) / (kNT * 4);   // >= 4 vectors per thread: the per-CTA prologue is amortised
+  if (g > 148 * 4) g = 148 * 4;
+  if (g < 1) g = 1;
   const size_t smem = 2 * (size_t)C * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
   if (layout == 0) bn_finalize_apply_kernel<0><<<(unsigned)g, kNT, smem, st>>>(p);
-  else if (layout == 1) bn_finalize_apply_kernel<1><<<(unsigned)g, kNT, smem, st>>>(p);
-  else bn_finalize_apply_kernel<2><<<(unsigned)g, kNT, smem, st>>>(p);
+  else bn_finalize_apply_kernel<1><<<(unsigned)g, kNT, smem, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
 }

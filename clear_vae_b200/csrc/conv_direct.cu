@@ -337,6 +337,51 @@ int launch_bwg(bool img_bf16, const __nv_bfloat16* feat, const void* img, float*
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Decoder fc layer Linear(2D -> 2048) (vae.py:33,137): K = 2D <= 64 is far too shallow for a tensor-core tile
+// (one k-block), so it runs on CUDA cores in fp32: thread = output column (its K weights in registers), a CTA
+// streams 32 rows of z through shared memory (broadcast reads), stores are 512-byte coalesced rows, and the
+// BatchNorm1d batch moments of the column are thread-local sums (two fp64 atomics per thread at the end).
+template <int MAXK>
+__global__ void __launch_bounds__(128) fc_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float* __restrict__ out, double* stats,
+                                                     int B, int K, int N) {
+  constexpr int R = 32;
+  __shared__ __align__(16) float sZ[R * MAXK];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int row0 = blockIdx.y * R;
+  const int nrows = min(R, B - row0);
+  for (int i = threadIdx.x; i < nrows * K; i += 128) sZ[(i / K) * MAXK + (i % K)] = __ldg(z + (long long)row0 * K + i);
+  float wr[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) wr[k] = (n < N && k < K) ? __ldg(w + (long long)n * K + k) : 0.f;
+  const float bv = (n < N && bias) ? __ldg(bias + n) : 0.f;
+  __syncthreads();
+  float s = 0.f, q = 0.f;
+  if (n < N) {
+    for (int r = 0; r < nrows; ++r) {
+      const float4* zr = reinterpret_cast<const float4*>(sZ + r * MAXK);
+      float a0 = bv, a1 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < MAXK / 4; ++k4) {
+        if (k4 * 4 < K) {
+          const float4 zz = zr[k4];
+          a0 = fmaf(zz.x, wr[4 * k4], a0); a1 = fmaf(zz.y, wr[4 * k4 + 1], a1);
+          a0 = fmaf(zz.z, wr[4 * k4 + 2], a0); a1 = fmaf(zz.w, wr[4 * k4 + 3], a1);
+        }
+      }
+      const float a = a0 + a1;
+      out[(long long)(row0 + r) * N + n] = a;
+      s += a;
+      q = fmaf(a, a, q);
+    }
+    if (stats != nullptr) {
+      atomicAdd(stats + n, (double)s);
+      atomicAdd(stats + N + n, (double)q);
+    }
+  }
+}
+
 inline int grid_for(long long npix) {
   long long g = (npix + kNT - 1) / kNT;
   const long long cap = 148 * 8;
@@ -427,6 +472,18 @@ int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const
     switch (C) { case 1: CV_BWG(4, 1, 4); case 2: CV_BWG(4, 2, 2); case 3: CV_BWG(4, 3, 2); default: CV_BWG(4, 4, 2); }
   }
 #undef CV_BWG
+}
+
+int clearvae_fc_fwd(const float* z, const float* weight, const float* bias, float* out, double* stats, int64_t B, int32_t K,
+                    int32_t N, void* stream) {
+  if (!z || !weight || !out || B <= 0 || K <= 0 || N <= 0) return CLEARVAE_EINVAL;
+  if (K > 64 || K % 4 != 0 || B > (1 << 24) || ((uintptr_t)z & 15)) return CLEARVAE_EUNSUPPORTED;
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)((B + 31) / 32));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K <= 16) fc_fwd_kernel<16><<<grid, 128, 0, st>>>(z, weight, bias, out, stats, (int)B, K, N);
+  else fc_fwd_kernel<64><<<grid, 128, 0, st>>>(z, weight, bias, out, stats, (int)B, K, N);
+  CV_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // extern "C"

@@ -28,6 +28,7 @@ struct MiParams {
   const float* y;
   const int64_t* perm;
   int B, Dx, H, Dy;
+  long long ldx, ldy;   // row strides (elements) of x / y: column slices of one [B, 2D] latent tensor are read in place
   const float* w[8];  // p_mu.0.weight [H,Dx], p_mu.0.bias, p_mu.2.weight [Dy,H], p_mu.2.bias, then p_logvar.*
   int mode;
   int np;             // length of the reduced output vector
@@ -74,13 +75,13 @@ __global__ void __launch_bounds__(kNT) mi_kernel(const MiParams p) {
   if (t < 2 * MAXD) sS[t] = 0.f;
   for (int idx = t; idx < kRows * Dx; idx += kNT) {
     const int r = idx / Dx, i = idx - r * Dx;
-    sx[i * kLd + r] = r < nrows ? __ldg(p.x + (long long)(row0 + r) * Dx + i) : 0.f;
+    sx[i * kLd + r] = r < nrows ? __ldg(p.x + (long long)(row0 + r) * p.ldx + i) : 0.f;
   }
   for (int idx = t; idx < kRows * Dy; idx += kNT) {
     const int r = idx / Dy, d = idx - r * Dy;
     const bool v = r < nrows;
-    sy[d * kLd + r] = v ? __ldg(p.y + (long long)(row0 + r) * Dy + d) : 0.f;
-    if (p.mode == CLEARVAE_MI_CLUB) sy2[d * kLd + r] = v ? __ldg(p.y + __ldg(p.perm + row0 + r) * Dy + d) : 0.f;
+    sy[d * kLd + r] = v ? __ldg(p.y + (long long)(row0 + r) * p.ldy + d) : 0.f;
+    if (p.mode == CLEARVAE_MI_CLUB) sy2[d * kLd + r] = v ? __ldg(p.y + __ldg(p.perm + row0 + r) * p.ldy + d) : 0.f;
   }
   __syncthreads();
   if (p.mode == CLEARVAE_MI_L1OUT) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kNT) mi_kernel(const MiParams p) {
     float a = 0.f, b = 0.f;
     if (d < Dy)
       for (int r = t / dp; r < B; r += kNT / dp) {
-        const float v = __ldg(p.y + (long long)r * Dy + d);
+        const float v = __ldg(p.y + (long long)r * p.ldy + d);
         a += v;
         b = fmaf(v, v, b);
       }
@@ -263,8 +264,9 @@ __global__ void __launch_bounds__(kNT) mi_kernel(const MiParams p) {
 
 // gx = g * dx_unit; gy = g * (dy_unit [+ (y * E_d - M_d) / B^2 for L1OUT])
 __global__ void mi_bound_bwd_kernel(int mode, const float* __restrict__ g, const float* __restrict__ dxu,
-                                    const float* __restrict__ dyu, const float* __restrict__ y, const float* __restrict__ em,
-                                    int B, int Dx, int Dy, float* __restrict__ gx, float* __restrict__ gy) {
+                                    const float* __restrict__ dyu, const float* __restrict__ y, long long ldy,
+                                    const float* __restrict__ em, int B, int Dx, int Dy, float* __restrict__ gx,
+                                    float* __restrict__ gy) {
   const float gv = __ldg(g);
   const float inv_n2 = 1.f / ((float)B * (float)B);
   const int nx = B * Dx, ny = B * Dy;
@@ -275,8 +277,8 @@ __global__ void mi_bound_bwd_kernel(int mode, const float* __restrict__ g, const
       const int k = i - nx;
       float v = dyu[k];
       if (mode == CLEARVAE_MI_L1OUT) {
-        const int d = k % Dy;
-        v += inv_n2 * (y[k] * em[d] - em[Dy + d]);
+        const int row = k / Dy, d = k - row * Dy;
+        v += inv_n2 * (y[(long long)row * ldy + d] * em[d] - em[Dy + d]);
       }
       gy[k] = gv * v;
     }
@@ -318,10 +320,10 @@ size_t clearvae_mi_workspace_bytes(int32_t mode, int64_t B, int32_t Dx, int32_t 
   return 256 + (size_t)grid * np_of(mode, Dx, H, Dy) * sizeof(float);
 }
 
-int clearvae_mi_estimator(int32_t mode, const float* x, const float* y, const int64_t* perm, int64_t B, int32_t Dx, int32_t H,
-                          int32_t Dy, const float* const* params_host, float* out, float* dx_unit, float* dy_unit,
+int clearvae_mi_estimator(int32_t mode, const float* x, int64_t ldx, const float* y, int64_t ldy, const int64_t* perm, int64_t B,
+                          int32_t Dx, int32_t H, int32_t Dy, const float* const* params_host, float* out, float* dx_unit, float* dy_unit,
                           void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x || !y || !params_host || !out || !workspace || B <= 0) return CLEARVAE_EINVAL;
+  if (!x || !y || !params_host || !out || !workspace || B <= 0 || ldx < Dx || ldy < Dy) return CLEARVAE_EINVAL;
   if (mode != CLEARVAE_MI_LEARN && mode != CLEARVAE_MI_CLUB && mode != CLEARVAE_MI_L1OUT) return CLEARVAE_EINVAL;
   if (mode == CLEARVAE_MI_CLUB && !perm) return CLEARVAE_EINVAL;
   if (mode != CLEARVAE_MI_LEARN && (!dx_unit || !dy_unit)) return CLEARVAE_EINVAL;
@@ -334,6 +336,7 @@ int clearvae_mi_estimator(int32_t mode, const float* x, const float* y, const in
   MiParams p{};
   p.x = x; p.y = y; p.perm = perm;
   p.B = (int)B; p.Dx = Dx; p.H = H; p.Dy = Dy;
+  p.ldx = ldx; p.ldy = ldy;
   for (int i = 0; i < 8; ++i) p.w[i] = params_host[i];
   p.mode = mode;
   p.np = np_of(mode, Dx, H, Dy);
@@ -353,12 +356,12 @@ int clearvae_mi_estimator(int32_t mode, const float* x, const float* y, const in
 }
 
 int clearvae_mi_bound_bwd(int32_t mode, const float* grad_out, const float* dx_unit, const float* dy_unit, const float* y,
-                          const float* out_fwd, int64_t B, int32_t Dx, int32_t Dy, float* gx, float* gy, void* stream) {
+                          int64_t ldy, const float* out_fwd, int64_t B, int32_t Dx, int32_t Dy, float* gx, float* gy, void* stream) {
   if (!grad_out || !dx_unit || !dy_unit || !gx || !gy || B <= 0) return CLEARVAE_EINVAL;
   if (mode == CLEARVAE_MI_L1OUT && (!y || !out_fwd)) return CLEARVAE_EINVAL;
   const long long n = B * (long long)(Dx + Dy);
   const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 4);
-  mi_bound_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mode, grad_out, dx_unit, dy_unit, y, out_fwd ? out_fwd + 1 : nullptr,
+  mi_bound_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mode, grad_out, dx_unit, dy_unit, y, ldy, out_fwd ? out_fwd + 1 : nullptr,
                                                               (int)B, Dx, Dy, gx, gy);
   CV_LAUNCH_CHECK();
   return 0;

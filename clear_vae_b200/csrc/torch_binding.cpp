@@ -298,6 +298,25 @@ bool conv_direct_wgrad(at::IntArrayRef geom, int64_t batch, const Tensor& src, a
   return true;
 }
 
+bool fc_fwd(const Tensor& z, const Tensor& weight, const OptTensor& bias, Tensor out, const OptTensor& stats) {
+  check_f32(z, "z");
+  check_f32(weight, "weight");
+  check_f32(out, "out");
+  const c10::cuda::CUDAGuard guard(z.device());
+  TORCH_CHECK(z.dim() == 2 && weight.dim() == 2 && weight.size(1) == z.size(1) && out.size(0) == z.size(0) && out.size(1) == weight.size(0),
+              "clearvae: fc_fwd shape mismatch");
+  double* st = nullptr;
+  if (stats.has_value() && stats->defined()) {
+    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kDouble && stats->numel() >= 2 * weight.size(0), "clearvae: bad stats buffer");
+    st = stats->data_ptr<double>();
+  }
+  const int rc = clearvae_fc_fwd(z.data_ptr<float>(), weight.data_ptr<float>(), optf(bias, "bias"), out.data_ptr<float>(), st, z.size(0),
+                                 (int32_t)z.size(1), (int32_t)weight.size(0), cur_stream());
+  if (rc == CLEARVAE_EUNSUPPORTED) return false;
+  check_rc(rc, "fc_fwd");
+  return true;
+}
+
 int dt_of(const Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.is_contiguous(), "clearvae: ", name, " must be a contiguous CUDA tensor");
   TORCH_CHECK(t.scalar_type() == at::kFloat || t.scalar_type() == at::kBFloat16, "clearvae: ", name, " must be fp32 or bf16");
@@ -397,25 +416,27 @@ Tensor bn_bwd_apply(const Tensor& g, const Tensor& y, const OptTensor& act, cons
   return dy;
 }
 
-std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor> bn_finalize_apply(Tensor stats, int64_t C, double count, const OptTensor& gamma,
-                                                                     const OptTensor& beta, const OptTensor& running_mean,
-                                                                     const OptTensor& running_var, double momentum, double eps,
-                                                                     int64_t expand, int64_t repeat, const Tensor& raw,
-                                                                     int64_t layout, int64_t HW) {
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> bn_finalize_apply(Tensor stats, int64_t C, double count, const OptTensor& gamma,
+                                                                             const OptTensor& beta, const OptTensor& running_mean,
+                                                                             const OptTensor& running_var, double momentum, double eps,
+                                                                             int64_t expand, int64_t repeat, const Tensor& raw,
+                                                                             int64_t layout, int64_t HW) {
   const c10::cuda::CUDAGuard guard(stats.device());
   TORCH_CHECK(stats.numel() >= 2 * C + 1, "clearvae: stats must hold 2*C moments + the ticket word");
   TORCH_CHECK(raw.is_cuda() && raw.is_contiguous(), "clearvae: raw must be a contiguous CUDA tensor");
   TORCH_CHECK(layout == 2 ? raw.scalar_type() == at::kFloat : raw.scalar_type() == at::kBFloat16, "clearvae: raw dtype does not match the layout");
   auto fopt = stats.options().dtype(at::kFloat);
+  auto bopt = raw.options().dtype(at::kBFloat16);
   Tensor scale = at::empty({C * expand}, fopt), shift = at::empty({C * expand}, fopt), mean = at::empty({C}, fopt), invstd = at::empty({C}, fopt);
-  Tensor act = at::empty(raw.sizes(), raw.options().dtype(at::kBFloat16));
+  Tensor act = layout == 3 ? at::empty({raw.size(0), raw.numel() / raw.size(0)}, bopt) : at::empty(raw.sizes(), bopt);
+  Tensor raw_cm = layout == 3 ? at::empty_like(act) : at::empty({0}, bopt);
   check_rc(clearvae_bn_finalize_apply(stats_ptr(stats), (int32_t)C, count, optf(gamma, "gamma"), optf(beta, "beta"),
                                       optf_mut(running_mean, "running_mean"), optf_mut(running_var, "running_var"), (float)momentum,
                                       (float)eps, (int32_t)repeat, scale.data_ptr<float>(), shift.data_ptr<float>(), (int32_t)expand,
                                       mean.data_ptr<float>(), invstd.data_ptr<float>(), raw.data_ptr(), (int32_t)layout, raw.numel(),
-                                      (int32_t)HW, act.data_ptr(), cur_stream()),
+                                      (int32_t)HW, act.data_ptr(), layout == 3 ? raw_cm.data_ptr() : nullptr, cur_stream()),
            "bn_finalize_apply");
-  return {act, scale, shift, mean, invstd};
+  return {act, scale, shift, mean, invstd, raw_cm};
 }
 
 Tensor bn_relu_apply(const Tensor& raw, const Tensor& scale, const Tensor& shift, int64_t C) {
@@ -461,12 +482,17 @@ bool conv_direct_fwd(at::IntArrayRef geom, int64_t batch, const Tensor& src, at:
 // ---------------------------------------------------------------------------
 // MI estimators (CLUB-S / L1OutUB) and fused Adam
 // ---------------------------------------------------------------------------
+void check_rows(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.dim() == 2 && (t.size(1) == 1 || t.stride(1) == 1) && t.stride(0) >= t.size(1),
+              "clearvae: ", name, " must be a CUDA float32 [B, D] view with unit column stride");
+}
+
 std::tuple<Tensor, Tensor, Tensor> mi_estimator(int64_t mode, const Tensor& x, const Tensor& y, const OptTensor& perm,
                                                 at::TensorList params, Tensor workspace) {
-  check_f32(x, "x");
-  check_f32(y, "y");
+  check_rows(x, "x");
+  check_rows(y, "y");
   const c10::cuda::CUDAGuard guard(x.device());
-  TORCH_CHECK(x.dim() == 2 && y.dim() == 2 && x.size(0) == y.size(0), "clearvae: x / y must be [B, D] with equal B");
+  TORCH_CHECK(x.size(0) == y.size(0), "clearvae: x / y must have equal B");
   TORCH_CHECK(params.size() == 8, "clearvae: 8 estimator parameters expected");
   const int64_t B = x.size(0), Dx = x.size(1), Dy = y.size(1), H = params[0].size(0);
   const float* pp[8];
@@ -491,8 +517,8 @@ std::tuple<Tensor, Tensor, Tensor> mi_estimator(int64_t mode, const Tensor& x, c
   Tensor dx = learn ? at::empty({0}, fopt) : at::empty({B, Dx}, fopt);
   Tensor dy = learn ? at::empty({0}, fopt) : at::empty({B, Dy}, fopt);
   TORCH_CHECK(workspace.is_cuda() && workspace.is_contiguous(), "clearvae: workspace must be a contiguous CUDA tensor");
-  check_rc(clearvae_mi_estimator((int32_t)mode, x.data_ptr<float>(), y.data_ptr<float>(), pm, B, (int32_t)Dx, (int32_t)H,
-                                 (int32_t)Dy, pp, out.data_ptr<float>(), learn ? nullptr : dx.data_ptr<float>(),
+  check_rc(clearvae_mi_estimator((int32_t)mode, x.data_ptr<float>(), x.stride(0), y.data_ptr<float>(), y.stride(0), pm, B, (int32_t)Dx,
+                                 (int32_t)H, (int32_t)Dy, pp, out.data_ptr<float>(), learn ? nullptr : dx.data_ptr<float>(),
                                  learn ? nullptr : dy.data_ptr<float>(), workspace.data_ptr(), (size_t)workspace.nbytes(),
                                  cur_stream()),
            "mi_estimator");
@@ -504,12 +530,12 @@ std::tuple<Tensor, Tensor> mi_bound_bwd(int64_t mode, const Tensor& grad_out, co
   check_f32(grad_out, "grad_out");
   check_f32(dx_unit, "dx_unit");
   check_f32(dy_unit, "dy_unit");
-  check_f32(y, "y");
+  check_rows(y, "y");
   check_f32(out_fwd, "out_fwd");
   const c10::cuda::CUDAGuard guard(y.device());
   Tensor gx = at::empty_like(dx_unit), gy = at::empty_like(dy_unit);
   check_rc(clearvae_mi_bound_bwd((int32_t)mode, grad_out.data_ptr<float>(), dx_unit.data_ptr<float>(), dy_unit.data_ptr<float>(),
-                                 y.data_ptr<float>(), out_fwd.data_ptr<float>(), dx_unit.size(0), (int32_t)dx_unit.size(1),
+                                 y.data_ptr<float>(), y.stride(0), out_fwd.data_ptr<float>(), dx_unit.size(0), (int32_t)dx_unit.size(1),
                                  (int32_t)dy_unit.size(1), gx.data_ptr<float>(), gy.data_ptr<float>(), cur_stream()),
            "mi_bound_bwd");
   return {gx, gy};
@@ -570,6 +596,7 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("conv_direct_fwd(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, Tensor(b!)? stats) -> bool");
   m.def("conv_direct_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> bool");
+  m.def("fc_fwd(Tensor z, Tensor weight, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats) -> bool");
   m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
   m.def("bn_finalize(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
@@ -585,7 +612,7 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("bn_relu_apply(Tensor raw, Tensor scale, Tensor shift, int C) -> Tensor");
   m.def("bn_finalize_apply(Tensor(a!) stats, int C, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
         "Tensor(c!)? running_var, float momentum, float eps, int expand, int repeat, Tensor raw, int layout, int HW) "
-        "-> (Tensor, Tensor, Tensor, Tensor, Tensor)");
+        "-> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("mi_estimator(int mode, Tensor x, Tensor y, Tensor? perm, Tensor[] params, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor)");
   m.def("mi_bound_bwd(int mode, Tensor grad_out, Tensor dx_unit, Tensor dy_unit, Tensor y, Tensor out_fwd) -> (Tensor, Tensor)");
   m.def("mi_workspace_bytes(int mode, int B, int Dx, int H, int Dy) -> int", &mi_workspace_bytes);
@@ -608,6 +635,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("conv_gemm", &conv_gemm);
   m.impl("conv_direct_fwd", &conv_direct_fwd);
   m.impl("conv_wgrad", &conv_wgrad);
+  m.impl("fc_fwd", &fc_fwd);
   m.impl("conv_direct_wgrad", &conv_direct_wgrad);
   m.impl("bn_finalize", &bn_finalize);
   m.impl("bn_reduce", &bn_reduce);

@@ -120,7 +120,11 @@ class EncoderFn(torch.autograd.Function):
             rm, rv = eng.enc_buffers[i]
             last = i == n - 1
             H = sp.hout
-            if last:
+            # last block: the heads read the reference's Flatten (channel-major) order.  In training the GEMM still
+            # writes channels-last (fast epilogue) and the fused finalize kernel emits the channel-major copies.
+            tr_last = (last and eng.training and eng.materialize and eng.act_dtype == torch.bfloat16 and i > 0
+                       and H * H * (sp.cout + 2) * 2 + 8 * sp.cout <= 48 * 1024)
+            if last and not tr_last:
                 raw = torch.empty(B, sp.cout * H * H, dtype=eng.act_dtype, device=dev)
                 dst_strides = nchw_strides(sp.cout, H, H)
             else:
@@ -140,9 +144,11 @@ class EncoderFn(torch.autograd.Function):
                 if mat:
                     # statistics -> scale/shift, running estimates, and relu(bn(raw)) written once in bf16, in one
                     # launch: every consumer GEMM then cp.async-copies its operand
-                    act, scale, shift, mean, invstd = ops.bn_finalize_apply(
+                    act, scale, shift, mean, invstd, raw_cm = ops.bn_finalize_apply(
                         st, sp.cout, float(nw * B * H * H), gamma, beta, rm, rv, BN_MOMENTUM, BN_EPS, H * H if last else 1,
-                        eng.bn_repeat, raw, 1 if last else 0, H * H if last else 1)
+                        eng.bn_repeat, raw, (3 if tr_last else 1) if last else 0, H * H if last else 1)
+                    if tr_last:
+                        raw, dst_strides = raw_cm, nchw_strides(sp.cout, H, H)
                 else:
                     scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
                                                                  BN_MOMENTUM, BN_EPS, H * H if last else 1, eng.bn_repeat)
@@ -263,15 +269,16 @@ class DecoderFn(torch.autograd.Function):
         fg = linear_geom(K0, N0)
         raw_fc = torch.empty(B, N0, dtype=torch.float32, device=dev)
         st = eng.stat_buf(("dec_fc",), N0, dev) if eng.training else None
-        ops.conv_gemm(fg, FPROP, B, z, [K0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, FPROP), fc_b, raw_fc,
-                      [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
+        if not (eng.use_direct and ops.fc_fwd(z, fc_w.detach(), fc_b.detach(), raw_fc, st)):   # K = 2D <= 64: fp32 CUDA-core kernel
+            ops.conv_gemm(fg, FPROP, B, z, [K0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, FPROP), fc_b, raw_fc,
+                          [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
         rm, rv = eng.dec_fc_buffers
         C0, H0 = specs[0].cin, specs[0].hin
         # BatchNorm1d + ReLU, written channels-last so the first transposed conv copies 16-byte channel runs
         if eng.training and eng.materialize and eng.act_dtype == torch.bfloat16 and C0 % 8 == 0:
             nw = _reduce_stats(eng, st)
-            a_fc, sc, sh, mean_fc, inv_fc = ops.bn_finalize_apply(st, N0, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM,
-                                                                   BN_EPS, 1, 1, raw_fc, 2, H0 * H0)
+            a_fc, sc, sh, mean_fc, inv_fc, _ = ops.bn_finalize_apply(st, N0, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM,
+                                                                      BN_EPS, 1, 1, raw_fc, 2, H0 * H0)
         else:
             if eng.training:
                 nw = _reduce_stats(eng, st)
@@ -309,8 +316,8 @@ class DecoderFn(torch.autograd.Function):
             if eng.training:
                 nw = _reduce_stats(eng, st)
                 if mat:
-                    act, scale, shift, mean, invstd = ops.bn_finalize_apply(st, sp.cout, float(nw * B * H * H), gamma, beta, rm, rv,
-                                                                            BN_MOMENTUM, BN_EPS, 1, 1, raw, 0, 1)
+                    act, scale, shift, mean, invstd, _ = ops.bn_finalize_apply(st, sp.cout, float(nw * B * H * H), gamma, beta, rm,
+                                                                               rv, BN_MOMENTUM, BN_EPS, 1, 1, raw, 0, 1)
                 else:
                     scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
                                                                  BN_MOMENTUM, BN_EPS, 1, 1)

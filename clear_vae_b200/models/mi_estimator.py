@@ -45,6 +45,11 @@ def _workspace(device, nbytes):
     return ws
 
 
+def _rows(t):
+    """[B, D] view with unit column stride: column slices of one latent tensor are passed in place (no copy kernel)."""
+    return t if (t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1) and t.stride(0) >= t.shape[1]) else t.contiguous()
+
+
 def _run(mode, x, y, perm, params):
     ops = _ops.ops()
     B, Dx = x.shape
@@ -58,7 +63,7 @@ class _Bound(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mode, x, y, perm, *params):
-        x, y = x.contiguous(), y.contiguous()
+        x, y = _rows(x), _rows(y)
         out, dx, dy = _run(mode, x, y, perm, [p.detach() for p in params])
         ctx.mode = mode
         ctx.save_for_backward(dx, dy, y, out)
@@ -76,7 +81,7 @@ class _Learn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, y, *params):
-        out, _, _ = _run(MI_LEARN, x.contiguous(), y.contiguous(), None, [p.detach() for p in params])
+        out, _, _ = _run(MI_LEARN, _rows(x), _rows(y), None, [p.detach() for p in params])
         ctx.shapes = [p.shape for p in params]
         ctx.save_for_backward(out)
         return out[0]
@@ -119,7 +124,7 @@ class _GaussianHeads(nn.Module):
         gradients in `.grad` of the eight parameters (views of one flat buffer)."""
         self._check(x_samples, y_samples)
         params = self._params8()
-        out, _, _ = _run(MI_LEARN, x_samples.detach().contiguous(), y_samples.detach().contiguous(), None,
+        out, _, _ = _run(MI_LEARN, _rows(x_samples.detach()), _rows(y_samples.detach()), None,
                          [p.detach() for p in params])
         o = 1
         for p in params:

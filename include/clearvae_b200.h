@@ -210,11 +210,13 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
 /* clearvae_bn_finalize + BatchNorm-apply + ReLU in one launch (train-mode nn.BatchNorm2d/1d + nn.ReLU, vae.py:17-18,34-35).
  * `stats` must hold 2*C moments followed by one zero-initialised ticket word (2*C + 1 doubles); it is cleared on exit.
  * layout 0: raw bf16 channels-last [.., C]; 1: raw bf16 channel-major [B, C*HW]; both -> act bf16 in the same layout;
- * layout 2: raw fp32 [B, C], C = C0*HW in (c0, hw) order -> act bf16 [B, HW, C0] (decoder fc block).  total = elements. */
+ * layout 2: raw fp32 [B, C], C = C0*HW in (c0, hw) order -> act bf16 [B, HW, C0] (decoder fc block);
+ * layout 3: raw bf16 channels-last [B, HW, C] -> act bf16 AND a copy of raw (raw_cm_bf16), both channel-major [B, C*HW]
+ *           (last encoder block: the reference's Flatten order, vae.py:26).  total = number of raw elements. */
 int clearvae_bn_finalize_apply(double* stats, int32_t C, double count, const float* gamma, const float* beta, float* running_mean,
                                float* running_var, float momentum, float eps, int32_t repeat, float* scale, float* shift,
                                int32_t expand, float* save_mean, float* save_invstd, const void* raw, int32_t layout, int64_t total,
-                               int32_t HW, void* act_bf16, void* stream);
+                               int32_t HW, void* act_bf16, void* raw_cm_bf16, void* stream);
 /* act = relu(raw * scale[c] + shift[c]) on a channels-last bf16 tensor, C % 8 == 0: BatchNorm-apply + ReLU
  * (vae.py:17-18 etc.) materialised once between two GEMMs so their operand loads are plain async copies */
 int clearvae_bn_relu_apply(const void* raw_bf16, const float* scale, const float* shift, int64_t total, int32_t C, void* act_bf16,
@@ -237,6 +239,11 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
 int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const clearvae_tensor4* dy,
                                float* dweight, void* stream);
 
+/* decoder fc layer out = z W^T + b (nn.Linear(2D, 2048), vae.py:33,137) in fp32 on CUDA cores, K = 2D <= 64, K % 4 == 0;
+ * `stats` (optional, 2*N doubles) accumulates the BatchNorm1d batch moments (sum, sum of squares) of every column */
+int clearvae_fc_fwd(const float* z, const float* weight, const float* bias, float* out, double* stats, int64_t B, int32_t K,
+                    int32_t N, void* stream);
+
 /* profiling hook (tools/conv_timeline.py): when non-NULL, every CTA of clearvae_conv_gemm writes 8 int64
  * %globaltimer stamps (start, prologue done, loads issued, loads landed, accumulator ready, epilogue done, exit) */
 int clearvae_debug_conv_timeline(long long* device_buffer);
@@ -254,15 +261,16 @@ int clearvae_debug_conv_timeline(long long* device_buffer);
  *                       out[1 .. 1+2*Dy) = column sums the backward needs;
  *   the bound modes also write the unit gradients d out[0] / dx, d out[0] / dy (direct part) to dx_unit / dy_unit;
  *   clearvae_mi_bound_bwd scales them by the incoming gradient (device scalar) and completes dy for L1OUT.
+ * x / y are [B, Dx] / [B, Dy] views with row strides ldx / ldy (elements): column slices of one latent tensor work in place.
  * `workspace` must be zero-initialised once (its first word is a self-resetting ticket counter).
  * ------------------------------------------------------------------------- */
 enum { CLEARVAE_MI_LEARN = 0, CLEARVAE_MI_CLUB = 1, CLEARVAE_MI_L1OUT = 2 };
 size_t clearvae_mi_workspace_bytes(int32_t mode, int64_t B, int32_t Dx, int32_t H, int32_t Dy);
-int clearvae_mi_estimator(int32_t mode, const float* x, const float* y, const int64_t* perm, int64_t B, int32_t Dx, int32_t H,
-                          int32_t Dy, const float* const* params_host, float* out, float* dx_unit, float* dy_unit,
+int clearvae_mi_estimator(int32_t mode, const float* x, int64_t ldx, const float* y, int64_t ldy, const int64_t* perm, int64_t B,
+                          int32_t Dx, int32_t H, int32_t Dy, const float* const* params_host, float* out, float* dx_unit, float* dy_unit,
                           void* workspace, size_t workspace_bytes, void* stream);
 int clearvae_mi_bound_bwd(int32_t mode, const float* grad_out, const float* dx_unit, const float* dy_unit, const float* y,
-                          const float* out_fwd, int64_t B, int32_t Dx, int32_t Dy, float* gx, float* gy, void* stream);
+                          int64_t ldy, const float* out_fwd, int64_t B, int32_t Dx, int32_t Dy, float* gx, float* gy, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Fused multi-tensor Adam: torch.optim.Adam defaults as built by the reference factories

@@ -107,7 +107,10 @@ class Emulator:
         _, unflat, dec = arch_spec(self.arch, self.cin)
         zr = r(z)
         wfc = r(st["decoder.0.weight"])
-        raw_fc = F.linear(zr, wfc, st["decoder.0.bias"])
+        if self.direct:   # the engine's fc forward is an fp32 CUDA-core kernel (its gradients stay bf16 tensor-core GEMMs)
+            raw_fc = F.linear(z, st["decoder.0.weight"], st["decoder.0.bias"])
+        else:
+            raw_fc = F.linear(zr, wfc, st["decoder.0.bias"])
         sc, sh, mean_fc, inv_fc = self._bn_fwd(raw_fc, "decoder.1", (0,))
         a_fc = r(torch.relu(raw_fc * sc + sh))
         tape["fc"] = dict(zr=zr, wfc=wfc, raw=raw_fc, a=a_fc, mean=mean_fc, invstd=inv_fc)
