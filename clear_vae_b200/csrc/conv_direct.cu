@@ -23,17 +23,26 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(kNT) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// MASKED = data-gradient use (see clearvae_conv_direct_dgrad): no bias; the epilogue applies the previous block's
+// ReLU mask and accumulates the BatchNorm-backward sums (sum g, sum g*y) instead of (sum y, sum y^2).
+template <int K, bool X_BF16, bool MASKED>
+__global__ void __launch_bounds__(kNT) conv_first_kernel(const void* __restrict__ xv_, const float* __restrict__ w,
                                                          const float* __restrict__ bias, void* __restrict__ out, int out_bf16,
-                                                         double* stats, int B, int Cin, int H, int W, int Ho, int Wo) {
+                                                         double* stats, int B, int Cin, int H, int W, int Ho, int Wo,
+                                                         const void* __restrict__ msk, int msk_bf16,
+                                                         const float* __restrict__ msk_scale, const float* __restrict__ msk_shift) {
   constexpr int CO = 32;
   __shared__ __align__(16) float sW[4 * K * K * CO];  // [ci*K*K + kh*K + kw][co]
   __shared__ float sRed[2][kNT / 32][CO];
+  __shared__ float sMs[2][CO];
   const int KK = Cin * K * K;
   for (int i = threadIdx.x; i < KK * CO; i += kNT) {
     const int k = i / CO, co = i % CO;  // reference layout w[co][ci][kh][kw] = w[co * KK + k]
     sW[i] = w[co * KK + k];
+  }
+  if (MASKED && threadIdx.x < CO) {
+    sMs[0][threadIdx.x] = msk_scale ? msk_scale[threadIdx.x] : 1.f;
+    sMs[1][threadIdx.x] = msk_shift ? msk_shift[threadIdx.x] : 0.f;
   }
   __syncthreads();
   float s[CO], q[CO];
@@ -45,9 +54,9 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const float* __restrict
     const long long n = pix / ((long long)Wo * Ho);
     float acc[CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
+    for (int c = 0; c < CO; ++c) acc[c] = (!MASKED && bias) ? __ldg(bias + c) : 0.f;
     for (int ci = 0; ci < Cin; ++ci) {
-      const float* xp = x + (n * Cin + ci) * (long long)H * W;
+      const long long xoff = (n * Cin + ci) * (long long)H * W;
 #pragma unroll
       for (int kh = 0; kh < K; ++kh) {
         const int ih = oh * 2 - 1 + kh;
@@ -55,7 +64,12 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const float* __restrict
         for (int kw = 0; kw < K; ++kw) {
           const int iw = ow * 2 - 1 + kw;
           const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-          const float xv = ok ? __ldg(xp + (long long)ih * W + iw) : 0.f;
+          float xv = 0.f;
+          if (ok) {
+            const long long o = xoff + (long long)ih * W + iw;
+            xv = X_BF16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(xv_) + o))
+                        : __ldg(reinterpret_cast<const float*>(xv_) + o);
+          }
           const float4* wr = reinterpret_cast<const float4*>(sW + ((ci * K + kh) * K + kw) * CO);
 #pragma unroll
           for (int c4 = 0; c4 < CO / 4; ++c4) {
@@ -68,8 +82,33 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const float* __restrict
         }
       }
     }
+    if (MASKED) {
+      float y[CO];
+      if (msk_bf16) {
+        const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(msk) + pix * CO);
 #pragma unroll
-    for (int c = 0; c < CO; ++c) { s[c] += acc[c]; q[c] = fmaf(acc[c], acc[c], q[c]); }
+        for (int i = 0; i < CO / 8; ++i) {
+          const uint4 u = __ldg(mp + i);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); y[8 * i + 2 * k] = f.x; y[8 * i + 2 * k + 1] = f.y; }
+        }
+      } else {
+        const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(msk) + pix * CO);
+#pragma unroll
+        for (int i = 0; i < CO / 4; ++i) { const float4 u = __ldg(mp + i); y[4 * i] = u.x; y[4 * i + 1] = u.y; y[4 * i + 2] = u.z; y[4 * i + 3] = u.w; }
+      }
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        const float a = fmaf(y[c], sMs[0][c], sMs[1][c]) > 0.f ? acc[c] : 0.f;
+        acc[c] = a;
+        s[c] += a;
+        q[c] = fmaf(a, y[c], q[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) { s[c] += acc[c]; q[c] = fmaf(acc[c], acc[c], q[c]); }
+    }
     if (out_bf16) {
       uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * CO);
 #pragma unroll
@@ -419,11 +458,11 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
     const int Ho = (g->Hin + 2 - g->k) / 2 + 1;
     const long long npix = batch * Ho * Ho;
     if (g->k == 3)
-      conv_first_kernel<3><<<grid_for(npix), kNT, 0, st>>>((const float*)src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
-                                                          stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho);
+      conv_first_kernel<3, false, false><<<grid_for(npix), kNT, 0, st>>>(src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
+                                                                        stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho, nullptr, 0, nullptr, nullptr);
     else
-      conv_first_kernel<4><<<grid_for(npix), kNT, 0, st>>>((const float*)src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
-                                                          stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho);
+      conv_first_kernel<4, false, false><<<grid_for(npix), kNT, 0, st>>>(src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
+                                                                        stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho, nullptr, 0, nullptr, nullptr);
   } else {
     const int Ho = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad;
     const long long npix = batch * 2 * ((Ho + 1) / 2) * ((Ho + 1) / 2);  // one thread per output-pixel pair
@@ -472,6 +511,34 @@ int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const
     switch (C) { case 1: CV_BWG(4, 1, 4); case 2: CV_BWG(4, 2, 2); case 3: CV_BWG(4, 3, 2); default: CV_BWG(4, 4, 2); }
   }
 #undef CV_BWG
+}
+
+int clearvae_conv_direct_dgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* dy, const float* weight,
+                               const clearvae_tensor4* dst, const clearvae_tensor4* mask_src, const float* mask_scale,
+                               const float* mask_shift, double* stats, void* stream) {
+  if (!g || !dy || !dy->ptr || !weight || !dst || !dst->ptr || !mask_src || !mask_src->ptr || batch <= 0) return CLEARVAE_EINVAL;
+  if (!g->transposed || g->stride != 2 || g->pad != 1 || (g->k != 3 && g->k != 4) || g->Hin != g->Win || g->Cin != 32 || g->Cout < 1 ||
+      g->Cout > 4)
+    return CLEARVAE_EUNSUPPORTED;
+  const int Ho = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad, Hi = g->Hin;
+  // dy: NCHW [B, Cout, Ho, Ho]; dst / mask: channels-last [B, Hin, Hin, 32]
+  if (dy->sw != 1 || dy->sh != Ho || dy->sc != (int64_t)Ho * Ho || dy->sn != (int64_t)g->Cout * Ho * Ho) return CLEARVAE_EUNSUPPORTED;
+  auto cl32 = [&](const clearvae_tensor4* t) {
+    return t->sc == 1 && t->sw == 32 && t->sh == (int64_t)Hi * 32 && t->sn == (int64_t)Hi * Hi * 32 && !((uintptr_t)t->ptr & 15);
+  };
+  if (!cl32(dst) || !cl32(mask_src)) return CLEARVAE_EUNSUPPORTED;
+  const long long npix = batch * Hi * Hi;
+  const bool xb = dy->dtype == CLEARVAE_BF16;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CV_DG(KK, XB)                                                                                                          \
+  conv_first_kernel<KK, XB, true><<<grid_for(npix), kNT, 0, st>>>(dy->ptr, weight, nullptr, dst->ptr, dst->dtype == CLEARVAE_BF16, stats, \
+                                                                  (int)batch, g->Cout, Ho, Ho, Hi, Hi, mask_src->ptr,          \
+                                                                  mask_src->dtype == CLEARVAE_BF16, mask_scale, mask_shift)
+  if (g->k == 3) { if (xb) CV_DG(3, true); else CV_DG(3, false); }
+  else { if (xb) CV_DG(4, true); else CV_DG(4, false); }
+#undef CV_DG
+  CV_LAUNCH_CHECK();
+  return 0;
 }
 
 int clearvae_fc_fwd(const float* z, const float* weight, const float* bias, float* out, double* stats, int64_t B, int32_t K,

@@ -298,6 +298,25 @@ bool conv_direct_wgrad(at::IntArrayRef geom, int64_t batch, const Tensor& src, a
   return true;
 }
 
+double* stats_ptr(const Tensor& t);
+bool conv_direct_dgrad(at::IntArrayRef geom, int64_t batch, const Tensor& dy, at::IntArrayRef dy_strides, const Tensor& weight, Tensor dst,
+                       at::IntArrayRef dst_strides, const Tensor& mask_src, at::IntArrayRef mask_strides, const OptTensor& mask_scale,
+                       const OptTensor& mask_shift, const OptTensor& stats) {
+  const c10::cuda::CUDAGuard guard(dy.device());
+  auto g = geom_from(geom);
+  auto y4 = t4(dy, dy_strides, "dy");
+  auto d4 = t4(dst, dst_strides, "dst");
+  auto m4 = t4(mask_src, mask_strides, "mask_src");
+  check_f32(weight, "weight");
+  double* st = nullptr;
+  if (stats.has_value() && stats->defined()) st = stats_ptr(*stats);
+  const int rc = clearvae_conv_direct_dgrad(&g, batch, &y4, weight.data_ptr<float>(), &d4, &m4, optf(mask_scale, "mask_scale"),
+                                            optf(mask_shift, "mask_shift"), st, cur_stream());
+  if (rc == CLEARVAE_EUNSUPPORTED) return false;
+  check_rc(rc, "conv_direct_dgrad");
+  return true;
+}
+
 bool fc_fwd(const Tensor& z, const Tensor& weight, const OptTensor& bias, Tensor out, const OptTensor& stats) {
   check_f32(z, "z");
   check_f32(weight, "weight");
@@ -596,6 +615,8 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("conv_direct_fwd(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, Tensor(b!)? stats) -> bool");
   m.def("conv_direct_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> bool");
+  m.def("conv_direct_dgrad(int[] geom, int batch, Tensor dy, int[] dy_strides, Tensor weight, Tensor(a!) dst, int[] dst_strides, "
+        "Tensor mask_src, int[] mask_strides, Tensor? mask_scale, Tensor? mask_shift, Tensor(b!)? stats) -> bool");
   m.def("fc_fwd(Tensor z, Tensor weight, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats) -> bool");
   m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
@@ -636,6 +657,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("conv_direct_fwd", &conv_direct_fwd);
   m.impl("conv_wgrad", &conv_wgrad);
   m.impl("fc_fwd", &fc_fwd);
+  m.impl("conv_direct_dgrad", &conv_direct_dgrad);
   m.impl("conv_direct_wgrad", &conv_direct_wgrad);
   m.impl("bn_finalize", &bn_finalize);
   m.impl("bn_reduce", &bn_reduce);

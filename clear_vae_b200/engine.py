@@ -46,20 +46,27 @@ def out_hw(transposed, k, s, p, op, h):
 
 
 class _PackCache:
-    """bf16 packed copies of a weight, keyed by GEMM role; refreshed when the master changes."""
+    """bf16 packed copies of a weight, keyed by GEMM role; refreshed when the master changes.
+
+    Eager mode: an entry is reused while the master's (version counter, data pointer) are unchanged.  Inside a CUDA
+    graph capture the version counter says nothing about *replays* (the optimiser node changes the weights every
+    replay), so an entry is reused only within the training step that packed it (`epoch`, bumped by the trainers at
+    the start of every step): each replay then re-packs every weight once, after which the 5 inner forwards of
+    CLEAR-MIM reuse the copy."""
 
     def __init__(self):
         self.entries = {}
+        self.epoch = 0
 
     def get(self, key, w: torch.Tensor, geom, role, cacheable=True):
         key = (key, role)
         ent = self.entries.get(key)
         ver = w._version
-        if (cacheable and ent is not None and ent[0] == ver and ent[1] == w.data_ptr()
-                and not torch.cuda.is_current_stream_capturing()):
-            return ent[2]
+        if cacheable and ent is not None and ent[0] == ver and ent[1] == w.data_ptr():
+            if ent[3] == self.epoch or not torch.cuda.is_current_stream_capturing():
+                return ent[2]
         packed = _ops.ops().conv_pack_weight(geom, role, w.detach().contiguous())
-        self.entries[key] = (ver, w.data_ptr(), packed)
+        self.entries[key] = (ver, w.data_ptr(), packed, self.epoch)
         return packed
 
 
@@ -401,17 +408,20 @@ class DecoderFn(torch.autograd.Function):
                 ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
                                dy, raw_strides, dw)
             grads[4 * j], grads[4 * j + 2], grads[4 * j + 3] = dw, dgamma, dbeta
-            pwd = eng.packs.get(("dec", j), w, sp.geom, DGRAD)
             if j > 0:
                 g = torch.empty(B, sp.hin, sp.hin, sp.cin, dtype=eng.grad_dtype, device=dev)
                 st = eng.stat_buf(("dec_b", j - 1), sp.cin, dev)
-                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g,
-                              nhwc_strides(sp.hin, sp.hin, sp.cin), EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
+                # Cout <= 4: the data gradient is a Conv2d(Cout -> 32) of dy — direct CUDA-core kernel
+                if not (last and eng.use_direct and ops.conv_direct_dgrad(sp.geom, B, dy, raw_strides, w.detach(), g,
+                                                                          nhwc_strides(sp.hin, sp.hin, sp.cin), src, src_strides,
+                                                                          pre[0], pre[1], st)):
+                    ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, eng.packs.get(("dec", j), w, sp.geom, DGRAD),
+                                  None, g, nhwc_strides(sp.hin, sp.hin, sp.cin), EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
             else:
                 # gradient w.r.t. the activated fc output, channel-major like a_fc
                 N0 = fc_w.shape[0]
                 g_a = torch.empty(B, N0, dtype=torch.float32, device=dev)
-                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g_a,
+                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, eng.packs.get(("dec", j), w, sp.geom, DGRAD), None, g_a,
                               nchw_strides(sp.cin, sp.hin, sp.hin), EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
         # fc block: BatchNorm1d + ReLU backward, then Linear
         K0, N0 = fc_w.shape[1], fc_w.shape[0]

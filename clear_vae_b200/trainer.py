@@ -110,6 +110,9 @@ class VAETrainer(Trainer):
         """One iteration of the reference loop body.  With `use_cuda_graph` the device body is captured on first
         use (per input shape) and replayed afterwards; injected noise / permutations force the eager path."""
         self._host_pre()
+        eng = getattr(self.model, "_engine", None)
+        if eng is not None:
+            eng.packs.epoch += 1   # packed-weight copies made inside a graph capture are valid for this step only
         if self.use_cuda_graph and not inject and X.is_cuda:
             out = self._graph_step(X, label)
         else:
@@ -152,6 +155,9 @@ class VAETrainer(Trainer):
         from . import _ops
         before = _ops.meter.launches()
         # thread-local error mode: the NCCL watchdog thread may touch CUDA while this thread captures (data parallel)
+        eng = getattr(self.model, "_engine", None)
+        if eng is not None:
+            eng.packs.epoch += 1   # nothing packed during the eager warm-up may be reused by captured kernels
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             out = self._device_step(sX, sl, **kw)
         dbg("captured")

@@ -239,6 +239,14 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
 int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const clearvae_tensor4* dy,
                                float* dweight, void* stream);
 
+/* data gradient of the last decoder layer ConvTranspose2d(32 -> C<=4, stride 2, pad 1) (vae.py:43,153): it is the
+ * Conv2d(C -> 32) of dy with the same weight tensor, so it runs on the direct first-layer kernel, with the previous block's
+ * ReLU mask (mask_src * mask_scale + mask_shift > 0) and the BatchNorm-backward sums (sum g, sum g*y) in the epilogue.
+ * dy: NCHW fp32|bf16; dst / mask_src: channels-last [B, Hin, Win, 32]. */
+int clearvae_conv_direct_dgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* dy, const float* weight,
+                               const clearvae_tensor4* dst, const clearvae_tensor4* mask_src, const float* mask_scale,
+                               const float* mask_shift, double* stats, void* stream);
+
 /* decoder fc layer out = z W^T + b (nn.Linear(2D, 2048), vae.py:33,137) in fp32 on CUDA cores, K = 2D <= 64, K % 4 == 0;
  * `stats` (optional, 2*N doubles) accumulates the BatchNorm1d batch moments (sum, sum of squares) of every column */
 int clearvae_fc_fwd(const float* z, const float* weight, const float* bias, float* out, double* stats, int64_t B, int32_t K,

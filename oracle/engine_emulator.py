@@ -171,6 +171,10 @@ class Emulator:
             da, dw = self._lin_grads(lambda a_, w_: F.conv_transpose2d(a_, w_, None, stride=L["s"], padding=L["p"],
                                                                        output_padding=L["op"]), (L["a_in"], w), dy)
             grads[f"decoder.{i}.weight"], grads[f"decoder.{i + 1}.weight"], grads[f"decoder.{i + 1}.bias"] = dw, dgam, dbeta
+            if self.direct and j == len(dec) - 1 and j > 0:
+                # the last layer's data gradient runs on the direct fp32 kernel: unrounded master weights
+                (da,) = self._lin_grads(lambda a_: F.conv_transpose2d(a_, st[f"decoder.{i}.weight"], None, stride=L["s"],
+                                                                      padding=L["p"], output_padding=L["op"]), (L["a_in"],), dy)
             if j > 0:
                 P = dec[j - 1]
                 mask = (P["y"] * self._bc(P["scale"], 4) + self._bc(P["shift"], 4)) > 0
