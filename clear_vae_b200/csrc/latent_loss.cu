@@ -298,7 +298,9 @@ template <int DP> struct TcCfg {
   static constexpr int KT = 3 * DP;                   // hi | lo | hi  (A)   x   hi | hi | lo  (B)
   static constexpr int A_BYTES = 128 * KT * 4;
   static constexpr int B_BYTES = BN * KT * 4;
-  static constexpr int SMEM = A_BYTES + 2 * B_BYTES + 2 * BN * 8 /*labels lo/hi x2*/ + 2048 /*barriers, flags, partials*/ + 1024;
+  // column-tile ring (operand + labels), decoupled from the two TMEM accumulators so the producers run ahead of the epilogue
+  static constexpr int NSB = DP <= 8 ? 4 : 3;
+  static constexpr int SMEM = A_BYTES + NSB * B_BYTES + NSB * BN * 8 /*labels lo/hi*/ + 2048 /*barriers, flags, partials*/ + 1024;
 };
 constexpr int kTcThreads = 13 * 32;
 
@@ -315,15 +317,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // stage one normalised row / column vector as [hi | second | third] K-major interleave chunks
 template <int DP>
-__device__ __forceinline__ void stage_split(const float* __restrict__ src, bool valid, int D, unsigned char* base, int rows,
-                                            int r, bool a_side, unsigned char* kmajor2 = nullptr) {
-  float v[DP];
+__device__ __forceinline__ void load_vec(const float* __restrict__ src, bool valid, int D, float (&v)[DP]) {
+  if (DP % 4 == 0 && D == DP) {   // contiguous, 16-byte aligned rows: vector loads
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) q = __ldg(reinterpret_cast<const float4*>(src) + c);
+      v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) v[d] = (valid && d < D) ? __ldg(src + d) : 0.f;
+  }
+}
+template <int DP>
+__device__ __forceinline__ void stage_split_vals(const float (&v)[DP], unsigned char* base, int rows, int r, bool a_side,
+                                                 unsigned char* kmajor2 = nullptr) {
   float ss = 0.f;
 #pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    v[d] = (valid && d < D) ? __ldg(src + d) : 0.f;
-    ss = fmaf(v[d], v[d], ss);
-  }
+  for (int d = 0; d < DP; ++d) ss = fmaf(v[d], v[d], ss);
   const float inv = 1.f / fmaxf(sqrtf(ss), kCosEps);
   float hi[DP], lo[DP];
 #pragma unroll
@@ -348,6 +360,13 @@ __device__ __forceinline__ void stage_split(const float* __restrict__ src, bool 
     for (int d = 0; d < DP; ++d) { dst[d * 4] = hi[d]; dst[(DP + d) * 4] = lo[d]; }
   }
 }
+template <int DP>
+__device__ __forceinline__ void stage_split(const float* __restrict__ src, bool valid, int D, unsigned char* base, int rows,
+                                            int r, bool a_side, unsigned char* kmajor2 = nullptr) {
+  float v[DP];
+  load_vec<DP>(src, valid, D, v);
+  stage_split_vals<DP>(v, base, rows, r, a_side, kmajor2);
+}
 
 template <int DP>
 __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdParams p) {
@@ -357,11 +376,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
   unsigned char* smem = smem_raw + ((1024u - (sm100::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::A_BYTES;
-  int* sLab = reinterpret_cast<int*>(sB + 2 * C::B_BYTES);            // [2][2][BN]: buffer, (lo, hi), column
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLab + 4 * BN);
-  uint64_t *b_full = bars, *b_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);                 // [0..1] sticky per-buffer "a column label's high word differs"
+  constexpr int NSB = C::NSB;
+  int* sLab = reinterpret_cast<int*>(sB + NSB * C::B_BYTES);          // [NSB][2][BN]: stage, (lo, hi), column
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLab + 2 * NSB * BN);
+  uint64_t *b_full = bars, *b_empty = bars + NSB, *l_empty = bars + 2 * NSB, *t_full = bars + 3 * NSB, *t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);                 // [NSB] sticky per-stage "a column label's high word differs"
   float* sRed = reinterpret_cast<float*>(sFlags + 4);                  // [kWarps + 1] + 2*128 partial sums
   float* sPart = sRed + 16;
 
@@ -402,9 +422,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
   if (t.snn) {
     using namespace sm100;
     if (threadIdx.x == 0) {
-      for (int b = 0; b < 2; ++b) { mbar_init(&b_full[b], 128); mbar_init(&b_empty[b], 1); mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
+      for (int b = 0; b < NSB; ++b) { mbar_init(&b_full[b], 128); mbar_init(&b_empty[b], 1); mbar_init(&l_empty[b], 8); sFlags[b] = 0; }
+      for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
       fence_barrier_init();
-      sFlags[0] = sFlags[1] = 0;
     }
     if (warp == 4) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
     // rows: A operand [hi | lo | hi], staged once (threads 0..127 = rows)
@@ -422,21 +442,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
 
     if (warp < 4) {
       // ================= column-tile producers =================
+      // BN / 128 columns per thread; the global loads of tile jt + 1 are issued before tile jt is normalised / split /
+      // stored, and the shared-memory ring lets this run NSB - 1 tiles ahead of the MMA + epilogue
+      constexpr int CPT = BN / 128;
+      float nv[CPT][DP];
+      long long nlab[CPT];
+      auto prefetch = [&](int jt) {
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+          const long long j = (long long)jt * BN + threadIdx.x + u * 128;
+          const bool valid = j < p.Bg;
+          load_vec<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, nv[u]);
+          nlab[u] = valid ? __ldg(p.lab_c + j) : 0;
+        }
+      };
+      prefetch(0);
       for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt & 1;
-        const uint32_t ph = ((jt >> 1) & 1) ^ 1;
-        mbar_wait(&b_empty[b], ph);
-        mbar_wait(&t_empty[b], ph);
+        const int b = jt % NSB;
+        const uint32_t ph = ((jt / NSB) & 1) ^ 1;
+        float cv_[CPT][DP];
+        long long clab[CPT];
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+          clab[u] = nlab[u];
+#pragma unroll
+          for (int d = 0; d < DP; ++d) cv_[u][d] = nv[u][d];
+        }
+        if (jt + 1 < ntiles) prefetch(jt + 1);
+        mbar_wait(&b_empty[b], ph);     // the MMA of tile jt - NSB has read the operand stage
+        mbar_wait(&l_empty[b], ph);     // the epilogue of tile jt - NSB has read the label stage
         unsigned char* bs = sB + b * C::B_BYTES;
         int any_diff = 0;
-        for (int cc = threadIdx.x; cc < BN; cc += 128) {
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+          const int cc = threadIdx.x + u * 128;
           const long long j = (long long)jt * BN + cc;
           const bool valid = j < p.Bg;
-          stage_split<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, bs, BN, cc, false);
-          const long long lab = valid ? p.lab_c[j] : 0;
-          sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
-          sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
-          any_diff |= (valid && (lab >> 32) != hi_ref) ? 1 : 0;
+          stage_split_vals<DP>(cv_[u], bs, BN, cc, false);
+          sLab[(b * 2 + 0) * BN + cc] = (int)(clab[u] & 0xffffffffll);
+          sLab[(b * 2 + 1) * BN + cc] = (int)(clab[u] >> 32);
+          any_diff |= (valid && (clab[u] >> 32) != hi_ref) ? 1 : 0;
         }
         any_diff = __any_sync(0xffffffffu, any_diff);
         if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);
@@ -448,17 +493,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
       if (lane == 0) {
         constexpr uint32_t idesc = instr_desc(kFmtTF32, 128, BN, 0, 0);
         for (int jt = 0; jt < ntiles; ++jt) {
-          const int b = jt & 1;
-          mbar_wait(&b_full[b], (jt >> 1) & 1);
+          const int b = jt & 1, sb = jt % NSB;
+          mbar_wait(&b_full[sb], (jt / NSB) & 1);
+          mbar_wait(&t_empty[b], ((jt >> 1) & 1) ^ 1);   // the epilogue has drained this TMEM accumulator
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + b * C::B_BYTES);
+          const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + sb * C::B_BYTES);
 #pragma unroll
           for (int k8 = 0; k8 < C::KT / 8; ++k8) {
             const uint64_t ad = smem_desc(a_base + k8 * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
             const uint64_t bd = smem_desc(b_base + k8 * 2 * (BN * 16), BN * 16, 128, kLayoutNone);
             umma_tf32(tmem_base + b * BN, ad, bd, idesc, k8 != 0 ? 1u : 0u);
           }
-          umma_commit(&b_empty[b]);
+          umma_commit(&b_empty[sb]);
           umma_commit(&t_full[b]);
         }
       }
@@ -475,16 +521,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
       const long long diag = p.row_off + i;    // global column index of this row's diagonal
       const bool ps = t.ps != 0;
       const float k2 = p.inv_tau * CV_LOG2E;
-      float sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f, sp0 = 0.f, sp1 = 0.f, sp2 = 0.f, sp3 = 0.f;
+      float sa0 = 0.f, sp0 = 0.f, sp1 = 0.f, sp2 = 0.f, sp3 = 0.f;
+      float2 sa01 = make_float2(0.f, 0.f), sa23 = make_float2(0.f, 0.f);
+      const float2 k2v = make_float2(k2, k2), nk2v = make_float2(-k2, -k2);
       constexpr int HALF = BN / 2;
       for (int jt = 0; jt < ntiles; ++jt) {
         const int b = jt & 1;
         mbar_wait(&t_full[b], (jt >> 1) & 1);
         tc_fence_after();
         const long long jbase = (long long)jt * BN + half * HALF;
-        const bool edge = (jbase + HALF > p.Bg) || (diag >= jbase && diag < jbase + HALF) || sFlags[b] || my_hi_odd;
-        const int* lab_lo = sLab + (b * 2 + 0) * BN + half * HALF;
-        const int* lab_hi = sLab + (b * 2 + 1) * BN + half * HALF;
+        const int sb = jt % NSB;   // shared-memory stage of this tile's labels (b = TMEM accumulator)
+        const bool edge = (jbase + HALF > p.Bg) || (diag >= jbase && diag < jbase + HALF) || sFlags[sb] || my_hi_odd;
+        const int* lab_lo = sLab + (sb * 2 + 0) * BN + half * HALF;
+        const int* lab_hi = sLab + (sb * 2 + 1) * BN + half * HALF;
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is exponentiated
         constexpr int NCH = HALF / 32;
         uint32_t raw[2][32];
@@ -500,11 +549,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
 #pragma unroll
             for (int q = 0; q < 32; q += 4) {
               const int4 l4 = *reinterpret_cast<const int4*>(lab_lo + c0 + q);
-              const float e0 = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
-              const float e1 = ex2_approx(fmaf(__uint_as_float(rw[q + 1]), k2, -k2));
-              const float e2 = ex2_approx(fmaf(__uint_as_float(rw[q + 2]), k2, -k2));
-              const float e3 = ex2_approx(fmaf(__uint_as_float(rw[q + 3]), k2, -k2));
-              sa0 += e0; sa1 += e1; sa2 += e2; sa3 += e3;
+              // packed fp32x2 pipe (FFMA2 / FADD2): half the issue slots for the scale and the running sum, which is
+              // what keeps this loop under the 8 issue slots per MUFU.EX2 the roofline allows
+              const float2 t01 = __ffma2_rn(make_float2(__uint_as_float(rw[q]), __uint_as_float(rw[q + 1])), k2v, nk2v);
+              const float2 t23 = __ffma2_rn(make_float2(__uint_as_float(rw[q + 2]), __uint_as_float(rw[q + 3])), k2v, nk2v);
+              const float e0 = ex2_approx(t01.x), e1 = ex2_approx(t01.y), e2 = ex2_approx(t23.x), e3 = ex2_approx(t23.y);
+              sa01 = __fadd2_rn(sa01, make_float2(e0, e1));
+              sa23 = __fadd2_rn(sa23, make_float2(e2, e3));
               sp0 += ((l4.x == my_lo) != ps) ? e0 : 0.f;
               sp1 += ((l4.y == my_lo) != ps) ? e1 : 0.f;
               sp2 += ((l4.z == my_lo) != ps) ? e2 : 0.f;
@@ -524,10 +575,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_fwd_tc_kernel(const FwdPara
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[b]);
+        if (lane == 0) { mbar_arrive(&t_empty[b]); mbar_arrive(&l_empty[sb]); }
       }
       // combine the two column halves of each row
-      const float sa = (sa0 + sa1) + (sa2 + sa3), sp = (sp0 + sp1) + (sp2 + sp3);
+      const float sa = ((sa01.x + sa01.y) + (sa23.x + sa23.y)) + sa0, sp = (sp0 + sp1) + (sp2 + sp3);
       if (half == 1) { sPart[r] = sa; sPart[128 + r] = sp; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0 && i < p.B) {
@@ -750,7 +801,10 @@ template <int DP> struct TcBwdCfg {
   static constexpr int A_BYTES = 128 * KT * 4;
   static constexpr int B_BYTES = BN * KT * 4;
   static constexpr int B2_BYTES = BN * 2 * DP * 4;    // [N_hi | N_lo]^T, K-major for the second GEMM
-  static constexpr int SMEM = A_BYTES + 2 * B_BYTES + 2 * B2_BYTES + 2 * BN * 16 /*labels lo/hi, c, q*/ + 2048 + 1024;
+  // column-tile ring, decoupled from the two TMEM S/P buffers: the producers (global loads + normalise + split) run
+  // NSB - 1 tiles ahead of the epilogue instead of waiting for the second MMA of tile jt - 2 to release their buffer
+  static constexpr int NSB = DP <= 16 ? 4 : 2;
+  static constexpr int SMEM = A_BYTES + NSB * (B_BYTES + B2_BYTES) + NSB * BN * 16 /*labels lo/hi, c, q*/ + 2048 + 1024;
 };
 
 template <int DP>
@@ -758,19 +812,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   using namespace sm100;
   using C = TcBwdCfg<DP>;
   constexpr int BN = C::BN;
+  constexpr int NSB = C::NSB;
   constexpr uint32_t kBufCols = 2 * BN;      // per buffer: [0,BN) S then P_hi, [BN,2BN) P_lo
   constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulator [128 x 2DP]
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::A_BYTES;
-  unsigned char* sB2 = sB + 2 * C::B_BYTES;
-  int* sLab = reinterpret_cast<int*>(sB2 + 2 * C::B2_BYTES);  // [2][2][BN]
-  float* sCQ = reinterpret_cast<float*>(sLab + 4 * BN);       // [2][2][BN]  (c_j, q_j)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sCQ + 4 * BN);
-  uint64_t *b_full = bars, *b_empty = bars + 2, *s_full = bars + 4, *p_full = bars + 6, *dn_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);
+  unsigned char* sB2 = sB + NSB * C::B_BYTES;
+  int* sLab = reinterpret_cast<int*>(sB2 + NSB * C::B2_BYTES);  // [NSB][2][BN]
+  float* sCQ = reinterpret_cast<float*>(sLab + 2 * NSB * BN);   // [NSB][2][BN]  (c_j, q_j)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCQ + 2 * NSB * BN);
+  uint64_t *b_full = bars, *b_empty = bars + NSB, *s_full = bars + 2 * NSB, *p_full = s_full + 2, *dn_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dn_full + 1);
+  int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);          // [NSB]
 
   const int term = blockIdx.y;
   const TermB& t = p.t[term];
@@ -781,10 +836,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   const float* cols = t.mu_cols ? t.mu_cols : t.mu;
 
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); }
+    for (int b = 0; b < NSB; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); sFlags[b] = 0; }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); }
     mbar_init(dn_full, 1);
     fence_barrier_init();
-    sFlags[0] = sFlags[1] = 0;
   }
   if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   const long long hi_ref = (long long)(p.lab_c[0] >> 32);
@@ -801,23 +856,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   if (warp < 4) {
     // ================= column-tile producers (one thread per column; warps 0-2 active) =================
     if (threadIdx.x < BN) {
-      for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt & 1;
-        mbar_wait(&b_empty[b], ((jt >> 1) & 1) ^ 1);
-        const int cc = threadIdx.x;
+      // the global loads of tile jt + 1 (vector, label, row statistics) are in flight while tile jt is normalised and stored
+      const int cc = threadIdx.x;
+      float nv[DP];
+      long long nlab;
+      float na, nq;
+      bool nvalid;
+      auto prefetch = [&](int jt) {
         const long long j = (long long)jt * BN + cc;
-        const bool valid = j < p.Bg;
-        stage_split<DP>(cols + (valid ? j : 0) * (long long)D, valid, D, sB + b * C::B_BYTES, BN, cc, false, sB2 + b * C::B2_BYTES);
-        const long long lab = valid ? p.lab_c[j] : 0;
+        nvalid = j < p.Bg;
+        load_vec<DP>(cols + (nvalid ? j : 0) * (long long)D, nvalid, D, nv);
+        nlab = nvalid ? __ldg(p.lab_c + j) : 0;
+        na = nvalid ? __ldg(t.stats_all + 2 * j) : INFINITY;
+        nq = nvalid ? __ldg(t.stats_all + 2 * j + 1) : INFINITY;
+      };
+      prefetch(0);
+      for (int jt = 0; jt < ntiles; ++jt) {
+        const int b = jt % NSB;
+        float cvv[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) cvv[d] = nv[d];
+        const long long lab = nlab;
+        const float a = na, q = nq;
+        const bool valid = nvalid;
+        if (jt + 1 < ntiles) prefetch(jt + 1);
+        mbar_wait(&b_empty[b], ((jt / NSB) & 1) ^ 1);
+        stage_split_vals<DP>(cvv, sB + b * C::B_BYTES, BN, cc, false, sB2 + b * C::B2_BYTES);
         sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
         sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
-        float a = INFINITY, q = INFINITY;
-        if (valid) { a = t.stats_all[2 * j]; q = t.stats_all[2 * j + 1]; }
         const bool fin = isfinite(a - q);
         sCQ[(b * 2 + 0) * BN + cc] = fin ? __expf(-a) : 0.f;
         sCQ[(b * 2 + 1) * BN + cc] = fin ? __expf(-q) : 0.f;
         const int any_diff = __any_sync(0xffffffffu, (valid && (lab >> 32) != hi_ref) ? 1 : 0);
-        if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);
+        if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);   // sticky per stage: only ever forces the exact (slow) epilogue path
         fence_proxy_async();
         mbar_arrive(&b_full[b]);
       }
@@ -829,10 +900,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       constexpr uint32_t idesc2 = instr_desc(kFmtTF32, 128, 2 * DP, 0, 0);
       const uint32_t a_base = smem_u32(sA);
       auto mma2 = [&](int jt) {
-        const int b = jt & 1;
+        const int b = jt & 1, sb = jt % NSB;
         mbar_wait(&p_full[b], (jt >> 1) & 1);
         tc_fence_after();
-        const uint32_t b2 = smem_u32(sB2 + b * C::B2_BYTES);
+        const uint32_t b2 = smem_u32(sB2 + sb * C::B2_BYTES);
 #pragma unroll
         for (int part = 0; part < 2; ++part) {        // A = P_hi, then P_lo (split keeps the coefficient at fp32 grade)
 #pragma unroll
@@ -841,13 +912,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
             umma_tf32_ts(tmem_base + kDnCol, tmem_base + b * kBufCols + part * BN + k8 * 8, bd, idesc2, (jt | part | k8) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&b_empty[b]);
+        umma_commit(&b_empty[sb]);
       };
       for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt & 1;
-        mbar_wait(&b_full[b], (jt >> 1) & 1);
+        const int b = jt & 1, sb = jt % NSB;
+        mbar_wait(&b_full[sb], (jt / NSB) & 1);
         tc_fence_after();
-        const uint32_t b_base = smem_u32(sB + b * C::B_BYTES);
+        const uint32_t b_base = smem_u32(sB + sb * C::B_BYTES);
 #pragma unroll
         for (int k8 = 0; k8 < C::KT / 8; ++k8) {
           const uint64_t ad = smem_desc(a_base + k8 * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
@@ -876,16 +947,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       const float a = t.stats_all[2 * diag], q = t.stats_all[2 * diag + 1];
       if (isfinite(a - q)) { ci = __expf(-a); qi = __expf(-q); }
     }
+    const float2 ci2 = make_float2(ci, ci), qi2 = make_float2(qi, qi), k2v = make_float2(k2, k2), nk2v = make_float2(-k2, -k2),
+                 neg1 = make_float2(-1.f, -1.f);
     for (int jt = grp; jt < ntiles; jt += 2) {
       const int b = grp;
       mbar_wait(&s_full[b], (jt >> 1) & 1);
       tc_fence_after();
       const long long jbase = (long long)jt * BN;
-      const bool edge = (jbase + BN > p.Bg) || (diag >= jbase && diag < jbase + BN) || sFlags[b] || my_hi_odd;
-      const int* lab_lo = sLab + (b * 2 + 0) * BN;
-      const int* lab_hi = sLab + (b * 2 + 1) * BN;
-      const float* cj = sCQ + (b * 2 + 0) * BN;
-      const float* qj = sCQ + (b * 2 + 1) * BN;
+      const int sb = jt % NSB;   // shared-memory stage of this column tile (b indexes the TMEM S/P buffer)
+      const bool edge = (jbase + BN > p.Bg) || (diag >= jbase && diag < jbase + BN) || sFlags[sb] || my_hi_odd;
+      const int* lab_lo = sLab + (sb * 2 + 0) * BN;
+      const int* lab_hi = sLab + (sb * 2 + 1) * BN;
+      const float* cj = sCQ + (sb * 2 + 0) * BN;
+      const float* qj = sCQ + (sb * 2 + 1) * BN;
       const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * kBufCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -898,18 +972,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
             const int4 l4 = *reinterpret_cast<const int4*>(lab_lo + c0 + q);
             const float4 c4 = *reinterpret_cast<const float4*>(cj + c0 + q);
             const float4 q4 = *reinterpret_cast<const float4*>(qj + c0 + q);
-            const float e0 = ex2_approx(fmaf(__uint_as_float(rw[q]), k2, -k2));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(rw[q + 1]), k2, -k2));
-            const float e2 = ex2_approx(fmaf(__uint_as_float(rw[q + 2]), k2, -k2));
-            const float e3 = ex2_approx(fmaf(__uint_as_float(rw[q + 3]), k2, -k2));
-            const float x0 = e0 * ((ci + c4.x) - (((l4.x == my_lo) != ps) ? (qi + q4.x) : 0.f));
-            const float x1 = e1 * ((ci + c4.y) - (((l4.y == my_lo) != ps) ? (qi + q4.y) : 0.f));
-            const float x2 = e2 * ((ci + c4.z) - (((l4.z == my_lo) != ps) ? (qi + q4.z) : 0.f));
-            const float x3 = e3 * ((ci + c4.w) - (((l4.w == my_lo) != ps) ? (qi + q4.w) : 0.f));
-            const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
-            rw[q] = __float_as_uint(h0); rw[q + 1] = __float_as_uint(h1); rw[q + 2] = __float_as_uint(h2); rw[q + 3] = __float_as_uint(h3);
-            lw[q] = __float_as_uint(x0 - h0); lw[q + 1] = __float_as_uint(x1 - h1);
-            lw[q + 2] = __float_as_uint(x2 - h2); lw[q + 3] = __float_as_uint(x3 - h3);
+            // packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2): ~7 issue slots per pair instead of ~12
+            const float2 t01 = __ffma2_rn(make_float2(__uint_as_float(rw[q]), __uint_as_float(rw[q + 1])), k2v, nk2v);
+            const float2 t23 = __ffma2_rn(make_float2(__uint_as_float(rw[q + 2]), __uint_as_float(rw[q + 3])), k2v, nk2v);
+            const float2 e01 = make_float2(ex2_approx(t01.x), ex2_approx(t01.y));
+            const float2 e23 = make_float2(ex2_approx(t23.x), ex2_approx(t23.y));
+            const float2 a01 = __fadd2_rn(ci2, make_float2(c4.x, c4.y)), a23 = __fadd2_rn(ci2, make_float2(c4.z, c4.w));
+            float2 b01 = __fadd2_rn(qi2, make_float2(q4.x, q4.y)), b23 = __fadd2_rn(qi2, make_float2(q4.z, q4.w));
+            b01.x = ((l4.x == my_lo) != ps) ? b01.x : 0.f;
+            b01.y = ((l4.y == my_lo) != ps) ? b01.y : 0.f;
+            b23.x = ((l4.z == my_lo) != ps) ? b23.x : 0.f;
+            b23.y = ((l4.w == my_lo) != ps) ? b23.y : 0.f;
+            const float2 x01 = __fmul2_rn(e01, __ffma2_rn(b01, neg1, a01));
+            const float2 x23 = __fmul2_rn(e23, __ffma2_rn(b23, neg1, a23));
+            const float2 h01 = make_float2(tf32_rna(x01.x), tf32_rna(x01.y)), h23 = make_float2(tf32_rna(x23.x), tf32_rna(x23.y));
+            const float2 l01 = __ffma2_rn(h01, neg1, x01), l23 = __ffma2_rn(h23, neg1, x23);
+            rw[q] = __float_as_uint(h01.x); rw[q + 1] = __float_as_uint(h01.y); rw[q + 2] = __float_as_uint(h23.x); rw[q + 3] = __float_as_uint(h23.y);
+            lw[q] = __float_as_uint(l01.x); lw[q + 1] = __float_as_uint(l01.y); lw[q + 2] = __float_as_uint(l23.x); lw[q + 3] = __float_as_uint(l23.y);
           }
         } else {
 #pragma unroll
