@@ -45,6 +45,7 @@ WORKLOAD_NAMES = {
     "clear64": "CLEAR-VAE, synthetic PACS-shaped 3x64x64, batch 128/GPU (BASELINE configs[3])",
 }
 N_POOL = 16  # distinct input batches rotated through the timed region
+CONV_GEMM_DRAM_BYTES_PER_LAUNCH = 11.6e6  # profiles/r1_conv_persist_ncu_raw.csv: mean dram read+write of the 8 captured launches
 
 
 def peaks():
@@ -67,10 +68,15 @@ def layer_flops(arch, cin, zdim, B):
         dec = [(rc[i], rc[i + 1], 4, 2 << i) for i in range(5)]
     f_enc = [2.0 * B * h * h * co * ci * k * k for (ci, co, k, h) in enc]
     f_dec = [2.0 * B * h * h * ci * co * k * k for (ci, co, k, h) in dec]
-    f_lin = [2.0 * B * 2048 * 4 * D, 2.0 * B * 2 * D * 2048]
-    fwd = sum(f_enc) + sum(f_dec) + sum(f_lin)
-    dgrad = fwd - f_enc[0]
-    return dict(fwd=fwd, dgrad=dgrad, wgrad=fwd)
+    f_heads, f_fc = 2.0 * B * 2048 * 4 * D, 2.0 * B * 2 * D * 2048
+    fwd = sum(f_enc) + sum(f_dec) + f_heads + f_fc
+    # what actually runs on the tensor-core GEMM kernel (`conv_gemm`): the first conv, the last conv-transpose (forward and
+    # data gradient) and the fc forward are CUDA-core kernels (conv_direct_* / fc_fwd)
+    tc_enc_fwd = sum(f_enc[1:]) + f_heads
+    tc_dec_fwd = sum(f_dec[:-1])
+    tc_dgrad = sum(f_enc[1:]) + f_heads + f_fc + sum(f_dec[:-1])
+    return dict(fwd=fwd, dgrad=fwd - f_enc[0], wgrad=fwd, tc_enc_fwd=tc_enc_fwd, tc_dec_fwd=tc_dec_fwd, tc_dgrad=tc_dgrad,
+                tc_wgrad=fwd - f_enc[0] - f_dec[-1])
 
 
 # --------------------------------------------------------------------------------------
@@ -196,37 +202,10 @@ def build_trainer(cfg, device):
 
 
 def latent_roofline(dev, pk):
-    """Fused latent-loss kernel pair at the top of BASELINE configs[4] (65536 all-gathered latents, D = 8):
+    """Fused latent-loss kernel pair at the top of BASELINE configs[4] (65536 all-gathered latents, D = 8 and D = 32):
     pairs/s against the measured MUFU ex2 rate — the pipe that bounds it (1 exp per (row, column) pair)."""
     import torch
     from clear_vae_b200.latent import latent_block
-    B, D = 65536, 8
-    g = torch.Generator().manual_seed(0)
-    mu_c = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
-    mu_s = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
-    lv = (torch.randn(B, D, generator=g) * .3).to(dev).requires_grad_(True)
-    eps = torch.randn(B, D, generator=g).to(dev)
-    lab = torch.randint(0, 10, (B,), generator=g).to(dev)
-    w = torch.tensor([0.1, 0.1, 100.0, 100.0, 0, 0, 0, 0], device=dev)
-
-    def run(n):
-        tf = tb = 0.0
-        for _ in range(n):
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            z, sc = latent_block([mu_c, mu_s], [lv, lv], [eps, eps], lab, snn=[1, 1], ps=[False, True], temperature=0.1)
-            e1.record()
-            torch.autograd.backward([sc], [w])
-            e2.record()
-            torch.cuda.synchronize()
-            tf += e0.elapsed_time(e1)
-            tb += e1.elapsed_time(e2)
-            mu_c.grad = mu_s.grad = lv.grad = None
-        return tf / n, tb / n
-
-    run(3)
-    tf, tb = run(5)
-    pairs = 2.0 * B * B  # two terms (content, style)
     probe = os.path.join(ROOT, "tools", "mufu_probe")
     peak, src = 4594.0, "recorded (tools/mufu_probe on this pool: 148 SMs x 16 ex2/clk)"
     try:
@@ -236,11 +215,41 @@ def latent_roofline(dev, pk):
             peak, src = max(vals), "measured now (tools/mufu_probe)"
     except Exception:
         pass
-    f, b = pairs / tf * 1e-6, pairs / tb * 1e-6
-    return dict(workload="contrastive + anti-contrastive terms, 65536 x 65536 pairs each, D=8, fp32 (3xTF32 on tcgen05)",
-                bound="mufu_ex2", unit="Gpair/s", peak=peak, peak_source=src,
-                forward=dict(ms=tf, achieved=f, frac=f / peak), backward=dict(ms=tb, achieved=b, frac=b / peak),
-                algorithmic="1 ex2 + 2*D (fwd) / 6*D (bwd) flop per pair; HBM bytes O(B*D), negligible")
+
+    def point(B, D):
+        g = torch.Generator().manual_seed(0)
+        mu_c = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+        mu_s = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+        lv = (torch.randn(B, D, generator=g) * .3).to(dev).requires_grad_(True)
+        eps = torch.randn(B, D, generator=g).to(dev)
+        lab = torch.randint(0, 10, (B,), generator=g).to(dev)
+        w = torch.tensor([0.1, 0.1, 100.0, 100.0, 0, 0, 0, 0], device=dev)
+
+        def run(n):
+            tf = tb = 0.0
+            for _ in range(n):
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                z, sc = latent_block([mu_c, mu_s], [lv, lv], [eps, eps], lab, snn=[1, 1], ps=[False, True], temperature=0.1)
+                e1.record()
+                torch.autograd.backward([sc], [w])
+                e2.record()
+                torch.cuda.synchronize()
+                tf += e0.elapsed_time(e1)
+                tb += e1.elapsed_time(e2)
+                mu_c.grad = mu_s.grad = lv.grad = None
+            return tf / n, tb / n
+
+        run(3)
+        tf, tb = run(5)
+        pairs = 2.0 * B * B  # two terms (content, style)
+        f, b = pairs / tf * 1e-6, pairs / tb * 1e-6
+        return dict(forward=dict(ms=tf, achieved=f, frac=f / peak), backward=dict(ms=tb, achieved=b, frac=b / peak))
+
+    d8, d32 = point(65536, 8), point(65536, 32)
+    return dict(workload="contrastive + anti-contrastive terms, 65536 x 65536 pairs each, fp32 (3xTF32 on tcgen05); headline D=8",
+                bound="mufu_ex2", unit="Gpair/s", peak=peak, peak_source=src, forward=d8["forward"], backward=d8["backward"],
+                d32=d32, algorithmic="1 ex2 + 2*D (fwd) / 6*D (bwd) flop per pair; HBM bytes O(B*D), negligible")
 
 
 def main():
@@ -332,11 +341,19 @@ def main():
     meter = _ops.meter
     meter.reset()
     tr.use_cuda_graph = False   # per-kernel event timing needs the eager path (same kernels, same order)
-    meter.timed = {"conv_gemm", "conv_direct_fwd", "conv_wgrad", "latent_fwd", "latent_bwd", "bn_finalize", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd",
-                   "bn_reduce", "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize"}
-    for i in range(2):
+    meter.timed = {"conv_gemm", "conv_direct_fwd", "conv_direct_dgrad", "conv_direct_wgrad", "fc_fwd", "conv_wgrad", "latent_fwd", "latent_bwd",
+                   "bn_finalize", "bn_finalize_apply", "bn_relu_apply", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd", "bn_reduce",
+                   "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize", "mi_estimator", "mi_bound_bwd", "adam_step"}
+    def queued_step(i):
+        # eager launches are CPU-bound: without work queued ahead, an event pair around one op would also time the host
+        # side of the op (output allocation, argument checks).  A spin kernel in front lets the host run ahead, so the
+        # events bracket back-to-back device execution only.
+        torch.cuda._sleep(int(1.5e8))   # ~75 ms: longer than the host needs to enqueue one eager step
         step_dev(i)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+
+    for i in range(2):
+        queued_step(i)
     dbg("profiling pass done")
     prof = meter.elapsed_ms()
     launches_per_step = meter.launches() // 2
@@ -345,8 +362,7 @@ def main():
     meter.reset()
     meter.timed = {dominant} if dominant else set()
     for i in range(K):          # eager pass over the same K steps: live CUDA-event timing of the dominant kernel
-        step_dev(i)
-    torch.cuda.synchronize()
+        queued_step(i)
     dom = meter.elapsed_ms().get(dominant, (0, 0.0))
     eager_launches = meter.launches()
     meter.reset()
@@ -394,18 +410,20 @@ def main():
     # ---- roofline of the dominant kernel (algorithmic flops from the layer geometry)
     pk = peaks()
     fl = layer_flops(cfg["arch"], cfg["cin"], cfg["z"], B)
-    n_fwd = {"clear": 1, "tc": 2, "mim": 6}[cfg["kind"]]
-    alg = {"conv_gemm": n_fwd * fl["fwd"] + fl["dgrad"], "conv_wgrad": fl["wgrad"]}
+    # forwards per step: CLEAR 1; TC 2 (second full forward for the discriminator); MIM 2 encoder + 6 decoder passes
+    n_enc, n_dec = {"clear": (1, 1), "tc": (2, 2), "mim": (2, 6)}[cfg["kind"]]
+    alg = {"conv_gemm": n_enc * fl["tc_enc_fwd"] + n_dec * fl["tc_dec_fwd"] + fl["tc_dgrad"], "conv_wgrad": fl["tc_wgrad"]}
     roof = None
     if dominant in alg and dom[0] > 0:
         per_step_ms = dom[1] / K
         ach = alg[dominant] / (per_step_ms * 1e-3) / 1e12
-        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r1_conv_tc_ncu_raw.csv: mean of
-        # dram__bytes_read.sum + dram__bytes_write.sum over the 8 conv launches of one forward); null for other kernels
-        traffic = 7.28e6 if (dominant == "conv_gemm" and args.config.startswith("mim")) else None
+        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r1_conv_persist_ncu_raw.csv: mean of
+        # dram__bytes_read.sum + dram__bytes_write.sum over the conv_gemm launches of one step); null for other kernels
+        traffic = CONV_GEMM_DRAM_BYTES_PER_LAUNCH if (dominant == "conv_gemm" and args.config.startswith("mim")) else None
         roof = dict(kernel=dominant, bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=traffic,
                     launches_per_step=dom[0] // K, ms_per_step=per_step_ms, peak_source=pk["src"] + " bf16 sustained",
-                    timing="CUDA events around every launch of this kernel, eager pass over the same K steps",
+                    timing="CUDA events around every launch of this kernel, eager pass over the same K steps (host run-ahead "
+                           "behind a spin kernel, so the pairs bracket device time only)",
                     algorithmic_gflop_per_step=alg[dominant] / 1e9)
     elif dominant is not None and dom[0] > 0:
         roof = dict(kernel=dominant, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None,

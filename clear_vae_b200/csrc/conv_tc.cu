@@ -1275,13 +1275,8 @@ int launch_persist(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_persist_kernel<BN, MASKED>, kPThreads, smem) != cudaSuccess || occ < 1)
-      occ = 1;
-    per_sm = occ > 2 ? 2 : occ;
-  }
+  // two CTAs per SM when registers (launch bounds) and shared memory (+1 KiB the driver reserves per CTA) allow it
+  const int per_sm = (BN <= 64 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
   int nsm = 148;
   const int grid = std::min(p.n_tiles, per_sm * nsm);
   conv_tc_persist_kernel<BN, MASKED><<<grid, kPThreads, smem, st>>>(tm, p);

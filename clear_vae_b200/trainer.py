@@ -171,13 +171,13 @@ class VAETrainer(Trainer):
         """data-parallel gradient averaging (one flat all-reduce); no-op on a single GPU."""
         d = self.dist
         if d is None or d.world == 1:
-            return
+            return 1.0
         import torch.distributed as td
         grads = [p.grad for p in params if p.grad is not None]
         flat = torch.cat([g.reshape(-1) for g in grads])
         td.all_reduce(flat, group=d.group)
-        flat.mul_(1.0 / d.world)
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        return 1.0 / d.world   # the rank average is applied by the optimiser kernel (grad_scale)
 
 
 class CLEARVAETrainer(VAETrainer):
@@ -200,8 +200,7 @@ class CLEARVAETrainer(VAETrainer):
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 1],
                                                         ps=[False, bool(hp["ps"])], sim_fn=self.sim_fn, eps=eps, dist=self.dist)
         torch.autograd.backward([recon, sc], [torch.ones_like(recon), self._weights_dev(X.device)])
-        self._sync_grads(list(vae.parameters()))
-        fused_adam_step(self.optimizer)
+        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
         return recon, sc
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -264,8 +263,7 @@ class ClearTCVAETrainer(VAETrainer):
         d_score = fc(z)
         mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
-        self._sync_grads(list(vae.parameters()))
-        fused_adam_step(self.optimizer)
+        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
@@ -275,8 +273,7 @@ class ClearTCVAETrainer(VAETrainer):
         factor_loss = F.binary_cross_entropy(torch.cat([d_joint, d_marg], 0),
                                              torch.cat([torch.ones_like(d_joint), torch.zeros_like(d_marg)], 0))
         factor_loss.backward()
-        self._sync_grads(list(fc.parameters()))
-        fused_adam_step(self.factor_optimizer)
+        fused_adam_step(self.factor_optimizer, self._sync_grads(list(fc.parameters())))
         return recon, sc, mi.detach(), factor_loss.detach()
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, factor_d_losses: list):
@@ -334,8 +331,7 @@ class ClearMIMVAETrainer(VAETrainer):
         zc, zs = z[:, :D], z[:, D:]
         mi = est(zc, zs, perm) if (perm is not None and isinstance(est, CLUBSample)) else est(zc, zs)
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
-        self._sync_grads(list(vae.parameters()))
-        fused_adam_step(self.optimizer)
+        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
         # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
         # The encoder is unchanged across the 5 iterations, so its output is computed once and its BatchNorm
         # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and
@@ -344,13 +340,25 @@ class ClearMIMVAETrainer(VAETrainer):
         dummy = torch.zeros(X.shape[0], dtype=torch.int64, device=X.device)
         with torch.no_grad():
             mu_c, lv_c, mu_s, lv_s = vae.encode(X, bn_repeat=5)
-        for j in range(5):
-            with torch.no_grad():
+            zs = []
+            for j in range(5):
                 e = (torch.randn_like(lv_c), torch.randn_like(lv_s)) if inner_eps is None else inner_eps[j]
                 z2, _ = latent_block([mu_c, mu_s], [lv_c, lv_s], list(e), dummy, snn=[0, 0], ps=[0, 0])
                 vae._decode(z2, None, stats_only=True)
-            ll = est.learning_grads(z2[:, :D], z2[:, D:])   # loss + all parameter gradients: one launch
-            self._sync_grads(list(est.parameters()))
+                zs.append(z2)
+        d = self.dist
+        if d is not None and d.world > 1:
+            # Data parallel: the five detached latent batches are all-gathered ONCE and every rank runs the (tiny)
+            # estimator updates on the global batch.  The fixed-order reduction of the estimator kernel makes the
+            # gradients bit-identical on all ranks, so the parameters stay in sync without five gradient all-reduces.
+            import torch.distributed as td
+            loc = torch.stack(zs)                                            # [5, B, 2D]
+            allz = torch.empty((d.world * 5,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
+            td.all_gather_into_tensor(allz, loc, group=d.group)               # rank-major concatenation along dim 0
+            allz = allz.view((d.world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, d.world * loc.shape[1], loc.shape[2])
+            zs = [allz[j] for j in range(5)]
+        for j in range(5):
+            ll = est.learning_grads(zs[j][:, :D], zs[j][:, D:])   # loss + all parameter gradients: one launch
             fused_adam_step(self.mi_estimator_optimizer)
             learn.append(ll)
         return recon, sc, mi.detach(), torch.stack(learn)

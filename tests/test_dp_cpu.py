@@ -48,8 +48,18 @@ def _worker(rank, world, port, q):
         ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(1))]
         ps[0].grad = torch.full((3, 2), float(rank + 1))
         ps[1].grad = torch.arange(5.0) * (rank + 1)
-        tr._sync_grads(ps)                                               # third parameter has no grad: skipped
-        assert torch.allclose(ps[0].grad, torch.full((3, 2), 1.5)) and torch.allclose(ps[1].grad, torch.arange(5.0) * 1.5)
+        scale = tr._sync_grads(ps)                                       # third parameter has no grad: skipped
+        assert scale == 1.0 / world                                      # the average is applied by the optimiser kernel
+        assert torch.allclose(ps[0].grad * scale, torch.full((3, 2), 1.5))
+        assert torch.allclose(ps[1].grad * scale, torch.arange(5.0) * 1.5)
+        # (5) the CLEAR-MIM estimator batches are gathered once as [world, 5, B, 2D] -> [5, world*B, 2D]
+        loc = torch.arange(5 * 3 * 4, dtype=torch.float32).view(5, 3, 4) + 1000.0 * rank
+        allz = torch.empty((world * 5,) + tuple(loc.shape[1:]))
+        td.all_gather_into_tensor(allz, loc)
+        glob = allz.view((world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, world * 3, 4)
+        for j in range(5):
+            for r in range(world):
+                assert torch.equal(glob[j, r * 3:(r + 1) * 3], torch.arange(5 * 3 * 4, dtype=torch.float32).view(5, 3, 4)[j] + 1000.0 * r)
         assert ps[2].grad is None
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
