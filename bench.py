@@ -278,6 +278,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         td.init_process_group("nccl", device_id=dev)
     _ops.load()
     cfg = CONFIGS[args.config]
