@@ -49,6 +49,7 @@ struct TermB {
   const float *mu, *lv, *eps, *mu_cols, *stats_all, *dz;
   float *dmu, *dlv;
   int snn, ps;
+  const float* lv_cols;
 };
 struct BwdParams {
   TermB t[2];
@@ -59,16 +60,63 @@ struct BwdParams {
   const float *scalars, *gscal;
 };
 
-enum { SIM_COS = CLEARVAE_SIM_COSINE, SIM_L2 = CLEARVAE_SIM_L2 };
+enum { SIM_COS = CLEARVAE_SIM_COSINE, SIM_L2 = CLEARVAE_SIM_L2, SIM_ML2 = CLEARVAE_SIM_MODIFIED_L2, SIM_JEF = CLEARVAE_SIM_JEFFREY,
+       SIM_MAH = CLEARVAE_SIM_MAHALANOBIS };
+// similarities that also read logvar (losses.py:62-84) stage up to three derived per-column arrays next to mu:
+//   modified_l2 : u = exp(-lv/2)                      s_ij = -sum_d (mu_j - mu_i)^2 u_i u_j
+//   mahalanobis : v = exp(lv)                         s_ij = -sum_d (mu_j - mu_i)^2 / ((v_i + v_j) / 2)
+//   jeffrey     : v, w = 1/v, h = 1/(v + 1e-8)        s_ij = -1/4 [ -2D + sum_d ((mu_j - mu_i)^2 (w_i + w_j) + v_j h_i + v_i h_j) ]
+// all symmetric in (i, j), so the backward still folds G^T into the row pass (coefficient G_ij + G_ji).
+template <int SIM> struct SimLv { static constexpr int N = SIM == SIM_JEF ? 3 : (SIM == SIM_ML2 || SIM == SIM_MAH) ? 1 : 0; };
+template <int SIM>
+__device__ __forceinline__ void lv_derive(float lv, float (&o)[3]) {
+  if (SIM == SIM_ML2) { o[0] = expf(-0.5f * lv); o[1] = o[2] = 0.f; }
+  else { const float v = expf(lv); o[0] = v; o[1] = 1.f / v; o[2] = 1.f / (v + 1e-8f); }
+}
+// one dimension of one pair: contribution to -s (acc), and the derivatives of s w.r.t. the ROW's mu_d and logvar_d
+template <int SIM, bool GRAD>
+__device__ __forceinline__ void pair_dim(float a, const float (&ri)[3], float x, float c0, float c1, float c2, float& acc, float& ds_da,
+                                         float& ds_dlv) {
+  const float df = x - a;
+  if (SIM == SIM_ML2) {
+    const float t = ri[0] * c0;
+    acc = fmaf(df * df, t, acc);
+    if (GRAD) { ds_da = 2.f * df * t; ds_dlv = 0.5f * df * df * t; }
+  } else if (SIM == SIM_MAH) {
+    const float iv = 2.f / (ri[0] + c0);          // 1 / V, V = (v_i + v_j) / 2
+    acc = fmaf(df * df, iv, acc);
+    if (GRAD) { ds_da = 2.f * df * iv; ds_dlv = 0.5f * df * df * iv * iv * ri[0]; }
+  } else {
+    acc += df * df * (ri[1] + c1) + c0 * ri[2] + ri[0] * c2;
+    if (GRAD) {
+      ds_da = 0.5f * df * (ri[1] + c1);
+      ds_dlv = -0.25f * (-df * df * ri[1] - c0 * ri[2] * ri[2] * ri[0] + ri[0] * c2);
+    }
+  }
+}
+template <int SIM>
+__device__ __forceinline__ float sim_from_acc(float acc, int D) {
+  return SIM == SIM_JEF ? -0.25f * (acc - 2.f * (float)D) : -acc;
+}
 
 // ---------------------------------------------------------------------------
 // column tile: thread `tid` stages column j0 + tid (normalised for cosine)
 // ---------------------------------------------------------------------------
 template <int DP, int SIM>
 __device__ __forceinline__ void stage_column(const float* __restrict__ cols, const long long* __restrict__ lab,
-                                             long long j, long long Bg, int D, float* sN, long long* sL) {
+                                             long long j, long long Bg, int D, float* sN, long long* sL,
+                                             const float* __restrict__ lv_cols = nullptr, float* sX = nullptr) {
   float v[DP];
   const int tid = threadIdx.x;
+  if (SimLv<SIM>::N > 0) {   // derived logvar arrays [N][DP][kTN] of the logvar-aware similarities
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      float o[3] = {0.f, 0.f, 0.f};
+      if (j < Bg && d < D) lv_derive<SIM>(__ldg(lv_cols + j * (long long)D + d), o);
+#pragma unroll
+      for (int k = 0; k < SimLv<SIM>::N; ++k) sX[(k * DP + d) * kTN + tid] = o[k];
+    }
+  }
   if (j < Bg) {
     const float* src = cols + j * (long long)D;
     if ((D & 3) == 0) {
@@ -196,14 +244,28 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
     float row[RM][DP], inv_norm[RM];
     long long rl[RM];
     load_rows<DP, RM, SIM>(t.mu, p.lab_r, row0, p.B, D, row, inv_norm, rl);
+    constexpr int NLV = SimLv<SIM>::N;
+    float rlv[RM][NLV > 0 ? DP : 1][3];
+    if constexpr (NLV > 0) {
+#pragma unroll
+      for (int r = 0; r < RM; ++r)
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const long long i = row0 + r;
+          rlv[r][d][0] = rlv[r][d][1] = rlv[r][d][2] = 0.f;
+          if (i < p.B && d < D) lv_derive<SIM>(__ldg(t.lv + i * (long long)D + d), rlv[r][d]);
+        }
+    }
     float sa[RM], sp[RM], ma[RM], mp[RM];
 #pragma unroll
     for (int r = 0; r < RM; ++r) { sa[r] = sp[r] = 0.f; ma[r] = mp[r] = -INFINITY; }
     const float k2 = p.inv_tau * CV_LOG2E;
     const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+    const float* lvc = t.lv_cols ? t.lv_cols : t.lv;
+    float* sX = sRed + kWarps + 1;   // [NLV][DP][kTN]
     for (long long j0 = 0; j0 < p.Bg; j0 += kTN) {
       __syncthreads();
-      stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL);
+      stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL, lvc, sX);
       __syncthreads();
       for (int jj = lane; jj < kTN; jj += 32) {
         const long long j = j0 + jj;
@@ -214,7 +276,18 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
         const long long lab = sL[jj];
 #pragma unroll
         for (int r = 0; r < RM; ++r) {
-          const float s = pair_sim<DP, SIM>(row[r], x);
+          float s;
+          if constexpr (NLV > 0) {
+            float acc = 0.f, u0, u1;
+#pragma unroll
+            for (int d = 0; d < DP; ++d)
+              if (d < D)
+                pair_dim<SIM, false>(row[r][d], rlv[r][d], x[d], sX[d * kTN + jj], NLV > 1 ? sX[(DP + d) * kTN + jj] : 0.f,
+                                     NLV > 2 ? sX[(2 * DP + d) * kTN + jj] : 0.f, acc, u0, u1);
+            s = sim_from_acc<SIM>(acc, D);
+          } else {
+            s = pair_sim<DP, SIM>(row[r], x);
+          }
           const bool cand = (j != p.row_off + row0 + r);
           const bool pos = cand && ((lab == rl[r]) != (t.ps != 0));
           if (FAST) {
@@ -665,20 +738,32 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
   long long* sL = reinterpret_cast<long long*>(sN + DP * kTN);  // [kTN]
   float* sC = reinterpret_cast<float*>(sL + kTN);               // [kTN]
   float* sQ = sC + kTN;                                         // [kTN]
+  float* sX = sQ + kTN;                                         // [NLV][DP][kTN] (logvar-aware similarities)
   const int term = blockIdx.y;
   const TermB& t = p.t[term];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * (kWarps * RM) + warp * RM;
   const int D = p.D;
   const float g_kl = p.gscal[term], g_loss = p.gscal[2 + term];
+  constexpr int NLV = SimLv<SIM>::N;
 
   float dn[RM][DP], row[RM][DP], inv_norm[RM], csum[RM];
+  float dl[RM][NLV > 0 ? DP : 1], rlv[RM][NLV > 0 ? DP : 1][3];
   long long rl[RM];
 #pragma unroll
   for (int r = 0; r < RM; ++r) {
     csum[r] = 0.f;
 #pragma unroll
     for (int d = 0; d < DP; ++d) dn[r][d] = 0.f;
+    if constexpr (NLV > 0) {
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const long long i = row0 + r;
+        dl[r][d] = 0.f;
+        rlv[r][d][0] = rlv[r][d][1] = rlv[r][d][2] = 0.f;
+        if (t.snn && i < p.B && d < D) lv_derive<SIM>(__ldg(t.lv + i * (long long)D + d), rlv[r][d]);
+      }
+    }
   }
   float w = 0.f;
   if (t.snn) {
@@ -700,9 +785,10 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
     }
     const float k2 = p.inv_tau * CV_LOG2E;
     const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+    const float* lvc = t.lv_cols ? t.lv_cols : t.lv;
     for (long long j0 = 0; j0 < p.Bg; j0 += kTN) {
       __syncthreads();
-      stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL);
+      stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL, lvc, sX);
       {
         const long long j = j0 + threadIdx.x;
         float a = INFINITY, b = INFINITY;
@@ -722,7 +808,21 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
         const float cj = sC[jj], qj = sQ[jj];
 #pragma unroll
         for (int r = 0; r < RM; ++r) {
-          const float s = pair_sim<DP, SIM>(row[r], x);
+          float s;
+          float da[NLV > 0 ? DP : 1], dv[NLV > 0 ? DP : 1];
+          if constexpr (NLV > 0) {
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+              da[d] = dv[d] = 0.f;
+              if (d < D)
+                pair_dim<SIM, true>(row[r][d], rlv[r][d], x[d], sX[d * kTN + jj], NLV > 1 ? sX[(DP + d) * kTN + jj] : 0.f,
+                                    NLV > 2 ? sX[(2 * DP + d) * kTN + jj] : 0.f, acc, da[d], dv[d]);
+            }
+            s = sim_from_acc<SIM>(acc, D);
+          } else {
+            s = pair_sim<DP, SIM>(row[r], x);
+          }
           const bool cand = (j != p.row_off + row0 + r);
           const bool pos = cand && ((lab == rl[r]) != (t.ps != 0));
           float coef;
@@ -735,9 +835,14 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
             if (pos) coef -= __expf(xs - qi[r]) + __expf(xs - qj);
           }
           coef = cand ? coef : 0.f;
-          csum[r] += coef;
+          if constexpr (NLV > 0) {
 #pragma unroll
-          for (int d = 0; d < DP; ++d) dn[r][d] = fmaf(coef, x[d], dn[r][d]);
+            for (int d = 0; d < DP; ++d) { dn[r][d] = fmaf(coef, da[d], dn[r][d]); dl[r][d] = fmaf(coef, dv[d], dl[r][d]); }
+          } else {
+            csum[r] += coef;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) dn[r][d] = fmaf(coef, x[d], dn[r][d]);
+          }
         }
       }
     }
@@ -754,15 +859,19 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
       for (int d = 0; d < DP; ++d) {
         dn[r][d] = cv::warp_sum(dn[r][d]);
         dot = fmaf(dn[r][d], row[r][d], dot);
+        if constexpr (NLV > 0) dl[r][d] = cv::warp_sum(dl[r][d]);
       }
     }
     if (i >= p.B) continue;
 #pragma unroll
     for (int d = 0; d < DP; ++d) {
       if ((d & 31) != lane || d >= D) continue;
-      float gm = 0.f, gl = 0.f;
+      float gm = 0.f, gl = 0.f, gl_snn = 0.f;
       if (t.snn) {
-        if (SIM == SIM_COS) {
+        if constexpr (NLV > 0) {
+          gm = w * dn[r][d];          // dn / dl already hold sum_j (G_ij + G_ji) ds_ij/d(mu_i, logvar_i)
+          gl_snn = w * dl[r][d];
+        } else if (SIM == SIM_COS) {
           // n = mu / max(|mu|, eps): the clamp is outside the graph (SURVEY §8a')
           const bool live = inv_norm[r] < 1.f / kCosEps;
           gm = w * (dn[r][d] - (live ? row[r][d] * dot : 0.f)) * inv_norm[r];
@@ -782,7 +891,7 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
         }
       }
       t.dmu[i * D + d] = gm;
-      if (t.dlv != nullptr) t.dlv[i * D + d] = gl;
+      if (t.dlv != nullptr) t.dlv[i * D + d] = gl + gl_snn;
     }
   }
 }
@@ -1090,15 +1199,15 @@ __global__ void pair_mask_kernel(const long long* lab_r, const long long* lab_c,
 // ---------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------
-template <int DP>
-constexpr size_t fwd_smem() { return (size_t)DP * kTN * 4 + kTN * 8 + (kWarps + 1) * 4; }
-template <int DP>
-constexpr size_t bwd_smem() { return (size_t)DP * kTN * 4 + kTN * 8 + 2 * kTN * 4; }
+template <int DP, int SIM>
+constexpr size_t fwd_smem() { return (size_t)DP * kTN * 4 + kTN * 8 + (kWarps + 1) * 4 + (size_t)SimLv<SIM>::N * DP * kTN * 4; }
+template <int DP, int SIM>
+constexpr size_t bwd_smem() { return (size_t)DP * kTN * 4 + kTN * 8 + 2 * kTN * 4 + (size_t)SimLv<SIM>::N * DP * kTN * 4; }
 
 template <int DP, int RM, int SIM, bool FAST>
 int launch_fwd(const FwdParams& p, int n_terms, cudaStream_t st) {
   auto kern = snn_fwd_kernel<DP, RM, SIM, FAST>;
-  constexpr size_t smem = fwd_smem<DP>();
+  constexpr size_t smem = fwd_smem<DP, SIM>();
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms);
   kern<<<grid, kTN, smem, st>>>(p);
@@ -1108,7 +1217,7 @@ int launch_fwd(const FwdParams& p, int n_terms, cudaStream_t st) {
 template <int DP, int RM, int SIM, bool FAST>
 int launch_bwd(const BwdParams& p, int n_terms, cudaStream_t st) {
   auto kern = snn_bwd_kernel<DP, RM, SIM, FAST>;
-  constexpr size_t smem = bwd_smem<DP>();
+  constexpr size_t smem = bwd_smem<DP, SIM>();
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms);
   kern<<<grid, kTN, smem, st>>>(p);
@@ -1128,11 +1237,24 @@ inline int pick_rm(int dp, long long B) {
       if (FASTV) return LAUNCH<DPV, RMV, SIM_COS, true>(P, NT, ST);                               \
       return LAUNCH<DPV, RMV, SIM_COS, false>(P, NT, ST);                                         \
     }                                                                                             \
-    return LAUNCH<DPV, RMV, SIM_L2, false>(P, NT, ST);                                            \
+    if (SIMV == SIM_L2) return LAUNCH<DPV, RMV, SIM_L2, false>(P, NT, ST);                        \
+  } while (0)
+// logvar-aware similarities: one row per warp (their per-dimension state fills the registers), D <= 32
+#define CV_DISPATCH_LV(LAUNCH, P, NT, ST, DPV, SIMV)                                             \
+  do {                                                                                            \
+    if (SIMV == SIM_ML2) return LAUNCH<DPV, 1, SIM_ML2, false>(P, NT, ST);                        \
+    if (SIMV == SIM_MAH) return LAUNCH<DPV, 1, SIM_MAH, false>(P, NT, ST);                        \
+    if (SIMV == SIM_JEF) return LAUNCH<DPV, 1, SIM_JEF, false>(P, NT, ST);                        \
   } while (0)
 
 #define CV_DISPATCH_D(LAUNCH, P, NT, ST, dp, rm, sim, fast)                                      \
   do {                                                                                            \
+    if (sim >= SIM_ML2) {                                                                         \
+      if (dp == 8) CV_DISPATCH_LV(LAUNCH, P, NT, ST, 8, sim);                                     \
+      if (dp == 16) CV_DISPATCH_LV(LAUNCH, P, NT, ST, 16, sim);                                   \
+      if (dp == 32) CV_DISPATCH_LV(LAUNCH, P, NT, ST, 32, sim);                                   \
+      return CLEARVAE_EUNSUPPORTED;                                                               \
+    }                                                                                             \
     if (dp == 8) { if (rm == 4) CV_DISPATCH(LAUNCH, P, NT, ST, 8, 4, sim, fast); CV_DISPATCH(LAUNCH, P, NT, ST, 8, 1, sim, fast); } \
     if (dp == 16) { if (rm == 2) CV_DISPATCH(LAUNCH, P, NT, ST, 16, 2, sim, fast); CV_DISPATCH(LAUNCH, P, NT, ST, 16, 1, sim, fast); } \
     if (dp == 32) CV_DISPATCH(LAUNCH, P, NT, ST, 32, 1, sim, fast);                               \
@@ -1203,7 +1325,7 @@ int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const i
                         int32_t finalize, void* workspace, size_t workspace_bytes, void* stream) {
   if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !workspace || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
   if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
-  if (sim_fn != SIM_COS && sim_fn != SIM_L2) return CLEARVAE_EUNSUPPORTED;
+  if (sim_fn < SIM_COS || sim_fn > SIM_MAH) return CLEARVAE_EUNSUPPORTED;
   if (pad_d(D) < 0) return CLEARVAE_EUNSUPPORTED;
   if (workspace_bytes < clearvae_latent_workspace_bytes(B, Bg, D, n_terms)) return CLEARVAE_EWORKSPACE;
   if (row_offset < 0 || row_offset + B > Bg) return CLEARVAE_EINVAL;
@@ -1213,6 +1335,7 @@ int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const i
     const clearvae_term_fwd& s = terms[i];
     if (!s.mu) return CLEARVAE_EINVAL;
     if (s.snn_enable && (!s.row_stats || !label_rows)) return CLEARVAE_EINVAL;
+    if (s.snn_enable && sim_fn >= SIM_ML2 && !s.logvar) return CLEARVAE_EINVAL;   // these similarities read logvar
     p.t[i] = TermF{s.mu, s.logvar, s.eps, s.mu_cols, s.logvar_cols, s.z, s.row_stats, s.snn_enable, s.ps};
     any_snn |= s.snn_enable != 0;
   }
@@ -1241,7 +1364,7 @@ int clearvae_latent_bwd(const clearvae_term_bwd* terms, int32_t n_terms, const i
                         const float* scalars, const float* gscal, void* stream) {
   if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !gscal || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
   if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
-  if (sim_fn != SIM_COS && sim_fn != SIM_L2) return CLEARVAE_EUNSUPPORTED;
+  if (sim_fn < SIM_COS || sim_fn > SIM_MAH) return CLEARVAE_EUNSUPPORTED;
   if (pad_d(D) < 0) return CLEARVAE_EUNSUPPORTED;
   if (row_offset < 0 || row_offset + B > Bg) return CLEARVAE_EINVAL;
   BwdParams p{};
@@ -1249,7 +1372,8 @@ int clearvae_latent_bwd(const clearvae_term_bwd* terms, int32_t n_terms, const i
     const clearvae_term_bwd& s = terms[i];
     if (!s.mu || !s.dmu) return CLEARVAE_EINVAL;
     if (s.snn_enable && (!s.row_stats_all || !label_rows)) return CLEARVAE_EINVAL;
-    p.t[i] = TermB{s.mu, s.logvar, s.eps, s.mu_cols, s.row_stats_all, s.dz, s.dmu, s.dlogvar, s.snn_enable, s.ps};
+    if (s.snn_enable && sim_fn >= SIM_ML2 && (!s.logvar || !s.dlogvar)) return CLEARVAE_EINVAL;
+    p.t[i] = TermB{s.mu, s.logvar, s.eps, s.mu_cols, s.row_stats_all, s.dz, s.dmu, s.dlogvar, s.snn_enable, s.ps, s.logvar_cols};
   }
   p.lab_r = reinterpret_cast<const long long*>(label_rows);
   p.lab_c = reinterpret_cast<const long long*>(label_cols ? label_cols : label_rows);

@@ -44,9 +44,9 @@ void* cur_stream() { return (void*)at::cuda::getCurrentCUDAStream().stream(); }
 // ---------------------------------------------------------------------------
 std::tuple<Tensor, Tensor, std::vector<Tensor>> latent_fwd(
     at::TensorList mu, const c10::List<OptTensor>& logvar, const c10::List<OptTensor>& eps,
-    const c10::List<OptTensor>& mu_cols, const Tensor& label_rows, const OptTensor& label_cols,
-    at::IntArrayRef snn, at::IntArrayRef ps, int64_t row_offset, int64_t sim_fn, int64_t loss_name, double tau,
-    bool finalize, bool want_z, Tensor workspace) {
+    const c10::List<OptTensor>& mu_cols, const c10::List<OptTensor>& logvar_cols, const Tensor& label_rows,
+    const OptTensor& label_cols, at::IntArrayRef snn, at::IntArrayRef ps, int64_t row_offset, int64_t sim_fn,
+    int64_t loss_name, double tau, bool finalize, bool want_z, Tensor workspace) {
   const int n = (int)mu.size();
   TORCH_CHECK(n >= 1 && n <= 2, "clearvae: 1 or 2 terms");
   TORCH_CHECK((int)logvar.size() == n && (int)eps.size() == n && (int)mu_cols.size() == n && (int)snn.size() == n &&
@@ -75,7 +75,7 @@ std::tuple<Tensor, Tensor, std::vector<Tensor>> latent_fwd(
     terms[i].logvar = fptr(logvar.get(i), "logvar", B, D);
     terms[i].eps = fptr(eps.get(i), "eps", B, D);
     terms[i].mu_cols = fptr(mu_cols.get(i), "mu_cols", Bg, D);
-    terms[i].logvar_cols = nullptr;
+    terms[i].logvar_cols = (int)logvar_cols.size() == n ? fptr(logvar_cols.get(i), "logvar_cols", Bg, D) : nullptr;
     terms[i].z = want_z ? z.data_ptr<float>() + i * D : nullptr;
     terms[i].snn_enable = (int32_t)snn[i];
     terms[i].ps = (int32_t)ps[i];
@@ -103,7 +103,8 @@ void snn_finalize(const Tensor& stats_all, int64_t term, Tensor scalars) {
 
 std::tuple<std::vector<Tensor>, std::vector<Tensor>> latent_bwd(
     at::TensorList mu, const c10::List<OptTensor>& logvar, const c10::List<OptTensor>& eps,
-    const c10::List<OptTensor>& mu_cols, const c10::List<OptTensor>& stats_all, const OptTensor& dz,
+    const c10::List<OptTensor>& mu_cols, const c10::List<OptTensor>& logvar_cols, const c10::List<OptTensor>& stats_all,
+    const OptTensor& dz,
     const Tensor& label_rows, const OptTensor& label_cols, at::IntArrayRef snn, at::IntArrayRef ps,
     int64_t row_offset, int64_t sim_fn, int64_t loss_name, double tau, const Tensor& scalars, const Tensor& gscal) {
   const int n = (int)mu.size();
@@ -151,6 +152,7 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>> latent_bwd(
     }
     terms[i].snn_enable = (int32_t)snn[i];
     terms[i].ps = (int32_t)ps[i];
+    terms[i].logvar_cols = (int)logvar_cols.size() == n ? fptr(logvar_cols.get(i), "logvar_cols", Bg, D) : nullptr;
   }
   check_rc(clearvae_latent_bwd(terms, n, label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)D,
                                (int32_t)(n * D), (int32_t)sim_fn, (int32_t)loss_name, (float)tau,
@@ -599,11 +601,11 @@ int64_t bn_act_workspace_bytes() { return (int64_t)clearvae_bn_act_workspace_byt
 }  // namespace
 
 TORCH_LIBRARY(clearvae, m) {
-  m.def("latent_fwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor label_rows, "
+  m.def("latent_fwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor?[] logvar_cols, Tensor label_rows, "
         "Tensor? label_cols, int[] snn, int[] ps, int row_offset, int sim_fn, int loss_name, float tau, "
         "bool finalize, bool want_z, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor[])");
   m.def("snn_finalize(Tensor stats_all, int term, Tensor(a!) scalars) -> ()");
-  m.def("latent_bwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor?[] stats_all, "
+  m.def("latent_bwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor?[] logvar_cols, Tensor?[] stats_all, "
         "Tensor? dz, Tensor label_rows, Tensor? label_cols, int[] snn, int[] ps, int row_offset, int sim_fn, "
         "int loss_name, float tau, Tensor scalars, Tensor gscal) -> (Tensor[], Tensor[])");
   m.def("pair_mask(Tensor label_rows, Tensor? label_cols, int row_offset, int ps) -> Tensor");

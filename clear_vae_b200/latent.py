@@ -17,6 +17,7 @@ import torch
 from . import _ops
 
 SIM_IDS = {"cosine": 0, "l2": 1, "modified_l2": 2, "jeffrey": 3, "mahalanobis": 4}
+_LOGVAR_SIMS = (2, 3, 4)   # similarities of losses.py:62-84 that also read (and give gradient to) logvar
 LOSS_IDS = {"snn_loss": 0, "supcon_in_loss": 1, "supcon_out_loss": 2}
 
 # indices into the packed scalar vector (include/clearvae_b200.h)
@@ -61,24 +62,29 @@ class _LatentBlock(torch.autograd.Function):
         B, D = mu[0].shape
         label = label.contiguous()
         want_z = cfg["want_z"]
+        use_lv = cfg["sim"] in _LOGVAR_SIMS
         if dist is None or dist.world == 1:
             ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n))
-            z, scalars, stats = ops.latent_fwd(mu, logvar, eps, [None] * n, label, None, cfg["snn"], cfg["ps"], 0,
+            z, scalars, stats = ops.latent_fwd(mu, logvar, eps, [None] * n, [None] * n, label, None, cfg["snn"], cfg["ps"], 0,
                                                cfg["sim"], cfg["loss"], cfg["tau"], True, want_z, ws)
-            cols, label_cols, stats_all, row_off = [None] * n, None, stats, 0
+            cols, lv_cols, label_cols, stats_all, row_off = [None] * n, [None] * n, None, stats, 0
         else:
             # one packed all-gather of the similarity operands + labels
             snn_terms = [i for i in range(n) if cfg["snn"][i]]
-            packed = torch.cat([mu[i] for i in snn_terms] + [label.view(B, 1).view(torch.float32)], dim=1)
+            per = 2 * D if use_lv else D   # logvar travels too for the logvar-dependent similarities
+            packed = torch.cat([torch.cat([mu[i], logvar[i]], 1) if use_lv else mu[i] for i in snn_terms]
+                               + [label.view(B, 1).view(torch.float32)], dim=1)
             g = _all_gather_rows(packed, dist)
-            cols = [None] * n
+            cols, lv_cols = [None] * n, [None] * n
             for k, i in enumerate(snn_terms):
-                cols[i] = g[:, k * D:(k + 1) * D].contiguous()
-            label_cols = g[:, len(snn_terms) * D:].contiguous().view(torch.int64).view(-1)
+                cols[i] = g[:, k * per:k * per + D].contiguous()
+                if use_lv:
+                    lv_cols[i] = g[:, k * per + D:(k + 1) * per].contiguous()
+            label_cols = g[:, len(snn_terms) * per:].contiguous().view(torch.int64).view(-1)
             row_off = dist.rank * B
             Bg = dist.world * B
             ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, Bg, D, n))
-            z, scalars, stats = ops.latent_fwd(mu, logvar, eps, cols, label, label_cols, cfg["snn"], cfg["ps"], row_off,
+            z, scalars, stats = ops.latent_fwd(mu, logvar, eps, cols, lv_cols, label, label_cols, cfg["snn"], cfg["ps"], row_off,
                                                cfg["sim"], cfg["loss"], cfg["tau"], False, want_z, ws)
             st_cat = _all_gather_rows(torch.cat([stats[i] for i in snn_terms], dim=1), dist) if snn_terms else None
             stats_all = [None] * n
@@ -88,7 +94,7 @@ class _LatentBlock(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.row_off = row_off
         ctx.n_saved = (len(mu), len(logvar), len(eps))
-        ctx.save_for_backward(label, label_cols, scalars, *mu, *logvar, *eps, *cols, *stats_all)
+        ctx.save_for_backward(label, label_cols, scalars, *mu, *logvar, *eps, *cols, *stats_all, *lv_cols)
         return z, scalars
 
     @staticmethod
@@ -98,7 +104,7 @@ class _LatentBlock(torch.autograd.Function):
         saved = ctx.saved_tensors
         label, label_cols, scalars = saved[0], saved[1], saved[2]
         rest = list(saved[3:])
-        mu, logvar, eps, cols, stats_all = (rest[k * n:(k + 1) * n] for k in range(5))
+        mu, logvar, eps, cols, stats_all, lv_cols = (rest[k * n:(k + 1) * n] for k in range(6))
         ops = _ops.ops()
         if dscal is None:
             dscal = torch.zeros(8, dtype=scalars.dtype, device=scalars.device)
@@ -112,7 +118,7 @@ class _LatentBlock(torch.autograd.Function):
             dz = dz.contiguous()
             if dz.numel() == 0:
                 dz = None
-        dmu, dlv = ops.latent_bwd(mu, logvar, eps, cols, stats_all, dz, label, label_cols, cfg["snn"], cfg["ps"],
+        dmu, dlv = ops.latent_bwd(mu, logvar, eps, cols, lv_cols, stats_all, dz, label, label_cols, cfg["snn"], cfg["ps"],
                                   ctx.row_off, cfg["sim"], cfg["loss"], cfg["tau"], scalars, dscal)
         g_mu = list(dmu)
         g_lv = [dlv[i] if logvar[i] is not None else None for i in range(n)]

@@ -60,6 +60,9 @@ def contrastive_loss(mu: torch.Tensor, logvar: torch.Tensor, label: torch.Tensor
                      loss_name: str = "snn_loss", ps: bool = False):
     """Temperature-scaled pairwise contrastive loss; mean over rows whose loss is finite
     (rows without a partner under the mask are dropped; `nan` if none is left)."""
-    _, sc = latent_block([mu], [None], [None], label.reshape(-1).long(), snn=[1], ps=[ps], sim_fn=sim_fn,
+    from .latent import SIM_IDS, _LOGVAR_SIMS
+    # jeffrey / mahalanobis / modified_l2 read logvar and give it a gradient (losses.py:62-84); cosine / l2 ignore it
+    lv = logvar if SIM_IDS.get(sim_fn) in _LOGVAR_SIMS else None
+    _, sc = latent_block([mu], [lv], [None], label.reshape(-1).long(), snn=[1], ps=[ps], sim_fn=sim_fn,
                          temperature=temperature, loss_name=loss_name, want_z=False)
     return sc[S_LOSS0]

@@ -103,6 +103,7 @@ typedef struct {
   float* dlogvar;        /* [B, D] out or NULL */
   int32_t snn_enable;
   int32_t ps;
+  const float* logvar_cols; /* [Bg, D] or NULL (= rows): only the logvar-dependent similarities read it */
 } clearvae_term_bwd;
 
 /* backward of the block. `gscal` (device, float[4]) = upstream grads of

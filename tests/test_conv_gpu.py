@@ -259,3 +259,104 @@ def test_direct_boundary_weight_gradient(transposed, k, op, c, H, B, img_bf16):
     a = torch.zeros(2, 14, 14, 32, device=DEV, dtype=torch.bfloat16)
     b2 = torch.zeros(2, 7, 7, 64, device=DEV, dtype=torch.bfloat16)
     assert not ops.conv_direct_wgrad([0, 3, 2, 1, 0, 32, 64, 14, 14], 2, a, nhwc_strides(a), b2, nhwc_strides(b2), other)
+
+
+@pytest.mark.parametrize("B,K,N", [(1024, 16, 2048), (37, 64, 2048), (5, 8, 130)])
+def test_direct_fc_forward(B, K, N):
+    """Linear(2D -> 2048) on the fp32 CUDA-core kernel + BatchNorm1d batch moments per column (vae.py:33-34)."""
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(B + K)
+    z = torch.randn(B, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out = torch.empty(B, N, device=DEV)
+    stats = torch.zeros(2 * N + 2, dtype=torch.float64, device=DEV)
+    assert ops.fc_fwd(z, w, b, out, stats)
+    want = (z.double() @ w.double().T + b.double())
+    assert rel_err(out.double(), want) < 2e-6
+    assert torch.allclose(stats[:N], want.sum(0), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(stats[N:2 * N], (want * want).sum(0), rtol=1e-5, atol=1e-4)
+    # K > 64 is declined (tensor-core GEMM takes over)
+    assert not ops.fc_fwd(torch.zeros(4, 128, device=DEV), torch.zeros(8, 128, device=DEV), None, torch.empty(4, 8, device=DEV), None)
+
+
+@pytest.mark.parametrize("layout,C,HW,B", [(0, 64, 49, 8), (0, 32, 196, 3), (1, 128, 16, 6), (1, 512, 4, 5), (2, 2048, 16, 64), (2, 2048, 4, 7),
+                                           (3, 128, 16, 9), (3, 512, 4, 4)])
+def test_bn_finalize_apply_layouts(layout, C, HW, B):
+    """statistics -> (scale, shift, mean, invstd, running estimates) + relu(bn(raw)) in one launch, all four layouts,
+    against nn.BatchNorm in training mode (vae.py:17-18,34-35)."""
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(layout * 100 + C + HW)
+    if layout == 0:      # channels-last [B, HW, C]
+        raw = (torch.randn(B, HW, C, generator=g) * 2 + 0.5).to(DEV).to(torch.bfloat16)
+        x_ncl = raw.float().permute(0, 2, 1)                     # [B, C, HW]
+    elif layout == 1:    # channel-major [B, C*HW]
+        raw = (torch.randn(B, C * HW, generator=g) * 2 + 0.5).to(DEV).to(torch.bfloat16)
+        x_ncl = raw.float().view(B, C, HW)
+    elif layout == 2:    # fc block: fp32 [B, C] (BatchNorm1d over C features), output permuted to [B, HW, C0]
+        raw = (torch.randn(B, C, generator=g) * 2 + 0.5).to(DEV)
+        x_ncl = raw.view(B, C, 1)
+    else:                # channels-last in, channel-major copies out
+        raw = (torch.randn(B, HW, C, generator=g) * 2 + 0.5).to(DEV).to(torch.bfloat16)
+        x_ncl = raw.float().permute(0, 2, 1)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(C, generator=g) * 0.3).to(DEV)
+    bn = torch.nn.BatchNorm1d(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+        bn.running_mean.normal_(generator=None); bn.running_var.uniform_(0.5, 2.0)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    want = torch.relu(bn(x_ncl))                                  # also updates bn.running_*
+    count = x_ncl.numel() // C
+    stats = torch.zeros(2 * C + 2, dtype=torch.float64, device=DEV)
+    stats[:C] = x_ncl.double().sum((0, 2))
+    stats[C:2 * C] = (x_ncl.double() ** 2).sum((0, 2))
+    expand = HW if layout in (1, 3) else 1
+    act, scale, shift, mean, invstd, raw_cm = ops.bn_finalize_apply(stats, C, float(count), gamma, beta, rm, rv, 0.1, 1e-5, expand, 1, raw,
+                                                                    layout, HW if layout != 0 else 1)
+    if layout == 0:
+        got = act.float().permute(0, 2, 1)
+    elif layout == 1:
+        got = act.float().view(B, C, HW)
+    elif layout == 2:
+        C0 = C // HW
+        got = act.float().view(B, HW, C0).permute(0, 2, 1).reshape(B, C, 1)   # back to the (c0, hw) feature order
+    else:
+        got = act.float().view(B, C, HW)
+        assert torch.equal(raw_cm.view(B, C, HW), raw.permute(0, 2, 1))
+    assert float((got - want).abs().max()) <= 8e-3 * float(want.abs().max()) + 1e-3          # bf16 output
+    assert torch.allclose(mean, x_ncl.mean((0, 2)), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(invstd, torch.rsqrt(x_ncl.var((0, 2), unbiased=False) + 1e-5), rtol=1e-5)
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-5, atol=1e-6) and torch.allclose(rv, bn.running_var, rtol=1e-5, atol=1e-6)
+    assert scale.numel() == C * expand and torch.allclose(scale.view(C, expand)[:, 0], gamma * invstd, rtol=1e-6)
+    assert float(stats.abs().max()) == 0.0                       # accumulator and ticket cleared for the next step
+
+
+@pytest.mark.parametrize("k,op,cout,H,B,dy_bf16", [(3, 1, 3, 14, 8, True), (3, 1, 1, 14, 5, False), (4, 0, 3, 32, 3, True)])
+def test_direct_last_layer_data_gradient(k, op, cout, H, B, dy_bf16):
+    """dgrad of ConvTranspose2d(32 -> C<=4) == Conv2d(C -> 32) of dy, with the ReLU mask and BN-backward sums fused."""
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(k + cout + H)
+    w = (torch.randn(32, cout, k, k, generator=g) / (cout * k * k) ** 0.5).to(DEV)
+    x = torch.randn(B, 32, H, H, generator=g).to(DEV).requires_grad_(True)
+    y = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=op)
+    Ho = y.shape[-1]
+    dy = torch.randn(B, cout, Ho, Ho, generator=g).to(DEV)
+    dy = bf(dy) if dy_bf16 else dy
+    (dx_want,) = torch.autograd.grad(y, x, dy)
+    raw = torch.randn(B, H, H, 32, generator=g).to(DEV).to(torch.bfloat16)     # previous block's raw output (mask source)
+    sc = (torch.rand(32, generator=g) + 0.5).to(DEV)
+    sh = (torch.randn(32, generator=g) * 0.3).to(DEV)
+    mask = (raw.float() * sc + sh) > 0
+    want = dx_want.permute(0, 2, 3, 1) * mask
+    dyt = dy.to(torch.bfloat16) if dy_bf16 else dy
+    dst = torch.empty(B, H, H, 32, device=DEV)
+    stats = torch.zeros(66, dtype=torch.float64, device=DEV)
+    assert ops.conv_direct_dgrad([1, k, 2, 1, op, 32, cout, H, H], B, dyt, [dyt.stride(0), dyt.stride(2), dyt.stride(3), dyt.stride(1)], w, dst,
+                                 nhwc_strides(dst), raw, nhwc_strides(raw), sc, sh, stats)
+    assert rel_err(dst, want) < 1e-5
+    assert torch.allclose(stats[:32].float(), want.sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[32:64].float(), (want * raw.float()).sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
