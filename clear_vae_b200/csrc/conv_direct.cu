@@ -35,6 +35,9 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const void* __restrict_
   __shared__ __align__(16) float sW[4 * K * K * CO];  // [ci*K*K + kh*K + kw][co]
   __shared__ float sRed[2][kNT / 32][CO];
   __shared__ float sMs[2][CO];
+  // per-channel statistics: each thread parks its 32 outputs in a padded tile and thread (column, row quarter) adds 32
+  // rows — two running registers per thread instead of 64, which is what lets 4-5 CTAs share an SM
+  __shared__ float sT[MASKED ? 2 : 1][kNT][CO + 1];
   const int KK = Cin * K * K;
   for (int i = threadIdx.x; i < KK * CO; i += kNT) {
     const int k = i / CO, co = i % CO;  // reference layout w[co][ci][kh][kw] = w[co * KK + k]
@@ -45,11 +48,12 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const void* __restrict_
     sMs[1][threadIdx.x] = msk_shift ? msk_shift[threadIdx.x] : 0.f;
   }
   __syncthreads();
-  float s[CO], q[CO];
-#pragma unroll
-  for (int c = 0; c < CO; ++c) s[c] = q[c] = 0.f;
+  float s_run = 0.f, q_run = 0.f;   // running sums of column (threadIdx.x & 31) over the row quarter (threadIdx.x >> 5)
   const long long npix = (long long)B * Ho * Wo;
-  for (long long pix = (long long)blockIdx.x * kNT + threadIdx.x; pix < npix; pix += (long long)gridDim.x * kNT) {
+  const long long npix_pad = (npix + kNT - 1) / kNT * kNT;   // whole CTA iterates together (barriers inside the loop)
+  for (long long pix0 = (long long)blockIdx.x * kNT + threadIdx.x; pix0 < npix_pad; pix0 += (long long)gridDim.x * kNT) {
+    const bool pvalid = pix0 < npix;
+    const long long pix = pvalid ? pix0 : 0;
     const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho);
     const long long n = pix / ((long long)Wo * Ho);
     float acc[CO];
@@ -100,15 +104,30 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const void* __restrict_
       }
 #pragma unroll
       for (int c = 0; c < CO; ++c) {
-        const float a = fmaf(y[c], sMs[0][c], sMs[1][c]) > 0.f ? acc[c] : 0.f;
+        const float a = (pvalid && fmaf(y[c], sMs[0][c], sMs[1][c]) > 0.f) ? acc[c] : 0.f;
         acc[c] = a;
-        s[c] += a;
-        q[c] = fmaf(a, y[c], q[c]);
+        if (stats != nullptr) { sT[0][threadIdx.x][c] = a; sT[MASKED ? 1 : 0][threadIdx.x][c] = a * y[c]; }
       }
-    } else {
+    } else if (stats != nullptr) {
 #pragma unroll
-      for (int c = 0; c < CO; ++c) { s[c] += acc[c]; q[c] = fmaf(acc[c], acc[c], q[c]); }
+      for (int c = 0; c < CO; ++c) sT[0][threadIdx.x][c] = pvalid ? acc[c] : 0.f;
     }
+    if (stats != nullptr) {
+      __syncthreads();
+      const int col = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 32;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 2) {
+        const float v0 = sT[0][r0 + rr][col], v1 = sT[0][r0 + rr + 1][col];
+        a0 += v0; a1 += v1;
+        if (MASKED) { b0 += sT[MASKED ? 1 : 0][r0 + rr][col]; b1 += sT[MASKED ? 1 : 0][r0 + rr + 1][col]; }
+        else { b0 = fmaf(v0, v0, b0); b1 = fmaf(v1, v1, b1); }
+      }
+      s_run += a0 + a1;
+      q_run += b0 + b1;
+      __syncthreads();
+    }
+    if (!pvalid) continue;
     if (out_bf16) {
       uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * CO);
 #pragma unroll
@@ -122,12 +141,8 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const void* __restrict_
     }
   }
   if (stats == nullptr) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int c = 0; c < CO; ++c) {
-    const float a = cv::warp_sum(s[c]), b = cv::warp_sum(q[c]);
-    if (lane == 0) { sRed[0][warp][c] = a; sRed[1][warp][c] = b; }
-  }
+  sRed[0][threadIdx.x >> 5][threadIdx.x & 31] = s_run;
+  sRed[1][threadIdx.x >> 5][threadIdx.x & 31] = q_run;
   __syncthreads();
   if (threadIdx.x < 2 * CO) {
     const int which = threadIdx.x / CO, c = threadIdx.x % CO;
