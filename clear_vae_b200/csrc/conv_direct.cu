@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict_
 // accumulators, one image value feeds FPT FMAs, image loads are 8/16-lane broadcasts served by L1.  As a 128-row
 // tensor-core GEMM this shape (M = C*K*K = 27..48) ran the scalar gather path and took ~250 us per layer.
 template <int K, int C, int FPT, bool IMG_BF16>
-__global__ void __launch_bounds__(kNT) boundary_wgrad_kernel(const __nv_bfloat16* __restrict__ feat, const void* __restrict__ img,
+__global__ void __launch_bounds__(kNT, (C * K * K * FPT <= 112 ? 3 : 2)) boundary_wgrad_kernel(const __nv_bfloat16* __restrict__ feat, const void* __restrict__ img,
                                                              float* __restrict__ dw, int B, int Hf, int Wf, int Hi, int Wi) {
   constexpr int FG = 32 / FPT;   // lanes per pixel slot
   constexpr int PS = 32 / FG;    // pixel slots per warp
@@ -303,15 +303,20 @@ __global__ void __launch_bounds__(kNT) boundary_wgrad_kernel(const __nv_bfloat16
 #pragma unroll
     for (int j = 0; j < FPT; ++j) acc[i][j] = 0.f;
   const int npix = B * Hf * Wf;                      // host guarantees < 2^31
-  const int nwarps = gridDim.x * (kNT / 32);
-  for (int q = blockIdx.x * (kNT / 32) + warp; q * PS < npix; q += nwarps) {
-    const int pix = q * PS + pg;
+  // each warp walks a contiguous range of work items (PS pixels each): the pixel coordinates advance incrementally (no
+  // integer division in the loop) and consecutive items re-use the image rows they share through L1
+  const int nitems = (npix + PS - 1) / PS;
+  const int nwarps = gridDim.x * (kNT / 32), gw = blockIdx.x * (kNT / 32) + warp;
+  const int per = (nitems + nwarps - 1) / nwarps;
+  const int q_begin = min(gw * per, nitems), q_end = min(q_begin + per, nitems);
+  int pix = q_begin * PS + pg;
+  int w = pix % Wf, h = (pix / Wf) % Hf, n = pix / (Wf * Hf);
+  const int HiWi = Hi * Wi;
+  for (int q = q_begin; q < q_end; ++q) {
     const bool pv = pix < npix;
-    const int pp = pv ? pix : 0;
-    const int w = pp % Wf, t2 = pp / Wf, h = t2 % Hf, n = t2 / Hf;
     float f[FPT];
     {
-      const __nv_bfloat16* fp = feat + (long long)pp * 32 + fg * FPT;
+      const __nv_bfloat16* fp = feat + (long long)(pv ? pix : 0) * 32 + fg * FPT;
       if (FPT == 4) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(fp));
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
@@ -329,26 +334,35 @@ __global__ void __launch_bounds__(kNT) boundary_wgrad_kernel(const __nv_bfloat16
     bool rok[K], cok[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { rok[k] = pv && h0 + k >= 0 && h0 + k < Hi; cok[k] = w0 + k >= 0 && w0 + k < Wi; }
+    // one row pointer per (channel, kh); the kw offsets are immediates
     const long long ibase = ((long long)n * C * Hi + h0) * Wi + w0;
-    // all image values of the patch first (independent loads in flight), then the FMAs
     float xv[C * KK];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-      for (int kh = 0; kh < K; ++kh)
+      for (int kh = 0; kh < K; ++kh) {
+        const long long roff = ibase + c * HiWi + kh * Wi;
+        if (IMG_BF16) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(img) + roff;
 #pragma unroll
-        for (int kw = 0; kw < K; ++kw) {
-          const long long off = ibase + (c * Hi + kh) * Wi + kw;
-          float x = 0.f;
-          if (rok[kh] && cok[kw])
-            x = IMG_BF16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(img) + off))
-                         : __ldg(reinterpret_cast<const float*>(img) + off);
-          xv[c * KK + kh * K + kw] = x;
+          for (int kw = 0; kw < K; ++kw) xv[c * KK + kh * K + kw] = (rok[kh] && cok[kw]) ? __bfloat162float(__ldg(rp + kw)) : 0.f;
+        } else {
+          const float* rp = reinterpret_cast<const float*>(img) + roff;
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) xv[c * KK + kh * K + kw] = (rok[kh] && cok[kw]) ? __ldg(rp + kw) : 0.f;
         }
+      }
 #pragma unroll
     for (int i = 0; i < C * KK; ++i)
 #pragma unroll
       for (int j = 0; j < FPT; ++j) acc[i][j] = fmaf(xv[i], f[j], acc[i][j]);
+    // next item of this lane: PS pixels further along the row-major pixel order (PS <= Wf)
+    pix += PS;
+    w += PS;
+    if (w >= Wf) {
+      w -= Wf;
+      if (++h == Hf) { h = 0; ++n; }
+    }
   }
   // pixel slots -> one value per (tap, feature) per warp; warps -> one per CTA (shared memory); CTAs -> fp32 atomics
 #pragma unroll
@@ -383,7 +397,7 @@ int launch_bwg(bool img_bf16, const __nv_bfloat16* feat, const void* img, float*
                cudaStream_t st) {
   const long long items = ((long long)B * Hf * Wf + FPT - 1) / FPT;   // warp iterations (FPT pixel slots per warp)
   const long long g = (items + kNT / 32 - 1) / (kNT / 32);
-  const long long cap = 148 * 2;                                       // 110-180 registers: two 128-thread CTAs per SM
+  const long long cap = 148 * (C * K * K * FPT <= 112 ? 3 : 2);        // CTAs per SM allowed by the accumulator count
   const int grid = (int)(g < 1 ? 1 : g > cap ? cap : g);
   if (img_bf16) boundary_wgrad_kernel<K, C, FPT, true><<<grid, kNT, 0, st>>>(feat, img, dw, B, Hf, Wf, Hi, Wi);
   else boundary_wgrad_kernel<K, C, FPT, false><<<grid, kNT, 0, st>>>(feat, img, dw, B, Hf, Wf, Hi, Wi);
@@ -511,6 +525,7 @@ int clearvae_conv_direct_wgrad(const clearvae_conv_geom* g, int64_t batch, const
     if (g->Cin != 32 || g->Cout < 1 || g->Cout > 4) return CLEARVAE_EUNSUPPORTED;
     feat = src; img = dy; C = g->Cout; Hf = g->Hin; Hi = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad;
   }
+  if (Hf < 4) return CLEARVAE_EUNSUPPORTED;   // the kernel advances up to 4 pixels along a row per step
   if (feat->dtype != CLEARVAE_BF16 || feat->sc != 1 || feat->sw != 32 || feat->sh != (int64_t)Hf * 32 ||
       feat->sn != (int64_t)Hf * Hf * 32 || ((uintptr_t)feat->ptr & 7))
     return CLEARVAE_EUNSUPPORTED;
