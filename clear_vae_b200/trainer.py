@@ -321,6 +321,13 @@ class ClearMIMVAETrainer(VAETrainer):
     def _needs_perm(self):
         return isinstance(self.mi_estimator, CLUBSample)
 
+    def _side_stream(self, device):
+        st = getattr(self, "_side", None)
+        if st is None or st.device != torch.device(device):
+            st = torch.cuda.Stream(device=device)
+            self._side = st
+        return st
+
     def _device_step(self, X, label, eps=None, inner_eps=None, perm=None):
         vae, est, hp = self.model, self.mi_estimator, self.hyperparameter
         D = vae.z_dim
@@ -341,11 +348,11 @@ class ClearMIMVAETrainer(VAETrainer):
         with torch.no_grad():
             mu_c, lv_c, mu_s, lv_s = vae.encode(X, bn_repeat=5)
             zs = []
-            for j in range(5):
+            for j in range(5):   # noise in the reference's order (c then s, iteration by iteration), then the reparameterisation
                 e = (torch.randn_like(lv_c), torch.randn_like(lv_s)) if inner_eps is None else inner_eps[j]
                 z2, _ = latent_block([mu_c, mu_s], [lv_c, lv_s], list(e), dummy, snn=[0, 0], ps=[0, 0])
-                vae._decode(z2, None, stats_only=True)
                 zs.append(z2)
+        z_est = zs
         d = self.dist
         if d is not None and d.world > 1:
             # Data parallel: the five detached latent batches are all-gathered ONCE and every rank runs the (tiny)
@@ -356,12 +363,24 @@ class ClearMIMVAETrainer(VAETrainer):
             allz = torch.empty((d.world * 5,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
             td.all_gather_into_tensor(allz, loc, group=d.group)               # rank-major concatenation along dim 0
             allz = allz.view((d.world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, d.world * loc.shape[1], loc.shape[2])
-            zs = [allz[j] for j in range(5)]
-        for j in range(5):
-            ll = est.learning_grads(zs[j][:, :D], zs[j][:, D:])   # loss + all parameter gradients: one launch
-            fused_adam_step(self.mi_estimator_optimizer)
-            learn.append(ll)
-        return recon, sc, mi.detach(), torch.stack(learn)
+            z_est = [allz[j] for j in range(5)]
+        # The five estimator updates (two ~10 us launches each, a handful of CTAs) depend only on the latents; the five
+        # decoder passes only feed BatchNorm running statistics.  They run as two parallel branches — a side stream in
+        # eager mode, a fork/join inside the captured graph — so the small estimator kernels fill SMs the decoder leaves idle.
+        main = torch.cuda.current_stream(X.device)
+        side = self._side_stream(X.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for j in range(5):
+                ll = est.learning_grads(z_est[j][:, :D], z_est[j][:, D:])   # loss + all parameter gradients: one launch
+                fused_adam_step(self.mi_estimator_optimizer)
+                learn.append(ll)
+            learn_t = torch.stack(learn)
+        with torch.no_grad():
+            for j in range(5):
+                vae._decode(zs[j], None, stats_only=True)
+        main.wait_stream(side)
+        return recon, sc, mi.detach(), learn_t
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, mi_losses: list, mi_learning_losses: list):
         self.model.train()
