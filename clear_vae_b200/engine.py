@@ -205,12 +205,14 @@ class EncoderFn(torch.autograd.Function):
         raw_last, _ = saved_raw[-1]
         sc_last, sh_last = saved_pre[-1]
         # heads: weight / bias gradients
-        d_heads_w = torch.zeros_like(heads_w)
-        if saved_act[-1] is not None:
-            ops.conv_wgrad(hg, B, saved_act[-1], [K, 0, 0, 1], None, None, False, dlat, [N, 0, 0, 1], d_heads_w)
-        else:
-            ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w)
-        d_heads_b = ops.colsum(dlat)
+        keep = [dlat]   # operands of side-stream kernels stay referenced until the join
+        with eng.wgrad_branch(dev):
+            d_heads_w = torch.zeros_like(heads_w)
+            if saved_act[-1] is not None:
+                ops.conv_wgrad(hg, B, saved_act[-1], [K, 0, 0, 1], None, None, False, dlat, [N, 0, 0, 1], d_heads_w)
+            else:
+                ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w)
+            d_heads_b = ops.colsum(dlat)
         # heads: data gradient with the last block's ReLU mask + BatchNorm sums in the epilogue
         g = torch.empty(B, K, dtype=eng.grad_dtype, device=dev)
         st = eng.stat_buf(("enc_b", n - 1), K, dev)
@@ -234,19 +236,21 @@ class EncoderFn(torch.autograd.Function):
             dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, last, BF16)
             if last:
                 raw_strides = nhwc_strides(H, H, sp.cout)
-            dw = torch.zeros_like(w)
             if i == 0:
                 src, src_strides, pre = x, nchw_strides(sp.cin, sp.hin, sp.hin), None
             else:
                 src, src_strides = saved_raw[i - 1]
                 pre = saved_pre[i - 1]
-            if i == 0 and eng.use_direct and ops.conv_direct_wgrad(sp.geom, B, src, src_strides, dy, raw_strides, dw):
-                pass  # Cin <= 4: register-blocked CUDA-core kernel
-            elif i > 0 and saved_act[i - 1] is not None:
-                ops.conv_wgrad(sp.geom, B, saved_act[i - 1], src_strides, None, None, False, dy, raw_strides, dw)
-            else:
-                ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
-                               dy, raw_strides, dw)
+            keep.append(dy)
+            with eng.wgrad_branch(dev):
+                dw = torch.zeros_like(w)
+                if i == 0 and eng.use_direct and ops.conv_direct_wgrad(sp.geom, B, src, src_strides, dy, raw_strides, dw):
+                    pass  # Cin <= 4: register-blocked CUDA-core kernel
+                elif i > 0 and saved_act[i - 1] is not None:
+                    ops.conv_wgrad(sp.geom, B, saved_act[i - 1], src_strides, None, None, False, dy, raw_strides, dw)
+                else:
+                    ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                                   pre is not None, dy, raw_strides, dw)
             grads[4 * i], grads[4 * i + 2], grads[4 * i + 3] = dw, dgamma, dbeta
             # grads[4*i+1] (conv bias) stays None: a bias feeding a train-mode BatchNorm has exactly zero gradient
             if i > 0:
@@ -255,6 +259,8 @@ class EncoderFn(torch.autograd.Function):
                 pwd = eng.packs.get(("enc", i), w, sp.geom, DGRAD)
                 ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g, nhwc_strides(sp.hin, sp.hin, sp.cin),
                               EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
+        eng.wgrad_join(dev)
+        del keep
         return (None, None, d_heads_w, d_heads_b, *grads)
 
 
@@ -380,6 +386,7 @@ class DecoderFn(torch.autograd.Function):
         tgt = target if ctx.has_target else xhat  # without a target the MSE term is absent (gr is None)
         g = ops.sigmoid_mse_bwd(xhat, tgt, gr, ge, raw_last, sp.cout, H * H, B, st)
         grads = [None] * len(params)
+        keep = []   # operands of side-stream kernels stay referenced until the join
         for j in range(n - 1, -1, -1):
             sp = specs[j]
             w, b, gamma, beta = params[4 * j:4 * j + 4]
@@ -393,20 +400,22 @@ class DecoderFn(torch.autograd.Function):
             if nw > 1:
                 dgamma, dbeta = dgamma / nw, dbeta / nw
             dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, False, BF16)
-            dw = torch.zeros_like(w)
             if j == 0:
                 src, src_strides, pre = a_fc, nhwc_strides(sp.hin, sp.hin, sp.cin), None
             else:
                 src, src_strides = saved_raw[j - 1]
                 pre = saved_pre[j - 1]
-            if (last and j > 0 and eng.use_direct and saved_act[j - 1] is not None and
-                    ops.conv_direct_wgrad(sp.geom, B, saved_act[j - 1], src_strides, dy, raw_strides, dw)):
-                pass  # Cout <= 4: register-blocked CUDA-core kernel
-            elif j > 0 and saved_act[j - 1] is not None:
-                ops.conv_wgrad(sp.geom, B, saved_act[j - 1], src_strides, None, None, False, dy, raw_strides, dw)
-            else:
-                ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None, pre is not None,
-                               dy, raw_strides, dw)
+            keep.append(dy)
+            with eng.wgrad_branch(dev):
+                dw = torch.zeros_like(w)
+                if (last and j > 0 and eng.use_direct and saved_act[j - 1] is not None and
+                        ops.conv_direct_wgrad(sp.geom, B, saved_act[j - 1], src_strides, dy, raw_strides, dw)):
+                    pass  # Cout <= 4: register-blocked CUDA-core kernel
+                elif j > 0 and saved_act[j - 1] is not None:
+                    ops.conv_wgrad(sp.geom, B, saved_act[j - 1], src_strides, None, None, False, dy, raw_strides, dw)
+                else:
+                    ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                                   pre is not None, dy, raw_strides, dw)
             grads[4 * j], grads[4 * j + 2], grads[4 * j + 3] = dw, dgamma, dbeta
             if j > 0:
                 g = torch.empty(B, sp.hin, sp.hin, sp.cin, dtype=eng.grad_dtype, device=dev)
@@ -433,11 +442,15 @@ class DecoderFn(torch.autograd.Function):
         if nw > 1:
             d_fc_g, d_fc_beta = d_fc_g / nw, d_fc_beta / nw
         dy_fc = ops.bn_bwd_apply(g_a, raw_fc, None, fc_aff[0], fc_aff[1], coef, N0, 1, False, F32)
-        d_fc_w = torch.zeros_like(fc_w)
-        ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
+        keep.append(dy_fc)
+        with eng.wgrad_branch(dev):
+            d_fc_w = torch.zeros_like(fc_w)
+            ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
         dz = torch.empty(B, K0, dtype=torch.float32, device=dev)
         ops.conv_gemm(fg, DGRAD, B, dy_fc, [N0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, DGRAD), None, dz,
                       [K0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
+        eng.wgrad_join(dev)
+        del keep
         return (None, dz, None, d_fc_w, None, d_fc_g, d_fc_beta, *grads)
 
 
@@ -459,6 +472,39 @@ class Engine:
         self.sync_bn = False
         self.use_direct = True   # direct kernels for the Cin<=4 / Cout<=4 boundary layers
         self.materialize = True  # write relu(bn(raw)) once in bf16 so the GEMM operand loads are pure cp.async copies
+        self.overlap_wgrad = True  # weight gradients on a side stream, overlapping the data-gradient chain
+        self._side = {}
+
+    # ---- weight-gradient branch -----------------------------------------------------------------------------
+    # dW of a block needs only that block's dy and input activation, while the data-gradient chain continues to the
+    # previous block: the weight-gradient kernels are issued on a side stream (a fork/join inside a captured graph),
+    # so two latency-bound kernels share the SMs instead of running back to back.
+    class _Branch:
+        def __init__(self, side, main):
+            self.side, self.main, self.ctx = side, main, None
+
+        def __enter__(self):
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            return self.ctx.__exit__(*exc)
+
+    def wgrad_branch(self, dev):
+        if not self.overlap_wgrad:
+            import contextlib
+            return contextlib.nullcontext()
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = torch.cuda.Stream(device=dev)
+        return Engine._Branch(side, torch.cuda.current_stream(dev))
+
+    def wgrad_join(self, dev):
+        side = self._side.get(dev)
+        if self.overlap_wgrad and side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev)
