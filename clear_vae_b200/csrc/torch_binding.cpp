@@ -562,6 +562,39 @@ std::tuple<Tensor, Tensor> mi_bound_bwd(int64_t mode, const Tensor& grad_out, co
   return {gx, gy};
 }
 
+std::tuple<Tensor, Tensor> tc_factor(int64_t mode, const Tensor& z, const Tensor& w1, const Tensor& b1, const Tensor& w2, const Tensor& b2,
+                                     Tensor workspace) {
+  check_rows(z, "z");
+  check_f32(w1, "w1");
+  check_f32(b1, "b1");
+  check_f32(w2, "w2");
+  check_f32(b2, "b2");
+  const c10::cuda::CUDAGuard guard(z.device());
+  const int64_t B = z.size(0), Z = z.size(1);
+  TORCH_CHECK(w1.numel() == Z * Z && b1.numel() == Z && w2.numel() == Z && b2.numel() == 1, "clearvae: factor_cls parameter shapes");
+  auto fopt = z.options();
+  const bool disc = mode == CLEARVAE_TC_DISC;
+  Tensor out = at::empty({disc ? 1 + Z * Z + 2 * Z + 1 : 1}, fopt);
+  Tensor dz = disc ? at::empty({0}, fopt) : at::empty({B, Z}, fopt);
+  TORCH_CHECK(workspace.is_cuda() && workspace.is_contiguous(), "clearvae: workspace must be a contiguous CUDA tensor");
+  check_rc(clearvae_tc_factor((int32_t)mode, z.data_ptr<float>(), z.stride(0), B, (int32_t)Z, w1.data_ptr<float>(), b1.data_ptr<float>(),
+                              w2.data_ptr<float>(), b2.data_ptr<float>(), out.data_ptr<float>(), disc ? nullptr : dz.data_ptr<float>(),
+                              workspace.data_ptr(), (size_t)workspace.nbytes(), cur_stream()),
+           "tc_factor");
+  return {out, dz};
+}
+
+int64_t tc_workspace_bytes(int64_t mode, int64_t B, int64_t Z) { return (int64_t)clearvae_tc_workspace_bytes((int32_t)mode, B, (int32_t)Z); }
+
+Tensor scale_by(const Tensor& grad_out, const Tensor& x) {
+  check_f32(grad_out, "grad_out");
+  check_f32(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty_like(x);
+  if (x.numel() > 0) check_rc(clearvae_scale(grad_out.data_ptr<float>(), x.data_ptr<float>(), x.numel(), y.data_ptr<float>(), cur_stream()), "scale");
+  return y;
+}
+
 int64_t mi_workspace_bytes(int64_t mode, int64_t B, int64_t Dx, int64_t H, int64_t Dy) {
   return (int64_t)clearvae_mi_workspace_bytes((int32_t)mode, B, (int32_t)Dx, (int32_t)H, (int32_t)Dy);
 }
@@ -639,6 +672,9 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("mi_estimator(int mode, Tensor x, Tensor y, Tensor? perm, Tensor[] params, Tensor(a!) workspace) -> (Tensor, Tensor, Tensor)");
   m.def("mi_bound_bwd(int mode, Tensor grad_out, Tensor dx_unit, Tensor dy_unit, Tensor y, Tensor out_fwd) -> (Tensor, Tensor)");
   m.def("mi_workspace_bytes(int mode, int B, int Dx, int H, int Dy) -> int", &mi_workspace_bytes);
+  m.def("tc_factor(int mode, Tensor z, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor(a!) workspace) -> (Tensor, Tensor)");
+  m.def("tc_workspace_bytes(int mode, int B, int Z) -> int", &tc_workspace_bytes);
+  m.def("scale_by(Tensor grad_out, Tensor x) -> Tensor");
   m.def("adam_step(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, Tensor(d!) steps, "
         "Tensor(e!) counter, float lr, float beta1, float beta2, float eps, float grad_scale) -> ()");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
@@ -671,6 +707,8 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("bn_relu_apply", &bn_relu_apply);
   m.impl("bn_finalize_apply", &bn_finalize_apply);
   m.impl("mi_estimator", &mi_estimator);
+  m.impl("tc_factor", &tc_factor);
+  m.impl("scale_by", &scale_by);
   m.impl("mi_bound_bwd", &mi_bound_bwd);
   m.impl("adam_step", &adam_step);
 }

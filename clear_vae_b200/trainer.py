@@ -256,23 +256,31 @@ class ClearTCVAETrainer(VAETrainer):
 
     def _device_step(self, X, label, eps=None, eps2=None):
         vae, fc, hp = self.model, self.factor_cls, self.hyperparameter
+        from . import tc
+        fp = tc.fused_params(fc) if X.is_cuda else None   # the reference's 2-layer discriminator -> one launch per use
         # --- VAE update (trainer.py:654-677)
         self.optimizer.zero_grad()
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
                                                         sim_fn=self.sim_fn, eps=eps, dist=self.dist)
-        d_score = fc(z)
-        mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
+        if fp is not None:
+            mi = tc.tc_bound(z, fp)
+        else:
+            d_score = fc(z)
+            mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
-        self.factor_optimizer.zero_grad()
-        d_joint = fc(z2)
-        d_marg = fc(factor_shuffling(z2))
-        factor_loss = F.binary_cross_entropy(torch.cat([d_joint, d_marg], 0),
-                                             torch.cat([torch.ones_like(d_joint), torch.zeros_like(d_marg)], 0))
-        factor_loss.backward()
+        if fp is not None:
+            factor_loss = tc.disc_grads(z2, fp)
+        else:
+            self.factor_optimizer.zero_grad()
+            d_joint = fc(z2)
+            d_marg = fc(factor_shuffling(z2))
+            factor_loss = F.binary_cross_entropy(torch.cat([d_joint, d_marg], 0),
+                                                 torch.cat([torch.ones_like(d_joint), torch.zeros_like(d_marg)], 0))
+            factor_loss.backward()
         fused_adam_step(self.factor_optimizer, self._sync_grads(list(fc.parameters())))
         return recon, sc, mi.detach(), factor_loss.detach()
 

@@ -282,6 +282,21 @@ int clearvae_mi_bound_bwd(int32_t mode, const float* grad_out, const float* dx_u
                           int64_t ldy, const float* out_fwd, int64_t B, int32_t Dx, int32_t Dy, float* gx, float* gy, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Density-ratio total-correlation term of CLEAR-TC-VAE: factor_cls = Linear(Z,Z)-ReLU-Linear(Z,1)-Sigmoid
+ * (trainer_utils.py:133-138), Z even, Z <= 64.  w1 [Z,Z], b1 [Z], w2 [Z] (the [1,Z] weight), b2 [1]; z [B, Z] with row stride ldz.
+ *   CLEARVAE_TC_BOUND : out[0] = mean relu(log(d / (1 - d))), d = factor_cls(z) (trainer.py:664-665); dz_unit [B,Z] = d out[0] / dz
+ *   CLEARVAE_TC_DISC  : out[0] = BCELoss(cat[factor_cls(z), factor_cls([z_c | roll(z_s, -1, 0)])], cat[1, 0])
+ *                       (trainer.py:573-587, 683-694), out[1..] = its gradient w.r.t. (w1, b1, w2, b2), flattened in that order
+ * `workspace` zero-initialised once (self-resetting ticket).  clearvae_scale: y = (*grad_out) * x  (device scalar).
+ * ------------------------------------------------------------------------- */
+enum { CLEARVAE_TC_BOUND = 0, CLEARVAE_TC_DISC = 1 };
+size_t clearvae_tc_workspace_bytes(int32_t mode, int64_t B, int32_t Z);
+int clearvae_tc_factor(int32_t mode, const float* z, int64_t ldz, int64_t B, int32_t Z, const float* w1, const float* b1,
+                       const float* w2, const float* b2, float* out, float* dz_unit, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int clearvae_scale(const float* grad_out, const float* x, int64_t n, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Fused multi-tensor Adam: torch.optim.Adam defaults as built by the reference factories
  * (trainer_utils.py:100,139-140,178-181; no weight decay, no amsgrad).  The *_host arrays hold n_tensors
  * device pointers; `steps` = n_steps device floats holding the common step count (all advanced by one),
