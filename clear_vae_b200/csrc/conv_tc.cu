@@ -625,6 +625,9 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cs = p.plan.Cs;
+  long long* const tl_buf = g_conv_timeline ? g_conv_timeline + (long long)blockIdx.x * 64 : nullptr;   // debug timeline
+#define CV_PTL(tile_no, k) do { if (tl_buf && (tile_no) < 15) tl_buf[4 + (tile_no) * 4 + (k)] = gtimer(); } while (0)
+  if (tl_buf && threadIdx.x == 0) tl_buf[0] = gtimer();
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NSP; ++s) { mbar_init(&full[s], BM + 1); mbar_init(&empty[s], 1); }
@@ -654,7 +657,9 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
     const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
     uint32_t kbg = 0, kbs = 0;  // k-blocks issued / announced
     PTile tl;
-    for (int tile = blockIdx.x; p_get_tile(p, tile, BN, &tl); tile += gridDim.x) {
+    int tno = 0;
+    for (int tile = blockIdx.x; p_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tno) {
+      if (threadIdx.x == 0) CV_PTL(tno, 0);
       const Cls& c = p.plan.cls[tl.cls];
       const int Kreal = c.ntaps * Cs;
       const long long Mc = p.batch * c.Hd * c.Wd;
@@ -697,6 +702,7 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
           ++kbs;
         }
       }
+      if (threadIdx.x == 0) CV_PTL(tno, 1);
     }
     cp_async_wait<0>();
     fence_proxy_async();
@@ -739,6 +745,7 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[b]);
+        CV_PTL((int)tcount, 2);
       }
     }
   } else {
@@ -881,12 +888,15 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
+      if (threadIdx.x == 192) CV_PTL((int)tcount, 3);
     }
     if (p.stats != nullptr && acc_n0 >= 0) flush();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (tl_buf && threadIdx.x == 0) tl_buf[1] = gtimer();
+#undef CV_PTL
 }
 
 // ---------------------------------------------------------------------------
