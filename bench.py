@@ -152,7 +152,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -285,7 +285,9 @@ def main():
     B, K, W = cfg["B"], args.steps, max(3, args.warmup)
     tr = build_trainer(cfg, dev)
     if world > 1:
-        tr.dist = DistSpec(td.group.WORLD, rank, world)
+        from clear_vae_b200.peer import PeerComm
+        peer = PeerComm.create(td.group.WORLD, rank, world, dev)   # None -> NCCL collectives (e.g. IPC mapping unavailable)
+        tr.dist = DistSpec(td.group.WORLD, rank, world, peer)
         for p in list(tr.model.parameters()):  # identical replicas
             td.broadcast(p.data, 0)
     tr.model.train()
@@ -342,9 +344,16 @@ def main():
     meter = _ops.meter
     meter.reset()
     tr.use_cuda_graph = False   # per-kernel event timing needs the eager path (same kernels, same order)
+    # ... and one stream: with the weight-gradient / estimator branches on side streams an event pair would also count
+    # whatever shares the SMs with the bracketed kernel
+    eng = getattr(tr.model, "_engine", None)
+    tr.overlap_branches = False
+    if eng is not None:
+        eng.overlap_wgrad = False
     meter.timed = {"conv_gemm", "conv_direct_fwd", "conv_direct_dgrad", "conv_direct_wgrad", "fc_fwd", "conv_wgrad", "latent_fwd", "latent_bwd",
                    "bn_finalize", "bn_finalize_apply", "bn_relu_apply", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd", "bn_reduce",
-                   "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize", "mi_estimator", "mi_bound_bwd", "adam_step"}
+                   "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize", "mi_estimator", "mi_bound_bwd", "adam_step",
+                   "peer_gather", "peer_allreduce"}
     def queued_step(i):
         # eager launches are CPU-bound: without work queued ahead, an event pair around one op would also time the host
         # side of the op (output allocation, argument checks).  A spin kernel in front lets the host run ahead, so the
@@ -365,10 +374,14 @@ def main():
     for i in range(K):          # eager pass over the same K steps: live CUDA-event timing of the dominant kernel
         queued_step(i)
     dom = meter.elapsed_ms().get(dominant, (0, 0.0))
+    dom_bytes = meter.bytes.get(dominant, 0)
     eager_launches = meter.launches()
     meter.reset()
     meter.timed = set()
     tr.use_cuda_graph = graphed
+    tr.overlap_branches = True
+    if eng is not None:
+        eng.overlap_wgrad = True
     dbg("eager kernel-timing pass done")
 
     # ---- timed region: device-resident inputs
@@ -383,7 +396,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / K
     dbg("timed region done")
-    clocks = sampler.stop()
     launches = tr._graph["launches"] * K if graphed else meter.launches()
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the step's scalars
@@ -400,6 +412,7 @@ def main():
     barrier()
     ms_e2e = max(t0.elapsed_time(t1), (time.perf_counter() - wall0) * 1e3) / K
     dbg("e2e region done")
+    clocks = sampler.stop()   # sampled across both timed regions (device-resident and end-to-end)
     h2d = pool_h[0][0].numel() * 4 + pool_h[0][1].numel() * 8
     d2h = vals.numel() * 4
 
@@ -415,20 +428,32 @@ def main():
     n_enc, n_dec = {"clear": (1, 1), "tc": (2, 2), "mim": (2, 6)}[cfg["kind"]]
     alg = {"conv_gemm": n_enc * fl["tc_enc_fwd"] + n_dec * fl["tc_dec_fwd"] + fl["tc_dgrad"], "conv_wgrad": fl["tc_wgrad"]}
     roof = None
-    if dominant in alg and dom[0] > 0:
+    if dominant is not None and dom[0] > 0:
+        # Two floors per launch set: operand bytes / HBM peak and (GEMM kernels) algorithmic flops / tensor peak; the larger
+        # floor is the roof that binds.  Operand bytes = every tensor argument and result of the op counted once per call
+        # (clear_vae_b200/_ops.py:_tensor_bytes) — an im2col re-read or an L2 miss does not add to it.
         per_step_ms = dom[1] / K
-        ach = alg[dominant] / (per_step_ms * 1e-3) / 1e12
+        bytes_step = dom_bytes / K
+        gbs = bytes_step / (per_step_ms * 1e-3) / 1e9
+        floor_hbm = bytes_step / (pk["hbm"] * 1e9)
+        flops = alg.get(dominant)
+        floor_tc = flops / (pk["tf"] * 1e12) if flops else 0.0
+        common = dict(kernel=dominant, launches_per_step=dom[0] // K, ms_per_step=per_step_ms, peak_source=pk["src"],
+                      timing="CUDA events around every launch of this kernel, eager single-stream pass over the same K steps "
+                             "(host run-ahead behind a spin kernel, so the pairs bracket device time only)",
+                      algorithmic_bytes_per_launch=bytes_step / max(1, dom[0] // K),
+                      hbm=dict(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"]))
         # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r1_conv_persist_ncu_raw.csv: mean of
         # dram__bytes_read.sum + dram__bytes_write.sum over the conv_gemm launches of one step); null for other kernels
         traffic = CONV_GEMM_DRAM_BYTES_PER_LAUNCH if (dominant == "conv_gemm" and args.config.startswith("mim")) else None
-        roof = dict(kernel=dominant, bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=traffic,
-                    launches_per_step=dom[0] // K, ms_per_step=per_step_ms, peak_source=pk["src"] + " bf16 sustained",
-                    timing="CUDA events around every launch of this kernel, eager pass over the same K steps (host run-ahead "
-                           "behind a spin kernel, so the pairs bracket device time only)",
-                    algorithmic_gflop_per_step=alg[dominant] / 1e9)
-    elif dominant is not None and dom[0] > 0:
-        roof = dict(kernel=dominant, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None,
-                    launches_per_step=dom[0] // K, ms_per_step=dom[1] / K, peak_source=pk["src"])
+        if flops:
+            tfs = flops / (per_step_ms * 1e-3) / 1e12
+            common["tensor"] = dict(achieved=tfs, peak=pk["tf"], unit="TFLOP/s", frac=tfs / pk["tf"],
+                                    algorithmic_gflop_per_step=flops / 1e9)
+        if floor_tc > floor_hbm:
+            roof = dict(bound="tensor", achieved=tfs, peak=pk["tf"], unit="TFLOP/s", frac=tfs / pk["tf"], traffic=traffic, **common)
+        else:
+            roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=traffic, **common)
 
     if rank == 0:
         cpu = None
@@ -449,7 +474,10 @@ def main():
                                 parallelism=f"dp{world}", cuda_graph=graphed, l2=f"rotating {N_POOL} distinct input batches "
                                 f"({N_POOL * h2d / 1e6:.0f} MB) > 126 MB L2; activations are rewritten every step",
                                 bn="per-GPU batch statistics", conv_math="bf16 operands, fp32 accumulate (tcgen05)",
-                                latent_math="fp32"),
+                                latent_math="fp32",
+                                collectives=("none (1 GPU)" if world == 1 else "one-shot peer-memory kernels over NVLink (csrc/peer_comm.cu)"
+                                             if tr.dist.peer is not None else "NCCL"),
+                                peer_error=(tr.dist.peer.error() if (world > 1 and tr.dist.peer is not None) else None)),
                     clocks=clocks,
                     e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e),

@@ -46,12 +46,14 @@ class _Meter:
         self.timed = set()        # op names to bracket with events
         self.events = defaultdict(list)
         self.meta = defaultdict(list)
+        self.bytes = defaultdict(int)   # per timed op: bytes of every tensor operand + result, each counted once per call
         self.enabled = True
 
     def reset(self):
         self.counts.clear()
         self.events.clear()
         self.meta.clear()
+        self.bytes.clear()
 
     def launches(self):
         return sum(v for k, v in self.counts.items() if k not in _HOST_ONLY)
@@ -62,6 +64,15 @@ class _Meter:
 
 
 meter = _Meter()
+
+
+def _tensor_bytes(x) -> int:
+    """operand footprint of a call: every tensor argument / result once (what the kernel must at least read or write)."""
+    if isinstance(x, torch.Tensor):
+        return x.numel() * x.element_size()
+    if isinstance(x, (list, tuple)):
+        return sum(_tensor_bytes(t) for t in x)
+    return 0
 
 
 class _Proxy:
@@ -84,6 +95,7 @@ class _Proxy:
                     out = _raw(*a, **k)
                     e1.record()
                     meter.events[_name].append((e0, e1))
+                    meter.bytes[_name] += _tensor_bytes(a) + _tensor_bytes(out)
                     return out
                 return _raw(*a, **k)
 

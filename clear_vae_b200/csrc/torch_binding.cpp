@@ -631,6 +631,52 @@ void adam_step(at::TensorList params, at::TensorList grads, at::TensorList exp_a
 
 int64_t bn_act_workspace_bytes() { return (int64_t)clearvae_bn_act_workspace_bytes(); }
 
+// ---- one-shot collectives over peer memory (bases = every rank's buffer as mapped into this process)
+std::vector<void*> peer_bases(at::IntArrayRef bases) {
+  TORCH_CHECK(!bases.empty() && bases.size() <= CLEARVAE_PEER_MAX_RANKS, "clearvae: 1..8 peer buffers");
+  std::vector<void*> b(bases.size());
+  for (size_t i = 0; i < bases.size(); ++i) b[i] = reinterpret_cast<void*>(static_cast<uintptr_t>(bases[i]));
+  return b;
+}
+
+void peer_gather(at::IntArrayRef bases, int64_t rank, int64_t buffer_bytes, at::TensorList src, at::TensorList dst) {
+  const size_t n = src.size();
+  TORCH_CHECK(n >= 1 && n <= CLEARVAE_PEER_MAX_PIECES && dst.size() == n, "clearvae: peer_gather takes 1..8 (src, dst) pairs");
+  const c10::cuda::CUDAGuard guard(src[0].device());
+  auto b = peer_bases(bases);
+  std::vector<const void*> s(n);
+  std::vector<void*> d(n);
+  std::vector<int64_t> nb(n);
+  for (size_t i = 0; i < n; ++i) {
+    TORCH_CHECK(src[i].is_cuda() && dst[i].is_cuda() && src[i].is_contiguous() && dst[i].is_contiguous(),
+                "clearvae: peer_gather needs contiguous CUDA tensors");
+    TORCH_CHECK(src[i].scalar_type() == dst[i].scalar_type(), "clearvae: peer_gather dtype mismatch");
+    nb[i] = (int64_t)src[i].numel() * (int64_t)src[i].element_size();
+    TORCH_CHECK((int64_t)dst[i].numel() * (int64_t)dst[i].element_size() == nb[i] * (int64_t)bases.size(),
+                "clearvae: peer_gather dst must hold world x src");
+    s[i] = src[i].data_ptr();
+    d[i] = dst[i].data_ptr();
+  }
+  check_rc(clearvae_peer_gather(b.data(), (int32_t)bases.size(), (int32_t)rank, buffer_bytes, (int32_t)n, s.data(), d.data(),
+                                nb.data(), cur_stream()), "peer_gather");
+}
+
+void peer_allreduce(at::IntArrayRef bases, int64_t rank, int64_t buffer_bytes, at::TensorList tensors) {
+  const size_t n = tensors.size();
+  if (n == 0) return;
+  const c10::cuda::CUDAGuard guard(tensors[0].device());
+  auto b = peer_bases(bases);
+  std::vector<float*> t(n);
+  std::vector<int64_t> ne(n);
+  for (size_t i = 0; i < n; ++i) {
+    check_f32(tensors[i], "tensor");
+    t[i] = tensors[i].data_ptr<float>();
+    ne[i] = tensors[i].numel();
+  }
+  check_rc(clearvae_peer_allreduce(b.data(), (int32_t)bases.size(), (int32_t)rank, buffer_bytes, (int32_t)n, t.data(), ne.data(),
+                                   cur_stream()), "peer_allreduce");
+}
+
 }  // namespace
 
 TORCH_LIBRARY(clearvae, m) {
@@ -678,6 +724,8 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("adam_step(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, Tensor(d!) steps, "
         "Tensor(e!) counter, float lr, float beta1, float beta2, float eps, float grad_scale) -> ()");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
+  m.def("peer_gather(int[] bases, int rank, int buffer_bytes, Tensor[] src, Tensor(a!)[] dst) -> ()");
+  m.def("peer_allreduce(int[] bases, int rank, int buffer_bytes, Tensor(a!)[] tensors) -> ()");
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "
         "bool pre_relu, Tensor packed_weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, int epilogue, "
         "Tensor? mask_src, int[] mask_strides, Tensor? mask_scale, Tensor? mask_shift, Tensor(b!)? stats) -> ()");
@@ -711,4 +759,6 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("scale_by", &scale_by);
   m.impl("mi_bound_bwd", &mi_bound_bwd);
   m.impl("adam_step", &adam_step);
+  m.impl("peer_gather", &peer_gather);
+  m.impl("peer_allreduce", &peer_allreduce);
 }

@@ -41,6 +41,7 @@ class DistSpec:
     group: object
     rank: int
     world: int
+    peer: object = None   # clear_vae_b200.peer.PeerComm: one-kernel exchanges over NVLink peer memory instead of NCCL
 
 
 def _all_gather_rows(t, dist):
@@ -69,27 +70,42 @@ class _LatentBlock(torch.autograd.Function):
                                                cfg["sim"], cfg["loss"], cfg["tau"], True, want_z, ws)
             cols, lv_cols, label_cols, stats_all, row_off = [None] * n, [None] * n, None, stats, 0
         else:
-            # one packed all-gather of the similarity operands + labels
             snn_terms = [i for i in range(n) if cfg["snn"][i]]
-            per = 2 * D if use_lv else D   # logvar travels too for the logvar-dependent similarities
-            packed = torch.cat([torch.cat([mu[i], logvar[i]], 1) if use_lv else mu[i] for i in snn_terms]
-                               + [label.view(B, 1).view(torch.float32)], dim=1)
-            g = _all_gather_rows(packed, dist)
             cols, lv_cols = [None] * n, [None] * n
-            for k, i in enumerate(snn_terms):
-                cols[i] = g[:, k * per:k * per + D].contiguous()
-                if use_lv:
-                    lv_cols[i] = g[:, k * per + D:(k + 1) * per].contiguous()
-            label_cols = g[:, len(snn_terms) * per:].contiguous().view(torch.int64).view(-1)
+            if dist.peer is not None:
+                # one kernel over NVLink peer memory: every operand lands as its own contiguous [Bg, ...] tensor
+                pieces = [mu[i] for i in snn_terms] + ([logvar[i] for i in snn_terms] if use_lv else []) + [label]
+                got = dist.peer.gather(pieces)
+                for k, i in enumerate(snn_terms):
+                    cols[i] = got[k]
+                    if use_lv:
+                        lv_cols[i] = got[len(snn_terms) + k]
+                label_cols = got[-1]
+            else:
+                # one packed NCCL all-gather of the similarity operands + labels
+                per = 2 * D if use_lv else D   # logvar travels too for the logvar-dependent similarities
+                packed = torch.cat([torch.cat([mu[i], logvar[i]], 1) if use_lv else mu[i] for i in snn_terms]
+                                   + [label.view(B, 1).view(torch.float32)], dim=1)
+                g = _all_gather_rows(packed, dist)
+                for k, i in enumerate(snn_terms):
+                    cols[i] = g[:, k * per:k * per + D].contiguous()
+                    if use_lv:
+                        lv_cols[i] = g[:, k * per + D:(k + 1) * per].contiguous()
+                label_cols = g[:, len(snn_terms) * per:].contiguous().view(torch.int64).view(-1)
             row_off = dist.rank * B
             Bg = dist.world * B
             ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, Bg, D, n))
             z, scalars, stats = ops.latent_fwd(mu, logvar, eps, cols, lv_cols, label, label_cols, cfg["snn"], cfg["ps"], row_off,
                                                cfg["sim"], cfg["loss"], cfg["tau"], False, want_z, ws)
-            st_cat = _all_gather_rows(torch.cat([stats[i] for i in snn_terms], dim=1), dist) if snn_terms else None
             stats_all = [None] * n
-            for k, i in enumerate(snn_terms):
-                stats_all[i] = st_cat[:, 2 * k:2 * k + 2].contiguous()
+            if snn_terms and dist.peer is not None:
+                for i, t in zip(snn_terms, dist.peer.gather([stats[i] for i in snn_terms])):
+                    stats_all[i] = t
+            elif snn_terms:
+                st_cat = _all_gather_rows(torch.cat([stats[i] for i in snn_terms], dim=1), dist)
+                for k, i in enumerate(snn_terms):
+                    stats_all[i] = st_cat[:, 2 * k:2 * k + 2].contiguous()
+            for i in snn_terms:
                 ops.snn_finalize(stats_all[i], i, scalars)
         ctx.cfg = cfg
         ctx.row_off = row_off

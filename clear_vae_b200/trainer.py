@@ -101,6 +101,7 @@ class VAETrainer(Trainer):
         return self._w_host.to(dev, non_blocking=True)  # inside a graph: a memcpy node re-reading the pinned buffer
 
     use_cuda_graph = False
+    overlap_branches = True   # False: every kernel of the step on one stream (bench.py's per-kernel event timing)
     _graph = None
 
     def _needs_perm(self):
@@ -174,6 +175,9 @@ class VAETrainer(Trainer):
             return 1.0
         import torch.distributed as td
         grads = [p.grad for p in params if p.grad is not None]
+        if d.peer is not None and sum(g.numel() for g in grads) * 4 + 16 * len(grads) <= d.peer.slot_bytes():
+            d.peer.allreduce_(grads)   # one kernel: pack -> publish -> pull + sum in rank order -> scatter back
+            return 1.0 / d.world
         flat = torch.cat([g.reshape(-1) for g in grads])
         td.all_reduce(flat, group=d.group)
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
@@ -366,17 +370,20 @@ class ClearMIMVAETrainer(VAETrainer):
             # Data parallel: the five detached latent batches are all-gathered ONCE and every rank runs the (tiny)
             # estimator updates on the global batch.  The fixed-order reduction of the estimator kernel makes the
             # gradients bit-identical on all ranks, so the parameters stay in sync without five gradient all-reduces.
-            import torch.distributed as td
-            loc = torch.stack(zs)                                            # [5, B, 2D]
-            allz = torch.empty((d.world * 5,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
-            td.all_gather_into_tensor(allz, loc, group=d.group)               # rank-major concatenation along dim 0
-            allz = allz.view((d.world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, d.world * loc.shape[1], loc.shape[2])
-            z_est = [allz[j] for j in range(5)]
+            if d.peer is not None:
+                z_est = d.peer.gather(zs)                                        # five pieces, one kernel, final layout
+            else:
+                import torch.distributed as td
+                loc = torch.stack(zs)                                            # [5, B, 2D]
+                allz = torch.empty((d.world * 5,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
+                td.all_gather_into_tensor(allz, loc, group=d.group)               # rank-major concatenation along dim 0
+                allz = allz.view((d.world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, d.world * loc.shape[1], loc.shape[2])
+                z_est = [allz[j] for j in range(5)]
         # The five estimator updates (two ~10 us launches each, a handful of CTAs) depend only on the latents; the five
         # decoder passes only feed BatchNorm running statistics.  They run as two parallel branches — a side stream in
         # eager mode, a fork/join inside the captured graph — so the small estimator kernels fill SMs the decoder leaves idle.
         main = torch.cuda.current_stream(X.device)
-        side = self._side_stream(X.device)
+        side = self._side_stream(X.device) if self.overlap_branches else main   # serial mode: per-kernel timing passes
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for j in range(5):

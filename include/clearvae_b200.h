@@ -307,6 +307,36 @@ int clearvae_adam_step(int32_t n_tensors, float* const* params_host, const float
                        float* const* exp_avg_sq_host, const int64_t* numel_host, float* steps, int32_t n_steps,
                        unsigned int* counter, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * One-shot collectives over NVLink peer memory (data-parallel step).  They replace the small NCCL
+ * exchanges a data-parallel port of the reference loop would issue per step (trainer.py:446-492 under DDP semantics):
+ * the all-gather of the similarity operands / labels / row statistics / estimator latents and the parameter-gradient
+ * all-reduce.  Every rank owns one buffer of `buffer_bytes` (identical on all ranks): a 4 KB header (arrival flags
+ * written by the peers, the device-side call counter) followed by two slots used alternately.  `bases_host[r]` is rank
+ * r's buffer as mapped into THIS process (own pointer at [rank]).  All ranks must issue the same sequence of calls on
+ * one stream; launches are CUDA-graph capturable.  Setup-time helpers (alloc / export / open / close / error) are the
+ * only entry points of the library that allocate or synchronise.
+ *   clearvae_peer_gather:    piece k of `bytes_host[k]` bytes (multiple of 4) per rank -> dst_host[k] = [world][bytes] .
+ *   clearvae_peer_allreduce: every tensor <- sum over ranks, fixed rank order (bit-identical on all ranks), in place.
+ *   clearvae_peer_error:     0 = no poll ever timed out (20 s); otherwise 1 + the rank that was missing.
+ * ------------------------------------------------------------------------- */
+#define CLEARVAE_PEER_MAX_RANKS 8
+#define CLEARVAE_PEER_MAX_PIECES 8
+#define CLEARVAE_PEER_HEADER_BYTES 4096
+#define CLEARVAE_PEER_HANDLE_BYTES 64
+int clearvae_peer_alloc(int64_t bytes, void** ptr);
+int clearvae_peer_free(void* ptr);
+int clearvae_peer_export(void* ptr, uint8_t* handle_host);
+int clearvae_peer_open(const uint8_t* handle_host, void** ptr);
+int clearvae_peer_close(void* ptr);
+int clearvae_peer_error(const void* local_base, int32_t* err_host);
+/* debug: %globaltimer stamps {start, staged, peers ready, pulled} (+2 spare) of CTA 0 for the last 64 calls, [64][6] u64 */
+int clearvae_peer_timeline(const void* local_base, uint64_t* stamps_host);
+int clearvae_peer_gather(void* const* bases_host, int32_t world, int32_t rank, int64_t buffer_bytes, int32_t n_pieces,
+                         const void* const* src_host, void* const* dst_host, const int64_t* bytes_host, void* stream);
+int clearvae_peer_allreduce(void* const* bases_host, int32_t world, int32_t rank, int64_t buffer_bytes, int32_t n_tensors,
+                            float* const* tensors_host, const int64_t* numel_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
