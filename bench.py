@@ -350,6 +350,7 @@ def main():
     tr.overlap_branches = False
     if eng is not None:
         eng.overlap_wgrad = False
+        eng.parallel_stats = False
     meter.timed = {"conv_gemm", "conv_direct_fwd", "conv_direct_dgrad", "conv_direct_wgrad", "fc_fwd", "conv_wgrad", "latent_fwd", "latent_bwd",
                    "bn_finalize", "bn_finalize_apply", "bn_relu_apply", "bn_bwd_coef", "bn_bwd_apply", "bn_act_fwd", "bn_reduce",
                    "sigmoid_mse_bwd", "conv_pack_weight", "colsum", "snn_finalize", "mi_estimator", "mi_bound_bwd", "adam_step",
@@ -382,6 +383,7 @@ def main():
     tr.overlap_branches = True
     if eng is not None:
         eng.overlap_wgrad = True
+        eng.parallel_stats = True
     dbg("eager kernel-timing pass done")
 
     # ---- timed region: device-resident inputs

@@ -1,6 +1,8 @@
 // Reconstruction term of the ELBO (losses.py:45-47): mean_b sum_{chw} (xhat - x)^2,
 // and its gradient.  Pure HBM streaming: 16-byte loads, grid sized to the SM count,
 // deterministic two-level reduction (per-CTA partials, last CTA folds them).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -65,6 +67,30 @@ inline int grid_for(long long n) {
   if (g < 1) g = 1;
   return (int)g;
 }
+// Several reparameterisation draws of the same (mu, logvar) in one launch (CLEAR-MIM inner loop, trainer.py:874-888:
+// five forwards of an unchanged encoder differ only in their noise).  z[j][b, h*D + d] = mu_h + eps[j][h] * exp(logvar_h / 2),
+// the same fmaf / expf expression as the latent kernel's fused reparameterisation (vae.py:56-60).
+struct ReparamTable {
+  const float* mu[2];
+  const float* lv[2];
+  const float* eps[CLEARVAE_REPARAM_MAX_DRAWS * 2];
+  float* z[CLEARVAE_REPARAM_MAX_DRAWS];
+  int heads, draws;
+};
+
+__global__ void __launch_bounds__(kNT) reparam_multi_kernel(const __grid_constant__ ReparamTable tb, long long B, int D) {
+  const long long n = B * D;
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n; i += (long long)gridDim.x * kNT) {
+    const long long b = i / D;
+    const int d = (int)(i - b * D);
+    for (int h = 0; h < tb.heads; ++h) {
+      const float m = __ldg(tb.mu[h] + i), sd = expf(0.5f * __ldg(tb.lv[h] + i));
+      for (int j = 0; j < tb.draws; ++j)
+        tb.z[j][b * (tb.heads * D) + h * D + d] = fmaf(__ldg(tb.eps[j * tb.heads + h] + i), sd, m);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -93,4 +119,34 @@ int clearvae_recon_bwd(const float* xhat, const float* x, const float* grad_out,
   CV_LAUNCH_CHECK();
   return 0;
 }
+
+int clearvae_reparam_multi(int32_t heads, int32_t draws, const float* const* mu_host, const float* const* logvar_host,
+                           const float* const* eps_host, float* const* z_host, int64_t B, int32_t D, void* stream) {
+  if (heads < 1 || heads > 2 || draws < 1 || draws > CLEARVAE_REPARAM_MAX_DRAWS || !mu_host || !logvar_host || !eps_host || !z_host ||
+      B < 0 || D < 1)
+    return CLEARVAE_EINVAL;
+  if (B == 0) return 0;
+  ReparamTable tb{};
+  for (int h = 0; h < heads; ++h) {
+    if (!mu_host[h] || !logvar_host[h]) return CLEARVAE_EINVAL;
+    tb.mu[h] = mu_host[h];
+    tb.lv[h] = logvar_host[h];
+  }
+  for (int j = 0; j < draws; ++j) {
+    if (!z_host[j]) return CLEARVAE_EINVAL;
+    tb.z[j] = z_host[j];
+    for (int h = 0; h < heads; ++h) {
+      if (!eps_host[j * heads + h]) return CLEARVAE_EINVAL;
+      tb.eps[j * heads + h] = eps_host[j * heads + h];
+    }
+  }
+  tb.heads = heads;
+  tb.draws = draws;
+  const long long n = B * D;
+  const int grid = (int)std::min<long long>(148 * 4, (n + kNT - 1) / kNT);
+  reparam_multi_kernel<<<grid, kNT, 0, (cudaStream_t)stream>>>(tb, B, D);
+  CV_LAUNCH_CHECK();
+  return 0;
 }
+
+}  // extern "C"

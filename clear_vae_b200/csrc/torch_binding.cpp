@@ -631,6 +631,31 @@ void adam_step(at::TensorList params, at::TensorList grads, at::TensorList exp_a
 
 int64_t bn_act_workspace_bytes() { return (int64_t)clearvae_bn_act_workspace_bytes(); }
 
+std::vector<Tensor> reparam_multi(at::TensorList mu, at::TensorList logvar, at::TensorList eps) {
+  const size_t heads = mu.size();
+  TORCH_CHECK(heads >= 1 && heads <= 2 && logvar.size() == heads && !eps.empty() && eps.size() % heads == 0,
+              "clearvae: reparam_multi takes 1-2 heads and draws x heads noise tensors");
+  const size_t draws = eps.size() / heads;
+  TORCH_CHECK(draws <= CLEARVAE_REPARAM_MAX_DRAWS, "clearvae: too many draws");
+  const c10::cuda::CUDAGuard guard(mu[0].device());
+  const int64_t B = mu[0].size(0), D = mu[0].size(1);
+  std::vector<const float*> pm(heads), pl(heads), pe(eps.size());
+  for (size_t h = 0; h < heads; ++h) {
+    pm[h] = fptr(mu[h], "mu", B, D);
+    pl[h] = fptr(logvar[h], "logvar", B, D);
+  }
+  for (size_t i = 0; i < eps.size(); ++i) pe[i] = fptr(eps[i], "eps", B, D);
+  std::vector<Tensor> z(draws);
+  std::vector<float*> pz(draws);
+  for (size_t j = 0; j < draws; ++j) {
+    z[j] = at::empty({B, (int64_t)heads * D}, mu[0].options());
+    pz[j] = z[j].data_ptr<float>();
+  }
+  check_rc(clearvae_reparam_multi((int32_t)heads, (int32_t)draws, pm.data(), pl.data(), pe.data(), pz.data(), B, (int32_t)D, cur_stream()),
+           "reparam_multi");
+  return z;
+}
+
 // ---- one-shot collectives over peer memory (bases = every rank's buffer as mapped into this process)
 std::vector<void*> peer_bases(at::IntArrayRef bases) {
   TORCH_CHECK(!bases.empty() && bases.size() <= CLEARVAE_PEER_MAX_RANKS, "clearvae: 1..8 peer buffers");
@@ -724,6 +749,7 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("adam_step(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, Tensor(d!) steps, "
         "Tensor(e!) counter, float lr, float beta1, float beta2, float eps, float grad_scale) -> ()");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
+  m.def("reparam_multi(Tensor[] mu, Tensor[] logvar, Tensor[] eps) -> Tensor[]");
   m.def("peer_gather(int[] bases, int rank, int buffer_bytes, Tensor[] src, Tensor(a!)[] dst) -> ()");
   m.def("peer_allreduce(int[] bases, int rank, int buffer_bytes, Tensor(a!)[] tensors) -> ()");
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "
@@ -759,6 +785,7 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("scale_by", &scale_by);
   m.impl("mi_bound_bwd", &mi_bound_bwd);
   m.impl("adam_step", &adam_step);
+  m.impl("reparam_multi", &reparam_multi);
   m.impl("peer_gather", &peer_gather);
   m.impl("peer_allreduce", &peer_allreduce);
 }

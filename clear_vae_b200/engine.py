@@ -290,12 +290,12 @@ class DecoderFn(torch.autograd.Function):
         # BatchNorm1d + ReLU, written channels-last so the first transposed conv copies 16-byte channel runs
         if eng.training and eng.materialize and eng.act_dtype == torch.bfloat16 and C0 % 8 == 0:
             nw = _reduce_stats(eng, st)
-            a_fc, sc, sh, mean_fc, inv_fc, _ = ops.bn_finalize_apply(st, N0, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM,
+            a_fc, sc, sh, mean_fc, inv_fc, _ = ops.bn_finalize_apply(st, N0, float(nw * B), fc_g, fc_beta, rm, rv, eng.momentum,
                                                                       BN_EPS, 1, 1, raw_fc, 2, H0 * H0)
         else:
             if eng.training:
                 nw = _reduce_stats(eng, st)
-                sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(nw * B), fc_g, fc_beta, rm, rv, BN_MOMENTUM, BN_EPS, 1, 1)
+                sc, sh, mean_fc, inv_fc = ops.bn_finalize(st, N0, 1, float(nw * B), fc_g, fc_beta, rm, rv, eng.momentum, BN_EPS, 1, 1)
             else:
                 sc, sh, mean_fc, inv_fc = eng.eval_affine(fc_g, fc_beta, rm, rv, 1)
             a_fc, _ = ops.bn_act_fwd(raw_fc, sc, sh, N0, 1, 1, C0, H0 * H0, _DT[eng.act_dtype], None, B, _ws(dev))
@@ -330,10 +330,10 @@ class DecoderFn(torch.autograd.Function):
                 nw = _reduce_stats(eng, st)
                 if mat:
                     act, scale, shift, mean, invstd, _ = ops.bn_finalize_apply(st, sp.cout, float(nw * B * H * H), gamma, beta, rm,
-                                                                               rv, BN_MOMENTUM, BN_EPS, 1, 1, raw, 0, 1)
+                                                                               rv, eng.momentum, BN_EPS, 1, 1, raw, 0, 1)
                 else:
                     scale, shift, mean, invstd = ops.bn_finalize(st, sp.cout, 1, float(nw * B * H * H), gamma, beta, rm, rv,
-                                                                 BN_MOMENTUM, BN_EPS, 1, 1)
+                                                                 eng.momentum, BN_EPS, 1, 1)
             else:
                 scale, shift, mean, invstd = eng.eval_affine(gamma, beta, rm, rv, 1)
                 if mat:
@@ -474,6 +474,10 @@ class Engine:
         self.materialize = True  # write relu(bn(raw)) once in bf16 so the GEMM operand loads are pure cp.async copies
         self.overlap_wgrad = True  # weight gradients on a side stream, overlapping the data-gradient chain
         self._side = {}
+        self.momentum = BN_MOMENTUM   # running-statistic momentum of the decoder forwards (1.0 inside parallel stat branches)
+        self.stat_tag = 0             # statistic-accumulator set: concurrent decoder passes must not share accumulators
+        self.parallel_stats = True    # CLEAR-MIM's statistics-only decoder passes as parallel graph branches
+        self._branch = {}
 
     # ---- weight-gradient branch -----------------------------------------------------------------------------
     # dW of a block needs only that block's dy and input activation, while the data-gradient chain continues to the
@@ -506,8 +510,33 @@ class Engine:
         if self.overlap_wgrad and side is not None:
             torch.cuda.current_stream(dev).wait_stream(side)
 
+    def branch_streams(self, n, dev):
+        st = self._branch.setdefault(("streams", dev), [])
+        while len(st) < n:
+            st.append(torch.cuda.Stream(device=dev))
+        return st[:n]
+
+    def branch_running(self, n, dev):
+        """[n, sum of 2C over the decoder's BatchNorm layers] zero-initialised scratch: row j receives pass j's batch mean /
+        unbiased variance of every layer (momentum 1), in the order (fc, convT 0, convT 1, ...) x (mean, var)."""
+        sizes = [self.dec_specs[0].cin * self.dec_specs[0].hin ** 2] + [sp.cout for sp in self.dec_specs]
+        key = ("running", n, dev)
+        t = self._branch.get(key)
+        if t is None:
+            t = self._branch[key] = torch.zeros(n, 2 * sum(sizes), dtype=torch.float32, device=dev)
+        return t, sizes
+
+    def prepack_decoder(self, fc_w, params):
+        """pack every decoder weight the forward GEMMs will ask for on the CURRENT stream (before branches fork)."""
+        specs = self.dec_specs
+        for j, sp in enumerate(specs):
+            last = j == len(specs) - 1
+            if last and self.use_direct and j > 0:
+                continue   # direct CUDA-core kernel reads the fp32 master
+            self.packs.get(("dec", j), params[4 * j], sp.geom, FPROP)
+
     def stat_buf(self, key, C, dev):
-        k = (key, C, dev)
+        k = (key, C, dev, self.stat_tag)
         t = self._stat.get(k)
         if t is None:
             t = _stats(C, dev)

@@ -135,6 +135,56 @@ class VAE(nn.Module):
         self._tick([bn] + [self.decoder[s.bn] for s in eng.dec_specs])
         return xhat, recon
 
+    def decode_stats_many(self, zs):
+        """Statistics-only train-mode decoder passes over several latent batches (CLEAR-MIM's inner forwards,
+        trainer.py:874-888, whose outputs are discarded): only the BatchNorm running statistics change.
+
+        The passes are independent except for those running statistics, so they run as parallel branches (side streams in
+        eager mode, fork/join nodes in a captured graph): every branch owns its statistic accumulators and writes its
+        batch mean / unbiased variance into its own scratch row (momentum 1); after the join the n momentum updates are
+        applied in order in closed form:  r <- (1-m)^n r + sum_j m (1-m)^(n-1-j) s_j."""
+        eng = self._eng()
+        n = len(zs)
+        dp_sync = eng.sync_bn and eng.dist is not None and eng.dist.world > 1   # SyncBN collectives stay on one stream
+        if not (eng.parallel_stats and self.training and n > 1 and zs[0].is_cuda) or dp_sync:
+            for z in zs:
+                self._decode(z, None, stats_only=True)
+            return
+        dev = zs[0].device
+        fc, bn = self.decoder[0], self.decoder[1]
+        params = self._dec_params()
+        eng.prepack_decoder(fc.weight, params)
+        scratch, sizes = eng.branch_running(n, dev)
+        main = torch.cuda.current_stream(dev)
+        side = eng.branch_streams(n - 1, dev)
+        real_fc, real_dec = eng.dec_fc_buffers, eng.dec_buffers
+        eng.stats_only, eng.momentum = True, 1.0
+        try:
+            for j in range(n):
+                st = main if j == 0 else side[j - 1]
+                if j:
+                    st.wait_stream(main)
+                rows = list(scratch[j].split([c for c in sizes for _ in (0, 1)]))
+                eng.dec_fc_buffers = (rows[0], rows[1])
+                eng.dec_buffers = [(rows[2 + 2 * i], rows[3 + 2 * i]) for i in range(len(eng.dec_specs))]
+                eng.stat_tag = j
+                with torch.cuda.stream(st):
+                    DecoderFn.apply(eng, zs[j], None, fc.weight, fc.bias, bn.weight, bn.bias, *params)
+        finally:
+            eng.stats_only, eng.momentum, eng.stat_tag = False, 0.1, 0
+            eng.dec_fc_buffers, eng.dec_buffers = real_fc, real_dec
+        for st in side:
+            main.wait_stream(st)
+        m = 0.1
+        coef = getattr(self, "_stat_coef", None)
+        if coef is None or coef.numel() != n or coef.device != dev:
+            coef = self._stat_coef = torch.tensor([m * (1 - m) ** (n - 1 - j) for j in range(n)], dtype=torch.float32, device=dev)
+        comb = torch.mv(scratch.t(), coef)                       # [sum 2C]
+        real = [real_fc[0], real_fc[1]] + [b for pair in real_dec for b in pair]
+        torch._foreach_mul_(real, (1 - m) ** n)
+        torch._foreach_add_(real, list(comb.split([c for c in sizes for _ in (0, 1)])))
+        self._tick([bn] + [self.decoder[s.bn] for s in eng.dec_specs], n)
+
     def sample(self, mu, logvar):
         """Reparameterisation (vae.py:56-60); the noise is drawn exactly like the reference
         (`randn_like` on a tensor of logvar's shape), the arithmetic runs in the latent kernel."""

@@ -356,14 +356,16 @@ class ClearMIMVAETrainer(VAETrainer):
         # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and
         # runs the decoder for its running-statistic side effects, as the reference's full forwards do.
         learn = []
-        dummy = torch.zeros(X.shape[0], dtype=torch.int64, device=X.device)
         with torch.no_grad():
             mu_c, lv_c, mu_s, lv_s = vae.encode(X, bn_repeat=5)
-            zs = []
-            for j in range(5):   # noise in the reference's order (c then s, iteration by iteration), then the reparameterisation
-                e = (torch.randn_like(lv_c), torch.randn_like(lv_s)) if inner_eps is None else inner_eps[j]
-                z2, _ = latent_block([mu_c, mu_s], [lv_c, lv_s], list(e), dummy, snn=[0, 0], ps=[0, 0])
-                zs.append(z2)
+            # noise in the reference's order (c then s, iteration by iteration); the five reparameterisations are one launch
+            e = [t for j in range(5) for t in ((torch.randn_like(lv_c), torch.randn_like(lv_s)) if inner_eps is None else inner_eps[j])]
+            if X.is_cuda:
+                from . import _ops
+                zs = list(_ops.ops().reparam_multi([mu_c, mu_s], [lv_c, lv_s], [t.contiguous() for t in e]))
+            else:   # CPU tensors: the latent op raises (no CPU path), exactly as before
+                dummy = torch.zeros(X.shape[0], dtype=torch.int64, device=X.device)
+                zs = [latent_block([mu_c, mu_s], [lv_c, lv_s], e[2 * j:2 * j + 2], dummy, snn=[0, 0], ps=[0, 0])[0] for j in range(5)]
         z_est = zs
         d = self.dist
         if d is not None and d.world > 1:
@@ -392,8 +394,7 @@ class ClearMIMVAETrainer(VAETrainer):
                 learn.append(ll)
             learn_t = torch.stack(learn)
         with torch.no_grad():
-            for j in range(5):
-                vae._decode(zs[j], None, stats_only=True)
+            vae.decode_stats_many(zs)
         main.wait_stream(side)
         return recon, sc, mi.detach(), learn_t
 

@@ -308,6 +308,15 @@ int clearvae_adam_step(int32_t n_tensors, float* const* params_host, const float
                        unsigned int* counter, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Several reparameterisation draws of one (mu, logvar) pair per head in one launch (vae.py:56-60 as called five times
+ * by CLEAR-MIM's inner loop, trainer.py:874-888): z_host[j] = [B, heads*D] with
+ * z[j][b, h*D + d] = mu[h][b,d] + eps[j*heads + h][b,d] * exp(logvar[h][b,d] / 2).  The *_host arrays hold device pointers.
+ * ------------------------------------------------------------------------- */
+#define CLEARVAE_REPARAM_MAX_DRAWS 8
+int clearvae_reparam_multi(int32_t heads, int32_t draws, const float* const* mu_host, const float* const* logvar_host,
+                           const float* const* eps_host, float* const* z_host, int64_t B, int32_t D, void* stream);
+
+/* ---------------------------------------------------------------------------
  * One-shot collectives over NVLink peer memory (data-parallel step).  They replace the small NCCL
  * exchanges a data-parallel port of the reference loop would issue per step (trainer.py:446-492 under DDP semantics):
  * the all-gather of the similarity operands / labels / row statistics / estimator latents and the parameter-gradient

@@ -162,3 +162,50 @@ def test_trainer_step_matches_reference_logs(tag):
         agree += int((np.sign(mine[big]) == np.sign(refd[big])).sum())
         total += int(big.sum())
     assert total > 100 and agree / total > 0.97, (agree, total)
+
+
+@pytest.mark.parametrize("arch", ["VAE", "VAE64"])
+def test_parallel_statistics_only_decoder_passes_equal_sequential_passes(arch):
+    """CLEAR-MIM's five discarded inner forwards (trainer.py:874-888) only move the decoder's BatchNorm running
+    statistics; running them as parallel branches + the closed-form momentum fold must give what five sequential
+    train-mode passes give (same kernels, same batch statistics; only the fp32 order of the momentum update differs)."""
+    from clear_vae_b200.models.vae import VAE, VAE64
+    torch.manual_seed(5)
+    cls, zdim = (VAE, 16) if arch == "VAE" else (VAE64, 64)
+    a = cls(zdim, 3).to(DEV)
+    b = cls(zdim, 3).to(DEV)
+    b.load_state_dict(a.state_dict())
+    a.train(), b.train()
+    g = torch.Generator().manual_seed(3)
+    zs = [torch.randn(256, zdim, generator=g).to(DEV) * (1 + j) for j in range(5)]
+    with torch.no_grad():
+        a._eng().parallel_stats = False
+        a.decode_stats_many(zs)
+        b.decode_stats_many(zs)
+        b.decode_stats_many(zs[:3])     # a different branch count reuses nothing stale
+        a.decode_stats_many(zs[:3])
+    torch.cuda.synchronize()
+    sa, sb = a.state_dict(), b.state_dict()
+    moved = 0
+    for k in sa:
+        if "running" in k:
+            assert torch.allclose(sa[k], sb[k], rtol=2e-6, atol=1e-7), (k, float((sa[k] - sb[k]).abs().max()))
+            moved += int(k.startswith("decoder") and not torch.equal(sa[k], torch.zeros_like(sa[k])) and not torch.equal(sa[k], torch.ones_like(sa[k])))
+        if "num_batches_tracked" in k:
+            assert int(sa[k]) == int(sb[k]) == (8 if k.startswith("decoder") else 0), k
+    assert moved >= 8
+
+
+def test_reparam_multi_matches_the_latent_kernel_bitwise():
+    from clear_vae_b200 import _ops
+    from clear_vae_b200.latent import latent_block
+    g = torch.Generator().manual_seed(11)
+    B, D = 1000, 8
+    mu = [torch.randn(B, D, generator=g).to(DEV) for _ in range(2)]
+    lv = [(torch.randn(B, D, generator=g) * 0.5).to(DEV) for _ in range(2)]
+    eps = [torch.randn(B, D, generator=g).to(DEV) for _ in range(10)]
+    zs = _ops.ops().reparam_multi(mu, lv, eps)
+    dummy = torch.zeros(B, dtype=torch.int64, device=DEV)
+    for j in range(5):
+        want, _ = latent_block(mu, lv, eps[2 * j:2 * j + 2], dummy, snn=[0, 0], ps=[0, 0])
+        assert torch.equal(zs[j], want)
