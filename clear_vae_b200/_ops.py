@@ -19,7 +19,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _EXT = os.path.join(_PKG, "_C.so")
 _LIB = os.path.join(_PKG, "_lib", "libclearvae_b200.so")
 _loaded = False
-_HOST_ONLY = {"latent_workspace_bytes", "recon_workspace_bytes", "bn_act_workspace_bytes", "mi_workspace_bytes", "tc_workspace_bytes"}
+_HOST_ONLY = {"latent_workspace_bytes", "latent_bwd_workspace_bytes", "recon_workspace_bytes", "bn_act_workspace_bytes", "mi_workspace_bytes", "tc_workspace_bytes"}
 
 
 class NativeExtensionMissing(RuntimeError):

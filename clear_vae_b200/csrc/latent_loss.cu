@@ -44,6 +44,11 @@ struct FwdParams {
   float* scalars;
   unsigned* ticket;
   float* kl_partial;  // [2][max_ctas]
+  // column split (small local batches, FFMA kernels): blockIdx.z sweeps columns [z*cps, (z+1)*cps); per-row partial
+  // (max_all, sum_all, max_pos, sum_pos) go to part[term][z][B][4] and the last CTA of the grid merges them in z order
+  int splits;
+  long long cps;
+  float* part;
 };
 struct TermB {
   const float *mu, *lv, *eps, *mu_cols, *stats_all, *dz;
@@ -58,6 +63,12 @@ struct BwdParams {
   int D, z_stride;
   float inv_tau;
   const float *scalars, *gscal;
+  // column split: partial (dn[DP], csum) per row -> part[term][z][B][DP+1]; the last of the `splits` CTAs of a row block
+  // (ticket per (term, blockIdx.x), self-resetting) merges them in z order and runs the row epilogue
+  int splits;
+  long long cps;
+  float* part;
+  unsigned* tickets;
 };
 
 enum { SIM_COS = CLEARVAE_SIM_COSINE, SIM_L2 = CLEARVAE_SIM_L2, SIM_ML2 = CLEARVAE_SIM_MODIFIED_L2, SIM_JEF = CLEARVAE_SIM_JEFFREY,
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
   const int D = p.D;
 
   // ---- reparameterisation + KL for the rows of this warp (lanes over d)
-  if (t.lv != nullptr) {
+  if (t.lv != nullptr && blockIdx.z == 0) {
     float kl = 0.f;
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
@@ -263,13 +274,15 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
     const float* cols = t.mu_cols ? t.mu_cols : t.mu;
     const float* lvc = t.lv_cols ? t.lv_cols : t.lv;
     float* sX = sRed + kWarps + 1;   // [NLV][DP][kTN]
-    for (long long j0 = 0; j0 < p.Bg; j0 += kTN) {
+    const long long jbeg = p.splits > 1 ? (long long)blockIdx.z * p.cps : 0;
+    const long long jend = p.splits > 1 ? min(p.Bg, jbeg + p.cps) : p.Bg;
+    for (long long j0 = jbeg; j0 < jend; j0 += kTN) {
       __syncthreads();
       stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL, lvc, sX);
       __syncthreads();
       for (int jj = lane; jj < kTN; jj += 32) {
         const long long j = j0 + jj;
-        if (j >= p.Bg) break;
+        if (j >= jend) break;
         float x[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) x[d] = sN[d * kTN + jj];
@@ -305,6 +318,22 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
       float oa, op;
+      if (p.splits > 1) {   // partial over this CTA's column range; merged by the last CTA below
+        if (FAST) {
+          sa[r] = cv::warp_sum(sa[r]);
+          sp[r] = cv::warp_sum(sp[r]);
+        } else {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            cv::lse_merge(ma[r], sa[r], __shfl_xor_sync(0xffffffffu, ma[r], o), __shfl_xor_sync(0xffffffffu, sa[r], o));
+            cv::lse_merge(mp[r], sp[r], __shfl_xor_sync(0xffffffffu, mp[r], o), __shfl_xor_sync(0xffffffffu, sp[r], o));
+          }
+        }
+        const long long i = row0 + r;
+        if (lane == 0 && i < p.B)
+          reinterpret_cast<float4*>(p.part)[((long long)term * p.splits + blockIdx.z) * p.B + i] = make_float4(ma[r], sa[r], mp[r], sp[r]);
+        continue;
+      }
       if (FAST) {
         oa = logf(cv::warp_sum(sa[r]));
         op = logf(cv::warp_sum(sp[r]));
@@ -330,11 +359,28 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned tk = atomicAdd(p.ticket, 1u);
-    sRed[kWarps] = (tk == gridDim.x * gridDim.y - 1) ? 1.f : 0.f;
+    sRed[kWarps] = (tk == gridDim.x * gridDim.y * gridDim.z - 1) ? 1.f : 0.f;
   }
   __syncthreads();
   if (sRed[kWarps] != 0.f) {
     __threadfence();
+    if (p.splits > 1) {   // merge the column-split partials in z order -> row statistics
+      for (int tt = 0; tt < (int)gridDim.y; ++tt) {
+        if (!p.t[tt].snn) continue;
+        for (long long i = threadIdx.x; i < p.B; i += kTN) {
+          float ma = -INFINITY, sa = 0.f, mp = -INFINITY, sp = 0.f;
+          for (int z = 0; z < p.splits; ++z) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part) + ((long long)tt * p.splits + z) * p.B + i);
+            if (FAST) { sa += v.y; sp += v.w; }
+            else { cv::lse_merge(ma, sa, v.x, v.y); cv::lse_merge(mp, sp, v.z, v.w); }
+          }
+          p.t[tt].stats[2 * i] = FAST ? logf(sa) : ma + logf(sa);
+          p.t[tt].stats[2 * i + 1] = FAST ? logf(sp) : mp + logf(sp);
+        }
+      }
+      __threadfence();
+      __syncthreads();
+    }
     for (int tt = 0; tt < (int)gridDim.y; ++tt) {
       if (p.t[tt].lv != nullptr) {
         float s = 0.f;
@@ -746,6 +792,7 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
   const int D = p.D;
   const float g_kl = p.gscal[term], g_loss = p.gscal[2 + term];
   constexpr int NLV = SimLv<SIM>::N;
+  if (!t.snn && blockIdx.z > 0) return;   // KL / reparam-only term: one CTA per row block does the epilogue
 
   float dn[RM][DP], row[RM][DP], inv_norm[RM], csum[RM];
   float dl[RM][NLV > 0 ? DP : 1], rlv[RM][NLV > 0 ? DP : 1][3];
@@ -786,7 +833,9 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
     const float k2 = p.inv_tau * CV_LOG2E;
     const float* cols = t.mu_cols ? t.mu_cols : t.mu;
     const float* lvc = t.lv_cols ? t.lv_cols : t.lv;
-    for (long long j0 = 0; j0 < p.Bg; j0 += kTN) {
+    const long long jbeg = p.splits > 1 ? (long long)blockIdx.z * p.cps : 0;
+    const long long jend = p.splits > 1 ? min(p.Bg, jbeg + p.cps) : p.Bg;
+    for (long long j0 = jbeg; j0 < jend; j0 += kTN) {
       __syncthreads();
       stage_column<DP, SIM>(cols, p.lab_c, j0 + threadIdx.x, p.Bg, D, sN, sL, lvc, sX);
       {
@@ -800,7 +849,7 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
       __syncthreads();
       for (int jj = lane; jj < kTN; jj += 32) {
         const long long j = j0 + jj;
-        if (j >= p.Bg) break;
+        if (j >= jend) break;
         float x[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) x[d] = sN[d * kTN + jj];
@@ -849,18 +898,66 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
   }
 
   // ---- epilogue: reduce over lanes, chain through the similarity operand, add KL / reparam grads
+  if (t.snn) {
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      csum[r] = cv::warp_sum(csum[r]);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        dn[r][d] = cv::warp_sum(dn[r][d]);
+        if constexpr (NLV > 0) dl[r][d] = cv::warp_sum(dl[r][d]);
+      }
+    }
+  }
+  if constexpr (NLV == 0) {
+    if (p.splits > 1 && t.snn) {
+      // column split: publish this CTA's partial sums; the last CTA of the row block merges them in z order
+      constexpr int PS = DP + 1;
+      float* part = p.part + ((long long)term * p.splits * p.B) * PS;
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        const long long i = row0 + r;
+        if (i >= p.B) continue;
+        float* dst = part + ((long long)blockIdx.z * p.B + i) * PS;
+#pragma unroll
+        for (int d = 0; d < DP; ++d)
+          if ((d & 31) == lane) dst[d] = dn[r][d];
+        if (lane == 0) dst[DP] = csum[r];
+      }
+      __shared__ int s_last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned* tk = p.tickets + (long long)term * gridDim.x + blockIdx.x;
+        s_last = (atomicAdd(tk, 1u) == (unsigned)p.splits - 1) ? 1 : 0;
+        if (s_last) *tk = 0u;
+      }
+      __syncthreads();
+      if (!s_last) return;
+      __threadfence();
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        const long long i = row0 + r;
+        csum[r] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) dn[r][d] = 0.f;
+        if (i >= p.B) continue;
+        for (int z = 0; z < p.splits; ++z) {
+          const float* src = part + ((long long)z * p.B + i) * PS;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) dn[r][d] += __ldcg(src + d);
+          csum[r] += __ldcg(src + DP);
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int r = 0; r < RM; ++r) {
     const long long i = row0 + r;
     float dot = 0.f;
     if (t.snn) {
-      csum[r] = cv::warp_sum(csum[r]);
 #pragma unroll
-      for (int d = 0; d < DP; ++d) {
-        dn[r][d] = cv::warp_sum(dn[r][d]);
-        dot = fmaf(dn[r][d], row[r][d], dot);
-        if constexpr (NLV > 0) dl[r][d] = cv::warp_sum(dl[r][d]);
-      }
+      for (int d = 0; d < DP; ++d) dot = fmaf(dn[r][d], row[r][d], dot);
     }
     if (i >= p.B) continue;
 #pragma unroll
@@ -1209,7 +1306,7 @@ int launch_fwd(const FwdParams& p, int n_terms, cudaStream_t st) {
   auto kern = snn_fwd_kernel<DP, RM, SIM, FAST>;
   constexpr size_t smem = fwd_smem<DP, SIM>();
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms);
+  dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms, (unsigned)max(1, p.splits));
   kern<<<grid, kTN, smem, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
@@ -1219,7 +1316,7 @@ int launch_bwd(const BwdParams& p, int n_terms, cudaStream_t st) {
   auto kern = snn_bwd_kernel<DP, RM, SIM, FAST>;
   constexpr size_t smem = bwd_smem<DP, SIM>();
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms);
+  dim3 grid((unsigned)((p.B + kWarps * RM - 1) / (kWarps * RM)), (unsigned)n_terms, (unsigned)max(1, p.splits));
   kern<<<grid, kTN, smem, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
@@ -1304,6 +1401,27 @@ struct WsLayout {
 
 inline int max_ctas_for(long long B) { return (int)((B + kWarps - 1) / kWarps); }
 
+// Column split of the FFMA kernels.  A CTA owns 8 rows and sweeps every column, staging each 256-column tile behind two
+// barriers: with few rows (a data-parallel shard against the gathered global batch: 1024 x 8192) the grid is one CTA per
+// SM and the sweep is a chain of exposed load latencies.  Splitting the columns over blockIdx.z puts 4+ CTAs on every SM.
+constexpr int kMaxSplits = 8;
+constexpr long long kSplitMaxRows = 4096;   // beyond this the row blocks alone fill the GPU (and the TC path takes over)
+inline int pick_splits(long long B, long long Bg, int n_terms, int sim) {
+  if (sim >= SIM_ML2 || B > kSplitMaxRows) return 1;
+  const long long ctas = (long long)max_ctas_for(B) * n_terms;
+  const long long tiles = (Bg + kTN - 1) / kTN;
+  long long s = (148 * 4 + ctas - 1) / ctas;
+  s = std::min<long long>(s, std::min<long long>(kMaxSplits, tiles));
+  return (int)std::max<long long>(1, s);
+}
+inline long long cols_per_split(long long Bg, int splits) {
+  const long long tiles = (Bg + kTN - 1) / kTN;
+  return ((tiles + splits - 1) / splits) * kTN;
+}
+inline size_t fwd_part_bytes(long long B, int n_terms) {
+  return B <= kSplitMaxRows ? (size_t)n_terms * kMaxSplits * (size_t)B * 4 * sizeof(float) : 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1316,7 +1434,15 @@ void clearvae_set_latent_tc_min_rows(int32_t rows) { g_tc_min_rows = rows; }
 size_t clearvae_latent_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms) {
   (void)Bg; (void)D; (void)n_terms;
   if (B < 0) return 0;
-  return sizeof(WsLayout) + (size_t)2 * max_ctas_for(B) * sizeof(float);
+  const size_t base = sizeof(WsLayout) + (size_t)2 * max_ctas_for(B) * sizeof(float);
+  return ((base + 15) & ~(size_t)15) + fwd_part_bytes(B, n_terms);
+}
+
+size_t clearvae_latent_bwd_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms) {
+  (void)Bg;
+  if (B < 0 || B > kSplitMaxRows || pad_d(D) < 0) return 256;
+  return 256 + (size_t)n_terms * max_ctas_for(B) * sizeof(unsigned) + 16 +
+         (size_t)n_terms * kMaxSplits * (size_t)B * (pad_d(D) + 1) * sizeof(float);
 }
 
 int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const int64_t* label_rows,
@@ -1347,7 +1473,12 @@ int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const i
   p.scalars = scalars;
   p.ticket = &reinterpret_cast<WsLayout*>(workspace)->ticket;
   p.kl_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sizeof(WsLayout));
-  (void)any_snn;
+  {
+    const size_t base = (sizeof(WsLayout) + (size_t)2 * max_ctas_for(B) * sizeof(float) + 15) & ~(size_t)15;
+    p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + base);
+    p.splits = any_snn ? pick_splits(B, Bg, n_terms, sim_fn) : 1;
+    p.cps = cols_per_split(Bg, p.splits);
+  }
   return dispatch_fwd(p, n_terms, sim_fn, fast_ok(sim_fn, temperature), (cudaStream_t)stream);
 }
 
@@ -1362,6 +1493,14 @@ int clearvae_latent_bwd(const clearvae_term_bwd* terms, int32_t n_terms, const i
                         const int64_t* label_cols, int64_t B, int64_t Bg, int64_t row_offset, int32_t D,
                         int32_t z_stride, int32_t sim_fn, int32_t loss_name, float temperature,
                         const float* scalars, const float* gscal, void* stream) {
+  return clearvae_latent_bwd_ws(terms, n_terms, label_rows, label_cols, B, Bg, row_offset, D, z_stride, sim_fn, loss_name,
+                                temperature, scalars, gscal, nullptr, 0, stream);
+}
+
+int clearvae_latent_bwd_ws(const clearvae_term_bwd* terms, int32_t n_terms, const int64_t* label_rows,
+                           const int64_t* label_cols, int64_t B, int64_t Bg, int64_t row_offset, int32_t D,
+                           int32_t z_stride, int32_t sim_fn, int32_t loss_name, float temperature,
+                           const float* scalars, const float* gscal, void* workspace, size_t workspace_bytes, void* stream) {
   if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !gscal || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
   if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
   if (sim_fn < SIM_COS || sim_fn > SIM_MAH) return CLEARVAE_EUNSUPPORTED;
@@ -1380,6 +1519,17 @@ int clearvae_latent_bwd(const clearvae_term_bwd* terms, int32_t n_terms, const i
   p.B = B; p.Bg = Bg; p.row_off = row_offset; p.D = D; p.z_stride = z_stride;
   p.inv_tau = 1.f / temperature;
   p.scalars = scalars; p.gscal = gscal;
+  p.splits = 1;
+  p.cps = cols_per_split(Bg, 1);
+  bool any_snn = false;
+  for (int i = 0; i < n_terms; ++i) any_snn |= terms[i].snn_enable != 0;
+  if (workspace && any_snn && workspace_bytes >= clearvae_latent_bwd_workspace_bytes(B, Bg, D, n_terms)) {
+    p.splits = pick_splits(B, Bg, n_terms, sim_fn);
+    p.cps = cols_per_split(Bg, p.splits);
+    p.tickets = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + 256);
+    const size_t off = (256 + (size_t)n_terms * max_ctas_for(B) * sizeof(unsigned) + 15) & ~(size_t)15;
+    p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off);
+  }
   return dispatch_bwd(p, n_terms, sim_fn, fast_ok(sim_fn, temperature), (cudaStream_t)stream);
 }
 

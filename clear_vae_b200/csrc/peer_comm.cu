@@ -89,26 +89,36 @@ __device__ __forceinline__ unsigned begin_call(PeerState* st, unsigned* s_seq) {
   return *s_seq;
 }
 
-// publish phase-1 data to the peers, then wait until every peer has published the same call
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// publish phase-1 data to the peers, then wait until every peer has published the same call.
+// Ordering chain: staging stores -> bar.sync -> thread 0: fence.gpu + arrive (gpu-scope atomic) -> last CTA observes the
+// full count -> st.release.sys of the call number into every peer's flag word -> peer: relaxed polls + fence.acq_rel.sys
+// -> bar.sync -> volatile pulls.  One gpu-scope fence per CTA and one system-scope release per peer, nothing per thread.
 __device__ __forceinline__ void publish_and_wait(const PeerTable& pt, PeerState* st, unsigned seq, int* s_last) {
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) *s_last = (atomicAdd(&st->arrive1, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (*s_last && (int)threadIdx.x < pt.world) {
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned*>(pt.base[threadIdx.x]) + pt.rank, seq);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *s_last = (atomicAdd(&st->arrive1, 1u) == gridDim.x - 1) ? 1 : 0;
   }
+  __syncthreads();
+  if (*s_last && (int)threadIdx.x < pt.world)
+    st_release_sys(reinterpret_cast<unsigned*>(pt.base[threadIdx.x]) + pt.rank, seq);
   if ((int)threadIdx.x < pt.world) {
     const unsigned* flag = reinterpret_cast<const unsigned*>(pt.base[pt.rank]) + threadIdx.x;
     const unsigned long long t0 = gtimer_ns();
     unsigned spins = 0;
-    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+    while ((int)(ld_relaxed_sys(flag) - seq) < 0) {
       if ((++spins & 1023u) == 0 && gtimer_ns() - t0 > kTimeoutNs) {
         atomicExch(&st->error, 1u + threadIdx.x);
         break;
       }
     }
+    __threadfence_system();
   }
   __syncthreads();
 }

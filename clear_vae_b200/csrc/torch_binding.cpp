@@ -106,7 +106,8 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>> latent_bwd(
     const c10::List<OptTensor>& mu_cols, const c10::List<OptTensor>& logvar_cols, const c10::List<OptTensor>& stats_all,
     const OptTensor& dz,
     const Tensor& label_rows, const OptTensor& label_cols, at::IntArrayRef snn, at::IntArrayRef ps,
-    int64_t row_offset, int64_t sim_fn, int64_t loss_name, double tau, const Tensor& scalars, const Tensor& gscal) {
+    int64_t row_offset, int64_t sim_fn, int64_t loss_name, double tau, const Tensor& scalars, const Tensor& gscal,
+    const OptTensor& workspace) {
   const int n = (int)mu.size();
   TORCH_CHECK(n >= 1 && n <= 2, "clearvae: 1 or 2 terms");
   check_f32(mu[0], "mu");
@@ -154,9 +155,16 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>> latent_bwd(
     terms[i].ps = (int32_t)ps[i];
     terms[i].logvar_cols = (int)logvar_cols.size() == n ? fptr(logvar_cols.get(i), "logvar_cols", Bg, D) : nullptr;
   }
-  check_rc(clearvae_latent_bwd(terms, n, label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)D,
-                               (int32_t)(n * D), (int32_t)sim_fn, (int32_t)loss_name, (float)tau,
-                               scalars.data_ptr<float>(), gscal.data_ptr<float>(), cur_stream()),
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  if (workspace.has_value() && workspace->defined()) {
+    TORCH_CHECK(workspace->is_cuda() && workspace->is_contiguous(), "clearvae: workspace must be a contiguous CUDA tensor");
+    ws = workspace->data_ptr();
+    ws_bytes = (size_t)workspace->numel() * workspace->element_size();
+  }
+  check_rc(clearvae_latent_bwd_ws(terms, n, label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)D,
+                                  (int32_t)(n * D), (int32_t)sim_fn, (int32_t)loss_name, (float)tau,
+                                  scalars.data_ptr<float>(), gscal.data_ptr<float>(), ws, ws_bytes, cur_stream()),
            "latent_bwd");
   return {dmu, dlv};
 }
@@ -177,6 +185,10 @@ Tensor pair_mask(const Tensor& label_rows, const OptTensor& label_cols, int64_t 
                               out.data_ptr<uint8_t>(), cur_stream()),
            "pair_mask");
   return out;
+}
+
+int64_t latent_bwd_workspace_bytes(int64_t B, int64_t Bg, int64_t D, int64_t n_terms) {
+  return (int64_t)clearvae_latent_bwd_workspace_bytes(B, Bg, (int32_t)D, (int32_t)n_terms);
 }
 
 int64_t latent_workspace_bytes(int64_t B, int64_t Bg, int64_t D, int64_t n_terms) {
@@ -711,7 +723,8 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("snn_finalize(Tensor stats_all, int term, Tensor(a!) scalars) -> ()");
   m.def("latent_bwd(Tensor[] mu, Tensor?[] logvar, Tensor?[] eps, Tensor?[] mu_cols, Tensor?[] logvar_cols, Tensor?[] stats_all, "
         "Tensor? dz, Tensor label_rows, Tensor? label_cols, int[] snn, int[] ps, int row_offset, int sim_fn, "
-        "int loss_name, float tau, Tensor scalars, Tensor gscal) -> (Tensor[], Tensor[])");
+        "int loss_name, float tau, Tensor scalars, Tensor gscal, Tensor(a!)? workspace=None) -> (Tensor[], Tensor[])");
+  m.def("latent_bwd_workspace_bytes(int B, int Bg, int D, int n_terms) -> int", &latent_bwd_workspace_bytes);
   m.def("pair_mask(Tensor label_rows, Tensor? label_cols, int row_offset, int ps) -> Tensor");
   m.def("latent_workspace_bytes(int B, int Bg, int D, int n_terms) -> int", &latent_workspace_bytes);
   m.def("recon_fwd(Tensor xhat, Tensor x, Tensor(a!) workspace) -> Tensor");

@@ -26,8 +26,8 @@ S_KL0, S_KL1, S_LOSS0, S_LOSS1, S_SUM0, S_SUM1, S_CNT0, S_CNT1 = range(8)
 _workspaces: dict = {}
 
 
-def _workspace(device, nbytes):
-    key = (device.type, device.index)
+def _workspace(device, nbytes, tag="fwd"):
+    key = (device.type, device.index, tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
@@ -134,8 +134,11 @@ class _LatentBlock(torch.autograd.Function):
             dz = dz.contiguous()
             if dz.numel() == 0:
                 dz = None
+        B, D = mu[0].shape
+        Bg = label_cols.numel() if label_cols is not None else B
+        ws = _workspace(mu[0].device, ops.latent_bwd_workspace_bytes(B, Bg, D, n), "bwd")   # column-split partials + tickets
         dmu, dlv = ops.latent_bwd(mu, logvar, eps, cols, lv_cols, stats_all, dz, label, label_cols, cfg["snn"], cfg["ps"],
-                                  ctx.row_off, cfg["sim"], cfg["loss"], cfg["tau"], scalars, dscal)
+                                  ctx.row_off, cfg["sim"], cfg["loss"], cfg["tau"], scalars, dscal, ws)
         g_mu = list(dmu)
         g_lv = [dlv[i] if logvar[i] is not None else None for i in range(n)]
         g_eps = [None] * n

@@ -114,6 +114,17 @@ int clearvae_latent_bwd(const clearvae_term_bwd* terms_host, int32_t n_terms,
                         int32_t sim_fn, int32_t loss_name, float temperature,
                         const float* scalars, const float* gscal, void* stream);
 
+/* Same backward with a workspace (zero-initialised once, left zeroed): lets the FFMA kernels split the column sweep over
+ * several CTAs per row block when the local batch is small (a data-parallel shard against the gathered global batch);
+ * partial sums are merged in a fixed order, so results stay bit-reproducible.  workspace == NULL: identical to
+ * clearvae_latent_bwd. */
+size_t clearvae_latent_bwd_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms);
+int clearvae_latent_bwd_ws(const clearvae_term_bwd* terms_host, int32_t n_terms,
+                           const int64_t* label_rows, const int64_t* label_cols,
+                           int64_t B, int64_t Bg, int64_t row_offset, int32_t D, int32_t z_stride,
+                           int32_t sim_fn, int32_t loss_name, float temperature,
+                           const float* scalars, const float* gscal, void* workspace, size_t workspace_bytes, void* stream);
+
 /* debug/test: positive/candidate sets of losses.py:107-110,131-135 as bytes
  * (bit0 = candidate j!=i, bit1 = positive), [B, Bg] — same index math as the kernels. */
 int clearvae_pair_mask(const int64_t* label_rows, const int64_t* label_cols, int64_t B, int64_t Bg,

@@ -51,38 +51,45 @@ if peer is not None:
     for o, og in zip(out + gs, out_g + gs_g):
         ok &= torch.equal(o, og)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    td.barrier(); torch.cuda.synchronize()
-    e0.record()
-    for _ in range(200):
-        graph.replay()
-    e1.record(); torch.cuda.synchronize()
-    t_peer = e0.elapsed_time(e1) / 200 * 1e3
-    tl = peer.timeline()
-    tl = tl[(tl > 0).all(1)]
-    ph = (tl[:, 1:] - tl[:, :-1]) / 1e3          # us: stage, publish+wait, pull
-    ev, od = ph[0::2].mean(0), ph[1::2].mean(0)   # calls alternate gather / all-reduce
-    if rank == 0:
-        print(f"   CTA-0 phases (us) stage / publish+wait / pull: {ev.tolist()} and {od.tolist()}", flush=True)
-    flat = torch.cat([t.reshape(-1) for t in grads]); packed = torch.cat([t.reshape(-1) for t in a])
+
+    def timed_graph(fn, reps=10, iters=100):
+        fn(); torch.cuda.synchronize(); td.barrier()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+            for _ in range(reps):
+                fn()
+        for _ in range(5):
+            gr.replay()
+        td.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            gr.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (iters * reps) * 1e3
+
+    def phases(tag):
+        tl = peer.timeline()
+        tl = tl[(tl > 0).all(1)]
+        ph = ((tl[:, 1:] - tl[:, :-1]) / 1e3).mean(0).tolist()
+        print(f"   rank {rank} {tag}: CTA-0 stage {ph[0]:.2f} us, publish+wait {ph[1]:.2f} us, pull {ph[2]:.2f} us", flush=True)
+
+    zg = [torch.zeros_like(t) for t in grads]
+    lat_pieces = [a[0], lab0]                                  # the latent exchange of configs[1]: mu [1024, 8] + labels
+    t_g = timed_graph(lambda: peer.gather(lat_pieces)); phases("gather(latents 40 KB)")
+    z5 = [torch.zeros(1024, 16, device=dev) for _ in range(5)]
+    t_g5 = timed_graph(lambda: peer.gather(z5)); phases("gather(5 x 64 KB)")
+    t_a = timed_graph(lambda: peer.allreduce_(zg)); phases("all-reduce(1.4 MB, 9 tensors)")
+    flat = torch.cat([t.reshape(-1) for t in zg]); packed = torch.cat([t.reshape(-1) for t in a[:1]] + [lab0.view(torch.float32)])
     gout = torch.empty(world * packed.numel(), device=dev)
-    def once_nccl():
-        td.all_gather_into_tensor(gout, packed)
-        td.all_reduce(flat)
-    once_nccl(); torch.cuda.synchronize()
-    g2 = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g2, capture_error_mode="thread_local"):
-        once_nccl()
-    for _ in range(20):
-        g2.replay()
-    td.barrier(); torch.cuda.synchronize()
-    e0.record()
-    for _ in range(200):
-        g2.replay()
-    e1.record(); torch.cuda.synchronize()
-    t_nccl = e0.elapsed_time(e1) / 200 * 1e3
+    t_ng = timed_graph(lambda: td.all_gather_into_tensor(gout, packed))
+    t_na = timed_graph(lambda: td.all_reduce(flat))
+    t_peer, t_nccl = t_g + t_a, t_ng + t_na
+    if rank == 0:
+        print(f"   per call, back to back in a graph: peer gather {t_g:.1f} us (5 pieces {t_g5:.1f} us) vs NCCL all-gather {t_ng:.1f} us; "
+              f"peer all-reduce {t_a:.1f} us vs NCCL all-reduce {t_na:.1f} us", flush=True)
     if rank == 0:
         print(f"peer kernels world={world}: match NCCL {bool(ok)}, all-reduce bit-identical across ranks {bool(same_bits)}, error flag {peer.error()}; "
-              f"gather(4 pieces, 51 KB/rank) + all-reduce(1.4 MB): {t_peer:.1f} us per pair vs NCCL all-gather + all-reduce {t_nccl:.1f} us", flush=True)
+              f"gather + all-reduce {t_peer:.1f} us vs NCCL {t_nccl:.1f} us", flush=True)
 for Bl, D in [(64, 8), (512, 32), (4096, 8)]:
     Bg = Bl * world
     mu_c, lv_c, mu_s, lv_s, e_c, e_s = ((torch.randn(Bg, D, generator=g) * s).to(dev) for s in (1, .3, 1, .3, 1, 1))
