@@ -1410,7 +1410,7 @@ inline int pick_splits(long long B, long long Bg, int n_terms, int sim) {
   if (sim >= SIM_ML2 || B > kSplitMaxRows) return 1;
   const long long ctas = (long long)max_ctas_for(B) * n_terms;
   const long long tiles = (Bg + kTN - 1) / kTN;
-  long long s = (148 * 4 + ctas - 1) / ctas;
+  long long s = (148 * 8 + ctas - 1) / ctas;   // aim for ~8 resident CTAs per SM
   s = std::min<long long>(s, std::min<long long>(kMaxSplits, tiles));
   return (int)std::max<long long>(1, s);
 }
