@@ -34,6 +34,7 @@ struct TermF {
   const float *mu, *lv, *eps, *mu_cols, *lv_cols;
   float *z, *stats;
   int snn, ps;
+  float* aux;   // [B] SupCon only: n_k (supcon_in) / positive count (supcon_out)
 };
 struct FwdParams {
   TermF t[2];
@@ -49,12 +50,14 @@ struct FwdParams {
   int splits;
   long long cps;
   float* part;
+  int loss;   // CLEARVAE_LOSS_*
 };
 struct TermB {
   const float *mu, *lv, *eps, *mu_cols, *stats_all, *dz;
   float *dmu, *dlv;
   int snn, ps;
   const float* lv_cols;
+  const float* aux_all;   // [Bg] SupCon only (see TermF::aux), all global rows
 };
 struct BwdParams {
   TermB t[2];
@@ -69,6 +72,7 @@ struct BwdParams {
   long long cps;
   float* part;
   unsigned* tickets;
+  int loss;   // CLEARVAE_LOSS_*
 };
 
 enum { SIM_COS = CLEARVAE_SIM_COSINE, SIM_L2 = CLEARVAE_SIM_L2, SIM_ML2 = CLEARVAE_SIM_MODIFIED_L2, SIM_JEF = CLEARVAE_SIM_JEFFREY,
@@ -268,8 +272,15 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
         }
     }
     float sa[RM], sp[RM], ma[RM], mp[RM];
+    // SupCon row losses (losses.py:140-170) share the sweep; they additionally need the positive count and, for
+    // supcon_out, the sum of the raw positive similarities.  The row statistics keep their (a, b) form with
+    //   supcon_in : b = lse_pos - log(n_k),  n_k = #positives (-1 under ps: the reference counts the undiagonalised mask)
+    //   supcon_out: b = (sum of positive similarities) / #positives        (0/0 = nan: the row is selected out)
+    // so that the row loss is a - b and the finite-row mean of `finalize_term` applies unchanged.
+    float pc[RM], ps_sum[RM];
 #pragma unroll
-    for (int r = 0; r < RM; ++r) { sa[r] = sp[r] = 0.f; ma[r] = mp[r] = -INFINITY; }
+    for (int r = 0; r < RM; ++r) { sa[r] = sp[r] = 0.f; ma[r] = mp[r] = -INFINITY; pc[r] = ps_sum[r] = 0.f; }
+    const bool supcon = p.loss != CLEARVAE_LOSS_SNN;
     const float k2 = p.inv_tau * CV_LOG2E;
     const float* cols = t.mu_cols ? t.mu_cols : t.mu;
     const float* lvc = t.lv_cols ? t.lv_cols : t.lv;
@@ -303,6 +314,10 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
           }
           const bool cand = (j != p.row_off + row0 + r);
           const bool pos = cand && ((lab == rl[r]) != (t.ps != 0));
+          if (supcon) {
+            pc[r] += pos ? 1.f : 0.f;
+            ps_sum[r] += pos ? s : 0.f;
+          }
           if (FAST) {
             const float e = exp2f(fmaf(s, k2, -k2));
             sa[r] += cand ? e : 0.f;
@@ -310,6 +325,7 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
           } else {
             const float xs = s * p.inv_tau;
             if (cand) cv::lse_push(ma[r], sa[r], xs);
+            else if (p.loss == CLEARVAE_LOSS_SUPCON_OUT) cv::lse_push(ma[r], sa[r], -999.f * p.inv_tau);  // losses.py:158
             if (pos) cv::lse_push(mp[r], sp[r], xs);
           }
         }
@@ -347,6 +363,19 @@ __global__ void __launch_bounds__(kTN) snn_fwd_kernel(const FwdParams p) {
         op = mp[r] + logf(sp[r]);
       }
       const long long i = row0 + r;
+      if (supcon) {
+        const float cnt = cv::warp_sum(pc[r]);
+        const float ssum = cv::warp_sum(ps_sum[r]);
+        float aux;
+        if (p.loss == CLEARVAE_LOSS_SUPCON_IN) {
+          aux = cnt - (t.ps != 0 ? 1.f : 0.f);
+          op = op - logf(aux);           // log(0) = -inf, log(<0) = nan: non-finite rows drop out like the reference's
+        } else {
+          aux = cnt;
+          op = ssum / cnt - (FAST ? p.inv_tau : 0.f);   // FAST: `oa` is relative to the shared shift 1/tau, keep a - b exact
+        }
+        if (lane == 0 && i < p.B && t.aux != nullptr) t.aux[i] = aux;
+      }
       if (lane == 0 && i < p.B) {
         t.stats[2 * i] = oa;
         t.stats[2 * i + 1] = op;
@@ -777,6 +806,24 @@ int launch_fwd_tc(const FwdParams& p, int n_terms, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
+// Per-row coefficients of the pair gradient from the forward statistics (a, b) [+ aux for the SupCon losses]:
+//   snn / supcon_in : c = e^{-a}, q = e^{-lse_pos}   (FAST; the general path keeps the logs and exponentiates per pair)
+//                     supcon_in stores b = lse_pos - log(n_k), and log(n_k) carries no gradient
+//   supcon_out      : c as above, q = tau / #pos     (the positive part of the row loss is linear in s; 1/tau factored out)
+// Non-finite rows (dropped from the mean) get zero coefficients.
+template <bool FAST>
+__device__ __forceinline__ void row_coef(int loss, float tau, bool fin, float a, float b, float aux, float& c, float& q) {
+  if (loss == CLEARVAE_LOSS_SUPCON_IN) b += logf(aux);
+  if (FAST) {
+    c = fin ? __expf(-a) : 0.f;
+    q = fin ? __expf(-b) : 0.f;
+  } else {
+    c = fin ? a : INFINITY;
+    q = fin ? b : INFINITY;
+  }
+  if (loss == CLEARVAE_LOSS_SUPCON_OUT) q = fin ? tau / aux : 0.f;   // 1/tau is factored out of the whole coefficient
+}
+
 template <int DP, int RM, int SIM, bool FAST>
 __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -827,8 +874,8 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
         b = t.stats_all[2 * (p.row_off + i) + 1];
       }
       const bool fin = isfinite(a - b);
-      if (FAST) { ci[r] = fin ? __expf(-a) : 0.f; qi[r] = fin ? __expf(-b) : 0.f; }
-      else      { ci[r] = fin ? a : INFINITY;   qi[r] = fin ? b : INFINITY; }
+      const float ax = (p.loss != CLEARVAE_LOSS_SNN && i < p.B) ? t.aux_all[p.row_off + i] : 1.f;
+      row_coef<FAST>(p.loss, 1.f / p.inv_tau, fin, a, b, ax, ci[r], qi[r]);
     }
     const float k2 = p.inv_tau * CV_LOG2E;
     const float* cols = t.mu_cols ? t.mu_cols : t.mu;
@@ -843,8 +890,8 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
         float a = INFINITY, b = INFINITY;
         if (j < p.Bg) { a = t.stats_all[2 * j]; b = t.stats_all[2 * j + 1]; }
         const bool fin = isfinite(a - b);
-        if (FAST) { sC[threadIdx.x] = fin ? __expf(-a) : 0.f; sQ[threadIdx.x] = fin ? __expf(-b) : 0.f; }
-        else      { sC[threadIdx.x] = fin ? a : INFINITY;   sQ[threadIdx.x] = fin ? b : INFINITY; }
+        const float ax = (p.loss != CLEARVAE_LOSS_SNN && j < p.Bg) ? t.aux_all[j] : 1.f;
+        row_coef<FAST>(p.loss, 1.f / p.inv_tau, fin, a, b, ax, sC[threadIdx.x], sQ[threadIdx.x]);
       }
       __syncthreads();
       for (int jj = lane; jj < kTN; jj += 32) {
@@ -875,7 +922,11 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
           const bool cand = (j != p.row_off + row0 + r);
           const bool pos = cand && ((lab == rl[r]) != (t.ps != 0));
           float coef;
-          if (FAST) {
+          if (p.loss == CLEARVAE_LOSS_SUPCON_OUT) {
+            // d(row loss)/ds = e^{s/tau - a} / tau - [pos] / #pos : the positive part is linear in s (losses.py:167)
+            const float e = FAST ? exp2f(fmaf(s, k2, -k2)) * (ci[r] + cj) : __expf(s * p.inv_tau - ci[r]) + __expf(s * p.inv_tau - cj);
+            coef = e - (pos ? (qi[r] + qj) : 0.f);
+          } else if (FAST) {
             const float e = exp2f(fmaf(s, k2, -k2));
             coef = e * ((ci[r] + cj) - (pos ? (qi[r] + qj) : 0.f));
           } else {
@@ -1367,7 +1418,7 @@ int g_tc_min_rows = 4096;
 
 int dispatch_fwd(const FwdParams& p, int n_terms, int sim, bool fast, cudaStream_t st) {
   const int dp = pad_d(p.D), rm = pick_rm(dp, p.B);
-  if (fast && sim == SIM_COS && dp <= 32 && p.B >= g_tc_min_rows) {
+  if (fast && sim == SIM_COS && dp <= 32 && p.B >= g_tc_min_rows && p.loss == CLEARVAE_LOSS_SNN) {
     bool all_snn = true;  // KL/reparam-only terms have no tile loop; keep them on the FFMA kernel
     for (int i = 0; i < n_terms; ++i) all_snn &= p.t[i].snn != 0;
     if (all_snn) {
@@ -1381,7 +1432,7 @@ int dispatch_fwd(const FwdParams& p, int n_terms, int sim, bool fast, cudaStream
 }
 int dispatch_bwd(const BwdParams& p, int n_terms, int sim, bool fast, cudaStream_t st) {
   const int dp = pad_d(p.D), rm = pick_rm(dp, p.B);
-  if (fast && sim == SIM_COS && dp <= 32 && p.B >= g_tc_min_rows) {
+  if (fast && sim == SIM_COS && dp <= 32 && p.B >= g_tc_min_rows && p.loss == CLEARVAE_LOSS_SNN) {
     bool all_snn = true;
     for (int i = 0; i < n_terms; ++i) all_snn &= p.t[i].snn != 0;
     if (all_snn) {
@@ -1406,8 +1457,8 @@ inline int max_ctas_for(long long B) { return (int)((B + kWarps - 1) / kWarps); 
 // SM and the sweep is a chain of exposed load latencies.  Splitting the columns over blockIdx.z puts 4+ CTAs on every SM.
 constexpr int kMaxSplits = 8;
 constexpr long long kSplitMaxRows = 4096;   // beyond this the row blocks alone fill the GPU (and the TC path takes over)
-inline int pick_splits(long long B, long long Bg, int n_terms, int sim) {
-  if (sim >= SIM_ML2 || B > kSplitMaxRows) return 1;
+inline int pick_splits(long long B, long long Bg, int n_terms, int sim, int loss) {
+  if (sim >= SIM_ML2 || B > kSplitMaxRows || loss != CLEARVAE_LOSS_SNN) return 1;
   const long long ctas = (long long)max_ctas_for(B) * n_terms;
   const long long tiles = (Bg + kTN - 1) / kTN;
   long long s = (148 * 8 + ctas - 1) / ctas;   // aim for ~8 resident CTAs per SM
@@ -1450,7 +1501,7 @@ int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const i
                         int32_t z_stride, int32_t sim_fn, int32_t loss_name, float temperature, float* scalars,
                         int32_t finalize, void* workspace, size_t workspace_bytes, void* stream) {
   if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !workspace || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
-  if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
+  if (loss_name < CLEARVAE_LOSS_SNN || loss_name > CLEARVAE_LOSS_SUPCON_OUT) return CLEARVAE_EUNSUPPORTED;
   if (sim_fn < SIM_COS || sim_fn > SIM_MAH) return CLEARVAE_EUNSUPPORTED;
   if (pad_d(D) < 0) return CLEARVAE_EUNSUPPORTED;
   if (workspace_bytes < clearvae_latent_workspace_bytes(B, Bg, D, n_terms)) return CLEARVAE_EWORKSPACE;
@@ -1462,7 +1513,8 @@ int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const i
     if (!s.mu) return CLEARVAE_EINVAL;
     if (s.snn_enable && (!s.row_stats || !label_rows)) return CLEARVAE_EINVAL;
     if (s.snn_enable && sim_fn >= SIM_ML2 && !s.logvar) return CLEARVAE_EINVAL;   // these similarities read logvar
-    p.t[i] = TermF{s.mu, s.logvar, s.eps, s.mu_cols, s.logvar_cols, s.z, s.row_stats, s.snn_enable, s.ps};
+    if (s.snn_enable && loss_name != CLEARVAE_LOSS_SNN && !s.row_aux) return CLEARVAE_EINVAL;
+    p.t[i] = TermF{s.mu, s.logvar, s.eps, s.mu_cols, s.logvar_cols, s.z, s.row_stats, s.snn_enable, s.ps, s.row_aux};
     any_snn |= s.snn_enable != 0;
   }
   p.lab_r = reinterpret_cast<const long long*>(label_rows);
@@ -1470,13 +1522,14 @@ int clearvae_latent_fwd(const clearvae_term_fwd* terms, int32_t n_terms, const i
   p.B = B; p.Bg = Bg; p.row_off = row_offset; p.D = D; p.z_stride = z_stride; p.finalize = finalize;
   p.max_ctas = max_ctas_for(B);
   p.inv_tau = 1.f / temperature;
+  p.loss = loss_name;
   p.scalars = scalars;
   p.ticket = &reinterpret_cast<WsLayout*>(workspace)->ticket;
   p.kl_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sizeof(WsLayout));
   {
     const size_t base = (sizeof(WsLayout) + (size_t)2 * max_ctas_for(B) * sizeof(float) + 15) & ~(size_t)15;
     p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + base);
-    p.splits = any_snn ? pick_splits(B, Bg, n_terms, sim_fn) : 1;
+    p.splits = any_snn ? pick_splits(B, Bg, n_terms, sim_fn, loss_name) : 1;
     p.cps = cols_per_split(Bg, p.splits);
   }
   return dispatch_fwd(p, n_terms, sim_fn, fast_ok(sim_fn, temperature), (cudaStream_t)stream);
@@ -1502,7 +1555,7 @@ int clearvae_latent_bwd_ws(const clearvae_term_bwd* terms, int32_t n_terms, cons
                            int32_t z_stride, int32_t sim_fn, int32_t loss_name, float temperature,
                            const float* scalars, const float* gscal, void* workspace, size_t workspace_bytes, void* stream) {
   if (!terms || n_terms < 1 || n_terms > 2 || !scalars || !gscal || B <= 0 || Bg <= 0 || D <= 0) return CLEARVAE_EINVAL;
-  if (loss_name != CLEARVAE_LOSS_SNN) return CLEARVAE_EUNSUPPORTED;
+  if (loss_name < CLEARVAE_LOSS_SNN || loss_name > CLEARVAE_LOSS_SUPCON_OUT) return CLEARVAE_EUNSUPPORTED;
   if (sim_fn < SIM_COS || sim_fn > SIM_MAH) return CLEARVAE_EUNSUPPORTED;
   if (pad_d(D) < 0) return CLEARVAE_EUNSUPPORTED;
   if (row_offset < 0 || row_offset + B > Bg) return CLEARVAE_EINVAL;
@@ -1512,19 +1565,22 @@ int clearvae_latent_bwd_ws(const clearvae_term_bwd* terms, int32_t n_terms, cons
     if (!s.mu || !s.dmu) return CLEARVAE_EINVAL;
     if (s.snn_enable && (!s.row_stats_all || !label_rows)) return CLEARVAE_EINVAL;
     if (s.snn_enable && sim_fn >= SIM_ML2 && (!s.logvar || !s.dlogvar)) return CLEARVAE_EINVAL;
-    p.t[i] = TermB{s.mu, s.logvar, s.eps, s.mu_cols, s.row_stats_all, s.dz, s.dmu, s.dlogvar, s.snn_enable, s.ps, s.logvar_cols};
+    if (s.snn_enable && loss_name != CLEARVAE_LOSS_SNN && !s.row_aux_all) return CLEARVAE_EINVAL;
+    p.t[i] = TermB{s.mu, s.logvar, s.eps, s.mu_cols, s.row_stats_all, s.dz, s.dmu, s.dlogvar, s.snn_enable, s.ps, s.logvar_cols,
+                   s.row_aux_all};
   }
   p.lab_r = reinterpret_cast<const long long*>(label_rows);
   p.lab_c = reinterpret_cast<const long long*>(label_cols ? label_cols : label_rows);
   p.B = B; p.Bg = Bg; p.row_off = row_offset; p.D = D; p.z_stride = z_stride;
   p.inv_tau = 1.f / temperature;
   p.scalars = scalars; p.gscal = gscal;
+  p.loss = loss_name;
   p.splits = 1;
   p.cps = cols_per_split(Bg, 1);
   bool any_snn = false;
   for (int i = 0; i < n_terms; ++i) any_snn |= terms[i].snn_enable != 0;
   if (workspace && any_snn && workspace_bytes >= clearvae_latent_bwd_workspace_bytes(B, Bg, D, n_terms)) {
-    p.splits = pick_splits(B, Bg, n_terms, sim_fn);
+    p.splits = pick_splits(B, Bg, n_terms, sim_fn, loss_name);
     p.cps = cols_per_split(Bg, p.splits);
     p.tickets = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + 256);
     const size_t off = (256 + (size_t)n_terms * max_ctas_for(B) * sizeof(unsigned) + 15) & ~(size_t)15;

@@ -66,7 +66,8 @@ std::tuple<Tensor, Tensor, std::vector<Tensor>> latent_fwd(
   auto fopt = mu[0].options();
   Tensor z = want_z ? at::empty({B, n * D}, fopt) : Tensor();
   Tensor scalars = at::zeros({CLEARVAE_NSCALARS}, fopt);
-  std::vector<Tensor> stats;
+  std::vector<Tensor> stats, aux;
+  const bool supcon = loss_name != CLEARVAE_LOSS_SNN;   // SupCon row losses carry one more per-row statistic
   clearvae_term_fwd terms[2];
   for (int i = 0; i < n; ++i) {
     check_f32(mu[i], "mu");
@@ -81,6 +82,11 @@ std::tuple<Tensor, Tensor, std::vector<Tensor>> latent_fwd(
     terms[i].ps = (int32_t)ps[i];
     stats.push_back(snn[i] ? at::empty({B, 2}, fopt) : at::empty({0, 2}, fopt));
     terms[i].row_stats = snn[i] ? stats.back().data_ptr<float>() : nullptr;
+    terms[i].row_aux = nullptr;
+    if (supcon) {
+      aux.push_back(snn[i] ? at::empty({B}, fopt) : at::empty({0}, fopt));
+      terms[i].row_aux = snn[i] ? aux.back().data_ptr<float>() : nullptr;
+    }
   }
   TORCH_CHECK(workspace.is_cuda() && workspace.is_contiguous(), "clearvae: workspace must be a contiguous CUDA tensor");
   check_rc(clearvae_latent_fwd(terms, n, label_rows.data_ptr<int64_t>(), lab_c, B, Bg, row_offset, (int32_t)D,
@@ -89,6 +95,7 @@ std::tuple<Tensor, Tensor, std::vector<Tensor>> latent_fwd(
                                (size_t)workspace.nbytes(), cur_stream()),
            "latent_fwd");
   if (!want_z) z = at::empty({0}, fopt);
+  for (auto& a : aux) stats.push_back(a);   // [stats_0 .. stats_{n-1}, aux_0 .. aux_{n-1}] for the SupCon row losses
   return {z, scalars, stats};
 }
 
@@ -141,6 +148,14 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>> latent_bwd(
     terms[i].mu_cols = fptr(mu_cols.get(i), "mu_cols", Bg, D);
     terms[i].row_stats_all = snn[i] ? fptr(stats_all.get(i), "stats_all", Bg, 2) : nullptr;
     TORCH_CHECK(!snn[i] || terms[i].row_stats_all, "clearvae: stats_all missing for an enabled term");
+    terms[i].row_aux_all = nullptr;
+    if (loss_name != CLEARVAE_LOSS_SNN && snn[i]) {
+      TORCH_CHECK((int)stats_all.size() == 2 * n, "clearvae: SupCon row losses need [stats..., aux...] from the forward");
+      const OptTensor a = stats_all.get(n + i);
+      TORCH_CHECK(a.has_value() && a->defined() && a->numel() == Bg, "clearvae: aux_all missing for an enabled term");
+      check_f32(*a, "aux_all");
+      terms[i].row_aux_all = a->data_ptr<float>();
+    }
     terms[i].dz = dzp ? dzp + i * D : nullptr;
     dmu.push_back(at::empty({B, D}, fopt));
     terms[i].dmu = dmu.back().data_ptr<float>();

@@ -68,7 +68,7 @@ class _LatentBlock(torch.autograd.Function):
             ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n))
             z, scalars, stats = ops.latent_fwd(mu, logvar, eps, [None] * n, [None] * n, label, None, cfg["snn"], cfg["ps"], 0,
                                                cfg["sim"], cfg["loss"], cfg["tau"], True, want_z, ws)
-            cols, lv_cols, label_cols, stats_all, row_off = [None] * n, [None] * n, None, stats, 0
+            cols, lv_cols, label_cols, stats_all, row_off = [None] * n, [None] * n, None, list(stats), 0
         else:
             snn_terms = [i for i in range(n) if cfg["snn"][i]]
             cols, lv_cols = [None] * n, [None] * n
@@ -97,20 +97,24 @@ class _LatentBlock(torch.autograd.Function):
             ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, Bg, D, n))
             z, scalars, stats = ops.latent_fwd(mu, logvar, eps, cols, lv_cols, label, label_cols, cfg["snn"], cfg["ps"], row_off,
                                                cfg["sim"], cfg["loss"], cfg["tau"], False, want_z, ws)
-            stats_all = [None] * n
+            supcon = cfg["loss"] != 0           # SupCon row losses: the op returns [stats..., aux...] (one more per-row statistic)
+            stats_all = [None] * (2 * n if supcon else n)
+            mine = [stats[i] for i in snn_terms] + ([stats[n + i] for i in snn_terms] if supcon else [])
             if snn_terms and dist.peer is not None:
-                for i, t in zip(snn_terms, dist.peer.gather([stats[i] for i in snn_terms])):
-                    stats_all[i] = t
+                got = dist.peer.gather(mine)
             elif snn_terms:
-                st_cat = _all_gather_rows(torch.cat([stats[i] for i in snn_terms], dim=1), dist)
-                for k, i in enumerate(snn_terms):
-                    stats_all[i] = st_cat[:, 2 * k:2 * k + 2].contiguous()
+                got = [_all_gather_rows(t, dist) for t in mine]
+            for k, i in enumerate(snn_terms):
+                stats_all[i] = got[k]
+                if supcon:
+                    stats_all[n + i] = got[len(snn_terms) + k]
             for i in snn_terms:
                 ops.snn_finalize(stats_all[i], i, scalars)
         ctx.cfg = cfg
         ctx.row_off = row_off
         ctx.n_saved = (len(mu), len(logvar), len(eps))
-        ctx.save_for_backward(label, label_cols, scalars, *mu, *logvar, *eps, *cols, *stats_all, *lv_cols)
+        ctx.n_stats = len(stats_all)
+        ctx.save_for_backward(label, label_cols, scalars, *mu, *logvar, *eps, *cols, *lv_cols, *stats_all)
         return z, scalars
 
     @staticmethod
@@ -120,7 +124,8 @@ class _LatentBlock(torch.autograd.Function):
         saved = ctx.saved_tensors
         label, label_cols, scalars = saved[0], saved[1], saved[2]
         rest = list(saved[3:])
-        mu, logvar, eps, cols, stats_all, lv_cols = (rest[k * n:(k + 1) * n] for k in range(6))
+        mu, logvar, eps, cols, lv_cols = (rest[k * n:(k + 1) * n] for k in range(5))
+        stats_all = rest[5 * n:5 * n + ctx.n_stats]
         ops = _ops.ops()
         if dscal is None:
             dscal = torch.zeros(8, dtype=scalars.dtype, device=scalars.device)

@@ -67,6 +67,9 @@ typedef struct {
   /* configuration */
   int32_t snn_enable;   /* 0: only reparam/KL for this term          */
   int32_t ps;           /* 0: same-label positives, 1: flipped mask  */
+  float* row_aux;       /* [B] out, SupCon row losses only (NULL for snn_loss): n_k of losses.py:141 (supcon_in) or the
+                           positive count of losses.py:164 (supcon_out); row_stats then holds (lse_all, b) with
+                           b = lse_pos - log(n_k) resp. mean positive similarity, so the row loss is always a - b */
 } clearvae_term_fwd;
 
 /* scalars written by the forward (float[CLEARVAE_NSCALARS]) */
@@ -104,6 +107,7 @@ typedef struct {
   int32_t snn_enable;
   int32_t ps;
   const float* logvar_cols; /* [Bg, D] or NULL (= rows): only the logvar-dependent similarities read it */
+  const float* row_aux_all; /* [Bg] row_aux of ALL global rows (SupCon row losses only, else NULL) */
 } clearvae_term_bwd;
 
 /* backward of the block. `gscal` (device, float[4]) = upstream grads of

@@ -32,8 +32,6 @@ def test_contrastive_matches_reference_goldens(golden_dir):
     from clear_vae_b200.losses import contrastive_loss
     n = 0
     for name, g, sim, tau, ln, ps in cases(golden_dir):
-        if ln != "snn_loss":
-            continue   # the SupCon row losses are oracle-only (never selected by a reference trainer)
         lv_sim = sim in ("jeffrey", "mahalanobis", "modified_l2")
         mu = torch.tensor(g[f"{name}/mu"], device=DEV, requires_grad=True)
         lv = torch.tensor(g[f"{name}/logvar"], device=DEV, requires_grad=lv_sim)
@@ -57,7 +55,7 @@ def test_contrastive_matches_reference_goldens(golden_dir):
             else:
                 assert lv.grad is None
         n += 1
-    assert n >= 40
+    assert n >= 44   # incl. the four SupCon row-loss cases (losses.py:140-170)
 
 
 def test_pair_mask_bit_exact():
@@ -302,3 +300,57 @@ def test_column_split_shard_against_oracle(sim, tau, D, ps):
         assert torch.equal(dmu[0], dmu2[0])                  # fixed-order merge: bit-reproducible
         dmu1, _ = ops.latent_bwd(*args, None)                 # no workspace -> unsplit sweep, same gradient
         assert np.abs(dmu1[0].cpu().numpy() - got).max() <= 1e-6 * np.abs(wg).max() + 1e-9
+
+
+def _supcon_torch(mu, label, sim, tau, name, ps):
+    """fp64 torch restatement of the two SupCon row losses + finite-row mean (oracle/latent_oracle.py:row_losses, which
+    follows losses.py:140-170), written on the valid rows only so that autograd gives clean gradients."""
+    mu = mu.double()
+    if sim == "cosine":
+        nrm = mu / mu.norm(dim=1, keepdim=True).clamp_min(1e-8)
+        S = nrm @ nrm.T
+    else:
+        S = -((mu[:, None, :] - mu[None, :, :]) ** 2).sum(-1)
+    B = mu.shape[0]
+    eye = torch.eye(B, dtype=torch.bool)
+    m = (label[None, :] == label[:, None]) != bool(ps)
+    pm = m & ~eye
+    cnt = pm.sum(1)
+    if name == "supcon_out_loss":
+        keep = cnt > 0
+        S2 = S.masked_fill(eye, -999.0)
+        val = -(S2 * pm).sum(1)[keep] / cnt[keep] + torch.logsumexp(S2[keep] / tau, dim=1)
+        return val[torch.isfinite(val)].mean()
+    n_k = m.sum(1) - 1
+    keep = (cnt > 0) & (n_k > 0)
+    S2 = S.masked_fill(eye, -float("inf"))[keep]
+    pos = S2.masked_fill(~m[keep], -float("inf"))
+    val = n_k[keep].double().log() - torch.logsumexp(pos / tau, dim=1) + torch.logsumexp(S2 / tau, dim=1)
+    return val[torch.isfinite(val)].mean()
+
+
+@pytest.mark.parametrize("name", ["supcon_in_loss", "supcon_out_loss"])
+@pytest.mark.parametrize("sim,tau,D", [("cosine", 0.1, 8), ("cosine", 0.02, 32), ("l2", 0.5, 16)])
+@pytest.mark.parametrize("ps", [False, True])
+def test_supcon_row_losses_against_oracle_and_fp64_autograd(name, sim, tau, D, ps):
+    """f-1: the SupCon row losses behind the same `contrastive_loss` signature (losses.py:124,140-170): value vs the numpy
+    oracle (itself pinned to the reference goldens), gradient vs an fp64 autograd restatement.  The batch holds singleton
+    classes (rows without positives are selected out) and, under ps, the n_k = #different - 1 quirk of losses.py:141."""
+    from clear_vae_b200.losses import contrastive_loss
+    gen = torch.Generator().manual_seed(23)
+    B = 333
+    mu_h = torch.randn(B, D, generator=gen) * (0.4 if sim == "l2" else 1.0)
+    lab_h = torch.randint(0, 7, (B,), generator=gen)
+    lab_h[:5] = torch.arange(100, 105)                      # singleton classes
+    mu = mu_h.to(DEV).requires_grad_(True)
+    got = contrastive_loss(mu, torch.zeros_like(mu), lab_h.to(DEV), sim, tau, name, ps)
+    want = lo.contrastive(mu_h.numpy(), np.zeros((B, D)), lab_h.numpy(), sim, tau, loss_name=name, ps=ps)
+    assert close(float(got), want, rel=3e-5 if sim == "l2" else LOSS_REL), (float(got), want)
+    ref_in = mu_h.clone().double().requires_grad_(True)
+    ref = _supcon_torch(ref_in, lab_h, sim, tau, name, ps)
+    assert abs(float(ref) - want) <= 1e-9 * abs(want) + 1e-12
+    ref.backward()
+    got.backward()
+    wg = ref_in.grad.numpy()
+    err = np.abs(mu.grad.cpu().numpy() - wg).max()
+    assert err <= GRAD_REL * np.abs(wg).max() + 1e-7, (err, np.abs(wg).max())
