@@ -238,12 +238,51 @@ class VAETrainer(Trainer):
         g["graph"].replay()
         return tuple(t.clone() for t in g["out"])  # the graph's output buffers are overwritten by the next replay
 
+    # ---- graph capture must not train: the eager warm-up steps below (allocator / workspace / optimiser-state
+    # warm-up that CUDA-graph capture requires) run on the real batch, so everything they touch is put back
+    def _stateful(self):
+        mods = [m for m in (self.model, getattr(self, "factor_cls", None), getattr(self, "mi_estimator", None)) if m is not None]
+        opts = [o for o in (self.optimizer, getattr(self, "factor_optimizer", None), getattr(self, "mi_estimator_optimizer", None))
+                if o is not None]
+        return mods, opts
+
+    def _snapshot_state(self, device):
+        mods, opts = self._stateful()
+        tensors = {}
+        for m in mods:
+            for t in list(m.parameters()) + list(m.buffers()):
+                tensors[t] = t.detach().clone()
+        known = set()
+        for o in opts:
+            for st in o.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        tensors[v] = v.detach().clone()
+                        known.add(id(v))
+        rng = (torch.get_rng_state(), torch.cuda.get_rng_state(device))
+        return tensors, known, rng
+
+    def _restore_state(self, snap, device):
+        tensors, known, rng = snap
+        _, opts = self._stateful()
+        with torch.no_grad():
+            for t, v in tensors.items():
+                t.copy_(v)
+            for o in opts:   # optimiser state created by the warm-up itself goes back to "never stepped"
+                for st in o.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v) and id(v) not in known:
+                            v.zero_()
+        torch.set_rng_state(rng[0])
+        torch.cuda.set_rng_state(rng[1], device)
+
     def _capture(self, X, label):
         import os, sys
         dbg = (lambda m: print(f"[capture] {m}", file=sys.stderr, flush=True)) if os.environ.get("CLEARVAE_DEBUG") else (lambda m: None)
         sX, sl = X.clone(), label.clone()
         perm = perm_host = None
         kw = {}
+        snap = self._snapshot_state(X.device)
         if self._needs_perm():
             perm_host = torch.stack([torch.randperm(X.shape[0]), torch.randperm(X.shape[0])]).pin_memory()   # two slots
             perm = perm_host[0].to(X.device)
@@ -255,6 +294,8 @@ class VAETrainer(Trainer):
             for _ in range(2):
                 self._device_step(sX, sl, **kw)
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore_state(snap, X.device)   # the warm-up steps were real updates: undo them (weights, BN buffers, Adam, RNG)
         torch.cuda.synchronize()
         dbg("begin capture")
         graph = torch.cuda.CUDAGraph()

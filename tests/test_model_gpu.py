@@ -209,3 +209,103 @@ def test_reparam_multi_matches_the_latent_kernel_bitwise():
     for j in range(5):
         want, _ = latent_block(mu, lv, eps[2 * j:2 * j + 2], dummy, snn=[0, 0], ps=[0, 0])
         assert torch.equal(zs[j], want)
+
+
+def test_device_prefetcher_hands_out_every_batch_intact_under_a_slow_consumer():
+    """`VAETrainer.prefetch` (the input path of `fit()`): three rotating device slots, one batch of look-ahead.  A consumer
+    that is far behind on the GPU (a 1 ms spin kernel in front of every use) must still read every batch unmodified —
+    a slot may only be refilled after the work enqueued on it has executed."""
+    from clear_vae_b200.trainer import DevicePrefetcher
+    gen = torch.Generator().manual_seed(4)
+    sizes = [64] * 9 + [17]          # ragged last batch, like a DataLoader without drop_last
+    src = [(torch.rand(b, 3, 28, 28, generator=gen).pin_memory(), torch.randint(0, 10, (b, 1), generator=gen).pin_memory()) for b in sizes]
+    kept = []
+    for X, y in DevicePrefetcher(src, torch.device(DEV)):
+        assert X.is_cuda and y.dtype == torch.int64 and y.dim() == 1
+        torch.cuda._sleep(2_000_000)
+        kept.append((X.clone(), y.clone()))       # executes after the spin, long after the next batches were staged
+    torch.cuda.synchronize()
+    assert len(kept) == len(src)
+    for (X, y), (xs, ys) in zip(kept, src):
+        assert torch.equal(X.cpu(), xs) and torch.equal(y.cpu(), ys.reshape(-1))
+
+
+def test_graph_replayed_fit_over_a_dataloader_matches_hand_fed_steps():
+    """`fit()` = DataLoader -> prefetcher -> CUDA-graph replay of the step, with host-written step inputs (annealer weight)
+    staged through alternating pinned slots.  Feeding the same batches by hand, one synchronised step at a time, must give
+    the same model: any race in the slots / prefetch buffers would show up as different weights.  (Weight gradients use
+    fp32 atomics, so equality is to rounding noise, not bitwise.)"""
+    from torch.utils.data import DataLoader, TensorDataset
+    from clear_vae_b200.utils.trainer_utils import get_clearvae_trainer
+    gen = torch.Generator().manual_seed(8)
+    X = torch.rand(64 * 10, 3, 28, 28, generator=gen)
+    y = torch.randint(0, 10, (64 * 10,), generator=gen)
+    loader = DataLoader(TensorDataset(X, y), batch_size=64, shuffle=False, pin_memory=True)
+
+    def make():
+        torch.manual_seed(21)
+        tr = get_clearvae_trainer(1 / 8, True, 5e-4, 16, 1e2, 0.1, torch.device(DEV), "VAE", 3)
+        tr.annealer.loc, tr.annealer.scale = 5, 2      # the KL weight changes every step: a stale slot would be visible
+        tr.use_cuda_graph = True
+        tr.model.train()
+        return tr
+
+    a = make()
+    torch.manual_seed(77)
+    a.fit(1, loader)
+    torch.cuda.synchronize()
+    b = make()
+    torch.manual_seed(77)
+    for xb, yb in loader:
+        b.train_step(xb.to(DEV), yb.to(DEV))
+        torch.cuda.synchronize()
+    assert a.annealer.current_step == b.annealer.current_step == 10
+    sa, sb = a.model.state_dict(), b.model.state_dict()
+    worst = 0.0
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            worst = max(worst, l2(sa[k], sb[k]))
+    assert worst < 2e-3, worst
+    moved = l2(sa["encoder.0.weight"], make().model.state_dict()["encoder.0.weight"])
+    assert moved > 10 * worst      # ... and the ten steps did move the weights by far more than that noise
+
+
+def test_first_graph_step_is_exactly_one_update():
+    """Capturing the step needs eager warm-up runs; they must leave no trace: after the first graphed `train_step` the
+    model has seen ONE update (Adam step counter, BatchNorm `num_batches_tracked`), the CPU generator has drawn what one
+    reference iteration draws, and a second trainer stepping eagerly from the same state lands on the same weights."""
+    from clear_vae_b200.utils.trainer_utils import get_clearmimvae_trainer
+    gen = torch.Generator().manual_seed(12)
+    X = torch.rand(128, 3, 28, 28, generator=gen).to(DEV)
+    y = torch.randint(0, 10, (128,), generator=gen).to(DEV)
+
+    def make():
+        torch.manual_seed(33)
+        tr = get_clearmimvae_trainer(1 / 8, "CLUBSample", 3, 5e-4, 2e-3, 16, 1e2, 0.1, torch.device(DEV), "VAE", 3)
+        tr.model.train()
+        return tr
+
+    a = make()
+    a.use_cuda_graph = True
+    torch.manual_seed(5)
+    a.train_step(X, y)
+    torch.cuda.synchronize()
+    cpu_state_after_graph = torch.get_rng_state()
+    b = make()
+    torch.manual_seed(5)
+    b.train_step(X, y)
+    torch.cuda.synchronize()
+    assert torch.equal(cpu_state_after_graph, torch.get_rng_state())        # one randperm each (CLUB-S), nothing else
+    for tr in (a, b):
+        assert int(tr.model.encoder[1].num_batches_tracked) == 6            # 1 full forward + 5 inner forwards (trainer.py:874-888)
+        assert int(tr.model.decoder[1].num_batches_tracked) == 6
+        st = tr.optimizer.state[next(iter(tr.model.parameters()))]
+        assert float(st["step"]) == 1.0
+        est_p = next(iter(tr.mi_estimator.parameters()))
+        assert float(tr.mi_estimator_optimizer.state[est_p]["step"]) == 5.0
+    # same update up to the noise the two paths draw differently (graph-safe Philox offsets) and fp32 atomics
+    sa, sb = a.model.state_dict(), b.model.state_dict()
+    init = make().model.state_dict()
+    for k in ("encoder.0.weight", "decoder.0.weight", "mu_c.weight"):
+        step_size = l2(sb[k], init[k])
+        assert step_size > 0 and l2(sa[k], sb[k]) < 0.6 * step_size + 1e-12, (k, l2(sa[k], sb[k]), step_size)
