@@ -128,6 +128,10 @@ def run_reference(args):
     cfg = CONFIGS[args.config]
     steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 2))
+    try:    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     sps, ms, cores, note = time_cpu(cfg, steps, warm)
     sample = f"{steps} full steps of batch {cfg['B']} after {warm} warm-up ({note})"
     line = dict(impl="reference", metric="train samples/sec", value=sps, unit="samples/s", n_gpus=args.gpus, steps=steps,

@@ -510,21 +510,7 @@ class ClearMIMVAETrainer(VAETrainer):
             else:   # CPU tensors: the latent op raises (no CPU path), exactly as before
                 dummy = torch.zeros(X.shape[0], dtype=torch.int64, device=X.device)
                 zs = [latent_block([mu_c, mu_s], [lv_c, lv_s], e[2 * j:2 * j + 2], dummy, snn=[0, 0], ps=[0, 0])[0] for j in range(5)]
-        z_est = zs
         d = self.dist
-        if d is not None and d.world > 1:
-            # Data parallel: the five detached latent batches are all-gathered ONCE and every rank runs the (tiny)
-            # estimator updates on the global batch.  The fixed-order reduction of the estimator kernel makes the
-            # gradients bit-identical on all ranks, so the parameters stay in sync without five gradient all-reduces.
-            if d.peer is not None:
-                z_est = d.peer.gather(zs)                                        # five pieces, one kernel, final layout
-            else:
-                import torch.distributed as td
-                loc = torch.stack(zs)                                            # [5, B, 2D]
-                allz = torch.empty((d.world * 5,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
-                td.all_gather_into_tensor(allz, loc, group=d.group)               # rank-major concatenation along dim 0
-                allz = allz.view((d.world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, d.world * loc.shape[1], loc.shape[2])
-                z_est = [allz[j] for j in range(5)]
         # The five estimator updates (two ~10 us launches each, a handful of CTAs) depend only on the latents; the five
         # decoder passes only feed BatchNorm running statistics.  They run as two parallel branches — a side stream in
         # eager mode, a fork/join inside the captured graph — so the small estimator kernels fill SMs the decoder leaves idle.
@@ -532,6 +518,22 @@ class ClearMIMVAETrainer(VAETrainer):
         side = self._side_stream(X.device) if self.overlap_branches else main   # serial mode: per-kernel timing passes
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            z_est = zs
+            if d is not None and d.world > 1:
+                # Data parallel: the five detached latent batches are gathered ONCE and every rank runs the (tiny)
+                # estimator updates on the global batch.  The fixed-order reduction of the estimator kernel makes the
+                # gradients bit-identical on all ranks, so the parameters stay in sync without five gradient all-reduces.
+                # The exchange sits on the estimator branch (the decoder passes do not wait for it); the join below
+                # orders it before the next step's collectives on every rank.
+                if d.peer is not None:
+                    z_est = d.peer.gather(zs)                                        # five pieces, one kernel, final layout
+                else:
+                    import torch.distributed as td
+                    loc = torch.stack(zs)                                            # [5, B, 2D]
+                    allz = torch.empty((d.world * 5,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
+                    td.all_gather_into_tensor(allz, loc, group=d.group)               # rank-major concatenation along dim 0
+                    allz = allz.view((d.world,) + tuple(loc.shape)).permute(1, 0, 2, 3).reshape(5, d.world * loc.shape[1], loc.shape[2])
+                    z_est = [allz[j] for j in range(5)]
             for j in range(5):
                 ll = est.learning_grads(z_est[j][:, :D], z_est[j][:, D:])   # loss + all parameter gradients: one launch
                 fused_adam_step(self.mi_estimator_optimizer)
