@@ -309,3 +309,45 @@ def test_first_graph_step_is_exactly_one_update():
         da, db = (sa[k] - init[k].to(DEV)).double().flatten(), (sb[k] - init[k].to(DEV)).double().flatten()
         assert 0.8 < float(da.norm() / db.norm()) < 1.25, (k, float(da.norm()), float(db.norm()))
         assert float(da @ db / (da.norm() * db.norm())) > 0.3, k
+
+
+@pytest.mark.parametrize("arch", ["VAE", "VAE64"])
+def test_eval_mode_forward_matches_the_torch_modules_and_evaluate_runs(arch):
+    """f-3: `evaluate()` runs the engine in eval mode (running-statistic BatchNorm).  The parameter containers are
+    ordinary torch modules, so calling them directly (cuDNN / cuBLAS, fp32) is an independent reference for the eval-mode
+    forward: latent parameters and reconstruction must agree within the bf16 envelope."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from clear_vae_b200.models.vae import VAE, VAE64
+    from clear_vae_b200.utils.trainer_utils import get_clearvae_trainer
+    torch.manual_seed(9)
+    hw, zdim = (28, 16) if arch == "VAE" else (64, 64)
+    tr = get_clearvae_trainer(1 / 8, True, 5e-4, zdim, 1e2, 0.1, torch.device(DEV), arch, 3)
+    vae = tr.model
+    gen = torch.Generator().manual_seed(2)
+    X = torch.rand(96, 3, hw, hw, generator=gen)
+    y = torch.randint(0, 4, (96,), generator=gen)
+    vae.train()
+    for i in range(3):                      # move the running statistics away from (0, 1)
+        tr.train_step(X[:64].to(DEV), y[:64].to(DEV))
+    vae.eval()
+    with torch.no_grad():
+        xd = X.to(DEV)
+        mu_c, lv_c, mu_s, lv_s = vae.encode(xd)
+        h = vae.encoder(xd)
+        for got, head in ((mu_c, vae.mu_c), (lv_c, vae.logvar_c), (mu_s, vae.mu_s), (lv_s, vae.logvar_s)):
+            want = head(h)
+            assert float((got - want).abs().max()) <= BF16_FWD * float(want.abs().max()) + 2e-3
+        z = torch.cat([mu_c, mu_s], 1)
+        xhat = vae.decode(z)
+        want = vae.decoder(z)
+        assert float((xhat - want).abs().max()) <= 2e-2     # sigmoid output in [0, 1]
+    loader = DataLoader(TensorDataset(X, y), batch_size=32)
+    mig, mse = tr.evaluate(loader, False, 0)
+    assert np.isfinite(mig) and np.isfinite(mse) and mse > 0
+    with torch.no_grad():
+        ref = torch.stack([((vae.decoder(torch.cat([vae.mu_c(vae.encoder(b)), vae.mu_s(vae.encoder(b))], 1)) - b) ** 2).flatten(1).sum(1).mean()
+                           for b in xd.split(32)]).mean()
+    # evaluate() reconstructs from sampled z (eval-mode forward still draws noise, vae.py:81-102), the line above from the
+    # means: same order of magnitude, not equal
+    assert 0.5 < mse / float(ref) < 2.0
+    assert not vae.training
