@@ -95,9 +95,23 @@ def build_ext(verbose=False, force=False):
     return EXT
 
 
+def build_tools(verbose=False, force=False):
+    """tools/mufu_probe: the ex2 throughput probe bench.py runs for the latent-loss roofline denominator."""
+    src = os.path.join(ROOT, "tools", "mufu_probe.cu")
+    out = os.path.join(ROOT, "tools", "mufu_probe")
+    if not os.path.exists(src) or (not force and _newer(out, [src])):
+        return out
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", src, "-o", out]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    _run(cmd)
+    return out
+
+
 def build_all(verbose=False, force=False):
     build_lib(verbose, force)
     build_ext(verbose, force)
+    build_tools(verbose, force)
     return LIB, EXT
 
 
