@@ -8,7 +8,8 @@
 //   phase 1  every CTA copies this rank's pieces into the rank's own slot of its peer buffer, fences system-wide and
 //            arrives on a local counter; the last CTA publishes `seq` to flag[rank] inside every peer's buffer
 //            (st.release.sys over NVLink);
-//   wait     `world` threads per CTA poll the local flags (ld.acquire.sys) until every peer has published `seq`;
+//   wait     `world` threads per CTA poll the local flags (relaxed system-scope loads, then one acquire fence) until every
+//            peer has published `seq`;
 //   phase 2  all threads PULL the peers' slots with volatile 16-byte loads over NVLink and write the final layout:
 //            gather   -> dst[piece][rank][...] (each piece lands as one contiguous [world*B, ...] tensor: no cat / slice),
 //            allreduce-> the element-wise sum in fixed rank order 0..world-1 (bit-identical on every rank) scattered back
@@ -58,11 +59,6 @@ struct ReduceArgs {
   int n;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
