@@ -302,31 +302,7 @@ def test_column_split_shard_against_oracle(sim, tau, D, ps):
         assert np.abs(dmu1[0].cpu().numpy() - got).max() <= 1e-6 * np.abs(wg).max() + 1e-9
 
 
-def _supcon_torch(mu, label, sim, tau, name, ps):
-    """fp64 torch restatement of the two SupCon row losses + finite-row mean (oracle/latent_oracle.py:row_losses, which
-    follows losses.py:140-170), written on the valid rows only so that autograd gives clean gradients."""
-    mu = mu.double()
-    if sim == "cosine":
-        nrm = mu / mu.norm(dim=1, keepdim=True).clamp_min(1e-8)
-        S = nrm @ nrm.T
-    else:
-        S = -((mu[:, None, :] - mu[None, :, :]) ** 2).sum(-1)
-    B = mu.shape[0]
-    eye = torch.eye(B, dtype=torch.bool)
-    m = (label[None, :] == label[:, None]) != bool(ps)
-    pm = m & ~eye
-    cnt = pm.sum(1)
-    if name == "supcon_out_loss":
-        keep = cnt > 0
-        S2 = S.masked_fill(eye, -999.0)
-        val = -(S2 * pm).sum(1)[keep] / cnt[keep] + torch.logsumexp(S2[keep] / tau, dim=1)
-        return val[torch.isfinite(val)].mean()
-    n_k = m.sum(1) - 1
-    keep = (cnt > 0) & (n_k > 0)
-    S2 = S.masked_fill(eye, -float("inf"))[keep]
-    pos = S2.masked_fill(~m[keep], -float("inf"))
-    val = n_k[keep].double().log() - torch.logsumexp(pos / tau, dim=1) + torch.logsumexp(S2 / tau, dim=1)
-    return val[torch.isfinite(val)].mean()
+from tests.helpers import supcon_torch as _supcon_torch  # noqa: E402  (fp64 restatement, pinned to the goldens on the CPU)
 
 
 @pytest.mark.parametrize("name", ["supcon_in_loss", "supcon_out_loss"])

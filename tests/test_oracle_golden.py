@@ -67,6 +67,26 @@ def test_contrastive_gradients_match_reference(golden_dir):
     assert n >= 20
 
 
+def test_supcon_gradient_restatement_matches_reference(golden_dir):
+    """The fp64 autograd restatement the GPU tests use for the SupCon gradients reproduces the reference's own
+    values and `dmu` on the golden cases (the numpy oracle has closed-form gradients for snn_loss only)."""
+    import torch
+    from tests.helpers import supcon_torch
+    n = 0
+    for name, g, sim, tau, ln, ps in _cases(golden_dir):
+        if ln == "snn_loss":
+            continue
+        mu = torch.tensor(g[f"{name}/mu"]).double().requires_grad_(True)
+        val = supcon_torch(mu, torch.tensor(g[f"{name}/label"]), str(sim), tau, str(ln), ps)
+        assert _close(float(val), float(g[f"{name}/loss"]), rel=1e-5, ab=5e-6), name
+        assert _close(float(val), lo.contrastive(g[f"{name}/mu"], g[f"{name}/logvar"], g[f"{name}/label"], sim, tau, ln, ps), rel=1e-9, ab=1e-9)
+        val.backward()
+        want = g[f"{name}/dmu"]
+        assert np.abs(mu.grad.numpy() - want).max() <= 1e-5 * np.abs(want).max() + 1e-8, name
+        n += 1
+    assert n == 4
+
+
 def test_row_drop_semantics(golden_dir):
     g = np.load(os.path.join(golden_dir, "contrastive.npz"))
     # singleton label: +inf row excluded; all rows excluded -> nan
