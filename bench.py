@@ -429,7 +429,7 @@ def main():
     barrier()
     ms_e2e_ev, ms_e2e_wall = t0.elapsed_time(t1) / K, (time.perf_counter() - wall0) * 1e3 / K
     ms_e2e = max(ms_e2e_ev, ms_e2e_wall)
-    assert bool(torch.isfinite(sink[:K, 0]).all()), "e2e read-back holds non-finite losses"
+    e2e_finite = bool(torch.isfinite(sink[:K, 0]).all())   # the read-back really holds every step's loss
     dbg("e2e region done")
     clocks = sampler.stop()   # sampled across both timed regions (device-resident and end-to-end)
     h2d = pool_h[0][0].numel() * 4 + pool_h[0][1].numel() * 8
@@ -499,7 +499,7 @@ def main():
                                 peer_error=(tr.dist.peer.error() if (world > 1 and tr.dist.peer is not None) else None)),
                     clocks=clocks,
                     e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=ms_e2e, ms_per_step_events=ms_e2e_ev, ms_per_step_wall=ms_e2e_wall,
+                             ms_per_step=ms_e2e, ms_per_step_events=ms_e2e_ev, ms_per_step_wall=ms_e2e_wall, losses_finite=e2e_finite,
                              path="VAETrainer.prefetch (H2D of batch i+1 on a copy stream) -> train_step -> async D2H of the "
                                   "step's scalars into pinned memory; region ends when the last read-back has landed"),
                     gpu_launches=launches, gpu_launches_per_step=launches_per_step, kernel_ms_per_step=breakdown,
