@@ -45,7 +45,35 @@ WORKLOAD_NAMES = {
     "clear64": "CLEAR-VAE, synthetic PACS-shaped 3x64x64, batch 128/GPU (BASELINE configs[3])",
 }
 N_POOL = 16  # distinct input batches rotated through the timed region
-CONV_GEMM_DRAM_BYTES_PER_LAUNCH = 11.6e6  # profiles/r1_conv_persist_ncu_raw.csv: mean dram read+write of the 8 captured launches
+SHAPES = {"clear28": "configs[0]", "mim_club": "configs[1]", "mim_l1out": "configs[1]", "tc64": "configs[2]", "clear64": "configs[3]"}
+
+
+def bench_config(name):
+    """`config` of the JSON line — identical on the b200 and the reference arm (same workload, same synthetic batches)."""
+    c = CONFIGS[name]
+    return dict(workload=WORKLOAD_NAMES[name], baseline_config=SHAPES[name], trainer=c["kind"], estimator=c.get("est"), model=c["arch"],
+                total_z_dim=c["z"], image=[c["cin"], c["hw"], c["hw"]], per_gpu_batch=c["B"], n_classes=c["ncls"],
+                hyperparameters=c["hp"], seed=101,
+                l2=f"inputs rotate through {N_POOL} distinct batches ({N_POOL * c['B'] * c['cin'] * c['hw'] ** 2 * 4 / 1e6:.0f} MB"
+                   f"{' > 126 MB L2' if N_POOL * c['B'] * c['cin'] * c['hw'] ** 2 * 4 > 126e6 else ''}); activations and gradients are rewritten every step")
+
+
+def input_pool(cfg, rank=0, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(101 + rank)
+    pool = [(torch.rand(cfg["B"], cfg["cin"], cfg["hw"], cfg["hw"], generator=g), torch.randint(0, cfg["ncls"], (cfg["B"],), generator=g))
+            for _ in range(N_POOL)]
+    return [(x.pin_memory(), y.pin_memory()) for x, y in pool] if pin else pool
+
+
+def ncu_traffic(kernel, config):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r2_ncu_traffic.json, written by
+    tools/ncu_summary.py from the raw CSV: mean of dram__bytes_read.sum + dram__bytes_write.sum over the captured launches)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        return d.get(config, {}).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def peaks():
@@ -104,12 +132,20 @@ def oracle_stepper(cfg, seed=101):
     return lambda: so.step(X, label)
 
 
-def time_cpu(cfg, steps, warmup):
+def time_cpu(cfg, steps, warmup, pool=None):
+    """The reference's own CPU implementation of the step on the host cores: the UNMODIFIED reference staged under oracle/_ref
+    (`kind` "reference") when it travelled with the snapshot, else the oracle port.  Returns (samples/s, ms/step, threads, kind, note)."""
     import torch
+    from oracle import ref_runner as rr
+    if rr.available() and cfg.get("est") != "L1OutUB":
+        pool = pool or input_pool(cfg)
+        sps, ms, _ = rr.time_train(cfg, "cpu", pool, steps, warmup)
+        return sps, ms, torch.get_num_threads(), "reference", ("unmodified reference `get_*_trainer(..., device='cpu')._train(loader, False, 1, ...)` "
+                                                               "(oracle/_ref, staged by oracle/stage_reference.py)")
     if cfg.get("est") == "L1OutUB":
-        note = "closed-form O(B*D) L1OutUB (the reference's own forward is CUDA-only: mi_estimator.py:185)"
+        note = "oracle port with the closed-form O(B*D) L1OutUB (the reference's own forward is CUDA-only: mi_estimator.py:185)"
     else:
-        note = "same step as the GPU arm"
+        note = "oracle port (oracle/model_oracle.py::StepOracle): reference not staged"
     step = oracle_stepper(cfg)
     for _ in range(warmup):
         step()
@@ -117,7 +153,7 @@ def time_cpu(cfg, steps, warmup):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return cfg["B"] / dt, dt * 1e3, torch.get_num_threads(), note
+    return cfg["B"] / dt, dt * 1e3, torch.get_num_threads(), "port", note
 
 
 def run_reference(args):
@@ -126,20 +162,35 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
+    steps, warm = args.steps, max(3, args.warmup)
     try:    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         pass
-    sps, ms, cores, note = time_cpu(cfg, steps, warm)
-    sample = f"{steps} full steps of batch {cfg['B']} after {warm} warm-up ({note})"
+    sps, ms, cores, kind, note = time_cpu(cfg, steps, warm)
+    sample = f"{steps} full steps of batch {cfg['B']} after {warm} warm-up steps; {note}"
     line = dict(impl="reference", metric="train samples/sec", value=sps, unit="samples/s", n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload=WORKLOAD_NAMES[args.config], device="host CPU", threads=cores),
-                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port", sample=sample),
+                data="synthetic", config=bench_config(args.config), impl_config=dict(device="host CPU", threads=cores),
+                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
+
+
+def eager_gpu_baseline(cfg, dev, pool, steps, warmup):
+    """Second same-box comparator: the UNMODIFIED reference in eager PyTorch on the B200 (cuDNN / cuBLAS / ATen),
+    host batches through its own DataLoader -> `.to(device)` path, per-step `float(loss)` synchronisation as written."""
+    import torch
+    from oracle import ref_runner as rr
+    if not rr.available():
+        return dict(unavailable="reference not staged (oracle/_ref missing)")
+    try:
+        sps, ms, _ = rr.time_train(cfg, str(dev), pool, steps, warmup)
+    except Exception as e:
+        return dict(unavailable=repr(e)[:300])
+    return dict(value=sps, unit="samples/s", ms_per_step=ms, steps=steps, warmup=warmup, kind="reference",
+                cudnn_allow_tf32=bool(torch.backends.cudnn.allow_tf32), matmul_allow_tf32=bool(torch.backends.cuda.matmul.allow_tf32),
+                path="unmodified reference get_*_trainer(..., device='cuda:0')._train over a pinned DataLoader (H2D + per-step float() inside)")
 
 
 # --------------------------------------------------------------------------------------
@@ -256,6 +307,29 @@ def latent_roofline(dev, pk):
                 d32=d32, algorithmic="1 ex2 + 2*D (fwd) / 6*D (bwd) flop per pair; HBM bytes O(B*D), negligible")
 
 
+def other_configs(args, K, W, budget_s=420.0):
+    """One summary per remaining BASELINE config (configs[0], [2], [3]) measured by a sub-run of this script on the same GPU:
+    value / e2e / dominant-kernel roofline / CPU and eager-B200 reference comparators, same timing rules as the headline."""
+    out, t0 = [], time.time()
+    for name in ("clear28", "tc64", "clear64"):
+        if name == args.config:
+            continue
+        if time.time() - t0 > budget_s:
+            out.append(dict(config=name, skipped="time budget of the default run"))
+            continue
+        cmd = [sys.executable, os.path.abspath(__file__), "--config", name, "--steps", str(min(K, 20)), "--warmup", str(W), "--sub",
+               "--no-latent", "--precision", args.precision]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            keep = ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "config", "e2e", "gpu_launches_per_step", "roofline",
+                    "cpu_baseline", "eager_gpu_baseline", "parity", "clocks")
+            out.append({k: d.get(k) for k in keep})
+        except Exception as e:
+            out.append(dict(config=name, error=repr(e)[:300]))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,6 +340,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-latent", action="store_true", help="skip the latent-loss roofline point")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-B200 reference comparator")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config summary lines (configs[0], [2], [3]) of the `configs` array")
+    ap.add_argument("--no-parity", action="store_true", help="skip the first-step parity check against the CPU step oracle")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"],
+                    help="conv / linear numerics: bf16 operands (default) or the fp32-grade bf16 x 3 split")
+    ap.add_argument("--sub", action="store_true", help="(internal) a per-config sub-run of the `configs` array")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -288,6 +368,9 @@ def main():
     cfg = CONFIGS[args.config]
     B, K, W = cfg["B"], args.steps, max(3, args.warmup)
     tr = build_trainer(cfg, dev)
+    tr.model.conv_precision = args.precision
+    sampler = ClockSampler(local)     # started before warm-up so the record never comes back empty; covers every timed region
+    sampler.start()
     if world > 1:
         from clear_vae_b200.peer import PeerComm
         peer = PeerComm.create(td.group.WORLD, rank, world, dev)   # None -> NCCL collectives (e.g. IPC mapping unavailable)
@@ -296,10 +379,25 @@ def main():
             td.broadcast(p.data, 0)
     tr.model.train()
 
-    g = torch.Generator().manual_seed(101 + rank)
-    pool_h = [(torch.rand(B, cfg["cin"], cfg["hw"], cfg["hw"], generator=g).pin_memory(),
-               torch.randint(0, cfg["ncls"], (B,), generator=g).pin_memory()) for _ in range(N_POOL)]
+    pool_h = input_pool(cfg, rank, pin=True)
     pool_d = [(x.to(dev), y.to(dev)) for x, y in pool_h]
+
+    # ---- parity gate on the very first step: the CUDA step and the CPU step oracle on the same batch, noise and permutation
+    parity = None
+    if world == 1 and not args.no_parity:
+        from oracle import parity as op
+        res = op.compare_step(tr, cfg, pool_h[0][0], pool_h[0][1])
+        tol = 1e-2 if args.precision == "bf16" else 1e-4
+        checked = {k: v[2] for k, v in res.items() if k in ("recon", "kl_c", "kl_s", "c_loss", "s_loss")}
+        checked.update({k: v[2] for k, v in res.items() if k.startswith("latent/")})
+        gerr = sorted(v[2] for k, v in res.items() if k.startswith("grad/"))
+        parity = dict(oracle="oracle/model_oracle.py::StepOracle (CPU fp32), same batch / eps / permutation", tolerance=tol,
+                      rel_err=checked, mi_loss=res.get("mi_loss", (None, None, None))[:2],
+                      grad_rel_l2=dict(median=gerr[len(gerr) // 2], max=gerr[-1]) if gerr else None,
+                      ok=all(v < tol for v in checked.values()))
+        if not parity["ok"]:
+            print(json.dumps(dict(error="first-step parity check failed", parity=parity)), file=sys.stderr, flush=True)
+            sys.exit(3)
 
     def step_dev(i):
         x, y = pool_d[i % N_POOL]
@@ -391,9 +489,7 @@ def main():
     dbg("eager kernel-timing pass done")
 
     # ---- timed region: device-resident inputs
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
@@ -462,9 +558,9 @@ def main():
                              "(host run-ahead behind a spin kernel, so the pairs bracket device time only)",
                       algorithmic_bytes_per_launch=bytes_step / max(1, dom[0] // K),
                       hbm=dict(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"]))
-        # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r1_conv_persist_ncu_raw.csv: mean of
-        # dram__bytes_read.sum + dram__bytes_write.sum over the conv_gemm launches of one step); null for other kernels
-        traffic = CONV_GEMM_DRAM_BYTES_PER_LAUNCH if (dominant == "conv_gemm" and args.config.startswith("mim")) else None
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this config (profiles/r2_ncu_traffic.json); null if
+        # this kernel / config was not captured
+        traffic = ncu_traffic(dominant, args.config)
         if flops:
             tfs = flops / (per_step_ms * 1e-3) / 1e12
             common["tensor"] = dict(achieved=tfs, peak=pk["tf"], unit="TFLOP/s", frac=tfs / pk["tf"],
@@ -474,13 +570,20 @@ def main():
         else:
             roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=traffic, **common)
 
+    if not e2e_finite:
+        print(json.dumps(dict(error="non-finite loss read back during the end-to-end region")), file=sys.stderr, flush=True)
+        sys.exit(4)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            csteps = 10
-            sps, cms, cores, note = time_cpu(cfg, csteps, 2)
-            cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
-                       sample=f"{csteps} full steps of batch {B} after 2 warm-up on the host ({note}); {cms:.0f} ms/step")
+            slow = cfg["arch"] == "VAE64"
+            csteps, cwarm = (3, 1) if slow else (10, 2)
+            sps, cms, cores, kind, note = time_cpu(cfg, csteps, cwarm, pool_h)
+            cpu = dict(value=sps, unit="samples/s", cores=cores, kind=kind,
+                       sample=f"{csteps} full steps of batch {B} after {cwarm} warm-up on the host; {note}; {cms:.0f} ms/step")
+        eager = None
+        if world == 1 and not args.no_eager_baseline:
+            eager = eager_gpu_baseline(cfg, dev, pool_h, K, W)
         lat = None
         if world == 1 and not args.no_latent:
             try:
@@ -488,22 +591,26 @@ def main():
             except Exception as e:  # never lose the headline line to the side measurement
                 lat = dict(error=repr(e))
         line = dict(metric="train samples/sec", value=world * B / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload=WORKLOAD_NAMES[args.config], per_gpu_batch=B, global_batch=world * B,
-                                parallelism=f"dp{world}", cuda_graph=graphed, l2=f"rotating {N_POOL} distinct input batches "
-                                f"({N_POOL * h2d / 1e6:.0f} MB) > 126 MB L2; activations are rewritten every step",
-                                bn="per-GPU batch statistics", conv_math="bf16 operands, fp32 accumulate (tcgen05)",
-                                latent_math="fp32",
-                                collectives=("none (1 GPU)" if world == 1 else "one-shot peer-memory kernels over NVLink (csrc/peer_comm.cu)"
-                                             if tr.dist.peer is not None else "NCCL"),
-                                peer_error=(tr.dist.peer.error() if (world > 1 and tr.dist.peer is not None) else None)),
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic", config=bench_config(args.config),
+                    impl_config=dict(global_batch=world * B, parallelism=f"dp{world}", cuda_graph=graphed,
+                                     bn="per-GPU batch statistics",
+                                     conv_math=("bf16 operands, fp32 accumulate (tcgen05)" if args.precision == "bf16" else
+                                                "fp32 activations, bf16 x 3 split products, fp32 accumulate (tcgen05)"),
+                                     precision=args.precision, latent_math="fp32",
+                                     collectives=("none (1 GPU)" if world == 1 else "one-shot peer-memory kernels over NVLink (csrc/peer_comm.cu)"
+                                                  if tr.dist.peer is not None else "NCCL"),
+                                     fallbacks="none: missing extension / unsupported discriminator / CPU tensors raise",
+                                     peer_error=(tr.dist.peer.error() if (world > 1 and tr.dist.peer is not None) else None)),
                     clocks=clocks,
                     e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e, ms_per_step_events=ms_e2e_ev, ms_per_step_wall=ms_e2e_wall, losses_finite=e2e_finite,
                              path="VAETrainer.prefetch (H2D of batch i+1 on a copy stream) -> train_step -> async D2H of the "
                                   "step's scalars into pinned memory; region ends when the last read-back has landed"),
                     gpu_launches=launches, gpu_launches_per_step=launches_per_step, kernel_ms_per_step=breakdown,
-                    roofline=roof, latent_roofline=lat, cpu_baseline=cpu)
+                    roofline=roof, latent_roofline=lat, cpu_baseline=cpu, eager_gpu_baseline=eager, parity=parity)
+        if world == 1 and not args.sub and not args.no_configs:
+            line["configs"] = other_configs(args, K, W)
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels keep the communicator busy: tearing the process group down with

@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include "clearvae_b200.h"
+#include "clearvae_b200_debug.h"
 
 #define CV_LOG2E 1.4426950408889634f
 

@@ -64,6 +64,7 @@ struct GemmParams {
   const float *msk_scale, *msk_shift;
   double* stats;
   int splits;  // split-K over grid.z (fp32 atomic epilogue); 1 = off
+  int x3;      // CLEARVAE_ROLE_SPLIT3: every k-block runs three times — (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) — fp32-grade products
   // persistent kernel: flattened (class, n-tile, m-tile) work list
   int tile_start[cvplan::kMaxClasses + 1];
   int n_tiles;
@@ -73,6 +74,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// hi / lo halves of the bf16 x 3 split: x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi)   (|x - hi - lo| <= 2^-17 |x|)
+__device__ __forceinline__ float split_lo(float x) { return x - __bfloat162float(__float2bfloat16(x)); }
 __device__ __forceinline__ float ld_elem(const void* base, long long off, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]) : reinterpret_cast<const float*>(base)[off];
 }
@@ -94,7 +97,7 @@ __device__ __forceinline__ void transpose_reduce32(float (&v)[32]) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ TmapPack tm, const GemmParams p) {
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ TmapPack tm_lo, const GemmParams p) {
   constexpr int kBStage = BN * BK * 2;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
   extern __shared__ unsigned char smem_raw[];
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   const int kb0 = nkb_all * split / p.splits;
   const int nkb = nkb_all * (split + 1) / p.splits - kb0;
   if (nkb <= 0) return;
+  const int nsub = p.x3 ? 3 : 1;          // passes per k-block (split mode: hi*hi, lo*hi, hi*lo)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 4) {
-    if (lane == 0) prefetch_tmap(&tm.t[cls_id]);
+    if (lane == 0) { prefetch_tmap(&tm.t[cls_id]); if (p.x3) prefetch_tmap(&tm_lo.t[cls_id]); }
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // Pure-copy operand (already activated bf16, channels contiguous): cp.async straight into the interleave layout,
     // zero-fill for padding taps / K padding; a k-block is announced two iterations after it was issued, so up to
     // three k-blocks of loads are in flight per thread and nothing is staged through registers.
-    const bool cpa = vec && p.src_bf16 && !has_pre && !p.pre_relu;
+    const bool cpa = vec && p.src_bf16 && !has_pre && !p.pre_relu && !p.x3;
     if (cpa) {
       const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
       for (int kb = 0; kb < nkb; ++kb) {
@@ -216,9 +220,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       mbar_arrive(&full[(nkb - 1) % NS]);
       if (threadIdx.x == 0) CV_TL(3);
     }
-    for (int kb = 0; kb < (cpa ? 0 : nkb); ++kb) {
-      const int s = kb % NS;
+    for (int it = 0; it < (cpa ? 0 : nkb * nsub); ++it) {
+      const int kb = it / nsub, sub = it - kb * nsub;
+      const bool want_lo = sub == 1;        // split mode: the second pass carries the low halves of A
+      const int s = it % NS;
       unsigned char* a_st = sA + s * kAStage;
+      const int t_save = t_cur, c_save = c_cur;
       if (vec) {
         // ---- phase 1: addresses + ALL loads of the k-block in flight (clamped address, masked afterwards)
         uint4 q0[8], q1[8];
@@ -240,7 +247,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
           c_cur += 8;
           if (c_cur >= Cs) { c_cur = 0; ++t_cur; }
         }
-        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
+        if (sub + 1 < nsub) { t_cur = t_save; c_cur = c_save; }   // the next pass walks the same k-block again
         // ---- phase 2: BatchNorm-apply + ReLU (scale/shift from shared memory), bf16 pack, 16-byte stores
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -265,12 +273,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
+          if (want_lo) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = split_lo(v[i]);
+          }
           uint4 out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           if (!ok[j]) out = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) = out;
         }
       } else {
-        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           const int kg = (kb0 + kb) * BK + j * 8;
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             float x = v[i];
             if (has_pre) x = fmaf(x, sScale[chn[i]], sShift[chn[i]]);
             if (p.pre_relu) x = fmaxf(x, 0.f);
+            if (want_lo) x = split_lo(x);
             v[i] = ok[i] ? x : 0.f;
           }
           *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) =
@@ -520,18 +533,19 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   } else if (warp == 4) {
     // ================= B producer: TMA =================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % NS;
-        mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+      for (int it = 0; it < nkb * nsub; ++it) {
+        const int kb = it / nsub, sub = it - kb * nsub;
+        const int s = it % NS;
+        mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], kBStage);
-        tma_load_2d(sB + s * kBStage, &tm.t[cls_id], &full[s], (kb0 + kb) * BK, n0);
+        tma_load_2d(sB + s * kBStage, sub == 2 ? &tm_lo.t[cls_id] : &tm.t[cls_id], &full[s], (kb0 + kb) * BK, n0);
       }
     }
   } else {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nkb * nsub; ++kb) {   // split mode: three passes per k-block, one accumulator
         const int s = kb % NS;
         mbar_wait(&full[s], (kb / NS) & 1);
         tc_fence_after();
@@ -916,6 +930,7 @@ struct WgradParams {
   const void* dy; long long y_n, y_h, y_w, y_c; int dy_bf16;
   float* dw;
   int splits;
+  int x3;   // split mode: every pixel block runs three times — (act_hi, dy_hi), (act_lo, dy_hi), (act_hi, dy_lo)
 };
 
 constexpr int WK = 64;                       // pixels per k-block
@@ -947,6 +962,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
   const long long kb_begin = nkb_total * split / p.splits, kb_end = nkb_total * (split + 1) / p.splits;
   const int nkb = (int)(kb_end - kb_begin);
   if (nkb <= 0) return;
+  const int nsub = p.x3 ? 3 : 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -970,7 +986,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
     const int Nn = p.plan.Nn;
     // both operands are plain bf16 channel runs: cp.async them into the MN-major interleave layout (zero-fill for
     // padding taps / rows past the problem), announcing each k-block two iterations after it was issued
-    const bool cpa = vec && p.src_bf16 && p.pre_scale == nullptr && !p.pre_relu && p.y_c == 1 && p.dy_bf16 && (Nn % 8 == 0);
+    const bool cpa = vec && p.src_bf16 && p.pre_scale == nullptr && !p.pre_relu && p.y_c == 1 && p.dy_bf16 && (Nn % 8 == 0) && !p.x3;
     if (cpa) {
       const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
       const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(p.dy);
@@ -1027,8 +1043,10 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
       fence_proxy_async();
       mbar_arrive(&full[(nkb - 1) % NS]);
     }
-    for (int kb = 0; kb < (cpa ? 0 : nkb); ++kb) {
-      const int s = kb % NS;
+    for (int it = 0; it < (cpa ? 0 : nkb * nsub); ++it) {
+      const int kb = it / nsub, sub = it - kb * nsub;
+      const bool a_lo = sub == 1, b_lo = sub == 2;
+      const int s = it % NS;
       const long long m = (kb_begin + kb) * WK + px;
       const bool mvalid = m < Mc;
       const long long mm = mvalid ? m : 0;
@@ -1086,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
           }
         }
       }
-      mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+      mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
       // ---- phase 2a: A = gathered activation (BatchNorm-apply + ReLU), mn-groups hf*8 .. hf*8+7
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -1113,6 +1131,10 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
+          if (a_lo) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = split_lo(v[i]);
+          }
           if (oka[j]) out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         } else if (mvalid && kidx < Kreal) {
           bool okk[8];
@@ -1134,6 +1156,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
             float x = ld_elem(p.src, off, p.src_bf16);
             if (p.pre_scale != nullptr) x = fmaf(x, sScale[ch], sShift[ch]);
             if (p.pre_relu) x = fmaxf(x, 0.f);
+            if (a_lo) x = split_lo(x);
             v[i] = vld ? x : 0.f;
           }
           (void)okk;
@@ -1149,13 +1172,24 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
           const int n = n0 + grp * 8;
           uint4 out = make_uint4(0u, 0u, 0u, 0u);
           if (dyvec && okb[j]) {
-            if (p.dy_bf16) out = qb0[j];
-            else out = make_uint4(pack_bf16(__uint_as_float(qb0[j].x), __uint_as_float(qb0[j].y)), pack_bf16(__uint_as_float(qb0[j].z), __uint_as_float(qb0[j].w)),
-                                  pack_bf16(__uint_as_float(qb1[j].x), __uint_as_float(qb1[j].y)), pack_bf16(__uint_as_float(qb1[j].z), __uint_as_float(qb1[j].w)));
+            if (p.dy_bf16) {
+              out = b_lo ? make_uint4(0u, 0u, 0u, 0u) : qb0[j];   // a bf16 gradient has no low half
+            } else {
+              float v[8] = {__uint_as_float(qb0[j].x), __uint_as_float(qb0[j].y), __uint_as_float(qb0[j].z), __uint_as_float(qb0[j].w),
+                            __uint_as_float(qb1[j].x), __uint_as_float(qb1[j].y), __uint_as_float(qb1[j].z), __uint_as_float(qb1[j].w)};
+              if (b_lo) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = split_lo(v[i]);
+              }
+              out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
           } else if (mvalid && n < Nn && !(dyvec && n + 8 <= Nn)) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (n + i < Nn) ? ld_elem(p.dy, dy_off + (n + i) * p.y_c, p.dy_bf16) : 0.f;
+            for (int i = 0; i < 8; ++i) {
+              v[i] = (n + i < Nn) ? ld_elem(p.dy, dy_off + (n + i) * p.y_c, p.dy_bf16) : 0.f;
+              if (b_lo) v[i] = split_lo(v[i]);
+            }
             out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
           *reinterpret_cast<uint4*>(b_st + grp * (WK * 16) + px * 16) = out;
@@ -1197,7 +1231,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
   } else if (warp == 5) {
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc(kFmtBF16, 128, BN, 1, 1);  // both operands MN-major
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nkb * nsub; ++kb) {
         const int s = kb % NS;
         mbar_wait(&full[s], (kb / NS) & 1);
         tc_fence_after();
@@ -1222,7 +1256,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
 // ---------------------------------------------------------------------------
 // weight packing: fp32 reference layout -> bf16 [class][n_pad][Kp], zero padded
 // ---------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+__global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo) {
   const Cls& c = plan.cls[blockIdx.y];
   const int n_pad = (plan.Nn + 15) / 16 * 16;
   const long long total = (long long)n_pad * c.Kp;
@@ -1234,6 +1268,7 @@ __global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w,
       v = w[n * plan.ws_n + ch * plan.ws_c + c.wtap[t]];
     }
     out[c.w_off + i] = __float2bfloat16(v);
+    if (out_lo != nullptr) out_lo[c.w_off + i] = __float2bfloat16(split_lo(v));   // split mode: W ~ W_hi + W_lo
   }
 }
 
@@ -1263,7 +1298,7 @@ inline int pick_bn(int Nn) {
 }
 
 template <int BN>
-int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) {
+int launch(const TmapPack& tm, const TmapPack& tm_lo, const GemmParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + 96 /*barriers + tmem slot*/ + kTabMax * 16 + 64 + 2 * kMaxPreC * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1271,7 +1306,7 @@ int launch(const TmapPack& tm, const GemmParams& p, dim3 grid, cudaStream_t st) 
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tm, p);
+  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tm, tm_lo, p);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -1326,8 +1361,8 @@ int clearvae_debug_conv_timeline(long long* device_buffer) {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
-                        const float* pre_shift, int32_t pre_relu, const clearvae_tensor4* dy, float* dweight, void* stream) {
+static int conv_wgrad_impl(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
+                           const float* pre_shift, int32_t pre_relu, const clearvae_tensor4* dy, float* dweight, int x3, void* stream) {
   if (!g || !src || !src->ptr || !dy || !dy->ptr || !dweight || batch <= 0) return CLEARVAE_EINVAL;
   if ((pre_scale == nullptr) != (pre_shift == nullptr)) return CLEARVAE_EINVAL;
   WgradParams p{};
@@ -1340,6 +1375,7 @@ int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearv
   p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu;
   fill_t4(dy, p.dy, p.y_n, p.y_h, p.y_w, p.y_c, p.dy_bf16);
   p.dw = dweight;
+  p.x3 = x3;
   int max_k = 0;
   long long max_m = 0;
   for (int i = 0; i < p.plan.n_classes; ++i) {
@@ -1361,21 +1397,36 @@ int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearv
   }
 }
 
+int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
+                        const float* pre_shift, int32_t pre_relu, const clearvae_tensor4* dy, float* dweight, void* stream) {
+  return conv_wgrad_impl(g, batch, src, pre_scale, pre_shift, pre_relu, dy, dweight, 0, stream);
+}
+int clearvae_conv_wgrad_split3(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src, const float* pre_scale,
+                               const float* pre_shift, int32_t pre_relu, const clearvae_tensor4* dy, float* dweight, void* stream) {
+  return conv_wgrad_impl(g, batch, src, pre_scale, pre_shift, pre_relu, dy, dweight, 1, stream);
+}
+
 size_t clearvae_conv_packed_weight_bytes(const clearvae_conv_geom* g, int32_t role) {
   Plan plan;
-  if (!g || !cvplan::make_plan(*g, role, BK, &plan)) return 0;
-  return (size_t)cvplan::packed_weight_elems(plan) * 2;
+  const int x3 = (role & CLEARVAE_ROLE_SPLIT3) != 0;
+  if (!g || !cvplan::make_plan(*g, role & ~CLEARVAE_ROLE_SPLIT3, BK, &plan)) return 0;
+  // split mode: [hi | lo], the lo half starting at the next 128-byte boundary
+  const size_t one = ((size_t)cvplan::packed_weight_elems(plan) * 2 + 127) / 128 * 128;
+  return x3 ? 2 * one : (size_t)cvplan::packed_weight_elems(plan) * 2;
 }
 
 int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const float* weight, void* packed, void* stream) {
   if (!g || !weight || !packed) return CLEARVAE_EINVAL;
   Plan plan;
-  if (!cvplan::make_plan(*g, role, BK, &plan)) return CLEARVAE_EUNSUPPORTED;
+  const int x3 = (role & CLEARVAE_ROLE_SPLIT3) != 0;
+  if (!cvplan::make_plan(*g, role & ~CLEARVAE_ROLE_SPLIT3, BK, &plan)) return CLEARVAE_EUNSUPPORTED;
   const int n_pad = (plan.Nn + 15) / 16 * 16;
   long long mx = 0;
   for (int i = 0; i < plan.n_classes; ++i) mx = std::max(mx, (long long)n_pad * plan.cls[i].Kp);
   dim3 grid((unsigned)std::min<long long>((mx + 255) / 256, 148 * 8), (unsigned)plan.n_classes);
-  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, weight, reinterpret_cast<__nv_bfloat16*>(packed));
+  const size_t one = ((size_t)cvplan::packed_weight_elems(plan) * 2 + 127) / 128 * 128;
+  __nv_bfloat16* lo = x3 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(packed) + one) : nullptr;
+  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, weight, reinterpret_cast<__nv_bfloat16*>(packed), lo);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -1389,24 +1440,30 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   if ((pre_scale == nullptr) != (pre_shift == nullptr)) return CLEARVAE_EINVAL;
   if ((uintptr_t)packed_weight & 127) return CLEARVAE_EINVAL;
   GemmParams p{};
+  p.x3 = (role & CLEARVAE_ROLE_SPLIT3) != 0;
+  role &= ~CLEARVAE_ROLE_SPLIT3;
   if (!cvplan::make_plan(*g, role, BK, &p.plan)) return CLEARVAE_EUNSUPPORTED;
   if (pre_scale != nullptr && p.plan.Cs > kMaxPreC) return CLEARVAE_EUNSUPPORTED;
   EncodeTiledFn enc = get_encode();
   if (!enc) return CLEARVAE_EUNSUPPORTED;
   const int BN = pick_bn(p.plan.Nn);
   const int n_pad = (p.plan.Nn + 15) / 16 * 16;
-  TmapPack tm{};
+  TmapPack tm{}, tm_lo{};
   long long max_m = 0;
+  const size_t lo_off = ((size_t)cvplan::packed_weight_elems(p.plan) * 2 + 127) / 128 * 128;   // split mode: [hi | lo]
   for (int i = 0; i < p.plan.n_classes; ++i) {
     const Cls& c = p.plan.cls[i];
     cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)c.Kp * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    void* base = (void*)(reinterpret_cast<const char*>(packed_weight) + (size_t)c.w_off * 2);
-    CUresult r = enc(&tm.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return CLEARVAE_EINVAL;
+    for (int h = 0; h < (p.x3 ? 2 : 1); ++h) {
+      void* base = (void*)(reinterpret_cast<const char*>(packed_weight) + (size_t)c.w_off * 2 + (h ? lo_off : 0));
+      CUresult r = enc(h ? &tm_lo.t[i] : &tm.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return CLEARVAE_EINVAL;
+    }
     max_m = std::max(max_m, (long long)batch * c.Hd * c.Wd);
   }
   p.batch = batch;
@@ -1438,7 +1495,7 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   // common case -> persistent warp-specialised kernel (see conv_tc_persist_kernel)
   static const bool no_persist = getenv("CLEARVAE_NO_PERSIST") != nullptr;
   const bool masked = epilogue != CLEARVAE_EPI_BIAS_STATS;
-  if (!no_persist && p.splits == 1 && p.src_bf16 && p.s_c == 1 && p.plan.Cs % 8 == 0 && pre_scale == nullptr && !pre_relu &&
+  if (!no_persist && !p.x3 && p.splits == 1 && p.src_bf16 && p.s_c == 1 && p.plan.Cs % 8 == 0 && pre_scale == nullptr && !pre_relu &&
       p.d_c == 1 && p.plan.Nn % BN == 0 && ((p.d_n | p.d_h | p.d_w) & 7) == 0 && !((uintptr_t)p.src & 15) &&
       ((p.s_n | p.s_h | p.s_w) & 7) == 0 && !((uintptr_t)p.dst & 15) &&
       (!masked || (p.m_c == 1 && ((p.m_n | p.m_h | p.m_w) & 7) == 0 && !((uintptr_t)p.msk & 15)))) {
@@ -1461,10 +1518,10 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   }
   dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)((n_pad + BN - 1) / BN), (unsigned)(p.plan.n_classes * p.splits));
   switch (BN) {
-    case 16: return launch<16>(tm, p, grid, st);
-    case 32: return launch<32>(tm, p, grid, st);
-    case 64: return launch<64>(tm, p, grid, st);
-    default: return launch<128>(tm, p, grid, st);
+    case 16: return launch<16>(tm, tm_lo, p, grid, st);
+    case 32: return launch<32>(tm, tm_lo, p, grid, st);
+    case 64: return launch<64>(tm, tm_lo, p, grid, st);
+    default: return launch<128>(tm, tm_lo, p, grid, st);
   }
 }
 

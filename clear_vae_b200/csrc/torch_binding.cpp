@@ -301,15 +301,15 @@ void conv_gemm(at::IntArrayRef geom, int64_t role, int64_t batch, const Tensor& 
 }
 
 void conv_wgrad(at::IntArrayRef geom, int64_t batch, const Tensor& src, at::IntArrayRef src_strides, const OptTensor& pre_scale,
-                const OptTensor& pre_shift, bool pre_relu, const Tensor& dy, at::IntArrayRef dy_strides, Tensor dweight) {
+                const OptTensor& pre_shift, bool pre_relu, const Tensor& dy, at::IntArrayRef dy_strides, Tensor dweight, bool split3) {
   const c10::cuda::CUDAGuard guard(src.device());
   auto g = geom_from(geom);
   auto s4 = t4(src, src_strides, "src");
   auto y4 = t4(dy, dy_strides, "dy");
   check_f32(dweight, "dweight");
   TORCH_CHECK(dweight.numel() == (int64_t)g.Cin * g.Cout * g.k * g.k, "clearvae: dweight size does not match the geometry");
-  check_rc(clearvae_conv_wgrad(&g, batch, &s4, optf(pre_scale, "pre_scale"), optf(pre_shift, "pre_shift"), pre_relu ? 1 : 0, &y4,
-                               dweight.data_ptr<float>(), cur_stream()),
+  check_rc((split3 ? clearvae_conv_wgrad_split3 : clearvae_conv_wgrad)(&g, batch, &s4, optf(pre_scale, "pre_scale"), optf(pre_shift, "pre_shift"),
+                                                                       pre_relu ? 1 : 0, &y4, dweight.data_ptr<float>(), cur_stream()),
            "conv_wgrad");
 }
 
@@ -753,7 +753,7 @@ TORCH_LIBRARY(clearvae, m) {
         "Tensor mask_src, int[] mask_strides, Tensor? mask_scale, Tensor? mask_shift, Tensor(b!)? stats) -> bool");
   m.def("fc_fwd(Tensor z, Tensor weight, Tensor? bias, Tensor(a!) out, Tensor(b!)? stats) -> bool");
   m.def("conv_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
-        "Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> ()");
+        "Tensor dy, int[] dy_strides, Tensor(a!) dweight, bool split3=False) -> ()");
   m.def("bn_finalize(Tensor(a!) stats, int C, int group, float count, Tensor? gamma, Tensor? beta, Tensor(b!)? running_mean, "
         "Tensor(c!)? running_var, float momentum, float eps, int expand, int repeat) -> (Tensor, Tensor, Tensor, Tensor)");
   m.def("bn_reduce(Tensor y, Tensor? g, Tensor? act, Tensor? mask_scale, Tensor? mask_shift, int C, int inner, int mode, Tensor(a!) stats) -> ()");

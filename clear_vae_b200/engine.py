@@ -141,8 +141,8 @@ class EncoderFn(torch.autograd.Function):
             # boundary layer (Cin <= 4): direct CUDA-core kernel; everything else: tcgen05 implicit GEMM
             if not (i == 0 and eng.use_direct and ops.conv_direct_fwd(sp.geom, B, src, src_strides, None, None, False,
                                                                       w.detach(), b.detach(), raw, dst_strides, st)):
-                pw = eng.packs.get(("enc", i), w, sp.geom, FPROP)
-                ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                pw = eng.packs.get(("enc", i), w, sp.geom, eng.role(FPROP))
+                ops.conv_gemm(sp.geom, eng.role(FPROP), B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
                               pre is not None, pw, b, raw, dst_strides, EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
             mat = eng.materialize and raw.dtype == torch.bfloat16
             act = None
@@ -177,8 +177,8 @@ class EncoderFn(torch.autograd.Function):
         N = heads_w.shape[0]
         lat = torch.empty(B, N, dtype=torch.float32, device=dev)
         hg = linear_geom(K, N)
-        pw = eng.packs.get("heads", heads_w, hg, FPROP, cacheable=False)
-        ops.conv_gemm(hg, FPROP, B, src, [K, 0, 0, 1], pre[0] if pre else None, pre[1] if pre else None, pre is not None, pw,
+        pw = eng.packs.get("heads", heads_w, hg, eng.role(FPROP), cacheable=False)
+        ops.conv_gemm(hg, eng.role(FPROP), B, src, [K, 0, 0, 1], pre[0] if pre else None, pre[1] if pre else None, pre is not None, pw,
                       heads_b, lat, [N, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
         if eng.debug is not None:
             eng.debug["enc_raw"] = [r for r, _ in saved_raw]
@@ -209,15 +209,15 @@ class EncoderFn(torch.autograd.Function):
         with eng.wgrad_branch(dev):
             d_heads_w = torch.zeros_like(heads_w)
             if saved_act[-1] is not None:
-                ops.conv_wgrad(hg, B, saved_act[-1], [K, 0, 0, 1], None, None, False, dlat, [N, 0, 0, 1], d_heads_w)
+                ops.conv_wgrad(hg, B, saved_act[-1], [K, 0, 0, 1], None, None, False, dlat, [N, 0, 0, 1], d_heads_w, eng.x3)
             else:
-                ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w)
+                ops.conv_wgrad(hg, B, raw_last, [K, 0, 0, 1], sc_last, sh_last, True, dlat, [N, 0, 0, 1], d_heads_w, eng.x3)
             d_heads_b = ops.colsum(dlat)
         # heads: data gradient with the last block's ReLU mask + BatchNorm sums in the epilogue
         g = torch.empty(B, K, dtype=eng.grad_dtype, device=dev)
         st = eng.stat_buf(("enc_b", n - 1), K, dev)
-        pw = eng.packs.get("heads", heads_w, hg, DGRAD, cacheable=False)
-        ops.conv_gemm(hg, DGRAD, B, dlat, [N, 0, 0, 1], None, None, False, pw, None, g, [K, 0, 0, 1], EPI_MASK_STATS,
+        pw = eng.packs.get("heads", heads_w, hg, eng.role(DGRAD), cacheable=False)
+        ops.conv_gemm(hg, eng.role(DGRAD), B, dlat, [N, 0, 0, 1], None, None, False, pw, None, g, [K, 0, 0, 1], EPI_MASK_STATS,
                       raw_last, [K, 0, 0, 1], sc_last, sh_last, st)
         grads = [None] * len(params)
         for i in range(n - 1, -1, -1):
@@ -233,7 +233,7 @@ class EncoderFn(torch.autograd.Function):
             if nw > 1:  # sums were global: undo the later rank-averaging's double count of the affine grads
                 dgamma, dbeta = dgamma / nw, dbeta / nw
             # the last block's tensors are channel-major (flatten order of the heads); its dy is written channels-last
-            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, last, BF16)
+            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, group, last, eng.dy_code())
             if last:
                 raw_strides = nhwc_strides(H, H, sp.cout)
             if i == 0:
@@ -247,17 +247,17 @@ class EncoderFn(torch.autograd.Function):
                 if i == 0 and eng.use_direct and ops.conv_direct_wgrad(sp.geom, B, src, src_strides, dy, raw_strides, dw):
                     pass  # Cin <= 4: register-blocked CUDA-core kernel
                 elif i > 0 and saved_act[i - 1] is not None:
-                    ops.conv_wgrad(sp.geom, B, saved_act[i - 1], src_strides, None, None, False, dy, raw_strides, dw)
+                    ops.conv_wgrad(sp.geom, B, saved_act[i - 1], src_strides, None, None, False, dy, raw_strides, dw, eng.x3)
                 else:
                     ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
-                                   pre is not None, dy, raw_strides, dw)
+                                   pre is not None, dy, raw_strides, dw, eng.x3)
             grads[4 * i], grads[4 * i + 2], grads[4 * i + 3] = dw, dgamma, dbeta
             # grads[4*i+1] (conv bias) stays None: a bias feeding a train-mode BatchNorm has exactly zero gradient
             if i > 0:
                 g = torch.empty(B, sp.hin, sp.hin, sp.cin, dtype=eng.grad_dtype, device=dev)
                 st = eng.stat_buf(("enc_b", i - 1), sp.cin, dev)
-                pwd = eng.packs.get(("enc", i), w, sp.geom, DGRAD)
-                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, pwd, None, g, nhwc_strides(sp.hin, sp.hin, sp.cin),
+                pwd = eng.packs.get(("enc", i), w, sp.geom, eng.role(DGRAD))
+                ops.conv_gemm(sp.geom, eng.role(DGRAD), B, dy, raw_strides, None, None, False, pwd, None, g, nhwc_strides(sp.hin, sp.hin, sp.cin),
                               EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
         eng.wgrad_join(dev)
         del keep
@@ -283,7 +283,7 @@ class DecoderFn(torch.autograd.Function):
         raw_fc = torch.empty(B, N0, dtype=torch.float32, device=dev)
         st = eng.stat_buf(("dec_fc",), N0, dev) if eng.training else None
         if not (eng.use_direct and ops.fc_fwd(z, fc_w.detach(), fc_b.detach(), raw_fc, st)):   # K = 2D <= 64: fp32 CUDA-core kernel
-            ops.conv_gemm(fg, FPROP, B, z, [K0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, FPROP), fc_b, raw_fc,
+            ops.conv_gemm(fg, eng.role(FPROP), B, z, [K0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, eng.role(FPROP)), fc_b, raw_fc,
                           [N0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, st)
         rm, rv = eng.dec_fc_buffers
         C0, H0 = specs[0].cin, specs[0].hin
@@ -321,8 +321,8 @@ class DecoderFn(torch.autograd.Function):
                                         pre is not None, w.detach(), b.detach(), raw, dst_strides, st)):
                 if raw.numel() == 0:
                     raw = torch.empty(B, sp.cout, H, H, dtype=torch.float32, device=dev)
-                ops.conv_gemm(sp.geom, FPROP, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
-                              pre is not None, eng.packs.get(("dec", j), w, sp.geom, FPROP), b, raw, dst_strides, EPI_BIAS_STATS,
+                ops.conv_gemm(sp.geom, eng.role(FPROP), B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
+                              pre is not None, eng.packs.get(("dec", j), w, sp.geom, eng.role(FPROP)), b, raw, dst_strides, EPI_BIAS_STATS,
                               None, [0, 0, 0, 0], None, None, st)
             mat = eng.materialize and not last and raw.dtype == torch.bfloat16
             act = None
@@ -399,7 +399,7 @@ class DecoderFn(torch.autograd.Function):
             coef, dgamma, dbeta = ops.bn_bwd_coef(st, sp.cout, 1, float(nw * B * H * H), gamma, mean, invstd)
             if nw > 1:
                 dgamma, dbeta = dgamma / nw, dbeta / nw
-            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, False, BF16)
+            dy = ops.bn_bwd_apply(g, raw, None, None, None, coef, sp.cout, inner, False, eng.dy_code())
             if j == 0:
                 src, src_strides, pre = a_fc, nhwc_strides(sp.hin, sp.hin, sp.cin), None
             else:
@@ -412,10 +412,10 @@ class DecoderFn(torch.autograd.Function):
                         ops.conv_direct_wgrad(sp.geom, B, saved_act[j - 1], src_strides, dy, raw_strides, dw)):
                     pass  # Cout <= 4: register-blocked CUDA-core kernel
                 elif j > 0 and saved_act[j - 1] is not None:
-                    ops.conv_wgrad(sp.geom, B, saved_act[j - 1], src_strides, None, None, False, dy, raw_strides, dw)
+                    ops.conv_wgrad(sp.geom, B, saved_act[j - 1], src_strides, None, None, False, dy, raw_strides, dw, eng.x3)
                 else:
                     ops.conv_wgrad(sp.geom, B, src, src_strides, pre[0] if pre else None, pre[1] if pre else None,
-                                   pre is not None, dy, raw_strides, dw)
+                                   pre is not None, dy, raw_strides, dw, eng.x3)
             grads[4 * j], grads[4 * j + 2], grads[4 * j + 3] = dw, dgamma, dbeta
             if j > 0:
                 g = torch.empty(B, sp.hin, sp.hin, sp.cin, dtype=eng.grad_dtype, device=dev)
@@ -424,13 +424,13 @@ class DecoderFn(torch.autograd.Function):
                 if not (last and eng.use_direct and ops.conv_direct_dgrad(sp.geom, B, dy, raw_strides, w.detach(), g,
                                                                           nhwc_strides(sp.hin, sp.hin, sp.cin), src, src_strides,
                                                                           pre[0], pre[1], st)):
-                    ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, eng.packs.get(("dec", j), w, sp.geom, DGRAD),
+                    ops.conv_gemm(sp.geom, eng.role(DGRAD), B, dy, raw_strides, None, None, False, eng.packs.get(("dec", j), w, sp.geom, eng.role(DGRAD)),
                                   None, g, nhwc_strides(sp.hin, sp.hin, sp.cin), EPI_MASK_STATS, src, src_strides, pre[0], pre[1], st)
             else:
                 # gradient w.r.t. the activated fc output, channel-major like a_fc
                 N0 = fc_w.shape[0]
                 g_a = torch.empty(B, N0, dtype=torch.float32, device=dev)
-                ops.conv_gemm(sp.geom, DGRAD, B, dy, raw_strides, None, None, False, eng.packs.get(("dec", j), w, sp.geom, DGRAD), None, g_a,
+                ops.conv_gemm(sp.geom, eng.role(DGRAD), B, dy, raw_strides, None, None, False, eng.packs.get(("dec", j), w, sp.geom, eng.role(DGRAD)), None, g_a,
                               nchw_strides(sp.cin, sp.hin, sp.hin), EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
         # fc block: BatchNorm1d + ReLU backward, then Linear
         K0, N0 = fc_w.shape[1], fc_w.shape[0]
@@ -445,9 +445,9 @@ class DecoderFn(torch.autograd.Function):
         keep.append(dy_fc)
         with eng.wgrad_branch(dev):
             d_fc_w = torch.zeros_like(fc_w)
-            ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w)
+            ops.conv_wgrad(fg, B, z, [K0, 0, 0, 1], None, None, False, dy_fc, [N0, 0, 0, 1], d_fc_w, eng.x3)
         dz = torch.empty(B, K0, dtype=torch.float32, device=dev)
-        ops.conv_gemm(fg, DGRAD, B, dy_fc, [N0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, DGRAD), None, dz,
+        ops.conv_gemm(fg, eng.role(DGRAD), B, dy_fc, [N0, 0, 0, 1], None, None, False, eng.packs.get("fc", fc_w, fg, eng.role(DGRAD)), None, dz,
                       [K0, 0, 0, 1], EPI_BIAS_STATS, None, [0, 0, 0, 0], None, None, None)
         eng.wgrad_join(dev)
         del keep
@@ -474,10 +474,31 @@ class Engine:
         self.materialize = True  # write relu(bn(raw)) once in bf16 so the GEMM operand loads are pure cp.async copies
         self.overlap_wgrad = True  # weight gradients on a side stream, overlapping the data-gradient chain
         self._side = {}
+        self.x3 = False          # fp32-grade convolutions: bf16 x 3 split products on fp32 activations (set_precision)
         self.momentum = BN_MOMENTUM   # running-statistic momentum of the decoder forwards (1.0 inside parallel stat branches)
         self.stat_tag = 0             # statistic-accumulator set: concurrent decoder passes must not share accumulators
         self.parallel_stats = True    # CLEAR-MIM's statistics-only decoder passes as parallel graph branches
         self._branch = {}
+
+    # ---- numerics ------------------------------------------------------------------------------------------
+    def set_precision(self, mode: str):
+        """'bf16' (default): bf16 activations / operands, fp32 accumulation — the fast path.
+        'fp32x3': fp32 activations and gradients in HBM, every tensor-core product as hi*hi + lo*hi + hi*lo of the bf16 split
+        of both operands (CLEARVAE_ROLE_SPLIT3) — the accuracy class of the reference's fp32 run, ~3x the MMA work."""
+        if mode not in ("bf16", "fp32x3"):
+            raise ValueError("precision must be 'bf16' or 'fp32x3'")
+        x3 = mode == "fp32x3"
+        if x3 != self.x3:
+            self.x3 = x3
+            self.act_dtype = torch.float32 if x3 else torch.bfloat16
+            self.materialize = not x3
+            self.packs = _PackCache()
+
+    def role(self, r):
+        return r | 16 if self.x3 else r
+
+    def dy_code(self):
+        return F32 if self.x3 else BF16
 
     # ---- weight-gradient branch -----------------------------------------------------------------------------
     # dW of a block needs only that block's dy and input activation, while the data-gradient chain continues to the
@@ -533,7 +554,7 @@ class Engine:
             last = j == len(specs) - 1
             if last and self.use_direct and j > 0:
                 continue   # direct CUDA-core kernel reads the fp32 master
-            self.packs.get(("dec", j), params[4 * j], sp.geom, FPROP)
+            self.packs.get(("dec", j), params[4 * j], sp.geom, eng.role(FPROP))
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev, self.stat_tag)

@@ -36,6 +36,9 @@ class VAE(nn.Module):
     """Weakly-supervised VAE with content / style latent halves (reference vae.py:7-102)."""
 
     _K, _ENC, _DEC, _UNFLAT, _OUT_PADS, _IMG = 3, (32, 64, 128), (128, 64, 32), (128, 4, 4), (0, 1, 1), 28
+    # numerics of the conv / linear stacks: "bf16" (fast path: bf16 operands, fp32 accumulate) or "fp32x3" (fp32 activations,
+    # bf16 x 3 split products on the tensor cores — fp32-grade, for parity runs against the reference's fp32 arithmetic)
+    conv_precision = "bf16"
 
     def __init__(self, total_z_dim, in_channel: int = 1, group_mode: str | None = None) -> None:
         super().__init__()
@@ -78,6 +81,7 @@ class VAE(nn.Module):
                 h = sp.hout
             self._engine = Engine(enc_specs, dec_specs)
         e = self._engine
+        e.set_precision(self.conv_precision)
         e.training = self.training
         e.dist, e.sync_bn = getattr(self, "dist", None), bool(getattr(self, "sync_bn", False))
         e.enc_buffers = [(self.encoder[s.bn].running_mean, self.encoder[s.bn].running_var) for s in e.enc_specs]

@@ -29,17 +29,14 @@ def _plain_adam(opt, group) -> bool:
 def _build(opt, gi, group, params):
     dev = params[0].device
     steps = torch.zeros(len(params), dtype=torch.float32, device=dev)
-    old = []
+    old = [float(opt.state[p]["step"]) if len(opt.state[p]) else 0.0 for p in params]
+    if len(set(old)) != 1:
+        return None  # parameters with different histories: leave this group to torch (state untouched)
     for p in params:
         st = opt.state[p]
         if len(st) == 0:
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            old.append(0.0)
-        else:
-            old.append(float(st["step"]))
-    if len(set(old)) != 1:
-        return None  # parameters with different histories: leave this group to torch
     steps.fill_(old[0])
     for i, p in enumerate(params):
         opt.state[p]["step"] = steps[i]  # 0-dim views of one buffer: the kernel advances all of them together
@@ -65,6 +62,15 @@ def fused_adam_step(opt, grad_scale: float = 1.0) -> None:
                for p in params):
             raise RuntimeError("clear_vae_b200.fused_adam_step: contiguous CUDA fp32 parameters required (no CPU path)")
         ent = per_opt.get(gi)
+        if ent is not None and not torch.cuda.is_current_stream_capturing():
+            # `load_state_dict` replaces the per-parameter `step` tensors: an entry whose counters are no longer the ones the
+            # optimiser holds is stale (bias correction would keep using the pre-load count) -> rebuild from the loaded state
+            lo, hi = ent["steps"].data_ptr(), ent["steps"].data_ptr() + 4 * ent["steps"].numel()
+            for p in params:
+                stp = opt.state[p].get("step") if len(opt.state[p]) else None
+                if not (torch.is_tensor(stp) and stp.is_cuda and lo <= stp.data_ptr() < hi):
+                    ent = None
+                    break
         if ent is None or ent["key"] != tuple(id(p) for p in params):
             ent = _build(opt, gi, group, params)
             if ent is None:

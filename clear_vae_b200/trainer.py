@@ -14,7 +14,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.optim.optimizer import Optimizer
 from torch.utils.data import DataLoader
 from tqdm import tqdm
@@ -100,6 +99,9 @@ class DevicePrefetcher:
             slots = self._slots[key] = [(torch.empty(X.shape, dtype=X.dtype, device=self.device),
                                          torch.empty(label.shape, dtype=torch.int64, device=self.device))
                                         for _ in range(self.NSLOT)]
+            # the caching allocator may hand back blocks that kernels already queued on the consumer's stream still read
+            # (e.g. the previous epoch's slots): the first copies into a new slot set are ordered after that stream
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         k = i % self.NSLOT
         Xd, ld = slots[k]
         if self._consumed[k] is not None:
@@ -123,6 +125,11 @@ class DevicePrefetcher:
 
     def __iter__(self):
         pending, i = None, 0
+        if self.enabled:
+            # a new pass over the slots (next epoch): the last two steps of the previous pass never recorded a
+            # "consumed" event, so order this pass's copies after everything the consumer has queued so far
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._consumed = [None] * self.NSLOT
         for batch in self.batches:
             if self.enabled and i >= 2:   # the consumer has enqueued its step on batch i-2 (the one before `pending`)
                 e = torch.cuda.Event()
@@ -139,8 +146,13 @@ class DevicePrefetcher:
 
 class VAETrainer(Trainer):
     def prefetch(self, batches):
-        """device batches of `batches` with the H2D copy of the next batch overlapped with the current step"""
-        return DevicePrefetcher(batches, self.device, self.transform)
+        """device batches of `batches` with the H2D copy of the next batch overlapped with the current step.  One prefetcher
+        (its copy stream and device slots) lives on the trainer across epochs."""
+        pf = getattr(self, "_prefetcher", None)
+        if pf is None or pf.device != torch.device(self.device) or pf.transform is not self.transform:
+            pf = self._prefetcher = DevicePrefetcher(batches, self.device, self.transform)
+        pf.batches = batches
+        return pf
 
     def _valid(self, dataloader, verbose, epoch_id):
         if verbose:
@@ -228,7 +240,11 @@ class VAETrainer(Trainer):
     def _graph_step(self, X, label):
         g = self._graph
         if g is None or g["X"].shape != X.shape:
-            g = self._capture(X, label)
+            cache = self.__dict__.setdefault("_graphs", {})   # one captured graph per input shape (partial last batches)
+            g = cache.get(tuple(X.shape))
+            if g is None or self._graph is None:
+                g = cache[tuple(X.shape)] = self._capture(X, label)
+            self._graph = g
         g["X"].copy_(X, non_blocking=True)
         g["label"].copy_(label, non_blocking=True)
         if g["perm"] is not None:  # CLUB-S: the CPU generator draws the permutation exactly like the reference
@@ -406,30 +422,21 @@ class ClearTCVAETrainer(VAETrainer):
     def _device_step(self, X, label, eps=None, eps2=None):
         vae, fc, hp = self.model, self.factor_cls, self.hyperparameter
         from . import tc
-        fp = tc.fused_params(fc) if X.is_cuda else None   # the reference's 2-layer discriminator -> one launch per use
+        fp = tc.fused_params(fc)   # the reference's 2-layer discriminator -> one launch per use
+        if fp is None:
+            raise RuntimeError("clear_vae_b200: factor_cls must be the reference's Linear(Z,Z)-ReLU-Linear(Z,1)-Sigmoid on the GPU with "
+                               "Z <= 64 (trainer_utils.py:133-138); there is no eager fallback for other discriminators")
         # --- VAE update (trainer.py:654-677)
         self.optimizer.zero_grad()
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
                                                         sim_fn=self.sim_fn, eps=eps, dist=self.dist)
-        if fp is not None:
-            mi = tc.tc_bound(z, fp)
-        else:
-            d_score = fc(z)
-            mi = F.relu(torch.log(d_score / (1 - d_score))).mean()
+        mi = tc.tc_bound(z, fp)
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
-        if fp is not None:
-            factor_loss = tc.disc_grads(z2, fp)
-        else:
-            self.factor_optimizer.zero_grad()
-            d_joint = fc(z2)
-            d_marg = fc(factor_shuffling(z2))
-            factor_loss = F.binary_cross_entropy(torch.cat([d_joint, d_marg], 0),
-                                                 torch.cat([torch.ones_like(d_joint), torch.zeros_like(d_marg)], 0))
-            factor_loss.backward()
+        factor_loss = tc.disc_grads(z2, fp)
         fused_adam_step(self.factor_optimizer, self._sync_grads(list(fc.parameters())))
         return recon, sc, mi.detach(), factor_loss.detach()
 

@@ -38,8 +38,6 @@ enum { CLEARVAE_SIM_COSINE = 0, CLEARVAE_SIM_L2 = 1, CLEARVAE_SIM_MODIFIED_L2 = 
 enum { CLEARVAE_LOSS_SNN = 0, CLEARVAE_LOSS_SUPCON_IN = 1, CLEARVAE_LOSS_SUPCON_OUT = 2 };
 
 int clearvae_version(void);
-/* tuning / test hook: minimum local batch for the tensor-core (tcgen05) latent forward; default 4096 */
-void clearvae_set_latent_tc_min_rows(int32_t rows);
 
 /* ---------------------------------------------------------------------------
  * Latent-head loss block.
@@ -170,6 +168,11 @@ typedef struct {
 } clearvae_tensor4;
 enum { CLEARVAE_F32 = 0, CLEARVAE_BF16 = 1 };
 enum { CLEARVAE_ROLE_FPROP = 0, CLEARVAE_ROLE_DGRAD = 1 };
+/* OR into `role` of clearvae_conv_packed_weight_bytes / clearvae_conv_pack_weight / clearvae_conv_gemm: fp32-grade products on
+ * the bf16 tensor cores ("bf16 x 3").  Each fp32 operand x is split as x ~ hi + lo (hi = bf16(x), lo = bf16(x - hi)) and
+ * hi*hi + lo*hi + hi*lo is accumulated in fp32 (TMEM): ~2^-17 relative error per product instead of 2^-9 — the accuracy class
+ * of the reference's own fp32 GPU run (cudnn.allow_tf32 = False).  The packed weight holds [hi | lo] (twice the bytes). */
+#define CLEARVAE_ROLE_SPLIT3 16
 /* epilogue of clearvae_conv_gemm */
 enum { CLEARVAE_EPI_BIAS_STATS = 0,  /* dst = acc + bias; stats += (sum v, sum v^2) per output channel      */
        CLEARVAE_EPI_MASK_STATS = 1   /* dst = g = acc * [mask_src*mask_scale+mask_shift > 0];
@@ -192,6 +195,11 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
 int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src,
                         const float* pre_scale, const float* pre_shift, int32_t pre_relu,
                         const clearvae_tensor4* dy, float* dweight, void* stream);
+
+/* the same weight gradient in split mode (see CLEARVAE_ROLE_SPLIT3): both operands hi + lo, three products per pixel block */
+int clearvae_conv_wgrad_split3(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src,
+                               const float* pre_scale, const float* pre_shift, int32_t pre_relu,
+                               const clearvae_tensor4* dy, float* dweight, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Train-mode BatchNorm around the GEMMs (nn.BatchNorm1d/2d at vae.py:17-44,115-154).
@@ -267,10 +275,6 @@ int clearvae_conv_direct_dgrad(const clearvae_conv_geom* g, int64_t batch, const
  * `stats` (optional, 2*N doubles) accumulates the BatchNorm1d batch moments (sum, sum of squares) of every column */
 int clearvae_fc_fwd(const float* z, const float* weight, const float* bias, float* out, double* stats, int64_t B, int32_t K,
                     int32_t N, void* stream);
-
-/* profiling hook (tools/conv_timeline.py): when non-NULL, every CTA of clearvae_conv_gemm writes 8 int64
- * %globaltimer stamps (start, prologue done, loads issued, loads landed, accumulator ready, epilogue done, exit) */
-int clearvae_debug_conv_timeline(long long* device_buffer);
 
 /* ---------------------------------------------------------------------------
  * Variational MI estimators of CLEAR-MIM (mi_estimator.py:108-198): Gaussian heads
@@ -354,8 +358,6 @@ int clearvae_peer_export(void* ptr, uint8_t* handle_host);
 int clearvae_peer_open(const uint8_t* handle_host, void** ptr);
 int clearvae_peer_close(void* ptr);
 int clearvae_peer_error(const void* local_base, int32_t* err_host);
-/* debug: %globaltimer stamps {start, staged, peers ready, pulled} (+2 spare) of CTA 0 for the last 64 calls, [64][6] u64 */
-int clearvae_peer_timeline(const void* local_base, uint64_t* stamps_host);
 int clearvae_peer_gather(void* const* bases_host, int32_t world, int32_t rank, int64_t buffer_bytes, int32_t n_pieces,
                          const void* const* src_host, void* const* dst_host, const int64_t* bytes_host, void* stream);
 int clearvae_peer_allreduce(void* const* bases_host, int32_t world, int32_t rank, int64_t buffer_bytes, int32_t n_tensors,

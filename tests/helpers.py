@@ -99,3 +99,37 @@ def supcon_torch(mu, label, sim, tau, name, ps):
     pos = S2.masked_fill(~m[keep], -float("inf"))
     val = n_k[keep].double().log() - torch.logsumexp(pos / tau, dim=1) + torch.logsumexp(S2 / tau, dim=1)
     return val[torch.isfinite(val)].mean()
+
+
+def snn_fp64_chunked(mu, label, tau, ps=False, device="cpu", chunk=4096):
+    """fp64 torch restatement of `contrastive_loss(..., "cosine", tau, "snn_loss", ps)` (losses.py:54-55, 98-137) that never
+    holds more than a [chunk, B] block: returns (loss, dloss/dmu) with the gradient from autograd, chunk by chunk (row side
+    and column side both accumulate into the same leaf).  Pinned against oracle/latent_oracle.py (numpy closed forms, themselves
+    pinned to the reference goldens) by tests/test_latent_gpu.py::test_fp64_chunked_restatement_is_pinned before it is
+    trusted at sizes the numpy oracle cannot reach in test time (B = 65536)."""
+    mu = mu.detach().to(device=device, dtype=torch.float64).requires_grad_(True)
+    label = label.to(device)
+    B = mu.shape[0]
+    total, count = torch.zeros((), dtype=torch.float64, device=device), 0
+    for r0 in range(0, B, chunk):
+        r1 = min(B, r0 + chunk)
+        n = mu / mu.norm(dim=1, keepdim=True).clamp_min(1e-8)
+        S = (n[r0:r1] @ n.T) / tau
+        idx = torch.arange(r0, r1, device=device)
+        eye = torch.zeros_like(S, dtype=torch.bool)
+        eye[idx - r0, idx] = True
+        m = (label[r0:r1, None] == label[None, :]) != bool(ps)
+        S = S.masked_fill(eye, -float("inf"))
+        pos = S.masked_fill(~m, -float("inf"))
+        has_pos = (m & ~eye).any(1)
+        # rows without positives are +inf in the reference and dropped by its finite-row mean
+        row = torch.logsumexp(S[has_pos], 1) - torch.logsumexp(pos[has_pos], 1)
+        fin = torch.isfinite(row)
+        part = row[fin].sum()
+        count += int(fin.sum())
+        total = total + part.detach()
+        if part.requires_grad:
+            part.backward()
+    if count == 0:
+        return float("nan"), torch.zeros_like(mu)
+    return float(total / count), (mu.grad / count)

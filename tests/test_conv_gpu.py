@@ -360,3 +360,70 @@ def test_direct_last_layer_data_gradient(k, op, cout, H, B, dy_bf16):
     assert rel_err(dst, want) < 1e-5
     assert torch.allclose(stats[:32].float(), want.sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
     assert torch.allclose(stats[32:64].float(), (want * raw.float()).sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp32-grade mode (CLEARVAE_ROLE_SPLIT3): fp32 operands, hi*hi + lo*hi + hi*lo on the bf16 tensor cores.
+# Reference = torch fp32 convolutions with TF32 off on the UNROUNDED operands; gate 2e-5 of the output scale (the plain
+# bf16 path needs bf16-rounded operands to meet the same gate — on unrounded operands it sits at ~3e-3).
+# ------------------------------------------------------------------------------------------------------------------
+SPLIT3 = 16
+
+
+@pytest.mark.parametrize("transposed,k,op,cin,cout,H,B", [(0, 3, 0, 32, 64, 14, 16), (0, 4, 0, 64, 128, 16, 8), (0, 4, 0, 3, 32, 16, 4),
+                                                           (1, 3, 1, 64, 32, 7, 8), (1, 4, 0, 256, 128, 4, 16), (1, 3, 1, 32, 3, 14, 8)])
+def test_split3_gemm_and_wgrad_are_fp32_grade(transposed, k, op, cin, cout, H, B):
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(7 * k + cin + cout + transposed)
+    x = torch.randn(B, cin, H, H, generator=g).to(DEV)
+    scale = (torch.rand(cin, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(cin, generator=g) * 0.3).to(DEV)
+    if transposed:
+        w = (torch.randn(cin, cout, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    else:
+        w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    act = torch.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    conv = (lambda a: F.conv_transpose2d(a, w, b, stride=2, padding=1, output_padding=op)) if transposed else \
+        (lambda a: F.conv2d(a, w, b, stride=2, padding=1))
+    act_r = act.detach().requires_grad_(True)
+    w.requires_grad_(True)
+    want = conv(act_r)
+    Ho = want.shape[-1]
+    geom = [transposed, k, 2, 1, op, cin, cout, H, H]
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    # forward with the BatchNorm-apply + ReLU pre-op on the fp32 operand, fp32 channels-last destination + statistics
+    dst = torch.empty(B, Ho, Ho, cout, device=DEV)
+    stats = torch.zeros(2 * cout + 2, dtype=torch.float64, device=DEV)
+    run_gemm(geom, 0 | SPLIT3, B, xn, nhwc_strides(xn), w.detach(), b, dst, nhwc_strides(dst), pre=(scale, shift), relu=True, stats=stats)
+    e = rel_err(dst.permute(0, 3, 1, 2), want.detach())
+    assert e < 2e-5, e
+    assert torch.allclose(stats[:cout], want.detach().double().sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+    # the plain bf16 path on the same unrounded operands is two orders of magnitude away: the split is what buys the accuracy
+    dst_b = torch.empty(B, Ho, Ho, cout, device=DEV)
+    run_gemm(geom, 0, B, xn, nhwc_strides(xn), w.detach(), b, dst_b, nhwc_strides(dst_b), pre=(scale, shift), relu=True)
+    assert rel_err(dst_b.permute(0, 3, 1, 2), want.detach()) > 20 * e
+    # data gradient and weight gradient
+    dy = torch.randn(B, cout, Ho, Ho, generator=g).to(DEV)
+    dx_want, dw_want = torch.autograd.grad(want, [act_r, w], dy)
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dx = torch.empty(B, H, H, cin, device=DEV)
+    run_gemm(geom, 1 | SPLIT3, B, dyn, nhwc_strides(dyn), w.detach(), None, dx, nhwc_strides(dx))
+    assert rel_err(dx.permute(0, 3, 1, 2), dx_want) < 2e-5
+    dw = torch.zeros_like(w)
+    ops.conv_wgrad(geom, B, xn, nhwc_strides(xn), scale, shift, True, dyn, nhwc_strides(dyn), dw, True)
+    assert rel_err(dw, dw_want) < 2e-5, rel_err(dw, dw_want)
+
+
+@pytest.mark.parametrize("B,K,N", [(300, 2048, 32), (128, 16, 2048), (1000, 2048, 128)])
+def test_split3_linear(B, K, N):
+    g = torch.Generator().manual_seed(B + K + N)
+    x = torch.randn(B, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    geom = [0, 1, 1, 0, 0, K, N, 1, 1]
+    dst = torch.empty(B, N, device=DEV)
+    run_gemm(geom, 0 | SPLIT3, B, x, (K, 0, 0, 1), w, b, dst, (N, 0, 0, 1))
+    want = (x.double() @ w.double().T + b.double()).float()
+    assert rel_err(dst, want) < 2e-5, rel_err(dst, want)

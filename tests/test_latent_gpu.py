@@ -330,3 +330,30 @@ def test_supcon_row_losses_against_oracle_and_fp64_autograd(name, sim, tau, D, p
     wg = ref_in.grad.numpy()
     err = np.abs(mu.grad.cpu().numpy() - wg).max()
     assert err <= GRAD_REL * np.abs(wg).max() + 1e-7, (err, np.abs(wg).max())
+
+
+@pytest.mark.parametrize("D", [8, 32])
+def test_65536_latents_tensor_core_path_against_fp64(D):
+    """The configuration `latent_roofline` is quoted on (BASELINE configs[4] top: 65536 latents, tcgen05 3xTF32 path):
+    forward value and the full gradient, both mask polarities in one launch, against the chunked fp64 restatement
+    (tests/helpers.py::snn_fp64_chunked, pinned on the CPU to the numpy oracle and through it to the reference goldens).
+    Gates: loss 1e-5 relative (+ fp32 LSE floor), gradient 1e-4 of its max — north_star's fp32 tolerances."""
+    from clear_vae_b200.latent import latent_block
+    from tests.helpers import snn_fp64_chunked
+    gen = torch.Generator().manual_seed(65536 + D)
+    B = 65536
+    mu_c, mu_s = torch.randn(B, D, generator=gen), torch.randn(B, D, generator=gen)
+    lab = torch.randint(0, 10, (B,), generator=gen)
+    a = mu_c.to(DEV).requires_grad_(True)
+    b = mu_s.to(DEV).requires_grad_(True)
+    _, sc = latent_block([a, b], [None, None], [None, None], lab.to(DEV), snn=[1, 1], ps=[False, True], temperature=0.1, want_z=False)
+    w = torch.zeros(8, device=DEV)
+    w[2], w[3] = 100.0, 100.0          # the trainers' alpha
+    torch.autograd.backward([sc], [w])
+    torch.cuda.synchronize()
+    for t, ps, idx in ((a, False, 2), (b, True, 3)):
+        want, wg = snn_fp64_chunked(t.detach(), lab, 0.1, ps, device=DEV, chunk=4096)
+        assert close(float(sc[idx]), want), (D, ps, float(sc[idx]), want)
+        wg = wg * 100.0
+        err = float((t.grad.double() - wg).abs().max())
+        assert err <= GRAD_REL * float(wg.abs().max()) + 1e-12, (D, ps, err, float(wg.abs().max()))

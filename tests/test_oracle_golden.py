@@ -143,3 +143,20 @@ def test_l1out_closed_form_is_the_executed_computation():
     B, D = 12, 5
     mu, lv, y = rng.normal(size=(B, D)), np.tanh(rng.normal(size=(B, D))), rng.normal(size=(B, D))
     assert abs(lo.l1out_bound_as_executed(mu, lv, y) - lo.l1out_bound_bruteforce(mu, lv, y)) < 1e-12
+
+
+def test_fp64_chunked_restatement_is_pinned():
+    """tests/helpers.py::snn_fp64_chunked (the oracle of the 65536-latent GPU test) == the numpy closed forms, values and
+    gradients, both mask polarities, with near-singleton labels (rows without positives are dropped)."""
+    import torch
+    from tests.helpers import snn_fp64_chunked
+    g = torch.Generator().manual_seed(1)
+    B, D = 700, 8
+    mu = torch.randn(B, D, generator=g)
+    lab = torch.randint(0, 300, (B,), generator=g)
+    for ps in (False, True):
+        val, grad = snn_fp64_chunked(mu, lab, 0.1, ps, chunk=256)
+        want = lo.contrastive(mu.numpy(), np.zeros((B, D)), lab.numpy(), "cosine", 0.1, ps=ps)
+        wg = lo.snn_grad(mu.numpy(), lab.numpy(), "cosine", 0.1, ps)
+        assert abs(val - want) <= 1e-12 * abs(want)
+        assert np.abs(grad.numpy() - wg).max() <= 1e-12 * np.abs(wg).max()

@@ -1,0 +1,79 @@
+"""GPU: whole-step parity AT THE BENCHMARKED SIZES (BASELINE.json configs[0..3]: B = 128 / 1024 / 512 / 128) and the
+fp32-grade convolution mode.
+
+Both sides run the same batch, the same injected reparameterisation noise and the same CLUB-S permutation
+(oracle/parity.py); the oracle is the functional CPU restatement pinned to the reference goldens
+(tests/test_oracle_golden.py).  Reference loop bodies: code/src/trainer.py:446-484, 646-699, 841-888.
+
+Gates
+  * default path (bf16 convolutions, fp32 latent block): loss components and latent parameters within the 1e-2 envelope
+    north_star states for bf16 convolutions;
+  * `conv_precision = "fp32x3"` (bf16 x 3 split products on fp32 activations): loss components within 1e-5 relative
+    (+ the fp32 log-sum-exp floor), every parameter gradient within 1e-4 relative L2 of the oracle's autograd gradient.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16 = 1e-2
+
+
+def _setup(name, precision="bf16", B=None):
+    import bench
+    from oracle import parity
+    cfg = dict(bench.CONFIGS[name])
+    if B is not None:
+        cfg["B"] = B
+    tr = bench.build_trainer(cfg, torch.device(DEV))
+    tr.model.conv_precision = precision
+    g = torch.Generator().manual_seed(101)
+    X = torch.rand(cfg["B"], cfg["cin"], cfg["hw"], cfg["hw"], generator=g)
+    y = torch.randint(0, cfg["ncls"], (cfg["B"],), generator=g)
+    old = torch.get_num_threads()
+    res = parity.compare_step(tr, cfg, X, y)
+    torch.set_num_threads(old)
+    return cfg, res
+
+
+def _report(res):
+    sc = {k: v for k, v in res.items() if "/" not in k}
+    gr = sorted(((v[2], k) for k, v in res.items() if k.startswith("grad/")), reverse=True)
+    lt = {k: v[2] for k, v in res.items() if k.startswith("latent/")}
+    return f"scalars={sc} latents={lt} worst_grads={gr[:4]}"
+
+
+@pytest.mark.parametrize("name", ["clear28", "mim_club", "mim_l1out", "tc64", "clear64"])
+def test_step_parity_at_benchmarked_size_bf16(name):
+    cfg, res = _setup(name)
+    msg = _report(res)
+    for k in ("recon", "kl_c", "kl_s", "c_loss"):
+        assert res[k][2] < BF16, (k, msg)
+    if "s_loss" in res:
+        assert res["s_loss"][2] < BF16, msg
+    if "mi_loss" in res:
+        got, want, _ = res["mi_loss"]
+        # CLUB-S / L1OutUB / TC bounds are differences of O(D) terms: 1e-2 of the bound plus 1e-2 of one term's scale (= 2D x 1e-2 x 0.5)
+        assert abs(got - want) < BF16 * abs(want) + BF16 * 0.05 * cfg["z"], msg
+    if "mi_learning" in res:
+        assert res["mi_learning"][2] < BF16, msg
+    if "factor_loss" in res:
+        assert res["factor_loss"][2] < BF16, msg
+    for k in ("mu_c", "logvar_c", "mu_s", "logvar_s"):
+        assert res[f"latent/{k}"][2] < BF16, (k, msg)
+
+
+@pytest.mark.parametrize("name,B", [("clear28", 128), ("mim_club", 1024), ("clear64", 128), ("tc64", 128)])
+def test_step_parity_fp32x3_losses_and_gradients(name, B):
+    cfg, res = _setup(name, "fp32x3", B)
+    msg = _report(res)
+    for k in ("recon", "kl_c", "kl_s", "c_loss", "s_loss", "mi_loss", "factor_loss"):
+        if k in res:
+            got, want, _ = res[k]
+            assert abs(got - want) < 1e-5 * abs(want) + 2e-6 * max(1.0, abs(want)) ** 0 + (5e-6 if k in ("mi_loss", "c_loss", "s_loss") else 0), (k, msg)
+    for k in ("mu_c", "logvar_c", "mu_s", "logvar_s"):
+        assert res[f"latent/{k}"][2] < 1e-5, (k, msg)
+    grads = {k: v[2] for k, v in res.items() if k.startswith("grad/")}
+    assert len(grads) >= 20
+    for k, e in grads.items():
+        assert e < 1e-4, (k, e, msg)
