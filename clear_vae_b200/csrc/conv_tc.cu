@@ -64,7 +64,7 @@ struct GemmParams {
   const float *msk_scale, *msk_shift;
   double* stats;
   int splits;  // split-K over grid.z (fp32 atomic epilogue); 1 = off
-  int x3;      // CLEARVAE_ROLE_SPLIT3: every k-block runs three times — (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) — fp32-grade products
+  int x3;      // CLEARVAE_ROLE_SPLIT3: every k-block runs kSplitPasses times over the bf16 parts of A and W — fp32-grade products
   // persistent kernel: flattened (class, n-tile, m-tile) work list
   int tile_start[cvplan::kMaxClasses + 1];
   int n_tiles;
@@ -74,8 +74,39 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// hi / lo halves of the bf16 x 3 split: x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi)   (|x - hi - lo| <= 2^-17 |x|)
-__device__ __forceinline__ float split_lo(float x) { return x - __bfloat162float(__float2bfloat16(x)); }
+// bf16 split of an fp32 value into three parts, x = p0 + p1 + p2 (+ <= 2^-25 |x|): p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1).
+// split_part(x, k) returns the fp32 value whose bf16 rounding is part k.
+__device__ __forceinline__ float split_part(float x, int k) {
+  if (k == 0) return x;
+  const float r1 = x - __bfloat162float(__float2bfloat16(x));
+  if (k == 1) return r1;
+  return r1 - __bfloat162float(__float2bfloat16(r1));
+}
+// Split mode (CLEARVAE_ROLE_SPLIT): every k-block runs six times, accumulating the products of operand parts
+// (a, w) = (0,0) (0,1) (1,0) (1,1) (0,2) (2,0) — everything down to 2^-24 of |a||w|, i.e. fp32-grade products on bf16 tensor cores.
+constexpr int kSplitPasses = 6;
+// The tensor core adds into its fp32 TMEM accumulator with truncation at the accumulator's exponent.  Split mode therefore keeps
+// three accumulators by magnitude class — (0,0) | (0,1),(1,0) | (1,1),(0,2),(2,0) — kAccStride columns apart, so the small
+// products are neither truncated at the big sum's ulp nor lengthen its chain; the epilogue adds the three in fp32.
+__device__ __forceinline__ int split_acc(int sub) { return sub == 0 ? 0 : sub <= 2 ? 1 : 2; }
+__device__ __forceinline__ void split_merge32(uint32_t (&raw)[32], uint32_t taddr, uint32_t acc_stride) {
+  uint32_t r1[32], r2[32];
+  sm100::tmem_ld32(taddr + acc_stride, r1);
+  sm100::tmem_ld32(taddr + 2 * acc_stride, r2);
+  sm100::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + (__uint_as_float(r1[i]) + __uint_as_float(r2[i])));
+}
+__device__ __forceinline__ void split_merge16(uint32_t (&raw)[16], uint32_t taddr, uint32_t acc_stride) {
+  uint32_t r1[16], r2[16];
+  sm100::tmem_ld16(taddr + acc_stride, r1);
+  sm100::tmem_ld16(taddr + 2 * acc_stride, r2);
+  sm100::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) + (__uint_as_float(r1[i]) + __uint_as_float(r2[i])));
+}
+__device__ __forceinline__ int split_a_part(int sub) { return (0x201100 >> (4 * sub)) & 3; }   // 0,0,1,1,0,2
+__device__ __forceinline__ int split_b_part(int sub) { return (0x021010 >> (4 * sub)) & 3; }   // 0,1,0,1,2,0
 __device__ __forceinline__ float ld_elem(const void* base, long long off, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]) : reinterpret_cast<const float*>(base)[off];
 }
@@ -97,9 +128,10 @@ __device__ __forceinline__ void transpose_reduce32(float (&v)[32]) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ TmapPack tm_lo, const GemmParams p) {
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ TmapPack tm_p1, const __grid_constant__ TmapPack tm_p2, const GemmParams p) {
   constexpr int kBStage = BN * BK * 2;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;
+  const uint32_t kTmemCols = p.x3 ? 4 * kAccStride : kAccStride;   // split mode: three accumulators (allocation is a power of two)
   extern __shared__ unsigned char smem_raw[];
   // 128-byte-swizzle atoms need 1024-byte alignment (the launch reserves the slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -126,7 +158,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   const int kb0 = nkb_all * split / p.splits;
   const int nkb = nkb_all * (split + 1) / p.splits - kb0;
   if (nkb <= 0) return;
-  const int nsub = p.x3 ? 3 : 1;          // passes per k-block (split mode: hi*hi, lo*hi, hi*lo)
+  const int nsub = p.x3 ? kSplitPasses : 1;   // passes per k-block (split mode: six part products)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -136,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 4) {
-    if (lane == 0) { prefetch_tmap(&tm.t[cls_id]); if (p.x3) prefetch_tmap(&tm_lo.t[cls_id]); }
+    if (lane == 0) { prefetch_tmap(&tm.t[cls_id]); if (p.x3) { prefetch_tmap(&tm_p1.t[cls_id]); prefetch_tmap(&tm_p2.t[cls_id]); } }
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -222,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     }
     for (int it = 0; it < (cpa ? 0 : nkb * nsub); ++it) {
       const int kb = it / nsub, sub = it - kb * nsub;
-      const bool want_lo = sub == 1;        // split mode: the second pass carries the low halves of A
+      const int a_part = split_a_part(sub);  // split mode: which bf16 part of A this pass carries
       const int s = it % NS;
       unsigned char* a_st = sA + s * kAStage;
       const int t_save = t_cur, c_save = c_cur;
@@ -273,9 +305,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (want_lo) {
+          if (a_part) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = split_lo(v[i]);
+            for (int i = 0; i < 8; ++i) v[i] = split_part(v[i], a_part);
           }
           uint4 out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           if (!ok[j]) out = make_uint4(0u, 0u, 0u, 0u);
@@ -316,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             float x = v[i];
             if (has_pre) x = fmaf(x, sScale[chn[i]], sShift[chn[i]]);
             if (p.pre_relu) x = fmaxf(x, 0.f);
-            if (want_lo) x = split_lo(x);
+            if (a_part) x = split_part(x, a_part);
             v[i] = ok[i] ? x : 0.f;
           }
           *reinterpret_cast<uint4*>(a_st + j * (BM * 16) + r * 16) =
@@ -353,9 +385,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
         if (CH == 32) {
           tmem_ld32(taddr, raw);
+          if (p.x3) { tmem_ld_wait(); split_merge32(raw, taddr, kAccStride); }
         } else {
           uint32_t r16[16];
           tmem_ld16(taddr, r16);
+          if (p.x3) { tmem_ld_wait(); split_merge16(r16, taddr, kAccStride); }
 #pragma unroll
           for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
         }
@@ -446,9 +480,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
       if (CH == 32) {
         tmem_ld32(taddr, raw);
+        if (p.x3) { tmem_ld_wait(); split_merge32(raw, taddr, kAccStride); }
       } else {
         uint32_t r16[16];
         tmem_ld16(taddr, r16);
+        if (p.x3) { tmem_ld_wait(); split_merge16(r16, taddr, kAccStride); }
 #pragma unroll
         for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
       }
@@ -538,25 +574,29 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         const int s = it % NS;
         mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], kBStage);
-        tma_load_2d(sB + s * kBStage, sub == 2 ? &tm_lo.t[cls_id] : &tm.t[cls_id], &full[s], (kb0 + kb) * BK, n0);
+        const int bp = p.x3 ? split_b_part(sub) : 0;
+        tma_load_2d(sB + s * kBStage, bp == 0 ? &tm.t[cls_id] : bp == 1 ? &tm_p1.t[cls_id] : &tm_p2.t[cls_id], &full[s], (kb0 + kb) * BK, n0);
       }
     }
   } else {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
-      for (int kb = 0; kb < nkb * nsub; ++kb) {   // split mode: three passes per k-block, one accumulator
+      for (int kb = 0; kb < nkb * nsub; ++kb) {   // split mode: six passes per k-block into three accumulators
         const int s = kb % NS;
         mbar_wait(&full[s], (kb / NS) & 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + s * kAStage), b_base = smem_u32(sB + s * kBStage);
+        const int sub = kb % nsub;
+        const uint32_t acc = p.x3 ? (uint32_t)split_acc(sub) * kAccStride : 0u;
+        const bool first = kb < nsub && (sub == 0 || sub == 1 || sub == 3);   // first pass that writes this accumulator
 #pragma unroll
         for (int k4 = 0; k4 < BK / 16; ++k4) {
           // A: interleave layout, 16-byte k-chunks BM*16 bytes apart (LBO), 8-row groups 128 bytes apart (SBO)
           const uint64_t ad = smem_desc(a_base + k4 * 2 * (BM * 16), BM * 16, 128, kLayoutNone);
           // B: 128-byte swizzled rows, 8-row groups 1024 bytes apart; K advance = +32 bytes inside the atom
           const uint64_t bd = smem_desc(b_base + k4 * 32, 16, 1024, kLayoutSw128);
-          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_f16(tmem_base + acc, ad, bd, idesc, (first && k4 == 0) ? 0u : 1u);
         }
         umma_commit(&empty[s]);
       }
@@ -930,7 +970,7 @@ struct WgradParams {
   const void* dy; long long y_n, y_h, y_w, y_c; int dy_bf16;
   float* dw;
   int splits;
-  int x3;   // split mode: every pixel block runs three times — (act_hi, dy_hi), (act_lo, dy_hi), (act_hi, dy_lo)
+  int x3;   // split mode: every pixel block runs six times over the bf16 parts of both operands (see kSplitPasses)
 };
 
 constexpr int WK = 64;                       // pixels per k-block
@@ -939,7 +979,8 @@ constexpr int kWStageA = 128 * WK * 2;       // 16 KiB
 template <int BN>
 __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p) {
   constexpr int kBStage = BN * WK * 2;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;
+  const uint32_t kTmemCols = p.x3 ? 4 * kAccStride : kAccStride;   // split mode: three accumulators by magnitude class
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -962,7 +1003,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
   const long long kb_begin = nkb_total * split / p.splits, kb_end = nkb_total * (split + 1) / p.splits;
   const int nkb = (int)(kb_end - kb_begin);
   if (nkb <= 0) return;
-  const int nsub = p.x3 ? 3 : 1;
+  const int nsub = p.x3 ? kSplitPasses : 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -1045,7 +1086,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
     }
     for (int it = 0; it < (cpa ? 0 : nkb * nsub); ++it) {
       const int kb = it / nsub, sub = it - kb * nsub;
-      const bool a_lo = sub == 1, b_lo = sub == 2;
+      const int a_lo = p.x3 ? split_a_part(sub) : 0, b_lo = p.x3 ? split_b_part(sub) : 0;
       const int s = it % NS;
       const long long m = (kb_begin + kb) * WK + px;
       const bool mvalid = m < Mc;
@@ -1133,7 +1174,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
           }
           if (a_lo) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = split_lo(v[i]);
+            for (int i = 0; i < 8; ++i) v[i] = split_part(v[i], a_lo);
           }
           if (oka[j]) out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         } else if (mvalid && kidx < Kreal) {
@@ -1156,7 +1197,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
             float x = ld_elem(p.src, off, p.src_bf16);
             if (p.pre_scale != nullptr) x = fmaf(x, sScale[ch], sShift[ch]);
             if (p.pre_relu) x = fmaxf(x, 0.f);
-            if (a_lo) x = split_lo(x);
+            if (a_lo) x = split_part(x, a_lo);
             v[i] = vld ? x : 0.f;
           }
           (void)okk;
@@ -1179,7 +1220,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
                             __uint_as_float(qb1[j].x), __uint_as_float(qb1[j].y), __uint_as_float(qb1[j].z), __uint_as_float(qb1[j].w)};
               if (b_lo) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = split_lo(v[i]);
+                for (int i = 0; i < 8; ++i) v[i] = split_part(v[i], b_lo);
               }
               out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
@@ -1188,7 +1229,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               v[i] = (n + i < Nn) ? ld_elem(p.dy, dy_off + (n + i) * p.y_c, p.dy_bf16) : 0.f;
-              if (b_lo) v[i] = split_lo(v[i]);
+              if (b_lo) v[i] = split_part(v[i], b_lo);
             }
             out = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
@@ -1213,9 +1254,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)ch0;
       if (CH == 32) {
         tmem_ld32(taddr, raw);
+        if (p.x3) { tmem_ld_wait(); split_merge32(raw, taddr, kAccStride); }
       } else {
         uint32_t r16[16];
         tmem_ld16(taddr, r16);
+        if (p.x3) { tmem_ld_wait(); split_merge16(r16, taddr, kAccStride); }
 #pragma unroll
         for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
       }
@@ -1236,12 +1279,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
         mbar_wait(&full[s], (kb / NS) & 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + s * kWStageA), b_base = smem_u32(sB + s * kBStage);
+        const int sub = kb % nsub;
+        const uint32_t acc = p.x3 ? (uint32_t)split_acc(sub) * kAccStride : 0u;
+        const bool first = kb < nsub && (sub == 0 || sub == 1 || sub == 3);
 #pragma unroll
         for (int k4 = 0; k4 < WK / 16; ++k4) {
           // MN-major interleave: 8-pixel k-groups 128 B apart (LBO), 8-channel mn-groups WK*16 B apart (SBO)
           const uint64_t ad = smem_desc(a_base + k4 * 256, 128, WK * 16, kLayoutNone);
           const uint64_t bd = smem_desc(b_base + k4 * 256, 128, WK * 16, kLayoutNone);
-          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_f16(tmem_base + acc, ad, bd, idesc, (first && k4 == 0) ? 0u : 1u);
         }
         umma_commit(&empty[s]);
       }
@@ -1256,7 +1302,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
 // ---------------------------------------------------------------------------
 // weight packing: fp32 reference layout -> bf16 [class][n_pad][Kp], zero padded
 // ---------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo) {
+__global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_p1, __nv_bfloat16* __restrict__ out_p2) {
   const Cls& c = plan.cls[blockIdx.y];
   const int n_pad = (plan.Nn + 15) / 16 * 16;
   const long long total = (long long)n_pad * c.Kp;
@@ -1268,7 +1314,10 @@ __global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w,
       v = w[n * plan.ws_n + ch * plan.ws_c + c.wtap[t]];
     }
     out[c.w_off + i] = __float2bfloat16(v);
-    if (out_lo != nullptr) out_lo[c.w_off + i] = __float2bfloat16(split_lo(v));   // split mode: W ~ W_hi + W_lo
+    if (out_p1 != nullptr) {   // split mode: W = W_0 + W_1 + W_2
+      out_p1[c.w_off + i] = __float2bfloat16(split_part(v, 1));
+      out_p2[c.w_off + i] = __float2bfloat16(split_part(v, 2));
+    }
   }
 }
 
@@ -1298,7 +1347,7 @@ inline int pick_bn(int Nn) {
 }
 
 template <int BN>
-int launch(const TmapPack& tm, const TmapPack& tm_lo, const GemmParams& p, dim3 grid, cudaStream_t st) {
+int launch(const TmapPack& tm, const TmapPack& tm_p1, const TmapPack& tm_p2, const GemmParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = NS * kAStage + NS * BN * BK * 2 + 96 /*barriers + tmem slot*/ + kTabMax * 16 + 64 + 2 * kMaxPreC * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1306,7 +1355,7 @@ int launch(const TmapPack& tm, const TmapPack& tm_lo, const GemmParams& p, dim3 
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tm, tm_lo, p);
+  conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tm, tm_p1, tm_p2, p);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -1410,9 +1459,9 @@ size_t clearvae_conv_packed_weight_bytes(const clearvae_conv_geom* g, int32_t ro
   Plan plan;
   const int x3 = (role & CLEARVAE_ROLE_SPLIT3) != 0;
   if (!g || !cvplan::make_plan(*g, role & ~CLEARVAE_ROLE_SPLIT3, BK, &plan)) return 0;
-  // split mode: [hi | lo], the lo half starting at the next 128-byte boundary
+  // split mode: [part 0 | part 1 | part 2], each part starting at a 128-byte boundary
   const size_t one = ((size_t)cvplan::packed_weight_elems(plan) * 2 + 127) / 128 * 128;
-  return x3 ? 2 * one : (size_t)cvplan::packed_weight_elems(plan) * 2;
+  return x3 ? 3 * one : (size_t)cvplan::packed_weight_elems(plan) * 2;
 }
 
 int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const float* weight, void* packed, void* stream) {
@@ -1425,8 +1474,9 @@ int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const f
   for (int i = 0; i < plan.n_classes; ++i) mx = std::max(mx, (long long)n_pad * plan.cls[i].Kp);
   dim3 grid((unsigned)std::min<long long>((mx + 255) / 256, 148 * 8), (unsigned)plan.n_classes);
   const size_t one = ((size_t)cvplan::packed_weight_elems(plan) * 2 + 127) / 128 * 128;
-  __nv_bfloat16* lo = x3 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(packed) + one) : nullptr;
-  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, weight, reinterpret_cast<__nv_bfloat16*>(packed), lo);
+  __nv_bfloat16* p1 = x3 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(packed) + one) : nullptr;
+  __nv_bfloat16* p2 = x3 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(packed) + 2 * one) : nullptr;
+  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, weight, reinterpret_cast<__nv_bfloat16*>(packed), p1, p2);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -1448,18 +1498,18 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   if (!enc) return CLEARVAE_EUNSUPPORTED;
   const int BN = pick_bn(p.plan.Nn);
   const int n_pad = (p.plan.Nn + 15) / 16 * 16;
-  TmapPack tm{}, tm_lo{};
+  TmapPack tm{}, tm_p1{}, tm_p2{};
   long long max_m = 0;
-  const size_t lo_off = ((size_t)cvplan::packed_weight_elems(p.plan) * 2 + 127) / 128 * 128;   // split mode: [hi | lo]
+  const size_t part_off = ((size_t)cvplan::packed_weight_elems(p.plan) * 2 + 127) / 128 * 128;   // split mode: [part 0 | 1 | 2]
   for (int i = 0; i < p.plan.n_classes; ++i) {
     const Cls& c = p.plan.cls[i];
     cuuint64_t dims[2] = {(cuuint64_t)c.Kp, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)c.Kp * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    for (int h = 0; h < (p.x3 ? 2 : 1); ++h) {
-      void* base = (void*)(reinterpret_cast<const char*>(packed_weight) + (size_t)c.w_off * 2 + (h ? lo_off : 0));
-      CUresult r = enc(h ? &tm_lo.t[i] : &tm.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+    for (int h = 0; h < (p.x3 ? 3 : 1); ++h) {
+      void* base = (void*)(reinterpret_cast<const char*>(packed_weight) + (size_t)c.w_off * 2 + h * part_off);
+      CUresult r = enc(h == 0 ? &tm.t[i] : h == 1 ? &tm_p1.t[i] : &tm_p2.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return CLEARVAE_EINVAL;
@@ -1518,10 +1568,10 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   }
   dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)((n_pad + BN - 1) / BN), (unsigned)(p.plan.n_classes * p.splits));
   switch (BN) {
-    case 16: return launch<16>(tm, tm_lo, p, grid, st);
-    case 32: return launch<32>(tm, tm_lo, p, grid, st);
-    case 64: return launch<64>(tm, tm_lo, p, grid, st);
-    default: return launch<128>(tm, tm_lo, p, grid, st);
+    case 16: return launch<16>(tm, tm_p1, tm_p2, p, grid, st);
+    case 32: return launch<32>(tm, tm_p1, tm_p2, p, grid, st);
+    case 64: return launch<64>(tm, tm_p1, tm_p2, p, grid, st);
+    default: return launch<128>(tm, tm_p1, tm_p2, p, grid, st);
   }
 }
 

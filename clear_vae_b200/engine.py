@@ -554,7 +554,7 @@ class Engine:
             last = j == len(specs) - 1
             if last and self.use_direct and j > 0:
                 continue   # direct CUDA-core kernel reads the fp32 master
-            self.packs.get(("dec", j), params[4 * j], sp.geom, eng.role(FPROP))
+            self.packs.get(("dec", j), params[4 * j], sp.geom, self.role(FPROP))
 
     def stat_buf(self, key, C, dev):
         k = (key, C, dev, self.stat_tag)

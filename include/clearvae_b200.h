@@ -169,9 +169,10 @@ typedef struct {
 enum { CLEARVAE_F32 = 0, CLEARVAE_BF16 = 1 };
 enum { CLEARVAE_ROLE_FPROP = 0, CLEARVAE_ROLE_DGRAD = 1 };
 /* OR into `role` of clearvae_conv_packed_weight_bytes / clearvae_conv_pack_weight / clearvae_conv_gemm: fp32-grade products on
- * the bf16 tensor cores ("bf16 x 3").  Each fp32 operand x is split as x ~ hi + lo (hi = bf16(x), lo = bf16(x - hi)) and
- * hi*hi + lo*hi + hi*lo is accumulated in fp32 (TMEM): ~2^-17 relative error per product instead of 2^-9 — the accuracy class
- * of the reference's own fp32 GPU run (cudnn.allow_tf32 = False).  The packed weight holds [hi | lo] (twice the bytes). */
+ * the bf16 tensor cores.  Each fp32 operand x is split into three bf16 parts, x = p0 + p1 + p2 (p0 = bf16(x), p1 = bf16(x - p0),
+ * p2 = bf16(x - p0 - p1): 24 significand bits), and the six part products down to 2^-24 |a||w| — (0,0) (0,1) (1,0) (1,1) (0,2)
+ * (2,0) — are accumulated in fp32 (TMEM): the accuracy class of the reference's own fp32 run (cudnn.allow_tf32 = False) at
+ * six times the MMA work.  The packed weight holds [p0 | p1 | p2] (three times the bytes, parts 128-byte aligned). */
 #define CLEARVAE_ROLE_SPLIT3 16
 /* epilogue of clearvae_conv_gemm */
 enum { CLEARVAE_EPI_BIAS_STATS = 0,  /* dst = acc + bias; stats += (sum v, sum v^2) per output channel      */
@@ -196,7 +197,7 @@ int clearvae_conv_wgrad(const clearvae_conv_geom* g, int64_t batch, const clearv
                         const float* pre_scale, const float* pre_shift, int32_t pre_relu,
                         const clearvae_tensor4* dy, float* dweight, void* stream);
 
-/* the same weight gradient in split mode (see CLEARVAE_ROLE_SPLIT3): both operands hi + lo, three products per pixel block */
+/* the same weight gradient in split mode (see CLEARVAE_ROLE_SPLIT3): both operands in three bf16 parts, six products per pixel block */
 int clearvae_conv_wgrad_split3(const clearvae_conv_geom* g, int64_t batch, const clearvae_tensor4* src,
                                const float* pre_scale, const float* pre_shift, int32_t pre_relu,
                                const clearvae_tensor4* dy, float* dweight, void* stream);

@@ -28,7 +28,7 @@ def oracle_for(tr, cfg, dtype=torch.float32):
     return so
 
 
-def compare_step(tr, cfg, X, label, seed=7, oracle_dtype=torch.float32):
+def compare_step(tr, cfg, X, label, seed=7, oracle_dtype=torch.float32, return_oracle=False):
     """Runs ONE training step on both sides (both are updated).  Returns {name: (cuda, oracle, rel_err)} for every logged
     scalar, plus 'latent/<k>' relative-L2 errors of the four latent parameter tensors and 'grad/<param>' relative-L2 errors
     of every VAE parameter gradient."""
@@ -82,4 +82,4 @@ def compare_step(tr, cfg, X, label, seed=7, oracle_dtype=torch.float32):
             res[f"grad/{k}"] = (None, None, l2(p.grad, ref))
     for k in ("mu_c", "logvar_c", "mu_s", "logvar_s"):
         res[f"latent/{k}"] = (None, None, l2(lp[k], lp_ref[k]))
-    return res
+    return (res, so) if return_oracle else res

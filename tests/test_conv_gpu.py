@@ -399,7 +399,7 @@ def test_split3_gemm_and_wgrad_are_fp32_grade(transposed, k, op, cin, cout, H, B
     run_gemm(geom, 0 | SPLIT3, B, xn, nhwc_strides(xn), w.detach(), b, dst, nhwc_strides(dst), pre=(scale, shift), relu=True, stats=stats)
     e = rel_err(dst.permute(0, 3, 1, 2), want.detach())
     assert e < 2e-5, e
-    assert torch.allclose(stats[:cout], want.detach().double().sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[:cout], want.detach().double().sum((0, 2, 3)), rtol=1e-5, atol=2e-5 * float(want.detach().abs().sum((0, 2, 3)).max()))
     # the plain bf16 path on the same unrounded operands is two orders of magnitude away: the split is what buys the accuracy
     dst_b = torch.empty(B, Ho, Ho, cout, device=DEV)
     run_gemm(geom, 0, B, xn, nhwc_strides(xn), w.detach(), b, dst_b, nhwc_strides(dst_b), pre=(scale, shift), relu=True)
