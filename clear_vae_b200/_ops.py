@@ -59,8 +59,17 @@ class _Meter:
         return sum(v for k, v in self.counts.items() if k not in _HOST_ONLY)
 
     def elapsed_ms(self):
-        """{op: (n, total_ms)} for the timed ops; call after a synchronize."""
-        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+        """{op: (n, total_ms)} for the timed ops; call after a synchronize.  A pair whose launch the host delivered late (the
+        device idles between the two events: first-use module load, a descheduled autograd thread) is not kernel time: values
+        beyond 8x the op's median are replaced by the median."""
+        out = {}
+        for k, v in self.events.items():
+            ts = [a.elapsed_time(b) for a, b in v]
+            if len(ts) >= 3:
+                med = sorted(ts)[len(ts) // 2]
+                ts = [t if t <= 8 * med else med for t in ts]
+            out[k] = (len(ts), sum(ts))
+        return out
 
 
 meter = _Meter()

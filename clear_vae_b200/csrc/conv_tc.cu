@@ -65,9 +65,14 @@ struct GemmParams {
   double* stats;
   int splits;  // split-K over grid.z (fp32 atomic epilogue); 1 = off
   int x3;      // CLEARVAE_ROLE_SPLIT3: every k-block runs kSplitPasses times over the bf16 parts of A and W — fp32-grade products
-  // persistent kernel: flattened (class, n-tile, m-tile) work list
+  // persistent kernels: flattened (class, n-tile, m-tile) work list
   int tile_start[cvplan::kMaxClasses + 1];
   int n_tiles;
+  // TMA-operand kernel: an m-tile of class c is a box of tn images x th rows x tw (= Wd) columns of the class-local output grid
+  // (rows of the GEMM tile in that order, tn * th * tw <= 128); tiles_h = m-tiles per image group along H, mtiles = m-tiles per n-tile
+  int t_tw[cvplan::kMaxClasses], t_th[cvplan::kMaxClasses], t_tn[cvplan::kMaxClasses], t_tiles_h[cvplan::kMaxClasses],
+      t_mtiles[cvplan::kMaxClasses];
+  int t_cb;        // channels per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -953,6 +958,279 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
 #undef CV_PTL
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-operand variant of the persistent kernel: the im2col A operand is no longer gathered by 128 threads with one cp.async per
+// 16 bytes (1024 per tap per tile), but by ONE tiled 4-D TMA instruction per (tap, <= 64-channel block): an m-tile is a box of
+// tn images x th rows x Wd columns of the (class-local) output grid, whose source pixels for tap (dh, dw) form the box
+// (c0, w = dw, h = h0 * sh + dh, n = img0) walked with traversal stride sh (elementStrides) — zero padding is the TMA's
+// out-of-bounds fill, and the tile lands densely as [row][channels] in the 64 / 128-byte swizzled K-major layout tcgen05 reads
+// (tools/tma_stride_probe.cu checks these semantics on the hardware).  Every tap re-reads its pixels from L2, but no thread
+// touches an operand byte: warp 0 = TMA (A and B), warp 1 = MMA issuer, warps 2-5 = epilogue, same mbarrier rings and
+// double-buffered TMEM accumulator as conv_tc_persist_kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTThreads = 192;
+
+struct TTile {
+  int cls, n0, img0, h0;
+};
+__device__ __forceinline__ bool t_get_tile(const GemmParams& p, int id, int BN, TTile* t) {
+  if (id >= p.n_tiles) return false;
+  int cls = 0;
+#pragma unroll
+  for (int i = 1; i < cvplan::kMaxClasses; ++i)
+    if (i < p.plan.n_classes && id >= p.tile_start[i]) cls = i;
+  const int local = id - p.tile_start[cls];
+  const int mt_all = p.t_mtiles[cls];
+  const int nt = local / mt_all, mt = local - nt * mt_all;
+  const int th_tiles = p.t_tiles_h[cls];
+  t->cls = cls;
+  t->n0 = nt * BN;
+  t->img0 = (mt / th_tiles) * p.t_tn[cls];
+  t->h0 = (mt % th_tiles) * p.t_th[cls];
+  return true;
+}
+
+template <int BN, bool MASKED>
+__global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__ TmapPack tmB,
+                                                                                 const GemmParams p) {
+  constexpr int NSP = persist_stages<BN>();
+  constexpr int kBStage = BN * BK * 2;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  constexpr int CH = BN < 32 ? BN : 32;
+  constexpr int NCH = BN / CH;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + NSP * kAStage;
+  float* sEp = reinterpret_cast<float*>(sB + NSP * kBStage);
+  float* sEp2 = sEp + BM * kEpLd;
+  float* sRed = sEp + (MASKED ? 2 : 1) * BM * kEpLd;                 // [2][4][BN]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 2 * 4 * BN);
+  uint64_t* empty = full + NSP;
+  uint64_t* acc_full = empty + NSP;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Cs = p.plan.Cs, cb = p.t_cb, kchunks = Cs / cb;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSP; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0)
+    for (int i = 0; i < p.plan.n_classes; ++i) { prefetch_tmap(&tmA.t[i]); prefetch_tmap(&tmB.t[i]); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: A box + weight slice per (tap, channel block) =================
+    if (lane == 0) {
+      uint32_t kbg = 0;
+      TTile tl;
+      const uint32_t b_bytes = (uint32_t)BN * cb * 2;
+      for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x) {
+        const Cls& c = p.plan.cls[tl.cls];
+        const uint32_t a_bytes = (uint32_t)(p.t_tn[tl.cls] * p.t_th[tl.cls] * p.t_tw[tl.cls]) * cb * 2;
+        const int hbase = tl.h0 * p.plan.sh;
+        for (int t = 0; t < c.ntaps; ++t) {
+          for (int cc = 0; cc < kchunks; ++cc, ++kbg) {
+            const int s = kbg % NSP;
+            mbar_wait(&empty[s], ((kbg / NSP) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
+            tma_load_4d(sA + s * kAStage, &tmA.t[tl.cls], &full[s], cc * cb, c.dw[t], hbase + c.dh[t], tl.img0);
+            tma_load_2d(sB + s * kBStage, &tmB.t[tl.cls], &full[s], t * Cs + cc * cb, tl.n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, 0);
+      const uint32_t layout = cb == 64 ? kLayoutSw128 : kLayoutSw64;
+      const uint32_t sbo = cb == 64 ? 1024u : 512u;      // 8 rows of 128 / 64 bytes
+      const int k4n = cb / 16;
+      uint32_t kbg = 0, tcount = 0;
+      TTile tl;
+      for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
+        const uint32_t b = tcount & 1;
+        mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const int nst = p.plan.cls[tl.cls].ntaps * kchunks;
+        for (int st = 0; st < nst; ++st, ++kbg) {
+          const int s = kbg % NSP;
+          mbar_wait(&full[s], (kbg / NSP) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * kAStage), b_base = smem_u32(sB + s * kBStage);
+          for (int k4 = 0; k4 < k4n; ++k4) {
+            // both operands K-major, rows of cb * 2 bytes, hardware swizzle; K advance = +32 bytes inside the swizzle atom
+            const uint64_t ad = smem_desc(a_base + k4 * 32, 16, sbo, layout);
+            const uint64_t bd = smem_desc(b_base + k4 * 32, 16, sbo, layout);
+            umma_f16(tmem_base + b * kAccCols, ad, bd, idesc, (st | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;
+    const int et = (int)threadIdx.x - 64;   // 0..127 among the epilogue threads
+    const int Nn = p.plan.Nn;
+    float run1[NCH], run2[NCH];             // running column sums of (quarter q, column ch*CH + lane)
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) run1[i] = run2[i] = 0.f;
+    int acc_n0 = -1;
+    auto flush = [&]() {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        if (lane < CH) { sRed[q * BN + i * CH + lane] = run1[i]; sRed[4 * BN + q * BN + i * CH + lane] = run2[i]; }
+        run1[i] = run2[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = et; col < BN; col += 128) {
+        const float a = (sRed[col] + sRed[BN + col]) + (sRed[2 * BN + col] + sRed[3 * BN + col]);
+        const float b2 = (sRed[4 * BN + col] + sRed[5 * BN + col]) + (sRed[6 * BN + col] + sRed[7 * BN + col]);
+        atomicAdd(p.stats + acc_n0 + col, (double)a);
+        atomicAdd(p.stats + Nn + acc_n0 + col, (double)b2);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    uint32_t tcount = 0;
+    TTile tl;
+    for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
+      const Cls& c = p.plan.cls[tl.cls];
+      const int tw = p.t_tw[tl.cls], thw = p.t_th[tl.cls] * tw;
+      const int n_l = r / thw, rem = r - n_l * thw, h_l = rem / tw, wd = rem - h_l * tw;
+      const int hd = tl.h0 + h_l;
+      const long long img = tl.img0 + n_l;
+      const bool mvalid = n_l < p.t_tn[tl.cls] && img < p.batch && hd < c.Hd;
+      const long long dst_off = img * p.d_n + (long long)(hd * p.plan.os + c.oa) * p.d_h + (long long)(wd * p.plan.os + c.ob) * p.d_w;
+      const long long msk_off = img * p.m_n + (long long)(hd * p.plan.os + c.oa) * p.m_h + (long long)(wd * p.plan.os + c.ob) * p.m_w;
+      if (p.stats != nullptr && tl.n0 != acc_n0) {
+        if (acc_n0 >= 0) flush();
+        acc_n0 = tl.n0;
+      }
+      const uint32_t b = tcount & 1;
+      mbar_wait(&acc_full[b], (tcount >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int ch0 = ci * CH;
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * kAccCols + ch0);
+        if (CH == 32) {
+          tmem_ld32(taddr, raw);
+        } else {
+          uint32_t r16[16];
+          tmem_ld16(taddr, r16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+        }
+        const int nb = tl.n0 + ch0;
+        float v[CH], u[CH];
+        if (!MASKED) {
+          float bsv[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) bsv[i] = p.bias != nullptr ? __ldg(p.bias + nb + i) : 0.f;
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = mvalid ? __uint_as_float(raw[i]) + bsv[i] : 0.f;
+        } else {
+          float y[CH];
+          if (p.msk_bf16) {
+            const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.msk) + (mvalid ? msk_off + nb : 0));
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+              const uint4 qv = __ldg(mp + i);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); y[8 * i + 2 * k] = f.x; y[8 * i + 2 * k + 1] = f.y; }
+            }
+          } else {
+            const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.msk) + (mvalid ? msk_off + nb : 0));
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) { const float4 qv = __ldg(mp + i); y[4 * i] = qv.x; y[4 * i + 1] = qv.y; y[4 * i + 2] = qv.z; y[4 * i + 3] = qv.w; }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float act = p.msk_scale ? fmaf(y[i], __ldg(p.msk_scale + nb + i), __ldg(p.msk_shift + nb + i)) : y[i];
+            const float a = (mvalid && act > 0.f) ? __uint_as_float(raw[i]) : 0.f;
+            v[i] = a;
+            u[i] = a * y[i];
+          }
+        }
+        if (ci == NCH - 1) {  // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[b]);
+        }
+        if (mvalid) {
+          if (p.dst_bf16) {
+            uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + nb);
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i)
+              d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dst) + dst_off + nb);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+        if (p.stats != nullptr) {
+          float4* row = reinterpret_cast<float4*>(sEp + r * kEpLd);
+#pragma unroll
+          for (int i = 0; i < CH / 4; ++i) row[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (MASKED) {
+            float4* row2 = reinterpret_cast<float4*>(sEp2 + r * kEpLd);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) row2[i] = make_float4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (lane < CH) {
+            const float* col = sEp + (q * 32) * kEpLd + lane;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            if (!MASKED) {
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                const float a0 = col[rr * kEpLd], a1 = col[(rr + 1) * kEpLd];
+                s1a += a0; s1b += a1; s2a = fmaf(a0, a0, s2a); s2b = fmaf(a1, a1, s2b);
+              }
+            } else {
+              const float* col2 = sEp2 + (q * 32) * kEpLd + lane;
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                s1a += col[rr * kEpLd]; s1b += col[(rr + 1) * kEpLd];
+                s2a += col2[rr * kEpLd]; s2b += col2[(rr + 1) * kEpLd];
+              }
+            }
+            run1[ci] += s1a + s1b;
+            run2[ci] += s2a + s2b;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+    }
+    if (p.stats != nullptr && acc_n0 >= 0) flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // ---------------------------------------------------------------------------
 // weight gradient:  dW[kidx, n] += sum_{pixels m} act[m @ tap(kidx), c(kidx)] * dy[m, n]
 //   GEMM with M = (tap, channel) rows, N = output channels, K = pixels (split over CTAs).
@@ -1377,6 +1655,26 @@ int launch_persist(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
   CV_LAUNCH_CHECK();
   return 0;
 }
+template <int BN, bool MASKED>
+int launch_tma(const TmapPack& tmA, const TmapPack& tmB, const GemmParams& p, cudaStream_t st) {
+  constexpr size_t smem = persist_smem<BN, MASKED>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  const int per_sm = (BN <= 64 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
+  const int grid = std::min(p.n_tiles, per_sm * 148);
+  conv_tma_kernel<BN, MASKED><<<grid, kTThreads, smem, st>>>(tmA, tmB, p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+template <int BN>
+int launch_tma_bn(const TmapPack& tmA, const TmapPack& tmB, const GemmParams& p, cudaStream_t st) {
+  return p.epi == CLEARVAE_EPI_BIAS_STATS ? launch_tma<BN, false>(tmA, tmB, p, st) : launch_tma<BN, true>(tmA, tmB, p, st);
+}
+
 template <int BN>
 int launch_persist_bn(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
   return p.epi == CLEARVAE_EPI_BIAS_STATS ? launch_persist<BN, false>(tm, p, st) : launch_persist<BN, true>(tm, p, st);
@@ -1549,6 +1847,63 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
       p.d_c == 1 && p.plan.Nn % BN == 0 && ((p.d_n | p.d_h | p.d_w) & 7) == 0 && !((uintptr_t)p.src & 15) &&
       ((p.s_n | p.s_h | p.s_w) & 7) == 0 && !((uintptr_t)p.dst & 15) &&
       (!masked || (p.m_c == 1 && ((p.m_n | p.m_h | p.m_w) & 7) == 0 && !((uintptr_t)p.msk & 15)))) {
+    // ---- first choice: the TMA-operand kernel (one bulk-tensor instruction per tap instead of 1024 cp.async)
+    static const bool no_tma_a = getenv("CLEARVAE_NO_TMA_A") != nullptr;
+    const int Cs = p.plan.Cs;
+    if (!no_tma_a && (Cs == 32 || Cs % 64 == 0) && batch < (1 << 24)) {
+      GemmParams q = p;
+      q.t_cb = Cs == 32 ? 32 : 64;
+      bool ok = true;
+      long long tiles = 0;
+      const int n_ntiles = q.plan.Nn / BN;
+      TmapPack tmA{}, tmB = tm;
+      for (int i = 0; i < q.plan.n_classes && ok; ++i) {
+        const Cls& c = q.plan.cls[i];
+        const int sh = q.plan.sh;
+        if (c.Wd > 128 || c.Wd * sh > 256) { ok = false; break; }
+        int tw = c.Wd, th, tn;
+        if (c.Hd * c.Wd <= 128) { th = c.Hd; tn = std::min<long long>(128 / (c.Hd * c.Wd), batch); }
+        else { th = 128 / c.Wd; tn = 1; }
+        if (th * sh > 256 || tn > 256) { ok = false; break; }
+        const int tiles_h = (c.Hd + th - 1) / th;
+        const long long mt = ((batch + tn - 1) / tn) * tiles_h;
+        q.t_tw[i] = tw; q.t_th[i] = th; q.t_tn[i] = tn; q.t_tiles_h[i] = tiles_h; q.t_mtiles[i] = (int)mt;
+        q.tile_start[i] = (int)tiles;
+        tiles += mt * n_ntiles;
+        cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)q.plan.Ws, (cuuint64_t)q.plan.Hs, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)q.s_w * 2, (cuuint64_t)q.s_h * 2, (cuuint64_t)q.s_n * 2};
+        cuuint32_t box[4] = {(cuuint32_t)q.t_cb, (cuuint32_t)(tw * sh), (cuuint32_t)(th * sh), (cuuint32_t)tn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)sh, (cuuint32_t)sh, 1};
+        // a Linear is a 1x1 "image" per sample (Hs = Ws = 1): strides of the unit dimensions are free but must be legal
+        if (q.plan.Ws == 1) strides[0] = (cuuint64_t)Cs * 2;
+        if (q.plan.Hs == 1) strides[1] = strides[0] * (cuuint64_t)q.plan.Ws;
+        if ((strides[0] | strides[1] | strides[2]) & 15) { ok = false; break; }
+        CUresult r = enc(&tmA.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.src), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, q.t_cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ok = false; break; }
+        if (q.t_cb == 32) {   // 64-byte weight rows: its own map (box 32 x BN, SWIZZLE_64B)
+          cuuint64_t wd[2] = {(cuuint64_t)c.Kp, (cuuint64_t)n_pad};
+          cuuint64_t ws[1] = {(cuuint64_t)c.Kp * 2};
+          cuuint32_t wb[2] = {32u, (cuuint32_t)BN};
+          cuuint32_t we[2] = {1, 1};
+          void* base = (void*)(reinterpret_cast<const char*>(packed_weight) + (size_t)c.w_off * 2);
+          r = enc(&tmB.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) { ok = false; break; }
+        }
+      }
+      if (ok && tiles > 0 && tiles < (1LL << 30)) {
+        q.tile_start[q.plan.n_classes] = (int)tiles;
+        q.n_tiles = (int)tiles;
+        switch (BN) {
+          case 16: return launch_tma_bn<16>(tmA, tmB, q, st);
+          case 32: return launch_tma_bn<32>(tmA, tmB, q, st);
+          case 64: return launch_tma_bn<64>(tmA, tmB, q, st);
+          default: return launch_tma_bn<128>(tmA, tmB, q, st);
+        }
+      }
+    }
     long long tiles = 0;
     const int n_ntiles = p.plan.Nn / BN;
     for (int i = 0; i < p.plan.n_classes; ++i) {

@@ -61,6 +61,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// 4-D tiled load (c = innermost channel index, w, h, n); out-of-bounds elements (negative or past the extent) are zero-filled,
+// traversal strides come from the tensor map's elementStrides
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c, int32_t w, int32_t h, int32_t n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_out, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols)
@@ -156,7 +166,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
-constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
+constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2, kLayoutSw64 = 4;
 
 // Instruction descriptor for kind::f16 / kind::tf32 (InstrDescriptor layout):
 //   [4,6) D format (1 = f32), [7,10) A format, [10,13) B format (0 f16, 1 bf16, 2 tf32),

@@ -427,3 +427,62 @@ def test_split3_linear(B, K, N):
     run_gemm(geom, 0 | SPLIT3, B, x, (K, 0, 0, 1), w, b, dst, (N, 0, 0, 1))
     want = (x.double() @ w.double().T + b.double()).float()
     assert rel_err(dst, want) < 2e-5, rel_err(dst, want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TMA-operand persistent kernel (bf16 channels-last operand, channels-last destination): every interior layer geometry of
+# VAE / VAE64 in both roles, batch sizes that leave partial image groups / partial row tiles, with the statistics and the
+# masked (ReLU + BatchNorm-backward sums) epilogues.  Reference: torch fp32 convolutions on the same bf16-valued operands.
+# ------------------------------------------------------------------------------------------------------------------
+_INTERIOR = [  # transposed, k, op, cin, cout, Hin
+    (0, 3, 0, 32, 64, 14), (0, 3, 0, 64, 128, 7), (1, 3, 0, 128, 64, 4), (1, 3, 1, 64, 32, 7),
+    (0, 4, 0, 32, 64, 32), (0, 4, 0, 64, 128, 16), (0, 4, 0, 128, 256, 8), (0, 4, 0, 256, 512, 4),
+    (1, 4, 0, 512, 256, 2), (1, 4, 0, 256, 128, 4), (1, 4, 0, 128, 64, 8), (1, 4, 0, 64, 32, 16),
+]
+
+
+@pytest.mark.parametrize("transposed,k,op,cin,cout,H", _INTERIOR)
+@pytest.mark.parametrize("B", [5, 37])
+def test_tma_operand_kernel_matches_torch(transposed, k, op, cin, cout, H, B):
+    g = torch.Generator().manual_seed(11 * k + cin + cout + H + B)
+    x = bf(torch.randn(B, cin, H, H, generator=g)).to(DEV)
+    if transposed:
+        w = bf(torch.randn(cin, cout, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+        fwd = lambda a: F.conv_transpose2d(a, w, b, stride=2, padding=1, output_padding=op)
+    else:
+        w = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+        fwd = lambda a: F.conv2d(a, w, b, stride=2, padding=1)
+    b = torch.randn(cout, generator=g).to(DEV)
+    xr = x.clone().requires_grad_(True)
+    want = fwd(xr)
+    Ho = want.shape[-1]
+    geom = [transposed, k, 2, 1, op, cin, cout, H, H]
+    xn = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)          # exact: values are bf16 already
+    dst = torch.empty(B, Ho, Ho, cout, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * cout + 2, dtype=torch.float64, device=DEV)
+    run_gemm(geom, 0, B, xn, nhwc_strides(xn), w, b, dst, nhwc_strides(dst), stats=stats)
+    wn = want.detach()
+    assert rel_err(dst.float().permute(0, 3, 1, 2), wn) < 6e-3                       # bf16 output rounding
+    assert torch.allclose(stats[:cout].float(), wn.sum((0, 2, 3)), rtol=1e-4, atol=2e-5 * float(wn.abs().sum((0, 2, 3)).max()))
+    assert torch.allclose(stats[cout:2 * cout].float(), (wn * wn).sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+    # fp32 destination: the accumulators themselves
+    dst32 = torch.empty(B, Ho, Ho, cout, device=DEV)
+    run_gemm(geom, 0, B, xn, nhwc_strides(xn), w, b, dst32, nhwc_strides(dst32))
+    assert rel_err(dst32.permute(0, 3, 1, 2), wn) < 2e-5
+    # data gradient with the previous block's ReLU mask + BatchNorm-backward sums in the epilogue
+    dy = bf(torch.randn(B, cout, Ho, Ho, generator=g)).to(DEV)
+    (dx_want,) = torch.autograd.grad(want, xr, dy)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    raw_prev = bf(torch.randn(B, H, H, cin, generator=g)).to(DEV).to(torch.bfloat16)   # previous block's raw output (mask source)
+    ms = (torch.rand(cin, generator=g) + 0.5).to(DEV)
+    mh = (torch.randn(cin, generator=g) * 0.3).to(DEV)
+    keep = (raw_prev.float() * ms + mh) > 0
+    gdst = torch.empty(B, H, H, cin, device=DEV)
+    st2 = torch.zeros(2 * cin + 2, dtype=torch.float64, device=DEV)
+    run_gemm(geom, 1, B, dyn, nhwc_strides(dyn), w, None, gdst, nhwc_strides(gdst), epi=1, mask=raw_prev,
+             mask_strides=nhwc_strides(raw_prev), mscale=ms, mshift=mh, stats=st2)
+    gw = dx_want.permute(0, 2, 3, 1) * keep
+    assert rel_err(gdst, gw) < 2e-5
+    assert torch.allclose(st2[:cin].float(), gw.sum((0, 1, 2)), rtol=1e-4, atol=2e-5 * float(gw.abs().sum((0, 1, 2)).max()))
+    assert torch.allclose(st2[cin:2 * cin].float(), (gw * raw_prev.float()).sum((0, 1, 2)), rtol=1e-4,
+                          atol=2e-5 * float((gw * raw_prev.float()).abs().sum((0, 1, 2)).max()))
