@@ -366,7 +366,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner / debug lines off stdout: one JSON line only
         td.init_process_group("nccl", device_id=dev)
     _ops.load()
     cfg = CONFIGS[args.config]
@@ -374,7 +374,8 @@ def main():
     tr = build_trainer(cfg, dev)
     tr.model.conv_precision = args.precision
     sampler = ClockSampler(local)     # started before warm-up so the record never comes back empty; covers every timed region
-    sampler.start()
+    if rank == 0:                     # one sampler per job: N nvidia-smi loops polling the driver at 50 Hz perturb N ranks' launches
+        sampler.start()
     if world > 1:
         from clear_vae_b200.peer import PeerComm
         peer = PeerComm.create(td.group.WORLD, rank, world, dev)   # None -> NCCL collectives (e.g. IPC mapping unavailable)
@@ -536,6 +537,16 @@ def main():
     h2d = pool_h[0][0].numel() * 4 + pool_h[0][1].numel() * 8
     d2h = vals.numel() * 4
 
+    peer_phases = None
+    if world > 1 and tr.dist.peer is not None:
+        # where the collectives' time goes: CTA-0 %globaltimer stamps of the last 64 peer calls (stage own pieces | publish + wait
+        # for every peer's flag = flag round trip + waiting for the slowest rank | pull)
+        tl = tr.dist.peer.timeline()
+        tl = tl[(tl > 0).all(1)]
+        if tl.numel():
+            ph = ((tl[:, 1:] - tl[:, :-1]) / 1e3)
+            peer_phases = dict(calls=int(tl.shape[0]), stage_us=float(ph[:, 0].mean()), publish_wait_us=float(ph[:, 1].mean()),
+                               publish_wait_us_max=float(ph[:, 1].max()), pull_us=float(ph[:, 2].mean()))
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -606,7 +617,8 @@ def main():
                                      collectives=("none (1 GPU)" if world == 1 else "one-shot peer-memory kernels over NVLink (csrc/peer_comm.cu)"
                                                   if tr.dist.peer is not None else "NCCL"),
                                      fallbacks="none: missing extension / unsupported discriminator / CPU tensors raise",
-                                     peer_error=(tr.dist.peer.error() if (world > 1 and tr.dist.peer is not None) else None)),
+                                     peer_error=(tr.dist.peer.error() if (world > 1 and tr.dist.peer is not None) else None),
+                                     peer_phases_rank0=peer_phases),
                     clocks=clocks,
                     e2e=dict(value=world * B / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e, ms_per_step_events=ms_e2e_ev, ms_per_step_wall=ms_e2e_wall, losses_finite=e2e_finite,

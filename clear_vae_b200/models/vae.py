@@ -218,21 +218,25 @@ class VAE(nn.Module):
         return self.generate(mu_c, logvar_c, mu_s, logvar_s, None, False), latent_params
 
     # -- fused training-step forward (used by the trainers) ----------------------------
-    def fused_step_forward(self, x, label, *, temperature, snn, ps, sim_fn="cosine", eps=None, dist=None):
+    def fused_step_forward(self, x, label, *, temperature, snn, ps, sim_fn="cosine", eps=None, dist=None, gather_z=False):
         """encode -> [reparam + KL + SNN terms] -> decode + reconstruction error.
 
         Returns (xhat, recon, z, scalars, latent_params); `scalars` as in `latent_block`.
         Equivalent to `forward(x, explicit=True)` followed by `vae_loss` and the
         `contrastive_loss` calls of the trainers (trainer.py:452-470), with the same
-        random draws.
+        random draws.  `gather_z` (data parallel only) appends the sampled latents of the global batch.
         """
         mu_c, logvar_c, mu_s, logvar_s = self.encode(x)
         if eps is None:
             eps = (torch.randn_like(logvar_c), torch.randn_like(logvar_s))
-        z, sc = latent_block([mu_c, mu_s], [logvar_c, logvar_s], list(eps), label, snn=snn, ps=ps, sim_fn=sim_fn,
-                             temperature=temperature, dist=dist)
+        out = latent_block([mu_c, mu_s], [logvar_c, logvar_s], list(eps), label, snn=snn, ps=ps, sim_fn=sim_fn,
+                           temperature=temperature, dist=dist, gather_z=gather_z)
+        z, sc = out[0], out[1]
         xhat, recon = self._decode(z, x)
-        return xhat, recon, z, sc, {"mu_c": mu_c, "logvar_c": logvar_c, "mu_s": mu_s, "logvar_s": logvar_s}
+        lp = {"mu_c": mu_c, "logvar_c": logvar_c, "mu_s": mu_s, "logvar_s": logvar_s}
+        if len(out) == 3:       # data parallel + gather_z: the sampled latents of the global batch as a sixth value
+            return xhat, recon, z, sc, lp, out[2]
+        return xhat, recon, z, sc, lp
 
 
 class VAE64(VAE):

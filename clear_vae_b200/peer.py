@@ -22,7 +22,7 @@ HEADER = 4096
 
 
 class PeerComm:
-    def __init__(self, group, rank: int, world: int, device, nbytes: int = 16 << 20):
+    def __init__(self, group, rank: int, world: int, device, nbytes: int = 64 << 20):
         import torch.distributed as td
         if world > 8:
             raise RuntimeError("peer-memory collectives cover one NVSwitch node (<= 8 ranks)")
@@ -84,6 +84,46 @@ class PeerComm:
     def slot_bytes(self):
         return ((self.nbytes - HEADER) // 2) & ~15
 
+    def fits(self, pieces) -> bool:
+        """whether one `gather` of these per-rank pieces fits a slot (callers fall back to the NCCL all-gather otherwise)"""
+        return len(pieces) <= 8 and sum(t.numel() * t.element_size() + 16 for t in pieces) * self.world <= self.slot_bytes()
+
+    def allreduce_chunked_(self, tensors):
+        """`allreduce_` for any total size: the list is cut into groups that fit one slot (<= 64 tensors each); a tensor larger
+        than a slot travels as consecutive flat views.  Same fixed rank order, so results stay bit-identical across ranks."""
+        cap = self.slot_bytes() // 4 - 64
+        group, used = [], 0
+
+        def flush():
+            nonlocal group, used
+            if group:
+                self.allreduce_(group)
+            group, used = [], 0
+
+        for t in tensors:
+            flat = t.view(-1)
+            o = 0
+            while o < flat.numel():
+                n = min(flat.numel() - o, cap - used)
+                if n <= 0 or len(group) >= 64:
+                    flush()
+                    continue
+                n -= (n % 4) if (o + n < flat.numel()) else 0     # keep 16-byte alignment of the next view
+                if n == 0:
+                    flush()
+                    continue
+                group.append(flat[o:o + n])
+                used += n + 4
+                o += n
+        flush()
+
+    def check(self):
+        """raise if any collective of this communicator ever timed out waiting for a peer (the kernels record the missing
+        rank instead of hanging; results after that are undefined)"""
+        e = self.error()
+        if e:
+            raise RuntimeError(f"clear_vae_b200.peer: a peer-memory collective timed out waiting for rank {e - 1}")
+
     def error(self) -> int:
         v = ctypes.c_int32(0)
         with torch.cuda.device(self.device):
@@ -110,7 +150,7 @@ class PeerComm:
 
     # ---- guarded construction -------------------------------------------------------------------------------------
     @staticmethod
-    def create(group, rank, world, device, nbytes: int = 16 << 20):
+    def create(group, rank, world, device, nbytes: int = 64 << 20):
         """Collective.  PeerComm when every rank mapped every peer and the self-test matched NCCL, else None (on all ranks)."""
         import torch.distributed as td
         if os.environ.get("CLEARVAE_PEER", "1") == "0" or world < 2 or world > 8:

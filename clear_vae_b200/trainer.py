@@ -249,10 +249,15 @@ class VAETrainer(Trainer):
         g["label"].copy_(label, non_blocking=True)
         if g["perm"] is not None:  # CLUB-S: the CPU generator draws the permutation exactly like the reference
             ph = g["perm_host"][self._slot()]
-            ph.copy_(torch.randperm(X.shape[0]))
+            ph.copy_(self._perm(ph.numel()))
             g["perm"].copy_(ph, non_blocking=True)
         g["graph"].replay()
-        return tuple(t.clone() for t in g["out"])  # the graph's output buffers are overwritten by the next replay
+        # the graph's output buffers are overwritten by the next replay: hand out copies — one launch for all of them
+        flat = g.get("flat")
+        if flat is None:
+            return tuple(t.clone() for t in g["out"])
+        c = flat.clone()
+        return tuple(c[a:b].view(sh) for (a, b, sh) in g["views"])
 
     # ---- graph capture must not train: the eager warm-up steps below (allocator / workspace / optimiser-state
     # warm-up that CUDA-graph capture requires) run on the real batch, so everything they touch is put back
@@ -300,7 +305,8 @@ class VAETrainer(Trainer):
         kw = {}
         snap = self._snapshot_state(X.device)
         if self._needs_perm():
-            perm_host = torch.stack([torch.randperm(X.shape[0]), torch.randperm(X.shape[0])]).pin_memory()   # two slots
+            nper = X.shape[0] * (self.dist.world if (self.dist is not None and self.dist.world > 1) else 1)   # permutation of the global batch
+            perm_host = torch.stack([torch.arange(nper), torch.arange(nper)]).pin_memory()   # two slots, rewritten before every replay
             perm = perm_host[0].to(X.device)
             kw["perm"] = perm
         side = torch.cuda.Stream()
@@ -323,27 +329,113 @@ class VAETrainer(Trainer):
             eng.packs.epoch += 1   # nothing packed during the eager warm-up may be reused by captured kernels
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             out = self._device_step(sX, sl, **kw)
+            # the step's (small, fp32) outputs packed into one buffer inside the graph: replays hand out one clone
+            flat = views = None
+            if all(t.dtype == torch.float32 for t in out):
+                flat = torch.cat([t.reshape(-1) for t in out])
+                views, o = [], 0
+                for t in out:
+                    views.append((o, o + t.numel(), tuple(t.shape)))
+                    o += t.numel()
         dbg("captured")
-        self._graph = dict(graph=graph, X=sX, label=sl, perm=perm, perm_host=perm_host, out=out,
+        self._graph = dict(graph=graph, X=sX, label=sl, perm=perm, perm_host=perm_host, out=out, flat=flat, views=views,
                            launches=_ops.meter.launches() - before)
         return self._graph
 
     dist: DistSpec | None = None
 
-    def _sync_grads(self, params):
-        """data-parallel gradient averaging (one flat all-reduce); no-op on a single GPU."""
+    # ---- data-parallel gradient averaging -------------------------------------------------------------------------
+    # north_star: "gradients are allreduced overlapped with backward".  The decoder's gradients are complete as soon as the
+    # decoder backward returns (autograd accumulates them before it runs the latent block and the encoder), so they travel
+    # as a first bucket on a communication stream while the latent + encoder backward still compute; the encoder / heads
+    # bucket follows on the same stream.  The optimiser kernel waits for that stream and applies the 1/world.  Buckets are
+    # launched from post-accumulate-grad hooks (fork / join nodes inside a captured graph); which parameters receive a
+    # gradient is learnt from the first (un-overlapped) step.
+    overlap_grad_sync = True
+
+    def _comm_stream(self, device):
+        st = getattr(self, "_comm", None)
+        if st is None or st.device != torch.device(device):
+            st = self._comm = torch.cuda.Stream(device=device)
+        return st
+
+    def _allreduce(self, grads):
         d = self.dist
-        if d is None or d.world == 1:
-            return 1.0
+        if d.peer is not None:
+            d.peer.allreduce_chunked_(grads)   # pack -> publish -> pull + sum in rank order -> scatter back, <= one slot per call
+            return
         import torch.distributed as td
-        grads = [p.grad for p in params if p.grad is not None]
-        if d.peer is not None and sum(g.numel() for g in grads) * 4 + 16 * len(grads) <= d.peer.slot_bytes():
-            d.peer.allreduce_(grads)   # one kernel: pack -> publish -> pull + sum in rank order -> scatter back
-            return 1.0 / d.world
         flat = torch.cat([g.reshape(-1) for g in grads])
         td.all_reduce(flat, group=d.group)
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+    def _arm_buckets(self, params):
+        """after the first synchronous step: bucket 0 = decoder parameters, bucket 1 = everything else (encoder, heads)"""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        live = [p for p in params if p.grad is not None]
+        b0 = [p for p in live if names.get(id(p), "").startswith("decoder.")]
+        b1 = [p for p in live if not names.get(id(p), "").startswith("decoder.")]
+        st = self._buckets = dict(params=[b0, b1], left=[len(b0), len(b1)], of={}, fired=[False, False], handles=[])
+        for bi, bucket in enumerate(st["params"]):
+            for p in bucket:
+                st["of"][id(p)] = bi
+                st["handles"].append(p.register_post_accumulate_grad_hook(self._grad_ready))
+
+    def _grad_ready(self, p):
+        st = getattr(self, "_buckets", None)
+        d = self.dist
+        if st is None or d is None or d.world == 1 or not getattr(self, "_sync_armed", False):
+            return
+        bi = st["of"].get(id(p))
+        if bi is None:
+            return
+        st["left"][bi] -= 1
+        if st["left"][bi] == 0:
+            dev = p.device
+            comm, cur = self._comm_stream(dev), torch.cuda.current_stream(dev)
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                self._allreduce([q.grad for q in st["params"][bi]])
+            st["fired"][bi] = True
+
+    def _begin_grad_sync(self):
+        """call before backward: arms the hooks of this step"""
+        st = getattr(self, "_buckets", None)
+        d = self.dist
+        self._sync_armed = bool(st is not None and d is not None and d.world > 1 and self.overlap_grad_sync and d.peer is not None)
+        if self._sync_armed:
+            st["left"] = [len(b) for b in st["params"]]
+            st["fired"] = [False, False]
+
+    def _sync_grads(self, params, model_grads=False):
+        """data-parallel gradient averaging; returns the factor the optimiser applies (1/world).  No-op on a single GPU."""
+        d = self.dist
+        if d is None or d.world == 1:
+            return 1.0
+        st = getattr(self, "_buckets", None)
+        if model_grads and getattr(self, "_sync_armed", False) and st is not None and all(st["fired"]):
+            dev = params[0].device
+            torch.cuda.current_stream(dev).wait_stream(self._comm_stream(dev))   # both buckets were launched during backward
+            self._sync_armed = False
+            return 1.0 / d.world
+        self._sync_armed = False
+        grads = [p.grad for p in params if p.grad is not None]
+        self._allreduce(grads)
+        if model_grads and st is None and self.overlap_grad_sync and d.peer is not None:
+            self._arm_buckets(params)
         return 1.0 / d.world   # the rank average is applied by the optimiser kernel (grad_scale)
+
+    def _perm(self, n):
+        """CLUB-S permutation (mi_estimator.py:138): the global CPU generator on one GPU, like the reference; under data
+        parallelism a trainer-owned generator seeded identically on every rank, so all ranks draw the same permutation of
+        the global batch without a broadcast"""
+        d = self.dist
+        if d is None or d.world == 1:
+            return torch.randperm(n)
+        g = getattr(self, "_perm_gen", None)
+        if g is None:
+            g = self._perm_gen = torch.Generator().manual_seed(20240229)
+        return torch.randperm(n, generator=g)
 
 
 class CLEARVAETrainer(VAETrainer):
@@ -365,8 +457,9 @@ class CLEARVAETrainer(VAETrainer):
         self.optimizer.zero_grad()
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 1],
                                                         ps=[False, bool(hp["ps"])], sim_fn=self.sim_fn, eps=eps, dist=self.dist)
+        self._begin_grad_sync()
         torch.autograd.backward([recon, sc], [torch.ones_like(recon), self._weights_dev(X.device)])
-        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
+        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters()), model_grads=True))
         return recon, sc
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -430,14 +523,21 @@ class ClearTCVAETrainer(VAETrainer):
         self.optimizer.zero_grad()
         xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
                                                         sim_fn=self.sim_fn, eps=eps, dist=self.dist)
-        mi = tc.tc_bound(z, fp)
+        mi = tc.tc_bound(z, fp)   # mean over rows of a per-row quantity: the local mean is exactly this rank's share of the global one
+        self._begin_grad_sync()
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
-        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
+        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters()), model_grads=True))
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
+        d = self.dist
+        if d is not None and d.world > 1:
+            # `factor_shuffling` rolls the style half across the WHOLE batch (trainer.py:583-585: row i pairs with row i+1, the
+            # last row of a shard with the first row of the next rank's): every rank runs the (tiny, deterministic)
+            # discriminator step on the gathered global batch — identical gradients on all ranks, no gradient all-reduce
+            z2 = d.peer.gather([z2])[0] if (d.peer is not None and d.peer.fits([z2])) else _gather_rows(z2, d)
         factor_loss = tc.disc_grads(z2, fp)
-        fused_adam_step(self.factor_optimizer, self._sync_grads(list(fc.parameters())))
+        fused_adam_step(self.factor_optimizer)
         return recon, sc, mi.detach(), factor_loss.detach()
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int, factor_d_losses: list):
@@ -496,12 +596,25 @@ class ClearMIMVAETrainer(VAETrainer):
         D = vae.z_dim
         # --- VAE update (trainer.py:848-871)
         self.optimizer.zero_grad()
-        xhat, recon, z, sc, _ = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
-                                                        sim_fn=self.sim_fn, eps=eps, dist=self.dist)
-        zc, zs = z[:, :D], z[:, D:]
-        mi = est(zc, zs, perm) if (perm is not None and isinstance(est, CLUBSample)) else est(zc, zs)
-        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
-        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters())))
+        d = self.dist
+        dp = d is not None and d.world > 1
+        out = vae.fused_step_forward(X, label, temperature=hp["temperature"], snn=[1, 0], ps=[False, False],
+                                     sim_fn=self.sim_fn, eps=eps, dist=self.dist, gather_z=dp)
+        xhat, recon, z, sc = out[0], out[1], out[2], out[3]
+        # Data parallel: CLUB-S pairs row i with row perm(i) of the WHOLE batch and L1OutUB's `all_probs` spans all y
+        # (mi_estimator.py:138-143, 170-191), so the bound is evaluated on the gathered latents by every rank (a few CTAs,
+        # deterministic => identical on all ranks).  Each rank back-propagates into its own rows only; with the bound weighted
+        # by `world` the later rank-average of the parameter gradients equals the single-process global-batch gradient.
+        zb = out[5] if dp else z
+        zc, zs = zb[:, :D], zb[:, D:]
+        if isinstance(est, CLUBSample):
+            mi = est(zc, zs, perm if perm is not None else self._perm(zb.shape[0]))
+        else:
+            mi = est(zc, zs)
+        lam = hp["lambda"] * (d.world if dp else 1)
+        self._begin_grad_sync()
+        torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, lam)])
+        fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters()), model_grads=True))
         # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
         # The encoder is unchanged across the 5 iterations, so its output is computed once and its BatchNorm
         # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and
@@ -517,7 +630,6 @@ class ClearMIMVAETrainer(VAETrainer):
             else:   # CPU tensors: the latent op raises (no CPU path), exactly as before
                 dummy = torch.zeros(X.shape[0], dtype=torch.int64, device=X.device)
                 zs = [latent_block([mu_c, mu_s], [lv_c, lv_s], e[2 * j:2 * j + 2], dummy, snn=[0, 0], ps=[0, 0])[0] for j in range(5)]
-        d = self.dist
         # The five estimator updates (two ~10 us launches each, a handful of CTAs) depend only on the latents; the five
         # decoder passes only feed BatchNorm running statistics.  They run as two parallel branches — a side stream in
         # eager mode, a fork/join inside the captured graph — so the small estimator kernels fill SMs the decoder leaves idle.
@@ -532,7 +644,7 @@ class ClearMIMVAETrainer(VAETrainer):
                 # gradients bit-identical on all ranks, so the parameters stay in sync without five gradient all-reduces.
                 # The exchange sits on the estimator branch (the decoder passes do not wait for it); the join below
                 # orders it before the next step's collectives on every rank.
-                if d.peer is not None:
+                if d.peer is not None and d.peer.fits(zs):
                     z_est = d.peer.gather(zs)                                        # five pieces, one kernel, final layout
                 else:
                     import torch.distributed as td
@@ -570,6 +682,13 @@ class ClearMIMVAETrainer(VAETrainer):
 
     def evaluate(self, dataloader, verbose, epoch_id):
         return _evaluate(self, dataloader, verbose, epoch_id, style_term=False)
+
+
+def _gather_rows(t, dist):
+    import torch.distributed as td
+    out = torch.empty((dist.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    td.all_gather_into_tensor(out, t.contiguous(), group=dist.group)
+    return out
 
 
 def _forward_with_eps(vae, X, eps):

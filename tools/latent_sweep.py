@@ -30,7 +30,7 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=dev)
         from clear_vae_b200.peer import PeerComm
         dist = DistSpec(td.group.WORLD, rank, world, PeerComm.create(td.group.WORLD, rank, world, dev, nbytes=64 << 20))
