@@ -28,8 +28,15 @@ import os as _os
 REDUNDANT_ROWS_MAX = int(_os.environ.get("CLEARVAE_DP_REDUNDANT_ROWS", "8192"))   # data parallel: up to this global batch every rank computes all rows' statistics itself (one exchange per step)
 
 
+def _stream_key(device):
+    return torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+
+
 def _workspace(device, nbytes, tag="fwd"):
-    key = (device.type, device.index, tag)
+    """Zero-initialised scratch the kernels leave zeroed (tickets, partial sums).  One buffer per (device, stream, tag): the
+    layout of tickets / partials depends on the problem shape (callers put it in `tag`), and two launches that may run
+    concurrently on different streams must not share one."""
+    key = (device.type, device.index, _stream_key(device), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
@@ -67,7 +74,7 @@ class _LatentBlock(torch.autograd.Function):
         want_z = cfg["want_z"]
         use_lv = cfg["sim"] in _LOGVAR_SIMS
         if dist is None or dist.world == 1:
-            ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n))
+            ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n), ("fwd", B, B, D, n))
             z, scalars, stats = ops.latent_fwd(mu, logvar, eps, [None] * n, [None] * n, label, None, cfg["snn"], cfg["ps"], 0,
                                                cfg["sim"], cfg["loss"], cfg["tau"], True, want_z, ws)
             cols, lv_cols, label_cols, stats_all, row_off = [None] * n, [None] * n, None, list(stats), 0
@@ -84,7 +91,7 @@ class _LatentBlock(torch.autograd.Function):
             # with the slowest rank, not its bytes.  Values are those of the single-process global batch, identical on all ranks.
             redundant = bool(snn_terms) and Bg <= REDUNDANT_ROWS_MAX and not use_lv and not supcon
             if redundant:
-                ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n))
+                ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n), ("fwd", B, B, D, n))
                 z, scalars, _ = ops.latent_fwd(mu, logvar, eps, [None] * n, [None] * n, label, None, [0] * n, cfg["ps"], 0,
                                                cfg["sim"], cfg["loss"], cfg["tau"], True, want_z, ws)
                 pieces = [mu[i] for i in snn_terms] + [label] + ([z] if cfg["gather_z"] else [])
@@ -97,7 +104,7 @@ class _LatentBlock(torch.autograd.Function):
                 label_cols = got[len(snn_terms)]
                 z_all = got[-1] if cfg["gather_z"] else None
                 gmu = [cols[i] if cols[i] is not None else cols[snn_terms[0]] for i in range(n)]   # terms without an SNN loss do nothing here
-                ws = _workspace(mu[0].device, ops.latent_workspace_bytes(Bg, Bg, D, n), "fwd_global")
+                ws = _workspace(mu[0].device, ops.latent_workspace_bytes(Bg, Bg, D, n), ("fwd", Bg, Bg, D, n))
                 _, sc_g, stats_g = ops.latent_fwd(gmu, [None] * n, [None] * n, [None] * n, [None] * n, label_cols, None, cfg["snn"],
                                                   cfg["ps"], 0, cfg["sim"], cfg["loss"], cfg["tau"], True, False, ws)
                 scalars = torch.cat([scalars[:2], sc_g[2:]])      # (kl of the local rows | loss, sum, count of the global batch)
@@ -123,7 +130,7 @@ class _LatentBlock(torch.autograd.Function):
                         if use_lv:
                             lv_cols[i] = g[:, k * per + D:(k + 1) * per].contiguous()
                     label_cols = g[:, len(snn_terms) * per:].contiguous().view(torch.int64).view(-1)
-                ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, Bg, D, n))
+                ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, Bg, D, n), ("fwd", B, Bg, D, n))
                 z, scalars, stats = ops.latent_fwd(mu, logvar, eps, cols, lv_cols, label, label_cols, cfg["snn"], cfg["ps"], row_off,
                                                    cfg["sim"], cfg["loss"], cfg["tau"], False, want_z, ws)
                 stats_all = [None] * (2 * n if supcon else n)
@@ -183,7 +190,7 @@ class _LatentBlock(torch.autograd.Function):
                 dz = None
         B, D = mu[0].shape
         Bg = label_cols.numel() if label_cols is not None else B
-        ws = _workspace(mu[0].device, ops.latent_bwd_workspace_bytes(B, Bg, D, n), "bwd")   # column-split partials + tickets
+        ws = _workspace(mu[0].device, ops.latent_bwd_workspace_bytes(B, Bg, D, n), ("bwd", B, Bg, D, n))   # column-split partials + tickets
         dmu, dlv = ops.latent_bwd(mu, logvar, eps, cols, lv_cols, stats_all, dz, label, label_cols, cfg["snn"], cfg["ps"],
                                   ctx.row_off, cfg["sim"], cfg["loss"], cfg["tau"], scalars, dscal, ws)
         g_mu = list(dmu)

@@ -36,11 +36,13 @@ _MAX_WIDTH = 32
 _ws: dict = {}
 
 
-def _workspace(device, nbytes):
-    key = (device.type, device.index)
+def _workspace(device, nbytes, shape=()):
+    # one zeroed scratch per (device, stream, problem shape): ticket / partial-sum layouts depend on the shape, and launches on
+    # different streams may overlap
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0, shape)
     ws = _ws.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)  # word 0 = self-resetting ticket
+        ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)  # word 0 = self-resetting ticket
         _ws[key] = ws
     return ws
 
@@ -54,7 +56,7 @@ def _run(mode, x, y, perm, params):
     ops = _ops.ops()
     B, Dx = x.shape
     H, Dy = params[0].shape[0], y.shape[1]
-    ws = _workspace(x.device, ops.mi_workspace_bytes(mode, B, Dx, H, Dy))
+    ws = _workspace(x.device, ops.mi_workspace_bytes(mode, B, Dx, H, Dy), (mode, B, Dx, H, Dy))
     return ops.mi_estimator(mode, x, y, perm, params, ws)
 
 

@@ -17,11 +17,13 @@ TC_BOUND, TC_DISC = 0, 1
 _ws: dict = {}
 
 
-def _workspace(device, nbytes):
-    key = (device.type, device.index)
+def _workspace(device, nbytes, shape=()):
+    # one zeroed scratch per (device, stream, problem shape): ticket / partial-sum layouts depend on the shape, and launches on
+    # different streams may overlap
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0, shape)
     ws = _ws.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)  # word 0 = self-resetting ticket
+        ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)  # word 0 = self-resetting ticket
         _ws[key] = ws
     return ws
 
@@ -51,7 +53,7 @@ class _Bound(torch.autograd.Function):
     def forward(ctx, z, w1, b1, w2, b2):
         ops = _ops.ops()
         z = _rows(z)
-        ws = _workspace(z.device, ops.tc_workspace_bytes(TC_BOUND, z.shape[0], z.shape[1]))
+        ws = _workspace(z.device, ops.tc_workspace_bytes(TC_BOUND, z.shape[0], z.shape[1]), (TC_BOUND,) + tuple(z.shape))
         out, dz = ops.tc_factor(TC_BOUND, z, w1.detach(), b1.detach(), w2.detach().reshape(-1), b2.detach(), ws)
         ctx.save_for_backward(dz)
         return out[0]
@@ -72,7 +74,7 @@ def disc_grads(z, params):
     ops = _ops.ops()
     z = _rows(z.detach())
     w1, b1, w2, b2 = params
-    ws = _workspace(z.device, ops.tc_workspace_bytes(TC_DISC, z.shape[0], z.shape[1]))
+    ws = _workspace(z.device, ops.tc_workspace_bytes(TC_DISC, z.shape[0], z.shape[1]), (TC_DISC,) + tuple(z.shape))
     out, _ = ops.tc_factor(TC_DISC, z, w1.detach(), b1.detach(), w2.detach().reshape(-1), b2.detach(), ws)
     o = 1
     for p in params:

@@ -18,7 +18,7 @@ dist = DistSpec(td.group.WORLD, rank, world, peer)
 if rank == 0:
     print("collectives:", "peer-memory kernels (NVLink, cudaIpc)" if peer is not None else "NCCL (peer memory unavailable)", flush=True)
 g = torch.Generator().manual_seed(1)
-if peer is not None:
+if peer is not None and not os.environ.get("DP_CHECK_ONLY"):
     # peer kernels vs NCCL, eager and replayed from a CUDA graph (device-side call counter), odd sizes included
     gg = torch.Generator().manual_seed(100 + rank)
     a = [torch.randn(n, d, generator=gg).to(dev) for n, d in ((1024, 8), (1024, 2), (333, 3))]
@@ -90,7 +90,7 @@ if peer is not None:
     if rank == 0:
         print(f"peer kernels world={world}: match NCCL {bool(ok)}, all-reduce bit-identical across ranks {bool(same_bits)}, error flag {peer.error()}; "
               f"gather + all-reduce {t_peer:.1f} us vs NCCL {t_nccl:.1f} us", flush=True)
-for Bl, D in [(64, 8), (512, 32), (4096, 8)]:
+for Bl, D in ([] if os.environ.get("DP_CHECK_ONLY") else [(64, 8), (512, 32), (4096, 8)]):
     Bg = Bl * world
     mu_c, lv_c, mu_s, lv_s, e_c, e_s = ((torch.randn(Bg, D, generator=g) * s).to(dev) for s in (1, .3, 1, .3, 1, 1))
     lab = torch.randint(0, 10, (Bg,), generator=g).to(dev)
@@ -154,7 +154,11 @@ def trainer_pair(kind, est=None):
         return get_cleartcvae_trainer(1 / 8, 1, 5e-4, 1e-4, 16, 1e2, 0.1, dev, "VAE", 3)
     a, b = make(), make()
     b.dist = dist
+    b.overlap_grad_sync = os.environ.get("DP_OVERLAP", "1") == "1"
     b.model.dist, b.model.sync_bn = dist_nccl, True
+    b._local = {}
+    for p_ in b.model.parameters():   # local gradients as autograd delivers them (registered before any bucket hook)
+        p_.register_post_accumulate_grad_hook(lambda q, store=b._local: store.__setitem__(id(q), q.grad.detach().clone()) if q.grad is not None else None)
     return a, b
 
 
@@ -177,12 +181,17 @@ for kind, est in (("mim", "CLUBSample"), ("mim", "L1OutUB"), ("tc", None)):
         o1 = one.train_step(X, lab, **kw1)
         o2 = dp.train_step(X[sl].contiguous(), lab[sl].contiguous(), **kw2)
         torch.cuda.synchronize()
-        worst = 0.0
+        worst, errs, red_ok = 0.0, [], True
         for (k, p1), (_, p2) in zip(one.model.named_parameters(), dp.model.named_parameters()):
             if p1.grad is None:
                 continue
             e = ((p2.grad / world - p1.grad).norm() / (p1.grad.norm() + 1e-30)).item()   # dp grads hold the rank SUM after the all-reduce
             worst = max(worst, e)
+            errs.append((e, k))
+            want = dp._local[id(p2)].clone(); td.all_reduce(want)
+            red_ok &= ((p2.grad - want).norm() / (want.norm() + 1e-30)).item() < 1e-5
+        if rank == 0:
+            print("      reduction == NCCL sum of local gradients:", red_ok, "| largest deviations:", [(round(e_, 4), k_) for e_, k_ in sorted(errs, reverse=True)[:5]], flush=True)
         aux1 = one.mi_estimator if kind == "mim" else one.factor_cls
         aux2 = dp.mi_estimator if kind == "mim" else dp.factor_cls
         aux_err = max(((a_ - b_).abs().max() / (a_.abs().max() + 1e-30)).item() for a_, b_ in zip(aux1.parameters(), aux2.parameters()))
@@ -207,7 +216,7 @@ if peer is not None:
     # registration order): the overlapped all-reduce must return exactly their rank sum
     local = {}
     for p_ in ta.model.parameters():
-        p_.register_post_accumulate_grad_hook(lambda q: local.__setitem__(id(q), q.grad.detach().clone()))
+        p_.register_post_accumulate_grad_hook(lambda q: local.__setitem__(id(q), q.grad.detach().clone()) if q.grad is not None else None)
     X64 = torch.rand(16, 3, 64, 64, generator=gg).to(dev); y64 = torch.randint(0, 7, (16,), generator=gg).to(dev)
     e64 = (torch.randn(16, 32, generator=gg).to(dev), torch.randn(16, 32, generator=gg).to(dev))
     worst = 0.0
@@ -219,7 +228,7 @@ if peer is not None:
         for pa in ta.model.parameters():
             if pa.grad is not None:
                 want = local[id(pa)].clone(); td.all_reduce(want)       # NCCL sum of the local gradients
-                exact &= bool(torch.allclose(pa.grad, want, rtol=1e-6, atol=1e-9))
+                exact &= ((pa.grad - want).norm() / (want.norm() + 1e-30)).item() < 1e-5     # rank-order sum vs NCCL's order
         if rank == 0:
             print(f"   step {step}: overlapped buckets == NCCL sum of the local gradients: {exact}", flush=True)
         for pa, pb in zip(ta.model.parameters(), tb.model.parameters()):
