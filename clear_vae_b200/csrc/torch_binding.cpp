@@ -683,6 +683,50 @@ std::vector<Tensor> reparam_multi(at::TensorList mu, at::TensorList logvar, at::
   return z;
 }
 
+// ---- group evidence (ML-VAE / GVAE baselines)
+std::tuple<Tensor, Tensor, Tensor> group_evidence_fwd(int64_t mode, const Tensor& mu, const Tensor& logvar, const Tensor& gid, int64_t G) {
+  const c10::cuda::CUDAGuard guard(mu.device());
+  const int64_t B = mu.size(0), D = mu.size(1);
+  const float* pm = fptr(mu, "mu", B, D);
+  const float* pl = fptr(logvar, "logvar", B, D);
+  TORCH_CHECK(gid.is_cuda() && gid.scalar_type() == at::kLong && gid.is_contiguous() && gid.numel() == B, "clearvae: group ids must be int64 [B] on CUDA");
+  TORCH_CHECK(G >= 1, "clearvae: at least one group");
+  Tensor mg = at::empty({G, D}, mu.options()), lg = at::empty({G, D}, mu.options()), cnt = at::empty({G}, mu.options());
+  check_rc(clearvae_group_evidence_fwd((int32_t)mode, pm, pl, gid.data_ptr<int64_t>(), B, (int32_t)D, (int32_t)G, mg.data_ptr<float>(),
+                                       lg.data_ptr<float>(), cnt.data_ptr<float>(), cur_stream()), "group_evidence_fwd");
+  return {mg, lg, cnt};
+}
+
+std::tuple<Tensor, Tensor> group_evidence_bwd(int64_t mode, const Tensor& mu, const Tensor& logvar, const Tensor& gid, const Tensor& mg,
+                                              const Tensor& lg, const Tensor& cnt, const Tensor& dmg, const Tensor& dlg) {
+  const c10::cuda::CUDAGuard guard(mu.device());
+  const int64_t B = mu.size(0), D = mu.size(1), G = mg.size(0);
+  Tensor dmu = at::empty_like(mu), dlv = at::empty_like(mu);
+  check_rc(clearvae_group_evidence_bwd((int32_t)mode, fptr(mu, "mu", B, D), fptr(logvar, "logvar", B, D), gid.data_ptr<int64_t>(),
+                                       fptr(mg, "mu_grp", G, D), fptr(lg, "logvar_grp", G, D), cnt.data_ptr<float>(), fptr(dmg, "dmu_grp", G, D),
+                                       fptr(dlg, "dlogvar_grp", G, D), B, (int32_t)D, dmu.data_ptr<float>(), dlv.data_ptr<float>(), cur_stream()),
+           "group_evidence_bwd");
+  return {dmu, dlv};
+}
+
+Tensor group_reparam_fwd(const Tensor& mg, const Tensor& lg, const Tensor& eps, const Tensor& gid) {
+  const c10::cuda::CUDAGuard guard(eps.device());
+  const int64_t B = eps.size(0), D = eps.size(1), G = mg.size(0);
+  Tensor z = at::empty_like(eps);
+  check_rc(clearvae_group_reparam_fwd(fptr(mg, "mu_grp", G, D), fptr(lg, "logvar_grp", G, D), fptr(eps, "eps", B, D), gid.data_ptr<int64_t>(), B,
+                                      (int32_t)D, z.data_ptr<float>(), cur_stream()), "group_reparam_fwd");
+  return z;
+}
+
+std::tuple<Tensor, Tensor> group_reparam_bwd(const Tensor& dz, const Tensor& eps, const Tensor& gid, int64_t G) {
+  const c10::cuda::CUDAGuard guard(eps.device());
+  const int64_t B = eps.size(0), D = eps.size(1);
+  Tensor a = at::empty({G, D}, eps.options()), b = at::empty({G, D}, eps.options());
+  check_rc(clearvae_group_reparam_bwd(fptr(dz, "dz", B, D), fptr(eps, "eps", B, D), gid.data_ptr<int64_t>(), B, (int32_t)D, (int32_t)G,
+                                      a.data_ptr<float>(), b.data_ptr<float>(), cur_stream()), "group_reparam_bwd");
+  return {a, b};
+}
+
 // ---- one-shot collectives over peer memory (bases = every rank's buffer as mapped into this process)
 std::vector<void*> peer_bases(at::IntArrayRef bases) {
   TORCH_CHECK(!bases.empty() && bases.size() <= CLEARVAE_PEER_MAX_RANKS, "clearvae: 1..8 peer buffers");
@@ -778,6 +822,11 @@ TORCH_LIBRARY(clearvae, m) {
         "Tensor(e!) counter, float lr, float beta1, float beta2, float eps, float grad_scale) -> ()");
   m.def("bn_act_workspace_bytes() -> int", &bn_act_workspace_bytes);
   m.def("reparam_multi(Tensor[] mu, Tensor[] logvar, Tensor[] eps) -> Tensor[]");
+  m.def("group_evidence_fwd(int mode, Tensor mu, Tensor logvar, Tensor group_id, int G) -> (Tensor, Tensor, Tensor)");
+  m.def("group_evidence_bwd(int mode, Tensor mu, Tensor logvar, Tensor group_id, Tensor mu_grp, Tensor logvar_grp, Tensor count, "
+        "Tensor dmu_grp, Tensor dlogvar_grp) -> (Tensor, Tensor)");
+  m.def("group_reparam_fwd(Tensor mu_grp, Tensor logvar_grp, Tensor eps, Tensor group_id) -> Tensor");
+  m.def("group_reparam_bwd(Tensor dz, Tensor eps, Tensor group_id, int G) -> (Tensor, Tensor)");
   m.def("peer_gather(int[] bases, int rank, int buffer_bytes, Tensor[] src, Tensor(a!)[] dst) -> ()");
   m.def("peer_allreduce(int[] bases, int rank, int buffer_bytes, Tensor(a!)[] tensors) -> ()");
   m.def("conv_gemm(int[] geom, int role, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, "
@@ -786,6 +835,10 @@ TORCH_LIBRARY(clearvae, m) {
 }
 
 TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
+  m.impl("group_evidence_fwd", &group_evidence_fwd);
+  m.impl("group_evidence_bwd", &group_evidence_bwd);
+  m.impl("group_reparam_fwd", &group_reparam_fwd);
+  m.impl("group_reparam_bwd", &group_reparam_bwd);
   m.impl("latent_fwd", &latent_fwd);
   m.impl("snn_finalize", &snn_finalize);
   m.impl("latent_bwd", &latent_bwd);

@@ -199,19 +199,32 @@ class VAE(nn.Module):
 
     def generate(self, mu_c, logvar_c, mu_s, logvar_s, g_dict: dict | None = None, explicit=False):
         if g_dict is not None:
-            raise NotImplementedError("group-evidence (ML-VAE / GVAE) sampling is outside the CLEAR-VAE hot path")
-        eps_c = torch.randn_like(logvar_c)  # c first, then s: same Philox consumption as vae.py:70,73
-        eps_s = torch.randn_like(logvar_s)
-        dummy = torch.zeros(mu_c.shape[0], dtype=torch.int64, device=mu_c.device)
-        z, _ = latent_block([mu_c, mu_s], [logvar_c, logvar_s], [eps_c, eps_s], dummy, snn=[0, 0], ps=[0, 0])
+            # ML-VAE / GVAE (vae.py:69-73): the content code is sampled group-wise from the accumulated evidence, the style code
+            # per sample; same order of random draws as the reference (groups on the CPU generator first, then `randn_like`)
+            from ..group import groupwise_reparam_each
+            z_c, _, _ = groupwise_reparam_each(mu_c, logvar_c, g_dict)
+            z_s = self.sample(mu_s, logvar_s)
+            z = torch.cat([z_c, z_s], dim=-1)
+        else:
+            eps_c = torch.randn_like(logvar_c)  # c first, then s: same Philox consumption as vae.py:70,73
+            eps_s = torch.randn_like(logvar_s)
+            dummy = torch.zeros(mu_c.shape[0], dtype=torch.int64, device=mu_c.device)
+            z, _ = latent_block([mu_c, mu_s], [logvar_c, logvar_s], [eps_c, eps_s], dummy, snn=[0, 0], ps=[0, 0])
         xhat = self.decode(z)
         return (xhat, z) if explicit else xhat
 
     def forward(self, x, label=None, explicit=False) -> tuple:
-        if label is not None:
-            raise NotImplementedError("label-conditioned group evidence (ML-VAE / GVAE) is outside the CLEAR-VAE hot path")
         mu_c, logvar_c, mu_s, logvar_s = self.encode(x)
+        g_dict = None
+        if label is not None:  # ML-VAE / GVAE: content parameters become the [G, D] group evidence (vae.py:84-88)
+            from ..group import accumulate_group_evidence
+            mu_c, logvar_c, g_dict = accumulate_group_evidence(mu_c, logvar_c, label, mode=self.mode)
         latent_params = {"mu_c": mu_c, "logvar_c": logvar_c, "mu_s": mu_s, "logvar_s": logvar_s}
+        if g_dict is not None:
+            if explicit:
+                xhat, z = self.generate(mu_c, logvar_c, mu_s, logvar_s, g_dict, True)
+                return xhat, latent_params, z
+            return self.generate(mu_c, logvar_c, mu_s, logvar_s, g_dict, False), latent_params
         if explicit:
             xhat, z = self.generate(mu_c, logvar_c, mu_s, logvar_s, None, True)
             return xhat, latent_params, z

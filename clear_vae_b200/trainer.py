@@ -728,3 +728,213 @@ def _evaluate(tr, dataloader, verbose, epoch_id, style_term):
         print("val_recontr_loss={:.3f}, val_kl_c={:.3f}, val_kl_s={:.3f}, val_c_loss={:.3f}".format(*t[:4])
               + (", val_s_loss={:.3f}".format(t[4]) if style_term else ""))
     return mig, float(t[0])
+
+
+# ======================================================================================================================
+# Comparison baselines of the reference's experiment scripts: supervised CNN / LAM classifiers on the
+# same conv trunk, the downstream MLP probe on frozen content latents, and the ML-VAE / GVAE group-evidence VAEs.  Same class
+# names, constructor signatures and loop semantics as `code/src/trainer.py:92-412`; the conv stacks (forward and backward) run
+# on the sm_100a kernels, the optimiser step is the fused Adam kernel.
+# ======================================================================================================================
+def _classifier_eval(trainer, forward, dataloader, verbose, epoch_id):
+    from .losses import accurary, auc
+    all_y, all_logits = [], []
+    with torch.no_grad():
+        for batch in tqdm(dataloader, disable=not verbose, desc=f"val-epoch {epoch_id}"):
+            X_batch, y_batch = batch[0], batch[1].reshape(-1)
+            all_logits.append(forward(X_batch.to(trainer.device)))
+            all_y.append(y_batch)
+    all_y, all_logits = torch.cat(all_y), torch.cat(all_logits)
+    return auc(all_logits, all_y), accurary(all_logits, all_y)
+
+
+class _ClassifierValid:
+    def _valid(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        if verbose:
+            import numpy as np
+            (aupr_scores, auroc_scores), acc = self.evaluate(dataloader, verbose, epoch_id)
+            print("val_aupr:", aupr_scores)
+            print(np.mean(list(aupr_scores.values())).round(3))
+            print("val_auroc:", auroc_scores)
+            print(np.mean(list(auroc_scores.values())).round(3))
+            print("val_acc:", acc.numpy().round(3))
+
+
+class DownstreamMLPTrainer(_ClassifierValid, Trainer):
+    """MLP probe on the (frozen) content means `vae.encode(x)[0]` (trainer.py:92-165)."""
+
+    def __init__(self, vae: nn.Module, model: nn.Module, optimizer: Optimizer, criterion: nn.Module, verbose_period: int,
+                 device: torch.device, transform=None) -> None:
+        super().__init__(model, optimizer, verbose_period, device, transform)
+        self.criterion = criterion
+        self.vae = vae
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        self.model.train()
+        with tqdm(dataloader, unit="batch", disable=not verbose) as bar:
+            bar.set_description(f"epoch {epoch_id}")
+            for batch in bar:
+                X_batch, y_batch = batch[0].to(self.device), batch[1].reshape(-1).long().to(self.device)
+                if self.transform:
+                    X_batch = self.transform(X_batch)
+                self.optimizer.zero_grad()
+                mu_c = self.vae.encode(X_batch)[0]
+                loss = self.criterion(self.model(mu_c), y_batch)
+                loss.backward()
+                self.optimizer.step()
+                bar.set_postfix(loss=float(loss))
+
+    def evaluate(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        self.model.eval()
+        return _classifier_eval(self, lambda X: self.model(self.vae.encode(X)[0]), dataloader, verbose, epoch_id)
+
+
+class SimpleCNNTrainer(_ClassifierValid, Trainer):
+    """Supervised CNN baseline (trainer.py:168-232): cross-entropy on `cnn(x)`."""
+
+    def __init__(self, model: nn.Module, optimizer: Optimizer, criterion: nn.Module, verbose_period: int, device: torch.device,
+                 transform=None) -> None:
+        super().__init__(model, optimizer, verbose_period, device, transform)
+        self.criterion = criterion
+
+    def train_step(self, X_batch, y_batch):
+        self.optimizer.zero_grad()
+        loss = self.criterion(self.model(X_batch), y_batch)
+        loss.backward()
+        fused_adam_step(self.optimizer)
+        return loss.detach()
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        self.model.train()
+        with tqdm(dataloader, unit="batch", disable=not verbose) as bar:
+            bar.set_description(f"epoch {epoch_id}")
+            for batch in bar:
+                X_batch, y_batch = batch[0].to(self.device), batch[1].reshape(-1).long().to(self.device)
+                if self.transform:
+                    X_batch = self.transform(X_batch)
+                loss = self.train_step(X_batch, y_batch)
+                if verbose:
+                    bar.set_postfix(loss=float(loss))
+
+    def evaluate(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        self.model.eval()
+        return _classifier_eval(self, self.model, dataloader, verbose, epoch_id)
+
+
+class LAMCNNTrainer(SimpleCNNTrainer):
+    """CNN + labelled LAM penalty (trainer.py:235-288): every sample is paired with a same-class sample of the batch."""
+
+    def __init__(self, model: nn.Module, optimizer: Optimizer, criterion: nn.Module, hyperparameter: dict[str, float],
+                 verbose_period: int, device: torch.device, transform=None):
+        super().__init__(model, optimizer, criterion, verbose_period, device, transform)
+        self.hyperparameter = hyperparameter
+
+    def ss_pairing(self, x, y):
+        """stratified shuffle: within every label stratum the samples are permuted (CPU generator, one `randperm` per
+        stratum in sorted-label order, like trainer.py:250-258)"""
+        new_x = x.clone()
+        for c in torch.unique(y):
+            _idx = (y == c).nonzero(as_tuple=True)[0]
+            _perm = torch.randperm(_idx.shape[0])
+            new_x[_idx] = x[_idx[_perm.to(_idx.device)]]
+        return new_x
+
+    def train_step(self, X_batch, y_batch, X_tilde_batch=None):
+        from .losses import lam_loss
+        cnn = self.model
+        if X_tilde_batch is None:
+            X_tilde_batch = self.ss_pairing(X_batch, y_batch)
+        self.optimizer.zero_grad()
+        logits = cnn(X_batch)
+        loss_ce = self.criterion(logits, y_batch)
+        loss_lam = lam_loss(cnn.net(X_batch), cnn.net(X_tilde_batch), y_batch, cnn.cls_head.weight)
+        loss = loss_ce + self.hyperparameter["lam_coef"] * loss_lam
+        loss.backward()
+        fused_adam_step(self.optimizer)
+        return loss_ce.detach(), loss_lam.detach()
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        self.model.train()
+        with tqdm(dataloader, unit="batch", disable=not verbose) as bar:
+            bar.set_description(f"epoch {epoch_id}")
+            for batch in bar:
+                X_batch, y_batch = batch[0].to(self.device), batch[1].reshape(-1).long().to(self.device)
+                if self.transform:
+                    X_batch = self.transform(X_batch)
+                loss_ce, loss_lam = self.train_step(X_batch, y_batch)
+                if verbose:
+                    bar.set_postfix(ce_loss=float(loss_ce), lam_loss=float(loss_lam))
+
+
+class HierarchicalVAETrainer(VAETrainer):
+    """ML-VAE / GVAE (trainer.py:291-412): the content parameters of a batch are pooled per label group
+    (`accumulate_group_evidence`), the content code is sampled group-wise, reconstruction and style KL are rescaled by
+    batch size / number of groups."""
+
+    def __init__(self, model: VAE, optimizer: Optimizer, hyperparameter: dict[str, float], verbose_period: int, device: torch.device,
+                 transform=None) -> None:
+        super().__init__(model, optimizer, verbose_period, device, transform)
+        self.hyperparameter = hyperparameter
+        self.annealer = LogisticAnnealer(loc=hyperparameter["loc"], scale=hyperparameter["scale"], beta=hyperparameter["beta"])
+
+    def fit(self, epochs: int, train_loader: DataLoader, valid_loader: None | DataLoader = None, eval_evidence_acc: bool = False):
+        for epoch in range(epochs):
+            verbose = (epoch % self.verbose_period) == 0
+            self._train(train_loader, verbose, epoch)
+            if valid_loader is not None:
+                self._valid(valid_loader, verbose, epoch, eval_evidence_acc)
+
+    def _group_adjust(self, B, m, *losses):
+        "B: batch size; m: number of groups"
+        return [loss * B / m for loss in losses]
+
+    def train_step(self, X, label):
+        """one iteration of trainer.py:338-362; returns (reconstr_loss, kl_c, kl_s) as logged there (after the group adjust)"""
+        vae = self.model
+        batch_size, n_groups = X.size(0), len(label.unique())
+        self.optimizer.zero_grad()
+        X_hat, latent_params = vae(X, label=label)
+        rec, kl_c, kl_s = vae_loss(X_hat, X, **latent_params)
+        rec, kl_s = self._group_adjust(batch_size, n_groups, rec, kl_s)
+        loss = rec + self.annealer(kl_c) + self.annealer(kl_s)
+        loss.backward()
+        fused_adam_step(self.optimizer)
+        self.annealer.step()
+        return rec.detach(), kl_c.detach(), kl_s.detach()
+
+    def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
+        self.model.train()
+        with tqdm(dataloader, unit="batch", disable=not verbose) as bar:
+            bar.set_description(f"epoch {epoch_id}")
+            for batch in bar:
+                X, label = self._batch(batch)
+                rec, kl_c, kl_s = self.train_step(X, label)
+                if verbose:
+                    bar.set_postfix(reconstr_loss=float(rec), kl_c=float(kl_c), kl_s=float(kl_s))
+
+    def _valid(self, dataloader, verbose, epoch_id, with_evidence_acc=False):
+        if verbose:
+            mig, mse = self.evaluate(dataloader, verbose, epoch_id, with_evidence_acc)
+            print(f"gMIG: {round(mig, 3)}; mse: {round(float(mse), 3)}")
+
+    def evaluate(self, dataloader, verbose, epoch_id, with_evidence_acc=False):
+        vae = self.model
+        vae.eval()
+        tot, n = None, 0
+        labels, lat_c, lat_s = [], [], []
+        with torch.no_grad():
+            for batch in tqdm(dataloader, disable=not verbose, desc=f"val-epoch {epoch_id}"):
+                X, label = self._batch(batch)
+                X_hat, latent_params, z = vae(X, label, explicit=True) if with_evidence_acc else vae(X, explicit=True)
+                vals = torch.stack(vae_loss(X_hat, X, **latent_params))
+                tot = vals if tot is None else tot + vals
+                n += 1
+                labels.append(label)
+                lat_c.append(z[:, :vae.z_dim])
+                lat_s.append(z[:, vae.z_dim:])
+        from .metrics import mutual_info_gap
+        mig = mutual_info_gap(torch.cat(labels), torch.cat(lat_c), torch.cat(lat_s))
+        t = (tot / n).tolist()
+        if verbose:
+            print("val_recontr_loss={:.3f}, val_kl_c={:.3f}, val_kl_s={:.3f}".format(*t))
+        return mig, float(t[0])

@@ -7,11 +7,14 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ..models.cnn import LAMCNN64Classifier, LAMCNNClassifier, SimpleCNN64Classifier, SimpleCNNClassifier
 from ..models.mi_estimator import CLUBSample, L1OutUB
 from ..models.vae import VAE, VAE64
-from ..trainer import CLEARVAETrainer, ClearMIMVAETrainer, ClearTCVAETrainer
+from ..trainer import (CLEARVAETrainer, ClearMIMVAETrainer, ClearTCVAETrainer, HierarchicalVAETrainer, LAMCNNTrainer,
+                       SimpleCNNTrainer)
 
 _ARCHS = {"VAE": VAE, "VAE64": VAE64}
+_CNN_ARCHS = {c.__name__: c for c in (SimpleCNNClassifier, SimpleCNN64Classifier, LAMCNNClassifier, LAMCNN64Classifier)}
 _ESTIMATORS = {"CLUBSample": CLUBSample, "L1OutUB": L1OutUB}
 
 
@@ -65,3 +68,31 @@ def get_clearmimvae_trainer(beta, mi_estimator: str, la, vae_lr, mi_estimator_lr
                               hyperparameter={"temperature": temperature, "beta": beta, "loc": 0, "scale": 1, "alpha": alpha,
                                               "lambda": la},
                               verbose_period=verbose_period, device=device)
+
+
+# ---- comparison baselines (trainer_utils.py:20-84) ----------------------------------------------------------------------
+def _cnn_arch(name):
+    if name not in _CNN_ARCHS:
+        raise NameError(f"name '{name}' is not defined")
+    return _CNN_ARCHS[name]
+
+
+def get_cnn_trainer(n_class, device, cnn_arch: str = "SimpleCNNClassifier", in_channel: int = 1, verbose_period: int = 5):
+    cnn = _cnn_arch(cnn_arch)(n_class=n_class, in_channel=in_channel).to(device)
+    optimizer = _adam(cnn.parameters(), 1e-4, device)
+    return SimpleCNNTrainer(cnn, optimizer, torch.nn.CrossEntropyLoss(), verbose_period=verbose_period, device=device)
+
+
+def get_lamcnn_trainer(n_class, device, lam_coef, cnn_arch: str = "LAMCNNClassifier", in_channel: int = 1, verbose_period: int = 5):
+    cnn = _cnn_arch(cnn_arch)(n_class=n_class, in_channel=in_channel).to(device)
+    optimizer = _adam(cnn.parameters(), 1e-4, device)
+    return LAMCNNTrainer(cnn, optimizer, torch.nn.CrossEntropyLoss(), {"lam_coef": lam_coef}, verbose_period=verbose_period,
+                         device=device)
+
+
+def get_hierarchical_vae_trainer(beta, vae_lr, z_dim, group_mode, device, vae_arch: str = "VAE", in_channel: int = 1,
+                                 verbose_period: int = 5):
+    vae = _arch(vae_arch)(total_z_dim=z_dim, in_channel=in_channel, group_mode=group_mode).to(device)
+    optimizer = _adam(vae.parameters(), vae_lr, device)
+    return HierarchicalVAETrainer(vae, optimizer, hyperparameter={"beta": beta, "scale": 1, "loc": 0}, verbose_period=verbose_period,
+                                  device=device)

@@ -337,6 +337,28 @@ int clearvae_reparam_multi(int32_t heads, int32_t draws, const float* const* mu_
                            const float* const* eps_host, float* const* z_host, int64_t B, int32_t D, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Group evidence of the ML-VAE / GVAE baselines (models/vae.py:159-223): `accumulate_group_evidence` and
+ * `groupwise_reparam_each` as segmented reductions over label groups.  group_id[i] in [0, G) is the rank of row i's label among
+ * the sorted unique labels of the batch (what `label.unique(sorted=True)` enumerates at vae.py:163); D <= 32.
+ *   fwd:  MLVAE  mu_g = sum_i mu_i e^{-lv_i} / sum_i e^{-lv_i},  lv_g = -LSE_i(-lv_i)          (vae.py:174-180)
+ *         GVAE   mu_g = mean_i mu_i,                              lv_g = LSE_i(lv_i) - log n_g   (vae.py:181-186)
+ *         count[g] = n_g (float)
+ *   bwd:  (dmu_grp, dlogvar_grp) [G, D] -> (dmu, dlogvar) [B, D], elementwise in the rows
+ *   reparam fwd:  z_i = mu_g(i) + eps_i exp(lv_g(i) / 2)                                         (vae.py:196-209)
+ *   reparam bwd:  dmu_grp[g] = sum_{i in g} dz_i,  dz_eps_grp[g] = sum_{i in g} dz_i eps_i  (d lv_g = dz_eps_grp * exp(lv_g / 2) / 2)
+ * ------------------------------------------------------------------------- */
+enum { CLEARVAE_GROUP_MLVAE = 0, CLEARVAE_GROUP_GVAE = 1 };
+int clearvae_group_evidence_fwd(int32_t mode, const float* mu, const float* logvar, const int64_t* group_id, int64_t B, int32_t D,
+                                int32_t G, float* mu_grp, float* logvar_grp, float* count, void* stream);
+int clearvae_group_evidence_bwd(int32_t mode, const float* mu, const float* logvar, const int64_t* group_id, const float* mu_grp,
+                                const float* logvar_grp, const float* count, const float* dmu_grp, const float* dlogvar_grp, int64_t B,
+                                int32_t D, float* dmu, float* dlogvar, void* stream);
+int clearvae_group_reparam_fwd(const float* mu_grp, const float* logvar_grp, const float* eps, const int64_t* group_id, int64_t B, int32_t D,
+                               float* z, void* stream);
+int clearvae_group_reparam_bwd(const float* dz, const float* eps, const int64_t* group_id, int64_t B, int32_t D, int32_t G, float* dmu_grp,
+                               float* dz_eps_grp, void* stream);
+
+/* ---------------------------------------------------------------------------
  * One-shot collectives over NVLink peer memory (data-parallel step).  They replace the small NCCL
  * exchanges a data-parallel port of the reference loop would issue per step (trainer.py:446-492 under DDP semantics):
  * the all-gather of the similarity operands / labels / row statistics / estimator latents and the parameter-gradient

@@ -356,3 +356,42 @@ def roll_style_half(z):
 def logistic_anneal(step, loc, scale, beta):
     """LogisticAnnealer.slope (trainer.py:29-34)."""
     return beta / (1.0 + math.exp(-(step - loc) / scale))
+
+
+# --------------------------------------------------------------------------
+# ML-VAE / GVAE group evidence (models/vae.py:159-223), numpy fp64
+# --------------------------------------------------------------------------
+def group_evidence(mu, logvar, label, mode):
+    """accumulate_group_evidence: per sorted unique label g, MLVAE  mu_g = sum mu e^{-lv} / sum e^{-lv}, lv_g = -LSE(-lv)
+    (vae.py:174-180);  GVAE  mu_g = mean mu, lv_g = LSE(lv) - log n (vae.py:181-186).  Returns (mu_g, lv_g, groups, gid)."""
+    mu, logvar = np.asarray(mu, np.float64), np.asarray(logvar, np.float64)
+    groups, gid = np.unique(np.asarray(label), return_inverse=True)
+    mg, lg = np.zeros((len(groups), mu.shape[1])), np.zeros((len(groups), mu.shape[1]))
+    for g in range(len(groups)):
+        m, l = mu[gid == g], logvar[gid == g]
+        if mode == "MLVAE":
+            a = -l
+            L = np.log(np.exp(a - a.max(0)).sum(0)) + a.max(0)
+            mg[g], lg[g] = (m * np.exp(a - L)).sum(0), -L
+        elif mode == "GVAE":
+            mg[g] = m.mean(0)
+            lg[g] = np.log(np.exp(l - l.max(0)).sum(0)) + l.max(0) - np.log(len(m))
+        else:
+            raise NotImplementedError("only support using MLVAE or GVAE")
+    return mg, lg, groups, gid
+
+
+def group_evidence_grad(mu, logvar, label, mode, dmu_g, dlv_g):
+    """gradient of sum(mu_g * dmu_g) + sum(lv_g * dlv_g) w.r.t. (mu, logvar) — closed form used by the CUDA backward"""
+    mu, logvar = np.asarray(mu, np.float64), np.asarray(logvar, np.float64)
+    mg, lg, groups, gid = group_evidence(mu, logvar, label, mode)
+    n = np.bincount(gid).astype(np.float64)
+    if mode == "MLVAE":
+        p = np.exp(lg[gid] - logvar)
+        return p * dmu_g[gid], p * (dlv_g[gid] - dmu_g[gid] * (mu - mg[gid]))
+    return dmu_g[gid] / n[gid, None], dlv_g[gid] * np.exp(logvar - lg[gid]) / n[gid, None]
+
+
+def group_reparam(mu_g, lv_g, gid, eps):
+    """groupwise_reparam_each in the original row order (vae.py:196-221): z_i = mu_g(i) + eps_i exp(lv_g(i) / 2)"""
+    return mu_g[gid] + eps * np.exp(0.5 * lv_g[gid])

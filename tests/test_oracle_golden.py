@@ -160,3 +160,31 @@ def test_fp64_chunked_restatement_is_pinned():
         wg = lo.snn_grad(mu.numpy(), lab.numpy(), "cosine", 0.1, ps)
         assert abs(val - want) <= 1e-12 * abs(want)
         assert np.abs(grad.numpy() - wg).max() <= 1e-12 * np.abs(wg).max()
+
+
+def test_group_evidence_oracle_matches_reference(golden_dir):
+    """ML-VAE / GVAE evidence accumulation + its closed-form gradient + the group-wise reparameterisation (row f-4) against the
+    reference's autograd values recorded by tests/golden/make_golden_baselines.py."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "baselines.npz"))
+    mu, lv, lab = g["ge/mu"], g["ge/lv"], g["ge/label"]
+    for mode in ("MLVAE", "GVAE"):
+        mg, lg, groups, gid = lo.group_evidence(mu, lv, lab, mode)
+        assert np.array_equal(groups, g[f"ge/{mode}/keys"])
+        assert np.allclose(mg, g[f"ge/{mode}/mu_g"], rtol=1e-5, atol=1e-6) and np.allclose(lg, g[f"ge/{mode}/lv_g"], rtol=1e-5, atol=1e-6)
+        # noise as the reference draws it: torch.randn(n, D) per group (sorted labels) on the seeded CPU generator
+        torch.manual_seed(77)
+        idx = [np.nonzero(gid == k)[0] for k in range(len(groups))]
+        e = torch.cat([torch.randn(len(i), mu.shape[1]) for i in idx]).numpy()
+        eps = np.zeros_like(e)
+        eps[np.concatenate(idx)] = e
+        z = lo.group_reparam(mg, lg, gid, eps)
+        assert np.allclose(z, g[f"ge/{mode}/z"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(np.concatenate(idx), g[f"ge/{mode}/indices"])
+        # gradient of f = sum(mu_g w1) + sum(lv_g w2) + sum(z w3)
+        w1, w2, w3 = g["ge/w1"], g["ge/w2"], g["ge/w3"]
+        dmg = w1 + np.stack([w3[gid == k].sum(0) for k in range(len(groups))])
+        dlg = w2 + np.stack([(w3 * eps)[gid == k].sum(0) for k in range(len(groups))]) * 0.5 * np.exp(0.5 * lg)
+        dmu, dlv = lo.group_evidence_grad(mu, lv, lab, mode, dmg, dlg)
+        assert np.allclose(dmu, g[f"ge/{mode}/dmu"], rtol=1e-4, atol=1e-6), mode
+        assert np.allclose(dlv, g[f"ge/{mode}/dlv"], rtol=1e-4, atol=1e-6), mode
