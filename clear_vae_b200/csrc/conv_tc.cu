@@ -1599,6 +1599,40 @@ __global__ void pack_weight_kernel(const Plan plan, const float* __restrict__ w,
   }
 }
 
+// All packed copies of a model in ONE launch (after the optimiser step): a device-resident table of (plan, class, source weight,
+// destination, first block); a block finds its entry by binary search over the block offsets.  Replaces one pack_weight_kernel
+// launch per (layer, role) per step — ~20 launches of 3-12 us each on the critical path of the next GEMM.
+struct MultiPackEntry {
+  Plan plan;
+  const float* w;
+  __nv_bfloat16* out;
+  int cls;
+  int block0;     // first block of this (entry, class)
+  int nblocks;
+  int pad;
+};
+__global__ void pack_weight_multi_kernel(const MultiPackEntry* __restrict__ tab, int n) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const MultiPackEntry& e = tab[lo];
+  const Cls& c = e.plan.cls[e.cls];
+  const int n_pad = (e.plan.Nn + 15) / 16 * 16;
+  const long long total = (long long)n_pad * c.Kp;
+  const int Cs = e.plan.Cs, kreal = c.ntaps * Cs;
+  for (long long i = (long long)(blockIdx.x - e.block0) * blockDim.x + threadIdx.x; i < total; i += (long long)e.nblocks * blockDim.x) {
+    const int nn = (int)(i / c.Kp), k = (int)(i % c.Kp);
+    float v = 0.f;
+    if (nn < e.plan.Nn && k < kreal) {
+      const int t = k / Cs, ch = k - t * Cs;
+      v = e.w[nn * e.plan.ws_n + ch * e.plan.ws_c + c.wtap[t]];
+    }
+    e.out[c.w_off + i] = __float2bfloat16(v);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------
@@ -1775,6 +1809,45 @@ int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const f
   __nv_bfloat16* p1 = x3 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(packed) + one) : nullptr;
   __nv_bfloat16* p2 = x3 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(packed) + 2 * one) : nullptr;
   pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, weight, reinterpret_cast<__nv_bfloat16*>(packed), p1, p2);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t clearvae_conv_pack_multi_table_bytes(int32_t n_weights) {
+  return n_weights > 0 ? (size_t)n_weights * cvplan::kMaxClasses * sizeof(MultiPackEntry) : 0;
+}
+
+int clearvae_conv_pack_multi_build(int32_t n_weights, const clearvae_conv_geom* geoms_host, const int32_t* roles_host,
+                                   const float* const* weights, void* const* packed, void* table_host, int32_t* n_entries,
+                                   int32_t* n_blocks) {
+  if (n_weights <= 0 || !geoms_host || !roles_host || !weights || !packed || !table_host || !n_entries || !n_blocks) return CLEARVAE_EINVAL;
+  MultiPackEntry* tab = reinterpret_cast<MultiPackEntry*>(table_host);
+  int ne = 0, nb = 0;
+  for (int i = 0; i < n_weights; ++i) {
+    if (!weights[i] || !packed[i] || (roles_host[i] & CLEARVAE_ROLE_SPLIT3)) return CLEARVAE_EINVAL;   // split packs stay per weight
+    Plan plan;
+    if (!cvplan::make_plan(geoms_host[i], roles_host[i], BK, &plan)) return CLEARVAE_EUNSUPPORTED;
+    const int n_pad = (plan.Nn + 15) / 16 * 16;
+    for (int c = 0; c < plan.n_classes; ++c) {
+      MultiPackEntry& e = tab[ne++];
+      e.plan = plan;
+      e.w = weights[i];
+      e.out = reinterpret_cast<__nv_bfloat16*>(packed[i]);
+      e.cls = c;
+      e.block0 = nb;
+      e.nblocks = (int)std::min<long long>(((long long)n_pad * plan.cls[c].Kp + 255) / 256, 64);
+      e.pad = 0;
+      nb += e.nblocks;
+    }
+  }
+  *n_entries = ne;
+  *n_blocks = nb;
+  return 0;
+}
+
+int clearvae_conv_pack_multi_launch(const void* table_device, int32_t n_entries, int32_t n_blocks, void* stream) {
+  if (!table_device || n_entries <= 0 || n_blocks <= 0) return CLEARVAE_EINVAL;
+  pack_weight_multi_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const MultiPackEntry*>(table_device), n_entries);
   CV_LAUNCH_CHECK();
   return 0;
 }

@@ -277,6 +277,38 @@ Tensor conv_pack_weight(at::IntArrayRef geom, int64_t role, const Tensor& weight
   return packed;
 }
 
+// table of (geometry, role, weight, packed) tuples for conv_pack_multi: built on the host, returned as a CUDA uint8 tensor whose
+// first 8 bytes of metadata travel separately (entries, blocks)
+std::tuple<Tensor, int64_t, int64_t> conv_pack_multi_build(at::IntArrayRef geoms_flat, at::IntArrayRef roles, at::TensorList weights,
+                                                          at::TensorList packed) {
+  const size_t n = weights.size();
+  TORCH_CHECK(n >= 1 && roles.size() == n && packed.size() == n && geoms_flat.size() == 9 * n, "clearvae: conv_pack_multi_build argument sizes");
+  std::vector<clearvae_conv_geom> g(n);
+  std::vector<int32_t> r(n);
+  std::vector<const float*> w(n);
+  std::vector<void*> pk(n);
+  for (size_t i = 0; i < n; ++i) {
+    g[i] = geom_from(geoms_flat.slice(9 * i, 9));
+    r[i] = (int32_t)roles[i];
+    check_f32(weights[i], "weight");
+    TORCH_CHECK(packed[i].is_cuda() && packed[i].scalar_type() == at::kBFloat16 && packed[i].is_contiguous(), "clearvae: packed buffers must be bf16 CUDA tensors");
+    TORCH_CHECK((size_t)packed[i].numel() * 2 >= clearvae_conv_packed_weight_bytes(&g[i], r[i]), "clearvae: packed buffer too small");
+    w[i] = weights[i].data_ptr<float>();
+    pk[i] = packed[i].data_ptr();
+  }
+  const size_t bytes = clearvae_conv_pack_multi_table_bytes((int32_t)n);
+  Tensor host = at::empty({(int64_t)bytes}, at::TensorOptions().dtype(at::kByte));
+  int32_t ne = 0, nb = 0;
+  check_rc(clearvae_conv_pack_multi_build((int32_t)n, g.data(), r.data(), w.data(), pk.data(), host.data_ptr(), &ne, &nb), "conv_pack_multi_build");
+  return {host, (int64_t)ne, (int64_t)nb};   // host table: the caller pins it and uploads it (stream-ordered, capture-safe)
+}
+
+void conv_pack_multi(const Tensor& table, int64_t n_entries, int64_t n_blocks) {
+  const c10::cuda::CUDAGuard guard(table.device());
+  TORCH_CHECK(table.is_cuda() && table.scalar_type() == at::kByte, "clearvae: the pack table must be a CUDA uint8 tensor");
+  check_rc(clearvae_conv_pack_multi_launch(table.data_ptr(), (int32_t)n_entries, (int32_t)n_blocks, cur_stream()), "conv_pack_multi");
+}
+
 void conv_gemm(at::IntArrayRef geom, int64_t role, int64_t batch, const Tensor& src, at::IntArrayRef src_strides,
                const OptTensor& pre_scale, const OptTensor& pre_shift, bool pre_relu, const Tensor& packed_weight,
                const OptTensor& bias, Tensor dst, at::IntArrayRef dst_strides, int64_t epilogue, const OptTensor& mask_src,
@@ -790,6 +822,8 @@ TORCH_LIBRARY(clearvae, m) {
   m.def("recon_bwd(Tensor xhat, Tensor x, Tensor grad_out) -> Tensor");
   m.def("recon_workspace_bytes() -> int", &recon_workspace_bytes);
   m.def("conv_pack_weight(int[] geom, int role, Tensor weight) -> Tensor");
+  m.def("conv_pack_multi_build(int[] geoms_flat, int[] roles, Tensor[] weights, Tensor[] packed) -> (Tensor, int, int)");
+  m.def("conv_pack_multi(Tensor table, int n_entries, int n_blocks) -> ()");
   m.def("conv_direct_fwd(int[] geom, int batch, Tensor src, int[] src_strides, Tensor? pre_scale, Tensor? pre_shift, bool pre_relu, "
         "Tensor weight, Tensor? bias, Tensor(a!) dst, int[] dst_strides, Tensor(b!)? stats) -> bool");
   m.def("conv_direct_wgrad(int[] geom, int batch, Tensor src, int[] src_strides, Tensor dy, int[] dy_strides, Tensor(a!) dweight) -> bool");
@@ -846,6 +880,8 @@ TORCH_LIBRARY_IMPL(clearvae, CUDA, m) {
   m.impl("recon_fwd", &recon_fwd);
   m.impl("recon_bwd", &recon_bwd);
   m.impl("conv_pack_weight", &conv_pack_weight);
+  m.impl("conv_pack_multi_build", &conv_pack_multi_build);
+  m.impl("conv_pack_multi", &conv_pack_multi);
   m.impl("conv_gemm", &conv_gemm);
   m.impl("conv_direct_fwd", &conv_direct_fwd);
   m.impl("conv_wgrad", &conv_wgrad);

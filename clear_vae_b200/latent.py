@@ -25,7 +25,7 @@ S_KL0, S_KL1, S_LOSS0, S_LOSS1, S_SUM0, S_SUM1, S_CNT0, S_CNT1 = range(8)
 
 _workspaces: dict = {}
 import os as _os
-REDUNDANT_ROWS_MAX = int(_os.environ.get("CLEARVAE_DP_REDUNDANT_ROWS", "8192"))   # data parallel: up to this global batch every rank computes all rows' statistics itself (one exchange per step)
+REDUNDANT_ROWS_MAX = int(_os.environ.get("CLEARVAE_DP_REDUNDANT_ROWS", "4096"))   # data parallel: up to this global batch every rank computes all rows' statistics itself (one exchange per step)
 
 
 def _stream_key(device):
@@ -86,9 +86,11 @@ class _LatentBlock(torch.autograd.Function):
             supcon = cfg["loss"] != 0           # SupCon row losses: the op returns [stats..., aux...] (one more per-row statistic)
             # ---- one exchange per step (global batch <= REDUNDANT_ROWS_MAX): reparameterisation + KL of the local rows first, so
             # the sampled z can travel WITH the similarity operands and labels in a single gather; every rank then evaluates the
-            # row statistics of ALL global rows itself (Bg x Bg pairs instead of B x Bg: tens of microseconds at Bg = 8192 on
-            # the tensor-core path) — cheaper than a second exchange of the [B, 2] statistics, whose cost is the synchronisation
-            # with the slowest rank, not its bytes.  Values are those of the single-process global batch, identical on all ranks.
+            # row statistics of ALL global rows itself (Bg x Bg pairs instead of B x Bg) — cheaper than a second exchange of the
+            # [B, 2] statistics, whose cost is the synchronisation with the slowest rank, not its bytes, as long as the global
+            # batch is small: measured at B = 1024 per GPU, 2 GPUs 1.71 -> 1.61 ms per step; at 8 GPUs (8192 global rows) the
+            # all-rows forward costs 0.13 ms more than it saves, hence the 4096-row limit.  Values are those of the single-process
+            # global batch, identical on all ranks.
             redundant = bool(snn_terms) and Bg <= REDUNDANT_ROWS_MAX and not use_lv and not supcon
             if redundant:
                 ws = _workspace(mu[0].device, ops.latent_workspace_bytes(B, B, D, n), ("fwd", B, B, D, n))

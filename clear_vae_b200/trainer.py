@@ -79,7 +79,7 @@ class DevicePrefetcher:
     dependency and starts at once.  Source tensors should be pinned (`DataLoader(pin_memory=True)`).  Same batches,
     same order as the wrapped iterable; batch i stays valid until the consumer asks for batch i+2."""
 
-    NSLOT = 3
+    NSLOT = 5   # device input slots: the host may stage up to four batches ahead of the step that is executing
 
     def __init__(self, batches, device, transform=None):
         self.batches, self.device, self.transform = batches, torch.device(device), transform
@@ -105,7 +105,7 @@ class DevicePrefetcher:
         k = i % self.NSLOT
         Xd, ld = slots[k]
         if self._consumed[k] is not None:
-            self._consumed[k].synchronize()      # the step that read this slot (batch i-3): normally long finished
+            self._consumed[k].synchronize()      # the step that read this slot (batch i - NSLOT): normally long finished
         with torch.cuda.stream(self.stream):
             Xd.copy_(X, non_blocking=True)
             ld.copy_(label, non_blocking=True)
@@ -175,15 +175,18 @@ class VAETrainer(Trainer):
     # buffer read at graph-execution time could already hold a later step's values; a slot is rewritten only after the
     # step that last used it has consumed it (`_slot_done`), which bounds the run-ahead to two steps.
     _step_no = 0
+    NSTAGE = 4   # pinned staging slots of the host-written step inputs = how many steps the host may run ahead of the device
+                 # (data parallel: a late graph launch on ANY rank stalls every rank at the next collective, so the queue must
+                 # be deep enough to absorb host jitter; two slots left one step of slack)
 
     def _slot(self):
-        return self._step_no & 1
+        return self._step_no % self.NSTAGE
 
     def _begin_step(self):
         self._step_no += 1
         ev = getattr(self, "_slot_done", None)
         if ev is None:
-            ev = self._slot_done = [None, None]
+            ev = self._slot_done = [None] * self.NSTAGE
         if ev[self._slot()] is not None:
             ev[self._slot()].synchronize()
 
@@ -197,7 +200,7 @@ class VAETrainer(Trainer):
         """grad weights of the packed scalars (kl_c, kl_s, c, s, ...) for autograd.backward, staged in pinned memory."""
         host = getattr(self, "_w_host", None)
         if host is None:
-            host = torch.zeros(2, 8, dtype=torch.float32)
+            host = torch.zeros(self.NSTAGE, 8, dtype=torch.float32)
             if torch.cuda.is_available():
                 host = host.pin_memory()
             self._w_host = host
@@ -217,6 +220,20 @@ class VAETrainer(Trainer):
     overlap_branches = True   # False: every kernel of the step on one stream (bench.py's per-kernel event timing)
     _graph = None
 
+    # ---- packed bf16 GEMM operands: refreshed in ONE launch right after the optimiser step (csrc/conv_tc.cu:
+    # pack_weight_multi_kernel), so the next step's GEMMs find them ready instead of each packing its weight first
+    def _engine_of(self):
+        m = self.model
+        return getattr(m, "_engine", None) or getattr(getattr(m, "net", None), "_engine", None)
+
+    def _refresh_packs(self):
+        eng = self._engine_of()
+        if eng is not None:
+            eng.packs.refresh_all()
+
+    def _weights_signature(self):
+        return tuple(p._version for p in self.model.parameters())
+
     def _needs_perm(self):
         return False
 
@@ -229,10 +246,16 @@ class VAETrainer(Trainer):
         eng = getattr(self.model, "_engine", None)
         if eng is not None:
             eng.packs.epoch += 1   # packed-weight copies made inside a graph capture are valid for this step only
+            # weights written from Python since the last step (load_state_dict, a broadcast, a manual edit): the packed copies
+            # the replayed graph would read are stale -> refresh them eagerly (graph replays do not move the version counters)
+            if self.use_cuda_graph and getattr(self, "_w_sig", None) is not None and self._w_sig != self._weights_signature():
+                self._refresh_packs()
         if self.use_cuda_graph and not inject and X.is_cuda:
             out = self._graph_step(X, label)
         else:
             out = self._device_step(X, label, **inject)
+        if eng is not None:
+            self._w_sig = self._weights_signature()
         self._end_step(X.device)
         self.annealer.step()
         return out
@@ -306,7 +329,7 @@ class VAETrainer(Trainer):
         snap = self._snapshot_state(X.device)
         if self._needs_perm():
             nper = X.shape[0] * (self.dist.world if (self.dist is not None and self.dist.world > 1) else 1)   # permutation of the global batch
-            perm_host = torch.stack([torch.arange(nper), torch.arange(nper)]).pin_memory()   # two slots, rewritten before every replay
+            perm_host = torch.stack([torch.arange(nper)] * self.NSTAGE).pin_memory()   # one slot per staging step, rewritten before every replay
             perm = perm_host[0].to(X.device)
             kw["perm"] = perm
         side = torch.cuda.Stream()
@@ -318,6 +341,7 @@ class VAETrainer(Trainer):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._restore_state(snap, X.device)   # the warm-up steps were real updates: undo them (weights, BN buffers, Adam, RNG)
+        self._refresh_packs()                 # ... and re-pack the GEMM operands from the restored weights (one launch, eager)
         torch.cuda.synchronize()
         dbg("begin capture")
         graph = torch.cuda.CUDAGraph()
@@ -460,6 +484,7 @@ class CLEARVAETrainer(VAETrainer):
         self._begin_grad_sync()
         torch.autograd.backward([recon, sc], [torch.ones_like(recon), self._weights_dev(X.device)])
         fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters()), model_grads=True))
+        self._refresh_packs()
         return recon, sc
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -527,6 +552,7 @@ class ClearTCVAETrainer(VAETrainer):
         self._begin_grad_sync()
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, hp["lambda"])])
         fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters()), model_grads=True))
+        self._refresh_packs()
         # --- density-ratio discriminator update (trainer.py:680-699)
         with torch.no_grad():
             _, _, z2 = vae(X, explicit=True) if eps2 is None else _forward_with_eps(vae, X, eps2)
@@ -615,6 +641,7 @@ class ClearMIMVAETrainer(VAETrainer):
         self._begin_grad_sync()
         torch.autograd.backward([recon, sc, mi], [torch.ones_like(recon), self._weights_dev(X.device), torch.full_like(mi, lam)])
         fused_adam_step(self.optimizer, self._sync_grads(list(vae.parameters()), model_grads=True))
+        self._refresh_packs()
         # --- estimator updates: 5 fresh forwards on detached latents (trainer.py:874-888)
         # The encoder is unchanged across the 5 iterations, so its output is computed once and its BatchNorm
         # running statistics receive 5 momentum updates; each iteration still draws fresh noise (c then s) and
@@ -736,6 +763,12 @@ def _evaluate(tr, dataloader, verbose, epoch_id, style_term):
 # names, constructor signatures and loop semantics as `code/src/trainer.py:92-412`; the conv stacks (forward and backward) run
 # on the sm_100a kernels, the optimiser step is the fused Adam kernel.
 # ======================================================================================================================
+def _refresh_model_packs(model):
+    eng = getattr(model, "_engine", None) or getattr(getattr(model, "net", None), "_engine", None)
+    if eng is not None:
+        eng.packs.refresh_all()
+
+
 def _classifier_eval(trainer, forward, dataloader, verbose, epoch_id):
     from .losses import accurary, auc
     all_y, all_logits = [], []
@@ -802,6 +835,7 @@ class SimpleCNNTrainer(_ClassifierValid, Trainer):
         loss = self.criterion(self.model(X_batch), y_batch)
         loss.backward()
         fused_adam_step(self.optimizer)
+        _refresh_model_packs(self.model)
         return loss.detach()
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -851,6 +885,7 @@ class LAMCNNTrainer(SimpleCNNTrainer):
         loss = loss_ce + self.hyperparameter["lam_coef"] * loss_lam
         loss.backward()
         fused_adam_step(self.optimizer)
+        _refresh_model_packs(self.model)
         return loss_ce.detach(), loss_lam.detach()
 
     def _train(self, dataloader: DataLoader, verbose: bool, epoch_id: int):
@@ -899,6 +934,7 @@ class HierarchicalVAETrainer(VAETrainer):
         loss = rec + self.annealer(kl_c) + self.annealer(kl_s)
         loss.backward()
         fused_adam_step(self.optimizer)
+        self._refresh_packs()
         self.annealer.step()
         return rec.detach(), kl_c.detach(), kl_s.detach()
 

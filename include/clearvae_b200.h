@@ -183,6 +183,16 @@ size_t clearvae_conv_packed_weight_bytes(const clearvae_conv_geom* g, int32_t ro
 /* fp32 reference-layout weight -> bf16 packed GEMM operand(s) of (geometry, role) */
 int clearvae_conv_pack_weight(const clearvae_conv_geom* g, int32_t role, const float* weight, void* packed, void* stream);
 
+/* All packed operands of a model refreshed in ONE launch (after the optimiser step, for the next step): `build` is pure host
+ * code that fills a table (clearvae_conv_pack_multi_table_bytes(n) bytes) describing n (geometry, role, weight, packed buffer)
+ * tuples; the caller copies the table to the device once (weights and packed buffers are persistent) and replays `launch`.
+ * Split-mode roles are not accepted (their packs stay per weight). */
+size_t clearvae_conv_pack_multi_table_bytes(int32_t n_weights);
+int clearvae_conv_pack_multi_build(int32_t n_weights, const clearvae_conv_geom* geoms_host, const int32_t* roles_host,
+                                   const float* const* weights, void* const* packed, void* table_host, int32_t* n_entries,
+                                   int32_t* n_blocks);
+int clearvae_conv_pack_multi_launch(const void* table_device, int32_t n_entries, int32_t n_blocks, void* stream);
+
 int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
                        const clearvae_tensor4* src, const float* pre_scale, const float* pre_shift, int32_t pre_relu,
                        const void* packed_weight, const float* bias, const clearvae_tensor4* dst, int32_t epilogue,
