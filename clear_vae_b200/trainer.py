@@ -145,6 +145,17 @@ class DevicePrefetcher:
 
 
 class VAETrainer(Trainer):
+    def fit(self, epochs: int, train_loader: DataLoader, valid_loader: None | DataLoader = None):
+        out = super().fit(epochs, train_loader, valid_loader)
+        self._check_collectives()
+        return out
+
+    def _check_collectives(self):
+        """a peer-memory collective that timed out records the missing rank instead of hanging: surface it (once per fit)"""
+        d = getattr(self, "dist", None)
+        if d is not None and getattr(d, "peer", None) is not None:
+            d.peer.check()
+
     def prefetch(self, batches):
         """device batches of `batches` with the H2D copy of the next batch overlapped with the current step.  One prefetcher
         (its copy stream and device slots) lives on the trainer across epochs."""
@@ -383,9 +394,14 @@ class VAETrainer(Trainer):
             st = self._comm = torch.cuda.Stream(device=device)
         return st
 
+    # one-shot peer all-reduce: every rank pulls (world - 1) x bytes — ideal for the latency-bound 1 MB of a 28x28 model, wasteful
+    # for VAE64's 12 MB buckets on 4-8 GPUs (7 x 12 MB per rank against NCCL's ring / NVLS 2 x 7/8 x 12 MB): large buckets go to NCCL
+    PEER_ALLREDUCE_MAX_BYTES = 4 << 20
+
     def _allreduce(self, grads):
         d = self.dist
-        if d.peer is not None:
+        nbytes = sum(g.numel() for g in grads) * 4
+        if d.peer is not None and (nbytes <= self.PEER_ALLREDUCE_MAX_BYTES or d.world <= 2):
             d.peer.allreduce_chunked_(grads)   # pack -> publish -> pull + sum in rank order -> scatter back, <= one slot per call
             return
         import torch.distributed as td
@@ -532,6 +548,7 @@ class ClearTCVAETrainer(VAETrainer):
             self._train(train_loader, verbose, epoch, factor_d_losses)
             if valid_loader is not None:
                 self._valid(valid_loader, verbose, epoch)
+        self._check_collectives()
         return factor_d_losses
 
     def _host_pre(self):
@@ -602,6 +619,7 @@ class ClearMIMVAETrainer(VAETrainer):
             self._train(train_loader, verbose, epoch, mi_losses, mi_learning_losses)
             if valid_loader is not None:
                 self._valid(valid_loader, verbose, epoch)
+        self._check_collectives()
         return mi_losses, mi_learning_losses
 
     def _host_pre(self):

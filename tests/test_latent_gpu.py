@@ -357,3 +357,53 @@ def test_65536_latents_tensor_core_path_against_fp64(D):
         wg = wg * 100.0
         err = float((t.grad.double() - wg).abs().max())
         assert err <= GRAD_REL * float(wg.abs().max()) + 1e-12, (D, ps, err, float(wg.abs().max()))
+
+
+def test_data_parallel_shards_alternating_with_global_batches_on_one_gpu(monkeypatch):
+    """The data-parallel latent path of every rank, emulated on one GPU (the exchange is replaced by the known global tensors), run
+    ALTERNATELY with single-process global-batch calls in the same process: row gradients x 1/world and the loss must equal the
+    global run.  Regression test of the scratch-buffer bug found at 4 / 8 GPUs in round 2: the column-split backward's tickets /
+    partials have a shape-dependent layout, and one cached buffer per device was corrupted by alternating shapes."""
+    import clear_vae_b200.latent as L
+    from clear_vae_b200.latent import DistSpec, latent_block
+    world, Bl, D = 4, 96, 8
+    Bg = world * Bl
+    g = torch.Generator().manual_seed(44)
+    mu_c, lv_c, mu_s, lv_s, e_c, e_s = ((torch.randn(Bg, D, generator=g) * s).to(DEV) for s in (1, .3, 1, .3, 1, 1))
+    lab = torch.randint(0, 10, (Bg,), generator=g).to(DEV)
+    w = torch.tensor([0.1, 0.1, 100.0, 0.0, 0, 0, 0, 0], device=DEV)
+    table = {}
+
+    def fake_gather(t, dist):
+        return table[(tuple(t.shape[1:]), t.dtype)]
+
+    monkeypatch.setattr(L, "_all_gather_rows", fake_gather)
+    for redundant in (4096, 0):          # single-exchange path (all-rows statistics) and the two-exchange path
+        monkeypatch.setattr(L, "REDUNDANT_ROWS_MAX", redundant)
+        for rep in range(2):
+            full = [t.clone().requires_grad_(True) for t in (mu_c, lv_c, mu_s, lv_s)]
+            z, sc = latent_block([full[0], full[2]], [full[1], full[3]], [e_c, e_s], lab, snn=[1, 0], ps=[False, False], temperature=0.1)
+            torch.autograd.backward([sc], [w])
+            # what the exchanges would deliver: the global operands, labels, and (two-exchange path) the global row statistics
+            ops = __import__("clear_vae_b200._ops", fromlist=["ops"]).ops()
+            ws = L._workspace(lab.device, ops.latent_workspace_bytes(Bg, Bg, D, 2), ("test", Bg))
+            _, _, st = ops.latent_fwd([mu_c, mu_s], [None, None], [None, None], [None, None], [None, None], lab, None, [1, 0], [0, 0], 0, 0, 0,
+                                      0.1, True, False, ws)
+            table.clear()
+            table[((D,), torch.float32)] = mu_c
+            table[((), torch.int64)] = lab
+            table[((2,), torch.float32)] = st[0]
+            table[((D + 2,), torch.float32)] = torch.cat([mu_c, lab.view(Bg, 1).view(torch.float32)], dim=1)   # the packed NCCL exchange
+            for r in range(world):
+                sl = slice(r * Bl, (r + 1) * Bl)
+                loc = [t[sl].clone().requires_grad_(True) for t in (mu_c, lv_c, mu_s, lv_s)]
+                dist = DistSpec(None, r, world, None)
+                z2, sc2 = latent_block([loc[0], loc[2]], [loc[1], loc[3]], [e_c[sl].contiguous(), e_s[sl].contiguous()], lab[sl].contiguous(),
+                                       snn=[1, 0], ps=[False, False], temperature=0.1, dist=dist)
+                torch.autograd.backward([sc2], [w])
+                assert abs(float(sc2[2]) - float(sc[2])) <= 2e-6 * abs(float(sc[2])), (redundant, rep, r)
+                assert torch.allclose(z2, z[sl], rtol=0, atol=1e-6)
+                # SNN gradients come back scaled by `world`; the KL part is a local mean over Bl rows
+                got = loc[0].grad / world - 0.1 * loc[0].detach() / Bl / world
+                want = full[0].grad[sl] - 0.1 * full[0].detach()[sl] / Bg
+                assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()), (redundant, rep, r)
