@@ -132,7 +132,7 @@ class DevicePrefetcher:
             self._consumed = [None] * self.NSLOT
         for batch in self.batches:
             if self.enabled and i >= 2:   # the consumer has enqueued its step on batch i-2 (the one before `pending`)
-                e = torch.cuda.Event()
+                e = torch.cuda.Event(blocking=True)   # the host sleeps instead of spinning while it waits (8 ranks share the host cores)
                 e.record(torch.cuda.current_stream(self.device))
                 self._consumed[(i - 2) % self.NSLOT] = e
             staged = self._stage(batch, i)
@@ -203,7 +203,7 @@ class VAETrainer(Trainer):
 
     def _end_step(self, device):
         if torch.device(device).type == "cuda":
-            e = torch.cuda.Event()
+            e = torch.cuda.Event(blocking=True)   # the host sleeps instead of spinning while it waits (8 ranks share the host cores)
             e.record(torch.cuda.current_stream(device))
             self._slot_done[self._slot()] = e
 
