@@ -969,6 +969,19 @@ __global__ void __launch_bounds__(kPThreads, (BN <= 64 ? 2 : 1)) conv_tc_persist
 // double-buffered TMEM accumulator as conv_tc_persist_kernel.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTThreads = 192;
+// Residency / ring depth of the TMA kernel.  tools/persist_timeline.py shows the epilogue (TMEM load -> bias / mask -> stores ->
+// shared-memory statistics) setting the pace of the small-channel layers at ~1.1 tiles per microsecond per SM: MMA commits run
+// ahead of "epilogue done" by a growing margin.  Three CTAs per SM with two stages each (twelve epilogue warps instead of eight)
+// did NOT raise that rate (14.8 vs 15.4 us on convT 64->32, slower on convT 128->64), so the limit is a per-SM resource of
+// the epilogue code, not its dependent latency; two CTAs x three stages stay.
+template <int BN, bool MASKED>
+constexpr int tma_ctas_per_sm() { return BN > 64 ? 1 : 2; }
+template <int BN, bool MASKED>
+constexpr int tma_stages() { return BN > 64 ? 4 : 3; }
+template <int BN, bool MASKED>
+constexpr size_t tma_smem() {
+  return (size_t)tma_stages<BN, MASKED>() * (kAStage + BN * BK * 2) + (MASKED ? 2 : 1) * BM * kEpLd * 4 + 2 * 4 * BN * 4 + 256 + 1024;
+}
 
 struct TTile {
   int cls, n0, img0, h0;
@@ -991,9 +1004,10 @@ __device__ __forceinline__ bool t_get_tile(const GemmParams& p, int id, int BN, 
 }
 
 template <int BN, bool MASKED>
-__global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__ TmapPack tmB,
-                                                                                 const GemmParams p) {
-  constexpr int NSP = persist_stages<BN>();
+__global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) conv_tma_kernel(const __grid_constant__ TmapPack tmA,
+                                                                                              const __grid_constant__ TmapPack tmB,
+                                                                                              const GemmParams p) {
+  constexpr int NSP = tma_stages<BN, MASKED>();
   constexpr int kBStage = BN * BK * 2;
   constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -1014,6 +1028,9 @@ __global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cs = p.plan.Cs, cb = p.t_cb, kchunks = Cs / cb;
+  long long* const tl_buf = g_conv_timeline ? g_conv_timeline + (long long)blockIdx.x * 64 : nullptr;   // debug timeline (tools/persist_timeline.py)
+#define CV_TTL(tile_no, k) do { if (tl_buf && (tile_no) < 15) tl_buf[4 + (tile_no) * 4 + (k)] = gtimer(); } while (0)
+  if (tl_buf && threadIdx.x == 0) tl_buf[0] = gtimer();
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NSP; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -1038,8 +1055,10 @@ __global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel
       uint32_t kbg = 0;
       TTile tl;
       const uint32_t b_bytes = (uint32_t)BN * cb * 2;
-      for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x) {
+      int tno = 0;
+      for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tno) {
         const Cls& c = p.plan.cls[tl.cls];
+        CV_TTL(tno, 0);
         const uint32_t a_bytes = (uint32_t)(p.t_tn[tl.cls] * p.t_th[tl.cls] * p.t_tw[tl.cls]) * cb * 2;
         const int hbase = tl.h0 * p.plan.sh;
         for (int t = 0; t < c.ntaps; ++t) {
@@ -1051,6 +1070,7 @@ __global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel
             tma_load_2d(sB + s * kBStage, &tmB.t[tl.cls], &full[s], t * Cs + cc * cb, tl.n0);
           }
         }
+        CV_TTL(tno, 1);
       }
     }
   } else if (warp == 1) {
@@ -1081,6 +1101,7 @@ __global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[b]);
+        CV_TTL((int)tcount, 2);
       }
     }
   } else {
@@ -1110,10 +1131,17 @@ __global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel
     };
     uint32_t tcount = 0;
     TTile tl;
+    int map_cls = -1, n_l = 0, h_l = 0, wd = 0;   // this thread's (image, row, column) inside a tile: depends on the class only
     for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
       const Cls& c = p.plan.cls[tl.cls];
-      const int tw = p.t_tw[tl.cls], thw = p.t_th[tl.cls] * tw;
-      const int n_l = r / thw, rem = r - n_l * thw, h_l = rem / tw, wd = rem - h_l * tw;
+      if (tl.cls != map_cls) {
+        const int tw = p.t_tw[tl.cls], thw = p.t_th[tl.cls] * tw;
+        n_l = r / thw;
+        const int rem = r - n_l * thw;
+        h_l = rem / tw;
+        wd = rem - h_l * tw;
+        map_cls = tl.cls;
+      }
       const int hd = tl.h0 + h_l;
       const long long img = tl.img0 + n_l;
       const bool mvalid = n_l < p.t_tn[tl.cls] && img < p.batch && hd < c.Hd;
@@ -1223,12 +1251,15 @@ __global__ void __launch_bounds__(kTThreads, (BN <= 64 ? 2 : 1)) conv_tma_kernel
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
+      if (et == 0) CV_TTL((int)tcount, 3);
     }
     if (p.stats != nullptr && acc_n0 >= 0) flush();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (tl_buf && threadIdx.x == 0) tl_buf[1] = gtimer();
+#undef CV_TTL
 }
 
 // ---------------------------------------------------------------------------
@@ -1691,14 +1722,15 @@ int launch_persist(const TmapPack& tm, const GemmParams& p, cudaStream_t st) {
 }
 template <int BN, bool MASKED>
 int launch_tma(const TmapPack& tmA, const TmapPack& tmB, const GemmParams& p, cudaStream_t st) {
-  constexpr size_t smem = persist_smem<BN, MASKED>();
+  constexpr size_t smem = tma_smem<BN, MASKED>();
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  const int per_sm = (BN <= 64 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
+  // resident CTAs per SM: the launch bound (registers) and shared memory (+1 KiB the driver reserves per CTA)
+  const int per_sm = std::max(1, std::min<int>(tma_ctas_per_sm<BN, MASKED>(), (int)((227 * 1024) / (smem + 1024))));
   const int grid = std::min(p.n_tiles, per_sm * 148);
   conv_tma_kernel<BN, MASKED><<<grid, kTThreads, smem, st>>>(tmA, tmB, p);
   CV_LAUNCH_CHECK();

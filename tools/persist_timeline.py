@@ -36,7 +36,7 @@ def run(name, tr, k, op, cin, cout, hin):
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     print(f"== {name}: {t.shape[0]} CTAs, kernel span {float(t[:, 1].max() - t0) / 1e3:.1f} us, CTA life mean {float((t[:, 1] - t[:, 0]).mean()) / 1e3:.1f} us")
-    for tile in range(6):
+    for tile in range(10):
         s = t[:, 4 + tile * 4:8 + tile * 4]
         ok = (s > 0).all(1)
         if ok.sum() == 0:
