@@ -457,6 +457,9 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// tf32 head by truncation (one LOP3; cvt.rna.tf32.f32 is a four-instruction sequence on sm_100a).  x - tf32_trunc(x) is exact in
+// fp32 and below 2^-10 |x|, so a (head, tail) pair read by the tensor core as two tf32 operands carries x to 2^-20 relative.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -1052,6 +1055,12 @@ __global__ void __launch_bounds__(kTN) snn_bwd_kernel(const BwdParams p) {
 //   ->  second MMA with A = P taken from TMEM:  dN += P [N_hi | N_lo]   (same shared tile, read MN-major)
 //   The [128 x 2D] gradient accumulator stays in TMEM for the whole column sweep.
 // ---------------------------------------------------------------------------
+// optional per-role timeline of CTA (0, 0) (tools/latent_timeline.py, include/clearvae_b200_debug.h): clock64 stamps of the first
+// 64 column tiles, 16 slots per tile -- 0/1 producer (stage free, staged), 2/3 MMA (operands seen, S issued), 4/5 MMA (P seen,
+// second GEMM issued), 8 epilogue (S seen), 9-11 chunk loaded, 12-14 chunk computed, 15 P published
+__device__ long long* g_latent_timeline = nullptr;
+#define LAT_TL(jt, slot) do { if (tl != nullptr && (jt) < 64) tl[(jt) * 16 + (slot)] = clock64(); } while (0)
+
 template <int DP> struct TcBwdCfg {
   static constexpr int BN = 96;                       // columns per tile: 2 x (S/P_hi + P_lo) + dN must fit 512 TMEM columns
   static constexpr int KT = 3 * DP;
@@ -1065,18 +1074,26 @@ template <int DP> struct TcBwdCfg {
   // the gradient's max.  Every FLUSH tiles the accumulator is drained into an fp32 shared-memory copy ([2DP][128], one row per
   // epilogue thread) and restarted, which bounds the chain length (measured error then <= 2e-5 of max at 65536 columns).
   static constexpr int FLUSH = 32;
+  // tcgen05.mma instructions that accumulate into the same TMEM columns execute back to back at the pipe's LATENCY (~77 cycles
+  // for these 128 x 2DP x 8 instructions, 8-32 cycles of work each: tools/latent_timeline.py showed the issuing thread spending
+  // 1855 cycles per tile in the 24 dependent instructions of the second GEMM).  The k-steps therefore rotate over NACC
+  // independent accumulators, summed when they are drained.  TMEM: 2 x 2BN + NACC x 2DP <= 512 columns.
+  static constexpr int NACC = DP <= 16 ? 4 : 2;
   static constexpr int ACC_BYTES = 2 * DP * 128 * 4;
   static constexpr int SMEM = A_BYTES + NSB * (B_BYTES + B2_BYTES) + NSB * BN * 16 /*labels lo/hi, c, q*/ + ACC_BYTES + 2048 + 1024;
 };
 
+constexpr int kTcBwdThreads = 12 * 32;   // warp 0 MMA issuer, 1-3 column producers, 4-11 epilogue: 3 warps per scheduler
 template <int DP>
-__global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdParams p) {
   using namespace sm100;
   using C = TcBwdCfg<DP>;
   constexpr int BN = C::BN;
   constexpr int NSB = C::NSB;
   constexpr uint32_t kBufCols = 2 * BN;      // per buffer: [0,BN) S then P_hi, [BN,2BN) P_lo
-  constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulator [128 x 2DP]
+  constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulators NACC x [128 x 2DP]
+  constexpr int NACC = C::NACC;
+  static_assert(2 * kBufCols + NACC * 2 * DP <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -1098,6 +1115,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   const int D = p.D;
   const int ntiles = (int)((p.Bg + BN - 1) / BN);
   const float* cols = t.mu_cols ? t.mu_cols : t.mu;
+  long long* const tl = (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8))
+                            ? g_latent_timeline : nullptr;
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < NSB; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); sFlags[b] = 0; }
@@ -1106,13 +1125,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
     mbar_init(dn_taken, 4);
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   const long long hi_ref = (long long)(p.lab_c[0] >> 32);
-  if (threadIdx.x < 128) {
-    const long long i = m0 + threadIdx.x;
-    stage_split<DP>(t.mu + (i < p.B ? i : 0) * (long long)D, i < p.B, D, sA, 128, threadIdx.x, true);
+  if (threadIdx.x >= 128 && threadIdx.x < 256) {
+    const int rr = threadIdx.x - 128;
+    const long long i = m0 + rr;
+    stage_split<DP>(t.mu + (i < p.B ? i : 0) * (long long)D, i < p.B, D, sA, 128, rr, true);
 #pragma unroll
-    for (int c = 0; c < 2 * DP; ++c) sAcc[c * 128 + threadIdx.x] = 0.f;
+    for (int c = 0; c < 2 * DP; ++c) sAcc[c * 128 + rr] = 0.f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -1120,11 +1140,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ================= column-tile producers (one thread per column; warps 0-2 active) =================
-    if (threadIdx.x < BN) {
+  static_assert(BN == 96, "three producer warps, one thread per column");
+  if (warp >= 1 && warp < 4) {
+    // ================= column-tile producers (one thread per column; warps 1-3) =================
+    {
       // the global loads of tile jt + 1 (vector, label, row statistics) are in flight while tile jt is normalised and stored
-      const int cc = threadIdx.x;
+      const int cc = threadIdx.x - 32;
       float nv[DP];
       long long nlab;
       float na, nq;
@@ -1148,6 +1169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
         const bool valid = nvalid;
         if (jt + 1 < ntiles) prefetch(jt + 1);
         mbar_wait(&b_empty[b], ((jt / NSB) & 1) ^ 1);
+        LAT_TL(jt, 0);
         stage_split_vals<DP>(cvv, sB + b * C::B_BYTES, BN, cc, false, sB2 + b * C::B2_BYTES);
         sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
         sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
@@ -1158,49 +1180,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
         if (lane == 0 && any_diff) atomicOr(&sFlags[b], 1);   // sticky per stage: only ever forces the exact (slow) epilogue path
         fence_proxy_async();
         mbar_arrive(&b_full[b]);
+        LAT_TL(jt, 1);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 0) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = instr_desc(kFmtTF32, 128, BN, 0, 0);
       constexpr uint32_t idesc2 = instr_desc(kFmtTF32, 128, 2 * DP, 0, 0);
-      const uint32_t a_base = smem_u32(sA);
+      // descriptors differ only in their start-address field (bits [0,14) of the low word, 16-byte units): one add per instruction
+      const uint64_t a_desc0 = smem_desc(smem_u32(sA), 128 * 16, 128, kLayoutNone);
+      const uint64_t b_desc0 = smem_desc(smem_u32(sB), BN * 16, 128, kLayoutNone);
+      const uint64_t b2_desc0 = smem_desc(smem_u32(sB2), 2 * DP * 16, 128, kLayoutNone);
       uint32_t drains = 0;   // accumulator chunks handed to the epilogue so far
       auto mma2 = [&](int jt) {
         const int b = jt & 1, sb = jt % NSB;
         mbar_wait(&p_full[b], (jt >> 1) & 1);
         tc_fence_after();
+        LAT_TL(jt, 4);
         const bool restart = (jt % FLUSH) == 0;       // first tile of a chunk: the accumulator starts over
         if (restart && jt > 0) {                      // ... once the epilogue has drained the previous chunk
           mbar_wait(dn_taken, (drains - 1) & 1);
           tc_fence_after();
         }
-        const uint32_t b2 = smem_u32(sB2 + sb * C::B2_BYTES);
+        const uint64_t b2d = b2_desc0 + (uint32_t)(sb * (C::B2_BYTES >> 4));
+        const uint32_t p_col = tmem_base + b * kBufCols;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {        // A = P_hi, then P_lo (split keeps the coefficient at fp32 grade)
 #pragma unroll
           for (int k8 = 0; k8 < BN / 8; ++k8) {
-            const uint64_t bd = smem_desc(b2 + k8 * 2 * (2 * DP * 16), 2 * DP * 16, 128, kLayoutNone);
-            umma_tf32_ts(tmem_base + kDnCol, tmem_base + b * kBufCols + part * BN + k8 * 8, bd, idesc2,
-                         (restart && part == 0 && k8 == 0) ? 0u : 1u);
+            const uint64_t bd = b2d + (uint32_t)(k8 * ((2 * (2 * DP * 16)) >> 4));
+            const int acc = (part * (BN / 8) + k8) % NACC;
+            umma_tf32_ts(tmem_base + kDnCol + acc * 2 * DP, p_col + part * BN + k8 * 8, bd, idesc2,
+                         (restart && part == 0 && k8 < NACC) ? 0u : 1u);
           }
         }
         umma_commit(&b_empty[sb]);
+        LAT_TL(jt, 5);
         if ((jt + 1) % FLUSH == 0 && jt + 1 < ntiles) { umma_commit(dn_full); ++drains; }   // chunk complete -> drain
       };
       for (int jt = 0; jt < ntiles; ++jt) {
         const int b = jt & 1, sb = jt % NSB;
         mbar_wait(&b_full[sb], (jt / NSB) & 1);
         tc_fence_after();
-        const uint32_t b_base = smem_u32(sB + sb * C::B_BYTES);
+        LAT_TL(jt, 2);
+        const uint64_t bsd = b_desc0 + (uint32_t)(sb * (C::B_BYTES >> 4));
 #pragma unroll
         for (int k8 = 0; k8 < C::KT / 8; ++k8) {
-          const uint64_t ad = smem_desc(a_base + k8 * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
-          const uint64_t bd = smem_desc(b_base + k8 * 2 * (BN * 16), BN * 16, 128, kLayoutNone);
+          const uint64_t ad = a_desc0 + (uint32_t)(k8 * ((2 * (128 * 16)) >> 4));
+          const uint64_t bd = bsd + (uint32_t)(k8 * ((2 * (BN * 16)) >> 4));
           umma_tf32(tmem_base + b * kBufCols, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[b]);
+        LAT_TL(jt, 3);
         if (jt > 0) mma2(jt - 1);
       }
       mma2(ntiles - 1);
@@ -1208,7 +1240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
     }
   } else {
     // ================= epilogue: two groups of 4 warps alternate over the column tiles =================
-    const int ew = warp - 5, lane_grp = warp & 3, grp = ew >> 2;
+    const int ew = warp - 4, lane_grp = warp & 3, grp = ew >> 2;
     const int r = lane_grp * 32 + lane;
     const long long i = m0 + r;
     const long long my_lab = i < p.B ? p.lab_r[i] : 0;
@@ -1231,12 +1263,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       mbar_wait(dn_full, drained & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 2 * DP; c0 += 16) {
+      for (int c0 = 0; c0 < NACC * 2 * DP; c0 += 16) {
         uint32_t r16[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + kDnCol + (uint32_t)c0, r16);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) sAcc[(c0 + q) * 128 + r] += __uint_as_float(r16[q]);
+        for (int q = 0; q < 16; ++q) sAcc[((c0 + q) % (2 * DP)) * 128 + r] += __uint_as_float(r16[q]);
       }
       tc_fence_before();
       __syncwarp();
@@ -1249,6 +1281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
         while ((drained + 1) * FLUSH <= jt && (drained + 1) * FLUSH < ntiles) drain();
       mbar_wait(&s_full[b], (jt >> 1) & 1);
       tc_fence_after();
+      LAT_TL(jt, 8);
       const long long jbase = (long long)jt * BN;
       const int sb = jt % NSB;   // shared-memory stage of this column tile (b indexes the TMEM S/P buffer)
       const bool edge = (jbase + BN > p.Bg) || (diag >= jbase && diag < jbase + BN) || sFlags[sb] || my_hi_odd;
@@ -1262,6 +1295,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
         uint32_t rw[32], lw[32];
         tmem_ld32(tcol + (uint32_t)c0, rw);
         tmem_ld_wait();
+        LAT_TL(jt, 9 + c0 / 32);
         if (!edge) {
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
@@ -1281,7 +1315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
             b23.y = ((l4.w == my_lo) != ps) ? b23.y : 0.f;
             const float2 x01 = __fmul2_rn(e01, __ffma2_rn(b01, neg1, a01));
             const float2 x23 = __fmul2_rn(e23, __ffma2_rn(b23, neg1, a23));
-            const float2 h01 = make_float2(tf32_rna(x01.x), tf32_rna(x01.y)), h23 = make_float2(tf32_rna(x23.x), tf32_rna(x23.y));
+            const float2 h01 = make_float2(tf32_trunc(x01.x), tf32_trunc(x01.y)), h23 = make_float2(tf32_trunc(x23.x), tf32_trunc(x23.y));
             const float2 l01 = __ffma2_rn(h01, neg1, x01), l23 = __ffma2_rn(h23, neg1, x23);
             rw[q] = __float_as_uint(h01.x); rw[q + 1] = __float_as_uint(h01.y); rw[q + 2] = __float_as_uint(h23.x); rw[q + 3] = __float_as_uint(h23.y);
             lw[q] = __float_as_uint(l01.x); lw[q + 1] = __float_as_uint(l01.y); lw[q + 2] = __float_as_uint(l23.x); lw[q + 3] = __float_as_uint(l23.y);
@@ -1299,6 +1333,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
             lw[q] = __float_as_uint(x - h);
           }
         }
+        LAT_TL(jt, 12 + c0 / 32);
         tmem_st32(tcol + (uint32_t)c0, rw);
         tmem_st32(tcol + (uint32_t)(BN + c0), lw);
       }
@@ -1306,6 +1341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      LAT_TL(jt, 15);
     }
     // ---- final: dN (TMEM) -> chain through the normalisation, add KL / reparam gradients
     if (grp == 0) {
@@ -1314,12 +1350,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
       tc_fence_after();
       float acc[2 * DP];
 #pragma unroll
-      for (int c0 = 0; c0 < 2 * DP; c0 += 16) {
+      for (int c = 0; c < 2 * DP; ++c) acc[c] = sAcc[c * 128 + r];
+#pragma unroll
+      for (int c0 = 0; c0 < NACC * 2 * DP; c0 += 16) {
         uint32_t r16[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + kDnCol + (uint32_t)c0, r16);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) acc[c0 + q] = __uint_as_float(r16[q]) + sAcc[(c0 + q) * 128 + r];
+        for (int q = 0; q < 16; ++q) acc[(c0 + q) % (2 * DP)] += __uint_as_float(r16[q]);
       }
       if (i < p.B) {
         const float g_kl = p.gscal[term], g_loss = p.gscal[2 + term];
@@ -1356,7 +1394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) snn_bwd_tc_kernel(const BwdPara
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 template <int DP>
@@ -1369,7 +1407,7 @@ int launch_bwd_tc(const BwdParams& p, int n_terms, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid((unsigned)((p.B + 127) / 128), (unsigned)n_terms);
-  kern<<<grid, kTcThreads, TcBwdCfg<DP>::SMEM, st>>>(p);
+  kern<<<grid, kTcBwdThreads, TcBwdCfg<DP>::SMEM, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
 }
@@ -1521,6 +1559,9 @@ int clearvae_version(void) { return 100; }
 
 /* tuning / test hook: minimum local batch for the tensor-core latent forward (default 4096) */
 void clearvae_set_latent_tc_min_rows(int32_t rows) { g_tc_min_rows = rows; }
+int clearvae_debug_latent_timeline(long long* device_buffer) {
+  return (int)cudaMemcpyToSymbol(g_latent_timeline, &device_buffer, sizeof(device_buffer));
+}
 
 size_t clearvae_latent_workspace_bytes(int64_t B, int64_t Bg, int32_t D, int32_t n_terms) {
   (void)Bg; (void)D; (void)n_terms;

@@ -19,6 +19,10 @@ void clearvae_set_latent_tc_min_rows(int32_t rows);
  * %globaltimer stamps (start, prologue done, loads issued, loads landed, accumulator ready, epilogue done, exit) */
 int clearvae_debug_conv_timeline(long long* device_buffer);
 
+/* profiling hook (tools/latent_timeline.py): when non-NULL, CTA (0, 0) of the tensor-core latent backward writes clock64 stamps
+ * for its first 64 column tiles, [64][16] int64: 0/1 producer, 2-5 MMA issuer, 8-15 epilogue (see csrc/latent_loss.cu) */
+int clearvae_debug_latent_timeline(long long* device_buffer);
+
 /* debug: %globaltimer stamps {start, staged, peers ready, pulled} (+2 spare) of CTA 0 for the last 64 peer calls, [64][6] u64 */
 int clearvae_peer_timeline(const void* local_base, uint64_t* stamps_host);
 
