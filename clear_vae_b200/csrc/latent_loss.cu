@@ -21,6 +21,7 @@
 // and under data parallelism no reduce-scatter of dZ.
 // Other similarities / tiny temperatures use running maxima (two accumulators
 // per set) like the reference's logsumexp (losses.py:87-95).
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -460,6 +461,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // tf32 head by truncation (one LOP3; cvt.rna.tf32.f32 is a four-instruction sequence on sm_100a).  x - tf32_trunc(x) is exact in
 // fp32 and below 2^-10 |x|, so a (head, tail) pair read by the tensor core as two tf32 operands carries x to 2^-20 relative.
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float bf16_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffff0000u); }
+// {lo -> bits [0,16), hi -> bits [16,32)} as round-to-nearest bf16
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -483,7 +491,8 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ src, bool val
 }
 template <int DP>
 __device__ __forceinline__ void stage_split_vals(const float (&v)[DP], unsigned char* base, int rows, int r, bool a_side,
-                                                 unsigned char* kmajor2 = nullptr) {
+                                                 unsigned char* kmajor2 = nullptr, unsigned char* kmajor2_bf16 = nullptr,
+                                                 int nb2 = 0) {
   float ss = 0.f;
 #pragma unroll
   for (int d = 0; d < DP; ++d) ss = fmaf(v[d], v[d], ss);
@@ -509,6 +518,20 @@ __device__ __forceinline__ void stage_split_vals(const float (&v)[DP], unsigned 
     float* dst = reinterpret_cast<float*>(kmajor2 + (size_t)(r >> 2) * (2 * DP * 16) + (r & 3) * 4);
 #pragma unroll
     for (int d = 0; d < DP; ++d) { dst[d * 4] = hi[d]; dst[(DP + d) * 4] = lo[d]; }
+  }
+  if (kmajor2_bf16 != nullptr) {
+    // second-GEMM operand in bf16: [n = part x d (nb2 rows)][k = column r], K-major interleave (16-byte chunk = 8 columns);
+    // three parts n0 + n1 + n2 carry the normalised vector to 24 bits
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(kmajor2_bf16 + (size_t)(r >> 3) * (nb2 * 16) + (r & 7) * 2);
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const float n = v[d] * inv;
+      const __nv_bfloat16 n0 = __float2bfloat16_rn(n);
+      const float r1 = n - __bfloat162float(n0);
+      const __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 n2 = __float2bfloat16_rn(r1 - __bfloat162float(n1));
+      dst[d * 8] = n0; dst[(DP + d) * 8] = n1; dst[(2 * DP + d) * 8] = n2;
+    }
   }
 }
 template <int DP>
@@ -1066,7 +1089,10 @@ template <int DP> struct TcBwdCfg {
   static constexpr int KT = 3 * DP;
   static constexpr int A_BYTES = 128 * KT * 4;
   static constexpr int B_BYTES = BN * KT * 4;
-  static constexpr int B2_BYTES = BN * 2 * DP * 4;    // [N_hi | N_lo]^T, K-major for the second GEMM
+  // second GEMM in bf16 (K = 16 columns per instruction): B operand [n0 | n1 | n2]^T (three bf16 parts, 24 bits), K-major,
+  // rows padded to a multiple of 16
+  static constexpr int NB2 = (3 * DP + 15) / 16 * 16;
+  static constexpr int B2_BYTES = BN * NB2 * 2;
   // column-tile ring, decoupled from the two TMEM S/P buffers: the producers (global loads + normalise + split) run
   // NSB - 1 tiles ahead of the epilogue instead of waiting for the second MMA of tile jt - 2 to release their buffer
   static constexpr int NSB = DP <= 16 ? 4 : 2;
@@ -1074,12 +1100,7 @@ template <int DP> struct TcBwdCfg {
   // the gradient's max.  Every FLUSH tiles the accumulator is drained into an fp32 shared-memory copy ([2DP][128], one row per
   // epilogue thread) and restarted, which bounds the chain length (measured error then <= 2e-5 of max at 65536 columns).
   static constexpr int FLUSH = 32;
-  // tcgen05.mma instructions that accumulate into the same TMEM columns execute back to back at the pipe's LATENCY (~77 cycles
-  // for these 128 x 2DP x 8 instructions, 8-32 cycles of work each: tools/latent_timeline.py showed the issuing thread spending
-  // 1855 cycles per tile in the 24 dependent instructions of the second GEMM).  The k-steps therefore rotate over NACC
-  // independent accumulators, summed when they are drained.  TMEM: 2 x 2BN + NACC x 2DP <= 512 columns.
-  static constexpr int NACC = DP <= 16 ? 4 : 2;
-  static constexpr int ACC_BYTES = 2 * DP * 128 * 4;
+  static constexpr int ACC_BYTES = DP * 128 * 4;
   static constexpr int SMEM = A_BYTES + NSB * (B_BYTES + B2_BYTES) + NSB * BN * 16 /*labels lo/hi, c, q*/ + ACC_BYTES + 2048 + 1024;
 };
 
@@ -1091,9 +1112,10 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   constexpr int BN = C::BN;
   constexpr int NSB = C::NSB;
   constexpr uint32_t kBufCols = 2 * BN;      // per buffer: [0,BN) S then P_hi, [BN,2BN) P_lo
-  constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulators NACC x [128 x 2DP]
-  constexpr int NACC = C::NACC;
-  static_assert(2 * kBufCols + NACC * 2 * DP <= 512, "TMEM budget");
+  constexpr uint32_t kPCol = BN;             // P0 (bf16 pairs) at [BN, BN + BN/2), P1 at [BN + BN/2, 2BN)
+  constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulator [128 x NB2]: columns part * DP + d
+  constexpr int NB2 = C::NB2;
+  static_assert(2 * kBufCols + NB2 <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -1101,8 +1123,8 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   unsigned char* sB2 = sB + NSB * C::B_BYTES;
   int* sLab = reinterpret_cast<int*>(sB2 + NSB * C::B2_BYTES);  // [NSB][2][BN]
   float* sCQ = reinterpret_cast<float*>(sLab + 2 * NSB * BN);   // [NSB][2][BN]  (c_j, q_j)
-  float* sAcc = sCQ + 2 * NSB * BN;                             // [2DP][128] fp32 copy of the drained dN chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + 2 * DP * 128);
+  float* sAcc = sCQ + 2 * NSB * BN;                             // [DP][128] fp32 copy of the drained dN chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + DP * 128);
   uint64_t *b_full = bars, *b_empty = bars + NSB, *s_full = bars + 2 * NSB, *p_full = s_full + 2, *dn_full = p_full + 2, *dn_taken = dn_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dn_taken + 1);
   constexpr int FLUSH = C::FLUSH;
@@ -1132,8 +1154,10 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
     const long long i = m0 + rr;
     stage_split<DP>(t.mu + (i < p.B ? i : 0) * (long long)D, i < p.B, D, sA, 128, rr, true);
 #pragma unroll
-    for (int c = 0; c < 2 * DP; ++c) sAcc[c * 128 + rr] = 0.f;
+    for (int c = 0; c < DP; ++c) sAcc[c * 128 + rr] = 0.f;
   }
+  if (NB2 > 3 * DP)   // padding rows of the second GEMM's B operand stay zero for the whole sweep
+    for (int o = threadIdx.x * 16; o < NSB * C::B2_BYTES; o += kTcBwdThreads * 16) *reinterpret_cast<uint4*>(sB2 + o) = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -1170,7 +1194,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         if (jt + 1 < ntiles) prefetch(jt + 1);
         mbar_wait(&b_empty[b], ((jt / NSB) & 1) ^ 1);
         LAT_TL(jt, 0);
-        stage_split_vals<DP>(cvv, sB + b * C::B_BYTES, BN, cc, false, sB2 + b * C::B2_BYTES);
+        stage_split_vals<DP>(cvv, sB + b * C::B_BYTES, BN, cc, false, nullptr, sB2 + b * C::B2_BYTES, NB2);
         sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
         sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
         const bool fin = isfinite(a - q);
@@ -1187,11 +1211,11 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = instr_desc(kFmtTF32, 128, BN, 0, 0);
-      constexpr uint32_t idesc2 = instr_desc(kFmtTF32, 128, 2 * DP, 0, 0);
+      constexpr uint32_t idesc2 = instr_desc(kFmtBF16, 128, NB2, 0, 0);
       // descriptors differ only in their start-address field (bits [0,14) of the low word, 16-byte units): one add per instruction
       const uint64_t a_desc0 = smem_desc(smem_u32(sA), 128 * 16, 128, kLayoutNone);
       const uint64_t b_desc0 = smem_desc(smem_u32(sB), BN * 16, 128, kLayoutNone);
-      const uint64_t b2_desc0 = smem_desc(smem_u32(sB2), 2 * DP * 16, 128, kLayoutNone);
+      const uint64_t b2_desc0 = smem_desc(smem_u32(sB2), NB2 * 16, 128, kLayoutNone);
       uint32_t drains = 0;   // accumulator chunks handed to the epilogue so far
       auto mma2 = [&](int jt) {
         const int b = jt & 1, sb = jt % NSB;
@@ -1206,13 +1230,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         const uint64_t b2d = b2_desc0 + (uint32_t)(sb * (C::B2_BYTES >> 4));
         const uint32_t p_col = tmem_base + b * kBufCols;
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {        // A = P_hi, then P_lo (split keeps the coefficient at fp32 grade)
+        for (int part = 0; part < 2; ++part) {        // A = P0, then P1 (bf16 head + bf16 tail: 16 significand bits)
 #pragma unroll
-          for (int k8 = 0; k8 < BN / 8; ++k8) {
-            const uint64_t bd = b2d + (uint32_t)(k8 * ((2 * (2 * DP * 16)) >> 4));
-            const int acc = (part * (BN / 8) + k8) % NACC;
-            umma_tf32_ts(tmem_base + kDnCol + acc * 2 * DP, p_col + part * BN + k8 * 8, bd, idesc2,
-                         (restart && part == 0 && k8 < NACC) ? 0u : 1u);
+          for (int k16 = 0; k16 < BN / 16; ++k16) {   // 16 columns = 8 TMEM words of A, two 16-byte K chunks of B per instruction
+            const uint64_t bd = b2d + (uint32_t)(k16 * ((2 * (NB2 * 16)) >> 4));
+            umma_f16_ts(tmem_base + kDnCol, p_col + kPCol + part * (BN / 2) + k16 * 8, bd, idesc2,
+                        (restart && part == 0 && k16 == 0) ? 0u : 1u);
           }
         }
         umma_commit(&b_empty[sb]);
@@ -1263,12 +1286,13 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       mbar_wait(dn_full, drained & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < NACC * 2 * DP; c0 += 16) {
+      for (int c0 = 0; c0 < NB2; c0 += 16) {
         uint32_t r16[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + kDnCol + (uint32_t)c0, r16);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) sAcc[((c0 + q) % (2 * DP)) * 128 + r] += __uint_as_float(r16[q]);
+        for (int q = 0; q < 16; ++q)
+          if (c0 + q < 3 * DP) sAcc[((c0 + q) % DP) * 128 + r] += __uint_as_float(r16[q]);
       }
       tc_fence_before();
       __syncwarp();
@@ -1292,7 +1316,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * kBufCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rw[32], lw[32];
+        uint32_t rw[32], p0w[16], p1w[16];
         tmem_ld32(tcol + (uint32_t)c0, rw);
         tmem_ld_wait();
         LAT_TL(jt, 9 + c0 / 32);
@@ -1315,10 +1339,13 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
             b23.y = ((l4.w == my_lo) != ps) ? b23.y : 0.f;
             const float2 x01 = __fmul2_rn(e01, __ffma2_rn(b01, neg1, a01));
             const float2 x23 = __fmul2_rn(e23, __ffma2_rn(b23, neg1, a23));
-            const float2 h01 = make_float2(tf32_trunc(x01.x), tf32_trunc(x01.y)), h23 = make_float2(tf32_trunc(x23.x), tf32_trunc(x23.y));
+            // bf16 head by truncation (the packed pair is one PRMT of the two high halves), bf16 tail of the exact remainder
+            const float2 h01 = make_float2(bf16_trunc(x01.x), bf16_trunc(x01.y)), h23 = make_float2(bf16_trunc(x23.x), bf16_trunc(x23.y));
             const float2 l01 = __ffma2_rn(h01, neg1, x01), l23 = __ffma2_rn(h23, neg1, x23);
-            rw[q] = __float_as_uint(h01.x); rw[q + 1] = __float_as_uint(h01.y); rw[q + 2] = __float_as_uint(h23.x); rw[q + 3] = __float_as_uint(h23.y);
-            lw[q] = __float_as_uint(l01.x); lw[q + 1] = __float_as_uint(l01.y); lw[q + 2] = __float_as_uint(l23.x); lw[q + 3] = __float_as_uint(l23.y);
+            p0w[q / 2] = __byte_perm(__float_as_uint(x01.x), __float_as_uint(x01.y), 0x7632);
+            p0w[q / 2 + 1] = __byte_perm(__float_as_uint(x23.x), __float_as_uint(x23.y), 0x7632);
+            p1w[q / 2] = pack_bf16x2(l01.x, l01.y);
+            p1w[q / 2 + 1] = pack_bf16x2(l23.x, l23.y);
           }
         } else {
 #pragma unroll
@@ -1328,14 +1355,18 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
             const bool cand = (j < p.Bg) && (j != diag);
             const bool same = (lab_lo[c0 + q] == my_lo) && (lab_hi[c0 + q] == my_hi);
             const float x = cand ? e * ((ci + cj[c0 + q]) - ((same != ps) ? (qi + qj[c0 + q]) : 0.f)) : 0.f;
-            const float h = tf32_rna(x);
-            rw[q] = __float_as_uint(h);
-            lw[q] = __float_as_uint(x - h);
+            rw[q] = __float_as_uint(x);
+          }
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const float x0 = __uint_as_float(rw[q]), x1 = __uint_as_float(rw[q + 1]);
+            p0w[q / 2] = __byte_perm(rw[q], rw[q + 1], 0x7632);
+            p1w[q / 2] = pack_bf16x2(x0 - bf16_trunc(x0), x1 - bf16_trunc(x1));
           }
         }
         LAT_TL(jt, 12 + c0 / 32);
-        tmem_st32(tcol + (uint32_t)c0, rw);
-        tmem_st32(tcol + (uint32_t)(BN + c0), lw);
+        tmem_st16(tcol + kPCol + (uint32_t)(c0 / 2), p0w);
+        tmem_st16(tcol + kPCol + (uint32_t)(BN / 2 + c0 / 2), p1w);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -1348,16 +1379,17 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       while ((drained + 1) * FLUSH < ntiles) drain();   // chunks completed after this group's last tile
       mbar_wait(dn_full, drained & 1);                  // the last (partial) chunk
       tc_fence_after();
-      float acc[2 * DP];
+      float acc[DP];
 #pragma unroll
-      for (int c = 0; c < 2 * DP; ++c) acc[c] = sAcc[c * 128 + r];
+      for (int c = 0; c < DP; ++c) acc[c] = sAcc[c * 128 + r];
 #pragma unroll
-      for (int c0 = 0; c0 < NACC * 2 * DP; c0 += 16) {
+      for (int c0 = 0; c0 < NB2; c0 += 16) {
         uint32_t r16[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + kDnCol + (uint32_t)c0, r16);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) acc[(c0 + q) % (2 * DP)] += __uint_as_float(r16[q]);
+        for (int q = 0; q < 16; ++q)
+          if (c0 + q < 3 * DP) acc[(c0 + q) % DP] += __uint_as_float(r16[q]);
       }
       if (i < p.B) {
         const float g_kl = p.gscal[term], g_loss = p.gscal[2 + term];
@@ -1370,7 +1402,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         const bool live = inv < 1.f / kCosEps;
         float dot = 0.f;
 #pragma unroll
-        for (int d = 0; d < DP; ++d) { n[d] = mu[d] * inv; acc[d] += acc[DP + d]; dot = fmaf(acc[d], n[d], dot); }
+        for (int d = 0; d < DP; ++d) { n[d] = mu[d] * inv; dot = fmaf(acc[d], n[d], dot); }
         const float invB = 1.f / (float)p.B;
 #pragma unroll
         for (int d = 0; d < DP; ++d) {
