@@ -489,7 +489,7 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ src, bool val
     for (int d = 0; d < DP; ++d) v[d] = (valid && d < D) ? __ldg(src + d) : 0.f;
   }
 }
-template <int DP>
+template <int DP, bool TRUNC = false>
 __device__ __forceinline__ void stage_split_vals(const float (&v)[DP], unsigned char* base, int rows, int r, bool a_side,
                                                  unsigned char* kmajor2 = nullptr, unsigned char* kmajor2_bf16 = nullptr,
                                                  int nb2 = 0) {
@@ -501,8 +501,13 @@ __device__ __forceinline__ void stage_split_vals(const float (&v)[DP], unsigned 
 #pragma unroll
   for (int d = 0; d < DP; ++d) {
     const float n = v[d] * inv;
-    hi[d] = tf32_rna(n);
-    lo[d] = tf32_rna(n - hi[d]);
+    if (TRUNC) {   // head by truncation, exact remainder (the tensor core drops the remainder's low bits itself)
+      hi[d] = tf32_trunc(n);
+      lo[d] = n - hi[d];
+    } else {
+      hi[d] = tf32_rna(n);
+      lo[d] = tf32_rna(n - hi[d]);
+    }
   }
   constexpr int NC = DP / 4;  // 16-byte chunks per D-block
 #pragma unroll
@@ -1095,7 +1100,8 @@ template <int DP> struct TcBwdCfg {
   static constexpr int B2_BYTES = BN * NB2 * 2;
   // column-tile ring, decoupled from the two TMEM S/P buffers: the producers (global loads + normalise + split) run
   // NSB - 1 tiles ahead of the epilogue instead of waiting for the second MMA of tile jt - 2 to release their buffer
-  static constexpr int NSB = DP <= 16 ? 4 : 2;
+  // (a stage is held from staging through S, the epilogue and the second GEMM: ~3.5 tile periods)
+  static constexpr int NSB = DP <= 8 ? 6 : DP <= 16 ? 5 : 2;
   // The TMEM accumulator of dN adds with truncation: over a 65536-column sweep (683 tiles x 24 MMAs) the bias reached 3.5e-4 of
   // the gradient's max.  Every FLUSH tiles the accumulator is drained into an fp32 shared-memory copy ([2DP][128], one row per
   // epilogue thread) and restarted, which bounds the chain length (measured error then <= 2e-5 of max at 65536 columns).
@@ -1104,7 +1110,11 @@ template <int DP> struct TcBwdCfg {
   static constexpr int SMEM = A_BYTES + NSB * (B_BYTES + B2_BYTES) + NSB * BN * 16 /*labels lo/hi, c, q*/ + ACC_BYTES + 2048 + 1024;
 };
 
-constexpr int kTcBwdThreads = 12 * 32;   // warp 0 MMA issuer, 1-3 column producers, 4-11 epilogue: 3 warps per scheduler
+// warp 0 issues the S GEMMs, warps 1-3 are the column producers, 4-11 the epilogue, 12 issues the second GEMMs.  Two issuing
+// threads because tcgen05.mma issue blocks while the pipe is busy (tools/latent_timeline.py: ~80 cycles per TS instruction, ~960
+// per tile): with one thread the S GEMM of the next tile of one epilogue group queued behind the other group's second GEMM and
+// the two groups ran in turns instead of side by side.
+constexpr int kTcBwdThreads = 13 * 32;
 template <int DP>
 __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdParams p) {
   using namespace sm100;
@@ -1126,7 +1136,8 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   float* sAcc = sCQ + 2 * NSB * BN;                             // [DP][128] fp32 copy of the drained dN chunks
   uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + DP * 128);
   uint64_t *b_full = bars, *b_empty = bars + NSB, *s_full = bars + 2 * NSB, *p_full = s_full + 2, *dn_full = p_full + 2, *dn_taken = dn_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dn_taken + 1);
+  uint64_t *s_empty = dn_taken + 1, *p_empty = s_empty + 2;   // S read by the epilogue / P consumed by the second GEMM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
   constexpr int FLUSH = C::FLUSH;
   int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);          // [NSB]
 
@@ -1137,12 +1148,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   const int D = p.D;
   const int ntiles = (int)((p.Bg + BN - 1) / BN);
   const float* cols = t.mu_cols ? t.mu_cols : t.mu;
-  long long* const tl = (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8))
+  long long* const tl = (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8 || warp == 12))
                             ? g_latent_timeline : nullptr;
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < NSB; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); sFlags[b] = 0; }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&s_empty[b], 4); mbar_init(&p_empty[b], 1); }
     mbar_init(dn_full, 1);
     mbar_init(dn_taken, 4);
     fence_barrier_init();
@@ -1194,7 +1205,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         if (jt + 1 < ntiles) prefetch(jt + 1);
         mbar_wait(&b_empty[b], ((jt / NSB) & 1) ^ 1);
         LAT_TL(jt, 0);
-        stage_split_vals<DP>(cvv, sB + b * C::B_BYTES, BN, cc, false, nullptr, sB2 + b * C::B2_BYTES, NB2);
+        stage_split_vals<DP, true>(cvv, sB + b * C::B_BYTES, BN, cc, false, nullptr, sB2 + b * C::B2_BYTES, NB2);
         sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
         sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
         const bool fin = isfinite(a - q);
@@ -1208,17 +1219,38 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       }
     }
   } else if (warp == 0) {
-    // ================= MMA issuer =================
+    // ================= S GEMM issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = instr_desc(kFmtTF32, 128, BN, 0, 0);
-      constexpr uint32_t idesc2 = instr_desc(kFmtBF16, 128, NB2, 0, 0);
       // descriptors differ only in their start-address field (bits [0,14) of the low word, 16-byte units): one add per instruction
       const uint64_t a_desc0 = smem_desc(smem_u32(sA), 128 * 16, 128, kLayoutNone);
       const uint64_t b_desc0 = smem_desc(smem_u32(sB), BN * 16, 128, kLayoutNone);
+      for (int jt = 0; jt < ntiles; ++jt) {
+        const int b = jt & 1, sb = jt % NSB;
+        mbar_wait(&b_full[sb], (jt / NSB) & 1);
+        mbar_wait(&s_empty[b], ((jt >> 1) & 1) ^ 1);   // the epilogue has read S of tile jt - 2 out of this buffer
+        tc_fence_after();
+        LAT_TL(jt, 2);
+        const uint64_t bsd = b_desc0 + (uint32_t)(sb * (C::B_BYTES >> 4));
+#pragma unroll
+        for (int k8 = 0; k8 < C::KT / 8; ++k8) {
+          const uint64_t ad = a_desc0 + (uint32_t)(k8 * ((2 * (128 * 16)) >> 4));
+          const uint64_t bd = bsd + (uint32_t)(k8 * ((2 * (BN * 16)) >> 4));
+          umma_tf32(tmem_base + b * kBufCols, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[b]);
+        LAT_TL(jt, 3);
+      }
+    }
+  } else if (warp == 12) {
+    // ================= second GEMM issuer: dN += P [n0 | n1 | n2] =================
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = instr_desc(kFmtBF16, 128, NB2, 0, 0);
       const uint64_t b2_desc0 = smem_desc(smem_u32(sB2), NB2 * 16, 128, kLayoutNone);
       uint32_t drains = 0;   // accumulator chunks handed to the epilogue so far
-      auto mma2 = [&](int jt) {
+      for (int jt = 0; jt < ntiles; ++jt) {
         const int b = jt & 1, sb = jt % NSB;
+        mbar_wait(&b_full[sb], (jt / NSB) & 1);       // (already implied by P of this tile: S was computed from the same stage)
         mbar_wait(&p_full[b], (jt >> 1) & 1);
         tc_fence_after();
         LAT_TL(jt, 4);
@@ -1238,28 +1270,11 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
                         (restart && part == 0 && k16 == 0) ? 0u : 1u);
           }
         }
-        umma_commit(&b_empty[sb]);
+        umma_commit(&b_empty[sb]);                    // the stage's S GEMM retired before this tile's P existed
+        umma_commit(&p_empty[b]);
         LAT_TL(jt, 5);
-        if ((jt + 1) % FLUSH == 0 && jt + 1 < ntiles) { umma_commit(dn_full); ++drains; }   // chunk complete -> drain
-      };
-      for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt & 1, sb = jt % NSB;
-        mbar_wait(&b_full[sb], (jt / NSB) & 1);
-        tc_fence_after();
-        LAT_TL(jt, 2);
-        const uint64_t bsd = b_desc0 + (uint32_t)(sb * (C::B_BYTES >> 4));
-#pragma unroll
-        for (int k8 = 0; k8 < C::KT / 8; ++k8) {
-          const uint64_t ad = a_desc0 + (uint32_t)(k8 * ((2 * (128 * 16)) >> 4));
-          const uint64_t bd = bsd + (uint32_t)(k8 * ((2 * (BN * 16)) >> 4));
-          umma_tf32(tmem_base + b * kBufCols, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
-        }
-        umma_commit(&s_full[b]);
-        LAT_TL(jt, 3);
-        if (jt > 0) mma2(jt - 1);
+        if (((jt + 1) % FLUSH == 0 && jt + 1 < ntiles) || jt + 1 == ntiles) { umma_commit(dn_full); ++drains; }   // chunk complete -> drain
       }
-      mma2(ntiles - 1);
-      umma_commit(dn_full);
     }
   } else {
     // ================= epilogue: two groups of 4 warps alternate over the column tiles =================
@@ -1320,6 +1335,11 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         tmem_ld32(tcol + (uint32_t)c0, rw);
         tmem_ld_wait();
         LAT_TL(jt, 9 + c0 / 32);
+        if (c0 + 32 >= BN) {            // S is in registers: the buffer's S columns may take tile jt + 2
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[b]);
+        }
         if (!edge) {
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
@@ -1365,6 +1385,10 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
           }
         }
         LAT_TL(jt, 12 + c0 / 32);
+        if (c0 == 0) {                  // P columns of this buffer: the second GEMM of tile jt - 2 has retired
+          mbar_wait(&p_empty[b], ((jt >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
         tmem_st16(tcol + kPCol + (uint32_t)(c0 / 2), p0w);
         tmem_st16(tcol + kPCol + (uint32_t)(BN / 2 + c0 / 2), p1w);
       }
