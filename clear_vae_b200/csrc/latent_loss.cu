@@ -1121,11 +1121,14 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   using C = TcBwdCfg<DP>;
   constexpr int BN = C::BN;
   constexpr int NSB = C::NSB;
-  constexpr uint32_t kBufCols = 2 * BN;      // per buffer: [0,BN) S then P_hi, [BN,2BN) P_lo
-  constexpr uint32_t kPCol = BN;             // P0 (bf16 pairs) at [BN, BN + BN/2), P1 at [BN + BN/2, 2BN)
-  constexpr uint32_t kDnCol = 2 * kBufCols;  // gradient accumulator [128 x NB2]: columns part * DP + d
+  // TMEM columns: two S buffers [b * BN, (b + 1) * BN), a ring of NPB coefficient buffers (P0 as bf16 pairs in the first BN / 2
+  // words, P1 in the second), the gradient accumulator [128 x NB2] (columns part * DP + d).  With a third P buffer (fits for
+  // DP <= 8) an epilogue group's first store no longer waits for the second GEMM of its own previous tile.
   constexpr int NB2 = C::NB2;
-  static_assert(2 * kBufCols + NB2 <= 512, "TMEM budget");
+  constexpr int NPB = (2 * BN + 3 * BN + NB2 <= 512) ? 3 : 2;
+  constexpr uint32_t kPCol = 2 * BN;
+  constexpr uint32_t kDnCol = kPCol + NPB * BN;
+  static_assert(kDnCol + NB2 <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -1135,9 +1138,9 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   float* sCQ = reinterpret_cast<float*>(sLab + 2 * NSB * BN);   // [NSB][2][BN]  (c_j, q_j)
   float* sAcc = sCQ + 2 * NSB * BN;                             // [DP][128] fp32 copy of the drained dN chunks
   uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + DP * 128);
-  uint64_t *b_full = bars, *b_empty = bars + NSB, *s_full = bars + 2 * NSB, *p_full = s_full + 2, *dn_full = p_full + 2, *dn_taken = dn_full + 1;
+  uint64_t *b_full = bars, *b_empty = bars + NSB, *s_full = bars + 2 * NSB, *p_full = s_full + 2, *dn_full = p_full + 3, *dn_taken = dn_full + 1;
   uint64_t *s_empty = dn_taken + 1, *p_empty = s_empty + 2;   // S read by the epilogue / P consumed by the second GEMM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 3);
   constexpr int FLUSH = C::FLUSH;
   int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);          // [NSB]
 
@@ -1153,7 +1156,8 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < NSB; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); sFlags[b] = 0; }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&s_empty[b], 4); mbar_init(&p_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); }
+    for (int b = 0; b < NPB; ++b) { mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1); }
     mbar_init(dn_full, 1);
     mbar_init(dn_taken, 4);
     fence_barrier_init();
@@ -1236,7 +1240,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         for (int k8 = 0; k8 < C::KT / 8; ++k8) {
           const uint64_t ad = a_desc0 + (uint32_t)(k8 * ((2 * (128 * 16)) >> 4));
           const uint64_t bd = bsd + (uint32_t)(k8 * ((2 * (BN * 16)) >> 4));
-          umma_tf32(tmem_base + b * kBufCols, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
+          umma_tf32(tmem_base + b * BN, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[b]);
         LAT_TL(jt, 3);
@@ -1249,9 +1253,9 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       const uint64_t b2_desc0 = smem_desc(smem_u32(sB2), NB2 * 16, 128, kLayoutNone);
       uint32_t drains = 0;   // accumulator chunks handed to the epilogue so far
       for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt & 1, sb = jt % NSB;
+        const int pb = jt % NPB, sb = jt % NSB;
         mbar_wait(&b_full[sb], (jt / NSB) & 1);       // (already implied by P of this tile: S was computed from the same stage)
-        mbar_wait(&p_full[b], (jt >> 1) & 1);
+        mbar_wait(&p_full[pb], (jt / NPB) & 1);
         tc_fence_after();
         LAT_TL(jt, 4);
         const bool restart = (jt % FLUSH) == 0;       // first tile of a chunk: the accumulator starts over
@@ -1260,18 +1264,18 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
           tc_fence_after();
         }
         const uint64_t b2d = b2_desc0 + (uint32_t)(sb * (C::B2_BYTES >> 4));
-        const uint32_t p_col = tmem_base + b * kBufCols;
+        const uint32_t p_col = tmem_base + kPCol + pb * BN;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {        // A = P0, then P1 (bf16 head + bf16 tail: 16 significand bits)
 #pragma unroll
           for (int k16 = 0; k16 < BN / 16; ++k16) {   // 16 columns = 8 TMEM words of A, two 16-byte K chunks of B per instruction
             const uint64_t bd = b2d + (uint32_t)(k16 * ((2 * (NB2 * 16)) >> 4));
-            umma_f16_ts(tmem_base + kDnCol, p_col + kPCol + part * (BN / 2) + k16 * 8, bd, idesc2,
+            umma_f16_ts(tmem_base + kDnCol, p_col + part * (BN / 2) + k16 * 8, bd, idesc2,
                         (restart && part == 0 && k16 == 0) ? 0u : 1u);
           }
         }
         umma_commit(&b_empty[sb]);                    // the stage's S GEMM retired before this tile's P existed
-        umma_commit(&p_empty[b]);
+        umma_commit(&p_empty[pb]);
         LAT_TL(jt, 5);
         if (((jt + 1) % FLUSH == 0 && jt + 1 < ntiles) || jt + 1 == ntiles) { umma_commit(dn_full); ++drains; }   // chunk complete -> drain
       }
@@ -1328,7 +1332,9 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       const int* lab_hi = sLab + (sb * 2 + 1) * BN;
       const float* cj = sCQ + (sb * 2 + 0) * BN;
       const float* qj = sCQ + (sb * 2 + 1) * BN;
-      const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * kBufCols);
+      const int pb = jt % NPB;
+      const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(b * BN);
+      const uint32_t pcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + kPCol + (uint32_t)(pb * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t rw[32], p0w[16], p1w[16];
@@ -1386,16 +1392,16 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         }
         LAT_TL(jt, 12 + c0 / 32);
         if (c0 == 0) {                  // P columns of this buffer: the second GEMM of tile jt - 2 has retired
-          mbar_wait(&p_empty[b], ((jt >> 1) & 1) ^ 1);
+          mbar_wait(&p_empty[pb], ((jt / NPB) & 1) ^ 1);
           tc_fence_after();
         }
-        tmem_st16(tcol + kPCol + (uint32_t)(c0 / 2), p0w);
-        tmem_st16(tcol + kPCol + (uint32_t)(BN / 2 + c0 / 2), p1w);
+        tmem_st16(pcol + (uint32_t)(c0 / 2), p0w);
+        tmem_st16(pcol + (uint32_t)(BN / 2 + c0 / 2), p1w);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(&p_full[pb]);
       LAT_TL(jt, 15);
     }
     // ---- final: dN (TMEM) -> chain through the normalisation, add KL / reparam gradients
