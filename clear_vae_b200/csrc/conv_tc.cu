@@ -1029,7 +1029,11 @@ __global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cs = p.plan.Cs, cb = p.t_cb, kchunks = Cs / cb;
   long long* const tl_buf = g_conv_timeline ? g_conv_timeline + (long long)blockIdx.x * 64 : nullptr;   // debug timeline (tools/persist_timeline.py)
-#define CV_TTL(tile_no, k) do { if (tl_buf && (tile_no) < 15) tl_buf[4 + (tile_no) * 4 + (k)] = gtimer(); } while (0)
+#define CV_TTL(tile_no, k) do { if (tl_buf && (tile_no) < 13) tl_buf[4 + (tile_no) * 4 + (k)] = gtimer(); } while (0)
+  // epilogue phase totals of thread 64 (SM clocks): [56] accumulator wait, [57] TMEM load + bias / mask, [58] global stores,
+  // [59] statistics (shared-memory transposition, two barriers), [60] whole loop, [61] tiles
+  long long ph_wait = 0, ph_ld = 0, ph_st = 0, ph_stat = 0, ph_t = 0, ph_all = 0;
+#define CV_PH(acc) do { if (tl_buf) { const long long now_ = clock64(); acc += now_ - ph_t; ph_t = now_; } } while (0)
   if (tl_buf && threadIdx.x == 0) tl_buf[0] = gtimer();
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -1132,6 +1136,7 @@ __global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) co
     uint32_t tcount = 0;
     TTile tl;
     int map_cls = -1, n_l = 0, h_l = 0, wd = 0;   // this thread's (image, row, column) inside a tile: depends on the class only
+    if (tl_buf) ph_all = ph_t = clock64();
     for (int tile = blockIdx.x; t_get_tile(p, tile, BN, &tl); tile += gridDim.x, ++tcount) {
       const Cls& c = p.plan.cls[tl.cls];
       if (tl.cls != map_cls) {
@@ -1154,6 +1159,7 @@ __global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) co
       const uint32_t b = tcount & 1;
       mbar_wait(&acc_full[b], (tcount >> 1) & 1);
       tc_fence_after();
+      CV_PH(ph_wait);
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         const int ch0 = ci * CH;
@@ -1205,6 +1211,7 @@ __global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) co
           tc_fence_before();
           mbar_arrive(&acc_empty[b]);
         }
+        CV_PH(ph_ld);
         if (mvalid) {
           if (p.dst_bf16) {
             uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dst) + dst_off + nb);
@@ -1218,6 +1225,7 @@ __global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) co
             for (int i = 0; i < CH / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
         }
+        CV_PH(ph_st);
         if (p.stats != nullptr) {
           float4* row = reinterpret_cast<float4*>(sEp + r * kEpLd);
 #pragma unroll
@@ -1250,16 +1258,21 @@ __global__ void __launch_bounds__(kTThreads, (tma_ctas_per_sm<BN, MASKED>())) co
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        CV_PH(ph_stat);
       }
       if (et == 0) CV_TTL((int)tcount, 3);
     }
     if (p.stats != nullptr && acc_n0 >= 0) flush();
+    if (tl_buf && et == 0) {
+      tl_buf[56] = ph_wait; tl_buf[57] = ph_ld; tl_buf[58] = ph_st; tl_buf[59] = ph_stat; tl_buf[60] = clock64() - ph_all; tl_buf[61] = tcount;
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
   if (tl_buf && threadIdx.x == 0) tl_buf[1] = gtimer();
 #undef CV_TTL
+#undef CV_PH
 }
 
 // ---------------------------------------------------------------------------

@@ -1101,26 +1101,33 @@ template <int DP> struct TcBwdCfg {
   // column-tile ring, decoupled from the two TMEM S/P buffers: the producers (global loads + normalise + split) run
   // NSB - 1 tiles ahead of the epilogue instead of waiting for the second MMA of tile jt - 2 to release their buffer
   // (a stage is held from staging through S, the epilogue and the second GEMM: ~3.5 tile periods)
-  static constexpr int NSB = DP <= 8 ? 6 : DP <= 16 ? 5 : 2;
+  static constexpr int NSB = DP <= 8 ? 6 : DP <= 16 ? 5 : 4;
+  // The first GEMM's operand (B_BYTES, the larger part) is only needed until S of its tile has been computed: it lives in its own
+  // shorter ring, released by the S issuer, so that D = 32 (36 KB per stage) still gets NSB stages of everything else.
+  static constexpr int NSB1 = DP <= 16 ? NSB : 2;
+  // D = 32: staging a tile (normalise + tf32 split + three bf16 parts of 32 dims per column) takes one thread per column
+  // ~2700 cycles, more than the rest of the pipeline needs per tile: two producer sets stage alternate tiles
+  static constexpr int NPROD = DP <= 16 ? 1 : 2;
+  static constexpr int THREADS = (13 + (NPROD - 1) * 3) * 32;
   // The TMEM accumulator of dN adds with truncation: over a 65536-column sweep (683 tiles x 24 MMAs) the bias reached 3.5e-4 of
   // the gradient's max.  Every FLUSH tiles the accumulator is drained into an fp32 shared-memory copy ([2DP][128], one row per
   // epilogue thread) and restarted, which bounds the chain length (measured error then <= 2e-5 of max at 65536 columns).
   static constexpr int FLUSH = 32;
   static constexpr int ACC_BYTES = DP * 128 * 4;
-  static constexpr int SMEM = A_BYTES + NSB * (B_BYTES + B2_BYTES) + NSB * BN * 16 /*labels lo/hi, c, q*/ + ACC_BYTES + 2048 + 1024;
+  static constexpr int SMEM = A_BYTES + NSB1 * B_BYTES + NSB * B2_BYTES + NSB * BN * 16 /*labels lo/hi, c, q*/ + ACC_BYTES + 2048 + 1024;
 };
 
 // warp 0 issues the S GEMMs, warps 1-3 are the column producers, 4-11 the epilogue, 12 issues the second GEMMs.  Two issuing
 // threads because tcgen05.mma issue blocks while the pipe is busy (tools/latent_timeline.py: ~80 cycles per TS instruction, ~960
 // per tile): with one thread the S GEMM of the next tile of one epilogue group queued behind the other group's second GEMM and
 // the two groups ran in turns instead of side by side.
-constexpr int kTcBwdThreads = 13 * 32;
+// (D = 32 adds warps 13-15 as a second producer set.)
 template <int DP>
-__global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(TcBwdCfg<DP>::THREADS, 1) snn_bwd_tc_kernel(const BwdParams p) {
   using namespace sm100;
   using C = TcBwdCfg<DP>;
   constexpr int BN = C::BN;
-  constexpr int NSB = C::NSB;
+  constexpr int NSB = C::NSB, NSB1 = C::NSB1, NPROD = C::NPROD;
   // TMEM columns: two S buffers [b * BN, (b + 1) * BN), a ring of NPB coefficient buffers (P0 as bf16 pairs in the first BN / 2
   // words, P1 in the second), the gradient accumulator [128 x NB2] (columns part * DP + d).  With a third P buffer (fits for
   // DP <= 8) an epilogue group's first store no longer waits for the second GEMM of its own previous tile.
@@ -1133,14 +1140,15 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::A_BYTES;
-  unsigned char* sB2 = sB + NSB * C::B_BYTES;
+  unsigned char* sB2 = sB + NSB1 * C::B_BYTES;
   int* sLab = reinterpret_cast<int*>(sB2 + NSB * C::B2_BYTES);  // [NSB][2][BN]
   float* sCQ = reinterpret_cast<float*>(sLab + 2 * NSB * BN);   // [NSB][2][BN]  (c_j, q_j)
   float* sAcc = sCQ + 2 * NSB * BN;                             // [DP][128] fp32 copy of the drained dN chunks
   uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + DP * 128);
   uint64_t *b_full = bars, *b_empty = bars + NSB, *s_full = bars + 2 * NSB, *p_full = s_full + 2, *dn_full = p_full + 3, *dn_taken = dn_full + 1;
   uint64_t *s_empty = dn_taken + 1, *p_empty = s_empty + 2;   // S read by the epilogue / P consumed by the second GEMM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 3);
+  uint64_t* b1_empty = p_empty + 3;                            // [NSB1] first-GEMM operand consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b1_empty + NSB1);
   constexpr int FLUSH = C::FLUSH;
   int* sFlags = reinterpret_cast<int*>(tmem_slot + 1);          // [NSB]
 
@@ -1156,6 +1164,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < NSB; ++b) { mbar_init(&b_full[b], BN); mbar_init(&b_empty[b], 1); sFlags[b] = 0; }
+    for (int b = 0; b < NSB1; ++b) mbar_init(&b1_empty[b], 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); }
     for (int b = 0; b < NPB; ++b) { mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1); }
     mbar_init(dn_full, 1);
@@ -1172,7 +1181,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
     for (int c = 0; c < DP; ++c) sAcc[c * 128 + rr] = 0.f;
   }
   if (NB2 > 3 * DP)   // padding rows of the second GEMM's B operand stay zero for the whole sweep
-    for (int o = threadIdx.x * 16; o < NSB * C::B2_BYTES; o += kTcBwdThreads * 16) *reinterpret_cast<uint4*>(sB2 + o) = make_uint4(0, 0, 0, 0);
+    for (int o = threadIdx.x * 16; o < NSB * C::B2_BYTES; o += C::THREADS * 16) *reinterpret_cast<uint4*>(sB2 + o) = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -1180,11 +1189,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
   const uint32_t tmem_base = *tmem_slot;
 
   static_assert(BN == 96, "three producer warps, one thread per column");
-  if (warp >= 1 && warp < 4) {
-    // ================= column-tile producers (one thread per column; warps 1-3) =================
+  if ((warp >= 1 && warp < 4) || warp >= 13) {
+    // ================= column-tile producers (one thread per column; warps 1-3, second set 13-15) =================
     {
-      // the global loads of tile jt + 1 (vector, label, row statistics) are in flight while tile jt is normalised and stored
-      const int cc = threadIdx.x - 32;
+      // the global loads of the set's next tile (vector, label, row statistics) are in flight while this one is normalised and stored
+      const int pset = warp >= 13 ? 1 : 0;
+      const int cc = threadIdx.x - (pset ? 13 * 32 : 32);
       float nv[DP];
       long long nlab;
       float na, nq;
@@ -1197,19 +1207,20 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
         na = nvalid ? __ldg(t.stats_all + 2 * j) : INFINITY;
         nq = nvalid ? __ldg(t.stats_all + 2 * j + 1) : INFINITY;
       };
-      prefetch(0);
-      for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt % NSB;
+      if (pset < ntiles) prefetch(pset);
+      for (int jt = pset; jt < ntiles; jt += NPROD) {
+        const int b = jt % NSB, b1 = jt % NSB1;
         float cvv[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) cvv[d] = nv[d];
         const long long lab = nlab;
         const float a = na, q = nq;
         const bool valid = nvalid;
-        if (jt + 1 < ntiles) prefetch(jt + 1);
+        if (jt + NPROD < ntiles) prefetch(jt + NPROD);
         mbar_wait(&b_empty[b], ((jt / NSB) & 1) ^ 1);
+        mbar_wait(&b1_empty[b1], ((jt / NSB1) & 1) ^ 1);
         LAT_TL(jt, 0);
-        stage_split_vals<DP, true>(cvv, sB + b * C::B_BYTES, BN, cc, false, nullptr, sB2 + b * C::B2_BYTES, NB2);
+        stage_split_vals<DP, true>(cvv, sB + b1 * C::B_BYTES, BN, cc, false, nullptr, sB2 + b * C::B2_BYTES, NB2);
         sLab[(b * 2 + 0) * BN + cc] = (int)(lab & 0xffffffffll);
         sLab[(b * 2 + 1) * BN + cc] = (int)(lab >> 32);
         const bool fin = isfinite(a - q);
@@ -1230,12 +1241,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
       const uint64_t a_desc0 = smem_desc(smem_u32(sA), 128 * 16, 128, kLayoutNone);
       const uint64_t b_desc0 = smem_desc(smem_u32(sB), BN * 16, 128, kLayoutNone);
       for (int jt = 0; jt < ntiles; ++jt) {
-        const int b = jt & 1, sb = jt % NSB;
+        const int b = jt & 1, sb = jt % NSB, sb1 = jt % NSB1;
         mbar_wait(&b_full[sb], (jt / NSB) & 1);
         mbar_wait(&s_empty[b], ((jt >> 1) & 1) ^ 1);   // the epilogue has read S of tile jt - 2 out of this buffer
         tc_fence_after();
         LAT_TL(jt, 2);
-        const uint64_t bsd = b_desc0 + (uint32_t)(sb * (C::B_BYTES >> 4));
+        const uint64_t bsd = b_desc0 + (uint32_t)(sb1 * (C::B_BYTES >> 4));
 #pragma unroll
         for (int k8 = 0; k8 < C::KT / 8; ++k8) {
           const uint64_t ad = a_desc0 + (uint32_t)(k8 * ((2 * (128 * 16)) >> 4));
@@ -1243,6 +1254,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) snn_bwd_tc_kernel(const BwdP
           umma_tf32(tmem_base + b * BN, ad, bd, idesc1, k8 != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[b]);
+        umma_commit(&b1_empty[sb1]);
         LAT_TL(jt, 3);
       }
     }
@@ -1469,7 +1481,7 @@ int launch_bwd_tc(const BwdParams& p, int n_terms, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid((unsigned)((p.B + 127) / 128), (unsigned)n_terms);
-  kern<<<grid, kTcBwdThreads, TcBwdCfg<DP>::SMEM, st>>>(p);
+  kern<<<grid, TcBwdCfg<DP>::THREADS, TcBwdCfg<DP>::SMEM, st>>>(p);
   CV_LAUNCH_CHECK();
   return 0;
 }

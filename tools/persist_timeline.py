@@ -36,6 +36,12 @@ def run(name, tr, k, op, cin, cout, hin):
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     print(f"== {name}: {t.shape[0]} CTAs, kernel span {float(t[:, 1].max() - t0) / 1e3:.1f} us, CTA life mean {float((t[:, 1] - t[:, 0]).mean()) / 1e3:.1f} us")
+    ph = t[:, 56:62]
+    ok = ph[:, 5] > 0
+    if ok.any():
+        m = ph[ok].mean(0)
+        print(f"   epilogue thread, cycles per tile (mean over {int(ok.sum())} CTAs, {m[5]:.1f} tiles each): accumulator wait {m[0] / m[5]:.0f} | TMEM load + bias/mask {m[1] / m[5]:.0f}"
+              f" | global stores {m[2] / m[5]:.0f} | statistics {m[3] / m[5]:.0f} | whole loop {m[4] / m[5]:.0f}")
     for tile in range(10):
         s = t[:, 4 + tile * 4:8 + tile * 4]
         ok = (s > 0).all(1)
