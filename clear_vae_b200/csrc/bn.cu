@@ -214,6 +214,53 @@ __global__ void __launch_bounds__(kNT) sigmoid_mse_bwd_kernel(const float* __res
   reduce_commit(d0, d1, c, C, blocked, stats);
 }
 
+// float4 form (fp32 raw, inner % 4 == 0, 16-byte aligned): thread = four consecutive positions of one channel, CTAs along y
+// stride over the samples; the scalar kernel ran at ~1.1 TB/s on the 3 x 28 x 28 output (35 us of a 1.5 ms step)
+__global__ void __launch_bounds__(kNT) sigmoid_mse_bwd_vec_kernel(const float4* __restrict__ xhat, const float4* __restrict__ x,
+                                                                  const float* __restrict__ grad_recon,
+                                                                  const float4* __restrict__ grad_ext, const float4* __restrict__ raw,
+                                                                  long long nper, int C, long long inner4, float twoInvB,
+                                                                  float4* __restrict__ g_pre, double* stats) {
+  const float gr = grad_recon ? __ldg(grad_recon) * twoInvB : 0.f;
+  const int chunks = (int)((inner4 + kNT - 1) / kNT);
+  const int c = blockIdx.x / chunks;
+  const long long i4 = (long long)(blockIdx.x % chunks) * kNT + threadIdx.x;
+  const long long period4 = (long long)C * inner4;
+  double d0 = 0.0, d1 = 0.0;
+  if (i4 < inner4) {
+    float s0 = 0.f, s1 = 0.f;
+    int cnt = 0;
+    const long long pos = c * inner4 + i4;
+    auto one = [&](const float4 xh, const float4 xv, const float4 rv, const float4 ge, long long i) {
+      float4 g;
+      g.x = (gr * (xh.x - xv.x) + ge.x) * (xh.x * (1.f - xh.x));
+      g.y = (gr * (xh.y - xv.y) + ge.y) * (xh.y * (1.f - xh.y));
+      g.z = (gr * (xh.z - xv.z) + ge.z) * (xh.z * (1.f - xh.z));
+      g.w = (gr * (xh.w - xv.w) + ge.w) * (xh.w * (1.f - xh.w));
+      g_pre[i] = g;
+      s0 += (g.x + g.y) + (g.z + g.w);
+      s1 = fmaf(g.x, rv.x, fmaf(g.y, rv.y, fmaf(g.z, rv.z, fmaf(g.w, rv.w, s1))));
+    };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long smp = blockIdx.y;
+    for (; smp + gridDim.y < nper; smp += 2 * (long long)gridDim.y) {   // two samples in flight
+      const long long i = smp * period4 + pos, j = i + (long long)gridDim.y * period4;
+      const float4 a0 = __ldg(xhat + i), a1 = __ldg(xhat + j), b0 = __ldg(x + i), b1 = __ldg(x + j);
+      const float4 r0 = __ldg(raw + i), r1 = __ldg(raw + j);
+      const float4 e0 = grad_ext ? __ldg(grad_ext + i) : z4, e1 = grad_ext ? __ldg(grad_ext + j) : z4;
+      one(a0, b0, r0, e0, i);
+      one(a1, b1, r1, e1, j);
+      if ((cnt += 2) >= 16) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }
+    }
+    if (smp < nper) {
+      const long long i = smp * period4 + pos;
+      one(__ldg(xhat + i), __ldg(x + i), __ldg(raw + i), grad_ext ? __ldg(grad_ext + i) : z4, i);
+    }
+    d0 += s0; d1 += s1;
+  }
+  reduce_commit(d0, d1, c, C, 1, stats);
+}
+
 // ---------------------------------------------------------------------------
 // BatchNorm backward coefficients from (S1 = sum g, S2 = sum g*y):
 //   sum g*xhat = r (S2 - mu S1);  dgamma = that;  dbeta = S1
@@ -562,6 +609,18 @@ int clearvae_sigmoid_mse_bwd(const float* xhat, const float* x, const float* gra
   if (total % period) return CLEARVAE_EINVAL;
   dim3 grid;
   int blocked;
+  if (raw_dtype == CLEARVAE_F32 && inner % 4 == 0 && inner >= 64 &&
+      !(((uintptr_t)xhat | (uintptr_t)x | (uintptr_t)raw | (uintptr_t)g_pre | (uintptr_t)grad_ext) & 15)) {
+    const long long inner4 = inner / 4, nper = total / period;
+    const long long gx = (long long)C * ((inner4 + kNT - 1) / kNT);
+    long long gy = (148 * 8 + gx - 1) / gx;
+    gy = gy > nper ? nper : gy < 1 ? 1 : gy;
+    sigmoid_mse_bwd_vec_kernel<<<dim3((unsigned)gx, (unsigned)gy), kNT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(xhat), reinterpret_cast<const float4*>(x), grad_recon, reinterpret_cast<const float4*>(grad_ext),
+        reinterpret_cast<const float4*>(raw), nper, C, inner4, 2.f / (float)batch, reinterpret_cast<float4*>(g_pre), stats);
+    CV_LAUNCH_CHECK();
+    return 0;
+  }
   reduce_grid(C, inner, total / period, &grid, &blocked);
   sigmoid_mse_bwd_kernel<<<grid, kNT, 0, (cudaStream_t)stream>>>(xhat, x, grad_recon, grad_ext, raw, raw_dtype, total, C, inner,
                                                                  2.f / (float)batch, blocked, g_pre, stats);

@@ -280,6 +280,169 @@ __global__ void __launch_bounds__(kNT) convt_last_kernel(const void* __restrict_
   }
 }
 
+// Same layer, materialised bf16 channels-last input (the training path).  CTA = one image x kRT input rows (+ one halo row on
+// either side), staged through shared memory with coalesced 16-byte loads: the previous form (every thread loading its own
+// 64-byte pixels from global memory, lanes 128 bytes apart) spent its time in L1 tag look-ups (32 lines per load instruction)
+// and ran at 32 us whatever its instruction count.  One thread = TWO adjacent output-pixel pairs (ow = 4jj .. 4jj+3) of one
+// output row: the weight vectors of a (kh, ci) are loaded once and feed both pairs (3 LDS.128 per 24 FMAs), the FMAs are
+// packed fp32x2 (co padded to 4 = two FFMA2 per tap), the input pixels of a kernel row stay packed as bf16 in registers.
+// Shared-memory pixels have an 80-byte pitch and their four 16-byte channel chunks are XOR-swizzled with bit 3 of the pixel
+// column, so the lanes of a quarter warp (pixel columns 2 apart) hit eight different 16-byte bank groups.
+constexpr int kPixPitch = 80;
+template <int K, int kRT>
+__global__ void __launch_bounds__(kNT) convt_last_x2_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out, double* stats,
+                                                            int B, int Cout, int Hi, int Wi, int Ho, int Wo) {
+  constexpr int CI = 32;
+  extern __shared__ __align__(16) unsigned char sIn[];   // [(kRT + 2) rows][Wi pixels][80 bytes]
+  __shared__ __align__(16) float sW[K * K * CI * 4];     // [kh*K+kw][ci][co padded to 4]
+  __shared__ float sRed[2][kNT / 32][4];
+  for (int i = threadIdx.x; i < K * K * CI * 4; i += kNT) {
+    const int co = i & 3, ci = (i >> 2) % CI, t = i / (4 * CI);
+    sW[i] = co < Cout ? w[(ci * Cout + co) * K * K + t] : 0.f;  // reference layout w[ci][co][kh][kw]
+  }
+  float bs[4];
+#pragma unroll
+  for (int co = 0; co < 4; ++co) bs[co] = (bias != nullptr && co < Cout) ? __ldg(bias + co) : 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const int W2 = (Wo + 1) / 2, W4 = (W2 + 1) / 2;
+  const int tiles_per_img = (Hi + kRT - 1) / kRT;
+  const long long ntiles = (long long)B * tiles_per_img;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long n = tile / tiles_per_img;
+    const int r0 = (int)(tile % tiles_per_img) * kRT;
+    const int row_lo = r0 - 1 < 0 ? 0 : r0 - 1;                    // first staged input row
+    const int row_hi = r0 + kRT + 1 > Hi ? Hi : r0 + kRT + 1;      // one past the last staged row
+    __syncthreads();                                               // previous tile's readers are done (also orders the sW fill)
+    {
+      const int nchunk = (row_hi - row_lo) * Wi * (CI / 8);
+      const uint4* g4 = reinterpret_cast<const uint4*>(src + ((n * Hi + row_lo) * Wi) * (long long)CI);
+      for (int c = threadIdx.x; c < nchunk; c += kNT) {
+        const int pix = c >> 2, c8 = c & 3, col = pix % Wi;
+        *reinterpret_cast<uint4*>(sIn + (size_t)pix * kPixPitch + ((c8 ^ ((col >> 3) & 1)) << 4)) = __ldg(g4 + c);
+      }
+    }
+    __syncthreads();
+    // input column j0 + ii (ii = -1 .. 2) feeds pair pp (0 / 1) with d = ii - pp: ow = 2j through kw0 = 1 - 2d, ow = 2j + 1 through kw1 = 2 - 2d
+    // all warps sweep the even output rows (one kernel row each), then the odd ones (two): no warp waits for another's parity
+    for (int it = threadIdx.x; it < 2 * ((kRT * W4 + kNT - 1) / kNT) * kNT; it += kNT) {
+      const int per = ((kRT * W4 + kNT - 1) / kNT) * kNT;
+      const int a = it >= per ? 1 : 0;
+      const int li = it - a * per;
+      if (li >= kRT * W4) continue;
+      const int rl = li / W4, jj = li - rl * W4;
+      const int oh = 2 * (r0 + rl) + a;
+      if (r0 + rl >= Hi || oh >= Ho) continue;
+      const int j0 = 2 * jj;
+      float2 acc[2][2][2];   // [pair][left / right pixel of the pair][co 01 / co 23]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&acc[0][0][0])[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        const int th = oh + 1 - kh;  // = 2 * ih
+        if (th < 0 || (th & 1) || (th >> 1) >= Hi) continue;   // warp-uniform (same row parity) except at the image border
+        const int ih = th >> 1;
+        const unsigned char* rowp = sIn + (size_t)(ih - row_lo) * Wi * kPixPitch;
+        uint4 v[4][CI / 8];
+#pragma unroll
+        for (int ii = -1; ii <= 2; ++ii) {
+          bool used = false;
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int d = ii - pp;
+            if (d >= -1 && d <= 1 && ((1 - 2 * d >= 0 && 1 - 2 * d < K) || (2 - 2 * d >= 0 && 2 - 2 * d < K))) used = true;
+          }
+          if (!used) continue;                                    // compile-time
+          const int iw = j0 + ii;
+          const bool ok = iw >= 0 && iw < Wi;
+          const unsigned char* pp8 = rowp + (ok ? iw : 0) * kPixPitch;
+          const int sw = (iw >> 3) & 1;
+#pragma unroll
+          for (int c8 = 0; c8 < CI / 8; ++c8)
+            v[ii + 1][c8] = ok ? *reinterpret_cast<const uint4*>(pp8 + ((c8 ^ sw) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        const float4* wrow = reinterpret_cast<const float4*>(sW + kh * K * CI * 4);
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+          float4 wv[K];
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) wv[kw] = wrow[kw * CI + ci];
+#pragma unroll
+          for (int ii = -1; ii <= 2; ++ii) {
+            float x = 0.f;
+            bool have = false;
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int d = ii - pp;
+              if (d < -1 || d > 1) continue;
+              const int kw0 = 1 - 2 * d, kw1 = 2 - 2 * d;
+              const bool use0 = kw0 >= 0 && kw0 < K, use1 = kw1 >= 0 && kw1 < K;
+              if (!use0 && !use1) continue;
+              if (!have) {
+                const uint4 u4 = v[ii + 1][ci / 8];
+                const uint32_t word = ((ci % 8) / 2 == 0) ? u4.x : ((ci % 8) / 2 == 1) ? u4.y : ((ci % 8) / 2 == 2) ? u4.z : u4.w;
+                x = __uint_as_float((ci & 1) ? (word & 0xffff0000u) : (word << 16));
+                have = true;
+              }
+              const float2 xx = make_float2(x, x);
+              if (use0) {
+                acc[pp][0][0] = __ffma2_rn(xx, make_float2(wv[kw0].x, wv[kw0].y), acc[pp][0][0]);
+                acc[pp][0][1] = __ffma2_rn(xx, make_float2(wv[kw0].z, wv[kw0].w), acc[pp][0][1]);
+              }
+              if (use1) {
+                acc[pp][1][0] = __ffma2_rn(xx, make_float2(wv[kw1].x, wv[kw1].y), acc[pp][1][0]);
+                acc[pp][1][1] = __ffma2_rn(xx, make_float2(wv[kw1].z, wv[kw1].w), acc[pp][1][1]);
+              }
+            }
+          }
+        }
+      }
+      const int ow0 = 4 * jj;
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        if (co < Cout) {
+          float y[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 a2 = acc[k >> 1][k & 1][co >> 1];
+            y[k] = ((co & 1) ? a2.y : a2.x) + bs[co];
+          }
+          if (out != nullptr) {  // statistics-only callers (CLEAR-MIM inner forwards) pass no destination
+            float* o = out + ((n * Cout + co) * Ho + oh) * (long long)Wo + ow0;
+            if (ow0 + 3 < Wo && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (ow0 + k < Wo) o[k] = y[k];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (ow0 + k < Wo) { s[co] += y[k]; q[co] = fmaf(y[k], y[k], q[co]); }
+        }
+      }
+    }
+  }
+  if (stats == nullptr) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float a = cv::warp_sum(s[c]), b = cv::warp_sum(q[c]);
+    if (lane == 0) { sRed[0][warp][c] = a; sRed[1][warp][c] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int which = threadIdx.x >> 2, c = threadIdx.x & 3;
+    if (c < Cout) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kNT / 32; ++wv) t += sRed[which][wv][c];
+      atomicAdd(stats + which * Cout + c, (double)t);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Weight gradient of the same two boundary layers (Conv2d(C<=4 -> 32) and ConvTranspose2d(32 -> C<=4), stride 2, pad 1):
 // both are  dW[f][c][kh][kw] = sum_{n,h,w} feat[n,h,w,f] * img[n,c,2h-1+kh,2w-1+kw]  with a 32-channel channels-last bf16
@@ -501,7 +664,27 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
   convt_last_kernel<KK, BF, PR><<<grid_for(npix), kNT, 0, st>>>(src->ptr, pre_scale, pre_shift, pre_relu, weight, bias,       \
                                                                 (float*)dst->ptr, stats, (int)batch, g->Cout, g->Hin, g->Win, Ho, Ho)
 #define CV_LAUNCH_P(KK, BF) do { if (pre) CV_LAUNCH_T(KK, BF, true); else CV_LAUNCH_T(KK, BF, false); } while (0)
-    if (g->k == 3) { if (bf) CV_LAUNCH_P(3, true); else CV_LAUNCH_P(3, false); }
+    // rows per CTA: the whole image when it is small (all warps sweep one parity at a time), 8 input rows otherwise
+    const int rt = g->Hin <= 16 ? 16 : 8;
+    const size_t stage_bytes = (size_t)(rt + 2) * g->Win * kPixPitch;
+    if (bf && !pre && stage_bytes <= 64 * 1024 && getenv("CLEARVAE_CONVT_LAST_V1") == nullptr) {
+      long long nt = batch * ((g->Hin + rt - 1) / rt);              // persistent past 8 CTAs per SM
+      if (nt > 148 * 8) nt = 148 * 8;
+      const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src->ptr);
+#define CV_LAUNCH_X2(KK, RT)                                                                                                  \
+  do {                                                                                                                        \
+    static bool attr_done = false;                                                                                            \
+    if (!attr_done) {                                                                                                         \
+      cudaFuncSetAttribute(convt_last_x2_kernel<KK, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);             \
+      attr_done = true;                                                                                                       \
+    }                                                                                                                         \
+    convt_last_x2_kernel<KK, RT><<<(unsigned)nt, kNT, stage_bytes, st>>>(sp, weight, bias, (float*)dst->ptr, stats, (int)batch, \
+                                                                         g->Cout, g->Hin, g->Win, Ho, Ho);                    \
+  } while (0)
+      if (g->k == 3) { if (rt == 16) CV_LAUNCH_X2(3, 16); else CV_LAUNCH_X2(3, 8); }
+      else { if (rt == 16) CV_LAUNCH_X2(4, 16); else CV_LAUNCH_X2(4, 8); }
+#undef CV_LAUNCH_X2
+    } else if (g->k == 3) { if (bf) CV_LAUNCH_P(3, true); else CV_LAUNCH_P(3, false); }
     else { if (bf) CV_LAUNCH_P(4, true); else CV_LAUNCH_P(4, false); }
 #undef CV_LAUNCH_P
 #undef CV_LAUNCH_T
