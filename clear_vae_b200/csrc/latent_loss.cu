@@ -453,6 +453,10 @@ template <int DP> struct TcCfg {
 };
 constexpr int kTcThreads = 13 * 32;
 
+// round-to-nearest, ties away from zero, to the 10-bit tf32 significand.  For finite inputs this is bit-identical to
+// cvt.rna.tf32.f32 (sign-magnitude: add half an ulp of the kept field, clear the dropped 13 bits), which sm_100a expands into
+// four instructions per value (add, mask, NaN/Inf test, select); every caller passes normalised, finite values.
+__device__ __forceinline__ float tf32_rna_finite(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -498,13 +502,24 @@ __device__ __forceinline__ void stage_split_vals(const float (&v)[DP], unsigned 
   for (int d = 0; d < DP; ++d) ss = fmaf(v[d], v[d], ss);
   const float inv = 1.f / fmaxf(sqrtf(ss), kCosEps);
   float hi[DP], lo[DP];
+  if (TRUNC) {   // head by truncation, exact remainder (the tensor core drops the remainder's low bits itself)
 #pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    const float n = v[d] * inv;
-    if (TRUNC) {   // head by truncation, exact remainder (the tensor core drops the remainder's low bits itself)
+    for (int d = 0; d < DP; ++d) {
+      const float n = v[d] * inv;
       hi[d] = tf32_trunc(n);
       lo[d] = n - hi[d];
-    } else {
+    }
+  } else if (isfinite(ss)) {   // every n is finite: the two-instruction rounding
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const float n = v[d] * inv;
+      hi[d] = tf32_rna_finite(n);
+      lo[d] = tf32_rna_finite(n - hi[d]);
+    }
+  } else {                     // NaN / Inf rows keep the instruction's semantics
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const float n = v[d] * inv;
       hi[d] = tf32_rna(n);
       lo[d] = tf32_rna(n - hi[d]);
     }
