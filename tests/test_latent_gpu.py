@@ -359,6 +359,31 @@ def test_65536_latents_tensor_core_path_against_fp64(D):
         assert err <= GRAD_REL * float(wg.abs().max()) + 1e-12, (D, ps, err, float(wg.abs().max()))
 
 
+@pytest.mark.parametrize("B,D", [(4500, 16), (5000, 4), (4100, 32)])
+def test_tensor_core_path_ragged_sizes_against_fp64(B, D):
+    """Tensor-core path at sizes that are multiples of neither the 128-row nor the 96-column tile, on the operand widths the
+    65536 test does not reach (D = 16: two coefficient buffers, five ring stages; D = 4: dims padded to 8; D = 32: split rings,
+    two producer sets), with more than 32 column tiles so the accumulator drain runs.  Same gates as at 65536."""
+    from clear_vae_b200.latent import latent_block
+    from tests.helpers import snn_fp64_chunked
+    gen = torch.Generator().manual_seed(B + D)
+    mu_c, mu_s = torch.randn(B, D, generator=gen), torch.randn(B, D, generator=gen)
+    lab = torch.randint(0, 7, (B,), generator=gen)
+    a = mu_c.to(DEV).requires_grad_(True)
+    b = mu_s.to(DEV).requires_grad_(True)
+    _, sc = latent_block([a, b], [None, None], [None, None], lab.to(DEV), snn=[1, 1], ps=[False, True], temperature=0.1, want_z=False)
+    w = torch.zeros(8, device=DEV)
+    w[2], w[3] = 100.0, 100.0
+    torch.autograd.backward([sc], [w])
+    torch.cuda.synchronize()
+    for t, ps, idx in ((a, False, 2), (b, True, 3)):
+        want, wg = snn_fp64_chunked(t.detach(), lab, 0.1, ps, device=DEV, chunk=2048)
+        assert close(float(sc[idx]), want), (D, ps, float(sc[idx]), want)
+        wg = wg * 100.0
+        err = float((t.grad.double() - wg).abs().max())
+        assert err <= GRAD_REL * float(wg.abs().max()) + 1e-12, (B, D, ps, err, float(wg.abs().max()))
+
+
 def test_data_parallel_shards_alternating_with_global_batches_on_one_gpu(monkeypatch):
     """The data-parallel latent path of every rank, emulated on one GPU (the exchange is replaced by the known global tensors), run
     ALTERNATELY with single-process global-batch calls in the same process: row gradients x 1/world and the loss must equal the
