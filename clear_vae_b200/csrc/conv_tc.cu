@@ -1327,6 +1327,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
   if (nkb <= 0) return;
   const int nsub = p.x3 ? kSplitPasses : 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // debug timeline (tools/wgrad_timeline.py): per CTA [0] start, [1] end (globaltimer ns); SM-clock totals of producer thread 0
+  // [8] index math + cp.async issue, [9] waiting for a free stage, [10] waiting for its own copies; of the MMA thread [11] waiting
+  // for operands, [12] issuing; [13] k-blocks; epilogue thread 0 [14] accumulator wait, [15] scatter-add
+  long long* const tl_buf = g_conv_timeline
+                                ? g_conv_timeline + ((long long)blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z)) * 64
+                                : nullptr;
+  long long ph_a = 0, ph_b = 0, ph_c = 0, ph_t = 0;
+#define WG_PH(acc) do { if (tl_buf) { const long long now_ = clock64(); acc += now_ - ph_t; ph_t = now_; } } while (0)
+  if (tl_buf && threadIdx.x == 0) tl_buf[0] = gtimer();
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -1354,6 +1363,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
       const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.src);
       const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(p.dy);
       constexpr int NG = BN / 8, NGH = (NG + 1) / 2;
+      if (tl_buf) ph_t = clock64();
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NS;
         const long long m = (kb_begin + kb) * WK + px;
@@ -1365,7 +1375,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
         const int hbase = hd * p.plan.sh, wbase = wd * p.plan.sh;
         const long long img_off = img * p.s_n;
         const long long dy_off = img * p.y_n + (long long)(hd * p.plan.os + c.oa) * p.y_h + (long long)(wd * p.plan.os + c.ob) * p.y_w;
+        WG_PH(ph_a);
         mbar_wait(&empty[s], ((kb / NS) & 1) ^ 1);
+        WG_PH(ph_b);
         const uint32_t a_dst = smem_u32(sA + s * kWStageA) + px * 16, b_dst = smem_u32(sB + s * kBStage) + px * 16;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1391,12 +1403,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
           }
         }
         cp_async_commit();
+        WG_PH(ph_a);
         if (kb >= 2) {
           cp_async_wait<2>();
           fence_proxy_async();
           mbar_arrive(&full[(kb - 2) % NS]);
         }
+        WG_PH(ph_c);
       }
+      if (tl_buf && threadIdx.x == 0) { tl_buf[8] = ph_a; tl_buf[9] = ph_b; tl_buf[10] = ph_c; tl_buf[13] = nkb; }
       if (nkb >= 2) {
         cp_async_wait<1>();
         fence_proxy_async();
@@ -1563,8 +1578,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
     }
 
     // ---- epilogue: scatter-add the tile into the reference weight layout
+    if (tl_buf) ph_t = clock64();
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    long long ph_e0 = 0, ph_e1 = 0;
+    WG_PH(ph_e0);
     const int kidx = k0 + threadIdx.x;
     const bool rvalid = kidx < Kreal;
     const int t = rvalid ? kidx / Cs : 0, ch = rvalid ? kidx - t * Cs : 0;
@@ -1593,13 +1611,17 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
         }
       }
     }
+    WG_PH(ph_e1);
+    if (tl_buf && threadIdx.x == 0) { tl_buf[14] = ph_e0; tl_buf[15] = ph_e1; }
   } else if (warp == 5) {
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc(kFmtBF16, 128, BN, 1, 1);  // both operands MN-major
+      if (tl_buf) ph_t = clock64();
       for (int kb = 0; kb < nkb * nsub; ++kb) {
         const int s = kb % NS;
         mbar_wait(&full[s], (kb / NS) & 1);
         tc_fence_after();
+        WG_PH(ph_a);
         const uint32_t a_base = smem_u32(sA + s * kWStageA), b_base = smem_u32(sB + s * kBStage);
         const int sub = kb % nsub;
         const uint32_t acc = p.x3 ? (uint32_t)split_acc(sub) * kAccStride : 0u;
@@ -1612,13 +1634,161 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WgradParams p)
           umma_f16(tmem_base + acc, ad, bd, idesc, (first && k4 == 0) ? 0u : 1u);
         }
         umma_commit(&empty[s]);
+        WG_PH(ph_b);
       }
       umma_commit(tmem_full);
+      if (tl_buf) { tl_buf[11] = ph_a; tl_buf[12] = ph_b; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (tl_buf && threadIdx.x == 0) tl_buf[1] = gtimer();
+#undef WG_PH
+}
+
+// ---------------------------------------------------------------------------
+// weight gradient, TMA operands (round 2, third session).  tools/wgrad_timeline.py showed the cp.async kernel above spending
+// ~3400 SM cycles per 64-pixel k-block in its producers (ten 16-byte copies per thread at 128-byte lane stride: LSU / L1 tag
+// throughput) against ~390 cycles of MMA issue.  Here a k-block is one BOX of pixels (tn images x th rows x tw columns of the
+// class-local output grid, tn*th*tw a multiple of 16, <= 128) and both operands arrive as tiled 4-D TMA boxes [pixel][channel]
+// with 128-byte (64 channels) or 64-byte (32 channels) swizzled rows -- which is exactly the canonical MN-major SWIZZLE_128B /
+// SWIZZLE_64B UMMA layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)): 64 (32) MN-contiguous elements per row, 8 pixel rows per atom,
+// SBO = 1024 (512) bytes between 8-row groups, LBO = one box between 64- (32-)channel blocks.  Operand A: the activation at
+// tap (dh, dw) of the M-tile's (tap, channel-block) pairs -- one box each, zero padding by out-of-bounds fill; operand B: dy on
+// the class grid (traversal stride `os`), zero beyond the grid / the batch, so padded box positions contribute nothing.
+//   warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (fp32 red.global.add into the reference weight layout).
+// ---------------------------------------------------------------------------
+struct WgradTmaParams {
+  Plan plan;
+  long long batch;
+  float* dw;
+  int splits;
+  int cb, cbn;                       // channels per A / B box (64 or 32)
+  int tw[cvplan::kMaxClasses], th[cvplan::kMaxClasses], tn[cvplan::kMaxClasses], tiles_h[cvplan::kMaxClasses], nbox[cvplan::kMaxClasses];
+};
+constexpr int kWtStages = 3;
+template <int BN>
+constexpr size_t wgrad_tma_smem() { return (size_t)kWtStages * (128 * 128 * 2 + BN * 128 * 2) + 256 + 1024; }
+
+template <int BN>
+__global__ void __launch_bounds__(kTThreads, 1) wgrad_tma_kernel(const __grid_constant__ TmapPack tmA, const __grid_constant__ TmapPack tmB,
+                                                                const WgradTmaParams p) {
+  constexpr int kAStageW = 128 * 128 * 2, kBStageW = BN * 128 * 2;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + kWtStages * kAStageW;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + kWtStages * kBStageW);
+  uint64_t* empty = full + kWtStages;
+  uint64_t* tmem_full = empty + kWtStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int cls_id = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const Cls& c = p.plan.cls[cls_id];
+  const int Cs = p.plan.Cs, Kreal = c.ntaps * Cs, cb = p.cb, cbn = p.cbn;
+  const int k0 = blockIdx.x * 128;  // first (tap, channel) row of this tile
+  if (k0 >= Kreal) return;
+  const int n0 = blockIdx.y * BN;
+  const int nbox = p.nbox[cls_id];
+  const int bx0 = (int)((long long)nbox * split / p.splits), bx1 = (int)((long long)nbox * (split + 1) / p.splits);
+  if (bx1 <= bx0) return;
+  const int tw = p.tw[cls_id], th = p.th[cls_id], tn = p.tn[cls_id], tiles_h = p.tiles_h[cls_id];
+  const int kpix = tw * th * tn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kWtStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA.t[cls_id]); prefetch_tmap(&tmB.t[cls_id]); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int na = 128 / cb, nb = BN / cbn;                    // boxes per stage
+  const uint32_t a_box = (uint32_t)kpix * cb * 2, b_box = (uint32_t)kpix * cbn * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n_a = 0;
+      for (int j = 0; j < na; ++j) n_a += (k0 + j * cb < Kreal) ? 1 : 0;
+      const uint32_t bytes = (uint32_t)n_a * a_box + (uint32_t)nb * b_box;
+      for (int bx = bx0; bx < bx1; ++bx) {
+        const int it = bx - bx0, s = it % kWtStages;
+        const int img0 = (bx / tiles_h) * tn, h0 = (bx % tiles_h) * th;
+        mbar_wait(&empty[s], ((it / kWtStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        for (int j = 0; j < na; ++j) {
+          const int kidx = k0 + j * cb;
+          if (kidx >= Kreal) break;
+          const int t = kidx / Cs, ch = kidx - t * Cs;
+          tma_load_4d(sA + s * kAStageW + j * a_box, &tmA.t[cls_id], &full[s], ch, c.dw[t], h0 * p.plan.sh + c.dh[t], img0);
+        }
+        for (int j = 0; j < nb; ++j)
+          tma_load_4d(sB + s * kBStageW + j * b_box, &tmB.t[cls_id], &full[s], n0 + j * cbn, c.ob, h0 * p.plan.os + c.oa, img0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(kFmtBF16, 128, BN, 1, 1);  // both operands MN-major
+      const uint32_t a_lay = cb == 64 ? kLayoutSw128 : kLayoutSw64, b_lay = cbn == 64 ? kLayoutSw128 : kLayoutSw64;
+      const uint32_t a_sbo = cb == 64 ? 1024u : 512u, b_sbo = cbn == 64 ? 1024u : 512u;   // 8 pixel rows of 128 / 64 bytes
+      for (int bx = bx0; bx < bx1; ++bx) {
+        const int it = bx - bx0, s = it % kWtStages;
+        mbar_wait(&full[s], (it / kWtStages) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * kAStageW), b_base = smem_u32(sB + s * kBStageW);
+        for (int k16 = 0; k16 < kpix / 16; ++k16) {
+          const uint64_t ad = smem_desc(a_base + k16 * 2 * a_sbo, a_box, a_sbo, a_lay);
+          const uint64_t bd = smem_desc(b_base + k16 * 2 * b_sbo, b_box, b_sbo, b_lay);
+          umma_f16(tmem_base, ad, bd, idesc, (it | k16) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ---- epilogue: scatter-add the tile into the reference weight layout
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int kidx = k0 + r;
+    const bool rvalid = kidx < Kreal;
+    const int t = rvalid ? kidx / Cs : 0, ch = rvalid ? kidx - t * Cs : 0;
+    const long long row_off = ch * p.plan.ws_c + c.wtap[t];
+    const int Nn = p.plan.Nn;
+    constexpr int CH = BN < 32 ? BN : 32;
+#pragma unroll 1
+    for (int ch0 = 0; ch0 < BN; ch0 += CH) {
+      uint32_t raw[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
+      if (CH == 32) {
+        tmem_ld32(taddr, raw);
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(taddr, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { raw[i] = r16[i]; raw[i + 16] = 0u; }
+      }
+      tmem_ld_wait();
+      if (rvalid) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int n = n0 + ch0 + i;
+          if (n < Nn) atomicAdd(p.dw + n * p.plan.ws_n + row_off, __uint_as_float(raw[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------
@@ -1778,6 +1948,20 @@ int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
+template <int BN>
+int launch_wgrad_tma(const TmapPack& tmA, const TmapPack& tmB, const WgradTmaParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = wgrad_tma_smem<BN>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  wgrad_tma_kernel<BN><<<grid, kTThreads, smem, st>>>(tmA, tmB, p);
+  CV_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1809,12 +1993,81 @@ static int conv_wgrad_impl(const clearvae_conv_geom* g, int64_t batch, const cle
     max_m = std::max(max_m, (long long)batch * p.plan.cls[i].Hd * p.plan.cls[i].Wd);
   }
   const int tiles = ((max_k + 127) / 128) * ((n_pad + BN - 1) / BN) * p.plan.n_classes;
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- first choice: TMA operands (plain bf16 channels-last activation and gradient, 32 or a multiple of 64 channels)
+  static const bool no_tma_w = getenv("CLEARVAE_NO_TMA_WGRAD") != nullptr;
+  EncodeTiledFn enc = get_encode();
+  const int Cs = p.plan.Cs, Nn = p.plan.Nn;
+  if (!no_tma_w && enc && !x3 && p.src_bf16 && p.dy_bf16 && p.s_c == 1 && p.y_c == 1 && pre_scale == nullptr && !pre_relu &&
+      (Cs == 32 || Cs % 64 == 0) && (Nn == 32 || Nn % 64 == 0) && BN >= 32 && Nn % BN == 0 && batch < (1 << 24) &&
+      !(((uintptr_t)p.src | (uintptr_t)p.dy) & 15) && ((p.s_n | p.s_h | p.s_w | p.y_n | p.y_h | p.y_w) & 7) == 0) {
+    WgradTmaParams q{};
+    q.plan = p.plan; q.batch = batch; q.dw = dweight;
+    q.cb = Cs == 32 ? 32 : 64;
+    q.cbn = Nn == 32 ? 32 : 64;
+    TmapPack tmA{}, tmB{};
+    bool ok = true;
+    long long max_box = 0;
+    for (int i = 0; i < q.plan.n_classes && ok; ++i) {
+      const Cls& c = q.plan.cls[i];
+      const int sh = q.plan.sh, os = q.plan.os;
+      const int tw = (c.Wd + 1) & ~1;                       // even box width: an odd grid gets one zero-filled column
+      if (tw > 128) { ok = false; break; }
+      const int th = std::min(c.Hd, 128 / tw);
+      int tn = (int)std::min<long long>(batch, std::min(256, 128 / (tw * th)));
+      while (tn > 1 && (tw * th * tn) % 16 != 0) --tn;      // the MMA consumes 16 pixels per instruction
+      const int kpix = tw * th * tn;
+      if (kpix % 16 != 0 || tw * sh > 256 || th * sh > 256 || tw * os > 256 || th * os > 256) { ok = false; break; }
+      q.tw[i] = tw; q.th[i] = th; q.tn[i] = tn;
+      q.tiles_h[i] = (c.Hd + th - 1) / th;
+      const long long nbox = ((batch + tn - 1) / tn) * q.tiles_h[i];
+      if (nbox >= (1LL << 30)) { ok = false; break; }
+      q.nbox[i] = (int)nbox;
+      max_box = std::max(max_box, nbox);
+      {
+        cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)q.plan.Ws, (cuuint64_t)q.plan.Hs, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)p.s_w * 2, (cuuint64_t)p.s_h * 2, (cuuint64_t)p.s_n * 2};
+        cuuint32_t box[4] = {(cuuint32_t)q.cb, (cuuint32_t)(tw * sh), (cuuint32_t)(th * sh), (cuuint32_t)tn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)sh, (cuuint32_t)sh, 1};
+        if (q.plan.Ws == 1) strides[0] = (cuuint64_t)Cs * 2;
+        if (q.plan.Hs == 1) strides[1] = strides[0] * (cuuint64_t)q.plan.Ws;
+        if ((strides[0] | strides[1] | strides[2]) & 15) { ok = false; break; }
+        if (enc(&tmA.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                q.cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { ok = false; break; }
+      }
+      {
+        cuuint64_t dims[4] = {(cuuint64_t)Nn, (cuuint64_t)q.plan.Wb, (cuuint64_t)q.plan.Hb, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)p.y_w * 2, (cuuint64_t)p.y_h * 2, (cuuint64_t)p.y_n * 2};
+        cuuint32_t box[4] = {(cuuint32_t)q.cbn, (cuuint32_t)(tw * os), (cuuint32_t)(th * os), (cuuint32_t)tn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)os, (cuuint32_t)os, 1};
+        if (q.plan.Wb == 1) strides[0] = (cuuint64_t)Nn * 2;
+        if (q.plan.Hb == 1) strides[1] = strides[0] * (cuuint64_t)q.plan.Wb;
+        if ((strides[0] | strides[1] | strides[2]) & 15) { ok = false; break; }
+        if (enc(&tmB.t[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                q.cbn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { ok = false; break; }
+      }
+    }
+    if (ok) {
+      // split the pixel boxes so the grid is ONE wave of (one-CTA-per-SM) CTAs, each keeping >= 2 boxes: with TMA operands a box
+      // costs ~0.4 us of main loop while the scatter-add epilogue costs 2-9 us per CTA and grows with the number of splits
+      long long sp = std::max<long long>(1, 148 / tiles);
+      sp = std::min<long long>(sp, std::max<long long>(1, max_box / 2));
+      q.splits = (int)sp;
+      dim3 grid((unsigned)((max_k + 127) / 128), (unsigned)(Nn / BN), (unsigned)(q.plan.n_classes * q.splits));
+      switch (BN) {
+        case 32: return launch_wgrad_tma<32>(tmA, tmB, q, grid, st);
+        case 64: return launch_wgrad_tma<64>(tmA, tmB, q, grid, st);
+        default: return launch_wgrad_tma<128>(tmA, tmB, q, grid, st);
+      }
+    }
+  }
   // split the pixel reduction so the grid is ~2 waves of 148 SMs, each CTA keeping >= 4 k-blocks
   long long splits = std::max<long long>(1, (2 * 148 + tiles - 1) / tiles);
   splits = std::min<long long>(splits, std::max<long long>(1, max_m / (WK * 4)));
   p.splits = (int)splits;
   dim3 grid((unsigned)((max_k + 127) / 128), (unsigned)((n_pad + BN - 1) / BN), (unsigned)(p.plan.n_classes * p.splits));
-  cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
     case 16: return launch_wgrad<16>(p, grid, st);
     case 32: return launch_wgrad<32>(p, grid, st);

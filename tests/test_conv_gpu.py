@@ -143,7 +143,10 @@ def test_preop_bf16_io_and_mask_epilogue():
 
 @pytest.mark.parametrize("transposed,k,op,cin,cout,H,B", [(0, 4, 0, 32, 64, 32, 8), (0, 3, 0, 3, 32, 28, 16), (0, 4, 0, 256, 512, 4, 32),
                                                            (1, 4, 0, 512, 256, 2, 32), (1, 3, 1, 32, 3, 14, 8), (1, 4, 0, 64, 32, 16, 8),
-                                                           (0, 4, 0, 3, 32, 64, 8), (1, 4, 0, 32, 3, 32, 8)])
+                                                           (0, 4, 0, 3, 32, 64, 8), (1, 4, 0, 32, 3, 32, 8),
+                                                           # the 28x28 stack: odd class grids (7, 3) take one zero-filled box column
+                                                           (0, 3, 0, 32, 64, 14, 16), (0, 3, 0, 64, 128, 7, 16), (1, 3, 0, 128, 64, 4, 16),
+                                                           (1, 3, 1, 64, 32, 7, 16), (1, 3, 1, 64, 32, 7, 5), (0, 4, 0, 128, 256, 8, 3)])
 def test_weight_gradient(transposed, k, op, cin, cout, H, B):
     from clear_vae_b200 import _ops
     ops = _ops.ops()
