@@ -153,6 +153,165 @@ __global__ void __launch_bounds__(kNT) conv_first_kernel(const void* __restrict_
   }
 }
 
+// Same layer, TWO horizontally adjacent output pixels per thread: the eight weight vectors of a tap are loaded once for both
+// (LDS : FMA 1:8 instead of 1:4), the FMAs are packed fp32x2, the two pixels share K - 2 of their K + 2 input columns, the thread
+// stores 128 contiguous bytes, and the statistics transposition (two tiles: sums and squares / mask products) runs once per pair.
+template <int K, bool X_BF16, bool MASKED>
+__global__ void __launch_bounds__(kNT) conv_first2_kernel(const void* __restrict__ xv_, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, void* __restrict__ out, int out_bf16,
+                                                          double* stats, int B, int Cin, int H, int W, int Ho, int Wo,
+                                                          const void* __restrict__ msk, int msk_bf16,
+                                                          const float* __restrict__ msk_scale, const float* __restrict__ msk_shift) {
+  constexpr int CO = 32;
+  __shared__ __align__(16) float sW[4 * K * K * CO];  // [ci*K*K + kh*K + kw][co]
+  __shared__ float sRed[2][kNT / 32][CO];
+  __shared__ float sMs[2][CO];
+  __shared__ float sT[2][kNT][CO + 1];
+  const int KK = Cin * K * K;
+  for (int i = threadIdx.x; i < KK * CO; i += kNT) {
+    const int k = i / CO, co = i % CO;  // reference layout w[co][ci][kh][kw] = w[co * KK + k]
+    sW[i] = w[co * KK + k];
+  }
+  if (MASKED && threadIdx.x < CO) {
+    sMs[0][threadIdx.x] = msk_scale ? msk_scale[threadIdx.x] : 1.f;
+    sMs[1][threadIdx.x] = msk_shift ? msk_shift[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  float s_run = 0.f, q_run = 0.f;   // running sums of column (threadIdx.x & 31) over the row quarter (threadIdx.x >> 5)
+  const int Wp = (Wo + 1) / 2;
+  const long long npair = (long long)B * Ho * Wp;
+  const long long npair_pad = (npair + kNT - 1) / kNT * kNT;   // whole CTA iterates together (barriers inside the loop)
+  for (long long pr0 = (long long)blockIdx.x * kNT + threadIdx.x; pr0 < npair_pad; pr0 += (long long)gridDim.x * kNT) {
+    const bool pvalid = pr0 < npair;
+    const long long pr = pvalid ? pr0 : 0;
+    const int ow = 2 * (int)(pr % Wp), oh = (int)((pr / Wp) % Ho);
+    const long long n = pr / ((long long)Wp * Ho);
+    const bool v1ok = pvalid && ow + 1 < Wo;
+    const long long pix = (n * Ho + oh) * (long long)Wo + ow;
+    float2 acc0[CO / 2], acc1[CO / 2];
+#pragma unroll
+    for (int c = 0; c < CO / 2; ++c) {
+      const float2 b2 = (!MASKED && bias) ? make_float2(__ldg(bias + 2 * c), __ldg(bias + 2 * c + 1)) : make_float2(0.f, 0.f);
+      acc0[c] = b2; acc1[c] = b2;
+    }
+    for (int ci = 0; ci < Cin; ++ci) {
+      const long long xoff = (n * Cin + ci) * (long long)H * W;
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        const int ih = oh * 2 - 1 + kh;
+        const bool rok = ih >= 0 && ih < H;
+        float xr[K + 2];
+#pragma unroll
+        for (int j = 0; j < K + 2; ++j) {
+          const int iw = ow * 2 - 1 + j;
+          float xv = 0.f;
+          if (rok && iw >= 0 && iw < W) {
+            const long long o = xoff + (long long)ih * W + iw;
+            xv = X_BF16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(xv_) + o))
+                        : __ldg(reinterpret_cast<const float*>(xv_) + o);
+          }
+          xr[j] = xv;
+        }
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const float4* wr = reinterpret_cast<const float4*>(sW + ((ci * K + kh) * K + kw) * CO);
+          const float2 x0 = make_float2(xr[kw], xr[kw]), x1 = make_float2(xr[kw + 2], xr[kw + 2]);
+#pragma unroll
+          for (int c4 = 0; c4 < CO / 4; ++c4) {
+            const float4 wv = wr[c4];
+            const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
+            acc0[2 * c4] = __ffma2_rn(x0, wa, acc0[2 * c4]);
+            acc0[2 * c4 + 1] = __ffma2_rn(x0, wb, acc0[2 * c4 + 1]);
+            acc1[2 * c4] = __ffma2_rn(x1, wa, acc1[2 * c4]);
+            acc1[2 * c4 + 1] = __ffma2_rn(x1, wb, acc1[2 * c4 + 1]);
+          }
+        }
+      }
+    }
+    float* a0 = reinterpret_cast<float*>(acc0);
+    float* a1 = reinterpret_cast<float*>(acc1);
+    if (MASKED) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float* a = half ? a1 : a0;
+        const bool ok = half ? v1ok : pvalid;
+        float y[CO];
+        const long long mp0 = ok ? (pix + half) * CO : 0;
+        if (msk_bf16) {
+          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(msk) + mp0);
+#pragma unroll
+          for (int i = 0; i < CO / 8; ++i) {
+            const uint4 u = __ldg(mp + i);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); y[8 * i + 2 * k] = f.x; y[8 * i + 2 * k + 1] = f.y; }
+          }
+        } else {
+          const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(msk) + mp0);
+#pragma unroll
+          for (int i = 0; i < CO / 4; ++i) { const float4 u = __ldg(mp + i); y[4 * i] = u.x; y[4 * i + 1] = u.y; y[4 * i + 2] = u.z; y[4 * i + 3] = u.w; }
+        }
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+          const float v = (ok && fmaf(y[c], sMs[0][c], sMs[1][c]) > 0.f) ? a[c] : 0.f;
+          a[c] = v;
+          if (stats != nullptr) {
+            if (half == 0) { sT[0][threadIdx.x][c] = v; sT[1][threadIdx.x][c] = v * y[c]; }
+            else { sT[0][threadIdx.x][c] += v; sT[1][threadIdx.x][c] += v * y[c]; }
+          }
+        }
+      }
+    } else if (stats != nullptr) {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        const float v0 = pvalid ? a0[c] : 0.f, v1 = v1ok ? a1[c] : 0.f;
+        sT[0][threadIdx.x][c] = v0 + v1;
+        sT[1][threadIdx.x][c] = fmaf(v0, v0, v1 * v1);
+      }
+    }
+    if (stats != nullptr) {
+      __syncthreads();
+      const int col = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 32;
+      float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 2) {
+        sa0 += sT[0][r0 + rr][col]; sa1 += sT[0][r0 + rr + 1][col];
+        sb0 += sT[1][r0 + rr][col]; sb1 += sT[1][r0 + rr + 1][col];
+      }
+      s_run += sa0 + sa1;
+      q_run += sb0 + sb1;
+      __syncthreads();
+    }
+    if (!pvalid) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half && !v1ok) break;
+      const float* a = half ? a1 : a0;
+      if (out_bf16) {
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + (pix + half) * CO);
+#pragma unroll
+        for (int c = 0; c < CO; c += 8)
+          o[c / 8] = make_uint4(pack2(a[c], a[c + 1]), pack2(a[c + 2], a[c + 3]), pack2(a[c + 4], a[c + 5]), pack2(a[c + 6], a[c + 7]));
+      } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (pix + half) * CO);
+#pragma unroll
+        for (int c = 0; c < CO; c += 4) o[c / 4] = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
+      }
+    }
+  }
+  if (stats == nullptr) return;
+  sRed[0][threadIdx.x >> 5][threadIdx.x & 31] = s_run;
+  sRed[1][threadIdx.x >> 5][threadIdx.x & 31] = q_run;
+  __syncthreads();
+  if (threadIdx.x < 2 * CO) {
+    const int which = threadIdx.x / CO, c = threadIdx.x % CO;
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kNT / 32; ++wv) t += sRed[which][wv][c];
+    atomicAdd(stats + which * CO + c, (double)t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // One thread = two horizontally adjacent output pixels (ow = 2j, 2j+1) of one output row; threads are ordered so that
 // a warp stays inside one row parity (uniform set of valid kh) — no divergence, weights are warp-broadcast from
@@ -649,12 +808,20 @@ int clearvae_conv_direct_fwd(const clearvae_conv_geom* g, int64_t batch, const c
     if (pre_scale || pre_relu) return CLEARVAE_EUNSUPPORTED;
     const int Ho = (g->Hin + 2 - g->k) / 2 + 1;
     const long long npix = batch * Ho * Ho;
-    if (g->k == 3)
+    static const bool v1 = getenv("CLEARVAE_CONV_FIRST_V1") != nullptr;
+    const long long npair = batch * Ho * ((Ho + 1) / 2);
+    if (v1 && g->k == 3)
       conv_first_kernel<3, false, false><<<grid_for(npix), kNT, 0, st>>>(src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
                                                                         stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho, nullptr, 0, nullptr, nullptr);
-    else
+    else if (v1)
       conv_first_kernel<4, false, false><<<grid_for(npix), kNT, 0, st>>>(src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
                                                                         stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho, nullptr, 0, nullptr, nullptr);
+    else if (g->k == 3)
+      conv_first2_kernel<3, false, false><<<grid_for(npair), kNT, 0, st>>>(src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
+                                                                         stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho, nullptr, 0, nullptr, nullptr);
+    else
+      conv_first2_kernel<4, false, false><<<grid_for(npair), kNT, 0, st>>>(src->ptr, weight, bias, dst->ptr, dst->dtype == CLEARVAE_BF16,
+                                                                         stats, (int)batch, g->Cin, g->Hin, g->Win, Ho, Ho, nullptr, 0, nullptr, nullptr);
   } else {
     const int Ho = (g->Hin - 1) * 2 - 2 + g->k + g->out_pad;
     const long long npix = batch * 2 * ((Ho + 1) / 2) * ((Ho + 1) / 2);  // one thread per output-pixel pair
@@ -740,13 +907,13 @@ int clearvae_conv_direct_dgrad(const clearvae_conv_geom* g, int64_t batch, const
     return t->sc == 1 && t->sw == 32 && t->sh == (int64_t)Hi * 32 && t->sn == (int64_t)Hi * Hi * 32 && !((uintptr_t)t->ptr & 15);
   };
   if (!cl32(dst) || !cl32(mask_src)) return CLEARVAE_EUNSUPPORTED;
-  const long long npix = batch * Hi * Hi;
+  (void)0;
   const bool xb = dy->dtype == CLEARVAE_BF16;
   cudaStream_t st = (cudaStream_t)stream;
 #define CV_DG(KK, XB)                                                                                                          \
-  conv_first_kernel<KK, XB, true><<<grid_for(npix), kNT, 0, st>>>(dy->ptr, weight, nullptr, dst->ptr, dst->dtype == CLEARVAE_BF16, stats, \
-                                                                  (int)batch, g->Cout, Ho, Ho, Hi, Hi, mask_src->ptr,          \
-                                                                  mask_src->dtype == CLEARVAE_BF16, mask_scale, mask_shift)
+  conv_first2_kernel<KK, XB, true><<<grid_for(batch * Hi * ((Hi + 1) / 2)), kNT, 0, st>>>(                                      \
+      dy->ptr, weight, nullptr, dst->ptr, dst->dtype == CLEARVAE_BF16, stats, (int)batch, g->Cout, Ho, Ho, Hi, Hi, mask_src->ptr, \
+      mask_src->dtype == CLEARVAE_BF16, mask_scale, mask_shift)
   if (g->k == 3) { if (xb) CV_DG(3, true); else CV_DG(3, false); }
   else { if (xb) CV_DG(4, true); else CV_DG(4, false); }
 #undef CV_DG
