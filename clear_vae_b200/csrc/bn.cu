@@ -410,32 +410,52 @@ __global__ void __launch_bounds__(kNT) bn_finalize_apply_kernel(const BnFaParams
   extern __shared__ float sAff[];  // [2][C]
   __shared__ int s_last;
   const int C = p.C;
-  for (int c = threadIdx.x; c < C; c += kNT) bn_channel_affine(p, c, blockIdx.x == 0, &sAff[c], &sAff[C + c]);
-  __syncthreads();
-  bn_ticket_clear(p, &s_last);   // all of this CTA's reads of the moments are done
   const uint4* raw = reinterpret_cast<const uint4*>(p.raw);
   uint4* out = reinterpret_cast<uint4*>(p.act);
   const long long n8 = p.total >> 3;
   const int C8 = C >> 3;
-  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n8; i += (long long)gridDim.x * kNT) {
-    const uint4 q = __ldg(raw + i);
+  const long long stride = (long long)gridDim.x * kNT;
+  long long i = (long long)blockIdx.x * kNT + threadIdx.x;
+  // the first two chunks are in flight while the moments are read and turned into (scale, shift); the ticket's atomic round trip
+  // overlaps the streaming loop (its result is only needed for the clear at the end)
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 q0 = i < n8 ? __ldg(raw + i) : z4, q1 = i + stride < n8 ? __ldg(raw + i + stride) : z4;
+  for (int c = threadIdx.x; c < C; c += kNT) bn_channel_affine(p, c, blockIdx.x == 0, &sAff[c], &sAff[C + c]);
+  __syncthreads();               // all of this CTA's reads of the moments are done
+  unsigned ticket = 0u;
+  if (threadIdx.x == 0) ticket = atomicAdd(reinterpret_cast<unsigned int*>(p.stats + 2 * p.C), 1u);
+  auto apply = [&](const uint4 q, long long idx) {
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
     float v[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
     if (LAYOUT == 0) {
-      const int c0 = (int)(i % C8) << 3;
+      const int c0 = (int)(idx % C8) << 3;
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sAff[c0 + k], sAff[C + c0 + k]), 0.f);
     } else {
-      const long long e0 = i << 3;
+      const long long e0 = idx << 3;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = (int)(((e0 + k) / p.HW) % C);
         v[k] = fmaxf(fmaf(v[k], sAff[c], sAff[C + c]), 0.f);
       }
     }
-    out[i] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    out[idx] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+  };
+  for (; i < n8; i += 2 * stride) {
+    const long long j = i + stride, i2 = i + 2 * stride, j2 = j + 2 * stride;
+    const uint4 n0 = i2 < n8 ? __ldg(raw + i2) : z4, n1 = j2 < n8 ? __ldg(raw + j2) : z4;   // next pair in flight
+    apply(q0, i);
+    if (j < n8) apply(q1, j);
+    q0 = n0; q1 = n1;
+  }
+  if (threadIdx.x == 0) s_last = ticket == gridDim.x * gridDim.y - 1 ? 1 : 0;
+  __syncthreads();
+  if (s_last) {   // the last CTA that has read its moments clears the accumulator (and the ticket) for the next step
+    __threadfence();
+    for (int k = threadIdx.x; k < 2 * p.C; k += kNT) p.stats[k] = 0.0;
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(p.stats + 2 * p.C) = 0u;
   }
 }
 
