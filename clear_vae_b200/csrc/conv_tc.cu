@@ -1848,6 +1848,65 @@ __global__ void pack_weight_multi_kernel(const MultiPackEntry* __restrict__ tab,
 }
 
 // ---------------------------------------------------------------------------
+// Skinny linear layer  out[B, N] = src[B, K] . W[N, K]^T + bias  with N = 16 or 32 and a deep K (the latent heads on the
+// 2048-wide flattened encoder output, the data gradient of the decoder's first Linear): 134 MFLOP for which a 128-row tcgen05
+// tile needs split-K over 16 CTAs, fp32 atomics on a zeroed destination and a memset (24 us per call on the step's critical path).
+// Here: CTA = 16 rows, eight warps each own K/8 of the reduction and run warp-level mma.sync.m16n8k16 (bf16, fp32 accumulate)
+// with A / B fragments loaded straight from global memory in the instruction's register layout (every 32-byte sector fully
+// used; W is L2 resident), partial tiles meet in shared memory, one pass adds the bias and stores.  No atomics, no memset.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t skinny_a_pair(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ uint32_t skinny_a_pair(const float* p) {   // fp32 rows are rounded to bf16 like the general kernel's gather
+  const float2 f = __ldg(reinterpret_cast<const float2*>(p));
+  return pack_bf16(f.x, f.y);
+}
+template <int NT, typename TS>   // n-tiles of 8 columns: N = 8 * NT; TS = source element type (bf16 or fp32)
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const TS* __restrict__ src, long long s_n, const __nv_bfloat16* __restrict__ w,
+                                                           int Kp, const float* __restrict__ bias, float* __restrict__ out, long long d_n,
+                                                           int B, int K) {
+  constexpr int N = 8 * NT;
+  __shared__ float sRed[8][16][N + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * 16;
+  const int ra = min(row0 + g, B - 1), rb = min(row0 + g + 8, B - 1);      // clamped: rows past the batch are computed and dropped
+  const int kslice = K / 8, kbeg = warp * kslice;
+  const TS* pa = src + (long long)ra * s_n + kbeg + t * 2;
+  const TS* pb = src + (long long)rb * s_n + kbeg + t * 2;
+  const __nv_bfloat16* pw = w + (long long)g * Kp + kbeg + t * 2;
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kslice; k += 16) {
+    const uint32_t a0 = skinny_a_pair(pa + k), a1 = skinny_a_pair(pb + k), a2 = skinny_a_pair(pa + k + 8), a3 = skinny_a_pair(pb + k + 8);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(pw + (long long)j * 8 * Kp + k));
+      const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(pw + (long long)j * 8 * Kp + k + 8));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                   : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {   // c0, c1: (row g, cols 2t, 2t+1); c2, c3: (row g + 8, same columns)
+    sRed[warp][g][j * 8 + 2 * t] = acc[j][0];
+    sRed[warp][g][j * 8 + 2 * t + 1] = acc[j][1];
+    sRed[warp][g + 8][j * 8 + 2 * t] = acc[j][2];
+    sRed[warp][g + 8][j * 8 + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 16 * N; o += 256) {
+    const int r = o / N, n = o - r * N;
+    if (row0 + r >= B) continue;
+    float v = bias != nullptr ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += sRed[wv][r][n];
+    out[(long long)(row0 + r) * d_n + n] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -2163,6 +2222,26 @@ int clearvae_conv_gemm(const clearvae_conv_geom* g, int32_t role, int64_t batch,
   role &= ~CLEARVAE_ROLE_SPLIT3;
   if (!cvplan::make_plan(*g, role, BK, &p.plan)) return CLEARVAE_EUNSUPPORTED;
   if (pre_scale != nullptr && p.plan.Cs > kMaxPreC) return CLEARVAE_EUNSUPPORTED;
+  {
+    // skinny linear layers (N = 16 / 32, deep K, plain bf16 rows, bias-only epilogue): warp-MMA kernel without split-K atomics
+    static const bool no_skinny = getenv("CLEARVAE_NO_SKINNY_LINEAR") != nullptr;
+    const Cls& c0 = p.plan.cls[0];
+    const int Nn = p.plan.Nn, Cs = p.plan.Cs;
+    if (!no_skinny && !p.x3 && g->k == 1 && g->Hin == 1 && g->Win == 1 && p.plan.n_classes == 1 && (Nn == 16 || Nn == 32) && Cs % 128 == 0 &&
+        Cs >= 512 && c0.Kp >= Cs && c0.w_off == 0 && src->sc == 1 && (src->sn & 1) == 0 && !((uintptr_t)src->ptr & 7) && pre_scale == nullptr && !pre_relu && epilogue == CLEARVAE_EPI_BIAS_STATS && stats == nullptr &&
+        dst->dtype == CLEARVAE_F32 && dst->sc == 1 && batch < (1LL << 27)) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(packed_weight);
+      const unsigned grid = (unsigned)((batch + 15) / 16);
+      cudaStream_t st = (cudaStream_t)stream;
+#define CV_SKINNY(NT, TS) skinny_linear_kernel<NT, TS><<<grid, 256, 0, st>>>(reinterpret_cast<const TS*>(src->ptr), src->sn, wp, c0.Kp, bias, \
+                                                                              (float*)dst->ptr, dst->sn, (int)batch, Cs)
+      if (src->dtype == CLEARVAE_BF16) { if (Nn == 32) CV_SKINNY(4, __nv_bfloat16); else CV_SKINNY(2, __nv_bfloat16); }
+      else { if (Nn == 32) CV_SKINNY(4, float); else CV_SKINNY(2, float); }
+#undef CV_SKINNY
+      CV_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) return CLEARVAE_EUNSUPPORTED;
   const int BN = pick_bn(p.plan.Nn);

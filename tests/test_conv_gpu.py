@@ -54,6 +54,30 @@ def test_linear_as_1x1(B, K, N):
     assert torch.allclose(stats[N:].float(), (want * want).sum(0), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("B,K,N,role,f32", [(300, 2048, 32, 0, False), (1024, 2048, 32, 0, False), (77, 4096, 32, 0, True),
+                                               (1000, 2048, 16, 1, True), (5, 512, 16, 1, False)])
+def test_skinny_linear_without_statistics(B, K, N, role, f32):
+    """The latent heads (N = 4D = 32) and the data gradient of the decoder's first Linear (N = 2D = 16) take the warp-MMA
+    kernel (no split-K atomics): same contract as the general GEMM, bias optional, ragged batch."""
+    g = torch.Generator().manual_seed(B + K + N)
+    x = bf(torch.randn(B, K, generator=g)).to(DEV)
+    if not f32:     # fp32 rows (bf16-representable here) are rounded to bf16 on load, like the general kernel's gather
+        x = x.to(torch.bfloat16)
+    if role == 0:   # y = x W^T + b, W [N, K]
+        w = bf(torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        geom = [0, 1, 1, 0, 0, K, N, 1, 1]
+        want = F.linear(x.float(), w, b)
+    else:           # dz = dy W, W [K, N] (forward Linear N -> K)
+        w = bf(torch.randn(K, N, generator=g) / K ** 0.5).to(DEV)
+        b = None
+        geom = [0, 1, 1, 0, 0, N, K, 1, 1]
+        want = x.float() @ w
+    dst = torch.full((B, N), float("nan"), device=DEV)
+    run_gemm(geom, role, B, x, (K, 0, 0, 1), w, b, dst, (N, 0, 0, 1))
+    assert rel_err(dst, want) < 2e-5, rel_err(dst, want)
+
+
 @pytest.mark.parametrize("k,cin,cout,H,B", [(4, 32, 64, 32, 8), (3, 32, 64, 14, 16), (4, 3, 32, 64, 4), (3, 1, 32, 28, 8),
                                              (4, 256, 512, 4, 32), (3, 64, 128, 7, 33)])
 def test_conv2d_fprop_and_dgrad(k, cin, cout, H, B):
