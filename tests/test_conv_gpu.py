@@ -198,7 +198,7 @@ def test_weight_gradient(transposed, k, op, cin, cout, H, B):
     assert rel_err(dw2 - 1.0, dw_want) < 5e-5
 
 
-@pytest.mark.parametrize("k,cin,H,B", [(3, 3, 28, 16), (3, 1, 28, 8), (4, 3, 64, 4)])
+@pytest.mark.parametrize("k,cin,H,B", [(3, 3, 28, 16), (3, 1, 28, 8), (4, 3, 64, 4), (3, 3, 26, 5), (4, 2, 18, 3)])   # last two: odd output width
 def test_direct_first_conv(k, cin, H, B):
     from clear_vae_b200 import _ops
     ops = _ops.ops()
@@ -241,6 +241,34 @@ def test_direct_last_conv_transpose(k, op, cout, H, B):
         assert ok
         assert rel_err(dst, want) < 1e-5
         assert torch.allclose(stats[:cout].float(), want.sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("k,op,cout,H,B", [(3, 1, 3, 14, 8), (3, 0, 3, 7, 5), (3, 1, 1, 14, 9), (4, 0, 3, 32, 3), (4, 0, 3, 16, 2), (3, 1, 4, 9, 3)])
+def test_direct_last_conv_transpose_materialised_input(k, op, cout, H, B):
+    """The training form of the last conv-transpose (`convt_last_x2_kernel`: bf16 activation already normalised, rows staged through
+    shared memory, two pixel pairs per thread): even / odd output sizes, image borders, 1-4 output channels, ragged batch, and the
+    statistics-only call of CLEAR-MIM's inner forwards (empty destination)."""
+    from clear_vae_b200 import _ops
+    ops = _ops.ops()
+    g = torch.Generator().manual_seed(11 * k + cout + H)
+    act = torch.relu(torch.randn(B, H, H, 32, generator=g)).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(32, cout, k, k, generator=g) / (32 * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    want = F.conv_transpose2d(act.float().permute(0, 3, 1, 2), w, b, stride=2, padding=1, output_padding=op)
+    Ho = want.shape[-1]
+    geom = [1, k, 2, 1, op, 32, cout, H, H]
+    dst = torch.full((B, cout, Ho, Ho), float("nan"), device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    assert ops.conv_direct_fwd(geom, B, act, nhwc_strides(act), None, None, False, w, b, dst,
+                               [dst.stride(0), dst.stride(2), dst.stride(3), dst.stride(1)], stats)
+    assert rel_err(dst, want) < 1e-5, rel_err(dst, want)
+    assert torch.allclose(stats[:cout].float(), want.sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[cout:].float(), (want * want).sum((0, 2, 3)), rtol=1e-4, atol=1e-2)
+    stats2 = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    empty = torch.empty((0,), dtype=torch.float32, device=DEV)
+    assert ops.conv_direct_fwd(geom, B, act, nhwc_strides(act), None, None, False, w, b, empty,
+                               [cout * Ho * Ho, Ho, 1, Ho * Ho], stats2)
+    assert torch.allclose(stats2, stats, rtol=1e-6, atol=1e-9)
 
 
 @pytest.mark.parametrize("transposed,k,op,c,H,B,img_bf16", [(0, 3, 0, 3, 28, 16, False), (0, 3, 0, 1, 28, 5, False), (0, 4, 0, 3, 64, 3, False),
