@@ -9,10 +9,21 @@ from clear_vae_b200.optim import fused_adam_step
 from clear_vae_b200.models.mi_estimator import CLUBSample
 
 cfg = bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "mim_club"]
-dev = torch.device("cuda", 0)
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:   # under torchrun: the data-parallel step (rank 0 prints)
+    import torch.distributed as td
+    td.init_process_group("nccl", device_id=dev)
 tr = bench.build_trainer(cfg, dev)
+if world > 1:
+    from clear_vae_b200.latent import DistSpec
+    from clear_vae_b200.peer import PeerComm
+    tr.dist = DistSpec(td.group.WORLD, rank, world, PeerComm.create(td.group.WORLD, rank, world, dev))
+    for p_ in list(tr.model.parameters()):
+        td.broadcast(p_.data, 0)
 tr.model.train()
-g = torch.Generator().manual_seed(101)
+g = torch.Generator().manual_seed(101 + rank)
 X = torch.rand(cfg["B"], cfg["cin"], cfg["hw"], cfg["hw"], generator=g).to(dev)
 y = torch.randint(0, cfg["ncls"], (cfg["B"],), generator=g).to(dev)
 for _ in range(4):
@@ -50,9 +61,11 @@ for rep in range(3):
     mark("step end (all branches joined)")
     tr._end_step(dev); tr.annealer.step()
     torch.cuda.synchronize()
+if rank != 0:
+    sys.exit(0)
 t0 = marks[0][1]
 prev = 0.0
-print(f"{cfg['kind']} {cfg['arch']} B={cfg['B']}: phase boundaries on the main stream (ms since start, delta)")
+print(f"world {world} | {cfg['kind']} {cfg['arch']} B={cfg['B']}: phase boundaries on the main stream (ms since start, delta)")
 for name, e in marks[1:]:
     t = t0.elapsed_time(e)
     print(f"  {t:8.3f}  +{t - prev:6.3f}  {name}")
