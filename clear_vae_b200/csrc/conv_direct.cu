@@ -907,7 +907,7 @@ int clearvae_conv_direct_dgrad(const clearvae_conv_geom* g, int64_t batch, const
     return t->sc == 1 && t->sw == 32 && t->sh == (int64_t)Hi * 32 && t->sn == (int64_t)Hi * Hi * 32 && !((uintptr_t)t->ptr & 15);
   };
   if (!cl32(dst) || !cl32(mask_src)) return CLEARVAE_EUNSUPPORTED;
-  (void)0;
+
   const bool xb = dy->dtype == CLEARVAE_BF16;
   cudaStream_t st = (cudaStream_t)stream;
 #define CV_DG(KK, XB)                                                                                                          \
