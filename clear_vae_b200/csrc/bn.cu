@@ -289,6 +289,54 @@ __global__ void bn_bwd_coef_kernel(double* stats, int C, int group, double count
 }
 
 // dy = a[ch] * g' + b[ch] * y + c[ch],  g' = g * [act > 0] when act is given
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// fp32 gradient and fp32 pre-activation, four consecutive elements per thread: either one channel per element run
+// (inner % 4 == 0: the NCHW last decoder block) or four consecutive channels (inner == 1: the decoder's fc block with its
+// recomputed ReLU mask).  The scalar kernel below paid an integer division and five scalar coefficient loads per element.
+template <bool SAME_CH>
+__global__ void __launch_bounds__(kNT) bn_bwd_apply_vec4_kernel(const float4* __restrict__ g, const float4* __restrict__ y,
+                                                                const float* __restrict__ mscale, const float* __restrict__ mshift,
+                                                                const float* __restrict__ coef, long long n4, int C, long long inner4,
+                                                                void* dy, int dy_bf) {
+  for (long long i = (long long)blockIdx.x * kNT + threadIdx.x; i < n4; i += (long long)gridDim.x * kNT) {
+    float4 gv = __ldg(g + i);
+    const float4 yv = __ldg(y + i);
+    float4 a, b, c;
+    if (SAME_CH) {
+      const int ch = (int)((i / inner4) % C);
+      const float a1 = __ldg(coef + ch), b1 = __ldg(coef + C + ch), c1 = __ldg(coef + 2 * C + ch);
+      a = make_float4(a1, a1, a1, a1); b = make_float4(b1, b1, b1, b1); c = make_float4(c1, c1, c1, c1);
+      if (mscale != nullptr) {
+        const float ms = __ldg(mscale + ch), mh = __ldg(mshift + ch);
+        if (!(fmaf(yv.x, ms, mh) > 0.f)) gv.x = 0.f;
+        if (!(fmaf(yv.y, ms, mh) > 0.f)) gv.y = 0.f;
+        if (!(fmaf(yv.z, ms, mh) > 0.f)) gv.z = 0.f;
+        if (!(fmaf(yv.w, ms, mh) > 0.f)) gv.w = 0.f;
+      }
+    } else {
+      const int ch = (int)((i * 4) % C);
+      a = __ldg(reinterpret_cast<const float4*>(coef + ch));
+      b = __ldg(reinterpret_cast<const float4*>(coef + C + ch));
+      c = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + ch));
+      if (mscale != nullptr) {
+        const float4 ms = __ldg(reinterpret_cast<const float4*>(mscale + ch)), mh = __ldg(reinterpret_cast<const float4*>(mshift + ch));
+        if (!(fmaf(yv.x, ms.x, mh.x) > 0.f)) gv.x = 0.f;
+        if (!(fmaf(yv.y, ms.y, mh.y) > 0.f)) gv.y = 0.f;
+        if (!(fmaf(yv.z, ms.z, mh.z) > 0.f)) gv.z = 0.f;
+        if (!(fmaf(yv.w, ms.w, mh.w) > 0.f)) gv.w = 0.f;
+      }
+    }
+    const float4 v = make_float4(fmaf(a.x, gv.x, fmaf(b.x, yv.x, c.x)), fmaf(a.y, gv.y, fmaf(b.y, yv.y, c.y)),
+                                 fmaf(a.z, gv.z, fmaf(b.z, yv.z, c.z)), fmaf(a.w, gv.w, fmaf(b.w, yv.w, c.w)));
+    if (dy_bf) reinterpret_cast<uint2*>(dy)[i] = make_uint2(bf2(v.x, v.y), bf2(v.z, v.w));
+    else reinterpret_cast<float4*>(dy)[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const void* g, int g_bf, const void* y, int y_bf, const void* act,
                                                            int act_bf, const float* __restrict__ mscale,
                                                            const float* __restrict__ mshift, const float* __restrict__ coef,
@@ -358,10 +406,6 @@ struct BnFaParams {
   const void* raw; void* act; long long total; int HW, C0;
 };
 
-__device__ __forceinline__ uint32_t bf2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 
 // per-channel statistics -> (scale, shift); `publish` threads also store the backward state and the running estimates.
 // The mean / variance are formed in fp64 (cancellation), everything after that in fp32.
@@ -669,6 +713,21 @@ int clearvae_bn_bwd_apply(const void* g, int32_t g_dtype, const void* y, int32_t
     if (gr > 148 * 8) gr = 148 * 8;
     bn_bwd_apply_vec_kernel<<<(unsigned)gr, kNT, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(g), reinterpret_cast<const uint4*>(y), coef, n8, C, reinterpret_cast<uint4*>(dy));
+    CV_LAUNCH_CHECK();
+    return 0;
+  }
+  if (!act && !to_nhwc && g_dtype == CLEARVAE_F32 && y_dtype == CLEARVAE_F32 && total % 4 == 0 &&
+      ((inner == 1 && C % 4 == 0) || inner % 4 == 0) &&
+      !(((uintptr_t)g | (uintptr_t)y | (uintptr_t)dy | (uintptr_t)coef | (uintptr_t)mask_scale | (uintptr_t)mask_shift) & 15)) {
+    const long long n4 = total / 4;
+    long long gr = (n4 + kNT - 1) / kNT;
+    if (gr > 148 * 8) gr = 148 * 8;
+    if (inner == 1)
+      bn_bwd_apply_vec4_kernel<false><<<(unsigned)gr, kNT, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), mask_scale, mask_shift, coef, n4, C, 1, dy, dy_dtype == CLEARVAE_BF16);
+    else
+      bn_bwd_apply_vec4_kernel<true><<<(unsigned)gr, kNT, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), mask_scale, mask_shift, coef, n4, C, inner / 4, dy, dy_dtype == CLEARVAE_BF16);
     CV_LAUNCH_CHECK();
     return 0;
   }
